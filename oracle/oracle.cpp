@@ -1,0 +1,738 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of BioD's BGZF-inflate -> BAM record decode -> pileup path.
+// Nothing in the product (biod_b200/, include/) links, imports or executes this
+// file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may use it, and there only as the checker / CPU baseline.
+//
+// Parity pin: the reference is D and cannot be compiled in this image (no dmd /
+// ldc2 / gdc), so this restatement is pinned against the reference's OWN golden
+// vectors instead (tests/test_oracle_golden.py): ex1_header.sam (3270 records,
+// test/unittests.d:303-312), first-record fields (unittests.d:92-103), the
+// pileup column counts {1470,1567} and first columns (unittests.d:334-367), the
+// in-module 10-read pileup vector (bam/pileup.d:735-825), the zero-coverage
+// vector (pileup.d:830-856), examples/make_pileup.d:20-30 and the five corrupted
+// BAMs (unittests.d:132-142).  Inflate itself is system libz — the very library
+// the reference links (bio/core/utils/zlib.d:6-245, Makefile:10 `-L-lz`).
+//
+// Every function cites the reference lines it follows.  Paths are relative to
+// /root/reference.
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+enum {
+  ORC_OK = 0,
+  ORC_ERR_BGZF = -1,    // BgzfException  (bio/core/bgzf/inputstream.d:41-43)
+  ORC_ERR_ZLIB = -2,    // ZlibException  (bio/core/utils/zlib.d:247-274)
+  ORC_ERR_FORMAT = -3,  // plain Exception (bam/reader.d:113, bgzf/block.d:150)
+  ORC_ERR_TRUNC = -4,   // ReadException from readExact (bam/readrange.d:169)
+  ORC_ERR_CIGAR = -7,   // PileupRead.assertCigarIndexIsValid (bam/pileup.d:224-228)
+  ORC_ERR_UNSORTED = -8 // not a reference error: input order the engine assumes
+};
+
+const uint32_t BGZF_MAX_BLOCK_SIZE = 65536;  // bio/core/bgzf/constants.d:60
+
+struct Block {
+  uint64_t coffset;   // start_offset          (bgzf/block.d:44)
+  uint32_t bsize;     // total block size - 1  (block.d:47)
+  uint32_t xlen;
+  uint32_t cdata_size;
+  uint32_t crc32;
+  uint32_t isize;     // input_size
+  uint64_t uoffset;   // prefix sum of isize over the blocks delivered so far
+  uint64_t payload;   // file offset of the deflate payload
+};
+
+struct Error {
+  int status = ORC_OK;
+  int zerr = 0;
+  uint64_t offset = 0;
+  std::string msg;
+};
+
+inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+inline uint32_t le32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// fillBgzfBufferFromStream — bio/core/bgzf/inputstream.d:54-199.
+// Returns 1 = block parsed, 0 = clean end of stream (:57-58, :75-76), <0 = error.
+int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, Block* b, Error* e) {
+  auto fail = [&](const std::string& m) {
+    e->status = ORC_ERR_BGZF;
+    e->offset = pos;
+    e->msg = "Error reading BGZF block starting from offset " + std::to_string(pos) + ": " + m;  // :63-64
+    return ORC_ERR_BGZF;
+  };
+  const char* kStream = "stream error: not enough data in stream";  // :194-196
+  if (pos >= len) return 0;                       // stream.eof() (:57)
+  // :72-79 — a short read of the 4 magic bytes is a clean EOF only if *zero*
+  // bytes were available; a partial magic keeps looping until read returns 0.
+  if (len - pos < 4) return 0;
+  if (!(d[pos] == 0x1f && d[pos + 1] == 0x8b && d[pos + 2] == 0x08 && d[pos + 3] == 0x04))
+    return fail("wrong BGZF magic");              // :82-84
+  uint64_t p = pos + 4 + 4 + 1 + 1;               // skip MTIME, XFL, OS (:88-97)
+  if (p + 2 > len) return fail(kStream);
+  uint32_t xlen = le16(d + p);                    // :99
+  p += 2;
+  uint32_t bsize = 0;
+  bool found = false;
+  uint32_t n = 0;
+  while (n < xlen) {                              // :106
+    if (p + 4 > len) return fail(kStream);
+    uint8_t si1 = d[p], si2 = d[p + 1];
+    uint32_t slen = le16(d + p + 2);
+    p += 4;
+    if (si1 == 66 && si2 == 67) {                 // 'B','C' (:115)
+      if (slen != 2)
+        return fail("wrong BC subfield length: " + std::to_string(slen) + "; expected 2");  // :118-121
+      if (found) return fail("duplicate field with block size");                            // :123-125
+      if (p + 2 > len) return fail(kStream);
+      bsize = le16(d + p);
+      found = true;
+    }
+    p += slen;                                    // :131-142 (seekCur never fails by itself)
+    n += 4 + slen;                                // :145-148
+  }
+  if (n != xlen)
+    return fail("total length of subfields in bytes (" + std::to_string(n) +
+                ") is not equal to gzip_extra_length (" + std::to_string(xlen) + ")");  // :152-157
+  if (!found) return fail("block size was not found in any subfield");                  // :159-161
+  int64_t cdata = (int64_t)bsize - (int64_t)xlen - 19;                                  // :164
+  if (cdata > (int64_t)BGZF_MAX_BLOCK_SIZE)
+    return fail("compressed data size is more than 65536 bytes, which is not allowed by current BAM specification");
+  // :176 readExact(buffer, cdata_size): a negative size converts to a huge
+  // size_t and the stream throws ReadException -> "stream error" (:194-196).
+  if (cdata < 0 || p + (uint64_t)cdata + 8 > len) return fail(kStream);
+  b->coffset = pos;
+  b->bsize = bsize;
+  b->xlen = xlen;
+  b->cdata_size = (uint32_t)cdata;
+  b->payload = p;
+  b->crc32 = le32(d + p + cdata);                 // :184
+  b->isize = le32(d + p + cdata + 4);             // :185
+  return 1;
+}
+
+// decompressBgzfBlock — bio/core/bgzf/block.d:127-216.
+int inflate_block(const uint8_t* d, const Block& b, uint8_t* out, Error* e) {
+  if (b.isize > BGZF_MAX_BLOCK_SIZE) {            // :150-152
+    e->status = ORC_ERR_FORMAT;
+    e->offset = b.coffset;
+    e->msg = "Uncompressed block size must be within 65536 bytes";
+    return e->status;
+  }
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  zs.next_in = const_cast<Bytef*>(d + b.payload);
+  zs.avail_in = b.cdata_size;
+  int err = inflateInit2(&zs, -15);               // :162
+  if (err) { e->status = ORC_ERR_ZLIB; e->zerr = err; e->offset = b.coffset; e->msg = "zlib init"; return e->status; }
+  zs.next_out = out;
+  zs.avail_out = b.isize;                         // :170
+  err = inflate(&zs, Z_FINISH);                   // :172
+  uint64_t total_out = zs.total_out;
+  inflateEnd(&zs);
+  if (err != Z_STREAM_END) {                      // :182-185
+    e->status = ORC_ERR_ZLIB;
+    e->zerr = err;
+    e->offset = b.coffset;
+    e->msg = "zlib error " + std::to_string(err);
+    return e->status;
+  }
+  // :175 `assert(zs.total_out == block.input_size)` and :187 the CRC assert are
+  // compiled out by -release (Makefile:33); a short stream would hand garbage
+  // stack bytes to the caller.  Restatement-defined: report it as Z_DATA_ERROR.
+  if (total_out != b.isize) {
+    e->status = ORC_ERR_ZLIB;
+    e->zerr = Z_DATA_ERROR;
+    e->offset = b.coffset;
+    e->msg = "inflated size differs from ISIZE";
+    return e->status;
+  }
+  return ORC_OK;
+}
+
+struct Bam {
+  const uint8_t* file = nullptr;
+  uint64_t flen = 0;
+  Error err;            // first error met (sticky)
+  // BGZF stream state: BgzfInputStream — inputstream.d:349-541
+  std::vector<Block> blocks;   // data blocks delivered, in order
+  std::vector<uint8_t> u;      // concatenated uncompressed bytes
+  uint64_t next_coffset = 0;
+  bool stream_done = false;    // supplier exhausted / ISIZE==0 block met (:393-394)
+  uint64_t end_coffset = 0;    // end_offset of the last delivered block
+  // header
+  std::string text;
+  std::vector<std::string> ref_names;
+  std::vector<int32_t> ref_lens;
+  uint64_t reads_start_u = 0;  // offset into u of the first record
+  uint64_t reads_start_vo = 0;
+  // records
+  bool decoded = false;
+  std::vector<uint64_t> rec_off;   // offset in u of each record's block_size prefix
+  std::vector<int32_t> block_size, ref_id, pos, end_pos, l_seq, next_ref, next_pos, tlen;
+  std::vector<uint16_t> bin, flag, n_cigar;
+  std::vector<uint8_t> mapq, l_read_name;
+  std::vector<uint64_t> start_vo, end_vo;
+  std::vector<uint64_t> cigar_off;
+  std::vector<uint32_t> cigar;
+};
+
+// One step of fillNextBlock + decompress (inputstream.d:386-424, block.d:127).
+// Returns 1 if a data block was appended, 0 at end of stream, <0 on error.
+int next_block(Bam* s) {
+  if (s->stream_done) return 0;
+  if (s->err.status) return s->err.status;
+  Block b;
+  int r = parse_bgzf_header(s->file, s->flen, s->next_coffset, &b, &s->err);
+  if (r < 0) return r;
+  if (r == 0) { s->stream_done = true; return 0; }
+  if (b.isize == 0) { s->stream_done = true; return 0; }   // BGZF EOF block (:393-394)
+  b.uoffset = s->u.size();
+  // enforce ISIZE <= 65536 before growing the buffer (block.d:150)
+  if (b.isize > BGZF_MAX_BLOCK_SIZE) { inflate_block(s->file, b, nullptr, &s->err); return s->err.status; }
+  s->u.resize(b.uoffset + b.isize);
+  r = inflate_block(s->file, b, s->u.data() + b.uoffset, &s->err);
+  if (r < 0) { s->u.resize(b.uoffset); return r; }
+  s->blocks.push_back(b);
+  s->next_coffset = b.coffset + b.bsize + 1;      // end_offset (block.d:53-55)
+  s->end_coffset = s->next_coffset;
+  return 1;
+}
+
+// Make at least `upto` uncompressed bytes available (or hit EOF / an error).
+int ensure(Bam* s, uint64_t upto) {
+  while (s->u.size() < upto) {
+    int r = next_block(s);
+    if (r <= 0) return r;
+  }
+  return 1;
+}
+
+// VirtualOffset of stream offset x — virtualoffset.d:43, with the normalisation
+// of inputstream.d:443-445,516-524: an offset that is exactly a block end is
+// reported as (next block's coffset, 0).
+uint64_t voffset_of(const Bam* s, uint64_t x) {
+  const auto& bl = s->blocks;
+  size_t lo = 0, hi = bl.size();
+  while (lo < hi) {            // last block with uoffset <= x
+    size_t m = (lo + hi) / 2;
+    if (bl[m].uoffset <= x) lo = m + 1; else hi = m;
+  }
+  if (lo == 0) return 0;
+  const Block& b = bl[lo - 1];
+  if (x - b.uoffset >= b.isize) return (uint64_t)(b.coffset + b.bsize + 1) << 16;
+  return (b.coffset << 16) | (x - b.uoffset);
+}
+
+// BamReader ctor — bam/reader.d:100-124, 579-597; referenceinfo.d:57-62.
+int parse_header(Bam* s) {
+  auto need = [&](uint64_t upto) -> int {
+    int r = ensure(s, upto);
+    if (r < 0) return r;
+    if (s->u.size() < upto) {
+      s->err.status = ORC_ERR_TRUNC;
+      s->err.msg = "not enough data in stream";
+      return s->err.status;
+    }
+    return 1;
+  };
+  int r;
+  // readString(4) on an empty/short stream yields a short string -> enforce fails.
+  r = ensure(s, 4);
+  if (r < 0) return r;
+  if (s->u.size() < 4 || memcmp(s->u.data(), "BAM\1", 4) != 0) {   // reader.d:111-113
+    s->err.status = ORC_ERR_FORMAT;
+    s->err.msg = "Invalid file format: expected BAM\\1";
+    return s->err.status;
+  }
+  uint64_t p = 4;
+  if ((r = need(p + 4)) < 0) return r;
+  int32_t l_text = (int32_t)le32(s->u.data() + p);                  // :580-581
+  p += 4;
+  if (l_text < 0) { s->err.status = ORC_ERR_FORMAT; s->err.msg = "negative l_text"; return s->err.status; }
+  if ((r = need(p + l_text)) < 0) return r;
+  s->text.assign((const char*)s->u.data() + p, l_text);             // :583
+  p += l_text;
+  if ((r = need(p + 4)) < 0) return r;
+  int32_t n_ref = (int32_t)le32(s->u.data() + p);                   // :588-589
+  p += 4;
+  for (int32_t i = 0; i < n_ref; i++) {
+    if ((r = need(p + 4)) < 0) return r;
+    int32_t l_name = (int32_t)le32(s->u.data() + p);                // referenceinfo.d:58-59
+    p += 4;
+    if (l_name < 0) { s->err.status = ORC_ERR_FORMAT; s->err.msg = "negative l_name"; return s->err.status; }
+    if ((r = need(p + l_name + 4)) < 0) return r;
+    std::string nm((const char*)s->u.data() + p, l_name);           // keeps the NUL (:60)
+    if (!nm.empty() && nm.back() == '\0') nm.pop_back();            // name() drops it (:41-43)
+    s->ref_names.push_back(nm);
+    p += l_name;
+    s->ref_lens.push_back((int32_t)le32(s->u.data() + p));          // :61
+    p += 4;
+  }
+  s->reads_start_u = p;
+  // reader.d:121-123: virtualTell() right after the header.  When the header
+  // ends exactly at a block end the stream has already stepped to the next
+  // block (inputstream.d:516-524) — which needs that block to be known.
+  ensure(s, p + 1);
+  if (s->err.status) {
+    // the error belongs to a later block; it must surface during iteration
+    // (unittests.d:139), not here.  Keep it sticky but report open as OK.
+  }
+  s->reads_start_vo = voffset_of(s, p);
+  return ORC_OK;
+}
+
+inline bool op_query(uint32_t raw) { return ((0x3C1A7u >> ((raw & 0xF) * 2)) & 1) != 0; }  // cigar.d:116-121
+inline bool op_ref(uint32_t raw)   { return ((0x3C1A7u >> ((raw & 0xF) * 2)) & 2) != 0; }  // cigar.d:116,124-126
+// 0x3C1A7 == 0b11_11_00_00_01_10_10_01_11 (cigar.d:116); op codes 9..15 shift past bit 17 -> 0.
+
+// BamReadRange.readNext — bam/readrange.d:118-173, fields — bam/read.d:907-1003,
+// basesCovered — read.d:255-262, end_position — read.d:1380-1383.
+int decode_records(Bam* s) {
+  if (s->decoded) return s->err.status;
+  s->decoded = true;
+  // inflate everything first (errors are sticky and re-raised below at the
+  // point the sequential reader would have met them)
+  while (next_block(s) > 0) {}
+  Error blk_err = s->err;
+  const uint64_t avail = s->u.size();
+  uint64_t p = s->reads_start_u;
+  s->cigar_off.push_back(0);
+  while (true) {
+    if (p >= avail) break;                      // stream.eof() / 0 bytes read (:125,:141-148)
+    if (avail - p < 4) {
+      // readBlock returned fewer than 4 bytes and then 0: range ends (:139-150),
+      // unless the stream stopped because of an error in the next block.
+      break;
+    }
+    int32_t bs = (int32_t)le32(s->u.data() + p);
+    if (bs < 32 || (uint64_t)bs > avail - p - 4) {
+      if (blk_err.status) break;                // the pending block error wins (raised below)
+      s->err.status = ORC_ERR_TRUNC;            // readExact throws (:169); <32 would be a RangeError in BamRead
+      s->err.offset = p;
+      s->err.msg = bs < 32 ? "record shorter than the fixed 32-byte core" : "not enough data in stream";
+      break;
+    }
+    const uint8_t* r = s->u.data() + p + 4;
+    uint32_t bin_mq_nl = le32(r + 8), flag_nc = le32(r + 12);
+    int32_t lseq = (int32_t)le32(r + 16);
+    uint32_t lname = bin_mq_nl & 0xFF, nc = flag_nc & 0xFFFF;
+    uint64_t need = 32ull + lname + 4ull * nc + (lseq > 0 ? (uint64_t)(lseq + 1) / 2 + lseq : 0);
+    if (lseq < 0 || need > (uint64_t)bs) {
+      s->err.status = ORC_ERR_TRUNC;
+      s->err.offset = p;
+      s->err.msg = "record fields exceed block_size";
+      break;
+    }
+    s->rec_off.push_back(p);
+    s->block_size.push_back(bs);
+    s->ref_id.push_back((int32_t)le32(r));
+    int32_t pos = (int32_t)le32(r + 4);
+    s->pos.push_back(pos);
+    s->bin.push_back((uint16_t)(bin_mq_nl >> 16));
+    s->mapq.push_back((uint8_t)(bin_mq_nl >> 8));
+    s->l_read_name.push_back((uint8_t)lname);
+    uint16_t flag = (uint16_t)(flag_nc >> 16);
+    s->flag.push_back(flag);
+    s->n_cigar.push_back((uint16_t)nc);
+    s->l_seq.push_back(lseq);
+    s->next_ref.push_back((int32_t)le32(r + 20));
+    s->next_pos.push_back((int32_t)le32(r + 24));
+    s->tlen.push_back((int32_t)le32(r + 28));
+    uint32_t covered = 0;
+    for (uint32_t k = 0; k < nc; k++) {
+      uint32_t raw = le32(r + 32 + lname + 4 * k);
+      s->cigar.push_back(raw);
+      if (op_ref(raw)) covered += raw >> 4;
+    }
+    if (flag & 0x4) covered = 0;                // read.d:257-259
+    s->cigar_off.push_back(s->cigar.size());
+    s->end_pos.push_back((int32_t)((uint32_t)pos + covered));
+    s->start_vo.push_back(voffset_of(s, p));    // readrange.d:64-66
+    p += 4 + (uint64_t)bs;
+    s->end_vo.push_back(voffset_of(s, p));      // readrange.d:55-57
+  }
+  if (!s->err.status && blk_err.status) s->err = blk_err;
+  return s->err.status;
+}
+
+// ---------------------------------------------------------------- pileup ----
+
+struct Cursor {              // PileupRead — bam/pileup.d:86-230
+  uint32_t read;             // index into the record table
+  int32_t end_position;      // EagerBamRead (read.d:1380-1383)
+  uint32_t op_index, op_raw, op_offset, qoff;
+};
+
+struct Pileup {
+  int status = 0;
+  std::string msg;
+  int ref_id = -1;
+  std::vector<int32_t> col_ref;
+  std::vector<uint64_t> col_pos, col_off;
+  std::vector<uint32_t> n_start;
+  std::vector<uint32_t> read_idx, qoff, op_index, op_offset;
+  std::vector<uint8_t> base, qual;
+};
+
+struct PileupSim {
+  const Bam* s;
+  Pileup* out;
+  std::vector<uint32_t> reads;   // filtered, in file order
+  size_t next = 0;
+  std::vector<Cursor> buf;
+  uint64_t position = 0;
+  int32_t ref = -1;
+  size_t n_starting = 0;
+  bool skip_zero;
+
+  const uint32_t* cig(uint32_t r) const { return s->cigar.data() + s->cigar_off[r]; }
+  uint32_t ncig(uint32_t r) const { return (uint32_t)(s->cigar_off[r + 1] - s->cigar_off[r]); }
+
+  bool reads_empty() const { return next >= reads.size(); }
+
+  void add(uint32_t r) {     // PileupRange.add :315-317, PileupRead ctor :175-192
+    Cursor c{};
+    c.read = r;
+    c.end_position = s->end_pos[r];
+    const uint32_t* cg = cig(r);
+    uint32_t n = ncig(r);
+    bool skipped_n = false;
+    for (c.op_index = 0; c.op_index < n; ++c.op_index) {
+      c.op_raw = cg[c.op_index];
+      if (op_ref(c.op_raw)) {
+        if ((c.op_raw & 0xF) != 3) break;            // type != 'N'
+        if ((c.op_raw >> 4) > 0) skipped_n = true;
+      } else if (op_query(c.op_raw)) {
+        c.qoff += c.op_raw >> 4;
+      }
+    }
+    // assertCigarIndexIsValid :224-228.  Restatement-defined: a leading N that
+    // is skipped without advancing the column makes the cursor run off the end
+    // of the CIGAR later (undefined in -release); both are reported as errors.
+    if ((c.op_index >= n || skipped_n) && !out->status) {
+      out->status = ORC_ERR_CIGAR;
+      out->msg = "Invalid read - CIGAR has no usable reference-consuming operation (record " + std::to_string(r) + ")";
+    }
+    buf.push_back(c);
+  }
+
+  void increment(Cursor& c) {   // incrementPosition :195-222
+    ++c.op_offset;
+    if (op_query(c.op_raw)) ++c.qoff;
+    if (c.op_offset >= (c.op_raw >> 4)) {
+      c.op_offset = 0;
+      const uint32_t* cg = cig(c.read);
+      uint32_t n = ncig(c.read);
+      for (++c.op_index; c.op_index < n; ++c.op_index) {
+        c.op_raw = cg[c.op_index];
+        if (op_ref(c.op_raw)) break;
+        if (op_query(c.op_raw)) c.qoff += c.op_raw >> 4;
+      }
+      // running past the end only happens on the very last live position of a
+      // read whose zero-length ops stole positions; the read dies before use.
+    }
+  }
+
+  void init_new_reference() {   // :399-424
+    uint32_t r = reads[next];
+    position = (uint64_t)(int64_t)s->pos[r];
+    ref = s->ref_id[r];
+    size_t n = 1;
+    add(r);
+    ++next;
+    while (!reads_empty()) {
+      r = reads[next];
+      if (s->ref_id[r] == ref && (uint64_t)(int64_t)s->pos[r] == position) { add(r); ++n; ++next; }
+      else break;
+    }
+    n_starting = n;
+  }
+
+  bool empty() const { return reads_empty() && buf.empty(); }   // :340-342
+
+  void pop_front() {            // :345-397
+    uint64_t pos = ++position;
+    size_t survived = 0;
+    for (size_t i = 0; i < buf.size(); ++i) {
+      if ((uint64_t)(int64_t)buf[i].end_position > pos) {
+        if (survived < i) buf[survived] = buf[i];
+        ++survived;
+      }
+    }
+    for (size_t i = 0; i < survived; ++i) increment(buf[i]);
+    buf.resize(survived);
+    n_starting = 0;
+    if (!reads_empty()) {
+      if (s->ref_id[reads[next]] != ref && survived == 0) {
+        init_new_reference();
+      } else {
+        size_t n = 0;
+        while (!reads_empty() && (uint64_t)(int64_t)s->pos[reads[next]] == pos && s->ref_id[reads[next]] == ref) {
+          add(reads[next]);
+          ++next;
+          ++n;
+        }
+        n_starting = n;
+        if (survived == 0 && n == 0 && skip_zero) init_new_reference();
+      }
+    }
+  }
+
+  void emit() {
+    out->col_ref.push_back(ref);
+    out->col_pos.push_back(position);
+    out->n_start.push_back((uint32_t)n_starting);
+    for (const Cursor& c : buf) {
+      const uint8_t* rec = s->u.data() + s->rec_off[c.read] + 4;
+      uint32_t lname = s->l_read_name[c.read];
+      uint32_t nc = s->n_cigar[c.read];
+      int32_t lseq = s->l_seq[c.read];
+      const uint8_t* seq = rec + 32 + lname + 4 * nc;
+      const uint8_t* ql = seq + (lseq + 1) / 2;
+      uint8_t base = '-', q = 255;                       // :115-134
+      if (op_query(c.op_raw) && op_ref(c.op_raw)) {
+        if ((int64_t)c.qoff < (int64_t)lseq) {
+          uint8_t byte = seq[c.qoff >> 1];               // read.d:364-383
+          uint8_t code = (c.qoff & 1) ? (byte & 0xF) : (byte >> 4);
+          base = (uint8_t)"=ACMGRSVTWYHKDBN"[code];      // bio/core/base.d:85
+          q = ql[c.qoff];                                // read.d:468-470
+        } else if (!out->status) {
+          out->status = ORC_ERR_CIGAR;                   // RangeError in D
+          out->msg = "query offset beyond sequence (record " + std::to_string(c.read) + ")";
+        }
+      }
+      out->read_idx.push_back(c.read);
+      out->base.push_back(base);
+      out->qual.push_back(q);
+      out->qoff.push_back(c.qoff);
+      out->op_index.push_back(c.op_index);
+      out->op_offset.push_back(c.op_offset);
+    }
+    out->col_off.push_back(out->read_idx.size());
+  }
+};
+
+// makePileup / pileupInstance (pileup.d:480-507, 683-694) when single_ref != 0,
+// pileupColumns (pileup.d:509-519) otherwise.
+Pileup* run_pileup(const Bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero,
+                   int64_t rec_begin, int64_t rec_end) {
+  Pileup* out = new Pileup;
+  out->col_off.push_back(0);
+  PileupSim sim;
+  sim.s = s;
+  sim.out = out;
+  sim.skip_zero = skip_zero != 0;
+  int64_t n = (int64_t)s->rec_off.size();
+  if (rec_end < 0 || rec_end > n) rec_end = n;
+  if (rec_begin < 0) rec_begin = 0;
+  for (int64_t r = rec_begin; r < rec_end; ++r)
+    if (s->end_pos[r] - s->pos[r] > 0) sim.reads.push_back((uint32_t)r);   // filter basesCovered()>0 (:481,:510)
+  if (single_ref) {
+    size_t k = 0;                                                           // :482-489
+    while (k < sim.reads.size() && (uint64_t)(int64_t)s->end_pos[sim.reads[k]] < start_from) ++k;
+    sim.reads.erase(sim.reads.begin(), sim.reads.begin() + k);
+    if (!sim.reads.empty()) {
+      out->ref_id = s->ref_id[sim.reads[0]];                                // :490-493
+      size_t m = 0;
+      while (m < sim.reads.size() && s->ref_id[sim.reads[m]] == out->ref_id) ++m;   // takeUntil :494
+      sim.reads.resize(m);
+    }
+  } else {
+    start_from = 0;
+    end_at = ~0ull;
+  }
+  if (!sim.reads.empty()) sim.init_new_reference();                         // :328-331
+  while (!sim.empty() && sim.position < start_from) sim.pop_front();        // :497-504
+  while (!sim.empty()) {
+    if (sim.position >= end_at) break;                                      // takeUntil :505
+    sim.emit();
+    sim.pop_front();
+  }
+  return out;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C API ----
+extern "C" {
+
+typedef struct Bam orc_bam;
+typedef struct Pileup orc_pileup;
+
+orc_bam* orc_open(const uint8_t* data, uint64_t len) {
+  Bam* s = new Bam;
+  s->file = data;
+  s->flen = len;
+  parse_header(s);
+  return s;
+}
+void orc_close(orc_bam* s) { delete s; }
+// status of open: an error in a block beyond the header is deferred to decode.
+int orc_open_status(const orc_bam* s) { return s->reads_start_u ? 0 : s->err.status; }
+int orc_status(const orc_bam* s) { return s->err.status; }
+int orc_zlib_errnum(const orc_bam* s) { return s->err.zerr; }
+uint64_t orc_err_offset(const orc_bam* s) { return s->err.offset; }
+const char* orc_errmsg(const orc_bam* s) { return s->err.msg.c_str(); }
+
+const char* orc_header_text(const orc_bam* s, uint64_t* len) { *len = s->text.size(); return s->text.data(); }
+int orc_n_refs(const orc_bam* s) { return (int)s->ref_names.size(); }
+const char* orc_ref_name(const orc_bam* s, int i) { return s->ref_names[i].c_str(); }
+int orc_ref_len(const orc_bam* s, int i) { return s->ref_lens[i]; }
+uint64_t orc_reads_start_voffset(const orc_bam* s) { return s->reads_start_vo; }
+uint64_t orc_reads_start_uoffset(const orc_bam* s) { return s->reads_start_u; }
+
+int orc_decode(orc_bam* s) { return decode_records(s); }
+uint64_t orc_n_blocks(const orc_bam* s) { return s->blocks.size(); }
+// field: 0 coffset, 1 bsize, 2 cdata_size, 3 crc32, 4 isize, 5 uoffset, 6 payload offset
+uint64_t orc_block_field(const orc_bam* s, uint64_t i, int f) {
+  const Block& b = s->blocks[i];
+  switch (f) {
+    case 0: return b.coffset; case 1: return b.bsize; case 2: return b.cdata_size; case 3: return b.crc32;
+    case 4: return b.isize; case 5: return b.uoffset; default: return b.payload;
+  }
+}
+const uint8_t* orc_udata(const orc_bam* s, uint64_t* len) { *len = s->u.size(); return s->u.data(); }
+uint64_t orc_n_records(const orc_bam* s) { return s->rec_off.size(); }
+uint64_t orc_n_cigar_total(const orc_bam* s) { return s->cigar.size(); }
+#define ORC_ARR(name, type, member) const type* orc_##name(const orc_bam* s) { return s->member.data(); }
+ORC_ARR(rec_off, uint64_t, rec_off)
+ORC_ARR(block_size, int32_t, block_size)
+ORC_ARR(ref_id, int32_t, ref_id)
+ORC_ARR(pos, int32_t, pos)
+ORC_ARR(end_pos, int32_t, end_pos)
+ORC_ARR(l_seq, int32_t, l_seq)
+ORC_ARR(next_ref, int32_t, next_ref)
+ORC_ARR(next_pos, int32_t, next_pos)
+ORC_ARR(tlen, int32_t, tlen)
+ORC_ARR(bin, uint16_t, bin)
+ORC_ARR(flag, uint16_t, flag)
+ORC_ARR(n_cigar, uint16_t, n_cigar)
+ORC_ARR(mapq, uint8_t, mapq)
+ORC_ARR(l_read_name, uint8_t, l_read_name)
+ORC_ARR(start_vo, uint64_t, start_vo)
+ORC_ARR(end_vo, uint64_t, end_vo)
+ORC_ARR(cigar_off, uint64_t, cigar_off)
+ORC_ARR(cigar, uint32_t, cigar)
+
+orc_pileup* orc_pileup_run(orc_bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero) {
+  decode_records(s);
+  return run_pileup(s, single_ref, start_from, end_at, skip_zero, 0, -1);
+}
+// pileup over records [rec_begin, rec_end) only — used to restate pileupChunks
+// (pileup.d:859-1015), whose front is makePileup(chain(prev_chunk, current_chunk), ...).
+orc_pileup* orc_pileup_run_range(orc_bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero,
+                                 int64_t rec_begin, int64_t rec_end) {
+  decode_records(s);
+  return run_pileup(s, single_ref, start_from, end_at, skip_zero, rec_begin, rec_end);
+}
+void orc_pileup_free(orc_pileup* p) { delete p; }
+int orc_pileup_status(const orc_pileup* p) { return p->status; }
+const char* orc_pileup_errmsg(const orc_pileup* p) { return p->msg.c_str(); }
+int orc_pileup_ref_id(const orc_pileup* p) { return p->ref_id; }
+uint64_t orc_pileup_n_columns(const orc_pileup* p) { return p->col_pos.size(); }
+uint64_t orc_pileup_n_entries(const orc_pileup* p) { return p->read_idx.size(); }
+#define ORC_PARR(name, type, member) const type* orc_pileup_##name(const orc_pileup* p) { return p->member.data(); }
+ORC_PARR(col_ref, int32_t, col_ref)
+ORC_PARR(col_pos, uint64_t, col_pos)
+ORC_PARR(col_off, uint64_t, col_off)
+ORC_PARR(n_start, uint32_t, n_start)
+ORC_PARR(read_idx, uint32_t, read_idx)
+ORC_PARR(qoff, uint32_t, qoff)
+ORC_PARR(op_index, uint32_t, op_index)
+ORC_PARR(op_offset, uint32_t, op_offset)
+ORC_PARR(base, uint8_t, base)
+ORC_PARR(qual, uint8_t, qual)
+
+// ------------------------------------------------------- CPU baseline legs ----
+// "Restated BioD CPU path (libz, g++ -O3), not the D binary" (BASELINE.md §2):
+// inflate with `threads` worker threads the way BgzfInputStream hands whole
+// blocks to a TaskPool (inputstream.d:414-417; default totalCPUs-1 workers),
+// framing + field decode + pileup single-threaded by construction
+// (readrange.d:118-173, pileup.d:345-397).  Returns seconds per leg.
+int orc_cpu_baseline(const uint8_t* data, uint64_t len, int threads, int do_pileup, double* t_inflate,
+                     double* t_decode, double* t_pileup, uint64_t* n_records, uint64_t* n_columns,
+                     uint64_t* n_entries, uint64_t* checksum) {
+  auto now = [] {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+  };
+  Bam* s = new Bam;
+  s->file = data;
+  s->flen = len;
+  double t0 = now();
+  // pass 1: header chain walk (serial, as the consumer thread does)
+  std::vector<Block> blocks;
+  uint64_t pos = 0, utotal = 0;
+  while (true) {
+    Block b;
+    int r = parse_bgzf_header(data, len, pos, &b, &s->err);
+    if (r < 0) { int st = s->err.status; delete s; return st; }
+    if (r == 0 || b.isize == 0) break;
+    if (b.isize > BGZF_MAX_BLOCK_SIZE) { delete s; return ORC_ERR_FORMAT; }
+    b.uoffset = utotal;
+    utotal += b.isize;
+    blocks.push_back(b);
+    pos = b.coffset + b.bsize + 1;
+  }
+  s->u.resize(utotal);
+  if (threads < 1) threads = 1;
+  std::vector<std::thread> pool;
+  std::vector<int> bad(threads, 0);
+  for (int t = 0; t < threads; t++) {
+    pool.emplace_back([&, t] {
+      Error e;
+      for (size_t i = t; i < blocks.size(); i += threads)
+        if (inflate_block(data, blocks[i], s->u.data() + blocks[i].uoffset, &e) < 0) bad[t] = e.status;
+    });
+  }
+  for (auto& th : pool) th.join();
+  for (int t = 0; t < threads; t++) if (bad[t]) { int st = bad[t]; delete s; return st; }
+  s->blocks = blocks;
+  s->stream_done = true;
+  double t1 = now();
+  // header parse over the already inflated stream, then the record walk
+  int r = parse_header(s);
+  if (r < 0) { delete s; return r; }
+  r = decode_records(s);
+  if (r < 0) { delete s; return r; }
+  double t2 = now();
+  *t_inflate = t1 - t0;
+  *t_decode = t2 - t1;
+  *n_records = s->rec_off.size();
+  *t_pileup = 0;
+  *n_columns = *n_entries = 0;
+  uint64_t cs = 0;
+  for (size_t i = 0; i < s->pos.size(); i++) cs = cs * 1099511628211ull + (uint32_t)s->end_pos[i];
+  if (do_pileup) {
+    Pileup* p = run_pileup(s, 0, 0, ~0ull, 1, 0, -1);
+    double t3 = now();
+    *t_pileup = t3 - t2;
+    *n_columns = p->col_pos.size();
+    *n_entries = p->read_idx.size();
+    for (size_t i = 0; i < p->base.size(); i++) cs = cs * 1099511628211ull + p->base[i] + 256u * p->qual[i];
+    int st = p->status;
+    delete p;
+    if (st) { delete s; return st; }
+  }
+  *checksum = cs;
+  delete s;
+  return 0;
+}
+
+}  // extern "C"

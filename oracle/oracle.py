@@ -1,0 +1,251 @@
+"""ctypes loader for the CPU oracle (TEST INFRASTRUCTURE ONLY — see oracle.cpp).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product (biod_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+OK, ERR_BGZF, ERR_ZLIB, ERR_FORMAT, ERR_TRUNC, ERR_CIGAR, ERR_UNSORTED = 0, -1, -2, -3, -4, -7, -8
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        u8p, u64 = C.POINTER(C.c_uint8), C.c_uint64
+        L.orc_open.restype = C.c_void_p
+        L.orc_open.argtypes = [C.c_void_p, u64]
+        L.orc_close.argtypes = [C.c_void_p]
+        for f in ("orc_open_status", "orc_status", "orc_zlib_errnum", "orc_n_refs", "orc_decode"):
+            getattr(L, f).restype = C.c_int
+            getattr(L, f).argtypes = [C.c_void_p]
+        for f in ("orc_err_offset", "orc_reads_start_voffset", "orc_reads_start_uoffset", "orc_n_blocks",
+                  "orc_n_records", "orc_n_cigar_total"):
+            getattr(L, f).restype = u64
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_errmsg.restype = C.c_char_p
+        L.orc_errmsg.argtypes = [C.c_void_p]
+        L.orc_header_text.restype = C.c_void_p
+        L.orc_header_text.argtypes = [C.c_void_p, C.POINTER(u64)]
+        L.orc_ref_name.restype = C.c_char_p
+        L.orc_ref_name.argtypes = [C.c_void_p, C.c_int]
+        L.orc_ref_len.restype = C.c_int
+        L.orc_ref_len.argtypes = [C.c_void_p, C.c_int]
+        L.orc_block_field.restype = u64
+        L.orc_block_field.argtypes = [C.c_void_p, u64, C.c_int]
+        L.orc_udata.restype = C.c_void_p
+        L.orc_udata.argtypes = [C.c_void_p, C.POINTER(u64)]
+        for name in list(_REC_ARRAYS) + ["cigar_off", "cigar"]:
+            fn = getattr(L, "orc_" + name)
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.c_void_p]
+        L.orc_pileup_run.restype = C.c_void_p
+        L.orc_pileup_run.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int]
+        L.orc_pileup_run_range.restype = C.c_void_p
+        L.orc_pileup_run_range.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int, C.c_int64, C.c_int64]
+        L.orc_pileup_free.argtypes = [C.c_void_p]
+        L.orc_pileup_status.restype = C.c_int
+        L.orc_pileup_status.argtypes = [C.c_void_p]
+        L.orc_pileup_errmsg.restype = C.c_char_p
+        L.orc_pileup_errmsg.argtypes = [C.c_void_p]
+        L.orc_pileup_ref_id.restype = C.c_int
+        L.orc_pileup_ref_id.argtypes = [C.c_void_p]
+        for f in ("orc_pileup_n_columns", "orc_pileup_n_entries"):
+            getattr(L, f).restype = u64
+            getattr(L, f).argtypes = [C.c_void_p]
+        for name in list(_PILEUP_ARRAYS) + ["col_off"]:
+            fn = getattr(L, "orc_pileup_" + name)
+            fn.restype = C.c_void_p
+            fn.argtypes = [C.c_void_p]
+        L.orc_cpu_baseline.restype = C.c_int
+        L.orc_cpu_baseline.argtypes = [C.c_void_p, u64, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3 + \
+            [C.POINTER(u64)] * 4
+        _LIB = L
+    return _LIB
+
+
+_REC_ARRAYS = {
+    "rec_off": np.uint64, "block_size": np.int32, "ref_id": np.int32, "pos": np.int32, "end_pos": np.int32,
+    "l_seq": np.int32, "next_ref": np.int32, "next_pos": np.int32, "tlen": np.int32, "bin": np.uint16,
+    "flag": np.uint16, "n_cigar": np.uint16, "mapq": np.uint8, "l_read_name": np.uint8,
+    "start_vo": np.uint64, "end_vo": np.uint64,
+}
+_PILEUP_ARRAYS = {
+    "col_ref": np.int32, "col_pos": np.uint64, "n_start": np.uint32, "read_idx": np.uint32, "qoff": np.uint32,
+    "op_index": np.uint32, "op_offset": np.uint32, "base": np.uint8, "qual": np.uint8,
+}
+
+
+def _arr(ptr, n, dtype):
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    buf = (C.c_uint8 * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+class OracleError(Exception):
+    def __init__(self, status, msg, zerr=0, offset=0):
+        super().__init__(f"oracle status {status}: {msg}")
+        self.status, self.msg, self.zerr, self.offset = status, msg, zerr, offset
+
+
+class Pileup:
+    """Result of makePileup / pileupColumns restated on the CPU."""
+
+    def __init__(self, L, h):
+        self.status = L.orc_pileup_status(h)
+        self.msg = L.orc_pileup_errmsg(h).decode()
+        self.ref_id = L.orc_pileup_ref_id(h)
+        nc, ne = L.orc_pileup_n_columns(h), L.orc_pileup_n_entries(h)
+        self.n_columns, self.n_entries = int(nc), int(ne)
+        for name, dt in _PILEUP_ARRAYS.items():
+            n = nc if name in ("col_ref", "col_pos", "n_start") else ne
+            setattr(self, name, _arr(getattr(L, "orc_pileup_" + name)(h), n, dt))
+        self.col_off = _arr(L.orc_pileup_col_off(h), nc + 1, np.uint64)
+        L.orc_pileup_free(h)
+
+    def bases(self, c):
+        a, b = int(self.col_off[c]), int(self.col_off[c + 1])
+        return self.base[a:b].tobytes().decode()
+
+
+class Bam:
+    """Restated BamReader: open parses the header; decode() walks every record."""
+
+    def __init__(self, data: bytes):
+        self._L = L = lib()
+        self._data = np.frombuffer(data, dtype=np.uint8)  # keep alive (oracle does not copy)
+        self._h = L.orc_open(self._data.ctypes.data, len(data))
+        st = L.orc_open_status(self._h)
+        if st:
+            e = self._error()
+            self.close()
+            raise e
+        n = C.c_uint64()
+        p = L.orc_header_text(self._h, C.byref(n))
+        self.header_text = C.string_at(p, n.value).decode("latin-1") if n.value else ""
+        self.ref_names = [L.orc_ref_name(self._h, i).decode() for i in range(L.orc_n_refs(self._h))]
+        self.ref_lens = [L.orc_ref_len(self._h, i) for i in range(L.orc_n_refs(self._h))]
+        self.reads_start_voffset = int(L.orc_reads_start_voffset(self._h))
+        self.reads_start_uoffset = int(L.orc_reads_start_uoffset(self._h))
+        self._decoded = False
+
+    def _error(self):
+        L = self._L
+        return OracleError(L.orc_status(self._h), L.orc_errmsg(self._h).decode(), L.orc_zlib_errnum(self._h),
+                           int(L.orc_err_offset(self._h)))
+
+    def close(self):
+        if self._h:
+            self._L.orc_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def decode(self, raise_on_error=True):
+        L = self._L
+        st = L.orc_decode(self._h)
+        self.status = st
+        self.error = self._error() if st else None
+        n = int(L.orc_n_records(self._h))
+        self.n_records = n
+        for name, dt in _REC_ARRAYS.items():
+            setattr(self, name, _arr(getattr(L, "orc_" + name)(self._h), n, dt))
+        self.cigar_off = _arr(L.orc_cigar_off(self._h), n + 1, np.uint64)
+        self.cigar = _arr(L.orc_cigar(self._h), int(L.orc_n_cigar_total(self._h)), np.uint32)
+        ln = C.c_uint64()
+        p = L.orc_udata(self._h, C.byref(ln))
+        self.udata = _arr(p, ln.value, np.uint8)
+        nb = int(L.orc_n_blocks(self._h))
+        self.n_blocks = nb
+        self.blocks = np.array([[L.orc_block_field(self._h, i, f) for f in range(7)] for i in range(nb)],
+                               dtype=np.uint64).reshape(nb, 7)
+        self._decoded = True
+        if st and raise_on_error:
+            raise self.error
+        return self
+
+    # -- record views (restating bam/read.d accessors) --------------------
+    def record_bytes(self, i):
+        o = int(self.rec_off[i]) + 4
+        return self.udata[o:o + int(self.block_size[i])]
+
+    def name(self, i):
+        r = self.record_bytes(i)
+        return r[32:32 + int(self.l_read_name[i]) - 1].tobytes().decode("latin-1")
+
+    def cigar_ops(self, i):
+        a, b = int(self.cigar_off[i]), int(self.cigar_off[i + 1])
+        return [(int(x) >> 4, "MIDNSHP=X???????"[int(x) & 15]) for x in self.cigar[a:b]]
+
+    def cigar_string(self, i):
+        ops = self.cigar_ops(i)
+        return "".join(f"{l}{o}" for l, o in ops) if ops else "*"
+
+    def sequence(self, i):
+        r = self.record_bytes(i)
+        o = 32 + int(self.l_read_name[i]) + 4 * int(self.n_cigar[i])
+        n = int(self.l_seq[i])
+        packed = r[o:o + (n + 1) // 2]
+        codes = np.empty(2 * len(packed), dtype=np.uint8)
+        codes[0::2] = packed >> 4
+        codes[1::2] = packed & 15
+        return np.frombuffer(b"=ACMGRSVTWYHKDBN", dtype=np.uint8)[codes[:n]].tobytes().decode()
+
+    def qualities(self, i):
+        r = self.record_bytes(i)
+        n = int(self.l_seq[i])
+        o = 32 + int(self.l_read_name[i]) + 4 * int(self.n_cigar[i]) + (n + 1) // 2
+        return r[o:o + n]
+
+    def tags_raw(self, i):
+        r = self.record_bytes(i)
+        n = int(self.l_seq[i])
+        o = 32 + int(self.l_read_name[i]) + 4 * int(self.n_cigar[i]) + (n + 1) // 2 + n
+        return r[o:].tobytes()
+
+    # -- pileup ------------------------------------------------------------
+    def make_pileup(self, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True):
+        return Pileup(self._L, self._L.orc_pileup_run(self._h, 1, start_from, end_at, int(skip_zero_coverage)))
+
+    def pileup_columns(self, skip_zero_coverage=True):
+        return Pileup(self._L, self._L.orc_pileup_run(self._h, 0, 0, 2**64 - 1, int(skip_zero_coverage)))
+
+    def make_pileup_range(self, rec_begin, rec_end, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
+                          single_ref=True):
+        return Pileup(self._L, self._L.orc_pileup_run_range(self._h, int(single_ref), start_from, end_at,
+                                                            int(skip_zero_coverage), rec_begin, rec_end))
+
+
+def cpu_baseline(data, threads, do_pileup=True):
+    """Time the restated CPU path on `data` (bytes-like BAM).  Returns a dict."""
+    L = lib()
+    a = np.frombuffer(data, dtype=np.uint8)
+    ti, td, tp = C.c_double(), C.c_double(), C.c_double()
+    nr, nc, ne, cs = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    st = L.orc_cpu_baseline(a.ctypes.data, len(a), threads, int(do_pileup), C.byref(ti), C.byref(td), C.byref(tp),
+                            C.byref(nr), C.byref(nc), C.byref(ne), C.byref(cs))
+    if st:
+        raise OracleError(st, "cpu baseline failed")
+    return dict(t_inflate=ti.value, t_decode=td.value, t_pileup=tp.value, n_records=nr.value,
+                n_columns=nc.value, n_entries=ne.value, checksum=cs.value)

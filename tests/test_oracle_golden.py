@@ -1,0 +1,244 @@
+"""Pins the CPU oracle against the reference's OWN golden vectors (no GPU needed).
+
+Every assertion below restates one made by BioD's tests; the citation is next to it.
+"""
+import numpy as np
+import pytest
+
+from conftest import fixture_bytes
+from bamutil import bam_record, make_bam, tag_z, tags_to_sam
+from oracle import oracle as orc
+
+
+@pytest.fixture(scope="module")
+def ex1():
+    return orc.Bam(fixture_bytes("ex1_header.bam")).decode()
+
+
+def test_header_fields(ex1):
+    # test/unittests.d:70-84
+    assert ex1.ref_names == ["chr1", "chr2"]
+    assert ex1.ref_lens == [1575, 1584]
+    assert ex1.header_text.startswith("@HD")
+
+
+def test_first_records(ex1):
+    # test/unittests.d:88-103
+    assert ex1.sequence(0) == "CTCAAGGTTGTTGCAAGGGGGTCTATGTGAACAAA"
+    assert bytes(ex1.qualities(0) + 33).decode() == "<<<7<<<;<<<<<<<<8;;<7;4<;<;;;;;94<;"
+    assert ex1.ref_names[ex1.ref_id[0]] == "chr1"
+    assert ex1.name(0) == "EAS56_57:6:190:289:82"
+    assert ex1.flag[0] == 69
+    assert ex1.pos[0] == 99
+    assert ex1.mapq[0] == 0
+    assert ex1.cigar_string(2) == "35M"
+
+
+def sam_line(b, i):
+    """BamRead.toSam restated for the fields the SAM golden holds (bam/read.d:613-700)."""
+    rn = "*" if b.ref_id[i] < 0 else b.ref_names[b.ref_id[i]]
+    if b.next_ref[i] < 0:
+        mrn = "*"
+    elif b.next_ref[i] == b.ref_id[i]:
+        mrn = "="
+    else:
+        mrn = b.ref_names[b.next_ref[i]]
+    seq = b.sequence(i) or "*"
+    q = b.qualities(i)
+    qs = "*" if len(q) == 0 or q[0] == 255 else bytes(q + 33).decode("latin-1")
+    f = [b.name(i), str(b.flag[i]), rn, str(b.pos[i] + 1), str(b.mapq[i]), b.cigar_string(i), mrn,
+         str(b.next_pos[i] + 1), str(b.tlen[i]), seq, qs]
+    return "\t".join(f + tags_to_sam(b.tags_raw(i)))
+
+
+def test_third_record_sam_text(ex1):
+    # test/unittests.d:103
+    assert sam_line(ex1, 2) == ("EAS51_64:3:190:727:308\t99\tchr1\t103\t99\t35M\t=\t263\t195\t"
+                                "GGTGCAGAGCCGAGTCACGGGGTTGCCAGCACAGG\t<<<<<<<<<<<<<<<<<<<<<<<<<<<::<<<844\t"
+                                "MF:i:18\tAq:i:73\tNM:i:0\tUQ:i:0\tH0:i:1\tH1:i:0")
+
+
+def test_all_records_equal_sam_golden(ex1):
+    # test/unittests.d:303 (3270 records) and :309-312 (SAM file == BAM file record for record)
+    assert ex1.n_records == 3270
+    sam = [l for l in fixture_bytes("ex1_header.sam").decode().split("\n") if l and not l.startswith("@")]
+    assert len(sam) == 3270
+    for i, line in enumerate(sam):
+        assert sam_line(ex1, i) == line, i
+
+
+@pytest.mark.parametrize("name,cls", [
+    ("duplicated_block_size.bam", orc.ERR_BGZF), ("no_block_size.bam", orc.ERR_BGZF),
+    ("wrong_extra_gzip_length.bam", orc.ERR_BGZF), ("wrong_bc_subfield_length.bam", orc.ERR_BGZF),
+    ("corrupted_zlib_archive.bam", orc.ERR_ZLIB)])
+def test_corrupted_files_raise_the_pinned_classes(name, cls):
+    # test/unittests.d:132-142 — either the constructor or the iteration throws
+    with pytest.raises(orc.OracleError) as ei:
+        orc.Bam(fixture_bytes(name)).decode()
+    assert ei.value.status == cls
+    if cls == orc.ERR_BGZF:
+        assert ei.value.msg.startswith("Error reading BGZF block starting from offset ")
+
+
+def test_error_messages_and_locations():
+    with pytest.raises(orc.OracleError) as ei:
+        orc.Bam(fixture_bytes("wrong_bc_subfield_length.bam")).decode()
+    assert ei.value.offset == 36489 and "wrong BC subfield length: 5; expected 2" in ei.value.msg
+    with pytest.raises(orc.OracleError) as ei:
+        orc.Bam(fixture_bytes("duplicated_block_size.bam"))
+    assert "duplicate field with block size" in ei.value.msg
+    with pytest.raises(orc.OracleError) as ei:
+        orc.Bam(fixture_bytes("no_block_size.bam"))
+    assert "block size was not found in any subfield" in ei.value.msg
+    with pytest.raises(orc.OracleError) as ei:
+        orc.Bam(fixture_bytes("corrupted_zlib_archive.bam")).decode()
+    assert ei.value.zerr == -3  # Z_DATA_ERROR
+
+
+def test_lazy_error_keeps_earlier_records():
+    # the fault is in block 3: records of blocks 1-2 are delivered before the throw (unittests.d:139)
+    b = orc.Bam(fixture_bytes("wrong_bc_subfield_length.bam")).decode(raise_on_error=False)
+    assert b.status == orc.ERR_BGZF and b.n_records > 0
+
+
+@pytest.mark.parametrize("name,n_blocks,n_bytes,n_reads", [
+    ("ex1_header.bam", 9, 456679, 3270), ("illu_20_chunk.bam", 3, 32310, 29), ("bins.bam", 28, 1670543, 16458),
+    ("tags.bam", 3, 31612, 417), ("b7_295_chunk.bam", 22, None, 449), ("mg1655_chunk.bam", 26, None, 556),
+    ("ion_20_chunk.bam", 13, None, 476), ("long_header.bam", 3, 75979, 0)])
+def test_valid_fixtures_decode(name, n_blocks, n_bytes, n_reads):
+    b = orc.Bam(fixture_bytes(name)).decode()
+    assert b.n_records == n_reads
+    assert b.n_blocks == n_blocks - 1  # SURVEY counts include the 28-byte EOF block
+    if n_bytes is not None:
+        assert len(b.udata) == n_bytes
+    # virtual offsets are consistent: each record starts where the previous one ended
+    if n_reads:
+        assert b.start_vo[0] == b.reads_start_voffset
+        assert np.array_equal(b.start_vo[1:], b.end_vo[:-1])
+
+
+def test_makepileup_stops_at_first_reference(ex1):
+    # test/unittests.d:320-330
+    p = ex1.make_pileup()
+    assert p.status == 0 and p.n_columns == 1470
+    assert set(p.col_ref.tolist()) == {0}
+    assert not (ex1.flag[p.read_idx] & 4).any()
+    assert (ex1.ref_id[p.read_idx] == 0).all()
+
+
+def test_pileupcolumns_counts_and_first_columns(ex1):
+    # test/unittests.d:334-367
+    p = ex1.pileup_columns()
+    assert p.status == 0
+    assert int((p.col_ref == 0).sum()) == 1470 and int((p.col_ref == 1).sum()) == 1567
+    assert (np.diff(p.col_ref) >= 0).all()
+    c0 = 0
+    c1 = int(np.argmax(p.col_ref == 1))
+    assert p.col_pos[c0] == 99 and ex1.name(int(p.read_idx[p.col_off[c0]])) == "EAS56_57:6:190:289:82"
+    assert p.col_pos[c1] == 0 and ex1.name(int(p.read_idx[p.col_off[c1]])) == "B7_591:8:4:841:340"
+    col_of_entry = np.repeat(np.arange(p.n_columns), np.diff(p.col_off).astype(np.int64))
+    assert (ex1.ref_id[p.read_idx] == p.col_ref[col_of_entry]).all()
+    assert not (ex1.flag[p.read_idx] & 4).any()
+
+
+# ---- in-module vectors of bam/pileup.d:699-857 -----------------------------------------------
+SEQS = ["ATTATGGACATTGTTTCCGTTATCATCATCATCATCATCATCATCATTATCATC",
+        "GACATTGTTTCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATC",
+        "ATTGTTTCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATCACC",
+        "TGTTTCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATCACCAC",
+        "TCCGTTATCATCATCATCATCATCATCATCATCATCATCATCATCACCACCACC",
+        "GTTATCATCATCATCATCATCATCATCATCATCATCATCATCATCGTCACCCTG",
+        "TCATCATCATCATAATCATCATCATCATCATCATCATCGTCACCCTGTGTTGAG",
+        "TCATCATCATCGTCACCCTGTGTTGAGGACAGAAGTAATTTCCCTTTCTTGGCT",
+        "TCATCATCATCATCACCACCACCACCCTGTGTTGAGGACAGAAGTAATATCCCT",
+        "CACCACCACCCTGTGTTGAGGACAGAAGTAATTTCCCTTTCTTGGCTGGTCACC"]
+CIGARS = ["54M", "54M", "50M3I1M", "54M", "54M", "54M", "2S52M", "16M15D38M", "13M3I38M", "54M"]
+POSITIONS = [758, 764, 767, 769, 773, 776, 785, 795, 804, 817]
+MDS = ["47C6", "54", "51", "50T3", "46T7", "45A0C7", "11C24A0C14", "11A3T0^CATCATCATCACCAC38", "15T29T5", "2T45T5"]
+
+
+def pileup_vector_bam():
+    recs = [bam_record(f"r{i}", SEQS[i], CIGARS[i], POSITIONS[i], tags=tag_z("MD", MDS[i])) for i in range(10)]
+    return make_bam([("20", 63025520)], recs)
+
+
+def test_pileup_unit_vector():
+    # bam/pileup.d:776-825
+    b = orc.Bam(pileup_vector_bam()).decode()
+    sub = b.make_pileup(796, 849, False)
+    full = b.make_pileup(0, 2**64 - 1, False)
+    assert sub.status == 0 and full.status == 0
+    assert sub.col_pos[0] == 796
+    assert sub.col_pos[-1] == 848  # half-open: the range is empty once position >= end_at (pileup.d:505)
+    k = int(np.argmax(full.col_pos == 796))
+    n = sub.n_columns
+    assert np.array_equal(np.diff(sub.col_off), np.diff(full.col_off)[k:k + n])  # :789
+    col = {int(p): c for c, p in enumerate(full.col_pos)}
+    assert full.bases(col[796]) == "CCCCCCAC"        # :793
+    assert full.bases(col[805]) == "TCCCCCCCC"       # :797
+    assert full.bases(col[806]) == "AAAAAAAGA"       # :801
+    assert full.bases(col[821]) == "AAGG-AA"         # :815
+    assert full.bases(col[826]) == "CCCCCC"          # :819
+    assert full.bases(col[849]) == "TAT"             # :823
+
+    def entry(pos, k_from_end):
+        c = col[pos]
+        return int(full.col_off[c + 1]) - k_from_end
+
+    # :805 cigar_after.front.type == 'D' at 810 for reads[coverage-2]
+    e = entry(810, 2)
+    r = int(full.read_idx[e])
+    assert b.cigar_ops(r)[int(full.op_index[e]) + 1][1] == "D"
+    # :809 cigar_before.back.type == 'I' at 817
+    e = entry(817, 2)
+    r = int(full.read_idx[e])
+    assert b.cigar_ops(r)[int(full.op_index[e]) - 1][1] == "I"
+    # :813 cigar_operation.type == 'D' at 821 for reads[coverage-3]
+    e = entry(821, 3)
+    r = int(full.read_idx[e])
+    assert b.cigar_ops(r)[int(full.op_index[e])][1] == "D"
+    assert full.qual[e] == 255 and full.base[e] == ord("-")
+
+
+def test_pileup_zero_coverage_vector():
+    # bam/pileup.d:830-856: with skip_zero_coverage=false one column per reference position of dna(reads)
+    seqs = ["CCCACATAGAAAGCTTGCTGTTTCTCTGTGGGAAGTTTTAACTTAGGTCAGCTT",
+            "TAGAAAGCTTGCTGTTTCTCTGTGGGAAGTTTTAACTTAGGTTAGCTTCATCTA",
+            "TTTTTCTTTCTTTCTTTGAAGAAGGCAGATTCCTGGTCCTGCCACTCAAATTTT",
+            "TTTCTTTCTTTCTTTGAAGAAGGCAGATTCCTGGTCCTGCCACTCAAATTTTCA"]
+    pos = [979, 985, 1046, 1048]
+    recs = [bam_record(f"r{i + 1}", seqs[i], "54M", pos[i]) for i in range(4)]
+    b = orc.Bam(make_bam([("20", 63025520)], recs)).decode()
+    p = b.make_pileup(0, 2**64 - 1, False)
+    assert p.n_columns == (1048 + 54) - 979
+    assert np.array_equal(p.col_pos, np.arange(979, 1048 + 54, dtype=np.uint64))
+    cov = np.diff(p.col_off)
+    assert (cov[985 + 54 - 979:1046 - 979] == 0).all() and cov[0] == 1
+    q = b.make_pileup(0, 2**64 - 1, True)
+    assert q.n_columns == int((cov > 0).sum())
+
+
+def test_make_pileup_example_invariant():
+    # examples/make_pileup.d:20-30: joiner(columns.reads_starting_here) == bam.reads
+    b = orc.Bam(fixture_bytes("illu_20_chunk.bam")).decode()
+    assert b.n_records == 29
+    p = b.make_pileup()
+    starting = []
+    for c in range(p.n_columns):
+        hi = int(p.col_off[c + 1])
+        starting += p.read_idx[hi - int(p.n_start[c]):hi].tolist()
+    assert starting == list(range(29))
+    # ... and column.reads.equalRange(column.position) is the same set (make_pileup.d:20-24)
+    for c in range(p.n_columns):
+        lo, hi = int(p.col_off[c]), int(p.col_off[c + 1])
+        here = [int(r) for r in p.read_idx[lo:hi] if b.pos[r] == p.col_pos[c]]
+        assert here == p.read_idx[hi - int(p.n_start[c]):hi].tolist()
+
+
+def test_bins_bam_all_cigar_ops():
+    # bins.bam is the only fixture with N, = and X operations
+    b = orc.Bam(fixture_bytes("bins.bam")).decode()
+    ops = set((b.cigar & 15).tolist())
+    assert {0, 1, 2, 3, 7, 8} <= ops
+    p = b.pileup_columns()
+    assert p.status == 0 and p.n_entries > 0
