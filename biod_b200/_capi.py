@@ -1,0 +1,111 @@
+"""ctypes binding of libbiod_b200.so (include/biod_b200.h).  Fails loudly when the CUDA library is
+missing: there is no CPU fallback anywhere in this package."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbiod_b200.so")
+
+OK, EOF = 0, 1
+ERR_BGZF, ERR_ZLIB, ERR_FORMAT, ERR_TRUNCATED, ERR_IO, ERR_CUDA, ERR_CIGAR, ERR_UNSORTED, ERR_ARG, ERR_NOMEM = \
+    -1, -2, -3, -4, -5, -6, -7, -8, -9, -10
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+u64p = C.POINTER(C.c_uint64)
+
+
+class Error(C.Structure):
+    _fields_ = [("status", C.c_int32), ("zlib_errnum", C.c_int32), ("file_offset", C.c_uint64),
+                ("message", C.c_char * 256)]
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("blocks_per_batch", C.c_int32), ("verify_crc", C.c_int32),
+                ("want_offsets", C.c_int32), ("pin_input", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class RecordBatch(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("first_index", C.c_uint64), ("data", u8p), ("data_len", C.c_uint64),
+                ("rec_off", u64p), ("block_size", i32p), ("ref_id", i32p), ("pos", i32p), ("end_pos", i32p),
+                ("bin_mq_nl", u32p), ("flag_nc", u32p), ("l_seq", i32p), ("cigar_off", u64p), ("cigar", u32p),
+                ("start_voffset", u64p), ("end_voffset", u64p)]
+
+
+class PileupParams(C.Structure):
+    _fields_ = [("single_ref", C.c_int32), ("skip_zero_coverage", C.c_int32), ("use_md_tag", C.c_int32),
+                ("want_query_offset", C.c_int32), ("start_from", C.c_uint64), ("end_at", C.c_uint64),
+                ("counts_only", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class ColumnBatch(C.Structure):
+    _fields_ = [("n_columns", C.c_uint64), ("n_entries", C.c_uint64), ("ref_id", C.c_int32),
+                ("last_of_pileup", C.c_int32), ("position", u64p), ("col_off", u64p), ("n_starting_here", u32p),
+                ("read_idx", u32p), ("base", u8p), ("qual", u8p), ("query_offset", u32p), ("counts", u32p)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libbiod_b200.so.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with biod_b200/csrc/build.sh — biod_b200 has no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.biodb_version.restype = C.c_char_p
+    L.biodb_default_options.argtypes = [C.POINTER(Options)]
+    L.biodb_open.restype = C.c_int
+    L.biodb_open.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(vp)]
+    L.biodb_open_memory.restype = C.c_int
+    L.biodb_open_memory.argtypes = [vp, C.c_size_t, C.POINTER(Options), C.POINTER(vp)]
+    L.biodb_close.argtypes = [vp]
+    L.biodb_last_error.restype = C.POINTER(Error)
+    L.biodb_last_error.argtypes = [vp]
+    L.biodb_open_error.restype = C.POINTER(Error)
+    L.biodb_header_text.restype = C.c_int
+    L.biodb_header_text.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t)]
+    L.biodb_n_refs.restype = C.c_int32
+    L.biodb_n_refs.argtypes = [vp]
+    L.biodb_ref_info.restype = C.c_int
+    L.biodb_ref_info.argtypes = [vp, C.c_int32, C.POINTER(C.c_char_p), i32p, i32p]
+    L.biodb_reads_start_voffset.restype = C.c_uint64
+    L.biodb_reads_start_voffset.argtypes = [vp]
+    L.biodb_file_size.restype = C.c_uint64
+    L.biodb_file_size.argtypes = [vp]
+    L.biodb_reads_begin.restype = C.c_int
+    L.biodb_reads_begin.argtypes = [vp, C.POINTER(vp)]
+    L.biodb_reads_next.restype = C.c_int
+    L.biodb_reads_next.argtypes = [vp, C.POINTER(RecordBatch)]
+    L.biodb_reads_end.argtypes = [vp]
+    L.biodb_reads_progress.restype = C.c_float
+    L.biodb_reads_progress.argtypes = [vp]
+    L.biodb_pileup_begin.restype = C.c_int
+    L.biodb_pileup_begin.argtypes = [vp, C.POINTER(PileupParams), C.POINTER(vp)]
+    L.biodb_pileup_next.restype = C.c_int
+    L.biodb_pileup_next.argtypes = [vp, C.POINTER(ColumnBatch)]
+    L.biodb_pileup_end.argtypes = [vp]
+    L.biodb_pileup_ref_id.restype = C.c_int32
+    L.biodb_pileup_ref_id.argtypes = [vp]
+    L.biodb_pileup_totals.argtypes = [vp, u64p, u64p, u64p]
+    L.biodb_dev_inflate.restype = C.c_int
+    L.biodb_dev_inflate.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp]
+    L.biodb_dev_scan_workspace_bytes.restype = C.c_size_t
+    L.biodb_dev_scan_workspace_bytes.argtypes = [C.c_uint32]
+    L.biodb_dev_scan_records.restype = C.c_int
+    L.biodb_dev_scan_records.argtypes = [vp, C.c_uint64, vp, C.c_uint32, C.c_int32, vp, vp, vp, C.c_size_t, vp]
+    _lib = L
+    return L
+
+
+EXPORTS = [
+    "biodb_version", "biodb_default_options", "biodb_open", "biodb_open_memory", "biodb_close", "biodb_last_error",
+    "biodb_open_error", "biodb_header_text", "biodb_n_refs", "biodb_ref_info", "biodb_reads_start_voffset",
+    "biodb_file_size", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
+    "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
+    "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes",
+]

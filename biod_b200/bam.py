@@ -1,0 +1,354 @@
+"""Host-side mirror of BioD's reader / pileup API over the C ABI (include/biod_b200.h).
+
+The reference is D (bio/std/hts/bam/{reader,read,pileup}.d); no D toolchain exists in this image, so this
+module plays the role the D binding (bindings/d/biod_b200.d) plays for real BioD users: same names,
+argument meaning and error classes, every byte of work done by the CUDA library.
+
+    bam = BamReader("file.bam")                    # bam/reader.d:127-138
+    for read in bam.reads(): ...                   # reader.d:228-231  -> BamRead views (read.d:81)
+    for column in makePileup(bam, start_from=..):  # pileup.d:683-694  -> PileupColumn (pileup.d:236-290)
+    for column in pileupColumns(bam): ...          # pileup.d:509-519
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+
+
+class BgzfException(Exception):
+    """bio/core/bgzf/inputstream.d:41-43"""
+
+
+class ZlibException(Exception):
+    """bio/core/utils/zlib.d:247-274"""
+
+    def __init__(self, msg, errnum):
+        super().__init__(msg)
+        self.errnum = errnum
+
+
+class BamFormatException(Exception):
+    """plain Exception of reader.d:113 / block.d:150"""
+
+
+class ReadException(Exception):
+    """contrib/undead/stream.d ReadException raised by readExact (readrange.d:169)"""
+
+
+class PileupException(Exception):
+    pass
+
+
+class CudaUnavailable(RuntimeError):
+    pass
+
+
+def _raise(err):
+    st, msg = err.status, err.message.decode("latin-1")
+    if st == capi.ERR_BGZF:
+        raise BgzfException(msg)
+    if st == capi.ERR_ZLIB:
+        raise ZlibException(msg, err.zlib_errnum)
+    if st == capi.ERR_FORMAT:
+        raise BamFormatException(msg)
+    if st == capi.ERR_TRUNCATED:
+        raise ReadException(msg)
+    if st == capi.ERR_CUDA:
+        raise CudaUnavailable(msg)
+    if st in (capi.ERR_CIGAR, capi.ERR_UNSORTED):
+        raise PileupException(msg)
+    raise RuntimeError(f"biod_b200 status {st}: {msg}")
+
+
+def _np(ptr, n, dtype):
+    n = int(n)
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    nbytes = n * np.dtype(dtype).itemsize
+    addr = C.addressof(ptr.contents)
+    return np.frombuffer((C.c_uint8 * nbytes).from_address(addr), dtype=dtype)
+
+
+CIGAR_CHARS = "MIDNSHP=X???????"          # cigar.d:109-111
+BASE_CHARS = np.frombuffer(b"=ACMGRSVTWYHKDBN", dtype=np.uint8)   # bio/core/base.d:85
+
+
+class ReferenceSequenceInfo:
+    """bam/referenceinfo.d:34-62"""
+
+    def __init__(self, name, length):
+        self.name, self.length = name, length
+
+
+class RecordBatch:
+    """One batch of decoded records: SoA tables (numpy views of library-owned pinned memory, valid until the
+    next batch is fetched) plus the raw uncompressed slice the BamRead views point into."""
+
+    FIELDS = {"rec_off": np.uint64, "block_size": np.int32, "ref_id": np.int32, "pos": np.int32, "end_pos": np.int32,
+              "bin_mq_nl": np.uint32, "flag_nc": np.uint32, "l_seq": np.int32}
+
+    def __init__(self, b, copy):
+        n = int(b.n)
+        self.n = n
+        self.first_index = int(b.first_index)
+        g = (lambda a: a.copy()) if copy else (lambda a: a)
+        self.data = g(_np(b.data, b.data_len, np.uint8))
+        for f, dt in self.FIELDS.items():
+            setattr(self, f, g(_np(getattr(b, f), n, dt)))
+        self.cigar_off = g(_np(b.cigar_off, n + 1, np.uint64))
+        self.cigar = g(_np(b.cigar, int(self.cigar_off[n]) if n else 0, np.uint32))
+        self.start_voffset = g(_np(b.start_voffset, n, np.uint64)) if b.start_voffset else None
+        self.end_voffset = g(_np(b.end_voffset, n, np.uint64)) if b.end_voffset else None
+
+    # derived columns (read.d:952-968)
+    @property
+    def flag(self):
+        return (self.flag_nc >> 16).astype(np.uint16)
+
+    @property
+    def n_cigar(self):
+        return (self.flag_nc & 0xFFFF).astype(np.uint16)
+
+    @property
+    def mapq(self):
+        return ((self.bin_mq_nl >> 8) & 0xFF).astype(np.uint8)
+
+    @property
+    def l_read_name(self):
+        return (self.bin_mq_nl & 0xFF).astype(np.uint8)
+
+    @property
+    def bin(self):
+        return (self.bin_mq_nl >> 16).astype(np.uint16)
+
+    def read(self, i):
+        return BamRead(self, i)
+
+
+class BamRead:
+    """Zero-copy view over one raw BAM record (bam/read.d:81-1031, layout :907-1003)."""
+
+    __slots__ = ("_b", "_i", "raw")
+
+    def __init__(self, batch, i):
+        self._b, self._i = batch, i
+        o = int(batch.rec_off[i]) + 4
+        self.raw = batch.data[o:o + int(batch.block_size[i])]
+
+    ref_id = property(lambda s: int(s._b.ref_id[s._i]))
+    position = property(lambda s: int(s._b.pos[s._i]))
+    end_position = property(lambda s: int(s._b.end_pos[s._i]))
+    flag = property(lambda s: int(s._b.flag_nc[s._i]) >> 16)
+    mapping_quality = property(lambda s: (int(s._b.bin_mq_nl[s._i]) >> 8) & 0xFF)
+    sequence_length = property(lambda s: int(s._b.l_seq[s._i]))
+    index = property(lambda s: s._b.first_index + s._i)
+    is_unmapped = property(lambda s: bool(s.flag & 4))
+    is_reverse_strand = property(lambda s: bool(s.flag & 16))
+
+    def basesCovered(self):
+        return 0 if self.is_unmapped else self.end_position - self.position
+
+    @property
+    def name(self):
+        ln = int(self._b.bin_mq_nl[self._i]) & 0xFF
+        return self.raw[32:32 + ln - 1].tobytes().decode("latin-1")
+
+    @property
+    def cigar(self):
+        a, b = int(self._b.cigar_off[self._i]), int(self._b.cigar_off[self._i + 1])
+        return [(int(x) >> 4, CIGAR_CHARS[int(x) & 15]) for x in self._b.cigar[a:b]]
+
+    def cigarString(self):
+        c = self.cigar
+        return "".join(f"{l}{o}" for l, o in c) if c else "*"
+
+    def _seq_off(self):
+        return 32 + (int(self._b.bin_mq_nl[self._i]) & 0xFF) + 4 * (int(self._b.flag_nc[self._i]) & 0xFFFF)
+
+    @property
+    def sequence(self):
+        n, o = self.sequence_length, self._seq_off()
+        packed = self.raw[o:o + (n + 1) // 2]
+        codes = np.empty(2 * len(packed), dtype=np.uint8)
+        codes[0::2] = packed >> 4
+        codes[1::2] = packed & 15
+        return BASE_CHARS[codes[:n]].tobytes().decode()
+
+    @property
+    def base_qualities(self):
+        n = self.sequence_length
+        o = self._seq_off() + (n + 1) // 2
+        return self.raw[o:o + n]
+
+    @property
+    def tags_raw(self):
+        n = self.sequence_length
+        return self.raw[self._seq_off() + (n + 1) // 2 + n:].tobytes()
+
+
+class BamReader:
+    """bam/reader.d:80-598 — the subset on the hot path."""
+
+    def __init__(self, source, blocks_per_batch=0, want_offsets=False, device=-1, task_pool=None):
+        # task_pool is accepted and ignored (reader.d:100-101): the device is the pool
+        self._L = L = capi.lib()
+        o = capi.Options()
+        L.biodb_default_options(C.byref(o))
+        o.device = device
+        if blocks_per_batch:
+            o.blocks_per_batch = blocks_per_batch
+        o.want_offsets = int(want_offsets)
+        h = C.c_void_p()
+        if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+            self._buf = np.frombuffer(source, dtype=np.uint8)
+            self.filename = None
+            st = L.biodb_open_memory(self._buf.ctypes.data, self._buf.size, C.byref(o), C.byref(h))
+        else:
+            self.filename = str(source)
+            st = L.biodb_open(self.filename.encode(), C.byref(o), C.byref(h))
+        if st != capi.OK:
+            _raise(L.biodb_open_error().contents)
+        self._h = h
+        t, n = C.c_char_p(), C.c_size_t()
+        L.biodb_header_text(h, C.byref(t), C.byref(n))
+        self.header_text = C.string_at(t, n.value).decode("latin-1") if n.value else ""
+        self.reference_sequences = []
+        for i in range(L.biodb_n_refs(h)):
+            nm, nl, ln = C.c_char_p(), C.c_int32(), C.c_int32()
+            L.biodb_ref_info(h, i, C.byref(nm), C.byref(nl), C.byref(ln))
+            self.reference_sequences.append(ReferenceSequenceInfo(C.string_at(nm, nl.value).decode("latin-1"), ln.value))
+        self.reads_start_voffset = int(L.biodb_reads_start_voffset(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.biodb_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self):
+        _raise(self._L.biodb_last_error(self._h).contents)
+
+    def hasReference(self, name):
+        return any(r.name == name for r in self.reference_sequences)
+
+    def read_batches(self, copy=False):
+        """Batches of decoded records; every call starts a fresh, independent pass (reader.d:228-231,553-569)."""
+        L = self._L
+        it = C.c_void_p()
+        if L.biodb_reads_begin(self._h, C.byref(it)) != capi.OK:
+            self._err()
+        try:
+            while True:
+                b = capi.RecordBatch()
+                st = L.biodb_reads_next(it, C.byref(b))
+                if st == capi.EOF:
+                    return
+                if st != capi.OK:
+                    self._err()
+                yield RecordBatch(b, copy)
+        finally:
+            L.biodb_reads_end(it)
+
+    def reads(self):
+        for batch in self.read_batches(copy=True):
+            for i in range(batch.n):
+                yield BamRead(batch, i)
+
+    def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
+                       want_query_offset=False, copy=False):
+        L = self._L
+        p = capi.PileupParams()
+        p.single_ref, p.skip_zero_coverage, p.use_md_tag = int(single_ref), int(skip_zero_coverage), int(use_md_tag)
+        p.want_query_offset, p.start_from, p.end_at = int(want_query_offset), start_from, end_at
+        pl = C.c_void_p()
+        if L.biodb_pileup_begin(self._h, C.byref(p), C.byref(pl)) != capi.OK:
+            self._err()
+        try:
+            while True:
+                cb = capi.ColumnBatch()
+                st = L.biodb_pileup_next(pl, C.byref(cb))
+                if st == capi.EOF:
+                    return
+                if st != capi.OK:
+                    self._err()
+                yield ColumnBatch(cb, copy)
+        finally:
+            L.biodb_pileup_end(pl)
+
+
+class ColumnBatch:
+    def __init__(self, cb, copy):
+        g = (lambda a: a.copy()) if copy else (lambda a: a)
+        nc, ne = int(cb.n_columns), int(cb.n_entries)
+        self.n_columns, self.n_entries, self.ref_id = nc, ne, int(cb.ref_id)
+        self.position = g(_np(cb.position, nc, np.uint64))
+        self.col_off = g(_np(cb.col_off, nc + 1, np.uint64))
+        self.n_starting_here = g(_np(cb.n_starting_here, nc, np.uint32))
+        self.read_idx = g(_np(cb.read_idx, ne, np.uint32))
+        self.base = g(_np(cb.base, ne, np.uint8))
+        self.qual = g(_np(cb.qual, ne, np.uint8))
+        self.query_offset = g(_np(cb.query_offset, ne, np.uint32)) if cb.query_offset else None
+
+
+class PileupColumn:
+    """bam/pileup.d:236-290"""
+
+    __slots__ = ("_b", "_c")
+
+    def __init__(self, batch, c):
+        self._b, self._c = batch, c
+
+    def _rng(self):
+        return int(self._b.col_off[self._c]), int(self._b.col_off[self._c + 1])
+
+    position = property(lambda s: int(s._b.position[s._c]))
+    ref_id = property(lambda s: s._b.ref_id)
+    reference_base = "N"
+
+    @property
+    def coverage(self):
+        a, b = self._rng()
+        return b - a
+
+    @property
+    def reads(self):
+        a, b = self._rng()
+        return self._b.read_idx[a:b]
+
+    @property
+    def reads_starting_here(self):
+        a, b = self._rng()
+        return self._b.read_idx[b - int(self._b.n_starting_here[self._c]):b]
+
+    @property
+    def bases(self):
+        a, b = self._rng()
+        return self._b.base[a:b].tobytes().decode()
+
+    @property
+    def base_qualities(self):
+        a, b = self._rng()
+        return self._b.qual[a:b]
+
+
+def _columns(reader, single_ref, **kw):
+    for batch in reader.column_batches(single_ref, copy=True, **kw):
+        for c in range(batch.n_columns):
+            yield PileupColumn(batch, c)
+
+
+def makePileup(reader, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True):
+    """bam/pileup.d:683-694"""
+    return _columns(reader, True, use_md_tag=use_md_tag, start_from=start_from, end_at=end_at,
+                    skip_zero_coverage=skip_zero_coverage)
+
+
+def pileupColumns(reader, use_md_tag=False, skip_zero_coverage=True):
+    """bam/pileup.d:509-519"""
+    return _columns(reader, False, use_md_tag=use_md_tag, skip_zero_coverage=skip_zero_coverage)

@@ -1,0 +1,56 @@
+// Internal launch interface between the host runtime and the three kernel families.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace biodb {
+
+// ---- inflate.cu ------------------------------------------------------------------------------
+struct InflateArgs {
+  const uint8_t* comp;          // device: compressed file slice
+  const uint64_t* payload_off;  // [n] byte offset of each block's raw-DEFLATE payload inside comp
+  const uint32_t* cdata_size;   // [n]
+  const uint64_t* out_off;      // [n] byte offset of each block's output inside out
+  const uint32_t* isize;        // [n]
+  uint8_t* out;
+  int32_t* status;              // [n] 0 / Z_DATA_ERROR / Z_BUF_ERROR
+  uint32_t n_blocks;
+};
+cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st);
+size_t inflate_smem_bytes();
+
+// ---- records.cu ------------------------------------------------------------------------------
+struct RecordArrays {
+  uint64_t* rec_off;
+  int32_t* block_size;
+  int32_t* ref_id;
+  int32_t* pos;
+  int32_t* end_pos;
+  uint32_t* bin_mq_nl;
+  uint32_t* flag_nc;
+  int32_t* l_seq;
+  uint64_t* cigar_off;   // [cap+1]
+  uint32_t* cigar;
+  uint64_t capacity;
+  uint64_t cigar_capacity;
+};
+constexpr int SCAN_SLOTS = 2048;   // max records that can start inside one 64 KiB block (65536/37 < 2048)
+struct ScanWorkspace {            // device scratch, sized by scan_workspace_bytes(n_blocks)
+  uint16_t* rel;                  // [n_blocks*SCAN_SLOTS] record starts relative to the block start
+  uint32_t* cnt;                  // [n_blocks] records whose prefix starts in the block
+  uint32_t* ncig;                 // [n_blocks] cigar words of those records
+  uint64_t* out;                  // [n_blocks] where the chain leaves the block (absolute offset in u)
+  uint64_t* in;                   // [n_blocks] where the chain entered (speculated, then true)
+  uint64_t* rec_base;             // [n_blocks+1] exclusive scan of cnt
+  uint64_t* cig_base;             // [n_blocks+1]
+  int32_t* bad;                   // [n_blocks] malformed-record flag met during the walk
+};
+size_t scan_workspace_bytes(uint32_t n_blocks);
+ScanWorkspace carve_scan_workspace(void* base, uint32_t n_blocks);
+// result (device, 4 x u64): n_records, tail offset, n_cigar_words, status
+cudaError_t launch_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t* block_uoff, uint32_t n_blocks,
+                                int final_slice, const RecordArrays& out, uint64_t* result, const ScanWorkspace& ws,
+                                cudaStream_t st);
+
+}  // namespace biodb

@@ -1,0 +1,388 @@
+// Coordinate-sorted pileup builder for sm_100a.
+//
+// Replaces PileupRange.popFront / initNewReference (bio/std/hts/bam/pileup.d:345-424), the
+// PileupRead CIGAR cursor (pileup.d:175-222), current_base / current_base_quality
+// (pileup.d:115-134) and the filters of pileupInstance / pileupColumns (pileup.d:480-519).
+//
+// The reference sweeps positions sequentially, carrying a list of live reads.  Here the same
+// columns are built data-parallel for one reference ("group") of start-sorted reads:
+//   premax[j]   = max end over reads <= j                       (max-scan)
+//   islands     = maximal position runs with coverage > 0       (flag + add-scan); with
+//                 skip_zero_coverage=false the whole group is one island (pileup.d:389-392)
+//   column c    = island column base + (position - island start)
+//   coverage    = +1/-1 difference array over columns            (atomics + add-scan)
+//   col_off     = exclusive scan of coverage
+//   hi[c], lo[c]= window of candidate reads for column c        (atomicMax marks + max-scans)
+//   entries     = one warp per column: ballot the candidates that are live at the position,
+//                 rank = popc of lower lanes -> file order inside the column, exactly the order
+//                 the reference's stable compaction keeps (pileup.d:351-359,381-383).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pileup.h"
+#include "scan.cuh"
+
+namespace biodb {
+
+namespace {
+
+constexpr int32_t DEAD = INT32_MIN;
+
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
+  uintptr_t a = (uintptr_t)p;
+  const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+  uint32_t sh = (uint32_t)(a & 3) * 8;
+  uint32_t lo = __ldg(w);
+  if (sh == 0) return lo;
+  uint32_t hi = __ldg(w + 1);
+  return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ uint32_t consume(uint32_t raw) { return (0x3C1A7u >> ((raw & 0xF) * 2)) & 3; }  // cigar.d:116
+
+__device__ __forceinline__ const uint8_t* record_body(const ReadsView& v, uint32_t j) {
+  return (j < v.n_carry ? v.carry_data : v.u) + v.rec_off[j] + 4;
+}
+
+// ---- group discovery ------------------------------------------------------------------------
+__global__ void find_groups_kernel(ReadsView v, uint32_t* boundaries, uint32_t* n_boundaries, uint32_t cap) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (j >= v.n) return;
+  if (v.ref_id[j] != v.ref_id[j - 1]) {
+    uint32_t k = atomicAdd(n_boundaries, 1u);
+    if (k < cap) boundaries[k] = j;
+  }
+}
+
+// ---- per-read preparation: liveness, CIGAR validity, sortedness ------------------------------
+// info[0] = error status, info[1] = index+1 of the last live read, info[2] = index+1 of first read with
+// end >= start_from (for the prefix-drop rule, pileup.d:482-489)
+__global__ void prep_kernel(ReadsView v, uint32_t g0, uint32_t g1, uint32_t drop_before, int32_t* eend, int32_t* info) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  int32_t pos = v.pos[j], end = v.end_pos[j];
+  bool live = (int32_t)((uint32_t)end - (uint32_t)pos) > 0 && j >= drop_before;   // basesCovered() > 0 (pileup.d:481)
+  if (live) {
+    // PileupRead constructor (pileup.d:175-192): first reference-consuming op that is not N
+    const uint8_t* rec = record_body(v, j);
+    uint32_t lname = v.bin_mq_nl[j] & 0xFF, nc = v.flag_nc[j] & 0xFFFF;
+    const uint8_t* cg = rec + 32 + lname;
+    bool ok = false, skipped_n = false;
+    for (uint32_t k = 0; k < nc; ++k) {
+      uint32_t raw = ld32u(cg + 4 * k);
+      if (consume(raw) & 2) {
+        if ((raw & 0xF) != 3) { ok = true; break; }
+        if (raw >> 4) skipped_n = true;
+      }
+    }
+    if (!ok || skipped_n) atomicCAS(&info[0], 0, -7);          // BIODB_ERR_CIGAR
+    if (pos < 0) atomicCAS(&info[0], 0, -8);
+    if (j > g0) {
+      int32_t pp = v.pos[j - 1], pe = v.end_pos[j - 1];
+      bool plive = (int32_t)((uint32_t)pe - (uint32_t)pp) > 0;
+      if (plive && pp > pos) atomicCAS(&info[0], 0, -8);       // BIODB_ERR_UNSORTED
+    }
+    atomicMax(&info[1], (int32_t)(j + 1));
+  }
+  eend[j] = live ? end : DEAD;
+}
+
+__global__ void first_kept_kernel(ReadsView v, uint32_t g0, uint32_t g1, uint64_t start_from, uint32_t* first) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  int32_t pos = v.pos[j], end = v.end_pos[j];
+  bool live = (int32_t)((uint32_t)end - (uint32_t)pos) > 0;
+  if (live && (uint64_t)(int64_t)end >= start_from) atomicMin(first, j);
+}
+
+// ---- islands -----------------------------------------------------------------------------------
+__global__ void island_flag_kernel(ReadsView v, uint32_t g0, uint32_t g1, const int32_t* eend, const int32_t* pm,
+                                   int skip_zero, uint32_t* flag) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  uint32_t f = 0;
+  if (eend[j] != DEAD) {
+    int32_t prev = (j == g0) ? DEAD : pm[j - 1];
+    if (prev == DEAD || (skip_zero && v.pos[j] >= prev)) f = 1;
+  }
+  flag[j] = f;
+}
+
+__global__ void island_table_kernel(ReadsView v, uint32_t g0, uint32_t g1, const uint32_t* flag, const uint32_t* iid1,
+                                    const int32_t* pm, IslandTable t) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  uint32_t id1 = iid1[j];
+  if (id1 == 0) return;                    // dead reads ahead of the first island
+  if (flag[j]) { t.start[id1 - 1] = v.pos[j]; t.first[id1 - 1] = j; }
+  if (j + 1 == g1 || flag[j + 1]) t.end[id1 - 1] = pm[j];
+}
+
+__global__ void island_cols_kernel(IslandTable t, uint32_t n_islands, int64_t clo, int64_t chi, uint32_t* ncol) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_islands) return;
+  int64_t cs = t.start[i], ce = t.end[i];
+  if (cs < clo) cs = clo;
+  if (ce > chi) ce = chi;
+  int64_t n = ce - cs;
+  if (n < 0) n = 0;
+  t.cs[i] = cs;
+  ncol[i] = (uint32_t)(n > 0x7fffffff ? 0x7fffffff : n);
+}
+
+// ---- per-read scatter into the column arrays ------------------------------------------------------
+__global__ void scatter_kernel(ReadsView v, uint32_t g0, uint32_t g1, const int32_t* eend, const int32_t* pm,
+                               const uint32_t* iid1, IslandTable t, const uint32_t* colbase, const uint32_t* ncol,
+                               ColumnScratch c) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  int32_t e = eend[j];
+  if (e == DEAD) return;
+  uint32_t i = iid1[j] - 1;
+  int64_t cs = t.cs[i];
+  uint32_t nc = ncol[i];
+  if (nc == 0) return;
+  int64_t ce = cs + nc;
+  int64_t pos = v.pos[j];
+  if (pos >= ce || (int64_t)e <= cs) return;           // no column of this batch sees the read
+  uint32_t base = colbase[i];
+  int64_t a = pos < cs ? cs : pos;
+  int64_t b = (int64_t)e < ce ? (int64_t)e : ce;
+  atomicAdd(&c.diff[base + (uint32_t)(a - cs)], 1);
+  atomicAdd(&c.diff[base + (uint32_t)(b - cs)], -1);
+  if (pos >= cs) atomicAdd(&c.nstart[base + (uint32_t)(pos - cs)], 1u);
+  atomicMax(&c.hi[base + (uint32_t)(a - cs)], j + 1);
+  // frontier read: extends the covered prefix, so it is the first live read from max(prev frontier, pos) on
+  int32_t prev = (j == g0) ? DEAD : pm[j - 1];
+  if (prev == DEAD || e > prev) {
+    int64_t f = (prev == DEAD || (int64_t)prev < pos) ? pos : (int64_t)prev;
+    if (f < cs) f = cs;
+    if (f < ce) atomicMax(&c.lo[base + (uint32_t)(f - cs)], j + 1);
+  }
+}
+
+__global__ void colpos_kernel(IslandTable t, const uint32_t* colbase, uint32_t n_islands, uint32_t n_col, uint64_t* col_pos) {
+  uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_col) return;
+  uint32_t lo = 0, hi = n_islands;       // last island with colbase <= c
+  while (hi - lo > 1) {
+    uint32_t m = (lo + hi) >> 1;
+    if (colbase[m] <= c) lo = m; else hi = m;
+  }
+  col_pos[c] = (uint64_t)(t.cs[lo] + (int64_t)(c - colbase[lo]));
+}
+
+// ---- column entries -------------------------------------------------------------------------------
+struct Entry { uint8_t base, qual; uint32_t qoff; bool bad; };
+
+// CIGAR cursor of read `rec` at reference offset k from its position (PileupRead ctor + k x incrementPosition,
+// pileup.d:175-222) and the base/quality there (pileup.d:115-134, read.d:364-383, base.d:85).
+__device__ __forceinline__ Entry cursor_at(const uint8_t* rec, uint32_t lname, uint32_t nc, int32_t lseq, uint32_t k) {
+  const uint8_t* cg = rec + 32 + lname;
+  const uint8_t* seq = cg + 4 * nc;
+  const uint8_t* ql = seq + ((uint32_t)lseq + 1) / 2;
+  Entry en;
+  en.base = '-';
+  en.qual = 255;
+  en.bad = false;
+  uint32_t qoff = 0, i = 0, raw = 0, t = 0;
+  for (; i < nc; ++i) {
+    raw = ld32u(cg + 4 * i);
+    t = consume(raw);
+    if (t & 2) { if ((raw & 0xF) != 3) break; }
+    else if (t & 1) qoff += raw >> 4;
+  }
+  uint32_t r = k;
+  while (i < nc) {
+    uint32_t len = raw >> 4;
+    uint32_t eff = len ? len : 1;          // a zero-length op still holds the cursor for one position (pileup.d:196-203)
+    if (r < eff) {
+      if (t == 3) {
+        qoff += r;
+        if (qoff < (uint32_t)lseq) {
+          uint8_t byte = __ldg(seq + (qoff >> 1));
+          uint32_t code = (qoff & 1) ? (byte & 0xF) : (byte >> 4);
+          en.base = (uint8_t)"=ACMGRSVTWYHKDBN"[code];
+          en.qual = __ldg(ql + qoff);
+        } else {
+          en.bad = true;
+        }
+      }
+      break;
+    }
+    r -= eff;
+    if (t & 1) qoff += eff;
+    for (++i; i < nc; ++i) {
+      raw = ld32u(cg + 4 * i);
+      t = consume(raw);
+      if (t & 2) break;
+      if (t & 1) qoff += raw >> 4;
+    }
+  }
+  en.qoff = qoff;
+  return en;
+}
+
+constexpr int ENT_WARPS = 8;
+constexpr int COLS_PER_WARP = 8;
+
+__global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, const int32_t* __restrict__ eend,
+                                                                 ColumnScratch c, ColumnOutput o, uint32_t n_col,
+                                                                 int32_t* info) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = blockIdx.x * ENT_WARPS + (threadIdx.x >> 5);
+  const uint32_t lt = (1u << lane) - 1;
+  uint32_t c0 = warp * COLS_PER_WARP;
+  for (uint32_t col = c0; col < c0 + COLS_PER_WARP && col < n_col; ++col) {
+    const int64_t p = (int64_t)o.col_pos[col];
+    uint32_t hi = c.hi[col], lo = c.lo[col];
+    uint64_t off = o.col_off[col];
+    if (hi == 0) continue;
+    lo = lo ? lo - 1 : 0;
+    for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
+      const uint32_t j = j0 + lane;
+      bool live = false;
+      int32_t pos = 0;
+      if (j < hi) {
+        int32_t e = eend[j];
+        pos = v.pos[j];
+        live = e != DEAD && (int64_t)pos <= p && (int64_t)e > p;
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        const uint64_t slot = off + __popc(m & lt);
+        const uint8_t* rec = record_body(v, j);
+        Entry en = cursor_at(rec, v.bin_mq_nl[j] & 0xFF, v.flag_nc[j] & 0xFFFF, v.l_seq[j], (uint32_t)(p - pos));
+        if (en.bad) atomicCAS(&info[0], 0, -7);
+        o.read_idx[slot] = j < v.n_carry ? v.carry_gidx[j] : (uint32_t)(v.first_index + (j - v.n_carry));
+        o.base[slot] = en.base;
+        o.qual[slot] = en.qual;
+        if (o.qoff) o.qoff[slot] = en.qoff;
+      }
+      off += __popc(m);
+    }
+  }
+}
+
+// ---- carry to the next batch ------------------------------------------------------------------------
+__global__ void carry_flag_kernel(uint32_t g0, uint32_t g1, const int32_t* eend, int64_t limit, uint32_t* flag) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  int32_t e = eend[j];
+  flag[j - g0] = (e != DEAD && (int64_t)e > limit) ? 1u : 0u;
+}
+
+__global__ void carry_size_kernel(ReadsView v, uint32_t g0, uint32_t g1, const int32_t* block_size, const uint32_t* flag,
+                                  uint64_t* bytes) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  // 4-byte prefix + body, padded to 4 so that unaligned-load helpers never straddle into the next record's page
+  bytes[j - g0] = flag[j - g0] ? (((uint64_t)block_size[j] + 4 + 3) & ~3ull) : 0;
+}
+
+__global__ void carry_copy_kernel(ReadsView v, uint32_t g0, uint32_t g1, const int32_t* block_size, const uint32_t* flag,
+                                  const uint32_t* slot_incl, const uint64_t* byte_excl, CarryOut out) {
+  // one warp per read
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  uint32_t j = g0 + w;
+  if (j >= g1 || !flag[j - g0]) return;
+  uint32_t s = slot_incl[j - g0] - 1;
+  uint64_t dst = byte_excl[j - g0];
+  if (lane == 0) {
+    out.pos[s] = v.pos[j];
+    out.end_pos[s] = v.end_pos[j];
+    out.ref_id[s] = v.ref_id[j];
+    out.rec_off[s] = dst;
+    out.bin_mq_nl[s] = v.bin_mq_nl[j];
+    out.flag_nc[s] = v.flag_nc[j];
+    out.l_seq[s] = v.l_seq[j];
+    out.block_size[s] = block_size[j];
+    out.gidx[s] = j < v.n_carry ? v.carry_gidx[j] : (uint32_t)(v.first_index + (j - v.n_carry));
+  }
+  const uint8_t* src = (j < v.n_carry ? v.carry_data : v.u) + v.rec_off[j];
+  uint32_t n = (uint32_t)block_size[j] + 4;
+  for (uint32_t i = lane; i < n; i += 32) out.data[dst + i] = src[i];
+}
+
+template <typename K, typename... A>
+inline void launch1d(K k, uint32_t n, cudaStream_t st, A... a) {
+  if (n == 0) return;
+  k<<<(n + 255) / 256, 256, 0, st>>>(a...);
+}
+
+}  // namespace
+
+void pileup_find_groups(const ReadsView& v, uint32_t* boundaries, uint32_t* n_boundaries, uint32_t cap, cudaStream_t st) {
+  cudaMemsetAsync(n_boundaries, 0, sizeof(uint32_t), st);
+  if (v.n > 1) launch1d(find_groups_kernel, v.n - 1, st, v, boundaries, n_boundaries, cap);
+}
+
+void pileup_first_kept(const ReadsView& v, uint32_t g0, uint32_t g1, uint64_t start_from, uint32_t* first, cudaStream_t st) {
+  cudaMemsetAsync(first, 0xff, sizeof(uint32_t), st);
+  launch1d(first_kept_kernel, g1 - g0, st, v, g0, g1, start_from, first);
+}
+
+// Phase 1: liveness, premax, islands, island column counts.  After it (sync) the host reads
+// n_islands = tmp32[tiles(n)] (flag scan total) and n_col = tmp32b total.
+void pileup_phase1(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t drop_before, int skip_zero, int64_t clo,
+                   int64_t chi, GroupScratch& s, cudaStream_t st) {
+  const uint32_t n = g1 - g0;
+  launch1d(prep_kernel, n, st, v, g0, g1, drop_before, s.eend, s.info);
+  device_scan<true>(s.eend + g0, s.pm + g0, n, s.tmp_i32, OpMax(), DEAD, st);
+  launch1d(island_flag_kernel, n, st, v, g0, g1, s.eend, s.pm, skip_zero, s.flag);
+  device_scan<true>(s.flag + g0, s.iid1 + g0, n, s.tmp_u32, OpAdd(), 0u, st);
+  launch1d(island_table_kernel, n, st, v, g0, g1, s.flag, s.iid1, s.pm, s.islands);
+  // n_islands is only known on the device: run the island kernels over the upper bound n and let
+  // entries beyond n_islands be harmless (ncol for them is computed from stale table rows, so zero them first)
+  s.clo = clo;
+  s.chi = chi;
+}
+
+void pileup_island_cols(uint32_t n_islands, GroupScratch& s, cudaStream_t st) {
+  launch1d(island_cols_kernel, n_islands, st, s.islands, n_islands, s.clo, s.chi, s.ncol);
+  device_scan<false>(s.ncol, s.colbase, n_islands, s.tmp_u32b, OpAdd(), 0u, st);
+}
+
+// Phase 2: columns.  cols.* must have room for n_col+1 and be zeroed (diff, nstart, hi, lo).
+void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_islands, uint32_t n_col, GroupScratch& s,
+                   ColumnScratch& c, ColumnOutput& o, cudaStream_t st) {
+  const uint32_t n = g1 - g0;
+  cudaMemsetAsync(c.diff, 0, (size_t)(n_col + 1) * 4, st);
+  cudaMemsetAsync(c.nstart, 0, (size_t)(n_col + 1) * 4, st);
+  cudaMemsetAsync(c.hi, 0, (size_t)(n_col + 1) * 4, st);
+  cudaMemsetAsync(c.lo, 0, (size_t)(n_col + 1) * 4, st);
+  launch1d(scatter_kernel, n, st, v, g0, g1, s.eend, s.pm, s.iid1, s.islands, s.colbase, s.ncol, c);
+  device_scan<true>(c.diff, c.diff, (uint64_t)n_col + 1, s.tmp_i32, OpAdd(), 0, st);            // coverage
+  device_scan<false>(c.diff, o.col_off, (uint64_t)n_col + 1, s.tmp_u64, OpAdd(), (uint64_t)0, st);  // col_off
+  device_scan<true>(c.hi, c.hi, (uint64_t)n_col, s.tmp_u32, OpMax(), 0u, st);
+  device_scan<true>(c.lo, c.lo, (uint64_t)n_col, s.tmp_u32b, OpMax(), 0u, st);
+  launch1d(colpos_kernel, n_col, st, s.islands, s.colbase, n_islands, n_col, o.col_pos);
+}
+
+void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st) {
+  if (n_col == 0) return;
+  uint32_t warps = (n_col + COLS_PER_WARP - 1) / COLS_PER_WARP;
+  uint32_t grid = (warps + ENT_WARPS - 1) / ENT_WARPS;
+  entries_kernel<<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, c, o, n_col, s.info);
+}
+
+// Carry: live reads of [g0,g1) with end > limit, compacted in order into `out`.
+// After the call (sync) the host reads the count = tmp_u32 total and bytes = tmp_u64 total.
+void pileup_carry(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, int64_t limit, GroupScratch& s,
+                  CarryOut& out, cudaStream_t st) {
+  const uint32_t n = g1 - g0;
+  if (n == 0) return;
+  launch1d(carry_flag_kernel, n, st, g0, g1, s.eend, limit, s.cflag);
+  launch1d(carry_size_kernel, n, st, v, g0, g1, block_size, s.cflag, s.cbytes);
+  device_scan<true>(s.cflag, s.cslot, n, s.tmp_u32, OpAdd(), 0u, st);
+  device_scan<false>(s.cbytes, s.cbytes, n, s.tmp_u64, OpAdd(), (uint64_t)0, st);
+}
+
+void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, GroupScratch& s,
+                       CarryOut& out, cudaStream_t st) {
+  const uint32_t n = g1 - g0;
+  if (n == 0) return;
+  uint64_t threads = (uint64_t)n * 32;
+  carry_copy_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(v, g0, g1, block_size, s.cflag, s.cslot, s.cbytes, out);
+}
+
+}  // namespace biodb

@@ -1,0 +1,95 @@
+// Internal interface of the pileup builder (pileup.cu) used by the host runtime.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace biodb {
+
+// The work table: carried-over reads of earlier batches (indices [0,n_carry)) followed by the
+// records of the current batch, all in file order.  rec_off of a carried read is relative to
+// carry_data, of a batch read relative to u.
+struct ReadsView {
+  const int32_t* pos;
+  const int32_t* end_pos;
+  const int32_t* ref_id;
+  const uint64_t* rec_off;
+  const uint32_t* bin_mq_nl;
+  const uint32_t* flag_nc;
+  const int32_t* l_seq;
+  const uint32_t* carry_gidx;   // [n_carry] file-order index of carried reads
+  const uint8_t* carry_data;
+  const uint8_t* u;
+  uint32_t n_carry;
+  uint32_t n;                   // carried + batch reads
+  uint64_t first_index;         // file-order index of batch read 0
+};
+
+struct IslandTable {
+  int32_t* start;   // position of the island's first read
+  int32_t* end;     // max end over the island
+  uint32_t* first;  // index of its first read
+  int64_t* cs;      // first emitted position after clipping
+};
+
+struct GroupScratch {            // sized by read capacity
+  int32_t* eend;                 // end_pos of live reads, INT32_MIN for filtered ones
+  int32_t* pm;                   // running max of eend
+  uint32_t* flag;                // island-start flags
+  uint32_t* iid1;                // 1-based island id
+  IslandTable islands;
+  uint32_t* ncol;
+  uint32_t* colbase;
+  uint32_t* cflag;
+  uint32_t* cslot;
+  uint64_t* cbytes;
+  int32_t* tmp_i32;              // scan tile aggregates (each sized for max(reads, columns+1))
+  uint32_t* tmp_u32;
+  uint32_t* tmp_u32b;
+  uint64_t* tmp_u64;
+  int32_t* info;                 // [4]: status, last live read + 1
+  int64_t clo, chi;
+};
+
+struct ColumnScratch {           // sized by column capacity + 1
+  int32_t* diff;                 // difference array, then coverage
+  uint32_t* nstart;
+  uint32_t* hi;
+  uint32_t* lo;
+};
+
+struct ColumnOutput {
+  uint64_t* col_pos;             // [n_col]
+  uint64_t* col_off;             // [n_col+1]
+  uint32_t* read_idx;            // [n_entries]
+  uint8_t* base;
+  uint8_t* qual;
+  uint32_t* qoff;                // or nullptr
+};
+
+struct CarryOut {
+  int32_t* pos;
+  int32_t* end_pos;
+  int32_t* ref_id;
+  uint64_t* rec_off;
+  uint32_t* bin_mq_nl;
+  uint32_t* flag_nc;
+  int32_t* l_seq;
+  int32_t* block_size;
+  uint32_t* gidx;
+  uint8_t* data;
+};
+
+void pileup_find_groups(const ReadsView& v, uint32_t* boundaries, uint32_t* n_boundaries, uint32_t cap, cudaStream_t st);
+void pileup_first_kept(const ReadsView& v, uint32_t g0, uint32_t g1, uint64_t start_from, uint32_t* first, cudaStream_t st);
+void pileup_phase1(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t drop_before, int skip_zero, int64_t clo,
+                   int64_t chi, GroupScratch& s, cudaStream_t st);
+void pileup_island_cols(uint32_t n_islands, GroupScratch& s, cudaStream_t st);
+void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_islands, uint32_t n_col, GroupScratch& s,
+                   ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
+void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
+void pileup_carry(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, int64_t limit, GroupScratch& s,
+                  CarryOut& out, cudaStream_t st);
+void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, GroupScratch& s,
+                       CarryOut& out, cudaStream_t st);
+
+}  // namespace biodb

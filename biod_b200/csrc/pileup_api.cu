@@ -1,0 +1,430 @@
+// Host side of the pileup: walks the file batch by batch (Pass), splits each batch into reference
+// groups, runs the pileup kernels per group and carries reads that reach past the batch forward —
+// the halo scheme of PileupChunkRange (bio/std/hts/bam/pileup.d:859-987): a batch emits columns up to
+// (not including) the position of its last read, later columns wait for the next batch.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "runtime.h"
+#include "scan.cuh"
+
+using namespace biodb;
+
+namespace {
+
+struct CarryBufs {
+  DevBuf a[9], data;     // pos,end,ref,rec_off,bin_mq_nl,flag_nc,l_seq,block_size,gidx
+  uint32_t n = 0;
+  uint64_t bytes = 0;
+  CarryOut out() const {
+    CarryOut o;
+    o.pos = a[0].as<int32_t>(); o.end_pos = a[1].as<int32_t>(); o.ref_id = a[2].as<int32_t>();
+    o.rec_off = a[3].as<uint64_t>(); o.bin_mq_nl = a[4].as<uint32_t>(); o.flag_nc = a[5].as<uint32_t>();
+    o.l_seq = a[6].as<int32_t>(); o.block_size = a[7].as<int32_t>(); o.gidx = a[8].as<uint32_t>();
+    o.data = data.as<uint8_t>();
+    return o;
+  }
+};
+
+}  // namespace
+
+struct biodb_pileup {
+  biodb_reader* r = nullptr;
+  biodb_pileup_params prm{};
+  Pass pass;
+  CarryBufs carry[2];
+  int cur = 0;
+  // continuation of a reference group across batches
+  bool cont = false;          // the last batch ended inside a group that had live reads
+  int32_t cont_ref = 0;
+  int64_t cont_pos = 0;       // columns below this position are already emitted
+  // single_ref state
+  bool started = false, done = false;
+  int32_t target_ref = -1;
+  // current batch
+  bool have_batch = false;
+  std::vector<uint32_t> bounds;   // group boundaries of the current view, [0, ..., n]
+  size_t gi = 0;
+  uint32_t n_view = 0, n_carry_view = 0;
+  uint64_t first_index = 0;
+  // scratch
+  DevBuf g[12], tmp[4], info, bnd, cs[4], out[6];
+  size_t read_cap = 0, col_cap = 0, ent_cap = 0;
+  PinBuf h_small, h_bnd, h_out[6];
+  uint64_t tot_cols = 0, tot_entries = 0;
+
+  biodb_status fail(int status, const std::string& msg) { return pass.fail(status, 0, 0, msg); }
+};
+
+#define PL_TRY(expr)                                                                            \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) return pl->fail(BIODB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+static ReadsView make_view(biodb_pileup* pl) {
+  Pass& p = pl->pass;
+  ReadsView v;
+  RecordArrays a = p.arrays(0);
+  v.pos = a.pos; v.end_pos = a.end_pos; v.ref_id = a.ref_id; v.rec_off = a.rec_off;
+  v.bin_mq_nl = a.bin_mq_nl; v.flag_nc = a.flag_nc; v.l_seq = a.l_seq;
+  v.carry_gidx = pl->carry[pl->cur].a[8].as<uint32_t>();
+  v.carry_data = pl->carry[pl->cur].data.as<uint8_t>();
+  v.u = p.d_u.as<uint8_t>();
+  v.n_carry = pl->n_carry_view;
+  v.n = pl->n_view;
+  v.first_index = pl->first_index;
+  return v;
+}
+
+static biodb_status ensure_read_scratch(biodb_pileup* pl, size_t n) {
+  if (n + 8 <= pl->read_cap) return BIODB_OK;
+  size_t cap = n + n / 4 + 1024;
+  cudaStream_t st = pl->pass.st;
+  static const size_t esz[12] = {4, 4, 4, 4, 4, 4, 4, 8, 4, 4, 4, 8};   // eend pm flag iid1 i.start i.end i.first i.cs ncol colbase cflag/cslot(2x) cbytes
+  for (int k = 0; k < 12; ++k) {
+    size_t b = cap * esz[k] * (k == 10 ? 2 : 1);
+    PL_TRY(pl->g[k].ensure(b, st));
+  }
+  pl->read_cap = cap;
+  return BIODB_OK;
+}
+
+static biodb_status ensure_tmp(biodb_pileup* pl, size_t elems) {
+  cudaStream_t st = pl->pass.st;
+  size_t t = scan_temp_elems(elems) + 8;
+  PL_TRY(pl->tmp[0].ensure(t * 4, st));
+  PL_TRY(pl->tmp[1].ensure(t * 4, st));
+  PL_TRY(pl->tmp[2].ensure(t * 4, st));
+  PL_TRY(pl->tmp[3].ensure(t * 8, st));
+  return BIODB_OK;
+}
+
+static GroupScratch scratch(biodb_pileup* pl) {
+  GroupScratch s;
+  s.eend = pl->g[0].as<int32_t>(); s.pm = pl->g[1].as<int32_t>(); s.flag = pl->g[2].as<uint32_t>();
+  s.iid1 = pl->g[3].as<uint32_t>();
+  s.islands.start = pl->g[4].as<int32_t>(); s.islands.end = pl->g[5].as<int32_t>();
+  s.islands.first = pl->g[6].as<uint32_t>(); s.islands.cs = pl->g[7].as<int64_t>();
+  s.ncol = pl->g[8].as<uint32_t>(); s.colbase = pl->g[9].as<uint32_t>();
+  s.cflag = pl->g[10].as<uint32_t>(); s.cslot = pl->g[10].as<uint32_t>() + pl->read_cap;
+  s.cbytes = pl->g[11].as<uint64_t>();
+  s.tmp_i32 = pl->tmp[0].as<int32_t>(); s.tmp_u32 = pl->tmp[1].as<uint32_t>(); s.tmp_u32b = pl->tmp[2].as<uint32_t>();
+  s.tmp_u64 = pl->tmp[3].as<uint64_t>();
+  s.info = pl->info.as<int32_t>();
+  s.clo = s.chi = 0;
+  return s;
+}
+
+// Fetch the next batch of records and lay the carried reads in front of it.
+static biodb_status load_batch(biodb_pileup* pl) {
+  Pass& p = pl->pass;
+  CarryBufs& c = pl->carry[pl->cur];
+  const uint64_t first = p.n_records_total;
+  biodb_status s = p.next((uint32_t)p.r->opts.blocks_per_batch, c.n);
+  if (s != BIODB_OK) return s;
+  pl->first_index = first;
+  pl->n_carry_view = c.n;
+  pl->n_view = c.n + (uint32_t)p.n;
+  cudaStream_t st = p.st;
+  if (c.n) {
+    RecordArrays a = p.arrays(0);
+    CarryOut o = c.out();
+    const size_t n = c.n;
+    PL_TRY(cudaMemcpyAsync(a.pos, o.pos, n * 4, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(cudaMemcpyAsync(a.end_pos, o.end_pos, n * 4, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(cudaMemcpyAsync(a.ref_id, o.ref_id, n * 4, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(cudaMemcpyAsync(a.rec_off, o.rec_off, n * 8, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(cudaMemcpyAsync(a.bin_mq_nl, o.bin_mq_nl, n * 4, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(cudaMemcpyAsync(a.flag_nc, o.flag_nc, n * 4, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(cudaMemcpyAsync(a.l_seq, o.l_seq, n * 4, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(cudaMemcpyAsync(a.block_size, o.block_size, n * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  biodb_status es = ensure_read_scratch(pl, pl->n_view);
+  if (es != BIODB_OK) return es;
+  es = ensure_tmp(pl, pl->n_view + 1);
+  if (es != BIODB_OK) return es;
+  // reference groups
+  pl->bounds.clear();
+  pl->bounds.push_back(0);
+  if (pl->n_view) {
+    const uint32_t cap = pl->n_view;
+    PL_TRY(pl->bnd.ensure((size_t)(cap + 2) * 4, st));
+    PL_TRY(pl->h_bnd.ensure((size_t)(cap + 2) * 4));
+    ReadsView v = make_view(pl);
+    uint32_t* d_b = pl->bnd.as<uint32_t>();
+    pileup_find_groups(v, d_b + 1, d_b, cap, st);
+    PL_TRY(cudaMemcpyAsync(pl->h_bnd.p, d_b, 4, cudaMemcpyDeviceToHost, st));
+    PL_TRY(cudaStreamSynchronize(st));
+    uint32_t nbnd = pl->h_bnd.as<uint32_t>()[0];
+    if (nbnd) {
+      PL_TRY(cudaMemcpyAsync(pl->h_bnd.as<uint32_t>() + 1, d_b + 1, (size_t)nbnd * 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaStreamSynchronize(st));
+      uint32_t* hb = pl->h_bnd.as<uint32_t>() + 1;
+      std::sort(hb, hb + nbnd);
+      for (uint32_t k = 0; k < nbnd; ++k) pl->bounds.push_back(hb[k]);
+    }
+    pl->bounds.push_back(pl->n_view);
+  }
+  pl->gi = 0;
+  pl->have_batch = true;
+  return BIODB_OK;
+}
+
+extern "C" {
+
+biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out) {
+  if (!r || !out) return BIODB_ERR_ARG;
+  biodb_pileup* pl = new biodb_pileup;
+  pl->r = r;
+  if (p) pl->prm = *p;
+  else { memset(&pl->prm, 0, sizeof pl->prm); pl->prm.skip_zero_coverage = 1; pl->prm.single_ref = 1; pl->prm.end_at = ~0ull; }
+  if (!pl->prm.single_ref) { pl->prm.start_from = 0; pl->prm.end_at = ~0ull; }
+  biodb_status s = pl->pass.init(r, r->reads_start_coffset, r->reads_start_uoffset);
+  if (s == BIODB_OK && (pl->info.ensure(64) != cudaSuccess || pl->h_small.ensure(256) != cudaSuccess)) s = BIODB_ERR_CUDA;
+  if (s != BIODB_OK) { delete pl; return s; }
+  *out = pl;
+  return BIODB_OK;
+}
+
+void biodb_pileup_end(biodb_pileup* pl) { delete pl; }
+int32_t biodb_pileup_ref_id(const biodb_pileup* pl) { return pl ? pl->target_ref : -1; }
+void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* n_columns, uint64_t* n_entries) {
+  if (!pl) return;
+  if (n_records) *n_records = pl->pass.n_records_total;
+  if (n_columns) *n_columns = pl->tot_cols;
+  if (n_entries) *n_entries = pl->tot_entries;
+}
+
+biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
+  if (!pl || !cols) return BIODB_ERR_ARG;
+  memset(cols, 0, sizeof *cols);
+  Pass& p = pl->pass;
+  cudaStream_t st = p.st;
+  const bool single = pl->prm.single_ref != 0;
+  const int skip_zero = pl->prm.skip_zero_coverage != 0;
+  while (true) {
+    if (pl->done) return BIODB_EOF;
+    if (!pl->have_batch || pl->gi + 1 >= pl->bounds.size()) {
+      pl->have_batch = false;
+      if (p.finished && (pl->carry[pl->cur].n == 0 || p.pending.status != 0)) {
+        biodb_status s = p.next(1, 0);          // raises the pending error, or EOF
+        if (s == BIODB_EOF) pl->done = true;
+        return s;
+      }
+      biodb_status s = load_batch(pl);
+      if (s == BIODB_EOF) { pl->done = true; return s; }
+      if (s != BIODB_OK) return s;
+      if (pl->n_view == 0) continue;
+    }
+    // ---- one reference group of the current batch -------------------------------------------------
+    const size_t gi = pl->gi++;
+    const uint32_t g0 = pl->bounds[gi], g1 = pl->bounds[gi + 1];
+    const bool last_group = gi + 2 == pl->bounds.size();
+    // later batches may add reads to this group; with an error pending, stop where the reference's
+    // sequential engine would have thrown (it needs the next read before it can finish the column)
+    const bool trailing = last_group && (!p.final_slice || p.pending.status != 0);
+    ReadsView v = make_view(pl);
+    GroupScratch s = scratch(pl);
+    int32_t* h = pl->h_small.as<int32_t>();
+    // reference id of the group
+    PL_TRY(cudaMemcpyAsync(h, v.ref_id + g0, 4, cudaMemcpyDeviceToHost, st));
+    PL_TRY(cudaMemsetAsync(s.info, 0, 16, st));
+    PL_TRY(cudaStreamSynchronize(st));
+    const int32_t ref = h[0];
+    const bool continues = pl->cont && gi == 0 && pl->cont_ref == ref;
+    if (!continues && gi == 0) pl->cont = false;
+    uint32_t drop_before = g0;
+    if (single) {
+      if (!pl->started) {
+        // pileupInstance (pileup.d:482-493): drop leading reads that end before start_from; the first
+        // read kept fixes the reference of the whole pileup
+        uint32_t* d_first = (uint32_t*)(s.info + 2);
+        pileup_first_kept(v, g0, g1, pl->prm.start_from, d_first, st);
+        PL_TRY(cudaMemcpyAsync(h, d_first, 4, cudaMemcpyDeviceToHost, st));
+        PL_TRY(cudaStreamSynchronize(st));
+        uint32_t first = (uint32_t)h[0];
+        if (first == 0xffffffffu) {
+          // nothing kept in this group: carried reads (none can exist yet) and the group are skipped
+          if (last_group) { pl->carry[pl->cur].n = 0; }
+          continue;
+        }
+        pl->started = true;
+        pl->target_ref = ref;
+        drop_before = first;
+      } else if (ref != pl->target_ref) {
+        pl->done = true;                         // takeUntil!"a.ref_id != b" (pileup.d:494)
+        return BIODB_EOF;
+      }
+    }
+    int64_t clo = INT64_MIN, chi = INT64_MAX;
+    if (continues) clo = pl->cont_pos;
+    if (single) {
+      if (pl->prm.start_from > (uint64_t)INT64_MAX) { pl->done = true; return BIODB_EOF; }
+      clo = std::max<int64_t>(clo, (int64_t)pl->prm.start_from);
+      if (pl->prm.end_at <= (uint64_t)INT64_MAX) chi = (int64_t)pl->prm.end_at;
+    }
+    // ---- phase 1: liveness, running max, islands ----------------------------------------------------
+    pileup_phase1(v, g0, g1, drop_before, skip_zero, clo, chi, s, st);
+    const uint32_t ng = g1 - g0;
+    const uint32_t t_reads = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
+    PL_TRY(cudaMemcpyAsync(h, s.tmp_u32 + t_reads, 4, cudaMemcpyDeviceToHost, st));           // n_islands
+    PL_TRY(cudaMemcpyAsync(h + 1, s.info, 8, cudaMemcpyDeviceToHost, st));                    // status, last live + 1
+    PL_TRY(cudaStreamSynchronize(st));
+    const uint32_t n_islands = (uint32_t)h[0];
+    const int32_t st1 = h[1];
+    const uint32_t last_live1 = (uint32_t)h[2];
+    if (st1 != 0)
+      return pl->fail(st1, st1 == BIODB_ERR_CIGAR ? "Invalid read - CIGAR has no usable reference-consuming operation"
+                                                  : "reads are not sorted by coordinate within the reference");
+    CarryBufs& ccur = pl->carry[pl->cur];
+    if (last_live1 == 0 || n_islands == 0) {
+      // no live reads here.  A trailing group keeps any earlier continuation alive only if it is the same ref.
+      if (last_group) ccur.n = 0;
+      if (!continues) pl->cont = false;
+      if (trailing && continues) pl->cont = true;
+      continue;
+    }
+    int64_t E = 0;
+    if (trailing) {
+      PL_TRY(cudaMemcpyAsync(h, v.pos + (last_live1 - 1), 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaStreamSynchronize(st));
+      E = h[0];
+      chi = std::min(chi, E);
+    }
+    s.clo = clo;
+    s.chi = chi;
+    // with skip_zero_coverage=false the column run of a continued group restarts exactly where the
+    // previous batch stopped, even if no read covers that position (pileup.d:389-392)
+    const bool force_lo = !skip_zero && continues;
+    if (force_lo) {
+      // island 0 of the group is the whole group: move its start down to the continuation point
+      int32_t lo32 = (int32_t)std::max<int64_t>(clo, INT32_MIN);
+      PL_TRY(cudaMemcpyAsync(h, s.islands.start, 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaStreamSynchronize(st));
+      if (h[0] > lo32) {
+        h[0] = lo32;
+        PL_TRY(cudaMemcpyAsync(s.islands.start, h, 4, cudaMemcpyHostToDevice, st));
+      }
+    }
+    pileup_island_cols(n_islands, s, st);
+    const uint32_t t_isl = (uint32_t)((n_islands + SCAN_TILE - 1) / SCAN_TILE);
+    PL_TRY(cudaMemcpyAsync(h, s.tmp_u32b + t_isl, 4, cudaMemcpyDeviceToHost, st));
+    PL_TRY(cudaStreamSynchronize(st));
+    const uint32_t n_col = (uint32_t)h[0];
+    if (n_col > 0x7ff00000u) return pl->fail(BIODB_ERR_NOMEM, "too many pileup columns in one batch; lower blocks_per_batch");
+    // ---- phase 2: columns ---------------------------------------------------------------------------------
+    uint64_t n_entries = 0;
+    if (n_col) {
+      if ((size_t)n_col + 8 > pl->col_cap) {
+        size_t cap = (size_t)n_col + n_col / 4 + 1024;
+        for (int k = 0; k < 4; ++k) PL_TRY(pl->cs[k].ensure(cap * 4, st));
+        PL_TRY(pl->out[0].ensure(cap * 8, st));
+        PL_TRY(pl->out[1].ensure(cap * 8, st));
+        pl->col_cap = cap;
+      }
+      biodb_status es = ensure_tmp(pl, std::max<size_t>(pl->n_view, n_col) + 2);
+      if (es != BIODB_OK) return es;
+      s = scratch(pl);
+      s.clo = clo;
+      s.chi = chi;
+      ColumnScratch c{pl->cs[0].as<int32_t>(), pl->cs[1].as<uint32_t>(), pl->cs[2].as<uint32_t>(), pl->cs[3].as<uint32_t>()};
+      ColumnOutput o{pl->out[0].as<uint64_t>(), pl->out[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr};
+      pileup_phase2(v, g0, g1, n_islands, n_col, s, c, o, st);
+      PL_TRY(cudaMemcpyAsync(pl->h_small.p, o.col_off + n_col, 8, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaStreamSynchronize(st));
+      n_entries = *pl->h_small.as<uint64_t>();
+      if (n_entries + 8 > pl->ent_cap) {
+        size_t cap = (size_t)n_entries + n_entries / 4 + 4096;
+        PL_TRY(pl->out[2].ensure(cap * 4, st));
+        PL_TRY(pl->out[3].ensure(cap, st));
+        PL_TRY(pl->out[4].ensure(cap, st));
+        if (pl->prm.want_query_offset) PL_TRY(pl->out[5].ensure(cap * 4, st));
+        pl->ent_cap = cap;
+      }
+      o.read_idx = pl->out[2].as<uint32_t>();
+      o.base = pl->out[3].as<uint8_t>();
+      o.qual = pl->out[4].as<uint8_t>();
+      o.qoff = pl->prm.want_query_offset ? pl->out[5].as<uint32_t>() : nullptr;
+      pileup_entries(v, n_col, s, c, o, st);
+      // results to the host
+      PL_TRY(pl->h_out[0].ensure((size_t)n_col * 8 + 16));
+      PL_TRY(pl->h_out[1].ensure((size_t)(n_col + 1) * 8 + 16));
+      PL_TRY(pl->h_out[2].ensure((size_t)n_col * 4 + 16));
+      PL_TRY(pl->h_out[3].ensure((size_t)n_entries * 4 + 16));
+      PL_TRY(pl->h_out[4].ensure((size_t)n_entries * 2 + 16));
+      PL_TRY(cudaMemcpyAsync(pl->h_out[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaMemcpyAsync(pl->h_out[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaMemcpyAsync(pl->h_out[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaMemcpyAsync(pl->h_out[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaMemcpyAsync(pl->h_out[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaMemcpyAsync(pl->h_out[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, st));
+      if (o.qoff) {
+        PL_TRY(pl->h_out[5].ensure((size_t)n_entries * 4 + 16));
+        PL_TRY(cudaMemcpyAsync(pl->h_out[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, st));
+      }
+      PL_TRY(cudaMemcpyAsync(h + 8, s.info, 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(cudaStreamSynchronize(st));
+      if (h[8] != 0) return pl->fail(h[8], "Invalid read - query offset beyond the sequence while building a column");
+    }
+    // ---- carry reads that reach past this batch ---------------------------------------------------------------
+    bool stop_after = false;
+    if (single && pl->prm.end_at <= (uint64_t)INT64_MAX && trailing && E >= (int64_t)pl->prm.end_at) stop_after = true;
+    if (last_group) {
+      CarryBufs& nxt = pl->carry[pl->cur ^ 1];
+      nxt.n = 0;
+      nxt.bytes = 0;
+      if (trailing && !stop_after) {
+        RecordArrays a = p.arrays(0);
+        CarryOut dummy{};
+        pileup_carry(v, g0, g1, a.block_size, E, s, dummy, st);
+        const uint32_t t_g = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
+        PL_TRY(cudaMemcpyAsync(h, s.tmp_u32 + t_g, 4, cudaMemcpyDeviceToHost, st));
+        PL_TRY(cudaMemcpyAsync(h + 2, s.tmp_u64 + t_g, 8, cudaMemcpyDeviceToHost, st));
+        PL_TRY(cudaStreamSynchronize(st));
+        const uint32_t nc = (uint32_t)h[0];
+        const uint64_t nbytes = *(uint64_t*)(h + 2);
+        if (nc) {
+          static const size_t esz[9] = {4, 4, 4, 8, 4, 4, 4, 4, 4};
+          for (int k = 0; k < 9; ++k) PL_TRY(nxt.a[k].ensure((size_t)(nc + 8) * esz[k], st));
+          PL_TRY(nxt.data.ensure((size_t)nbytes + 256, st));
+          CarryOut co = nxt.out();
+          pileup_carry_copy(v, g0, g1, a.block_size, s, co, st);
+          PL_TRY(cudaStreamSynchronize(st));
+        }
+        nxt.n = nc;
+        nxt.bytes = nbytes;
+        pl->cont = true;
+        pl->cont_ref = ref;
+        pl->cont_pos = E;
+      } else {
+        pl->cont = false;
+      }
+      pl->cur ^= 1;
+    }
+    if (stop_after) pl->done = true;
+    if (single && !trailing) pl->done = true;   // the group of the target reference is complete
+    if (n_col == 0) {
+      if (pl->done) return BIODB_EOF;
+      continue;
+    }
+    cols->n_columns = n_col;
+    cols->n_entries = n_entries;
+    cols->ref_id = ref;
+    cols->last_of_pileup = pl->done ? 1 : 0;
+    cols->position = pl->h_out[0].as<uint64_t>();
+    cols->col_off = pl->h_out[1].as<uint64_t>();
+    cols->n_starting_here = pl->h_out[2].as<uint32_t>();
+    cols->read_idx = pl->h_out[3].as<uint32_t>();
+    cols->base = pl->h_out[4].as<uint8_t>();
+    cols->qual = pl->h_out[4].as<uint8_t>() + n_entries;
+    cols->query_offset = pl->prm.want_query_offset ? pl->h_out[5].as<uint32_t>() : nullptr;
+    pl->tot_cols += n_col;
+    pl->tot_entries += n_entries;
+    return BIODB_OK;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,636 @@
+// Host runtime + C ABI of libbiod_b200.so (see include/biod_b200.h and runtime.h).
+#include "runtime.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+using namespace biodb;
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return this->fail(BIODB_ERR_CUDA, 0, 0, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+namespace biodb {
+
+cudaError_t DevBuf::ensure(size_t bytes, cudaStream_t st, size_t keep) {
+  if (bytes <= cap) return cudaSuccess;
+  size_t ncap = std::max(bytes, cap + cap / 2);
+  ncap = (ncap + 255) & ~(size_t)255;
+  void* np = nullptr;
+  cudaError_t e = cudaMalloc(&np, ncap);
+  if (e != cudaSuccess) return e;
+  if (p) {
+    if (keep) {
+      e = cudaMemcpyAsync(np, p, std::min(keep, cap), cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { cudaFree(np); return e; }
+    } else {
+      cudaStreamSynchronize(st);
+    }
+    cudaFree(p);
+  }
+  p = np;
+  cap = ncap;
+  return cudaSuccess;
+}
+
+cudaError_t PinBuf::ensure(size_t bytes) {
+  if (bytes <= cap) return cudaSuccess;
+  size_t ncap = std::max(bytes, cap + cap / 2);
+  void* np = nullptr;
+  cudaError_t e = cudaHostAlloc(&np, ncap, cudaHostAllocDefault);
+  if (e != cudaSuccess) return e;
+  if (p) cudaFreeHost(p);
+  p = np;
+  cap = ncap;
+  return cudaSuccess;
+}
+
+static inline uint16_t le16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static inline uint32_t le32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+static void set_error(biodb_error* e, int status, int zerr, uint64_t off, const std::string& msg) {
+  e->status = status;
+  e->zlib_errnum = zerr;
+  e->file_offset = off;
+  snprintf(e->message, sizeof e->message, "%s", msg.c_str());
+}
+
+// BGZF member header — the checks and messages of fillBgzfBufferFromStream
+// (bio/core/bgzf/inputstream.d:54-199).  1 = block, 0 = clean end of stream, <0 = BgzfException.
+int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, BlockInfo* b, biodb_error* e) {
+  auto bad = [&](const std::string& why) {
+    set_error(e, BIODB_ERR_BGZF, 0, pos, "Error reading BGZF block starting from offset " + std::to_string(pos) + ": " + why);
+    return (int)BIODB_ERR_BGZF;
+  };
+  static const char* kShort = "stream error: not enough data in stream";
+  if (pos >= len || len - pos < 4) return 0;
+  const uint8_t* h = d + pos;
+  if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 0x08 || h[3] != 0x04) return bad("wrong BGZF magic");
+  if (pos + 12 > len) return bad(kShort);
+  const uint32_t xlen = le16(h + 10);
+  uint64_t q = pos + 12;
+  uint32_t seen = 0, bsize = 0;
+  bool have = false;
+  while (seen < xlen) {
+    if (q + 4 > len) return bad(kShort);
+    const uint8_t s1 = d[q], s2 = d[q + 1];
+    const uint32_t slen = le16(d + q + 2);
+    if (s1 == 'B' && s2 == 'C') {
+      if (slen != 2) return bad("wrong BC subfield length: " + std::to_string(slen) + "; expected 2");
+      if (have) return bad("duplicate field with block size");
+      if (q + 6 > len) return bad(kShort);
+      bsize = le16(d + q + 4);
+      have = true;
+    }
+    q += 4 + slen;
+    seen += 4 + slen;
+  }
+  if (seen != xlen)
+    return bad("total length of subfields in bytes (" + std::to_string(seen) + ") is not equal to gzip_extra_length (" +
+               std::to_string(xlen) + ")");
+  if (!have) return bad("block size was not found in any subfield");
+  const int64_t cdata = (int64_t)bsize - (int64_t)xlen - 19;
+  if (cdata > 65536)
+    return bad("compressed data size is more than 65536 bytes, which is not allowed by current BAM specification");
+  if (cdata < 0 || q + (uint64_t)cdata + 8 > len) return bad(kShort);
+  b->coffset = pos;
+  b->payload = q;
+  b->bsize = bsize;
+  b->cdata_size = (uint32_t)cdata;
+  b->crc32 = le32(d + q + cdata);
+  b->isize = le32(d + q + cdata + 4);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------- Pass ----
+
+Pass::~Pass() {
+  if (st) {
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
+  }
+}
+
+biodb_status Pass::fail(int status, int zerr, uint64_t off, const std::string& msg) {
+  set_error(&r->err, status, zerr, off, msg);
+  finished = true;
+  return (biodb_status)status;
+}
+
+biodb_status Pass::init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset) {
+  r = rd;
+  if (cudaSetDevice(rd->device) != cudaSuccess) return fail(BIODB_ERR_CUDA, 0, 0, "cudaSetDevice failed");
+  CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  next_coffset = coffset;
+  first_skip = uoffset;
+  CUDA_TRY(h_result.ensure(64));
+  CUDA_TRY(d_result.ensure(64));
+  return BIODB_OK;
+}
+
+RecordArrays Pass::arrays(uint64_t front) const {
+  RecordArrays a;
+  a.rec_off = d_rec[0].as<uint64_t>() + front;
+  a.block_size = d_rec[1].as<int32_t>() + front;
+  a.ref_id = d_rec[2].as<int32_t>() + front;
+  a.pos = d_rec[3].as<int32_t>() + front;
+  a.end_pos = d_rec[4].as<int32_t>() + front;
+  a.bin_mq_nl = d_rec[5].as<uint32_t>() + front;
+  a.flag_nc = d_rec[6].as<uint32_t>() + front;
+  a.l_seq = d_rec[7].as<int32_t>() + front;
+  a.cigar_off = d_rec[8].as<uint64_t>() + front;
+  a.cigar = d_rec[9].as<uint32_t>();
+  a.capacity = rec_capacity;
+  a.cigar_capacity = cigar_capacity;
+  return a;
+}
+
+uint64_t Pass::voffset_of(uint64_t x) const {
+  // VirtualOffset (virtualoffset.d:43); an offset that is exactly a block end reports the next
+  // block with uoffset 0 (inputstream.d:443-445,516-524).
+  size_t lo = 0, hi = segs.size();
+  while (lo < hi) {
+    size_t m = (lo + hi) / 2;
+    if (segs[m].ustart <= x) lo = m + 1; else hi = m;
+  }
+  if (lo == 0) return 0;
+  const Seg& s = segs[lo - 1];
+  if (x - s.ustart >= s.len) return s.cend << 16;
+  return (s.coffset << 16) | (uint64_t)(s.within + (x - s.ustart));
+}
+
+biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
+  n = n_cigar = 0;
+  if (finished) {
+    if (pending.status) { r->err = pending; return (biodb_status)pending.status; }
+    if (front_slots == 0) return BIODB_EOF;
+    // nothing left in the file, but the caller still holds carried reads: hand out an empty final batch
+    if (rec_front < front_slots || rec_capacity == 0) {
+      rec_front = std::max(rec_front, front_slots);
+      rec_capacity = std::max<uint64_t>(rec_capacity, 1024);
+      cigar_capacity = std::max<uint64_t>(cigar_capacity, 1024);
+      static const size_t esz0[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
+      for (int a = 0; a < 9; ++a) CUDA_TRY(d_rec[a].ensure((size_t)(rec_capacity + rec_front + 2) * esz0[a], st));
+      CUDA_TRY(d_rec[9].ensure((size_t)(cigar_capacity + 2) * 4, st));
+    }
+    u_len = 0;
+    tail = 0;
+    final_slice = true;
+    return BIODB_OK;
+  }
+  // ---- 1. walk the BSIZE chain on the host (18 bytes per block) ----------------------------------
+  blocks.clear();
+  while (blocks.size() < max_blocks && !supplier_done && !pending.status) {
+    BlockInfo b;
+    int rc = parse_bgzf_header(r->file, r->flen, next_coffset, &b, &pending);
+    if (rc < 0) break;
+    if (rc == 0 || b.isize == 0) { supplier_done = true; break; }     // EOF block ends the stream (inputstream.d:393-394)
+    if (b.isize > 65536) {                                             // block.d:150-152
+      set_error(&pending, BIODB_ERR_FORMAT, 0, b.coffset, "Uncompressed block size must be within 65536 bytes");
+      break;
+    }
+    blocks.push_back(b);
+    next_coffset = b.coffset + b.bsize + 1;
+  }
+  const uint32_t nb = (uint32_t)blocks.size();
+  bool last_batch = supplier_done || pending.status != 0;
+  if (nb == 0 && carry_tail_len == 0 && front_slots == 0) {
+    finished = true;
+    if (pending.status) { r->err = pending; return (biodb_status)pending.status; }
+    return BIODB_EOF;
+  }
+  // ---- 2. per-block tables ---------------------------------------------------------------------------
+  const bool has_carry = carry_tail_len > 0;
+  const uint32_t nsb = nb + (has_carry ? 1 : 0);          // scan blocks (the carried tail is a pseudo block)
+  const size_t tab_bytes = (size_t)nb * (8 + 8 + 4 + 4) + (size_t)(nsb + 2) * 8 + 64;
+  CUDA_TRY(h_tab.ensure(tab_bytes));
+  CUDA_TRY(d_tab.ensure(tab_bytes, st));
+  uint8_t* hp = h_tab.as<uint8_t>();
+  uint64_t* h_payload = (uint64_t*)hp;
+  uint64_t* h_outoff = h_payload + nb;
+  uint64_t* h_buoff = h_outoff + nb;
+  uint32_t* h_cdata = (uint32_t*)(h_buoff + nsb + 2);
+  uint32_t* h_isize = h_cdata + nb;
+  const uint64_t c0 = nb ? blocks[0].coffset : 0;
+  const uint64_t c1 = nb ? blocks[nb - 1].coffset + blocks[nb - 1].bsize + 1 : 0;
+  segs.swap(next_segs);
+  next_segs.clear();
+  uint64_t off = carry_tail_len;
+  uint32_t k = 0;
+  if (has_carry) h_buoff[k++] = 0;
+  for (uint32_t i = 0; i < nb; ++i) {
+    h_payload[i] = blocks[i].payload - c0;
+    h_outoff[i] = off;
+    h_cdata[i] = blocks[i].cdata_size;
+    h_isize[i] = blocks[i].isize;
+    h_buoff[k++] = off;
+    segs.push_back(Seg{off, blocks[i].coffset, 0, blocks[i].isize, blocks[i].coffset + blocks[i].bsize + 1});
+    off += blocks[i].isize;
+  }
+  h_buoff[k] = off;
+  if (!has_carry && nb) h_buoff[0] += first_skip;         // the first record of the file sits behind the header
+  first_skip = 0;
+  u_len = off;
+  uint8_t* dp = d_tab.as<uint8_t>();
+  const uint64_t* d_payload = (const uint64_t*)dp;
+  const uint64_t* d_outoff = d_payload + nb;
+  const uint64_t* d_buoff = d_outoff + nb;
+  const uint32_t* d_cdata = (const uint32_t*)(d_buoff + nsb + 2);
+  const uint32_t* d_isize = d_cdata + nb;
+  // ---- 3. device buffers -------------------------------------------------------------------------------
+  CUDA_TRY(d_comp.ensure((size_t)(c1 - c0) + 256, st));
+  CUDA_TRY(d_u.ensure((size_t)u_len + 256, st));
+  CUDA_TRY(d_status.ensure((size_t)nb * 4 + 16, st));
+  CUDA_TRY(h_status.ensure((size_t)nb * 4 + 16));
+  CUDA_TRY(d_ws.ensure(scan_workspace_bytes(nsb), st));
+  if (has_carry)
+    CUDA_TRY(cudaMemcpyAsync(d_u.p, d_carry_tail.p, carry_tail_len, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_tab.p, h_tab.p, tab_bytes, cudaMemcpyHostToDevice, st));
+  if (nb) {
+    CUDA_TRY(cudaMemcpyAsync(d_comp.p, r->file + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+    InflateArgs ia{d_comp.as<uint8_t>(), d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb};
+    CUDA_TRY(launch_inflate(ia, st));
+    CUDA_TRY(cudaMemcpyAsync(h_status.p, d_status.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int32_t* hs = h_status.as<int32_t>();
+    for (uint32_t i = 0; i < nb; ++i) {
+      if (hs[i] != 0) {
+        // the blocks before the faulty one are still delivered; the ZlibException surfaces when the
+        // iteration reaches it (test/unittests.d:140-142)
+        set_error(&pending, BIODB_ERR_ZLIB, hs[i], blocks[i].coffset,
+                  std::string("zlib error ") + std::to_string(hs[i]) + (hs[i] == -3 ? " (data error)" : " (buffer error)"));
+        u_len = h_outoff[i];
+        blocks.resize(i);
+        last_batch = true;
+        break;
+      }
+    }
+  }
+  const uint32_t nb2 = (uint32_t)blocks.size();
+  const uint32_t nsb2 = nb2 + (has_carry ? 1 : 0);
+  if (nb2 != nb) {
+    // truncated slice: rewrite the boundary table tail
+    h_buoff[nsb2] = u_len;
+    CUDA_TRY(cudaMemcpyAsync((void*)(d_buoff + nsb2), &h_buoff[nsb2], 8, cudaMemcpyHostToDevice, st));
+    while (!segs.empty() && segs.back().ustart >= u_len) segs.pop_back();
+  }
+  final_slice = last_batch;
+  end_coffset_last = segs.empty() ? next_coffset : segs.back().cend;
+  if (raw_mode) {
+    tail = u_len;
+    if (last_batch) finished = true;
+    return BIODB_OK;
+  }
+  // ---- 4. record scan (grow the tables and retry when they are too small) ------------------------------
+  const int eof_semantics = (last_batch && pending.status == 0) ? 1 : 0;
+  uint64_t want_rec = std::max<uint64_t>(rec_capacity, u_len / 96 + 1024);
+  uint64_t want_cig = std::max<uint64_t>(cigar_capacity, want_rec * 2);
+  ScanWorkspace ws = carve_scan_workspace(d_ws.p, nsb2);
+  for (int attempt = 0; attempt < 8; ++attempt) {
+    if (want_rec != rec_capacity || want_cig != cigar_capacity || rec_front < front_slots) {
+      rec_capacity = want_rec;
+      cigar_capacity = want_cig;
+      rec_front = std::max(rec_front, front_slots);
+      static const size_t esz[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
+      for (int a = 0; a < 9; ++a) CUDA_TRY(d_rec[a].ensure((size_t)(rec_capacity + rec_front + 2) * esz[a], st));
+      CUDA_TRY(d_rec[9].ensure((size_t)(cigar_capacity + 2) * 4, st));
+    }
+    RecordArrays ra = arrays(front_slots);
+    CUDA_TRY(launch_scan_records(d_u.as<uint8_t>(), u_len, d_buoff, nsb2, eof_semantics, ra, d_result.as<uint64_t>(), ws, st));
+    CUDA_TRY(cudaMemcpyAsync(h_result.p, d_result.p, 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t* res = h_result.as<uint64_t>();
+    if ((int64_t)res[3] == BIODB_ERR_NOMEM) {
+      want_rec = std::max<uint64_t>(res[0] + res[0] / 8 + 1024, rec_capacity);
+      want_cig = std::max<uint64_t>(res[2] + res[2] / 8 + 1024, cigar_capacity);
+      continue;
+    }
+    n = res[0];
+    tail = res[1];
+    n_cigar = res[2];
+    if ((int64_t)res[3] == BIODB_ERR_TRUNCATED && pending.status == 0) {
+      set_error(&pending, BIODB_ERR_TRUNCATED, 0, end_coffset_last, "not enough data in stream (truncated or malformed BAM record)");
+      last_batch = true;
+      final_slice = true;
+    }
+    break;
+  }
+  // ---- 5. carry the cut record at the end of the slice into the next one ---------------------------------
+  carry_tail_len = 0;
+  if (!last_batch && tail < u_len) {
+    carry_tail_len = u_len - tail;
+    CUDA_TRY(d_carry_tail.ensure((size_t)carry_tail_len + 256, st));
+    CUDA_TRY(cudaMemcpyAsync(d_carry_tail.p, d_u.as<uint8_t>() + tail, carry_tail_len, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (const Seg& s : segs) {
+      uint64_t a = std::max(s.ustart, tail), b = s.ustart + s.len;
+      if (a < b) next_segs.push_back(Seg{a - tail, s.coffset, (uint32_t)(s.within + (a - s.ustart)), (uint32_t)(b - a), s.cend});
+    }
+  }
+  n_records_total += n;
+  if (last_batch) finished = true;
+  return BIODB_OK;
+}
+
+}  // namespace biodb
+
+// =========================================================================================== C ABI ====
+
+static thread_local biodb_error g_open_error;
+
+extern "C" {
+
+const char* biodb_version(void) { return "biod_b200 0.1 (sm_100a)"; }
+
+void biodb_default_options(biodb_options* o) {
+  memset(o, 0, sizeof *o);
+  o->device = -1;
+  o->blocks_per_batch = 8192;
+}
+
+const biodb_error* biodb_open_error(void) { return &g_open_error; }
+const biodb_error* biodb_last_error(const biodb_reader* r) { return r ? &r->err : &g_open_error; }
+
+static biodb_status open_common(biodb_reader* r) {
+  // BamReader constructor (bam/reader.d:100-124): magic, header text, reference table — the blocks
+  // that hold them are inflated on the device, then parsed here.
+  Pass p;
+  p.raw_mode = true;
+  biodb_status s = p.init(r, 0, 0);
+  if (s != BIODB_OK) return s;
+  std::vector<uint8_t> u;
+  biodb::PinBuf host;
+  bool done = false;
+  auto fetch = [&]() -> biodb_status {   // append the next few blocks to u
+    biodb_status st = p.next(4, 0);
+    if (st != BIODB_OK) { done = true; return st; }
+    size_t fresh = (size_t)p.u_len;   // raw_mode: the slice is the plain byte stream
+    size_t carry = 0;
+    if (fresh) {
+      if (host.ensure(fresh) != cudaSuccess) return BIODB_ERR_CUDA;
+      if (cudaMemcpy(host.p, p.d_u.p, fresh, cudaMemcpyDeviceToHost) != cudaSuccess) return BIODB_ERR_CUDA;
+      u.insert(u.end(), host.as<uint8_t>() + carry, host.as<uint8_t>() + fresh);
+    }
+    if (p.finished) done = true;
+    return BIODB_OK;
+  };
+  // remember where each block's bytes start so the first record's virtual offset can be computed
+  std::vector<BlockInfo> seen;
+  std::vector<uint64_t> ustart;
+  biodb_status deferred = BIODB_OK;
+  auto need = [&](size_t upto) -> biodb_status {
+    while (u.size() < upto && !done) {
+      size_t before = u.size();
+      biodb_status st = fetch();
+      if (st != BIODB_OK && st != BIODB_EOF) { deferred = st; break; }
+      uint64_t o = before;
+      for (const BlockInfo& b : p.blocks) { seen.push_back(b); ustart.push_back(o); o += b.isize; }
+      if (st == BIODB_EOF) break;
+    }
+    if (u.size() >= upto) return BIODB_OK;
+    if (deferred != BIODB_OK) return deferred;         // the error lies inside the header: raise it now
+    set_error(&r->err, BIODB_ERR_TRUNCATED, 0, 0, "not enough data in stream");
+    return BIODB_ERR_TRUNCATED;
+  };
+  need(4);
+  if (u.size() < 4 || memcmp(u.data(), "BAM\1", 4) != 0) {
+    if (deferred != BIODB_OK && u.size() < 4) return deferred;
+    set_error(&r->err, BIODB_ERR_FORMAT, 0, 0, "Invalid file format: expected BAM\\1");   // reader.d:111-113
+    return BIODB_ERR_FORMAT;
+  }
+  size_t q = 4;
+  if ((s = need(q + 4)) != BIODB_OK) return s;
+  int32_t l_text = (int32_t)le32(u.data() + q);
+  q += 4;
+  if (l_text < 0) { set_error(&r->err, BIODB_ERR_FORMAT, 0, 0, "negative l_text"); return BIODB_ERR_FORMAT; }
+  if ((s = need(q + (size_t)l_text + 4)) != BIODB_OK) return s;
+  r->text.assign((const char*)u.data() + q, (size_t)l_text);
+  q += (size_t)l_text;
+  int32_t n_ref = (int32_t)le32(u.data() + q);
+  q += 4;
+  for (int32_t i = 0; i < n_ref; ++i) {
+    if ((s = need(q + 4)) != BIODB_OK) return s;
+    int32_t l_name = (int32_t)le32(u.data() + q);      // referenceinfo.d:57-62
+    q += 4;
+    if (l_name < 0) { set_error(&r->err, BIODB_ERR_FORMAT, 0, 0, "negative l_name"); return BIODB_ERR_FORMAT; }
+    if ((s = need(q + (size_t)l_name + 4)) != BIODB_OK) return s;
+    std::string nm((const char*)u.data() + q, (size_t)l_name);
+    if (!nm.empty() && nm.back() == '\0') nm.pop_back();
+    r->ref_names.push_back(nm);
+    q += (size_t)l_name;
+    r->ref_lens.push_back((int32_t)le32(u.data() + q));
+    q += 4;
+  }
+  // virtualTell() right after the header (reader.d:121-123)
+  need(q + 1);   // make the block that holds the first record known, if there is one
+  size_t bi = 0;
+  while (bi + 1 < seen.size() && ustart[bi + 1] <= q) ++bi;
+  if (seen.empty()) return BIODB_ERR_FORMAT;
+  if (q - ustart[bi] >= seen[bi].isize) {
+    r->reads_start_coffset = seen[bi].coffset + seen[bi].bsize + 1;
+    r->reads_start_uoffset = 0;
+  } else {
+    r->reads_start_coffset = seen[bi].coffset;
+    r->reads_start_uoffset = (uint32_t)(q - ustart[bi]);
+  }
+  r->reads_start_vo = (r->reads_start_coffset << 16) | r->reads_start_uoffset;
+  memset(&r->err, 0, sizeof r->err);   // errors of later blocks surface during iteration (unittests.d:139)
+  return BIODB_OK;
+}
+
+static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biodb_reader** out) {
+  if (opts) r->opts = *opts; else biodb_default_options(&r->opts);
+  if (r->opts.blocks_per_batch <= 0) r->opts.blocks_per_batch = 8192;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "no CUDA device: biod_b200 has no CPU fallback");
+    delete r;
+    return BIODB_ERR_CUDA;
+  }
+  if (r->opts.device < 0) { if (cudaGetDevice(&r->device) != cudaSuccess) r->device = 0; }
+  else r->device = r->opts.device;
+  biodb_status s = open_common(r);
+  if (s != BIODB_OK) {
+    g_open_error = r->err;
+    if (!g_open_error.status) set_error(&g_open_error, s, 0, 0, "open failed");
+    delete r;
+    return s;
+  }
+  *out = r;
+  return BIODB_OK;
+}
+
+biodb_status biodb_open_memory(const void* data, size_t len, const biodb_options* opts, biodb_reader** out) {
+  if (!data || !out) return BIODB_ERR_ARG;
+  biodb_reader* r = new biodb_reader;
+  r->file = (const uint8_t*)data;
+  r->flen = len;
+  if (opts && opts->pin_input && len)
+    r->registered = cudaHostRegister((void*)data, len, cudaHostRegisterReadOnly) == cudaSuccess ||
+                    cudaHostRegister((void*)data, len, cudaHostRegisterDefault) == cudaSuccess;
+  cudaGetLastError();
+  return finish_open(r, opts, out);
+}
+
+biodb_status biodb_open(const char* path, const biodb_options* opts, biodb_reader** out) {
+  if (!path || !out) return BIODB_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) {
+    set_error(&g_open_error, BIODB_ERR_IO, 0, 0, std::string("cannot open ") + path);
+    return BIODB_ERR_IO;
+  }
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  biodb_reader* r = new biodb_reader;
+  if (r->owned.ensure((size_t)sz + 64) != cudaSuccess) {
+    fclose(f);
+    delete r;
+    set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "cannot allocate pinned memory for the file (no CUDA device?)");
+    return BIODB_ERR_CUDA;
+  }
+  size_t got = fread(r->owned.p, 1, (size_t)sz, f);
+  fclose(f);
+  if (got != (size_t)sz) {
+    delete r;
+    set_error(&g_open_error, BIODB_ERR_IO, 0, 0, std::string("short read on ") + path);
+    return BIODB_ERR_IO;
+  }
+  r->file = r->owned.as<uint8_t>();
+  r->flen = (uint64_t)sz;
+  return finish_open(r, opts, out);
+}
+
+void biodb_close(biodb_reader* r) {
+  if (!r) return;
+  if (r->registered) cudaHostUnregister((void*)r->file);
+  delete r;
+}
+
+biodb_status biodb_header_text(const biodb_reader* r, const char** text, size_t* len) {
+  if (!r || !text || !len) return BIODB_ERR_ARG;
+  *text = r->text.data();
+  *len = r->text.size();
+  return BIODB_OK;
+}
+int32_t biodb_n_refs(const biodb_reader* r) { return r ? (int32_t)r->ref_names.size() : 0; }
+biodb_status biodb_ref_info(const biodb_reader* r, int32_t i, const char** name, int32_t* name_len, int32_t* length) {
+  if (!r || i < 0 || (size_t)i >= r->ref_names.size()) return BIODB_ERR_ARG;
+  if (name) *name = r->ref_names[i].c_str();
+  if (name_len) *name_len = (int32_t)r->ref_names[i].size();
+  if (length) *length = r->ref_lens[i];
+  return BIODB_OK;
+}
+uint64_t biodb_reads_start_voffset(const biodb_reader* r) { return r ? r->reads_start_vo : 0; }
+uint64_t biodb_file_size(const biodb_reader* r) { return r ? r->flen : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------- reads ----
+
+struct biodb_reads {
+  Pass pass;
+  PinBuf h_data, h_arr[10], h_vo[2];
+};
+
+extern "C" {
+
+biodb_status biodb_reads_begin(biodb_reader* r, biodb_reads** out) {
+  if (!r || !out) return BIODB_ERR_ARG;
+  biodb_reads* it = new biodb_reads;
+  biodb_status s = it->pass.init(r, r->reads_start_coffset, r->reads_start_uoffset);
+  if (s != BIODB_OK) { delete it; return s; }
+  *out = it;
+  return BIODB_OK;
+}
+
+biodb_status biodb_reads_next(biodb_reads* it, biodb_record_batch* batch) {
+  if (!it || !batch) return BIODB_ERR_ARG;
+  Pass& p = it->pass;
+  memset(batch, 0, sizeof *batch);
+  const uint64_t first = p.n_records_total;
+  biodb_status s;
+  do {
+    s = p.next((uint32_t)p.r->opts.blocks_per_batch, 0);
+  } while (s == BIODB_OK && p.n == 0 && !p.finished);   // a slice may hold only part of one huge record
+  if (s != BIODB_OK) return s;
+  if (p.n == 0) return p.next(1, 0);                      // finished: raises the pending error or EOF
+  const uint64_t n = p.n;
+  const uint64_t used = p.tail;                           // bytes of the slice covered by whole records
+  auto pull = [&](PinBuf& h, const void* d, size_t bytes) -> bool {
+    if (h.ensure(bytes + 16) != cudaSuccess) return false;
+    return cudaMemcpyAsync(h.p, d, bytes, cudaMemcpyDeviceToHost, p.st) == cudaSuccess;
+  };
+  static const size_t esz[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
+  bool ok = pull(it->h_data, p.d_u.p, (size_t)used);
+  for (int a = 0; a < 9 && ok; ++a) ok = pull(it->h_arr[a], p.d_rec[a].p, (size_t)(n + (a == 8 ? 1 : 0)) * esz[a]);
+  ok = ok && pull(it->h_arr[9], p.d_rec[9].p, (size_t)p.n_cigar * 4);
+  if (!ok || cudaStreamSynchronize(p.st) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "device to host copy failed");
+  batch->n = n;
+  batch->first_index = first;
+  batch->data = it->h_data.as<uint8_t>();
+  batch->data_len = used;
+  batch->rec_off = it->h_arr[0].as<uint64_t>();
+  batch->block_size = it->h_arr[1].as<int32_t>();
+  batch->ref_id = it->h_arr[2].as<int32_t>();
+  batch->pos = it->h_arr[3].as<int32_t>();
+  batch->end_pos = it->h_arr[4].as<int32_t>();
+  batch->bin_mq_nl = it->h_arr[5].as<uint32_t>();
+  batch->flag_nc = it->h_arr[6].as<uint32_t>();
+  batch->l_seq = it->h_arr[7].as<int32_t>();
+  batch->cigar_off = it->h_arr[8].as<uint64_t>();
+  batch->cigar = it->h_arr[9].as<uint32_t>();
+  if (p.r->opts.want_offsets) {
+    if (it->h_vo[0].ensure((size_t)n * 8 + 8) != cudaSuccess || it->h_vo[1].ensure((size_t)n * 8 + 8) != cudaSuccess)
+      return p.fail(BIODB_ERR_CUDA, 0, 0, "pinned allocation failed");
+    uint64_t* sv = it->h_vo[0].as<uint64_t>();
+    uint64_t* ev = it->h_vo[1].as<uint64_t>();
+    for (uint64_t i = 0; i < n; ++i) {
+      sv[i] = p.voffset_of(batch->rec_off[i]);                                  // readrange.d:64-66
+      ev[i] = p.voffset_of(batch->rec_off[i] + 4 + (uint64_t)batch->block_size[i]);   // readrange.d:55-57
+    }
+    batch->start_voffset = sv;
+    batch->end_voffset = ev;
+  }
+  return BIODB_OK;
+}
+
+void biodb_reads_end(biodb_reads* it) { delete it; }
+
+float biodb_reads_progress(const biodb_reads* it) {
+  if (!it || !it->pass.r || it->pass.r->flen == 0) return 0.f;
+  return (float)((double)it->pass.next_coffset / (double)it->pass.r->flen);
+}
+
+// ---- device-resident stage API --------------------------------------------------------------------------
+
+biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off, const uint32_t* cdata_size,
+                               const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
+                               int32_t* status, uint32_t* crc, void* stream) {
+  (void)crc;
+  InflateArgs ia{comp, payload_off, cdata_size, out_off, isize, out, status, n_blocks};
+  return launch_inflate(ia, (cudaStream_t)stream) == cudaSuccess ? BIODB_OK : BIODB_ERR_CUDA;
+}
+
+size_t biodb_dev_scan_workspace_bytes(uint32_t n_blocks) { return scan_workspace_bytes(n_blocks); }
+
+biodb_status biodb_dev_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t* block_uoff, uint32_t n_blocks,
+                                    int32_t final_slice, biodb_dev_records* o, uint64_t* result, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (!o || workspace_bytes < scan_workspace_bytes(n_blocks)) return BIODB_ERR_ARG;
+  RecordArrays ra{o->rec_off, o->block_size, o->ref_id, o->pos, o->end_pos, o->bin_mq_nl, o->flag_nc, o->l_seq,
+                  o->cigar_off, o->cigar, o->capacity, o->cigar_capacity};
+  ScanWorkspace ws = carve_scan_workspace(workspace, n_blocks);
+  return launch_scan_records(u, u_len, block_uoff, n_blocks, final_slice, ra, result, ws, (cudaStream_t)stream) == cudaSuccess
+             ? BIODB_OK
+             : BIODB_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// Host runtime behind the C ABI: file / block-table handling, device + pinned buffers, the batch
+// pipeline (H2D -> inflate -> record scan -> [pileup] -> D2H).  No CPU inflate / decode / pileup
+// path exists here by design: without a CUDA device every entry point fails with BIODB_ERR_CUDA.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/biod_b200.h"
+#include "kernels.h"
+#include "pileup.h"
+
+namespace biodb {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  // grows (never shrinks); contents are NOT preserved unless keep > 0
+  cudaError_t ensure(size_t bytes, cudaStream_t st = 0, size_t keep = 0);
+  template <typename T> T* as() const { return (T*)p; }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~PinBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t ensure(size_t bytes);
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct BlockInfo {      // BgzfBlock (bgzf/block.d:42-73)
+  uint64_t coffset;     // start_offset
+  uint64_t payload;     // file offset of the deflate payload
+  uint32_t bsize;       // total size - 1
+  uint32_t cdata_size;
+  uint32_t crc32;
+  uint32_t isize;       // input_size
+};
+
+struct Seg {            // where a run of uncompressed bytes of the current slice came from
+  uint64_t ustart;      // offset inside the slice
+  uint64_t coffset;     // BGZF block start
+  uint32_t within;      // offset inside that block's uncompressed data
+  uint32_t len;
+  uint64_t cend;        // end_offset of the block (start of the next one)
+};
+
+}  // namespace biodb
+
+struct biodb_reader {
+  biodb_options opts;
+  int device = 0;
+  const uint8_t* file = nullptr;
+  uint64_t flen = 0;
+  biodb::PinBuf owned;            // file contents when opened by path
+  bool registered = false;
+  std::string text;
+  std::vector<std::string> ref_names;
+  std::vector<int32_t> ref_lens;
+  uint64_t reads_start_vo = 0;
+  uint64_t reads_start_coffset = 0;
+  uint32_t reads_start_uoffset = 0;
+  bool reads_start_at_eof = false;
+  biodb_error err{};
+};
+
+namespace biodb {
+
+// One sequential pass over the BGZF blocks of a reader: owns a CUDA stream and all buffers.
+struct Pass {
+  biodb_reader* r = nullptr;
+  cudaStream_t st = nullptr;
+  // position in the file
+  uint64_t next_coffset = 0;
+  uint32_t first_skip = 0;          // bytes of the first block that precede the first record
+  bool supplier_done = false;       // EOF block / end of file reached (inputstream.d:393-394)
+  biodb_error pending{};            // error to raise once the blocks before it are consumed
+  bool finished = false;
+  uint64_t n_records_total = 0;
+  // host staging
+  std::vector<BlockInfo> blocks;    // blocks of the current batch
+  PinBuf h_tab;                     // per-block tables (payload_off, out_off, cdata, isize, block_uoff)
+  PinBuf h_status, h_result;
+  // device
+  DevBuf d_comp, d_tab, d_status, d_u, d_carry_tail, d_ws, d_result;
+  DevBuf d_rec[10];                 // RecordArrays columns
+  uint64_t rec_capacity = 0, cigar_capacity = 0;
+  uint64_t rec_front = 0;           // slots reserved in front of the batch records (pileup carry)
+  // current slice
+  uint64_t u_len = 0;
+  uint64_t carry_tail_len = 0;      // bytes of a cut record carried into the next slice
+  std::vector<Seg> segs, next_segs;
+  uint64_t end_coffset_last = 0;
+  uint64_t n = 0, n_cigar = 0, tail = 0;
+  bool final_slice = false;
+  bool raw_mode = false;            // header pass: inflate only, no record scan, no carry
+
+  ~Pass();
+  biodb_status init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset);
+  // Inflate + scan the next batch.  BIODB_OK (n may be 0), BIODB_EOF, or an error.
+  biodb_status next(uint32_t max_blocks, uint64_t front_slots);
+  RecordArrays arrays(uint64_t front) const;
+  uint64_t voffset_of(uint64_t x) const;
+  biodb_status fail(int status, int zerr, uint64_t off, const std::string& msg);
+};
+
+int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, BlockInfo* b, biodb_error* e);
+
+}  // namespace biodb

@@ -1,0 +1,194 @@
+/*
+ * biod_b200.h — C ABI of libbiod_b200.so: BGZF inflate -> BAM record/CIGAR decode -> pileup on one B200.
+ *
+ * This is the drop-in boundary for BioD's hot path.  BioD's only existing FFI is libz
+ * (bio/core/utils/zlib.d:6-245, linked with -L-lz, Makefile:10); the D-side binding for this library
+ * sits next to it (see INTEGRATION.md and bindings/d/biod_b200.d) and feeds BioD's own range types:
+ *
+ *   biodb_open / biodb_open_memory        <- BamReader.this(string) / this(Stream)   bam/reader.d:100-138
+ *   biodb_header_text / biodb_n_refs ...  <- readSamHeader / readReferenceSequencesInfo  reader.d:579-597
+ *   biodb_reads_begin / _next / _end      <- BamReader.reads -> BamReadRange          reader.d:228-231,
+ *                                            readNext                                   readrange.d:118-173
+ *                                            (BGZF part: fillBgzfBufferFromStream       bgzf/inputstream.d:54-199,
+ *                                             decompressBgzfBlock                        bgzf/block.d:127-216)
+ *   biodb_pileup_begin / _next / _end     <- makePileup / pileupColumns / PileupRange   bam/pileup.d:683,509,295
+ *   biodb_dev_*                           <- the same three stages on caller-owned DEVICE buffers
+ *                                            (what bench.py's HBM-resident `value` times)
+ *
+ * Conventions: plain pointers and sizes only; every call returns a biodb_status; no exceptions, no
+ * callbacks into the host language.  One consumer thread per handle; any number of handles may be used
+ * concurrently (MultiBamReader opens N readers, bam/multireader.d:218).  All host arrays handed out are
+ * owned by the library (pinned host memory), stay valid until the next *_next call on the same iterator
+ * or its *_end, and are WRITABLE (BamRead's constructor flips bit 0 of the read-name NUL, read.d:495,880).
+ */
+#ifndef BIOD_B200_H
+#define BIOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum biodb_status {
+  BIODB_OK = 0,
+  BIODB_EOF = 1,            /* iterator exhausted (not an error) */
+  BIODB_ERR_BGZF = -1,      /* -> BgzfException            bgzf/inputstream.d:41-43,63-64 */
+  BIODB_ERR_ZLIB = -2,      /* -> ZlibException(errnum)    core/utils/zlib.d:247-274; errnum in biodb_error.zlib_errnum */
+  BIODB_ERR_FORMAT = -3,    /* -> Exception: "Invalid file format: expected BAM\1" reader.d:113; ISIZE>65536 block.d:150 */
+  BIODB_ERR_TRUNCATED = -4, /* -> ReadException from readExact on a cut record     readrange.d:169 */
+  BIODB_ERR_IO = -5,        /* open/read failure */
+  BIODB_ERR_CUDA = -6,      /* CUDA runtime failure, or no usable device: there is NO CPU fallback */
+  BIODB_ERR_CIGAR = -7,     /* PileupRead.assertCigarIndexIsValid pileup.d:224-228 */
+  BIODB_ERR_UNSORTED = -8,  /* pileup input not coordinate-sorted within a reference */
+  BIODB_ERR_ARG = -9,
+  BIODB_ERR_NOMEM = -10
+} biodb_status;
+
+typedef struct biodb_error {
+  int32_t status;        /* biodb_status of the failed call */
+  int32_t zlib_errnum;   /* Z_DATA_ERROR (-3) / Z_BUF_ERROR (-5) when status == BIODB_ERR_ZLIB */
+  uint64_t file_offset;  /* compressed offset of the BGZF block at fault, when known */
+  char message[256];     /* same text BioD puts in the exception */
+} biodb_error;
+
+typedef struct biodb_options {
+  int32_t device;            /* CUDA ordinal; -1 = current device */
+  int32_t blocks_per_batch;  /* BGZF blocks inflated per GPU batch; 0 = default (8192) */
+  int32_t verify_crc;        /* 1 = check each block's CRC32 on the device (debug builds of BioD assert it, block.d:187) */
+  int32_t want_offsets;      /* 1 = fill start/end virtual offsets (withOffsets policy, readrange.d:51-66) */
+  int32_t pin_input;         /* 1 = cudaHostRegister the caller's buffer in biodb_open_memory */
+  int32_t reserved[3];
+} biodb_options;
+
+typedef struct biodb_reader biodb_reader;
+typedef struct biodb_reads biodb_reads;
+typedef struct biodb_pileup biodb_pileup;
+
+/* ---- lifetime -------------------------------------------------------------------------------------- */
+const char* biodb_version(void);
+void biodb_default_options(biodb_options* o);
+/* Opens a BAM file (read into pinned host memory) and parses the header on the way: the header blocks
+ * are inflated ON THE DEVICE.  Errors in later blocks surface when iteration reaches them
+ * (test/unittests.d:139). */
+biodb_status biodb_open(const char* path, const biodb_options* opts, biodb_reader** out);
+/* Same over a caller-owned buffer (the MemoryStream case, bgzf/outputstream.d:233-242).  The buffer must
+ * outlive the reader. */
+biodb_status biodb_open_memory(const void* data, size_t len, const biodb_options* opts, biodb_reader** out);
+void biodb_close(biodb_reader* r);
+/* Last error of this reader / its iterators.  Never NULL. */
+const biodb_error* biodb_last_error(const biodb_reader* r);
+/* Error of a failed biodb_open* call (thread-local). */
+const biodb_error* biodb_open_error(void);
+
+/* ---- header (reader.d:150-215) ----------------------------------------------------------------------- */
+biodb_status biodb_header_text(const biodb_reader* r, const char** text, size_t* len);
+int32_t biodb_n_refs(const biodb_reader* r);
+biodb_status biodb_ref_info(const biodb_reader* r, int32_t i, const char** name, int32_t* name_len, int32_t* length);
+uint64_t biodb_reads_start_voffset(const biodb_reader* r);   /* reader.d:121-123 */
+uint64_t biodb_file_size(const biodb_reader* r);
+
+/* ---- records ------------------------------------------------------------------------------------------ */
+typedef struct biodb_record_batch {
+  uint64_t n;                  /* records in this batch */
+  uint64_t first_index;        /* file-order index of record 0 of the batch */
+  uint8_t* data;               /* raw uncompressed stream slice; record i = data[rec_off[i]+4 .. rec_off[i]+4+block_size[i]) */
+  uint64_t data_len;
+  const uint64_t* rec_off;     /* [n] offset of each record's 4-byte block_size prefix inside data */
+  const int32_t* block_size;   /* [n] */
+  const int32_t* ref_id;       /* [n]  read.d:85 */
+  const int32_t* pos;          /* [n]  read.d:93 */
+  const int32_t* end_pos;      /* [n]  position + basesCovered()  read.d:255-262,1380-1383 */
+  const uint32_t* bin_mq_nl;   /* [n]  bin<<16 | mapq<<8 | l_read_name   read.d:952-962 */
+  const uint32_t* flag_nc;     /* [n]  flag<<16 | n_cigar_op             read.d:963-968 */
+  const int32_t* l_seq;        /* [n] */
+  const uint64_t* cigar_off;   /* [n+1] into cigar */
+  const uint32_t* cigar;       /* packed len<<4|op words  cigar.d:58-148 */
+  const uint64_t* start_voffset; /* [n] or NULL unless options.want_offsets   readrange.d:38-48 */
+  const uint64_t* end_voffset;   /* [n] or NULL */
+} biodb_record_batch;
+
+/* Every call starts an independent pass over the file from the first record, like BamReader.reads
+ * (reader.d:228-231,553-569): any number may be alive and interleaved. */
+biodb_status biodb_reads_begin(biodb_reader* r, biodb_reads** out);
+/* BIODB_OK with a batch, BIODB_EOF at the end, or the error met at this point of the stream. */
+biodb_status biodb_reads_next(biodb_reads* it, biodb_record_batch* batch);
+void biodb_reads_end(biodb_reads* it);
+/* Progress in [0,1] by compressed bytes consumed (readsWithProgress, reader.d:233-279). */
+float biodb_reads_progress(const biodb_reads* it);
+
+/* ---- pileup -------------------------------------------------------------------------------------------- */
+typedef struct biodb_pileup_params {
+  int32_t single_ref;          /* 1 = makePileup (first reference only, pileup.d:490-494); 0 = pileupColumns */
+  int32_t skip_zero_coverage;  /* pileup.d:389-392 */
+  int32_t use_md_tag;          /* accepted; reference bases are reconstructed by the host binding (next row N1) */
+  int32_t want_query_offset;   /* 1 = also return PileupRead.query_offset per entry (pileup.d:146-149) */
+  uint64_t start_from;         /* pileup.d:482-489,497-504 (single_ref only) */
+  uint64_t end_at;             /* pileup.d:505 (single_ref only); UINT64_MAX = none */
+  int32_t counts_only;         /* 1 = per-column A,C,G,T,other,del counts instead of entries */
+  int32_t reserved[3];
+} biodb_pileup_params;
+
+typedef struct biodb_column_batch {
+  uint64_t n_columns;
+  uint64_t n_entries;
+  int32_t ref_id;              /* all columns of one batch lie on one reference (PileupColumn.ref_id, pileup.d:257-259) */
+  int32_t last_of_pileup;      /* 1 on the final batch */
+  const uint64_t* position;    /* [n_columns]   PileupColumn.position  pileup.d:262-264 */
+  const uint64_t* col_off;     /* [n_columns+1] entries of column c = [col_off[c], col_off[c+1]); coverage = difference */
+  const uint32_t* n_starting_here; /* [n_columns] reads_starting_here = last n entries  pileup.d:272-274 */
+  const uint32_t* read_idx;    /* [n_entries] file-order record index, column-major, file order inside a column */
+  const uint8_t* base;         /* [n_entries] current_base ('-' inside D/N)            pileup.d:115-122 */
+  const uint8_t* qual;         /* [n_entries] current_base_quality (255 inside D/N)    pileup.d:127-134 */
+  const uint32_t* query_offset;/* [n_entries] or NULL */
+  const uint32_t* counts;      /* [n_columns*6] A,C,G,T,other,deletion — only with counts_only */
+} biodb_column_batch;
+
+biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);
+biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols);
+void biodb_pileup_end(biodb_pileup* pl);
+/* Reference id of the pileup (AbstractPileup.ref_id, pileup.d:455-457); valid after the first _next. */
+int32_t biodb_pileup_ref_id(const biodb_pileup* pl);
+/* Totals over the whole pass so far (for benches and checks). */
+void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* n_columns, uint64_t* n_entries);
+
+/* ---- device-resident stage API (all pointers are DEVICE pointers; stream is a cudaStream_t) ------------- */
+/* Inflate n BGZF blocks.  Block i's raw-DEFLATE payload is comp[payload_off[i] .. +cdata_size[i]); its
+ * ISIZE bytes are written at out + out_off[i].  `comp` must be readable 32 bytes past the last payload.
+ * status[i] = 0, Z_DATA_ERROR (-3) or Z_BUF_ERROR (-5), matching inflate(Z_FINISH) of block.d:172.
+ * crc (may be NULL): when given, the CRC32 of each block's output is written there. */
+biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off, const uint32_t* cdata_size,
+                               const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
+                               int32_t* status, uint32_t* crc, void* stream);
+
+typedef struct biodb_dev_records {
+  uint64_t capacity;     /* in: room (records) in each array below */
+  uint64_t cigar_capacity;
+  uint64_t* rec_off;
+  int32_t* block_size;
+  int32_t* ref_id;
+  int32_t* pos;
+  int32_t* end_pos;
+  uint32_t* bin_mq_nl;
+  uint32_t* flag_nc;
+  int32_t* l_seq;
+  uint64_t* cigar_off;   /* [capacity+1] */
+  uint32_t* cigar;
+} biodb_dev_records;
+
+/* Walk the records of an uncompressed stream slice `u[0..u_len)` that starts at a record boundary.
+ * block_uoff[n_blocks+1] are the BGZF block boundaries inside u (used to walk blocks in parallel).
+ * On return (after the stream is synchronised) result[0] = number of complete records,
+ * result[1] = offset of the first byte not consumed (tail of a cut record), result[2] = cigar words,
+ * result[3] = 0 or a biodb_status (malformed record).  `final_slice` selects end-of-file semantics
+ * (readrange.d:139-150). */
+biodb_status biodb_dev_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t* block_uoff, uint32_t n_blocks,
+                                    int32_t final_slice, biodb_dev_records* out, uint64_t* result /* device, [4] */,
+                                    void* workspace, size_t workspace_bytes, void* stream);
+size_t biodb_dev_scan_workspace_bytes(uint32_t n_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIOD_B200_H */

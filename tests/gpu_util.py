@@ -1,0 +1,63 @@
+"""Shared helpers of the GPU parity tests: run the CUDA path through the C ABI and gather whole-file tables."""
+import numpy as np
+
+from biod_b200 import BamReader
+
+REC_FIELDS = ["block_size", "ref_id", "pos", "end_pos", "bin_mq_nl", "flag_nc", "l_seq"]
+
+
+def gpu_records(data, blocks_per_batch=0, want_offsets=True):
+    """Decode every record on the GPU.  Returns (reader, dict of whole-file arrays, list of raw record bytes)."""
+    rd = BamReader(data, blocks_per_batch=blocks_per_batch, want_offsets=want_offsets)
+    cols = {f: [] for f in REC_FIELDS + ["start_voffset", "end_voffset", "n_cigar_rec"]}
+    cigar, raws = [], []
+    err = None
+    try:
+        for b in rd.read_batches(copy=True):
+            for f in REC_FIELDS:
+                cols[f].append(getattr(b, f))
+            cols["start_voffset"].append(b.start_voffset)
+            cols["end_voffset"].append(b.end_voffset)
+            cols["n_cigar_rec"].append(np.diff(b.cigar_off).astype(np.uint64))
+            cigar.append(b.cigar)
+            for i in range(b.n):
+                o = int(b.rec_off[i]) + 4
+                raws.append(b.data[o:o + int(b.block_size[i])].tobytes())
+    except Exception as e:  # noqa: BLE001 - the tests look at the class
+        err = e
+    out = {k: (np.concatenate(v) if v else np.zeros(0)) for k, v in cols.items()}
+    out["cigar"] = np.concatenate(cigar) if cigar else np.zeros(0, dtype=np.uint32)
+    return rd, out, raws, err
+
+
+def gpu_pileup(data, single_ref, blocks_per_batch=0, **kw):
+    rd = BamReader(data, blocks_per_batch=blocks_per_batch)
+    pos, ref, cov, nstart, ridx, base, qual, qoff = [], [], [], [], [], [], [], []
+    for b in rd.column_batches(single_ref, want_query_offset=True, copy=True, **kw):
+        pos.append(b.position)
+        ref.append(np.full(b.n_columns, b.ref_id, dtype=np.int32))
+        cov.append(np.diff(b.col_off).astype(np.uint64))
+        nstart.append(b.n_starting_here)
+        ridx.append(b.read_idx)
+        base.append(b.base)
+        qual.append(b.qual)
+        qoff.append(b.query_offset)
+    cat = lambda v, dt: np.concatenate(v) if v else np.zeros(0, dtype=dt)  # noqa: E731
+    cov = cat(cov, np.uint64)
+    return dict(col_pos=cat(pos, np.uint64), col_ref=cat(ref, np.int32), cov=cov,
+                col_off=np.concatenate([[0], np.cumsum(cov)]).astype(np.uint64), n_start=cat(nstart, np.uint32),
+                read_idx=cat(ridx, np.uint32), base=cat(base, np.uint8), qual=cat(qual, np.uint8),
+                qoff=cat(qoff, np.uint32))
+
+
+def assert_pileup_equal(g, o):
+    """g: gpu_pileup dict, o: oracle.Pileup"""
+    assert len(g["col_pos"]) == o.n_columns, (len(g["col_pos"]), o.n_columns)
+    assert np.array_equal(g["col_pos"], o.col_pos)
+    assert np.array_equal(g["col_ref"], o.col_ref)
+    assert np.array_equal(g["col_off"], o.col_off)
+    assert np.array_equal(g["n_start"], o.n_start)
+    assert np.array_equal(g["read_idx"], o.read_idx)
+    assert np.array_equal(g["base"], o.base)
+    assert np.array_equal(g["qual"], o.qual)
+    assert np.array_equal(g["qoff"], o.qoff)

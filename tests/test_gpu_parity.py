@@ -1,0 +1,244 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import fixture_bytes
+from bamutil import bam_record, make_bam, tag_z
+from gpu_util import REC_FIELDS, assert_pileup_equal, gpu_pileup, gpu_records
+from oracle import oracle as orc
+from test_oracle_golden import CIGARS, MDS, POSITIONS, SEQS, pileup_vector_bam
+
+pytestmark = pytest.mark.gpu
+
+VALID = ["ex1_header.bam", "illu_20_chunk.bam", "bins.bam", "tags.bam", "b7_295_chunk.bam", "mg1655_chunk.bam",
+         "ion_20_chunk.bam", "long_header.bam"]
+
+
+def check_records(data, bpb):
+    o = orc.Bam(data).decode()
+    rd, g, raws, err = gpu_records(data, blocks_per_batch=bpb)
+    assert err is None, err
+    assert rd.header_text == o.header_text
+    assert [r.name for r in rd.reference_sequences] == o.ref_names
+    assert [r.length for r in rd.reference_sequences] == o.ref_lens
+    assert rd.reads_start_voffset == o.reads_start_voffset
+    assert len(raws) == o.n_records
+    for f in REC_FIELDS:
+        exp = getattr(o, f) if hasattr(o, f) else None
+        if f == "bin_mq_nl":
+            exp = (o.bin.astype(np.uint32) << 16) | (o.mapq.astype(np.uint32) << 8) | o.l_read_name
+        if f == "flag_nc":
+            exp = (o.flag.astype(np.uint32) << 16) | o.n_cigar
+        assert np.array_equal(g[f], exp), f
+    assert np.array_equal(g["cigar"], o.cigar)
+    assert np.array_equal(g["n_cigar_rec"], np.diff(o.cigar_off))
+    assert np.array_equal(g["start_voffset"], o.start_vo)
+    assert np.array_equal(g["end_voffset"], o.end_vo)
+    for i, raw in enumerate(raws):
+        assert raw == o.record_bytes(i).tobytes(), i
+    return o
+
+
+@pytest.mark.parametrize("name", VALID)
+@pytest.mark.parametrize("bpb", [0, 3, 1])
+def test_records_match_oracle(name, bpb):
+    check_records(fixture_bytes(name), bpb)
+
+
+@pytest.mark.parametrize("name", VALID[:-1])
+@pytest.mark.parametrize("bpb", [0, 2])
+def test_pileup_columns_match_oracle(name, bpb):
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    assert_pileup_equal(gpu_pileup(data, False, bpb), o.pileup_columns())
+    assert_pileup_equal(gpu_pileup(data, True, bpb), o.make_pileup())
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "bins.bam"])
+def test_pileup_with_zero_coverage_columns(name):
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    assert_pileup_equal(gpu_pileup(data, False, 2, skip_zero_coverage=False), o.pileup_columns(False))
+    assert_pileup_equal(gpu_pileup(data, True, 3, skip_zero_coverage=False), o.make_pileup(0, 2**64 - 1, False))
+
+
+def test_ex1_pins_on_gpu():
+    # test/unittests.d:303, :334-367 through the CUDA path itself
+    data = fixture_bytes("ex1_header.bam")
+    g = gpu_pileup(data, False)
+    assert int((g["col_ref"] == 0).sum()) == 1470 and int((g["col_ref"] == 1).sum()) == 1567
+    assert g["col_pos"][0] == 99
+    rd, rec, raws, err = gpu_records(data)
+    assert err is None and len(raws) == 3270
+
+
+def test_pileup_unit_vector_on_gpu():
+    # bam/pileup.d:776-825
+    data = pileup_vector_bam()
+    o = orc.Bam(data).decode()
+    for bpb in (0, 1):
+        assert_pileup_equal(gpu_pileup(data, True, bpb, start_from=796, end_at=849, skip_zero_coverage=False),
+                            o.make_pileup(796, 849, False))
+        full = gpu_pileup(data, True, bpb, skip_zero_coverage=False)
+        assert_pileup_equal(full, o.make_pileup(0, 2**64 - 1, False))
+    col = {int(p): c for c, p in enumerate(full["col_pos"])}
+
+    def bases(p):
+        a, b = int(full["col_off"][col[p]]), int(full["col_off"][col[p] + 1])
+        return full["base"][a:b].tobytes().decode()
+
+    assert bases(796) == "CCCCCCAC" and bases(805) == "TCCCCCCCC" and bases(806) == "AAAAAAAGA"
+    assert bases(821) == "AAGG-AA" and bases(826) == "CCCCCC" and bases(849) == "TAT"
+
+
+@pytest.mark.parametrize("start,end", [(0, 2**64 - 1), (500, 900), (1000, 1001), (99, 100), (5000, 6000), (0, 99)])
+@pytest.mark.parametrize("skip", [True, False])
+def test_make_pileup_ranges(start, end, skip):
+    data = fixture_bytes("ex1_header.bam")
+    o = orc.Bam(data).decode()
+    for bpb in (0, 2):
+        assert_pileup_equal(gpu_pileup(data, True, bpb, start_from=start, end_at=end, skip_zero_coverage=skip),
+                            o.make_pileup(start, end, skip))
+
+
+@pytest.mark.parametrize("name,cls", [
+    ("duplicated_block_size.bam", "BgzfException"), ("no_block_size.bam", "BgzfException"),
+    ("wrong_extra_gzip_length.bam", "BgzfException"), ("wrong_bc_subfield_length.bam", "BgzfException"),
+    ("corrupted_zlib_archive.bam", "ZlibException")])
+def test_corrupted_files_raise_the_pinned_classes(name, cls):
+    # test/unittests.d:132-142
+    data = fixture_bytes(name)
+    with pytest.raises(orc.OracleError) as oe:
+        orc.Bam(data).decode()
+    try:
+        rd, g, raws, err = gpu_records(data, blocks_per_batch=2)
+    except Exception as e:  # noqa: BLE001  raised by the constructor
+        err, raws = e, []
+    assert err is not None and type(err).__name__ == cls
+    if cls == "BgzfException":
+        assert str(err) == oe.value.msg
+    else:
+        assert err.errnum == oe.value.zerr == -3
+    # records ahead of the fault are still delivered, exactly as many as the oracle sees
+    ob = None
+    try:
+        ob = orc.Bam(data).decode(raise_on_error=False)
+    except orc.OracleError:
+        pass
+    if ob is not None:
+        assert len(raws) == ob.n_records
+
+
+def synthetic(n=3000, seed=7, refs=(("chrA", 100000), ("chrB", 50000)), indel=True):
+    rng = np.random.default_rng(seed)
+    recs, k = [], 0
+    for rid, (_, ln) in enumerate(refs):
+        pos = 0
+        for _ in range(n // len(refs)):
+            pos += int(rng.geometric(0.2)) - 1
+            L = int(rng.integers(30, 151))
+            seq = "".join("ACGTN"[i] for i in rng.choice(5, L, p=[.24, .24, .24, .24, .04]))
+            qual = bytes(rng.integers(2, 42, L).tolist())
+            cig = f"{L}M"
+            r = rng.random()
+            if indel and r < 0.5 and L > 40:
+                a = int(rng.integers(5, L - 20))
+                kind = rng.integers(0, 6)
+                if kind == 0:
+                    x = int(rng.integers(1, 10)); cig = f"{a}M{x}I{L - a - x}M"
+                elif kind == 1:
+                    x = int(rng.integers(1, 10)); cig = f"{a}M{x}D{L - a}M"
+                elif kind == 2:
+                    x = int(rng.integers(50, 400)); cig = f"{a}M{x}N{L - a}M"
+                elif kind == 3:
+                    x = int(rng.integers(1, 15)); cig = f"{x}S{L - x}M"
+                elif kind == 4:
+                    x = int(rng.integers(1, 15)); cig = f"3H{L - x}M{x}S"
+                else:
+                    cig = f"{a}={1}X{L - a - 1}M2P"
+            flag = 0
+            if rng.random() < 0.03:
+                flag, cig = 4, "*" if rng.random() < 0.5 else cig
+            if cig == "*":
+                cig = ""
+            recs.append(bam_record(f"q{k}", seq, cig, pos, ref_id=rid, flag=flag, qual=qual,
+                                   mapq=int(rng.integers(0, 61)), tags=tag_z("XX", "y" * int(rng.integers(0, 30)))))
+            k += 1
+    return list(refs), recs
+
+
+@pytest.mark.parametrize("straddle", [False, True])
+@pytest.mark.parametrize("level", [0, 1, 6, 9])
+def test_synthetic_mixed_cigar(straddle, level):
+    refs, recs = synthetic()
+    data = make_bam(refs, recs, level=level, straddle=straddle, block_size=0xFF00 if not straddle else 4000)
+    o = check_records(data, 5)
+    for skip in (True, False):
+        assert_pileup_equal(gpu_pileup(data, False, 3, skip_zero_coverage=skip), o.pileup_columns(skip))
+    assert_pileup_equal(gpu_pileup(data, True, 2, start_from=1234, end_at=40000), o.make_pileup(1234, 40000))
+
+
+def test_empty_and_headers_only():
+    data = make_bam([("c", 10)], [])
+    rd, g, raws, err = gpu_records(data)
+    assert err is None and raws == []
+    assert gpu_pileup(data, False)["col_pos"].size == 0
+    # a file that is only an EOF block is not a BAM (reader.d:113)
+    from bamutil import BGZF_EOF
+    with pytest.raises(Exception) as ei:
+        gpu_records(BGZF_EOF)
+    assert type(ei.value).__name__ == "BamFormatException"
+
+
+def test_stream_stops_at_first_empty_block():
+    # inputstream.d:393-394: an ISIZE==0 block in the middle silently ends the read range
+    from bamutil import BGZF_EOF, bam_header, bgzf_block
+    refs, recs = synthetic(200, indel=False)
+    hdr = bam_header("@HD\tVN:1.6\n", refs)
+    data = bgzf_block(hdr) + bgzf_block(b"".join(recs[:100])) + BGZF_EOF + bgzf_block(b"".join(recs[100:])) + BGZF_EOF
+    o = orc.Bam(data).decode()
+    assert o.n_records == 100
+    rd, g, raws, err = gpu_records(data)
+    assert err is None and len(raws) == 100
+
+
+def test_truncated_record_raises_read_exception():
+    from bamutil import bam_header, bgzf_block, BGZF_EOF
+    refs, recs = synthetic(50, indel=False)
+    hdr = bam_header("@HD\tVN:1.6\n", refs)
+    body = b"".join(recs)
+    data = bgzf_block(hdr) + bgzf_block(body[:-20]) + BGZF_EOF
+    o = orc.Bam(data).decode(raise_on_error=False)
+    assert o.status == orc.ERR_TRUNC
+    rd, g, raws, err = gpu_records(data)
+    assert type(err).__name__ == "ReadException" and len(raws) == o.n_records
+    # fewer than 4 stray bytes end the range silently (readrange.d:139-150)
+    data = bgzf_block(hdr) + bgzf_block(body + b"\x01\x02") + BGZF_EOF
+    rd, g, raws, err = gpu_records(data)
+    assert err is None and len(raws) == len(recs)
+
+
+def test_independent_interleaved_passes():
+    # every bam.reads call is a fresh pass (reader.d:228-231); examples/make_pileup.d iterates four times
+    from biod_b200 import BamReader
+    data = fixture_bytes("ex1_header.bam")
+    rd = BamReader(data, blocks_per_batch=2)
+    a, b = rd.reads(), rd.reads()
+    names_a, names_b = [], []
+    for _ in range(1000):
+        names_a.append(next(a).name)
+    for _ in range(500):
+        names_b.append(next(b).name)
+    assert names_a[:500] == names_b
+    assert sum(1 for _ in rd.reads()) == 3270
+
+
+def test_make_pileup_example_invariant_on_gpu():
+    # examples/make_pileup.d:20-30
+    from biod_b200 import BamReader, makePileup
+    data = fixture_bytes("illu_20_chunk.bam")
+    bam = BamReader(data)
+    starting = []
+    for column in makePileup(bam, True):
+        starting += column.reads_starting_here.tolist()
+    assert starting == list(range(29))
