@@ -204,7 +204,9 @@ __device__ __forceinline__ Entry cursor_at(const uint8_t* rec, uint32_t lname, u
           en.base = (uint8_t)"=ACMGRSVTWYHKDBN"[code];
           en.qual = __ldg(ql + qoff);
         } else {
-          en.bad = true;
+          // SEQ shorter than the CIGAR says (e.g. SEQ '*'): BioD's lazy accessor would raise a RangeError only
+          // if asked for this base; the eager builder marks it with base 0x00 / quality 255 instead.
+          en.base = 0;
         }
       }
       break;

@@ -511,9 +511,12 @@ struct PileupSim {
           uint8_t code = (c.qoff & 1) ? (byte & 0xF) : (byte >> 4);
           base = (uint8_t)"=ACMGRSVTWYHKDBN"[code];      // bio/core/base.d:85
           q = ql[c.qoff];                                // read.d:468-470
-        } else if (!out->status) {
-          out->status = ORC_ERR_CIGAR;                   // RangeError in D
-          out->msg = "query offset beyond sequence (record " + std::to_string(c.read) + ")";
+        } else {
+          // sequence[query_offset] past l_seq (e.g. SEQ '*' with a CIGAR, as in bins.bam) is a RangeError
+          // in D — but only if the consumer asks for the base; building the column never touches it.
+          // Restatement-defined for an eager builder: base 0x00, quality 255, no error.
+          base = 0;
+          q = 255;
         }
       }
       out->read_idx.push_back(c.read);
