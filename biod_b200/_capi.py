@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbiod_b200.so")
+LIB_PATH = os.environ.get("BIODB_LIB") or os.path.join(_HERE, "libbiod_b200.so")   # BIODB_LIB: kernel-variant experiments
 
 OK, EOF = 0, 1
 ERR_BGZF, ERR_ZLIB, ERR_FORMAT, ERR_TRUNCATED, ERR_IO, ERR_CUDA, ERR_CIGAR, ERR_UNSORTED, ERR_ARG, ERR_NOMEM = \
@@ -23,7 +23,8 @@ class Error(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("blocks_per_batch", C.c_int32), ("verify_crc", C.c_int32),
-                ("want_offsets", C.c_int32), ("pin_input", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("want_offsets", C.c_int32), ("pin_input", C.c_int32), ("resident_input", C.c_int32),
+                ("device_output", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class RecordBatch(C.Structure):
@@ -31,6 +32,13 @@ class RecordBatch(C.Structure):
                 ("rec_off", u64p), ("block_size", i32p), ("ref_id", i32p), ("pos", i32p), ("end_pos", i32p),
                 ("bin_mq_nl", u32p), ("flag_nc", u32p), ("l_seq", i32p), ("cigar_off", u64p), ("cigar", u32p),
                 ("start_voffset", u64p), ("end_voffset", u64p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("total_ms", C.c_double), ("inflate_ms", C.c_double), ("scan_ms", C.c_double), ("pileup_ms", C.c_double),
+                ("inflate_launches", C.c_uint64), ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("compressed_bytes", C.c_uint64), ("uncompressed_bytes", C.c_uint64),
+                ("n_blocks", C.c_uint64), ("n_records", C.c_uint64)]
 
 
 class PileupParams(C.Structure):
@@ -92,6 +100,8 @@ def lib():
     L.biodb_pileup_ref_id.restype = C.c_int32
     L.biodb_pileup_ref_id.argtypes = [vp]
     L.biodb_pileup_totals.argtypes = [vp, u64p, u64p, u64p]
+    L.biodb_reads_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.biodb_pileup_stats.argtypes = [vp, C.POINTER(Stats)]
     L.biodb_dev_inflate.restype = C.c_int
     L.biodb_dev_inflate.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp]
     L.biodb_dev_scan_workspace_bytes.restype = C.c_size_t
@@ -107,5 +117,6 @@ EXPORTS = [
     "biodb_open_error", "biodb_header_text", "biodb_n_refs", "biodb_ref_info", "biodb_reads_start_voffset",
     "biodb_file_size", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
+    "biodb_reads_stats", "biodb_pileup_stats",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes",
 ]

@@ -27,39 +27,75 @@ namespace biodb {
 
 namespace {
 
-constexpr int IN_HALF = 2048;             // bytes per TMA chunk
+#ifndef BIODB_IN_HALF
+#define BIODB_IN_HALF 1024
+#endif
+#ifndef BIODB_OUT_RING
+#define BIODB_OUT_RING 4096
+#endif
+constexpr int IN_HALF = BIODB_IN_HALF;    // bytes per TMA chunk
 constexpr int IN_RING = 2 * IN_HALF;
 constexpr int IN_WORDS = IN_RING / 4;
 constexpr int IN_HALF_WORDS = IN_HALF / 4;
-constexpr int OUT_RING = 8192;
+constexpr int OUT_RING = BIODB_OUT_RING;
 constexpr uint32_t OMASK = OUT_RING - 1;
-constexpr int RING_VALID = OUT_RING - 320;  // any source byte this close to opos is still in the ring
 constexpr int FLUSH = 512;
+// bytes that may sit in the ring not yet flushed: < 2*FLUSH + one match (258) + one literal run (<= 54)
+constexpr int MAX_PENDING = 2 * FLUSH + 258 + 64;
+constexpr int RING_VALID = OUT_RING - MAX_PENDING - 64;  // any source byte this close to opos is still in the ring
+static_assert(RING_VALID >= 1024, "output ring too small");
 constexpr int LIT_BITS = 10;
 constexpr int DIST_BITS = 8;
 constexpr int CL_BITS = 7;
 
-constexpr uint32_t ENT_SLOW = 0x30u;      // kind 3, code length 0 -> canonical slow path
-constexpr uint32_t ENT_INVALID = 0x130u;  // kind 3, flag -> invalid code
+// LUT entry layout (u32).  litlen: [0,8) literal byte | [8,10) kind | [10,19) length base | [19,22) extra bits |
+// [28,32) code length.  dist: [0,2) kind | [8,23) distance base | [24,28) extra bits | [28,32) code length.
+// code-length code: [8,13) symbol | [28,32) code length.
+constexpr uint32_t K_LIT = 0, K_LEN = 1, K_EOB = 2, K_SPECIAL = 3;
+constexpr uint32_t ENT_SLOW = K_SPECIAL << 8;                 // code longer than the LUT index: canonical slow path
+constexpr uint32_t ENT_INVALID = (K_SPECIAL << 8) | (1u << 10);
+constexpr uint32_t DENT_SLOW = K_SPECIAL;
+constexpr uint32_t DENT_INVALID = K_SPECIAL | (1u << 8);
 constexpr int Z_DATA = -3;
 constexpr int Z_BUF = -5;
 
 enum { KIND_LITLEN = 0, KIND_DIST = 1, KIND_CODELEN = 2 };
 
 struct __align__(16) WarpSmem {
-  uint32_t in_ring[IN_WORDS];          // 4096
-  uint8_t out_ring[OUT_RING];          // 8192
+  uint32_t in_ring[IN_WORDS];
+  uint8_t out_ring[OUT_RING];
   uint32_t lut_lit[1 << LIT_BITS];     // 4096
   uint32_t lut_dist[1 << DIST_BITS];   // 1024 (also hosts the 128-entry code-length LUT)
   uint16_t sorted_lit[288];
   uint16_t sorted_dist[32];
   uint16_t cnt_lit[16];
   uint16_t cnt_dist[16];
-  uint8_t lens[352];                  // [0,19) code-length code, [32,32+316) litlen+dist lengths
+  uint8_t lens[352];                   // [0,19) code-length code, [32,32+316) litlen+dist lengths
   unsigned long long mbar[2];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// explicit shared-space accesses with a 32-bit address: keeps ptxas from rebuilding the shared-window base
+// (S2R SR_CgaCtaId + LEA) inside the hot loop
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -95,24 +131,26 @@ __device__ __forceinline__ uint32_t len_entry(int s /*0..28*/, int cl) {
   if (s < 8) { base = 3 + s; eb = 0; }
   else if (s == 28) { base = 258; eb = 0; }
   else { eb = (uint32_t)(s - 4) >> 2; base = 3 + ((4u + ((s - 4) & 3)) << eb); }
-  return (uint32_t)cl | (1u << 4) | (base << 8) | (eb << 20);
+  return ((uint32_t)cl << 28) | (K_LEN << 8) | (base << 10) | (eb << 19);
 }
 __device__ __forceinline__ uint32_t dist_entry(int d /*0..29*/, int cl) {
   uint32_t base, eb;
   if (d < 4) { base = 1 + d; eb = 0; }
   else { eb = (uint32_t)(d - 2) >> 1; base = 1 + ((2u + (d & 1)) << eb); }
-  return (uint32_t)cl | (base << 8) | (eb << 24);
+  return ((uint32_t)cl << 28) | (base << 8) | (eb << 24);
 }
 __device__ __forceinline__ uint32_t make_entry(int kind, int sym, int cl) {
   if (kind == KIND_LITLEN) {
-    if (sym < 256) return (uint32_t)cl | ((uint32_t)sym << 8);
-    if (sym == 256) return (uint32_t)cl | (2u << 4);
+    if (sym < 256) return ((uint32_t)cl << 28) | (uint32_t)sym;
+    if (sym == 256) return ((uint32_t)cl << 28) | (K_EOB << 8);
     if (sym > 285) return ENT_INVALID;            // 286/287 exist only in the fixed code and are invalid
     return len_entry(sym - 257, cl);
   }
-  if (kind == KIND_DIST) return sym > 29 ? ENT_INVALID : dist_entry(sym, cl);
-  return (uint32_t)cl | ((uint32_t)sym << 8);     // code-length code
+  if (kind == KIND_DIST) return sym > 29 ? DENT_INVALID : dist_entry(sym, cl);
+  return ((uint32_t)cl << 28) | ((uint32_t)sym << 8);     // code-length code
 }
+__device__ __forceinline__ uint32_t slow_marker(int kind) { return kind == KIND_DIST ? DENT_SLOW : ENT_SLOW; }
+__device__ __forceinline__ uint32_t invalid_marker(int kind) { return kind == KIND_DIST ? DENT_INVALID : ENT_INVALID; }
 
 // Warp-cooperative canonical-Huffman table build (RFC 1951 §3.2.2).
 // Returns 0 ok, 1 = empty code (LUT all-invalid), -1 = over-subscribed / incomplete set.
@@ -136,7 +174,7 @@ __device__ int build_table(const uint8_t* lens, int n, uint32_t* lut, uint16_t* 
     if (cnt[len]) maxlen = len;
   }
   if (over) return -1;
-  for (int i = lane; i < (1 << PB); i += 32) lut[i] = ENT_INVALID;
+  for (int i = lane; i < (1 << PB); i += 32) lut[i] = invalid_marker(kind);
   if (lane < 16) cnt_out[lane] = 0;
   __syncwarp();
   if (maxlen == 0) return 1;
@@ -184,7 +222,7 @@ __device__ int build_table(const uint8_t* lens, int n, uint32_t* lut, uint16_t* 
         uint32_t e = make_entry(kind, sym, l);
         for (uint32_t i = rev; i < (1u << PB); i += (1u << l)) lut[i] = e;
       } else {
-        lut[rev & ((1u << PB) - 1)] = ENT_SLOW;
+        lut[rev & ((1u << PB) - 1)] = slow_marker(kind);
       }
     }
   }
@@ -206,7 +244,7 @@ __device__ __forceinline__ uint32_t slow_decode(uint64_t bitbuf, const uint16_t*
     first <<= 1;
     code <<= 1;
   }
-  return ENT_INVALID;
+  return invalid_marker(kind);
 }
 
 struct Decoder {
@@ -240,8 +278,8 @@ struct Decoder {
 }  // namespace
 
 __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  WarpSmem* s = reinterpret_cast<WarpSmem*>(smem_raw);
+  __shared__ WarpSmem sm;
+  WarpSmem* s = &sm;
   const int lane = threadIdx.x;
   const uint32_t blk = blockIdx.x;
   if (blk >= a.n_blocks) return;
@@ -285,8 +323,12 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
   const uint64_t total_bits = (uint64_t)csize * 8;
   const uint32_t skip_bits = skip * 8;
   int status = 0;
-  uint32_t opos = 0;       // bytes produced
-  uint32_t flushed = 0;    // bytes already stored to HBM
+  uint32_t o = oa;          // oa + bytes produced: ring index is (o & OMASK)
+  uint32_t flushed = 0;     // bytes already stored to HBM
+  const uint32_t ring = smem_u32(s->out_ring);
+  const uint32_t lutl = smem_u32(s->lut_lit);
+  const uint32_t lutd = smem_u32(s->lut_dist);
+#define OPOS() (o - oa)
 
   // pull one 32-bit word from the staging ring (warp-uniform)
   auto pull = [&]() {
@@ -316,20 +358,30 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
     uint32_t head = (16 - ((oa + f) & 15)) & 15;
     if (head > fe - f) head = fe - f;
     if (head) {
-      if ((uint32_t)lane < head) gout[f + lane] = s->out_ring[(oa + f + lane) & OMASK];
+      if ((uint32_t)lane < head) gout[f + lane] = (uint8_t)lds8(ring + ((oa + f + lane) & OMASK));
       f += head;
     }
     uint32_t n16 = (fe - f) >> 4;
     for (uint32_t i = lane; i < n16; i += 32) {
-      uint4 v = *reinterpret_cast<const uint4*>(&s->out_ring[(oa + f + 16 * i) & OMASK]);
-      *reinterpret_cast<uint4*>(gout + f + 16 * i) = v;
+      uint4 v = lds128(ring + ((oa + f + 16 * i) & OMASK));
+      __stcs(reinterpret_cast<uint4*>(gout + f + 16 * i), v);
     }
     f += n16 << 4;
     uint32_t tail = fe - f;
-    if ((uint32_t)lane < tail) gout[f + lane] = s->out_ring[(oa + f + lane) & OMASK];
+    if ((uint32_t)lane < tail) gout[f + lane] = (uint8_t)lds8(ring + ((oa + f + lane) & OMASK));
     flushed = fe;
     __syncwarp();
   };
+  // flush whole 512-byte granules once two are pending; an overrun of ISIZE ends the block (Z_BUF_ERROR)
+#define MAYBE_FLUSH()                                                  \
+  do {                                                                 \
+    if (OPOS() - flushed >= 2 * FLUSH) {                               \
+      if (OPOS() > isize) { status = Z_BUF; break; }                   \
+      __syncwarp();                                                    \
+      uint32_t fe_ = OPOS() - (o & (FLUSH - 1));                       \
+      if (fe_ > flushed) flush_to(fe_);                                \
+    }                                                                  \
+  } while (0)
 
   bool last = false;
   while (!last && status == 0) {
@@ -350,22 +402,17 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
       DROP(32);
       if ((len ^ 0xffff) != nlen) { status = Z_DATA; break; }
       if ((uint64_t)len * 8 + CONSUMED() > total_bits) { status = Z_BUF; break; }   // input runs out first ...
-      if (opos + len > isize) { status = Z_BUF; break; }                            // ... or the output does
+      if (OPOS() + len > isize) { status = Z_BUF; break; }                          // ... or the output does
       uint32_t left = len;
-      while (left) {
+      while (left && status == 0) {
         REFILL();
         uint32_t take = left < 4 ? left : 4;
-        if ((uint32_t)d.bitcnt < take * 8) { REFILL(); }
         uint32_t v = (uint32_t)d.bitbuf;
-        if ((uint32_t)lane < take) s->out_ring[(oa + opos + lane) & OMASK] = (uint8_t)(v >> (8 * lane));
+        if ((uint32_t)lane < take) sts8(ring + ((o + lane) & OMASK), v >> (8 * lane));
         DROP((int)take * 8);
-        opos += take;
+        o += take;
         left -= take;
-        if (opos - flushed >= 2 * FLUSH) {
-          __syncwarp();
-          uint32_t fe = opos - ((oa + opos) & (FLUSH - 1));
-          if (fe > flushed) flush_to(fe);
-        }
+        MAYBE_FLUSH();
       }
       __syncwarp();
       continue;
@@ -418,8 +465,8 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
       while (idx < total) {
         REFILL();
         uint32_t e = cl_lut[d.bitbuf & ((1u << CL_BITS) - 1)];
-        if ((e >> 4) & 3) { status = Z_DATA; break; }   // unused code of an (impossible here) incomplete set
-        int cl = e & 15;
+        int cl = e >> 28;
+        if (cl == 0) { status = Z_DATA; break; }         // unused code of an (impossible here) incomplete set
         int sym = (e >> 8) & 31;
         DROP(cl);
         if (sym < 16) {
@@ -462,103 +509,118 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
 
     // ---- symbol loop ---------------------------------------------------------------------
     while (true) {
-      REFILL();
-      uint32_t e = s->lut_lit[d.bitbuf & ((1u << LIT_BITS) - 1)];
-      if ((e & 0x3f) == ENT_SLOW) {
+      REFILL();                       // >= 33 valid bits
+      MAYBE_FLUSH();
+      if (status) break;
+      uint32_t e;
+      // literal fast loop on the low 32 bits of the bit buffer: every lane stores the same byte to the same ring
+      // slot (one shared-memory wavefront); it runs while at least LIT_BITS of the 32 bits are unread
+      {
+        uint32_t lo = (uint32_t)d.bitbuf, used = 0;
+        while (true) {
+          e = lds32(lutl + ((lo << 2) & (((1u << LIT_BITS) - 1) << 2)));
+          if (e & (3u << 8)) break;     // not a literal
+          sts8(ring + (o & OMASK), e);
+          ++o;
+          const uint32_t cl = e >> 28;
+          lo >>= cl;
+          used += cl;
+          if (used > 32 - LIT_BITS) break;
+        }
+        DROP(used);
+      }
+      if ((e & (3u << 8)) == 0) continue;   // ran low on bits after a literal
+      if (((e >> 8) & 3) == K_SPECIAL) {
+        REFILL();
         if (e == ENT_SLOW) e = slow_decode(d.bitbuf, s->cnt_lit, s->sorted_lit, KIND_LITLEN);
-        if ((e & 0x3f) == ENT_SLOW) {   // invalid code
+        if (((e >> 8) & 3) == K_SPECIAL) {   // invalid code
+          status = (CONSUMED() + 1 > total_bits) ? Z_BUF : Z_DATA;
+          break;
+        }
+        if (((e >> 8) & 3) == K_LIT) {       // a literal with a long code
+          sts8(ring + (o & OMASK), e);
+          ++o;
+          DROP(e >> 28);
+          continue;
+        }
+      }
+      DROP(e >> 28);
+      const uint32_t kind = (e >> 8) & 3;
+      if (kind == K_EOB) break;
+      // ---- length / distance pair ---------------------------------------------------------
+      REFILL();                       // the literal run may have left fewer bits than the extra bits need
+      const uint32_t eb = (e >> 19) & 7;
+      const uint32_t len = ((e >> 10) & 0x1ff) + ((uint32_t)d.bitbuf & ((1u << eb) - 1));
+      DROP((int)eb);
+      REFILL();
+      uint32_t e2 = lds32(lutd + (((uint32_t)d.bitbuf << 2) & (((1u << DIST_BITS) - 1) << 2)));
+      if ((e2 & 3) == K_SPECIAL) {
+        if (e2 == DENT_SLOW) e2 = slow_decode(d.bitbuf, s->cnt_dist, s->sorted_dist, KIND_DIST);
+        if ((e2 & 3) == K_SPECIAL) {
           status = (CONSUMED() + 1 > total_bits) ? Z_BUF : Z_DATA;
           break;
         }
       }
-      int cl = e & 15;
-      DROP(cl);
-      uint32_t kind = (e >> 4) & 3;
-      if (kind == 0) {
-        // literal
-        if (opos >= isize) { status = Z_BUF; break; }
-        s->out_ring[(oa + opos) & OMASK] = (uint8_t)(e >> 8);
-        ++opos;
-      } else if (kind == 1) {
-        uint32_t eb = (e >> 20) & 7;
-        uint32_t len = ((e >> 8) & 0x1ff) + ((uint32_t)d.bitbuf & ((1u << eb) - 1));
-        DROP((int)eb);
-        REFILL();
-        uint32_t e2 = s->lut_dist[d.bitbuf & ((1u << DIST_BITS) - 1)];
-        if ((e2 & 0x3f) == ENT_SLOW) {
-          if (e2 == ENT_SLOW) e2 = slow_decode(d.bitbuf, s->cnt_dist, s->sorted_dist, KIND_DIST);
-          if ((e2 & 0x3f) == ENT_SLOW) {
-            status = (CONSUMED() + 1 > total_bits) ? Z_BUF : Z_DATA;
-            break;
-          }
-        }
-        int cl2 = e2 & 15;
-        DROP(cl2);
-        uint32_t eb2 = (e2 >> 24) & 15;
-        uint32_t dist = ((e2 >> 8) & 0x7fff) + ((uint32_t)d.bitbuf & ((1u << eb2) - 1));
-        DROP((int)eb2);
-        if (CONSUMED() > total_bits) { status = Z_BUF; break; }
-        if (dist > opos) { status = Z_DATA; break; }           // distance too far back
-        if (opos + len > isize) { status = Z_BUF; break; }     // output space exhausted mid-match
-        // ---- LZ77 copy, warp-cooperative -------------------------------------------------
-        const uint32_t sp = opos - dist;
-        if (dist <= (uint32_t)RING_VALID) {
-          if (dist >= len) {
-            for (uint32_t i = lane; i < len; i += 32)
-              s->out_ring[(oa + opos + i) & OMASK] = s->out_ring[(oa + sp + i) & OMASK];
-          } else {
-            uint32_t m = (uint32_t)lane % dist, k = 32u % dist;
-            for (uint32_t i = lane; i < len; i += 32) {
-              s->out_ring[(oa + opos + i) & OMASK] = s->out_ring[(oa + sp + m) & OMASK];
-              m += k;
-              if (m >= dist) m -= dist;
-            }
-          }
+      DROP(e2 >> 28);
+      const uint32_t eb2 = (e2 >> 24) & 15;
+      const uint32_t dist = ((e2 >> 8) & 0x7fff) + ((uint32_t)d.bitbuf & ((1u << eb2) - 1));
+      DROP((int)eb2);
+      const uint32_t opos = OPOS();
+      if (opos > isize) { status = Z_BUF; break; }             // an earlier literal overran the output
+      if (CONSUMED() > total_bits) { status = Z_BUF; break; }
+      if (dist > opos) { status = Z_DATA; break; }             // distance too far back
+      if (opos + len > isize) { status = Z_BUF; break; }       // output space exhausted mid-match
+      // ---- LZ77 copy, warp-cooperative ---------------------------------------------------
+      const uint32_t sp = o - dist;                            // ring-relative source start
+      if (dist <= (uint32_t)RING_VALID) {
+        if (dist >= len) {
+          for (uint32_t i = lane; i < len; i += 32) sts8(ring + ((o + i) & OMASK), lds8(ring + ((sp + i) & OMASK)));
         } else {
-          // far match: the source is older than the ring and therefore already flushed (dist > len here)
-          for (uint32_t i = lane; i < len; i += 32)
-            s->out_ring[(oa + opos + i) & OMASK] = __ldcg(gout + sp + i);
+          uint32_t m = (uint32_t)lane % dist, k = 32u % dist;
+          for (uint32_t i = lane; i < len; i += 32) {
+            sts8(ring + ((o + i) & OMASK), lds8(ring + ((sp + m) & OMASK)));
+            m += k;
+            if (m >= dist) m -= dist;
+          }
         }
-        opos += len;
-        __syncwarp();
-      } else if (kind == 2) {
-        break;   // end of block
+      } else {
+        // far match: the source is older than the ring and therefore already flushed (dist > len here)
+        const uint8_t* g = gout + (opos - dist);
+        for (uint32_t i = lane; i < len; i += 32) sts8(ring + ((o + i) & OMASK), __ldcg(g + i));
       }
-      if (opos - flushed >= 2 * FLUSH) {
-        __syncwarp();
-        uint32_t fe = opos - ((oa + opos) & (FLUSH - 1));
-        if (fe > flushed) flush_to(fe);
-      }
+      o += len;
+      __syncwarp();
     }
     if (status == 0 && CONSUMED() > total_bits) status = Z_BUF;
+    if (status == 0 && OPOS() > isize) status = Z_BUF;
   }
 
   // drain any TMA chunk still in flight before the CTA (and its shared memory) retires
   while (d.waited < d.issued) d.wait_chunk(d.waited, 0);
 
+  if (status != 0 && status != Z_BUF && OPOS() > isize) status = Z_BUF;   // the output overran before the fault
   if (status == Z_DATA && CONSUMED() > total_bits) status = Z_BUF;   // zlib would have run out of input first
-  if (status == 0 && opos != isize) status = Z_DATA;   // stream ended short of ISIZE: -release BioD would hand out garbage (block.d:175); reported as a data error
+  if (status == 0 && OPOS() != isize) status = Z_DATA;   // stream ended short of ISIZE: -release BioD would hand out garbage (block.d:175); reported as a data error
   if (status == 0) {
     __syncwarp();
-    if (opos > flushed) flush_to(opos);
+    if (OPOS() > flushed) flush_to(OPOS());
   }
   if (lane == 0) a.status[blk] = status;
 #undef REFILL
 #undef DROP
 #undef CONSUMED
+#undef OPOS
+#undef MAYBE_FLUSH
 }
+
+unsigned long long g_kernel_launches = 0;
 
 size_t inflate_smem_bytes() { return sizeof(WarpSmem); }
 
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st) {
   if (a.n_blocks == 0) return cudaSuccess;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WarpSmem));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
-  inflate_kernel<<<a.n_blocks, 32, sizeof(WarpSmem), st>>>(a);
+  inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a);
+  ++g_kernel_launches;
   return cudaGetLastError();
 }
 

@@ -6,6 +6,9 @@
 
 namespace biodb {
 
+// number of kernel launches issued by this library (all streams); read as deltas for biodb_stats
+extern unsigned long long g_kernel_launches;
+
 // ---- inflate.cu ------------------------------------------------------------------------------
 struct InflateArgs {
   const uint8_t* comp;          // device: compressed file slice

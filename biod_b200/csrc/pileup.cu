@@ -309,6 +309,7 @@ template <typename K, typename... A>
 inline void launch1d(K k, uint32_t n, cudaStream_t st, A... a) {
   if (n == 0) return;
   k<<<(n + 255) / 256, 256, 0, st>>>(a...);
+  ++g_kernel_launches;
 }
 
 }  // namespace
@@ -365,6 +366,7 @@ void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnS
   uint32_t warps = (n_col + COLS_PER_WARP - 1) / COLS_PER_WARP;
   uint32_t grid = (warps + ENT_WARPS - 1) / ENT_WARPS;
   entries_kernel<<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, c, o, n_col, s.info);
+  ++g_kernel_launches;
 }
 
 // Carry: live reads of [g0,g1) with end > limit, compacted in order into `out`.
@@ -385,6 +387,7 @@ void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32
   if (n == 0) return;
   uint64_t threads = (uint64_t)n * 32;
   carry_copy_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(v, g0, g1, block_size, s.cflag, s.cslot, s.cbytes, out);
+  ++g_kernel_launches;
 }
 
 }  // namespace biodb

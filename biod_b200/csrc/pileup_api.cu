@@ -54,6 +54,8 @@ struct biodb_pileup {
   size_t read_cap = 0, col_cap = 0, ent_cap = 0;
   PinBuf h_small, h_bnd, h_out[6];
   uint64_t tot_cols = 0, tot_entries = 0;
+  ColumnOutput dev_cols{};
+  uint32_t* dev_nstart = nullptr;
 
   biodb_status fail(int status, const std::string& msg) { return pass.fail(status, 0, 0, msg); }
 };
@@ -190,6 +192,9 @@ biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, b
 }
 
 void biodb_pileup_end(biodb_pileup* pl) { delete pl; }
+void biodb_pileup_stats(const biodb_pileup* pl, biodb_stats* out) {
+  if (pl && out) *out = pl->pass.stats;
+}
 int32_t biodb_pileup_ref_id(const biodb_pileup* pl) { return pl ? pl->target_ref : -1; }
 void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* n_columns, uint64_t* n_entries) {
   if (!pl) return;
@@ -267,7 +272,9 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
       if (pl->prm.end_at <= (uint64_t)INT64_MAX) chi = (int64_t)pl->prm.end_at;
     }
     // ---- phase 1: liveness, running max, islands ----------------------------------------------------
+    p.stage_begin();
     pileup_phase1(v, g0, g1, drop_before, skip_zero, clo, chi, s, st);
+    p.stats.pileup_ms += p.stage_end();
     const uint32_t ng = g1 - g0;
     const uint32_t t_reads = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
     PL_TRY(cudaMemcpyAsync(h, s.tmp_u32 + t_reads, 4, cudaMemcpyDeviceToHost, st));           // n_islands
@@ -309,7 +316,9 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
         PL_TRY(cudaMemcpyAsync(s.islands.start, h, 4, cudaMemcpyHostToDevice, st));
       }
     }
+    p.stage_begin();
     pileup_island_cols(n_islands, s, st);
+    p.stats.pileup_ms += p.stage_end();
     const uint32_t t_isl = (uint32_t)((n_islands + SCAN_TILE - 1) / SCAN_TILE);
     PL_TRY(cudaMemcpyAsync(h, s.tmp_u32b + t_isl, 4, cudaMemcpyDeviceToHost, st));
     PL_TRY(cudaStreamSynchronize(st));
@@ -332,7 +341,9 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
       s.chi = chi;
       ColumnScratch c{pl->cs[0].as<int32_t>(), pl->cs[1].as<uint32_t>(), pl->cs[2].as<uint32_t>(), pl->cs[3].as<uint32_t>()};
       ColumnOutput o{pl->out[0].as<uint64_t>(), pl->out[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr};
+      p.stage_begin();
       pileup_phase2(v, g0, g1, n_islands, n_col, s, c, o, st);
+      p.stats.pileup_ms += p.stage_end();
       PL_TRY(cudaMemcpyAsync(pl->h_small.p, o.col_off + n_col, 8, cudaMemcpyDeviceToHost, st));
       PL_TRY(cudaStreamSynchronize(st));
       n_entries = *pl->h_small.as<uint64_t>();
@@ -348,8 +359,14 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
       o.base = pl->out[3].as<uint8_t>();
       o.qual = pl->out[4].as<uint8_t>();
       o.qoff = pl->prm.want_query_offset ? pl->out[5].as<uint32_t>() : nullptr;
+      p.stage_begin();
       pileup_entries(v, n_col, s, c, o, st);
+      p.stats.pileup_ms += p.stage_end();
+      pl->dev_cols = o;
+      pl->dev_nstart = c.nstart;
       // results to the host
+      if (!p.r->opts.device_output) {
+      p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + n_entries * (6 + (o.qoff ? 4 : 0));
       PL_TRY(pl->h_out[0].ensure((size_t)n_col * 8 + 16));
       PL_TRY(pl->h_out[1].ensure((size_t)(n_col + 1) * 8 + 16));
       PL_TRY(pl->h_out[2].ensure((size_t)n_col * 4 + 16));
@@ -365,6 +382,7 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
         PL_TRY(pl->h_out[5].ensure((size_t)n_entries * 4 + 16));
         PL_TRY(cudaMemcpyAsync(pl->h_out[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, st));
       }
+      }
       PL_TRY(cudaMemcpyAsync(h + 8, s.info, 4, cudaMemcpyDeviceToHost, st));
       PL_TRY(cudaStreamSynchronize(st));
       if (h[8] != 0) return pl->fail(h[8], "Invalid read - query offset beyond the sequence while building a column");
@@ -379,7 +397,9 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
       if (trailing && !stop_after) {
         RecordArrays a = p.arrays(0);
         CarryOut dummy{};
+        p.stage_begin();
         pileup_carry(v, g0, g1, a.block_size, E, s, dummy, st);
+        p.stats.pileup_ms += p.stage_end();
         const uint32_t t_g = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
         PL_TRY(cudaMemcpyAsync(h, s.tmp_u32 + t_g, 4, cudaMemcpyDeviceToHost, st));
         PL_TRY(cudaMemcpyAsync(h + 2, s.tmp_u64 + t_g, 8, cudaMemcpyDeviceToHost, st));
@@ -410,10 +430,23 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
       if (pl->done) return BIODB_EOF;
       continue;
     }
+    p.mark_end();
     cols->n_columns = n_col;
     cols->n_entries = n_entries;
     cols->ref_id = ref;
     cols->last_of_pileup = pl->done ? 1 : 0;
+    pl->tot_cols += n_col;
+    pl->tot_entries += n_entries;
+    if (p.r->opts.device_output) {
+      cols->position = pl->dev_cols.col_pos;
+      cols->col_off = pl->dev_cols.col_off;
+      cols->n_starting_here = pl->dev_nstart;
+      cols->read_idx = pl->dev_cols.read_idx;
+      cols->base = pl->dev_cols.base;
+      cols->qual = pl->dev_cols.qual;
+      cols->query_offset = pl->dev_cols.qoff;
+      return BIODB_OK;
+    }
     cols->position = pl->h_out[0].as<uint64_t>();
     cols->col_off = pl->h_out[1].as<uint64_t>();
     cols->n_starting_here = pl->h_out[2].as<uint32_t>();
@@ -421,8 +454,6 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
     cols->base = pl->h_out[4].as<uint8_t>();
     cols->qual = pl->h_out[4].as<uint8_t>() + n_entries;
     cols->query_offset = pl->prm.want_query_offset ? pl->h_out[5].as<uint32_t>() : nullptr;
-    pl->tot_cols += n_col;
-    pl->tot_entries += n_entries;
     return BIODB_OK;
   }
 }

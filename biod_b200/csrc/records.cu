@@ -282,6 +282,7 @@ cudaError_t launch_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t
                                 cudaStream_t st) {
   uint32_t grid = (n_blocks + WARPS - 1) / WARPS;
   if (n_blocks) scan_walk_kernel<<<grid, WARPS * 32, 0, st>>>(u, u_len, block_uoff, n_blocks, ws);
+  g_kernel_launches += n_blocks ? 3 : 1;
   scan_resolve_kernel<<<1, 256, 0, st>>>(u, u_len, block_uoff, n_blocks, final_slice, ws, out, result);
   if (n_blocks) scan_extract_kernel<<<grid, WARPS * 32, 0, st>>>(u, block_uoff, n_blocks, ws, out);
   return cudaGetLastError();

@@ -116,6 +116,32 @@ Pass::~Pass() {
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
   }
+  for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b})
+    if (e) cudaEventDestroy(e);
+}
+
+void Pass::mark_begin() {
+  if (began) return;
+  began = true;
+  launches0 = g_kernel_launches;
+  cudaEventRecord(ev_begin, st);
+}
+void Pass::mark_end() {
+  if (!began) return;
+  cudaEventRecord(ev_end, st);
+  cudaEventSynchronize(ev_end);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, ev_begin, ev_end) == cudaSuccess) stats.total_ms = ms;
+  stats.kernel_launches = g_kernel_launches - launches0;
+  stats.n_records = n_records_total;
+}
+void Pass::stage_begin() { cudaEventRecord(ev_a, st); }
+double Pass::stage_end() {
+  cudaEventRecord(ev_b, st);
+  cudaEventSynchronize(ev_b);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev_a, ev_b);
+  return ms;
 }
 
 biodb_status Pass::fail(int status, int zerr, uint64_t off, const std::string& msg) {
@@ -128,6 +154,10 @@ biodb_status Pass::init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset) {
   r = rd;
   if (cudaSetDevice(rd->device) != cudaSuccess) return fail(BIODB_ERR_CUDA, 0, 0, "cudaSetDevice failed");
   CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&ev_begin));
+  CUDA_TRY(cudaEventCreate(&ev_end));
+  CUDA_TRY(cudaEventCreate(&ev_a));
+  CUDA_TRY(cudaEventCreate(&ev_b));
   next_coffset = coffset;
   first_skip = uoffset;
   CUDA_TRY(h_result.ensure(64));
@@ -185,6 +215,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     final_slice = true;
     return BIODB_OK;
   }
+  mark_begin();
   // ---- 1. walk the BSIZE chain on the host (18 bytes per block) ----------------------------------
   blocks.clear();
   while (blocks.size() < max_blocks && !supplier_done && !pending.status) {
@@ -245,7 +276,8 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   const uint32_t* d_cdata = (const uint32_t*)(d_buoff + nsb + 2);
   const uint32_t* d_isize = d_cdata + nb;
   // ---- 3. device buffers -------------------------------------------------------------------------------
-  CUDA_TRY(d_comp.ensure((size_t)(c1 - c0) + 256, st));
+  const bool resident = r->d_file.p != nullptr;
+  if (!resident) CUDA_TRY(d_comp.ensure((size_t)(c1 - c0) + 256, st));
   CUDA_TRY(d_u.ensure((size_t)u_len + 256, st));
   CUDA_TRY(d_status.ensure((size_t)nb * 4 + 16, st));
   CUDA_TRY(h_status.ensure((size_t)nb * 4 + 16));
@@ -254,9 +286,19 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     CUDA_TRY(cudaMemcpyAsync(d_u.p, d_carry_tail.p, carry_tail_len, cudaMemcpyDeviceToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(d_tab.p, h_tab.p, tab_bytes, cudaMemcpyHostToDevice, st));
   if (nb) {
-    CUDA_TRY(cudaMemcpyAsync(d_comp.p, r->file + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
-    InflateArgs ia{d_comp.as<uint8_t>(), d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb};
+    if (!resident) {
+      CUDA_TRY(cudaMemcpyAsync(d_comp.p, r->file + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+      stats.h2d_bytes += c1 - c0;
+    }
+    const uint8_t* comp = resident ? r->d_file.as<uint8_t>() + c0 : d_comp.as<uint8_t>();
+    InflateArgs ia{comp, d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb};
+    stage_begin();
     CUDA_TRY(launch_inflate(ia, st));
+    stats.inflate_ms += stage_end();
+    stats.inflate_launches += 1;
+    stats.n_blocks += nb;
+    stats.compressed_bytes += c1 - c0;
+    stats.uncompressed_bytes += off - (has_carry ? carry_tail_len : 0);
     CUDA_TRY(cudaMemcpyAsync(h_status.p, d_status.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const int32_t* hs = h_status.as<int32_t>();
@@ -303,7 +345,9 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
       CUDA_TRY(d_rec[9].ensure((size_t)(cigar_capacity + 2) * 4, st));
     }
     RecordArrays ra = arrays(front_slots);
+    stage_begin();
     CUDA_TRY(launch_scan_records(d_u.as<uint8_t>(), u_len, d_buoff, nsb2, eof_semantics, ra, d_result.as<uint64_t>(), ws, st));
+    stats.scan_ms += stage_end();
     CUDA_TRY(cudaMemcpyAsync(h_result.p, d_result.p, 32, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const uint64_t* res = h_result.as<uint64_t>();
@@ -463,6 +507,14 @@ static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biod
     delete r;
     return s;
   }
+  if (r->opts.resident_input && r->flen) {
+    if (r->d_file.ensure((size_t)r->flen + 256) != cudaSuccess ||
+        cudaMemcpy(r->d_file.p, r->file, (size_t)r->flen, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "cannot make the compressed file resident in device memory");
+      delete r;
+      return BIODB_ERR_CUDA;
+    }
+  }
   *out = r;
   return BIODB_OK;
 }
@@ -573,6 +625,8 @@ biodb_status biodb_reads_next(biodb_reads* it, biodb_record_batch* batch) {
   for (int a = 0; a < 9 && ok; ++a) ok = pull(it->h_arr[a], p.d_rec[a].p, (size_t)(n + (a == 8 ? 1 : 0)) * esz[a]);
   ok = ok && pull(it->h_arr[9], p.d_rec[9].p, (size_t)p.n_cigar * 4);
   if (!ok || cudaStreamSynchronize(p.st) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "device to host copy failed");
+  p.stats.d2h_bytes += used + n * 44 + 8 + p.n_cigar * 4;
+  p.mark_end();
   batch->n = n;
   batch->first_index = first;
   batch->data = it->h_data.as<uint8_t>();
@@ -603,6 +657,10 @@ biodb_status biodb_reads_next(biodb_reads* it, biodb_record_batch* batch) {
 }
 
 void biodb_reads_end(biodb_reads* it) { delete it; }
+
+void biodb_reads_stats(const biodb_reads* it, biodb_stats* out) {
+  if (it && out) *out = it->pass.stats;
+}
 
 float biodb_reads_progress(const biodb_reads* it) {
   if (!it || !it->pass.r || it->pass.r->flen == 0) return 0.f;

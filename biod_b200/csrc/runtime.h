@@ -64,6 +64,7 @@ struct biodb_reader {
   uint32_t reads_start_uoffset = 0;
   bool reads_start_at_eof = false;
   biodb_error err{};
+  biodb::DevBuf d_file;           // options.resident_input: the compressed file in HBM
 };
 
 namespace biodb {
@@ -96,6 +97,15 @@ struct Pass {
   uint64_t n = 0, n_cigar = 0, tail = 0;
   bool final_slice = false;
   bool raw_mode = false;            // header pass: inflate only, no record scan, no carry
+  // measurement (biodb_stats)
+  biodb_stats stats{};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
+  bool began = false;
+  unsigned long long launches0 = 0;
+  void mark_begin();                // first operation of the pass
+  void mark_end();                  // call with the stream idle-able: records + syncs, updates total_ms
+  void stage_begin();               // events around a group of launches of one stage
+  double stage_end();               // returns elapsed ms (synchronises the stream)
 
   ~Pass();
   biodb_status init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset);

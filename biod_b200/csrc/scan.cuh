@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "kernels.h"
+
 namespace biodb {
 
 struct OpAdd {
@@ -134,6 +136,7 @@ inline size_t scan_temp_elems(uint64_t n) { return (size_t)((n + SCAN_TILE - 1) 
 template <bool INCLUSIVE, typename TIn, typename T, typename Op>
 inline void device_scan(const TIn* in, T* out, uint64_t n, T* tile_tmp, Op op, T identity, cudaStream_t st) {
   uint32_t n_tiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+  g_kernel_launches += n_tiles ? 3 : 1;
   if (n_tiles == 0) {
     scan_tiles_kernel<T, Op><<<1, SCAN_THREADS, 0, st>>>(tile_tmp, 0, op, identity);
     return;

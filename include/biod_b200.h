@@ -59,7 +59,9 @@ typedef struct biodb_options {
   int32_t verify_crc;        /* 1 = check each block's CRC32 on the device (debug builds of BioD assert it, block.d:187) */
   int32_t want_offsets;      /* 1 = fill start/end virtual offsets (withOffsets policy, readrange.d:51-66) */
   int32_t pin_input;         /* 1 = cudaHostRegister the caller's buffer in biodb_open_memory */
-  int32_t reserved[3];
+  int32_t resident_input;    /* 1 = copy the whole compressed file to HBM once at open; passes then read it from there */
+  int32_t device_output;     /* 1 = biodb_pileup_next hands out DEVICE pointers (no device->host copy of the columns) */
+  int32_t reserved[1];
 } biodb_options;
 
 typedef struct biodb_reader biodb_reader;
@@ -152,6 +154,20 @@ void biodb_pileup_end(biodb_pileup* pl);
 int32_t biodb_pileup_ref_id(const biodb_pileup* pl);
 /* Totals over the whole pass so far (for benches and checks). */
 void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* n_columns, uint64_t* n_entries);
+
+/* ---- measurement ---------------------------------------------------------------------------------------- */
+typedef struct biodb_stats {
+  double total_ms;        /* CUDA-event time from the first to the last operation of the pass, on its stream */
+  double inflate_ms;      /* sum over launches of the inflate kernel (events around each launch) */
+  double scan_ms;         /* record scanner kernels */
+  double pileup_ms;       /* pileup kernels */
+  uint64_t inflate_launches, kernel_launches;
+  uint64_t h2d_bytes, d2h_bytes;
+  uint64_t compressed_bytes, uncompressed_bytes;   /* algorithmic bytes moved by the inflate kernel */
+  uint64_t n_blocks, n_records;
+} biodb_stats;
+void biodb_reads_stats(const biodb_reads* it, biodb_stats* out);
+void biodb_pileup_stats(const biodb_pileup* pl, biodb_stats* out);
 
 /* ---- device-resident stage API (all pointers are DEVICE pointers; stream is a cudaStream_t) ------------- */
 /* Inflate n BGZF blocks.  Block i's raw-DEFLATE payload is comp[payload_off[i] .. +cdata_size[i]); its
