@@ -3,8 +3,12 @@
 // the halo scheme of PileupChunkRange (bio/std/hts/bam/pileup.d:859-987): a batch emits columns up to
 // (not including) the position of its last read, later columns wait for the next batch.
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "runtime.h"
@@ -26,6 +30,23 @@ struct CarryBufs {
     o.data = data.as<uint8_t>();
     return o;
   }
+};
+
+// One set of output buffers: device side written by the pileup kernels, host side (pinned) filled by an
+// asynchronous copy on the copy stream.  Two sets alternate so that batch k+1 is computed and copied while
+// the caller still reads batch k.
+struct OutSet {
+  DevBuf d[7];      // col_pos, col_off, nstart, read_idx, base, qual, qoff
+  PinBuf h[6];      // col_pos, col_off, nstart, read_idx, base|qual, qoff
+  size_t col_cap = 0, ent_cap = 0;
+  cudaEvent_t computed = nullptr, done = nullptr;
+};
+
+struct Desc {       // what the producer hands to biodb_pileup_next
+  biodb_status st = BIODB_OK;
+  biodb_error err{};
+  biodb_column_batch cols{};
+  int set = -1;
 };
 
 }  // namespace
@@ -50,12 +71,26 @@ struct biodb_pileup {
   uint32_t n_view = 0, n_carry_view = 0;
   uint64_t first_index = 0;
   // scratch
-  DevBuf g[12], tmp[4], info, bnd, cs[4], out[6];
-  size_t read_cap = 0, col_cap = 0, ent_cap = 0;
-  PinBuf h_small, h_bnd, h_out[6];
+  DevBuf g[12], tmp[4], info, bnd, cs[3];
+  size_t read_cap = 0, col_cap = 0;
+  PinBuf h_small, h_bnd;
   uint64_t tot_cols = 0, tot_entries = 0;
-  ColumnOutput dev_cols{};
-  uint32_t* dev_nstart = nullptr;
+  // pipelining: producer thread + two output sets
+  OutSet sets[2];
+  cudaStream_t copy_st = nullptr;
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<Desc> ready;
+  int free_sets = 2;         // sets the producer may still fill
+  int next_set = 0;
+  int held_set = -1;         // set whose pointers the caller currently holds
+  bool stop = false, worker_started = false, worker_done = false;
+  cudaEvent_t last_done = nullptr;
+
+  ~biodb_pileup();
+  void shutdown();
+  void reset(const biodb_pileup_params* p);
 
   biodb_status fail(int status, const std::string& msg) { return pass.fail(status, 0, 0, msg); }
 };
@@ -175,23 +210,117 @@ static biodb_status load_batch(biodb_pileup* pl) {
   return BIODB_OK;
 }
 
+biodb_pileup::~biodb_pileup() {
+  shutdown();
+  for (OutSet& o : sets) {
+    if (o.computed) cudaEventDestroy(o.computed);
+    if (o.done) cudaEventDestroy(o.done);
+  }
+  if (copy_st) cudaStreamDestroy(copy_st);
+}
+
+void biodb_pileup::shutdown() {
+  if (worker_started) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv.notify_all();
+    if (worker.joinable()) worker.join();
+    worker_started = false;
+  }
+  if (pass.st) cudaStreamSynchronize(pass.st);
+  if (copy_st) cudaStreamSynchronize(copy_st);
+}
+
+void biodb_pileup::reset(const biodb_pileup_params* p) {
+  if (p) prm = *p;
+  else { memset(&prm, 0, sizeof prm); prm.skip_zero_coverage = 1; prm.single_ref = 1; prm.end_at = ~0ull; }
+  if (!prm.single_ref) { prm.start_from = 0; prm.end_at = ~0ull; }
+  carry[0].n = carry[1].n = 0;
+  cur = 0;
+  cont = false;
+  started = done = false;
+  target_ref = -1;
+  have_batch = false;
+  bounds.clear();
+  gi = 0;
+  tot_cols = tot_entries = 0;
+  ready.clear();
+  free_sets = 2;
+  next_set = 0;
+  held_set = -1;
+  stop = worker_done = false;
+  last_done = nullptr;
+}
+
+static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* cols);
+
+static void producer_main(biodb_pileup* pl) {
+  cudaSetDevice(pl->r->device);
+  while (true) {
+    int set;
+    {
+      std::unique_lock<std::mutex> lk(pl->mu);
+      pl->cv.wait(lk, [&] { return pl->stop || pl->free_sets > 0; });
+      if (pl->stop) break;
+      --pl->free_sets;
+      set = pl->next_set;
+      pl->next_set ^= 1;
+    }
+    Desc d;
+    d.set = set;
+    d.st = produce(pl, pl->sets[set], &d.cols);
+    if (d.st != BIODB_OK && d.st != BIODB_EOF) d.err = pl->r->err;
+    {
+      std::lock_guard<std::mutex> lk(pl->mu);
+      pl->ready.push_back(d);
+      if (d.st != BIODB_OK) pl->worker_done = true;
+    }
+    pl->cv.notify_all();
+    if (d.st != BIODB_OK) break;
+  }
+}
+
 extern "C" {
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out) {
   if (!r || !out) return BIODB_ERR_ARG;
-  biodb_pileup* pl = new biodb_pileup;
+  biodb_pileup* pl = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(r->pool_mu);
+    if (!r->pileup_pool.empty()) { pl = (biodb_pileup*)r->pileup_pool.back(); r->pileup_pool.pop_back(); }
+  }
+  if (pl) {
+    pl->reset(p);
+    pl->pass.rewind(r->reads_start_coffset, r->reads_start_uoffset);
+    *out = pl;
+    return BIODB_OK;
+  }
+  pl = new biodb_pileup;
   pl->r = r;
-  if (p) pl->prm = *p;
-  else { memset(&pl->prm, 0, sizeof pl->prm); pl->prm.skip_zero_coverage = 1; pl->prm.single_ref = 1; pl->prm.end_at = ~0ull; }
-  if (!pl->prm.single_ref) { pl->prm.start_from = 0; pl->prm.end_at = ~0ull; }
+  pl->reset(p);
   biodb_status s = pl->pass.init(r, r->reads_start_coffset, r->reads_start_uoffset);
   if (s == BIODB_OK && (pl->info.ensure(64) != cudaSuccess || pl->h_small.ensure(256) != cudaSuccess)) s = BIODB_ERR_CUDA;
+  if (s == BIODB_OK && cudaStreamCreateWithFlags(&pl->copy_st, cudaStreamNonBlocking) != cudaSuccess) s = BIODB_ERR_CUDA;
+  for (OutSet& o : pl->sets)
+    if (s == BIODB_OK && (cudaEventCreate(&o.computed) != cudaSuccess || cudaEventCreate(&o.done) != cudaSuccess)) s = BIODB_ERR_CUDA;
   if (s != BIODB_OK) { delete pl; return s; }
   *out = pl;
   return BIODB_OK;
 }
 
-void biodb_pileup_end(biodb_pileup* pl) { delete pl; }
+void biodb_pileup_end(biodb_pileup* pl) {
+  if (!pl) return;
+  pl->shutdown();
+  biodb_reader* r = pl->r;
+  {
+    std::lock_guard<std::mutex> lk(r->pool_mu);
+    if (r->pileup_pool.size() < 2) { r->pileup_pool.push_back(pl); return; }   // keep the buffers for the next pass
+  }
+  delete pl;
+}
+void biodb_pileup_destroy_pooled(void* p) { delete (biodb_pileup*)p; }
 void biodb_pileup_stats(const biodb_pileup* pl, biodb_stats* out) {
   if (pl && out) *out = pl->pass.stats;
 }
@@ -203,8 +332,51 @@ void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* 
   if (n_entries) *n_entries = pl->tot_entries;
 }
 
+// Consumer side: hand out the next finished batch.  The producer thread works one batch ahead; the buffers of
+// the batch returned here stay valid until the next call.
 biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
   if (!pl || !cols) return BIODB_ERR_ARG;
+  memset(cols, 0, sizeof *cols);
+  if (!pl->worker_started) {
+    pl->worker_started = true;
+    pl->worker = std::thread(producer_main, pl);
+  }
+  Desc d;
+  {
+    std::unique_lock<std::mutex> lk(pl->mu);
+    if (pl->held_set >= 0) {            // the caller is done with the previous batch: its set may be refilled
+      pl->held_set = -1;
+      ++pl->free_sets;
+      pl->cv.notify_all();
+    }
+    pl->cv.wait(lk, [&] { return !pl->ready.empty(); });
+    d = pl->ready.front();
+    if (d.st == BIODB_OK) pl->ready.pop_front();   // EOF / errors stay at the head: every later call repeats them
+  }
+  if (d.st == BIODB_OK) {
+    OutSet& os = pl->sets[d.set];
+    cudaEventSynchronize(os.done);
+    pl->last_done = os.done;
+    pl->held_set = d.set;
+    *cols = d.cols;
+    pl->tot_cols += d.cols.n_columns;
+    pl->tot_entries += d.cols.n_entries;
+    return BIODB_OK;
+  }
+  // end of the pass: the pass time runs from its first operation to the completion of the last copy
+  if (pl->last_done && pl->pass.began) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, pl->pass.ev_begin, pl->last_done) == cudaSuccess && ms > pl->pass.stats.total_ms)
+      pl->pass.stats.total_ms = ms;
+  }
+  if (d.st != BIODB_EOF) pl->r->err = d.err;
+  return d.st;
+}
+
+}  // extern "C"
+
+// Producer side: compute the next non-empty column batch into `os` and start its copy to the host.
+static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* cols) {
   memset(cols, 0, sizeof *cols);
   Pass& p = pl->pass;
   cudaStream_t st = p.st;
@@ -329,59 +501,73 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
     if (n_col) {
       if ((size_t)n_col + 8 > pl->col_cap) {
         size_t cap = (size_t)n_col + n_col / 4 + 1024;
-        for (int k = 0; k < 4; ++k) PL_TRY(pl->cs[k].ensure(cap * 4, st));
-        PL_TRY(pl->out[0].ensure(cap * 8, st));
-        PL_TRY(pl->out[1].ensure(cap * 8, st));
+        for (int k = 0; k < 3; ++k) PL_TRY(pl->cs[k].ensure(cap * 4, st));
         pl->col_cap = cap;
+      }
+      if ((size_t)n_col + 8 > os.col_cap) {
+        size_t cap = (size_t)n_col + n_col / 4 + 1024;
+        PL_TRY(os.d[0].ensure(cap * 8, st));
+        PL_TRY(os.d[1].ensure(cap * 8, st));
+        PL_TRY(os.d[2].ensure(cap * 4, st));
+        if (!p.r->opts.device_output) {
+          PL_TRY(os.h[0].ensure(cap * 8));
+          PL_TRY(os.h[1].ensure(cap * 8));
+          PL_TRY(os.h[2].ensure(cap * 4));
+        }
+        os.col_cap = cap;
       }
       biodb_status es = ensure_tmp(pl, std::max<size_t>(pl->n_view, n_col) + 2);
       if (es != BIODB_OK) return es;
       s = scratch(pl);
       s.clo = clo;
       s.chi = chi;
-      ColumnScratch c{pl->cs[0].as<int32_t>(), pl->cs[1].as<uint32_t>(), pl->cs[2].as<uint32_t>(), pl->cs[3].as<uint32_t>()};
-      ColumnOutput o{pl->out[0].as<uint64_t>(), pl->out[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr};
+      ColumnScratch c{pl->cs[0].as<int32_t>(), os.d[2].as<uint32_t>(), pl->cs[1].as<uint32_t>(), pl->cs[2].as<uint32_t>()};
+      ColumnOutput o{os.d[0].as<uint64_t>(), os.d[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr};
       p.stage_begin();
       pileup_phase2(v, g0, g1, n_islands, n_col, s, c, o, st);
       p.stats.pileup_ms += p.stage_end();
       PL_TRY(cudaMemcpyAsync(pl->h_small.p, o.col_off + n_col, 8, cudaMemcpyDeviceToHost, st));
       PL_TRY(cudaStreamSynchronize(st));
       n_entries = *pl->h_small.as<uint64_t>();
-      if (n_entries + 8 > pl->ent_cap) {
-        size_t cap = (size_t)n_entries + n_entries / 4 + 4096;
-        PL_TRY(pl->out[2].ensure(cap * 4, st));
-        PL_TRY(pl->out[3].ensure(cap, st));
-        PL_TRY(pl->out[4].ensure(cap, st));
-        if (pl->prm.want_query_offset) PL_TRY(pl->out[5].ensure(cap * 4, st));
-        pl->ent_cap = cap;
+      const bool want_q = pl->prm.want_query_offset != 0;
+      if (n_entries + 8 > os.ent_cap) {
+        size_t cap = (size_t)n_entries + n_entries / 8 + 4096;
+        PL_TRY(os.d[3].ensure(cap * 4, st));
+        PL_TRY(os.d[4].ensure(cap, st));
+        PL_TRY(os.d[5].ensure(cap, st));
+        if (!p.r->opts.device_output) {
+          PL_TRY(os.h[3].ensure(cap * 4));
+          PL_TRY(os.h[4].ensure(cap * 2));
+        }
+        os.ent_cap = cap;
       }
-      o.read_idx = pl->out[2].as<uint32_t>();
-      o.base = pl->out[3].as<uint8_t>();
-      o.qual = pl->out[4].as<uint8_t>();
-      o.qoff = pl->prm.want_query_offset ? pl->out[5].as<uint32_t>() : nullptr;
+      if (want_q) {
+        PL_TRY(os.d[6].ensure(os.ent_cap * 4, st));
+        if (!p.r->opts.device_output) PL_TRY(os.h[5].ensure(os.ent_cap * 4));
+      }
+      o.read_idx = os.d[3].as<uint32_t>();
+      o.base = os.d[4].as<uint8_t>();
+      o.qual = os.d[5].as<uint8_t>();
+      o.qoff = want_q ? os.d[6].as<uint32_t>() : nullptr;
       p.stage_begin();
       pileup_entries(v, n_col, s, c, o, st);
       p.stats.pileup_ms += p.stage_end();
-      pl->dev_cols = o;
-      pl->dev_nstart = c.nstart;
-      // results to the host
+      PL_TRY(cudaEventRecord(os.computed, st));
+      // results to the host on the copy stream: overlaps with the carry kernels and the next batch
       if (!p.r->opts.device_output) {
-      p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + n_entries * (6 + (o.qoff ? 4 : 0));
-      PL_TRY(pl->h_out[0].ensure((size_t)n_col * 8 + 16));
-      PL_TRY(pl->h_out[1].ensure((size_t)(n_col + 1) * 8 + 16));
-      PL_TRY(pl->h_out[2].ensure((size_t)n_col * 4 + 16));
-      PL_TRY(pl->h_out[3].ensure((size_t)n_entries * 4 + 16));
-      PL_TRY(pl->h_out[4].ensure((size_t)n_entries * 2 + 16));
-      PL_TRY(cudaMemcpyAsync(pl->h_out[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, st));
-      PL_TRY(cudaMemcpyAsync(pl->h_out[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, st));
-      PL_TRY(cudaMemcpyAsync(pl->h_out[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, st));
-      PL_TRY(cudaMemcpyAsync(pl->h_out[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, st));
-      PL_TRY(cudaMemcpyAsync(pl->h_out[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, st));
-      PL_TRY(cudaMemcpyAsync(pl->h_out[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, st));
-      if (o.qoff) {
-        PL_TRY(pl->h_out[5].ensure((size_t)n_entries * 4 + 16));
-        PL_TRY(cudaMemcpyAsync(pl->h_out[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, st));
-      }
+        cudaStream_t cs = pl->copy_st;
+        PL_TRY(cudaStreamWaitEvent(cs, os.computed, 0));
+        p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + n_entries * (6 + (want_q ? 4 : 0));
+        PL_TRY(cudaMemcpyAsync(os.h[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
+        PL_TRY(cudaMemcpyAsync(os.h[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, cs));
+        PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
+        PL_TRY(cudaMemcpyAsync(os.h[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+        PL_TRY(cudaMemcpyAsync(os.h[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+        PL_TRY(cudaMemcpyAsync(os.h[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+        if (want_q) PL_TRY(cudaMemcpyAsync(os.h[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+        PL_TRY(cudaEventRecord(os.done, cs));
+      } else {
+        PL_TRY(cudaEventRecord(os.done, st));
       }
       PL_TRY(cudaMemcpyAsync(h + 8, s.info, 4, cudaMemcpyDeviceToHost, st));
       PL_TRY(cudaStreamSynchronize(st));
@@ -435,27 +621,24 @@ biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols) {
     cols->n_entries = n_entries;
     cols->ref_id = ref;
     cols->last_of_pileup = pl->done ? 1 : 0;
-    pl->tot_cols += n_col;
-    pl->tot_entries += n_entries;
     if (p.r->opts.device_output) {
-      cols->position = pl->dev_cols.col_pos;
-      cols->col_off = pl->dev_cols.col_off;
-      cols->n_starting_here = pl->dev_nstart;
-      cols->read_idx = pl->dev_cols.read_idx;
-      cols->base = pl->dev_cols.base;
-      cols->qual = pl->dev_cols.qual;
-      cols->query_offset = pl->dev_cols.qoff;
+      cols->position = os.d[0].as<uint64_t>();
+      cols->col_off = os.d[1].as<uint64_t>();
+      cols->n_starting_here = os.d[2].as<uint32_t>();
+      cols->read_idx = os.d[3].as<uint32_t>();
+      cols->base = os.d[4].as<uint8_t>();
+      cols->qual = os.d[5].as<uint8_t>();
+      cols->query_offset = pl->prm.want_query_offset ? os.d[6].as<uint32_t>() : nullptr;
       return BIODB_OK;
     }
-    cols->position = pl->h_out[0].as<uint64_t>();
-    cols->col_off = pl->h_out[1].as<uint64_t>();
-    cols->n_starting_here = pl->h_out[2].as<uint32_t>();
-    cols->read_idx = pl->h_out[3].as<uint32_t>();
-    cols->base = pl->h_out[4].as<uint8_t>();
-    cols->qual = pl->h_out[4].as<uint8_t>() + n_entries;
-    cols->query_offset = pl->prm.want_query_offset ? pl->h_out[5].as<uint32_t>() : nullptr;
+    cols->position = os.h[0].as<uint64_t>();
+    cols->col_off = os.h[1].as<uint64_t>();
+    cols->n_starting_here = os.h[2].as<uint32_t>();
+    cols->read_idx = os.h[3].as<uint32_t>();
+    cols->base = os.h[4].as<uint8_t>();
+    cols->qual = os.h[4].as<uint8_t>() + n_entries;
+    cols->query_offset = pl->prm.want_query_offset ? os.h[5].as<uint32_t>() : nullptr;
     return BIODB_OK;
   }
 }
 
-}  // extern "C"

@@ -165,6 +165,23 @@ biodb_status Pass::init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset) {
   return BIODB_OK;
 }
 
+void Pass::rewind(uint64_t coffset, uint32_t uoffset) {
+  next_coffset = coffset;
+  first_skip = uoffset;
+  supplier_done = false;
+  memset(&pending, 0, sizeof pending);
+  finished = false;
+  n_records_total = 0;
+  blocks.clear();
+  u_len = carry_tail_len = 0;
+  segs.clear();
+  next_segs.clear();
+  n = n_cigar = tail = 0;
+  final_slice = false;
+  memset(&stats, 0, sizeof stats);
+  began = false;
+}
+
 RecordArrays Pass::arrays(uint64_t front) const {
   RecordArrays a;
   a.rec_off = d_rec[0].as<uint64_t>() + front;
@@ -560,8 +577,13 @@ biodb_status biodb_open(const char* path, const biodb_options* opts, biodb_reade
   return finish_open(r, opts, out);
 }
 
+void biodb_pileup_destroy_pooled(void* p);
+static void reads_destroy_pooled(void* p);
+
 void biodb_close(biodb_reader* r) {
   if (!r) return;
+  for (void* p : r->pileup_pool) biodb_pileup_destroy_pooled(p);
+  for (void* p : r->reads_pool) reads_destroy_pooled(p);
   if (r->registered) cudaHostUnregister((void*)r->file);
   delete r;
 }
@@ -594,8 +616,20 @@ struct biodb_reads {
 
 extern "C" {
 
+static void reads_destroy_pooled(void* p) { delete (biodb_reads*)p; }
+
 biodb_status biodb_reads_begin(biodb_reader* r, biodb_reads** out) {
   if (!r || !out) return BIODB_ERR_ARG;
+  {
+    std::lock_guard<std::mutex> lk(r->pool_mu);
+    if (!r->reads_pool.empty()) {
+      biodb_reads* it = (biodb_reads*)r->reads_pool.back();
+      r->reads_pool.pop_back();
+      it->pass.rewind(r->reads_start_coffset, r->reads_start_uoffset);
+      *out = it;
+      return BIODB_OK;
+    }
+  }
   biodb_reads* it = new biodb_reads;
   biodb_status s = it->pass.init(r, r->reads_start_coffset, r->reads_start_uoffset);
   if (s != BIODB_OK) { delete it; return s; }
@@ -656,7 +690,16 @@ biodb_status biodb_reads_next(biodb_reads* it, biodb_record_batch* batch) {
   return BIODB_OK;
 }
 
-void biodb_reads_end(biodb_reads* it) { delete it; }
+void biodb_reads_end(biodb_reads* it) {
+  if (!it) return;
+  biodb_reader* r = it->pass.r;
+  if (it->pass.st) cudaStreamSynchronize(it->pass.st);
+  {
+    std::lock_guard<std::mutex> lk(r->pool_mu);
+    if (r->reads_pool.size() < 2) { r->reads_pool.push_back(it); return; }
+  }
+  delete it;
+}
 
 void biodb_reads_stats(const biodb_reads* it, biodb_stats* out) {
   if (it && out) *out = it->pass.stats;

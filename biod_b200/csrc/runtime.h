@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -65,6 +66,9 @@ struct biodb_reader {
   bool reads_start_at_eof = false;
   biodb_error err{};
   biodb::DevBuf d_file;           // options.resident_input: the compressed file in HBM
+  // finished passes park their buffers here so that the next pass does not reallocate them
+  std::mutex pool_mu;
+  std::vector<void*> pileup_pool, reads_pool;
 };
 
 namespace biodb {
@@ -109,6 +113,7 @@ struct Pass {
 
   ~Pass();
   biodb_status init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset);
+  void rewind(uint64_t coffset, uint32_t uoffset);   // start a new pass, keeping every buffer
   // Inflate + scan the next batch.  BIODB_OK (n may be 0), BIODB_EOF, or an error.
   biodb_status next(uint32_t max_blocks, uint64_t front_slots);
   RecordArrays arrays(uint64_t front) const;
