@@ -1,0 +1,221 @@
+/*
+    D binding of libbiod_b200.so (include/biod_b200.h) for BioD.
+
+    Place next to bio/core/utils/zlib.d (BioD's only other FFI, bio/core/utils/zlib.d:6-245) and link with
+    -L-lbiod_b200 in addition to -L-lz (Makefile:10).  Written against BioD v0.2.4; it could not be compiled
+    in the build image (no D toolchain), see INTEGRATION.md.
+
+    GpuBamReader implements IBamSamReader (bio/std/hts/bam/abstractreader.d:34-49) so every consumer of the
+    range API keeps working; BamRead stays BioD's own struct — a view over raw record bytes
+    (bio/std/hts/bam/read.d:865) — built over slices of the library's writable record buffer.
+*/
+module bio.std.hts.bam.gpu;
+
+import bio.std.hts.bam.read : BamRead;
+import bio.std.hts.bam.readrange : BamReadBlock;
+import bio.std.hts.bam.abstractreader : IBamSamReader;
+import bio.std.hts.bam.referenceinfo : ReferenceSequenceInfo;
+import bio.std.hts.sam.header : SamHeader;
+import bio.core.bgzf.inputstream : BgzfException;
+import bio.core.bgzf.virtualoffset : VirtualOffset;
+import bio.core.utils.zlib : ZlibException;
+import contrib.undead.stream : ReadException;
+import std.parallelism : TaskPool, taskPool;
+import std.string : toStringz;
+import std.conv : to;
+
+extern (C) nothrow @nogc {
+    enum : int {
+        BIODB_OK = 0, BIODB_EOF = 1, BIODB_ERR_BGZF = -1, BIODB_ERR_ZLIB = -2, BIODB_ERR_FORMAT = -3,
+        BIODB_ERR_TRUNCATED = -4, BIODB_ERR_IO = -5, BIODB_ERR_CUDA = -6, BIODB_ERR_CIGAR = -7,
+        BIODB_ERR_UNSORTED = -8, BIODB_ERR_ARG = -9, BIODB_ERR_NOMEM = -10
+    }
+    struct biodb_error { int status; int zlib_errnum; ulong file_offset; char[256] message; }
+    struct biodb_options {
+        int device = -1; int blocks_per_batch; int verify_crc; int want_offsets; int pin_input;
+        int resident_input; int device_output; int[1] reserved;
+    }
+    struct biodb_reader; struct biodb_reads; struct biodb_pileup;
+    struct biodb_record_batch {
+        ulong n; ulong first_index; ubyte* data; ulong data_len;
+        const(ulong)* rec_off; const(int)* block_size; const(int)* ref_id; const(int)* pos; const(int)* end_pos;
+        const(uint)* bin_mq_nl; const(uint)* flag_nc; const(int)* l_seq; const(ulong)* cigar_off; const(uint)* cigar;
+        const(ulong)* start_voffset; const(ulong)* end_voffset;
+    }
+    struct biodb_pileup_params {
+        int single_ref; int skip_zero_coverage; int use_md_tag; int want_query_offset;
+        ulong start_from; ulong end_at; int counts_only; int[3] reserved;
+    }
+    struct biodb_column_batch {
+        ulong n_columns; ulong n_entries; int ref_id; int last_of_pileup;
+        const(ulong)* position; const(ulong)* col_off; const(uint)* n_starting_here;
+        const(uint)* read_idx; const(ubyte)* base; const(ubyte)* qual; const(uint)* query_offset; const(uint)* counts;
+    }
+    void biodb_default_options(biodb_options*);
+    int biodb_open(const(char)* path, const(biodb_options)*, biodb_reader**);
+    int biodb_open_memory(const(void)* data, size_t len, const(biodb_options)*, biodb_reader**);
+    void biodb_close(biodb_reader*);
+    const(biodb_error)* biodb_last_error(const(biodb_reader)*);
+    const(biodb_error)* biodb_open_error();
+    int biodb_header_text(const(biodb_reader)*, const(char)** text, size_t* len);
+    int biodb_n_refs(const(biodb_reader)*);
+    int biodb_ref_info(const(biodb_reader)*, int i, const(char)** name, int* name_len, int* length);
+    ulong biodb_reads_start_voffset(const(biodb_reader)*);
+    int biodb_reads_begin(biodb_reader*, biodb_reads**);
+    int biodb_reads_next(biodb_reads*, biodb_record_batch*);
+    void biodb_reads_end(biodb_reads*);
+    float biodb_reads_progress(const(biodb_reads)*);
+    int biodb_pileup_begin(biodb_reader*, const(biodb_pileup_params)*, biodb_pileup**);
+    int biodb_pileup_next(biodb_pileup*, biodb_column_batch*);
+    void biodb_pileup_end(biodb_pileup*);
+    int biodb_pileup_ref_id(const(biodb_pileup)*);
+}
+
+/// Maps a status + error record to the exception classes BioD's tests pin (test/unittests.d:132-142).
+private void raise(const(biodb_error)* e) {
+    auto msg = to!string(e.message.ptr);
+    switch (e.status) {
+        case BIODB_ERR_BGZF:      throw new BgzfException(msg);                 // bgzf/inputstream.d:41-43
+        case BIODB_ERR_ZLIB:      throw new ZlibException(e.zlib_errnum);       // core/utils/zlib.d:247-274
+        case BIODB_ERR_TRUNCATED: throw new ReadException(msg);                 // readrange.d:169
+        default:                  throw new Exception(msg);                     // reader.d:113, block.d:150
+    }
+}
+
+/// Input range of BamRead over GPU-decoded batches: `empty/front/popFront` like BamReadRange (readrange.d:82-188).
+struct GpuBamReadRange(bool withOffsets = false) {
+    private biodb_reader* _h;
+    private biodb_reads* _it;
+    private biodb_record_batch _b;
+    private size_t _i;
+    private bool _empty;
+    private BamRead _current;
+    private IBamSamReader _reader;
+
+    this(biodb_reader* h, IBamSamReader reader) {
+        _h = h; _reader = reader;
+        if (biodb_reads_begin(h, &_it) != BIODB_OK) raise(biodb_last_error(h));
+        fetch();
+    }
+    ~this() { if (_it !is null) { biodb_reads_end(_it); _it = null; } }
+    @disable this(this);
+
+    bool empty() @property const { return _empty; }
+    static if (withOffsets) {
+        BamReadBlock front() @property {
+            return BamReadBlock(VirtualOffset(_b.start_voffset[_i]), VirtualOffset(_b.end_voffset[_i]), _current);
+        }
+    } else {
+        ref BamRead front() @property { return _current; }
+    }
+    void popFront() { ++_i; if (_i >= _b.n) fetch(); else load(); }
+
+    private void fetch() {
+        auto st = biodb_reads_next(_it, &_b);
+        if (st == BIODB_EOF) { _empty = true; return; }
+        if (st != BIODB_OK) raise(biodb_last_error(_h));
+        _i = 0;
+        load();
+    }
+    private void load() {
+        auto o = cast(size_t)_b.rec_off[_i] + 4;
+        // the slice is writable library-owned pinned memory, valid until the next batch: the same rule as
+        // BioD's own slab (readrange.d:176-184); BamRead.dup copies (read.d:585-592)
+        _current = BamRead(_b.data[o .. o + _b.block_size[_i]]);               // read.d:482-504
+        _current.associateWithReader(_reader);                                  // read.d:841-843
+    }
+}
+
+/// Drop-in for BamReader on the streaming path (bam/reader.d:80-598).
+class GpuBamReader : IBamSamReader {
+    private biodb_reader* _h;
+    private string _filename;
+    private SamHeader _header;
+    private string _headertext;
+    private ReferenceSequenceInfo[] _refs;
+
+    this(string filename, TaskPool pool = taskPool) {     // the TaskPool is accepted and ignored (reader.d:100-101)
+        _filename = filename;
+        biodb_options o; biodb_default_options(&o);
+        o.want_offsets = 1;
+        if (biodb_open(filename.toStringz, &o, &_h) != BIODB_OK) raise(biodb_open_error());
+        const(char)* t; size_t n;
+        biodb_header_text(_h, &t, &n);
+        _headertext = t[0 .. n].idup;
+        foreach (i; 0 .. biodb_n_refs(_h)) {
+            const(char)* nm; int nl, len;
+            biodb_ref_info(_h, i, &nm, &nl, &len);
+            _refs ~= ReferenceSequenceInfo(nm[0 .. nl].idup, len);
+        }
+    }
+    ~this() { if (_h !is null) biodb_close(_h); }
+
+    SamHeader header() @property { if (_header is null) _header = new SamHeader(_headertext); return _header; }
+    const(ReferenceSequenceInfo)[] reference_sequences() @property const nothrow { return _refs; }
+    string filename() @property const { return _filename; }
+    auto reads(alias IteratePolicy = void)() @property { return GpuBamReadRange!false(_h, this); }
+    auto readsWithOffsets() @property { return GpuBamReadRange!true(_h, this); }
+    std.range.InputRange!BamRead allReads() @property {
+        import std.range : inputRangeObject;
+        return inputRangeObject(reads());
+    }
+    void assumeSequentialProcessing() {}   // batches already reuse their buffer (reader.d:324)
+    package biodb_reader* handle() { return _h; }
+}
+
+/// Pileup column over a GPU column batch; same surface as PileupColumn (pileup.d:236-290) for the fields
+/// MaqSnpCaller reads (snpcallers/maq.d:396-410,468-483).
+struct GpuPileupColumn {
+    private const(biodb_column_batch)* _b;
+    private size_t _c;
+    ulong position() @property const { return _b.position[_c]; }
+    int ref_id() @property const { return _b.ref_id; }
+    size_t coverage() @property const { return cast(size_t)(_b.col_off[_c + 1] - _b.col_off[_c]); }
+    char reference_base() @property const { return 'N'; }
+    const(uint)[] reads() @property const { return _b.read_idx[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]]; }
+    const(uint)[] reads_starting_here() @property const {
+        auto e = cast(size_t)_b.col_off[_c + 1];
+        return _b.read_idx[e - _b.n_starting_here[_c] .. e];
+    }
+    const(char)[] bases() @property const {
+        return cast(const(char)[])_b.base[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]];
+    }
+    const(ubyte)[] base_qualities() @property const { return _b.qual[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]]; }
+}
+
+/// Input range of columns; `makePileup(GpuBamReader, ...)` mirrors pileup.d:683-694, `pileupColumns` pileup.d:509-519.
+struct GpuPileup {
+    private biodb_reader* _h;
+    private biodb_pileup* _p;
+    private biodb_column_batch _b;
+    private size_t _c;
+    private bool _empty;
+    this(biodb_reader* h, bool single_ref, bool use_md_tag, ulong start_from, ulong end_at, bool skip_zero_coverage) {
+        _h = h;
+        biodb_pileup_params prm;
+        prm.single_ref = single_ref; prm.skip_zero_coverage = skip_zero_coverage; prm.use_md_tag = use_md_tag;
+        prm.start_from = start_from; prm.end_at = end_at;
+        if (biodb_pileup_begin(h, &prm, &_p) != BIODB_OK) raise(biodb_last_error(h));
+        fetch();
+    }
+    ~this() { if (_p !is null) { biodb_pileup_end(_p); _p = null; } }
+    @disable this(this);
+    bool empty() @property const { return _empty; }
+    GpuPileupColumn front() @property { return GpuPileupColumn(&_b, _c); }
+    void popFront() { if (++_c >= _b.n_columns) fetch(); }
+    int ref_id() @property { return biodb_pileup_ref_id(_p); }
+    private void fetch() {
+        auto st = biodb_pileup_next(_p, &_b);
+        if (st == BIODB_EOF) { _empty = true; return; }
+        if (st != BIODB_OK) raise(biodb_last_error(_h));
+        _c = 0;
+    }
+}
+
+auto makePileup(GpuBamReader bam, bool use_md_tag = false, ulong start_from = 0, ulong end_at = ulong.max,
+                bool skip_zero_coverage = true) {
+    return GpuPileup(bam.handle, true, use_md_tag, start_from, end_at, skip_zero_coverage);
+}
+auto pileupColumns(GpuBamReader bam, bool use_md_tag = false, bool skip_zero_coverage = true) {
+    return GpuPileup(bam.handle, false, use_md_tag, 0, ulong.max, skip_zero_coverage);
+}

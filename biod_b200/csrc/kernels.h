@@ -9,6 +9,10 @@ namespace biodb {
 // number of kernel launches issued by this library (all streams); read as deltas for biodb_stats
 extern unsigned long long g_kernel_launches;
 
+// Small copies done by a kernel instead of a DMA engine: on the compute stream they must not queue behind the
+// gigabyte-sized device->host copies of the previous batch.  dst/src may be device memory or mapped pinned host memory.
+cudaError_t launch_copy_bytes(void* dst, const void* src, size_t bytes, cudaStream_t st);
+
 // ---- inflate.cu ------------------------------------------------------------------------------
 struct InflateArgs {
   const uint8_t* comp;          // device: compressed file slice

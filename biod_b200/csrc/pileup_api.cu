@@ -170,14 +170,14 @@ static biodb_status load_batch(biodb_pileup* pl) {
     RecordArrays a = p.arrays(0);
     CarryOut o = c.out();
     const size_t n = c.n;
-    PL_TRY(cudaMemcpyAsync(a.pos, o.pos, n * 4, cudaMemcpyDeviceToDevice, st));
-    PL_TRY(cudaMemcpyAsync(a.end_pos, o.end_pos, n * 4, cudaMemcpyDeviceToDevice, st));
-    PL_TRY(cudaMemcpyAsync(a.ref_id, o.ref_id, n * 4, cudaMemcpyDeviceToDevice, st));
-    PL_TRY(cudaMemcpyAsync(a.rec_off, o.rec_off, n * 8, cudaMemcpyDeviceToDevice, st));
-    PL_TRY(cudaMemcpyAsync(a.bin_mq_nl, o.bin_mq_nl, n * 4, cudaMemcpyDeviceToDevice, st));
-    PL_TRY(cudaMemcpyAsync(a.flag_nc, o.flag_nc, n * 4, cudaMemcpyDeviceToDevice, st));
-    PL_TRY(cudaMemcpyAsync(a.l_seq, o.l_seq, n * 4, cudaMemcpyDeviceToDevice, st));
-    PL_TRY(cudaMemcpyAsync(a.block_size, o.block_size, n * 4, cudaMemcpyDeviceToDevice, st));
+    PL_TRY(launch_copy_bytes(a.pos, o.pos, n * 4, st));
+    PL_TRY(launch_copy_bytes(a.end_pos, o.end_pos, n * 4, st));
+    PL_TRY(launch_copy_bytes(a.ref_id, o.ref_id, n * 4, st));
+    PL_TRY(launch_copy_bytes(a.rec_off, o.rec_off, n * 8, st));
+    PL_TRY(launch_copy_bytes(a.bin_mq_nl, o.bin_mq_nl, n * 4, st));
+    PL_TRY(launch_copy_bytes(a.flag_nc, o.flag_nc, n * 4, st));
+    PL_TRY(launch_copy_bytes(a.l_seq, o.l_seq, n * 4, st));
+    PL_TRY(launch_copy_bytes(a.block_size, o.block_size, n * 4, st));
   }
   biodb_status es = ensure_read_scratch(pl, pl->n_view);
   if (es != BIODB_OK) return es;
@@ -193,11 +193,11 @@ static biodb_status load_batch(biodb_pileup* pl) {
     ReadsView v = make_view(pl);
     uint32_t* d_b = pl->bnd.as<uint32_t>();
     pileup_find_groups(v, d_b + 1, d_b, cap, st);
-    PL_TRY(cudaMemcpyAsync(pl->h_bnd.p, d_b, 4, cudaMemcpyDeviceToHost, st));
+    PL_TRY(launch_copy_bytes(pl->h_bnd.p, d_b, 4, st));
     PL_TRY(cudaStreamSynchronize(st));
     uint32_t nbnd = pl->h_bnd.as<uint32_t>()[0];
     if (nbnd) {
-      PL_TRY(cudaMemcpyAsync(pl->h_bnd.as<uint32_t>() + 1, d_b + 1, (size_t)nbnd * 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(launch_copy_bytes(pl->h_bnd.as<uint32_t>() + 1, d_b + 1, (size_t)nbnd * 4, st));
       PL_TRY(cudaStreamSynchronize(st));
       uint32_t* hb = pl->h_bnd.as<uint32_t>() + 1;
       std::sort(hb, hb + nbnd);
@@ -407,7 +407,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     GroupScratch s = scratch(pl);
     int32_t* h = pl->h_small.as<int32_t>();
     // reference id of the group
-    PL_TRY(cudaMemcpyAsync(h, v.ref_id + g0, 4, cudaMemcpyDeviceToHost, st));
+    PL_TRY(launch_copy_bytes(h, v.ref_id + g0, 4, st));
     PL_TRY(cudaMemsetAsync(s.info, 0, 16, st));
     PL_TRY(cudaStreamSynchronize(st));
     const int32_t ref = h[0];
@@ -420,7 +420,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         // read kept fixes the reference of the whole pileup
         uint32_t* d_first = (uint32_t*)(s.info + 2);
         pileup_first_kept(v, g0, g1, pl->prm.start_from, d_first, st);
-        PL_TRY(cudaMemcpyAsync(h, d_first, 4, cudaMemcpyDeviceToHost, st));
+        PL_TRY(launch_copy_bytes(h, d_first, 4, st));
         PL_TRY(cudaStreamSynchronize(st));
         uint32_t first = (uint32_t)h[0];
         if (first == 0xffffffffu) {
@@ -449,8 +449,8 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     p.stats.pileup_ms += p.stage_end();
     const uint32_t ng = g1 - g0;
     const uint32_t t_reads = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
-    PL_TRY(cudaMemcpyAsync(h, s.tmp_u32 + t_reads, 4, cudaMemcpyDeviceToHost, st));           // n_islands
-    PL_TRY(cudaMemcpyAsync(h + 1, s.info, 8, cudaMemcpyDeviceToHost, st));                    // status, last live + 1
+    PL_TRY(launch_copy_bytes(h, s.tmp_u32 + t_reads, 4, st));           // n_islands
+    PL_TRY(launch_copy_bytes(h + 1, s.info, 8, st));                    // status, last live + 1
     PL_TRY(cudaStreamSynchronize(st));
     const uint32_t n_islands = (uint32_t)h[0];
     const int32_t st1 = h[1];
@@ -468,7 +468,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     }
     int64_t E = 0;
     if (trailing) {
-      PL_TRY(cudaMemcpyAsync(h, v.pos + (last_live1 - 1), 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(launch_copy_bytes(h, v.pos + (last_live1 - 1), 4, st));
       PL_TRY(cudaStreamSynchronize(st));
       E = h[0];
       chi = std::min(chi, E);
@@ -481,18 +481,18 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     if (force_lo) {
       // island 0 of the group is the whole group: move its start down to the continuation point
       int32_t lo32 = (int32_t)std::max<int64_t>(clo, INT32_MIN);
-      PL_TRY(cudaMemcpyAsync(h, s.islands.start, 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(launch_copy_bytes(h, s.islands.start, 4, st));
       PL_TRY(cudaStreamSynchronize(st));
       if (h[0] > lo32) {
         h[0] = lo32;
-        PL_TRY(cudaMemcpyAsync(s.islands.start, h, 4, cudaMemcpyHostToDevice, st));
+        PL_TRY(launch_copy_bytes(s.islands.start, h, 4, st));
       }
     }
     p.stage_begin();
     pileup_island_cols(n_islands, s, st);
     p.stats.pileup_ms += p.stage_end();
     const uint32_t t_isl = (uint32_t)((n_islands + SCAN_TILE - 1) / SCAN_TILE);
-    PL_TRY(cudaMemcpyAsync(h, s.tmp_u32b + t_isl, 4, cudaMemcpyDeviceToHost, st));
+    PL_TRY(launch_copy_bytes(h, s.tmp_u32b + t_isl, 4, st));
     PL_TRY(cudaStreamSynchronize(st));
     const uint32_t n_col = (uint32_t)h[0];
     if (n_col > 0x7ff00000u) return pl->fail(BIODB_ERR_NOMEM, "too many pileup columns in one batch; lower blocks_per_batch");
@@ -526,7 +526,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       p.stage_begin();
       pileup_phase2(v, g0, g1, n_islands, n_col, s, c, o, st);
       p.stats.pileup_ms += p.stage_end();
-      PL_TRY(cudaMemcpyAsync(pl->h_small.p, o.col_off + n_col, 8, cudaMemcpyDeviceToHost, st));
+      PL_TRY(launch_copy_bytes(pl->h_small.p, o.col_off + n_col, 8, st));
       PL_TRY(cudaStreamSynchronize(st));
       n_entries = *pl->h_small.as<uint64_t>();
       const bool want_q = pl->prm.want_query_offset != 0;
@@ -569,7 +569,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       } else {
         PL_TRY(cudaEventRecord(os.done, st));
       }
-      PL_TRY(cudaMemcpyAsync(h + 8, s.info, 4, cudaMemcpyDeviceToHost, st));
+      PL_TRY(launch_copy_bytes(h + 8, s.info, 4, st));
       PL_TRY(cudaStreamSynchronize(st));
       if (h[8] != 0) return pl->fail(h[8], "Invalid read - query offset beyond the sequence while building a column");
     }
@@ -587,8 +587,8 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         pileup_carry(v, g0, g1, a.block_size, E, s, dummy, st);
         p.stats.pileup_ms += p.stage_end();
         const uint32_t t_g = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
-        PL_TRY(cudaMemcpyAsync(h, s.tmp_u32 + t_g, 4, cudaMemcpyDeviceToHost, st));
-        PL_TRY(cudaMemcpyAsync(h + 2, s.tmp_u64 + t_g, 8, cudaMemcpyDeviceToHost, st));
+        PL_TRY(launch_copy_bytes(h, s.tmp_u32 + t_g, 4, st));
+        PL_TRY(launch_copy_bytes(h + 2, s.tmp_u64 + t_g, 8, st));
         PL_TRY(cudaStreamSynchronize(st));
         const uint32_t nc = (uint32_t)h[0];
         const uint64_t nbytes = *(uint64_t*)(h + 2);

@@ -253,6 +253,34 @@ __global__ void __launch_bounds__(WARPS * 32) scan_extract_kernel(const uint8_t*
 
 }  // namespace
 
+namespace {
+__global__ void copy_bytes_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t bytes) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 15) == 0) {
+    const uint4* s4 = (const uint4*)src;
+    uint4* d4 = (uint4*)dst;
+    for (size_t n = bytes >> 4; i < n; i += stride) d4[i] = s4[i];
+  } else if ((((uintptr_t)dst | (uintptr_t)src | bytes) & 3) == 0) {
+    const uint32_t* s4 = (const uint32_t*)src;
+    uint32_t* d4 = (uint32_t*)dst;
+    for (size_t n = bytes >> 2; i < n; i += stride) d4[i] = s4[i];
+  } else {
+    for (; i < bytes; i += stride) dst[i] = src[i];
+  }
+}
+}  // namespace
+
+cudaError_t launch_copy_bytes(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  size_t blocks = (bytes / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 2048) blocks = 2048;
+  copy_bytes_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint8_t*)dst, (const uint8_t*)src, bytes);
+  ++g_kernel_launches;
+  return cudaGetLastError();
+}
+
 size_t scan_workspace_bytes(uint32_t n_blocks) {
   size_t nb = n_blocks + 1;
   size_t bytes = 0;

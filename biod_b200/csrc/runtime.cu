@@ -42,7 +42,7 @@ cudaError_t PinBuf::ensure(size_t bytes) {
   if (bytes <= cap) return cudaSuccess;
   size_t ncap = std::max(bytes, cap + cap / 2);
   void* np = nullptr;
-  cudaError_t e = cudaHostAlloc(&np, ncap, cudaHostAllocDefault);
+  cudaError_t e = cudaHostAlloc(&np, ncap, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e != cudaSuccess) return e;
   if (p) cudaFreeHost(p);
   p = np;
@@ -300,7 +300,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   CUDA_TRY(h_status.ensure((size_t)nb * 4 + 16));
   CUDA_TRY(d_ws.ensure(scan_workspace_bytes(nsb), st));
   if (has_carry)
-    CUDA_TRY(cudaMemcpyAsync(d_u.p, d_carry_tail.p, carry_tail_len, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(launch_copy_bytes(d_u.p, d_carry_tail.p, carry_tail_len, st));
   CUDA_TRY(cudaMemcpyAsync(d_tab.p, h_tab.p, tab_bytes, cudaMemcpyHostToDevice, st));
   if (nb) {
     if (!resident) {
@@ -316,7 +316,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     stats.n_blocks += nb;
     stats.compressed_bytes += c1 - c0;
     stats.uncompressed_bytes += off - (has_carry ? carry_tail_len : 0);
-    CUDA_TRY(cudaMemcpyAsync(h_status.p, d_status.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(launch_copy_bytes(h_status.p, d_status.p, (size_t)nb * 4, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const int32_t* hs = h_status.as<int32_t>();
     for (uint32_t i = 0; i < nb; ++i) {
@@ -365,7 +365,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     stage_begin();
     CUDA_TRY(launch_scan_records(d_u.as<uint8_t>(), u_len, d_buoff, nsb2, eof_semantics, ra, d_result.as<uint64_t>(), ws, st));
     stats.scan_ms += stage_end();
-    CUDA_TRY(cudaMemcpyAsync(h_result.p, d_result.p, 32, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(launch_copy_bytes(h_result.p, d_result.p, 32, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const uint64_t* res = h_result.as<uint64_t>();
     if ((int64_t)res[3] == BIODB_ERR_NOMEM) {
@@ -388,7 +388,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   if (!last_batch && tail < u_len) {
     carry_tail_len = u_len - tail;
     CUDA_TRY(d_carry_tail.ensure((size_t)carry_tail_len + 256, st));
-    CUDA_TRY(cudaMemcpyAsync(d_carry_tail.p, d_u.as<uint8_t>() + tail, carry_tail_len, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(launch_copy_bytes(d_carry_tail.p, d_u.as<uint8_t>() + tail, carry_tail_len, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (const Seg& s : segs) {
       uint64_t a = std::max(s.ustart, tail), b = s.ustart + s.len;
