@@ -299,6 +299,12 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
   uint32_t flushed = 0;     // bytes already stored to HBM
   // deferred far match: bytes already requested from L2, to be stored into the ring later
   uint32_t pend_len = 0, pend_o = 0, pv0 = 0, pv1 = 0;
+  // fused record-chain walk (records.cu): next record start inside this block, records / cigar words found so far
+  const bool walking = a.walk.rel != nullptr;
+  const uint32_t sb = blk + a.walk.sb_offset;
+  const uint32_t win0 = (walking && blk == 0) ? a.walk.in0 : 0;
+  uint32_t wnext = win0, wcnt = 0, wncig = 0;
+  int wbad = WALK_OK;
 #define OPOS() (o - oa)
 
   // pull one 32-bit word from the staging ring (warp-uniform)
@@ -331,6 +337,34 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
       __syncwarp();
     }
   };
+  // little-endian u32 at block-relative offset x, read from the output ring
+  auto ring32 = [&](uint32_t x) -> uint32_t {
+    const uint32_t r0 = oa + x;
+    return lds8(ring + (r0 & OMASK)) | (lds8(ring + ((r0 + 1) & OMASK)) << 8) | (lds8(ring + ((r0 + 2) & OMASK)) << 16) |
+           (lds8(ring + ((r0 + 3) & OMASK)) << 24);
+  };
+  // follow the block_size chain (readrange.d:118-173) over the records whose 24 leading bytes are already produced
+  auto walk_upto = [&](uint32_t avail, bool final) {
+    while (wbad == WALK_OK && wnext < isize) {
+      if (wnext + 24 > avail) {
+        if (final) wbad = WALK_INCOMPLETE;     // the header straddles the block end: the resolve kernel finishes it
+        break;
+      }
+      const int32_t bs = (int32_t)ring32(wnext);
+      if (bs < 32) { wbad = WALK_BAD_SIZE; break; }
+      if (obase + wnext + 4 + (uint64_t)bs > a.walk.u_len) { wbad = WALK_TAIL; break; }
+      const uint32_t bin_mq_nl = ring32(wnext + 12), flag_nc = ring32(wnext + 16);
+      const int32_t l_seq = (int32_t)ring32(wnext + 20);
+      const uint32_t lname = bin_mq_nl & 0xFF, nc = flag_nc & 0xFFFF;
+      const uint64_t need = 32ull + lname + 4ull * nc + (l_seq > 0 ? ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq : 0);
+      if (l_seq < 0 || need > (uint64_t)bs) { wbad = WALK_BAD_FIELDS; break; }
+      // relative to the chain entry of the block, as scan_extract_kernel expects (block_uoff[0] includes in0)
+      if (lane == 0 && wcnt < (uint32_t)SCAN_SLOTS) a.walk.rel[(size_t)sb * SCAN_SLOTS + wcnt] = (uint16_t)(wnext - win0);
+      ++wcnt;
+      wncig += nc;
+      wnext += 4 + (uint32_t)bs;
+    }
+  };
   auto flush_to = [&](uint32_t fe) {
     // copy ring bytes [flushed, fe) to HBM; 16-byte vector stores where the global address allows
     uint32_t f = flushed;
@@ -357,6 +391,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
       if (OPOS() > isize) { status = Z_BUF; return; }
       complete_pending();
       __syncwarp();
+      if (walking) walk_upto(OPOS(), false);
       const uint32_t fe = OPOS() - (o & (FLUSH - 1));
       if (fe > flushed) flush_to(fe);
     }
@@ -597,9 +632,19 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
   if (status == 0) {
     complete_pending();
     __syncwarp();
+    if (walking) walk_upto(isize, true);
     if (OPOS() > flushed) flush_to(OPOS());
   }
-  if (lane == 0) a.status[blk] = status;
+  if (lane == 0) {
+    a.status[blk] = status;
+    if (walking) {
+      a.walk.cnt[sb] = wcnt;
+      a.walk.ncig[sb] = wncig;
+      a.walk.in[sb] = obase + ((blk == 0) ? a.walk.in0 : 0);
+      a.walk.out[sb] = obase + wnext;
+      a.walk.bad[sb] = status ? WALK_TAIL : wbad;
+    }
+  }
 #undef REFILL
 #undef DROP
 #undef CONSUMED

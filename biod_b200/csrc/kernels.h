@@ -14,6 +14,23 @@ extern unsigned long long g_kernel_launches;
 cudaError_t launch_copy_bytes(void* dst, const void* src, size_t bytes, cudaStream_t st);
 
 // ---- inflate.cu ------------------------------------------------------------------------------
+constexpr int SCAN_SLOTS = 2048;   // max records that can start inside one 64 KiB block (65536/37 < 2048)
+
+// Optional fused record-chain walk (see records.cu): the inflate warp follows the block_size chain of its own
+// block out of the shared-memory output ring, assuming a record starts at the block boundary.
+struct WalkOut {
+  uint16_t* rel;      // [n_scan_blocks * SCAN_SLOTS] record starts relative to the block start (nullptr = no walk)
+  uint32_t* cnt;
+  uint32_t* ncig;
+  uint64_t* out;      // absolute offset (in the slice) where the chain stopped
+  uint64_t* in;       // absolute offset where it entered
+  int32_t* bad;       // stop reason (WALK_*)
+  uint32_t sb_offset; // scan-block index of BGZF block 0 (1 when a carried tail forms pseudo block 0)
+  uint32_t in0;       // entry offset inside block 0 (bytes of header in front of the first record)
+  uint64_t u_len;     // length of the whole slice
+};
+enum { WALK_OK = 0, WALK_TAIL = 1, WALK_BAD_SIZE = 2, WALK_BAD_FIELDS = 3, WALK_INCOMPLETE = 4 };
+
 struct InflateArgs {
   const uint8_t* comp;          // device: compressed file slice
   const uint64_t* payload_off;  // [n] byte offset of each block's raw-DEFLATE payload inside comp
@@ -23,6 +40,7 @@ struct InflateArgs {
   uint8_t* out;
   int32_t* status;              // [n] 0 / Z_DATA_ERROR / Z_BUF_ERROR
   uint32_t n_blocks;
+  WalkOut walk;
 };
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st);
 size_t inflate_smem_bytes();
@@ -42,7 +60,6 @@ struct RecordArrays {
   uint64_t capacity;
   uint64_t cigar_capacity;
 };
-constexpr int SCAN_SLOTS = 2048;   // max records that can start inside one 64 KiB block (65536/37 < 2048)
 struct ScanWorkspace {            // device scratch, sized by scan_workspace_bytes(n_blocks)
   uint16_t* rel;                  // [n_blocks*SCAN_SLOTS] record starts relative to the block start
   uint32_t* cnt;                  // [n_blocks] records whose prefix starts in the block
@@ -56,8 +73,10 @@ struct ScanWorkspace {            // device scratch, sized by scan_workspace_byt
 size_t scan_workspace_bytes(uint32_t n_blocks);
 ScanWorkspace carve_scan_workspace(void* base, uint32_t n_blocks);
 // result (device, 4 x u64): n_records, tail offset, n_cigar_words, status
+// n_walk: number of leading scan blocks whose chain still has to be walked by scan_walk_kernel (all of them,
+// or only the carried-tail pseudo block when the inflate kernel already walked the rest).
 cudaError_t launch_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t* block_uoff, uint32_t n_blocks,
-                                int final_slice, const RecordArrays& out, uint64_t* result, const ScanWorkspace& ws,
-                                cudaStream_t st);
+                                uint32_t n_walk, int final_slice, const RecordArrays& out, uint64_t* result,
+                                const ScanWorkspace& ws, cudaStream_t st);
 
 }  // namespace biodb

@@ -35,13 +35,13 @@ __device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
 // consume bits of CIGAR_TYPE (bam/cigar.d:116): bit0 query-consuming, bit1 reference-consuming
 __device__ __forceinline__ uint32_t cigar_consume(uint32_t raw) { return (0x3C1A7u >> ((raw & 0xF) * 2)) & 3; }
 
-enum { WALK_OK = 0, WALK_TAIL = 1, WALK_BAD_SIZE = 2, WALK_BAD_FIELDS = 3 };
 
 // Walk the record chain from absolute offset `p` while record starts lie inside [*, end).
 // Returns the stop reason; *out = offset where the walk stopped.
 __device__ int walk_block(const uint8_t* u, uint64_t u_len, uint64_t p, uint64_t blk_start, uint64_t end,
-                          uint16_t* rel, uint32_t* cnt_out, uint32_t* ncig_out, uint64_t* out) {
-  uint32_t cnt = 0, ncig = 0;
+                          uint16_t* rel, uint32_t* cnt_out, uint32_t* ncig_out, uint64_t* out, uint32_t cnt0 = 0,
+                          uint32_t ncig0 = 0) {
+  uint32_t cnt = cnt0, ncig = ncig0;
   int why = WALK_OK;
   while (p < end) {
     if (p + 4 > u_len) { why = WALK_TAIL; break; }
@@ -98,20 +98,26 @@ __global__ void __launch_bounds__(256) scan_resolve_kernel(const uint8_t* __rest
   }
   if (t == 0) first_fail = n_blocks;
   __syncthreads();
-  // block b is mis-speculated if the chain does not arrive exactly at its start
-  for (uint32_t b = 1 + t; b < n_blocks; b += blockDim.x)
-    if (ws.out[b - 1] != block_uoff[b] || ws.bad[b - 1] != WALK_OK) atomicMin(&first_fail, b);
+  // block b needs the sequential repair if the chain does not arrive exactly at its start, if the walk of the
+  // previous block stopped early, or if its own (fused) walk could not finish inside the block
+  for (uint32_t b = t; b < n_blocks; b += blockDim.x) {
+    bool fail = ws.bad[b] == WALK_INCOMPLETE;
+    if (b > 0 && (ws.out[b - 1] != block_uoff[b] || ws.bad[b - 1] != WALK_OK)) fail = true;
+    if (fail) atomicMin(&first_fail, b);
+  }
   __syncthreads();
   if (t == 0) {
     uint32_t b = first_fail;
     if (b >= n_blocks) {
       s_last = n_blocks - 1;
       s_why = ws.bad[n_blocks - 1];
-    } else if (ws.bad[b - 1] != WALK_OK) {
+    } else if (b > 0 && ws.bad[b - 1] != WALK_OK && ws.bad[b - 1] != WALK_INCOMPLETE) {
       s_last = b - 1;
       s_why = ws.bad[b - 1];
     } else {
-      uint64_t in = ws.out[b - 1];
+      // entry point of block b: where the previous block's chain left off (blocks before b are all consistent)
+      uint64_t in = (b == 0) ? ws.in[0] : ws.out[b - 1];
+      if (b > 0 && ws.bad[b - 1] == WALK_INCOMPLETE) { --b; in = ws.in[b]; }
       uint32_t last = n_blocks - 1;
       int why = WALK_OK;
       for (; b < n_blocks; ++b) {
@@ -125,6 +131,12 @@ __global__ void __launch_bounds__(256) scan_resolve_kernel(const uint8_t* __rest
           uint64_t out;
           ws.bad[b] = walk_block(u, u_len, in, start, end, ws.rel + (size_t)b * SCAN_SLOTS, &cnt, &ncig, &out);
           ws.cnt[b] = cnt; ws.ncig[b] = ncig; ws.out[b] = out; ws.in[b] = in;
+        } else if (ws.bad[b] == WALK_INCOMPLETE) {   // finish a walk whose last header straddles the block end
+          uint32_t cnt, ncig;
+          uint64_t out;
+          ws.bad[b] = walk_block(u, u_len, ws.out[b], start, end, ws.rel + (size_t)b * SCAN_SLOTS, &cnt, &ncig, &out,
+                                 ws.cnt[b], ws.ncig[b]);
+          ws.cnt[b] = cnt; ws.ncig[b] = ncig; ws.out[b] = out;
         }
         if (ws.bad[b] != WALK_OK) { last = b; why = ws.bad[b]; break; }
         in = ws.out[b];
@@ -306,11 +318,12 @@ ScanWorkspace carve_scan_workspace(void* base, uint32_t n_blocks) {
 }
 
 cudaError_t launch_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t* block_uoff, uint32_t n_blocks,
-                                int final_slice, const RecordArrays& out, uint64_t* result, const ScanWorkspace& ws,
-                                cudaStream_t st) {
+                                uint32_t n_walk, int final_slice, const RecordArrays& out, uint64_t* result,
+                                const ScanWorkspace& ws, cudaStream_t st) {
   uint32_t grid = (n_blocks + WARPS - 1) / WARPS;
-  if (n_blocks) scan_walk_kernel<<<grid, WARPS * 32, 0, st>>>(u, u_len, block_uoff, n_blocks, ws);
-  g_kernel_launches += n_blocks ? 3 : 1;
+  if (n_walk > n_blocks) n_walk = n_blocks;
+  if (n_walk) scan_walk_kernel<<<(n_walk + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(u, u_len, block_uoff, n_walk, ws);
+  g_kernel_launches += (n_blocks ? 2 : 1) + (n_walk ? 1 : 0);
   scan_resolve_kernel<<<1, 256, 0, st>>>(u, u_len, block_uoff, n_blocks, final_slice, ws, out, result);
   if (n_blocks) scan_extract_kernel<<<grid, WARPS * 32, 0, st>>>(u, block_uoff, n_blocks, ws, out);
   return cudaGetLastError();

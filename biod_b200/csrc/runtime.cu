@@ -308,7 +308,13 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
       stats.h2d_bytes += c1 - c0;
     }
     const uint8_t* comp = resident ? r->d_file.as<uint8_t>() + c0 : d_comp.as<uint8_t>();
-    InflateArgs ia{comp, d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb};
+    InflateArgs ia{comp, d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb, WalkOut{}};
+    if (!raw_mode) {
+      // fused record-chain walk: the inflate warps follow the block_size chain of their own block
+      ScanWorkspace w0 = carve_scan_workspace(d_ws.p, nsb);
+      ia.walk = WalkOut{w0.rel, w0.cnt, w0.ncig, w0.out, w0.in, w0.bad, has_carry ? 1u : 0u,
+                        has_carry ? 0u : (uint32_t)(h_buoff[0]), u_len};
+    }
     stage_begin();
     CUDA_TRY(launch_inflate(ia, st));
     stats.inflate_ms += stage_end();
@@ -363,7 +369,9 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     }
     RecordArrays ra = arrays(front_slots);
     stage_begin();
-    CUDA_TRY(launch_scan_records(d_u.as<uint8_t>(), u_len, d_buoff, nsb2, eof_semantics, ra, d_result.as<uint64_t>(), ws, st));
+    // only the carried-tail pseudo block still needs the stand-alone walk kernel
+    CUDA_TRY(launch_scan_records(d_u.as<uint8_t>(), u_len, d_buoff, nsb2, (has_carry || nb == 0) ? 1u : 0u, eof_semantics, ra,
+                                 d_result.as<uint64_t>(), ws, st));
     stats.scan_ms += stage_end();
     CUDA_TRY(launch_copy_bytes(h_result.p, d_result.p, 32, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -716,7 +724,7 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
                                const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
                                int32_t* status, uint32_t* crc, void* stream) {
   (void)crc;
-  InflateArgs ia{comp, payload_off, cdata_size, out_off, isize, out, status, n_blocks};
+  InflateArgs ia{comp, payload_off, cdata_size, out_off, isize, out, status, n_blocks, WalkOut{}};
   return launch_inflate(ia, (cudaStream_t)stream) == cudaSuccess ? BIODB_OK : BIODB_ERR_CUDA;
 }
 
@@ -729,7 +737,7 @@ biodb_status biodb_dev_scan_records(const uint8_t* u, uint64_t u_len, const uint
   RecordArrays ra{o->rec_off, o->block_size, o->ref_id, o->pos, o->end_pos, o->bin_mq_nl, o->flag_nc, o->l_seq,
                   o->cigar_off, o->cigar, o->capacity, o->cigar_capacity};
   ScanWorkspace ws = carve_scan_workspace(workspace, n_blocks);
-  return launch_scan_records(u, u_len, block_uoff, n_blocks, final_slice, ra, result, ws, (cudaStream_t)stream) == cudaSuccess
+  return launch_scan_records(u, u_len, block_uoff, n_blocks, n_blocks, final_slice, ra, result, ws, (cudaStream_t)stream) == cudaSuccess
              ? BIODB_OK
              : BIODB_ERR_CUDA;
 }
