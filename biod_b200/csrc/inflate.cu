@@ -36,6 +36,9 @@ namespace {
 #ifndef BIODB_OUT_RING
 #define BIODB_OUT_RING 4096
 #endif
+#ifndef BIODB_LIT_UNROLL2
+#define BIODB_LIT_UNROLL2 0
+#endif
 #ifndef BIODB_LIT_BITS
 #define BIODB_LIT_BITS 10
 #endif
@@ -531,6 +534,29 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
       // slot (one shared-memory wavefront); it runs while at least LIT_BITS of the 32 bits are unread
       {
         uint32_t lo = (uint32_t)bitbuf, used = 0;
+#if BIODB_LIT_UNROLL2
+        // two literals per trip: the second lookup is issued before the first literal is known to be one
+        while (true) {
+          e = lds16(lutl + ((lo << 1) & (((1u << LIT_BITS) - 1) << 1)));
+          const uint32_t cl = e >> 12;
+          const uint32_t lo1 = lo >> cl;
+          const uint32_t e1 = lds16(lutl + ((lo1 << 1) & (((1u << LIT_BITS) - 1) << 1)));
+          if (e & (3u << 8)) break;     // not a literal
+          sts8(ring + (o & OMASK), e);
+          ++o;
+          lo = lo1;
+          used += cl;
+          if (used > 32 - LIT_BITS) break;
+          e = e1;
+          if (e & (3u << 8)) break;
+          sts8(ring + (o & OMASK), e);
+          ++o;
+          const uint32_t cl1 = e >> 12;
+          lo >>= cl1;
+          used += cl1;
+          if (used > 32 - LIT_BITS) break;
+        }
+#else
         while (true) {
           e = lds16(lutl + ((lo << 1) & (((1u << LIT_BITS) - 1) << 1)));
           if (e & (3u << 8)) break;     // not a literal
@@ -541,6 +567,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
           used += cl;
           if (used > 32 - LIT_BITS) break;
         }
+#endif
         DROP(used);
       }
       if ((e & (3u << 8)) == 0) continue;   // ran low on bits after a literal

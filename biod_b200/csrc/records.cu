@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(WARPS * 32) scan_walk_kernel(const uint8_t* __
 }
 
 // Verify the speculation, repair it sequentially where it failed, then scan the per-block counts.
-__global__ void __launch_bounds__(256) scan_resolve_kernel(const uint8_t* __restrict__ u, uint64_t u_len,
+__global__ void __launch_bounds__(1024) scan_resolve_kernel(const uint8_t* __restrict__ u, uint64_t u_len,
                                                            const uint64_t* __restrict__ block_uoff, uint32_t n_blocks,
                                                            int final_slice, ScanWorkspace ws, RecordArrays ra,
                                                            uint64_t* __restrict__ result) {
@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(256) scan_resolve_kernel(const uint8_t* __rest
   }
   __syncthreads();
   const uint32_t last = s_last;
-  // exclusive scans of cnt / ncig; blocks past `last` hold no records
+  // exclusive scans of cnt / ncig; blocks past `last` hold no records.  Both 32-bit counts ride in one u64
+  // (records < 2^32 and cigar words < 2^32 per slice) through a shuffle-based block scan.
   for (uint32_t base = 0; base < n_blocks + 1; base += blockDim.x) {
     const uint32_t b = base + t;
     uint64_t c = 0, g = 0;
@@ -158,23 +159,28 @@ __global__ void __launch_bounds__(256) scan_resolve_kernel(const uint8_t* __rest
       c = ws.cnt[b];
       g = ws.ncig[b];
     }
-    s_scan[0][t] = c;
-    s_scan[1][t] = g;
+    const uint32_t lane = t & 31, wid = t >> 5;
+    uint64_t vc = c, vg = g;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint64_t oc = __shfl_up_sync(0xffffffffu, vc, d), og = __shfl_up_sync(0xffffffffu, vg, d);
+      if (lane >= (uint32_t)d) { vc += oc; vg += og; }
+    }
+    if (lane == 31) { s_scan[0][wid] = vc; s_scan[1][wid] = vg; }
     __syncthreads();
-    for (uint32_t off = 1; off < blockDim.x; off <<= 1) {
-      uint64_t a0 = 0, a1 = 0;
-      if (t >= off) { a0 = s_scan[0][t - off]; a1 = s_scan[1][t - off]; }
-      __syncthreads();
-      s_scan[0][t] += a0;
-      s_scan[1][t] += a1;
-      __syncthreads();
+    uint64_t pc = 0, pg = 0, tc = 0, tg = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w) {
+      const uint64_t xc = s_scan[0][w], xg = s_scan[1][w];
+      if (w < wid) { pc += xc; pg += xg; }
+      tc += xc;
+      tg += xg;
     }
     if (b <= n_blocks) {
-      ws.rec_base[b] = s_carry[0] + s_scan[0][t] - c;
-      ws.cig_base[b] = s_carry[1] + s_scan[1][t] - g;
+      ws.rec_base[b] = s_carry[0] + pc + vc - c;
+      ws.cig_base[b] = s_carry[1] + pg + vg - g;
     }
     __syncthreads();
-    if (t == blockDim.x - 1) { s_carry[0] += s_scan[0][t]; s_carry[1] += s_scan[1][t]; }
+    if (t == 0) { s_carry[0] += tc; s_carry[1] += tg; }
     __syncthreads();
   }
   if (t == 0) {
@@ -324,7 +330,7 @@ cudaError_t launch_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t
   if (n_walk > n_blocks) n_walk = n_blocks;
   if (n_walk) scan_walk_kernel<<<(n_walk + WARPS - 1) / WARPS, WARPS * 32, 0, st>>>(u, u_len, block_uoff, n_walk, ws);
   g_kernel_launches += (n_blocks ? 2 : 1) + (n_walk ? 1 : 0);
-  scan_resolve_kernel<<<1, 256, 0, st>>>(u, u_len, block_uoff, n_blocks, final_slice, ws, out, result);
+  scan_resolve_kernel<<<1, 1024, 0, st>>>(u, u_len, block_uoff, n_blocks, final_slice, ws, out, result);
   if (n_blocks) scan_extract_kernel<<<grid, WARPS * 32, 0, st>>>(u, block_uoff, n_blocks, ws, out);
   return cudaGetLastError();
 }
