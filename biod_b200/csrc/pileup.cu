@@ -56,24 +56,35 @@ __global__ void find_groups_kernel(ReadsView v, uint32_t* boundaries, uint32_t* 
 // ---- per-read preparation: liveness, CIGAR validity, sortedness ------------------------------
 // info[0] = error status, info[1] = index+1 of the last live read, info[2] = index+1 of first read with
 // end >= start_from (for the prefix-drop rule, pileup.d:482-489)
-__global__ void prep_kernel(ReadsView v, uint32_t g0, uint32_t g1, uint32_t drop_before, int32_t* eend, int32_t* info) {
+__global__ void prep_kernel(ReadsView v, uint32_t g0, uint32_t g1, uint32_t drop_before, int32_t* eend, uint4* rinfo,
+                            int32_t* info) {
   uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= g1) return;
   int32_t pos = v.pos[j], end = v.end_pos[j];
   bool live = (int32_t)((uint32_t)end - (uint32_t)pos) > 0 && j >= drop_before;   // basesCovered() > 0 (pileup.d:481)
   if (live) {
-    // PileupRead constructor (pileup.d:175-192): first reference-consuming op that is not N
+    // PileupRead constructor (pileup.d:175-192): first reference-consuming op that is not N; query-consuming
+    // ops in front of it (S, I) advance the query offset
     const uint8_t* rec = record_body(v, j);
     uint32_t lname = v.bin_mq_nl[j] & 0xFF, nc = v.flag_nc[j] & 0xFFFF;
     const uint8_t* cg = rec + 32 + lname;
     bool ok = false, skipped_n = false;
-    for (uint32_t k = 0; k < nc; ++k) {
+    uint32_t qoff0 = 0, k = 0, first_t = 0;
+    for (; k < nc; ++k) {
       uint32_t raw = ld32u(cg + 4 * k);
-      if (consume(raw) & 2) {
-        if ((raw & 0xF) != 3) { ok = true; break; }
+      uint32_t t = consume(raw);
+      if (t & 2) {
+        if ((raw & 0xF) != 3) { ok = true; first_t = t; break; }
         if (raw >> 4) skipped_n = true;
+      } else if (t & 1) {
+        qoff0 += raw >> 4;
       }
     }
+    // "simple" read: that op is M/=/X and no other reference-consuming op follows, so the cursor at reference
+    // offset k is just query offset qoff0 + k
+    bool simple = ok && first_t == 3;
+    for (uint32_t q = k + 1; simple && q < nc; ++q)
+      if (consume(ld32u(cg + 4 * q)) & 2) simple = false;
     if (!ok || skipped_n) atomicCAS(&info[0], 0, -7);          // BIODB_ERR_CIGAR
     if (pos < 0) atomicCAS(&info[0], 0, -8);
     if (j > g0) {
@@ -82,6 +93,9 @@ __global__ void prep_kernel(ReadsView v, uint32_t g0, uint32_t g1, uint32_t drop
       if (plive && pp > pos) atomicCAS(&info[0], 0, -8);       // BIODB_ERR_UNSORTED
     }
     atomicMax(&info[1], (int32_t)(j + 1));
+    const uint64_t seq = (uint64_t)(uintptr_t)(cg + 4 * nc);
+    const uint32_t gidx = j < v.n_carry ? v.carry_gidx[j] : (uint32_t)(v.first_index + (j - v.n_carry));
+    rinfo[j] = make_uint4((uint32_t)seq, (uint32_t)(seq >> 32), (qoff0 & 0x7fffffffu) | (simple ? 0x80000000u : 0u), gidx);
   }
   eend[j] = live ? end : DEAD;
 }
@@ -172,7 +186,7 @@ __global__ void colpos_kernel(IslandTable t, const uint32_t* colbase, uint32_t n
 }
 
 // ---- column entries -------------------------------------------------------------------------------
-struct Entry { uint8_t base, qual; uint32_t qoff; bool bad; };
+struct Entry { uint8_t base, qual; uint32_t qoff; };
 
 // CIGAR cursor of read `rec` at reference offset k from its position (PileupRead ctor + k x incrementPosition,
 // pileup.d:175-222) and the base/quality there (pileup.d:115-134, read.d:364-383, base.d:85).
@@ -183,7 +197,6 @@ __device__ __forceinline__ Entry cursor_at(const uint8_t* rec, uint32_t lname, u
   Entry en;
   en.base = '-';
   en.qual = 255;
-  en.bad = false;
   uint32_t qoff = 0, i = 0, raw = 0, t = 0;
   for (; i < nc; ++i) {
     raw = ld32u(cg + 4 * i);
@@ -227,17 +240,35 @@ __device__ __forceinline__ Entry cursor_at(const uint8_t* rec, uint32_t lname, u
 constexpr int ENT_WARPS = 8;
 constexpr int COLS_PER_WARP = 8;
 
+// 4-bit code -> IUPAC character without a memory lookup: "=ACMGRSV" "TWYHKDBN" packed little-endian (base.d:85)
+__device__ __forceinline__ uint32_t base_char(uint32_t code) {
+  const uint64_t t = (code & 8) ? 0x4E42444B48595754ull : 0x565352474D43413Dull;
+  return (uint32_t)(t >> ((code & 7) * 8)) & 0xFF;
+}
+
 __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, const int32_t* __restrict__ eend,
-                                                                 ColumnScratch c, ColumnOutput o, uint32_t n_col,
-                                                                 int32_t* info) {
+                                                                 const uint4* __restrict__ rinfo, ColumnScratch c,
+                                                                 ColumnOutput o, uint32_t n_col, int32_t* info) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = blockIdx.x * ENT_WARPS + (threadIdx.x >> 5);
   const uint32_t lt = (1u << lane) - 1;
-  uint32_t c0 = warp * COLS_PER_WARP;
-  for (uint32_t col = c0; col < c0 + COLS_PER_WARP && col < n_col; ++col) {
-    const int64_t p = (int64_t)o.col_pos[col];
-    uint32_t hi = c.hi[col], lo = c.lo[col];
-    uint64_t off = o.col_off[col];
+  const uint32_t c0 = warp * COLS_PER_WARP;
+  if (c0 >= n_col) return;
+  // the warp's columns: one lane each loads position / window / offset, the rest is broadcast by shuffles
+  uint32_t my_p = 0, my_hi = 0, my_lo = 0;
+  uint64_t my_off = 0;
+  if (lane < COLS_PER_WARP && c0 + lane < n_col) {
+    my_p = (uint32_t)o.col_pos[c0 + lane];
+    my_hi = c.hi[c0 + lane];
+    my_lo = c.lo[c0 + lane];
+    my_off = o.col_off[c0 + lane];
+  }
+  const uint32_t ncols = min((uint32_t)COLS_PER_WARP, n_col - c0);
+  for (uint32_t ci = 0; ci < ncols; ++ci) {
+    const int32_t p = (int32_t)__shfl_sync(0xffffffffu, my_p, ci);       // BAM positions are int32 (read.d:93)
+    const uint32_t hi = __shfl_sync(0xffffffffu, my_hi, ci);
+    uint32_t lo = __shfl_sync(0xffffffffu, my_lo, ci);
+    uint64_t off = __shfl_sync(0xffffffffu, my_off, ci);
     if (hi == 0) continue;
     lo = lo ? lo - 1 : 0;
     for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
@@ -245,20 +276,39 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
       bool live = false;
       int32_t pos = 0;
       if (j < hi) {
-        int32_t e = eend[j];
+        const int32_t e = eend[j];
         pos = v.pos[j];
-        live = e != DEAD && (int64_t)pos <= p && (int64_t)e > p;
+        live = e != DEAD && pos <= p && e > p;
       }
       const uint32_t m = __ballot_sync(0xffffffffu, live);
       if (live) {
         const uint64_t slot = off + __popc(m & lt);
-        const uint8_t* rec = record_body(v, j);
-        Entry en = cursor_at(rec, v.bin_mq_nl[j] & 0xFF, v.flag_nc[j] & 0xFFFF, v.l_seq[j], (uint32_t)(p - pos));
-        if (en.bad) atomicCAS(&info[0], 0, -7);
-        o.read_idx[slot] = j < v.n_carry ? v.carry_gidx[j] : (uint32_t)(v.first_index + (j - v.n_carry));
-        o.base[slot] = en.base;
-        o.qual[slot] = en.qual;
-        if (o.qoff) o.qoff[slot] = en.qoff;
+        const uint4 ri = rinfo[j];
+        const uint32_t k = (uint32_t)(p - pos);
+        uint32_t base = '-', qual = 255, qoff;
+        if (ri.z & 0x80000000u) {
+          // single M/=/X run: query offset is linear in the column (pileup.d:195-203)
+          const int32_t lseq = v.l_seq[j];
+          const uint8_t* seq = (const uint8_t*)(uintptr_t)(((uint64_t)ri.y << 32) | ri.x);
+          qoff = (ri.z & 0x7fffffffu) + k;
+          if (qoff < (uint32_t)lseq) {
+            const uint32_t byte = __ldg(seq + (qoff >> 1));
+            base = base_char((qoff & 1) ? (byte & 0xF) : (byte >> 4));
+            qual = __ldg(seq + (((uint32_t)lseq + 1) >> 1) + qoff);
+          } else {
+            base = 0;      // SEQ shorter than the CIGAR says: see cursor_at
+          }
+        } else {
+          const uint8_t* rec = record_body(v, j);
+          Entry en = cursor_at(rec, v.bin_mq_nl[j] & 0xFF, v.flag_nc[j] & 0xFFFF, v.l_seq[j], k);
+          base = en.base;
+          qual = en.qual;
+          qoff = en.qoff;
+        }
+        o.read_idx[slot] = ri.w;
+        o.base[slot] = (uint8_t)base;
+        o.qual[slot] = (uint8_t)qual;
+        if (o.qoff) o.qoff[slot] = qoff;
       }
       off += __popc(m);
     }
@@ -329,7 +379,7 @@ void pileup_first_kept(const ReadsView& v, uint32_t g0, uint32_t g1, uint64_t st
 void pileup_phase1(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t drop_before, int skip_zero, int64_t clo,
                    int64_t chi, GroupScratch& s, cudaStream_t st) {
   const uint32_t n = g1 - g0;
-  launch1d(prep_kernel, n, st, v, g0, g1, drop_before, s.eend, s.info);
+  launch1d(prep_kernel, n, st, v, g0, g1, drop_before, s.eend, s.rinfo, s.info);
   device_scan<true>(s.eend + g0, s.pm + g0, n, s.tmp_i32, OpMax(), DEAD, st);
   launch1d(island_flag_kernel, n, st, v, g0, g1, s.eend, s.pm, skip_zero, s.flag);
   device_scan<true>(s.flag + g0, s.iid1 + g0, n, s.tmp_u32, OpAdd(), 0u, st);
@@ -365,7 +415,7 @@ void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnS
   if (n_col == 0) return;
   uint32_t warps = (n_col + COLS_PER_WARP - 1) / COLS_PER_WARP;
   uint32_t grid = (warps + ENT_WARPS - 1) / ENT_WARPS;
-  entries_kernel<<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, c, o, n_col, s.info);
+  entries_kernel<<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
   ++g_kernel_launches;
 }
 

@@ -34,6 +34,7 @@ struct IslandTable {
 struct GroupScratch {            // sized by read capacity
   int32_t* eend;                 // end_pos of live reads, INT32_MIN for filtered ones
   int32_t* pm;                   // running max of eend
+  uint4* rinfo;                  // per live read: {seq pointer lo, hi, query offset at the first column | simple<<31, file-order index}
   uint32_t* flag;                // island-start flags
   uint32_t* iid1;                // 1-based island id
   IslandTable islands;

@@ -71,7 +71,7 @@ struct biodb_pileup {
   uint32_t n_view = 0, n_carry_view = 0;
   uint64_t first_index = 0;
   // scratch
-  DevBuf g[12], tmp[4], info, bnd, cs[3];
+  DevBuf g[13], tmp[4], info, bnd, cs[3];
   size_t read_cap = 0, col_cap = 0;
   PinBuf h_small, h_bnd;
   uint64_t tot_cols = 0, tot_entries = 0;
@@ -125,6 +125,7 @@ static biodb_status ensure_read_scratch(biodb_pileup* pl, size_t n) {
     size_t b = cap * esz[k] * (k == 10 ? 2 : 1);
     PL_TRY(pl->g[k].ensure(b, st));
   }
+  PL_TRY(pl->g[12].ensure(cap * 16, st));
   pl->read_cap = cap;
   return BIODB_OK;
 }
@@ -142,6 +143,7 @@ static biodb_status ensure_tmp(biodb_pileup* pl, size_t elems) {
 static GroupScratch scratch(biodb_pileup* pl) {
   GroupScratch s;
   s.eend = pl->g[0].as<int32_t>(); s.pm = pl->g[1].as<int32_t>(); s.flag = pl->g[2].as<uint32_t>();
+  s.rinfo = pl->g[12].as<uint4>();
   s.iid1 = pl->g[3].as<uint32_t>();
   s.islands.start = pl->g[4].as<int32_t>(); s.islands.end = pl->g[5].as<int32_t>();
   s.islands.first = pl->g[6].as<uint32_t>(); s.islands.cs = pl->g[7].as<int64_t>();
