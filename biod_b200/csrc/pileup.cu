@@ -238,7 +238,7 @@ __device__ __forceinline__ Entry cursor_at(const uint8_t* rec, uint32_t lname, u
 }
 
 constexpr int ENT_WARPS = 8;
-constexpr int COLS_PER_WARP = 8;
+constexpr int CHUNK = 32;            // columns per warp
 
 // 4-bit code -> IUPAC character without a memory lookup: "=ACMGRSV" "TWYHKDBN" packed little-endian (base.d:85)
 __device__ __forceinline__ uint32_t base_char(uint32_t code) {
@@ -246,61 +246,74 @@ __device__ __forceinline__ uint32_t base_char(uint32_t code) {
   return (uint32_t)(t >> ((code & 7) * 8)) & 0xFF;
 }
 
+// Read-stationary column builder.  A warp owns CHUNK consecutive columns; lane ci keeps column ci's position and
+// its running output offset.  The candidate reads of the chunk ([lo of its first column, hi of its last)) are
+// taken 32 at a time, one per lane, their cursor data loaded ONCE; then for every column of the chunk the lanes
+// whose read is live there are balloted, ranked (popc of lower lanes = file order, pileup.d:351-359,381-383)
+// and write read_idx / base / qual at consecutive slots.
 __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, const int32_t* __restrict__ eend,
                                                                  const uint4* __restrict__ rinfo, ColumnScratch c,
                                                                  ColumnOutput o, uint32_t n_col, int32_t* info) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = blockIdx.x * ENT_WARPS + (threadIdx.x >> 5);
   const uint32_t lt = (1u << lane) - 1;
-  const uint32_t c0 = warp * COLS_PER_WARP;
+  const uint32_t c0 = warp * CHUNK;
   if (c0 >= n_col) return;
-  // the warp's columns: one lane each loads position / window / offset, the rest is broadcast by shuffles
-  uint32_t my_p = 0, my_hi = 0, my_lo = 0;
-  uint64_t my_off = 0;
-  if (lane < COLS_PER_WARP && c0 + lane < n_col) {
-    my_p = (uint32_t)o.col_pos[c0 + lane];
-    my_hi = c.hi[c0 + lane];
-    my_lo = c.lo[c0 + lane];
-    my_off = o.col_off[c0 + lane];
+  const uint32_t ncols = min((uint32_t)CHUNK, n_col - c0);
+  const uint64_t chunk_off = o.col_off[c0];
+  int32_t my_p = 0;               // BAM positions are int32 (read.d:93)
+  uint32_t my_off = 0;            // running offset of column `lane` relative to chunk_off
+  if (lane < ncols) {
+    my_p = (int32_t)o.col_pos[c0 + lane];
+    my_off = (uint32_t)(o.col_off[c0 + lane] - chunk_off);
   }
-  const uint32_t ncols = min((uint32_t)COLS_PER_WARP, n_col - c0);
-  for (uint32_t ci = 0; ci < ncols; ++ci) {
-    const int32_t p = (int32_t)__shfl_sync(0xffffffffu, my_p, ci);       // BAM positions are int32 (read.d:93)
-    const uint32_t hi = __shfl_sync(0xffffffffu, my_hi, ci);
-    uint32_t lo = __shfl_sync(0xffffffffu, my_lo, ci);
-    uint64_t off = __shfl_sync(0xffffffffu, my_off, ci);
-    if (hi == 0) continue;
-    lo = lo ? lo - 1 : 0;
-    for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
-      const uint32_t j = j0 + lane;
-      bool live = false;
-      int32_t pos = 0;
-      if (j < hi) {
-        const int32_t e = eend[j];
-        pos = v.pos[j];
-        live = e != DEAD && pos <= p && e > p;
-      }
+  const int32_t p_first = __shfl_sync(0xffffffffu, my_p, 0), p_last = __shfl_sync(0xffffffffu, my_p, ncols - 1);
+  uint32_t lo = c.lo[c0];
+  const uint32_t hi = c.hi[c0 + ncols - 1];
+  if (hi == 0) return;
+  lo = lo ? lo - 1 : 0;
+  for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
+    const uint32_t j = j0 + lane;
+    int32_t e = DEAD, pos = 0, lseq = 0;
+    uint4 ri = make_uint4(0, 0, 0, 0);
+    if (j < hi) {
+      e = eend[j];
+      pos = v.pos[j];
+    }
+    // a chunk may span several islands, so positions are not contiguous: test against its first / last position
+    bool cand = e != DEAD && pos <= p_last && e > p_first;
+    if (!__any_sync(0xffffffffu, cand)) continue;
+    if (cand) {
+      ri = rinfo[j];
+      lseq = v.l_seq[j];
+    }
+    const uint8_t* seq = (const uint8_t*)(uintptr_t)(((uint64_t)ri.y << 32) | ri.x);
+    const uint8_t* ql = seq + (((uint32_t)lseq + 1) >> 1);
+    const bool simple = (ri.z & 0x80000000u) != 0;
+    const uint32_t qoff0 = ri.z & 0x7fffffffu;
+    for (uint32_t ci = 0; ci < ncols; ++ci) {
+      const int32_t p = __shfl_sync(0xffffffffu, my_p, ci);
+      const bool live = cand && pos <= p && e > p;
       const uint32_t m = __ballot_sync(0xffffffffu, live);
+      if (m == 0) continue;
+      const uint32_t coff = __shfl_sync(0xffffffffu, my_off, ci);
       if (live) {
-        const uint64_t slot = off + __popc(m & lt);
-        const uint4 ri = rinfo[j];
+        const uint64_t slot = chunk_off + coff + __popc(m & lt);
         const uint32_t k = (uint32_t)(p - pos);
         uint32_t base = '-', qual = 255, qoff;
-        if (ri.z & 0x80000000u) {
+        if (simple) {
           // single M/=/X run: query offset is linear in the column (pileup.d:195-203)
-          const int32_t lseq = v.l_seq[j];
-          const uint8_t* seq = (const uint8_t*)(uintptr_t)(((uint64_t)ri.y << 32) | ri.x);
-          qoff = (ri.z & 0x7fffffffu) + k;
+          qoff = qoff0 + k;
           if (qoff < (uint32_t)lseq) {
             const uint32_t byte = __ldg(seq + (qoff >> 1));
             base = base_char((qoff & 1) ? (byte & 0xF) : (byte >> 4));
-            qual = __ldg(seq + (((uint32_t)lseq + 1) >> 1) + qoff);
+            qual = __ldg(ql + qoff);
           } else {
             base = 0;      // SEQ shorter than the CIGAR says: see cursor_at
           }
         } else {
           const uint8_t* rec = record_body(v, j);
-          Entry en = cursor_at(rec, v.bin_mq_nl[j] & 0xFF, v.flag_nc[j] & 0xFFFF, v.l_seq[j], k);
+          Entry en = cursor_at(rec, v.bin_mq_nl[j] & 0xFF, v.flag_nc[j] & 0xFFFF, lseq, k);
           base = en.base;
           qual = en.qual;
           qoff = en.qoff;
@@ -310,7 +323,7 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
         o.qual[slot] = (uint8_t)qual;
         if (o.qoff) o.qoff[slot] = qoff;
       }
-      off += __popc(m);
+      if (lane == ci) my_off += __popc(m);
     }
   }
 }
@@ -413,7 +426,7 @@ void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_isla
 
 void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st) {
   if (n_col == 0) return;
-  uint32_t warps = (n_col + COLS_PER_WARP - 1) / COLS_PER_WARP;
+  uint32_t warps = (n_col + CHUNK - 1) / CHUNK;
   uint32_t grid = (warps + ENT_WARPS - 1) / ENT_WARPS;
   entries_kernel<<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
   ++g_kernel_launches;
