@@ -344,13 +344,18 @@ __global__ void carry_size_kernel(ReadsView v, uint32_t g0, uint32_t g1, const i
   bytes[j - g0] = flag[j - g0] ? (((uint64_t)block_size[j] + 4 + 3) & ~3ull) : 0;
 }
 
-__global__ void carry_copy_kernel(ReadsView v, uint32_t g0, uint32_t g1, const int32_t* block_size, const uint32_t* flag,
-                                  const uint32_t* slot_incl, const uint64_t* byte_excl, CarryOut out) {
-  // one warp per read
-  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  uint32_t j = g0 + w;
-  if (j >= g1 || !flag[j - g0]) return;
-  uint32_t s = slot_incl[j - g0] - 1;
+__global__ void carry_index_kernel(uint32_t g0, uint32_t g1, const uint32_t* flag, const uint32_t* slot_incl, uint32_t* cidx) {
+  uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g1) return;
+  if (flag[j - g0]) cidx[slot_incl[j - g0] - 1] = j;
+}
+
+__global__ void carry_copy_kernel(ReadsView v, uint32_t g0, const int32_t* block_size, const uint32_t* cidx, uint32_t n_carry_out,
+                                  const uint64_t* byte_excl, CarryOut out) {
+  // one warp per carried read
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= n_carry_out) return;
+  uint32_t j = cidx[s];
   uint64_t dst = byte_excl[j - g0];
   if (lane == 0) {
     out.pos[s] = v.pos[j];
@@ -444,12 +449,14 @@ void pileup_carry(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* b
   device_scan<false>(s.cbytes, s.cbytes, n, s.tmp_u64, OpAdd(), (uint64_t)0, st);
 }
 
-void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, GroupScratch& s,
-                       CarryOut& out, cudaStream_t st) {
+void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, uint32_t n_carry_out,
+                       GroupScratch& s, CarryOut& out, cudaStream_t st) {
   const uint32_t n = g1 - g0;
-  if (n == 0) return;
-  uint64_t threads = (uint64_t)n * 32;
-  carry_copy_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(v, g0, g1, block_size, s.cflag, s.cslot, s.cbytes, out);
+  if (n == 0 || n_carry_out == 0) return;
+  uint32_t* cidx = s.ncol;     // the island column counts are dead once the entries are written
+  launch1d(carry_index_kernel, n, st, g0, g1, s.cflag, s.cslot, cidx);
+  uint64_t threads = (uint64_t)n_carry_out * 32;
+  carry_copy_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, st>>>(v, g0, block_size, cidx, n_carry_out, s.cbytes, out);
   ++g_kernel_launches;
 }
 

@@ -90,7 +90,7 @@ void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_isla
 void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
 void pileup_carry(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, int64_t limit, GroupScratch& s,
                   CarryOut& out, cudaStream_t st);
-void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, GroupScratch& s,
-                       CarryOut& out, cudaStream_t st);
+void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, uint32_t n_carry_out,
+                       GroupScratch& s, CarryOut& out, cudaStream_t st);
 
 }  // namespace biodb

@@ -273,7 +273,11 @@ static void producer_main(biodb_pileup* pl) {
     Desc d;
     d.set = set;
     d.st = produce(pl, pl->sets[set], &d.cols);
-    if (d.st != BIODB_OK && d.st != BIODB_EOF) d.err = pl->r->err;
+    if (d.st != BIODB_OK) {
+      cudaStreamSynchronize(pl->pass.st);
+      pl->pass.collect_timing();
+      if (d.st != BIODB_EOF) d.err = pl->r->err;
+    }
     {
       std::lock_guard<std::mutex> lk(pl->mu);
       pl->ready.push_back(d);
@@ -448,7 +452,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     // ---- phase 1: liveness, running max, islands ----------------------------------------------------
     p.stage_begin();
     pileup_phase1(v, g0, g1, drop_before, skip_zero, clo, chi, s, st);
-    p.stats.pileup_ms += p.stage_end();
+    p.stage_end(&p.stats.pileup_ms);
     const uint32_t ng = g1 - g0;
     const uint32_t t_reads = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
     PL_TRY(launch_copy_bytes(h, s.tmp_u32 + t_reads, 4, st));           // n_islands
@@ -492,7 +496,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     }
     p.stage_begin();
     pileup_island_cols(n_islands, s, st);
-    p.stats.pileup_ms += p.stage_end();
+    p.stage_end(&p.stats.pileup_ms);
     const uint32_t t_isl = (uint32_t)((n_islands + SCAN_TILE - 1) / SCAN_TILE);
     PL_TRY(launch_copy_bytes(h, s.tmp_u32b + t_isl, 4, st));
     PL_TRY(cudaStreamSynchronize(st));
@@ -527,7 +531,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       ColumnOutput o{os.d[0].as<uint64_t>(), os.d[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr};
       p.stage_begin();
       pileup_phase2(v, g0, g1, n_islands, n_col, s, c, o, st);
-      p.stats.pileup_ms += p.stage_end();
+      p.stage_end(&p.stats.pileup_ms);
       PL_TRY(launch_copy_bytes(pl->h_small.p, o.col_off + n_col, 8, st));
       PL_TRY(cudaStreamSynchronize(st));
       n_entries = *pl->h_small.as<uint64_t>();
@@ -553,7 +557,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       o.qoff = want_q ? os.d[6].as<uint32_t>() : nullptr;
       p.stage_begin();
       pileup_entries(v, n_col, s, c, o, st);
-      p.stats.pileup_ms += p.stage_end();
+      p.stage_end(&p.stats.pileup_ms);
       PL_TRY(cudaEventRecord(os.computed, st));
       // results to the host on the copy stream: overlaps with the carry kernels and the next batch
       if (!p.r->opts.device_output) {
@@ -587,7 +591,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         CarryOut dummy{};
         p.stage_begin();
         pileup_carry(v, g0, g1, a.block_size, E, s, dummy, st);
-        p.stats.pileup_ms += p.stage_end();
+        p.stage_end(&p.stats.pileup_ms);
         const uint32_t t_g = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
         PL_TRY(launch_copy_bytes(h, s.tmp_u32 + t_g, 4, st));
         PL_TRY(launch_copy_bytes(h + 2, s.tmp_u64 + t_g, 8, st));
@@ -599,7 +603,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
           for (int k = 0; k < 9; ++k) PL_TRY(nxt.a[k].ensure((size_t)(nc + 8) * esz[k], st));
           PL_TRY(nxt.data.ensure((size_t)nbytes + 256, st));
           CarryOut co = nxt.out();
-          pileup_carry_copy(v, g0, g1, a.block_size, s, co, st);
+          pileup_carry_copy(v, g0, g1, a.block_size, nc, s, co, st);
           PL_TRY(cudaStreamSynchronize(st));
         }
         nxt.n = nc;

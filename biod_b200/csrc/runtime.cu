@@ -118,6 +118,8 @@ Pass::~Pass() {
   }
   for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b})
     if (e) cudaEventDestroy(e);
+  for (const Timed& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+  for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
 }
 
 void Pass::mark_begin() {
@@ -130,18 +132,36 @@ void Pass::mark_end() {
   if (!began) return;
   cudaEventRecord(ev_end, st);
   cudaEventSynchronize(ev_end);
+  collect_timing();
   float ms = 0;
   if (cudaEventElapsedTime(&ms, ev_begin, ev_end) == cudaSuccess) stats.total_ms = ms;
   stats.kernel_launches = g_kernel_launches - launches0;
   stats.n_records = n_records_total;
 }
-void Pass::stage_begin() { cudaEventRecord(ev_a, st); }
-double Pass::stage_end() {
-  cudaEventRecord(ev_b, st);
-  cudaEventSynchronize(ev_b);
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ev_a, ev_b);
-  return ms;
+static cudaEvent_t pool_event(std::vector<cudaEvent_t>& pool) {
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void Pass::stage_begin() {
+  stage_a = pool_event(ev_pool);
+  cudaEventRecord(stage_a, st);
+}
+void Pass::stage_end(double* acc) {
+  cudaEvent_t b = pool_event(ev_pool);
+  cudaEventRecord(b, st);
+  timed.push_back(Timed{stage_a, b, acc});
+  stage_a = nullptr;
+}
+void Pass::collect_timing() {
+  for (const Timed& t : timed) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) *t.acc += ms;
+    ev_pool.push_back(t.a);
+    ev_pool.push_back(t.b);
+  }
+  timed.clear();
 }
 
 biodb_status Pass::fail(int status, int zerr, uint64_t off, const std::string& msg) {
@@ -317,7 +337,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     }
     stage_begin();
     CUDA_TRY(launch_inflate(ia, st));
-    stats.inflate_ms += stage_end();
+    stage_end(&stats.inflate_ms);
     stats.inflate_launches += 1;
     stats.n_blocks += nb;
     stats.compressed_bytes += c1 - c0;
@@ -372,7 +392,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     // only the carried-tail pseudo block still needs the stand-alone walk kernel
     CUDA_TRY(launch_scan_records(d_u.as<uint8_t>(), u_len, d_buoff, nsb2, (has_carry || nb == 0) ? 1u : 0u, eof_semantics, ra,
                                  d_result.as<uint64_t>(), ws, st));
-    stats.scan_ms += stage_end();
+    stage_end(&stats.scan_ms);
     CUDA_TRY(launch_copy_bytes(h_result.p, d_result.p, 32, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const uint64_t* res = h_result.as<uint64_t>();

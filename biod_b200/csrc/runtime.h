@@ -108,8 +108,15 @@ struct Pass {
   unsigned long long launches0 = 0;
   void mark_begin();                // first operation of the pass
   void mark_end();                  // call with the stream idle-able: records + syncs, updates total_ms
-  void stage_begin();               // events around a group of launches of one stage
-  double stage_end();               // returns elapsed ms (synchronises the stream)
+  // stage timing without extra synchronisation: event pairs are recorded around the launches of a stage and
+  // turned into milliseconds at the next point where the stream is synchronised anyway
+  struct Timed { cudaEvent_t a, b; double* acc; };
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<Timed> timed;
+  cudaEvent_t stage_a = nullptr;
+  void stage_begin();
+  void stage_end(double* acc);
+  void collect_timing();            // call when the stream is known to be idle
 
   ~Pass();
   biodb_status init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset);
