@@ -47,6 +47,13 @@ class PileupParams(C.Structure):
                 ("counts_only", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("first_coffset", C.c_uint64), ("end_coffset", C.c_uint64), ("halo_coffset", C.c_uint64),
+                ("lo_ref", C.c_int32), ("hi_ref", C.c_int32), ("lo_pos", C.c_int64), ("hi_pos", C.c_int64),
+                ("n_halo_records", C.c_uint64), ("n_own_records", C.c_uint64),
+                ("max_end_all", C.c_int64), ("max_end_outside_tail", C.c_int64)]
+
+
 class ColumnBatch(C.Structure):
     _fields_ = [("n_columns", C.c_uint64), ("n_entries", C.c_uint64), ("ref_id", C.c_int32),
                 ("last_of_pileup", C.c_int32), ("position", u64p), ("col_off", u64p), ("n_starting_here", u32p),
@@ -94,6 +101,9 @@ def lib():
     L.biodb_reads_progress.argtypes = [vp]
     L.biodb_pileup_begin.restype = C.c_int
     L.biodb_pileup_begin.argtypes = [vp, C.POINTER(PileupParams), C.POINTER(vp)]
+    L.biodb_pileup_begin_shard.restype = C.c_int
+    L.biodb_pileup_begin_shard.argtypes = [vp, C.POINTER(PileupParams), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.biodb_pileup_shard_info.argtypes = [vp, C.POINTER(ShardInfo)]
     L.biodb_pileup_next.restype = C.c_int
     L.biodb_pileup_next.argtypes = [vp, C.POINTER(ColumnBatch)]
     L.biodb_pileup_end.argtypes = [vp]
@@ -117,6 +127,6 @@ EXPORTS = [
     "biodb_open_error", "biodb_header_text", "biodb_n_refs", "biodb_ref_info", "biodb_reads_start_voffset",
     "biodb_file_size", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
-    "biodb_reads_stats", "biodb_pileup_stats",
+    "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes",
 ]

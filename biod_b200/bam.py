@@ -261,19 +261,28 @@ class BamReader:
                 yield BamRead(batch, i)
 
     def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
-                       want_query_offset=False, copy=False):
+                       want_query_offset=False, copy=False, shard=None, halo_blocks=8, shard_info=None):
+        """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015)."""
         L = self._L
         p = capi.PileupParams()
         p.single_ref, p.skip_zero_coverage, p.use_md_tag = int(single_ref), int(skip_zero_coverage), int(use_md_tag)
         p.want_query_offset, p.start_from, p.end_at = int(want_query_offset), start_from, end_at
         pl = C.c_void_p()
-        if L.biodb_pileup_begin(self._h, C.byref(p), C.byref(pl)) != capi.OK:
+        if shard is not None:
+            st = L.biodb_pileup_begin_shard(self._h, C.byref(p), shard[0], shard[1], halo_blocks, C.byref(pl))
+        else:
+            st = L.biodb_pileup_begin(self._h, C.byref(p), C.byref(pl))
+        if st != capi.OK:
             self._err()
         try:
             while True:
                 cb = capi.ColumnBatch()
                 st = L.biodb_pileup_next(pl, C.byref(cb))
                 if st == capi.EOF:
+                    if shard_info is not None:
+                        si = capi.ShardInfo()
+                        L.biodb_pileup_shard_info(pl, C.byref(si))
+                        shard_info.update({f: getattr(si, f) for f, _ in si._fields_})
                     return
                 if st != capi.OK:
                     self._err()

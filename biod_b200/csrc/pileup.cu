@@ -373,6 +373,17 @@ __global__ void carry_copy_kernel(ReadsView v, uint32_t g0, const int32_t* block
   for (uint32_t i = lane; i < n; i += 32) out.data[dst + i] = src[i];
 }
 
+// shard halo check: max end_pos over records [0, *n_all) / [0, *n_head) with the given reference
+__global__ void max_end_kernel(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, uint32_t n_all,
+                               const uint64_t* n_head_ptr, int32_t ref, int32_t* out /*[2]*/) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_all) return;
+  int32_t e = end_pos[i];
+  if (ref_id[i] != ref || e <= pos[i]) return;
+  atomicMax(&out[0], e);
+  if ((uint64_t)i < *n_head_ptr) atomicMax(&out[1], e);
+}
+
 template <typename K, typename... A>
 inline void launch1d(K k, uint32_t n, cudaStream_t st, A... a) {
   if (n == 0) return;
@@ -385,6 +396,11 @@ inline void launch1d(K k, uint32_t n, cudaStream_t st, A... a) {
 void pileup_find_groups(const ReadsView& v, uint32_t* boundaries, uint32_t* n_boundaries, uint32_t cap, cudaStream_t st) {
   cudaMemsetAsync(n_boundaries, 0, sizeof(uint32_t), st);
   if (v.n > 1) launch1d(find_groups_kernel, v.n - 1, st, v, boundaries, n_boundaries, cap);
+}
+
+void pileup_max_end(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, uint32_t n, const uint64_t* n_head_ptr,
+                    int32_t ref, int32_t* out, cudaStream_t st) {
+  launch1d(max_end_kernel, n, st, ref_id, pos, end_pos, n, n_head_ptr, ref, out);
 }
 
 void pileup_first_kept(const ReadsView& v, uint32_t g0, uint32_t g1, uint64_t start_from, uint32_t* first, cudaStream_t st) {

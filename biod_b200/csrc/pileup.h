@@ -80,6 +80,8 @@ struct CarryOut {
   uint8_t* data;
 };
 
+void pileup_max_end(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, uint32_t n, const uint64_t* n_head_ptr,
+                    int32_t ref, int32_t* out, cudaStream_t st);
 void pileup_find_groups(const ReadsView& v, uint32_t* boundaries, uint32_t* n_boundaries, uint32_t cap, cudaStream_t st);
 void pileup_first_kept(const ReadsView& v, uint32_t g0, uint32_t g1, uint64_t start_from, uint32_t* first, cudaStream_t st);
 void pileup_phase1(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t drop_before, int skip_zero, int64_t clo,

@@ -61,6 +61,13 @@ struct biodb_pileup {
   bool cont = false;          // the last batch ended inside a group that had live reads
   int32_t cont_ref = 0;
   int64_t cont_pos = 0;       // columns below this position are already emitted
+  // shard mode (biodb_pileup_begin_shard)
+  bool sharded = false;
+  biodb_shard_info shard{};
+  uint32_t halo_blocks_left = 0;     // halo blocks not yet seen by the scanner
+  uint64_t index_bias = 0;           // records of the halo: read_idx counts from the shard's first own record
+  uint64_t tail_coffset = 0;         // first block of the shard's last `halo_blocks` blocks
+  DevBuf d_maxend;                   // [2] int32 maxima + u64 scratch
   // single_ref state
   bool started = false, done = false;
   int32_t target_ref = -1;
@@ -164,7 +171,29 @@ static biodb_status load_batch(biodb_pileup* pl) {
   const uint64_t first = p.n_records_total;
   biodb_status s = p.next((uint32_t)p.r->opts.blocks_per_batch, c.n);
   if (s != BIODB_OK) return s;
-  pl->first_index = first;
+  if (pl->sharded && pl->halo_blocks_left && p.blocks.size()) {
+    // records that start in the halo blocks: rec_base[h] of the scan workspace (the halo is the head of the first batch)
+    uint32_t hb = std::min<uint32_t>(pl->halo_blocks_left, (uint32_t)p.blocks.size());
+    ScanWorkspace w = carve_scan_workspace(p.d_ws.p, (uint32_t)p.blocks.size() + (p.segs.size() > p.blocks.size() ? 1 : 0));
+    uint64_t* hh = (uint64_t*)pl->h_small.p;
+    PL_TRY(launch_copy_bytes(hh + 8, w.rec_base + hb + (p.segs.size() > p.blocks.size() ? 1 : 0), 8, p.st));
+    PL_TRY(cudaStreamSynchronize(p.st));
+    pl->index_bias += hh[8];
+    pl->shard.n_halo_records = pl->index_bias;
+    pl->halo_blocks_left -= hb;
+  }
+  if (pl->sharded && p.n) {
+    // halo check: largest end among this batch's own records on hi_ref, over all and over those that start before
+    // the shard's tail blocks.  Records of the halo (index < bias) may be included: they only raise the bound.
+    const uint32_t off = p.segs.size() > p.blocks.size() ? 1 : 0;
+    uint32_t nbt = 0;
+    while (nbt < p.blocks.size() && p.blocks[nbt].coffset < pl->tail_coffset) ++nbt;
+    ScanWorkspace w = carve_scan_workspace(p.d_ws.p, (uint32_t)p.blocks.size() + off);
+    RecordArrays a = p.arrays(c.n);
+    pileup_max_end(a.ref_id, a.pos, a.end_pos, (uint32_t)p.n, w.rec_base + nbt + off, pl->shard.hi_ref,
+                   pl->d_maxend.as<int32_t>(), p.st);
+  }
+  pl->first_index = first;      // shard mode: counted from the first halo record; the stitch subtracts n_halo_records
   pl->n_carry_view = c.n;
   pl->n_view = c.n + (uint32_t)p.n;
   cudaStream_t st = p.st;
@@ -254,6 +283,10 @@ void biodb_pileup::reset(const biodb_pileup_params* p) {
   held_set = -1;
   stop = worker_done = false;
   last_done = nullptr;
+  sharded = false;
+  memset(&shard, 0, sizeof shard);
+  halo_blocks_left = 0;
+  index_bias = 0;
 }
 
 static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* cols);
@@ -314,6 +347,95 @@ biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, b
   if (s != BIODB_OK) { delete pl; return s; }
   *out = pl;
   return BIODB_OK;
+}
+
+// (ref, pos) of the first record that starts in the block at `coffset` (assumed to be a record boundary).
+static biodb_status peek_first_record(biodb_reader* r, uint64_t coffset, int32_t* ref, int64_t* pos) {
+  Pass p;
+  biodb_status s = p.init(r, coffset, 0);
+  if (s != BIODB_OK) return s;
+  s = p.next(1, 0);
+  if (s != BIODB_OK) return s;
+  if (p.n == 0) { *ref = -1; *pos = 0; return BIODB_OK; }
+  int32_t h[2];
+  RecordArrays a = p.arrays(0);
+  if (cudaMemcpy(&h[0], a.ref_id, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(&h[1], a.pos, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return p.fail(BIODB_ERR_CUDA, 0, 0, "peek failed");
+  *ref = h[0];
+  *pos = h[1];
+  return BIODB_OK;
+}
+
+biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
+                                      uint32_t halo_blocks, biodb_pileup** out) {
+  if (!r || !out || n_shards == 0 || shard >= n_shards) return BIODB_ERR_ARG;
+  biodb_pileup_params p2;
+  if (prm) p2 = *prm; else { memset(&p2, 0, sizeof p2); p2.skip_zero_coverage = 1; }
+  p2.single_ref = 0;                       // pileupColumns semantics
+  p2.start_from = 0;
+  p2.end_at = ~0ull;
+  biodb_status s = r->build_block_index();
+  if (s != BIODB_OK) return s;
+  const std::vector<uint64_t>& bi = r->block_index;
+  const size_t nb = bi.size();
+  // cut points at equal compressed-byte fractions of the data blocks
+  auto cut = [&](uint32_t k) -> size_t {
+    if (k == 0) return 0;
+    if (k >= n_shards || nb == 0) return nb;
+    const uint64_t a = bi[0], z = r->data_end_coffset;
+    const uint64_t target = a + (uint64_t)((double)(z - a) * k / n_shards);
+    return (size_t)(std::lower_bound(bi.begin(), bi.end(), target) - bi.begin());
+  };
+  const size_t b0 = cut(shard), b1 = cut(shard + 1);
+  biodb_shard_info sh{};
+  sh.first_coffset = b0 < nb ? bi[b0] : r->data_end_coffset;
+  sh.end_coffset = b1 < nb ? bi[b1] : r->data_end_coffset;
+  const size_t hb = (shard == 0) ? 0 : std::min<size_t>(halo_blocks, b0);
+  sh.halo_coffset = (b0 - hb) < nb ? bi[b0 - hb] : r->data_end_coffset;
+  sh.lo_ref = 0;
+  sh.lo_pos = INT64_MIN;
+  sh.hi_ref = -1;
+  sh.hi_pos = INT64_MAX;
+  if (shard > 0 && b0 < nb) {
+    s = peek_first_record(r, bi[b0], &sh.lo_ref, &sh.lo_pos);
+    if (s != BIODB_OK) return s;
+  } else if (shard > 0) {
+    sh.lo_ref = -1;                        // empty shard at the end of the file
+    sh.lo_pos = INT64_MAX;
+  }
+  if (b1 < nb) {
+    s = peek_first_record(r, bi[b1], &sh.hi_ref, &sh.hi_pos);
+    if (s != BIODB_OK) return s;
+  }
+  s = biodb_pileup_begin(r, &p2, out);
+  if (s != BIODB_OK) return s;
+  biodb_pileup* pl = *out;
+  pl->sharded = true;
+  pl->shard = sh;
+  pl->halo_blocks_left = (uint32_t)hb;
+  {
+    const size_t tb = b1 > halo_blocks ? b1 - halo_blocks : 0;
+    pl->tail_coffset = tb < nb ? bi[std::max(tb, b0)] : r->data_end_coffset;
+    int32_t init[2] = {INT32_MIN, INT32_MIN};
+    if (pl->d_maxend.ensure(64) != cudaSuccess || cudaMemcpy(pl->d_maxend.p, init, 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+      biodb_pileup_end(pl);
+      return BIODB_ERR_CUDA;
+    }
+  }
+  pl->pass.rewind(sh.halo_coffset, sh.halo_coffset == r->reads_start_coffset ? r->reads_start_uoffset : 0);
+  pl->pass.stop_coffset = sh.end_coffset;
+  return BIODB_OK;
+}
+
+void biodb_pileup_shard_info(const biodb_pileup* pl, biodb_shard_info* out) {
+  if (!pl || !out) return;
+  *out = pl->shard;
+  out->n_own_records = pl->pass.n_records_total - pl->index_bias;
+  int32_t m[2] = {INT32_MIN, INT32_MIN};
+  if (pl->d_maxend.p) cudaMemcpy(m, pl->d_maxend.p, 8, cudaMemcpyDeviceToHost);
+  out->max_end_all = m[0] == INT32_MIN ? INT64_MIN : m[0];
+  out->max_end_outside_tail = m[1] == INT32_MIN ? INT64_MIN : m[1];
 }
 
 void biodb_pileup_end(biodb_pileup* pl) {
@@ -444,6 +566,17 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     }
     int64_t clo = INT64_MIN, chi = INT64_MAX;
     if (continues) clo = pl->cont_pos;
+    if (pl->sharded) {
+      // column keys (ref, pos) of this shard: [lo, hi); unmapped (ref -1) sorts last
+      auto key = [](int32_t rf) { return rf < 0 ? (int64_t)1 << 40 : (int64_t)rf; };
+      const biodb_shard_info& sh = pl->shard;
+      if (key(ref) < key(sh.lo_ref) || key(ref) > key(sh.hi_ref)) {
+        if (last_group) { pl->carry[pl->cur].n = 0; pl->cont = false; }
+        continue;                                    // a reference that belongs to a neighbouring shard
+      }
+      if (ref == sh.lo_ref) clo = std::max(clo, sh.lo_pos);
+      if (ref == sh.hi_ref) chi = std::min(chi, sh.hi_pos);
+    }
     if (single) {
       if (pl->prm.start_from > (uint64_t)INT64_MAX) { pl->done = true; return BIODB_EOF; }
       clo = std::max<int64_t>(clo, (int64_t)pl->prm.start_from);

@@ -186,6 +186,7 @@ biodb_status Pass::init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset) {
 }
 
 void Pass::rewind(uint64_t coffset, uint32_t uoffset) {
+  stop_coffset = ~0ull;
   next_coffset = coffset;
   first_skip = uoffset;
   supplier_done = false;
@@ -256,6 +257,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   // ---- 1. walk the BSIZE chain on the host (18 bytes per block) ----------------------------------
   blocks.clear();
   while (blocks.size() < max_blocks && !supplier_done && !pending.status) {
+    if (next_coffset >= stop_coffset) { supplier_done = true; break; }
     BlockInfo b;
     int rc = parse_bgzf_header(r->file, r->flen, next_coffset, &b, &pending);
     if (rc < 0) break;
@@ -429,6 +431,22 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
 }
 
 }  // namespace biodb
+
+biodb_status biodb_reader::build_block_index() {
+  if (!block_index.empty()) return BIODB_OK;
+  uint64_t pos = reads_start_coffset;
+  biodb_error e{};
+  while (true) {
+    BlockInfo b;
+    int rc = parse_bgzf_header(file, flen, pos, &b, &e);
+    if (rc < 0) { err = e; return (biodb_status)e.status; }
+    if (rc == 0 || b.isize == 0) break;
+    block_index.push_back(pos);
+    pos = b.coffset + b.bsize + 1;
+  }
+  data_end_coffset = pos;
+  return BIODB_OK;
+}
 
 // =========================================================================================== C ABI ====
 

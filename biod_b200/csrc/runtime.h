@@ -69,6 +69,10 @@ struct biodb_reader {
   // finished passes park their buffers here so that the next pass does not reallocate them
   std::mutex pool_mu;
   std::vector<void*> pileup_pool, reads_pool;
+  // coffset of every data block from the first record on (built on demand for sharding)
+  std::vector<uint64_t> block_index;
+  uint64_t data_end_coffset = 0;
+  biodb_status build_block_index();
 };
 
 namespace biodb {
@@ -79,6 +83,7 @@ struct Pass {
   cudaStream_t st = nullptr;
   // position in the file
   uint64_t next_coffset = 0;
+  uint64_t stop_coffset = ~0ull;      // shard end: blocks at or beyond it are not read
   uint32_t first_skip = 0;          // bytes of the first block that precede the first record
   bool supplier_done = false;       // EOF block / end of file reached (inputstream.d:393-394)
   biodb_error pending{};            // error to raise once the blocks before it are consumed

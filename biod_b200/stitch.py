@@ -21,3 +21,19 @@ def stitch_counts(n_columns, n_entries, n_records, device="cpu"):
     return dict(rank=rank, world=world, col_base=int(base[rank, 0]), ent_base=int(base[rank, 1]),
                 rec_base=int(base[rank, 2]), totals=tuple(int(x) for x in tot),
                 per_rank=[tuple(int(x) for x in row) for row in table])
+
+
+def halo_sufficient(shards):
+    """Exactness check of a sharded pileup (see biodb_shard_info): `shards` = list of shard-info dicts in shard order.
+    True iff no read outside a shard's halo reaches into its column range."""
+    for s in range(1, len(shards)):
+        lo_ref, lo_pos = shards[s]["lo_ref"], shards[s]["lo_pos"]
+        for q in range(s):
+            if shards[q]["hi_ref"] != lo_ref:
+                continue
+            if shards[s]["halo_coffset"] <= shards[q]["first_coffset"]:
+                continue                      # the halo re-reads all of shard q
+            m = shards[q]["max_end_outside_tail"] if q == s - 1 else shards[q]["max_end_all"]
+            if m > lo_pos:
+                return False
+    return True

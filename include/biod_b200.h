@@ -148,6 +148,30 @@ typedef struct biodb_column_batch {
 } biodb_column_batch;
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);
+/* Sharded pileup (pileupChunks semantics, pileup.d:859-1015): shard `shard` of `n_shards` reads a
+ * contiguous range of BGZF blocks (cut at equal compressed-byte fractions, which must be record boundaries — true for
+ * files written by BioD / htslib unless a record exceeds a block) plus a halo of `halo_blocks` trailing blocks of the
+ * previous shard, and emits exactly the columns from the position of its own first read up to (not including) the
+ * position of the next shard's first read.  Concatenating the shards' batches in shard order gives the columns of an
+ * unsharded biodb_pileup_begin pass; read_idx counts from the first record the shard reads (its first halo record):
+ * global index = read_idx - n_halo_records + (records owned by all earlier shards), the base the stitch provides.
+ * pileupColumns semantics only. */
+typedef struct biodb_shard_info {
+  uint64_t first_coffset, end_coffset;   /* own block range */
+  uint64_t halo_coffset;                 /* where reading starts */
+  int32_t lo_ref, hi_ref;                /* column keys (ref, pos): [lo, hi) ; ref -1 sorts last */
+  int64_t lo_pos, hi_pos;
+  uint64_t n_halo_records;               /* records in the halo blocks (valid after the first batch) */
+  uint64_t n_own_records;                /* records starting in the own range (valid at EOF) */
+  /* halo check (valid at EOF): largest end position among this shard's own reads on reference hi_ref — over all of
+   * them, and over those outside its last `halo_blocks` blocks (which the next shard re-reads as its halo).  The
+   * sharded result equals the sequential one iff, for every later shard s that starts on the same reference,
+   * max_end_outside_tail (previous shard) / max_end_all (earlier shards) <= s.lo_pos.  INT64_MIN when none. */
+  int64_t max_end_all, max_end_outside_tail;
+} biodb_shard_info;
+biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* p, uint32_t shard, uint32_t n_shards,
+                                      uint32_t halo_blocks, biodb_pileup** out);
+void biodb_pileup_shard_info(const biodb_pileup* pl, biodb_shard_info* out);
 biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols);
 void biodb_pileup_end(biodb_pileup* pl);
 /* Reference id of the pileup (AbstractPileup.ref_id, pileup.d:455-457); valid after the first _next. */

@@ -61,3 +61,46 @@ def assert_pileup_equal(g, o):
     assert np.array_equal(g["base"], o.base)
     assert np.array_equal(g["qual"], o.qual)
     assert np.array_equal(g["qoff"], o.qoff)
+
+
+def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, **kw):
+    """Run every shard of a sharded pileup (one after the other on this GPU) and stitch the column tables the way
+    biod_b200.stitch does across ranks: concatenate in shard order, rebase read_idx by the record counts."""
+    rd = BamReader(data, blocks_per_batch=blocks_per_batch)
+    parts, infos = [], []
+    for s in range(n_shards):
+        pos, ref, cov, nstart, ridx, base, qual, qoff = [], [], [], [], [], [], [], []
+        info = {}
+        for b in rd.column_batches(False, want_query_offset=True, copy=True, shard=(s, n_shards), halo_blocks=halo_blocks,
+                                   shard_info=info, **kw):
+            pos.append(b.position)
+            ref.append(np.full(b.n_columns, b.ref_id, dtype=np.int32))
+            cov.append(np.diff(b.col_off).astype(np.uint64))
+            nstart.append(b.n_starting_here)
+            ridx.append(b.read_idx)
+            base.append(b.base)
+            qual.append(b.qual)
+            qoff.append(b.query_offset)
+        parts.append((pos, ref, cov, nstart, ridx, base, qual, qoff))
+        infos.append(info)
+    rec_base = np.concatenate([[0], np.cumsum([i["n_own_records"] for i in infos])]).astype(np.uint64)
+    cat = lambda v, dt: np.concatenate(v) if v else np.zeros(0, dtype=dt)  # noqa: E731
+    out = {k: [] for k in ("col_pos", "col_ref", "cov", "n_start", "read_idx", "base", "qual", "qoff")}
+    for s, (pos, ref, cov, nstart, ridx, base, qual, qoff) in enumerate(parts):
+        out["col_pos"] += pos
+        out["col_ref"] += ref
+        out["cov"] += cov
+        out["n_start"] += nstart
+        shift = (int(rec_base[s]) - int(infos[s]["n_halo_records"])) % 2**32
+        out["read_idx"] += [((r.astype(np.uint64) + np.uint64(shift)) & np.uint64(0xFFFFFFFF)).astype(np.uint32) for r in ridx]
+        out["base"] += base
+        out["qual"] += qual
+        out["qoff"] += qoff
+    dts = dict(col_pos=np.uint64, col_ref=np.int32, cov=np.uint64, n_start=np.uint32, read_idx=np.uint32, base=np.uint8,
+               qual=np.uint8, qoff=np.uint32)
+    res = {k: cat(v, dts[k]) for k, v in out.items()}
+    res["col_off"] = np.concatenate([[0], np.cumsum(res["cov"])]).astype(np.uint64)
+    res["shards"] = infos
+    from biod_b200.stitch import halo_sufficient
+    res["halo_ok"] = halo_sufficient(infos)
+    return res

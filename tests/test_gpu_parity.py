@@ -242,3 +242,34 @@ def test_make_pileup_example_invariant_on_gpu():
     for column in makePileup(bam, True):
         starting += column.reads_starting_here.tolist()
     assert starting == list(range(29))
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "bins.bam", "b7_295_chunk.bam", "ion_20_chunk.bam"])
+@pytest.mark.parametrize("n_shards,halo", [(2, 8), (3, 2), (5, 8)])
+def test_sharded_pileup_equals_unsharded(name, n_shards, halo):
+    # shards by BGZF block range + halo; concatenated shard outputs == one sequential pass
+    from gpu_util import gpu_pileup_sharded
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    g = gpu_pileup_sharded(data, n_shards, halo_blocks=halo, blocks_per_batch=3)
+    assert sum(i["n_own_records"] for i in g["shards"]) == o.n_records
+    if not g["halo_ok"]:
+        # bins.bam holds reads spanning megabases and the *_chunk files pile hundreds of reads on one spot: the
+        # stitch check must notice that a small halo is not enough, and a halo reaching back to the start of
+        # the file must then be exact
+        assert name != "ex1_header.bam"
+        g = gpu_pileup_sharded(data, n_shards, halo_blocks=10**6, blocks_per_batch=3)
+        assert g["halo_ok"]
+    assert_pileup_equal(g, o.pileup_columns())
+
+
+@pytest.mark.parametrize("skip", [True, False])
+def test_sharded_pileup_synthetic(skip):
+    from gpu_util import gpu_pileup_sharded
+    from tools import bamgen
+    data = bamgen.generate(60000, 3, True, level=1, threads=4).tobytes()
+    o = orc.Bam(data).decode()
+    for n_shards in (2, 4, 7):
+        g = gpu_pileup_sharded(data, n_shards, halo_blocks=4, blocks_per_batch=16, skip_zero_coverage=skip)
+        assert g["halo_ok"]
+        assert_pileup_equal(g, o.pileup_columns(skip))
