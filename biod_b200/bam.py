@@ -190,7 +190,7 @@ class BamRead:
 class BamReader:
     """bam/reader.d:80-598 — the subset on the hot path."""
 
-    def __init__(self, source, blocks_per_batch=0, want_offsets=False, device=-1, task_pool=None):
+    def __init__(self, source, blocks_per_batch=0, want_offsets=False, device=-1, task_pool=None, verify_crc=False):
         # task_pool is accepted and ignored (reader.d:100-101): the device is the pool
         self._L = L = capi.lib()
         o = capi.Options()
@@ -199,6 +199,7 @@ class BamReader:
         if blocks_per_batch:
             o.blocks_per_batch = blocks_per_batch
         o.want_offsets = int(want_offsets)
+        o.verify_crc = int(verify_crc)
         h = C.c_void_p()
         if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
             self._buf = np.frombuffer(source, dtype=np.uint8)
@@ -261,12 +262,13 @@ class BamReader:
                 yield BamRead(batch, i)
 
     def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
-                       want_query_offset=False, copy=False, shard=None, halo_blocks=8, shard_info=None):
+                       want_query_offset=False, copy=False, shard=None, halo_blocks=8, shard_info=None, counts_only=False):
         """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015)."""
         L = self._L
         p = capi.PileupParams()
         p.single_ref, p.skip_zero_coverage, p.use_md_tag = int(single_ref), int(skip_zero_coverage), int(use_md_tag)
         p.want_query_offset, p.start_from, p.end_at = int(want_query_offset), start_from, end_at
+        p.counts_only = int(counts_only)
         pl = C.c_void_p()
         if shard is not None:
             st = L.biodb_pileup_begin_shard(self._h, C.byref(p), shard[0], shard[1], halo_blocks, C.byref(pl))
@@ -303,6 +305,7 @@ class ColumnBatch:
         self.base = g(_np(cb.base, ne, np.uint8))
         self.qual = g(_np(cb.qual, ne, np.uint8))
         self.query_offset = g(_np(cb.query_offset, ne, np.uint32)) if cb.query_offset else None
+        self.counts = g(_np(cb.counts, nc * 6, np.uint32)).reshape(nc, 6) if cb.counts else None
 
 
 class PileupColumn:

@@ -45,6 +45,11 @@ struct InflateArgs {
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st);
 size_t inflate_smem_bytes();
 
+// ---- crc32.cu ---------------------------------------------------------------------------------
+// CRC-32 of each block's inflated bytes (options.verify_crc; BioD asserts it in debug builds, block.d:187)
+cudaError_t launch_crc32(const uint8_t* out, const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks,
+                         uint32_t* crc, cudaStream_t st);
+
 // ---- records.cu ------------------------------------------------------------------------------
 struct RecordArrays {
   uint64_t* rec_off;

@@ -251,6 +251,7 @@ __device__ __forceinline__ uint32_t base_char(uint32_t code) {
 // taken 32 at a time, one per lane, their cursor data loaded ONCE; then for every column of the chunk the lanes
 // whose read is live there are balloted, ranked (popc of lower lanes = file order, pileup.d:351-359,381-383)
 // and write read_idx / base / qual at consecutive slots.
+template <bool COUNTS>
 __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, const int32_t* __restrict__ eend,
                                                                  const uint4* __restrict__ rinfo, ColumnScratch c,
                                                                  ColumnOutput o, uint32_t n_col, int32_t* info) {
@@ -270,7 +271,12 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
   const int32_t p_first = __shfl_sync(0xffffffffu, my_p, 0), p_last = __shfl_sync(0xffffffffu, my_p, ncols - 1);
   uint32_t lo = c.lo[c0];
   const uint32_t hi = c.hi[c0 + ncols - 1];
-  if (hi == 0) return;
+  uint32_t cnt[6] = {0, 0, 0, 0, 0, 0};     // COUNTS: A, C, G, T, other, deletion of column `lane`
+  if (hi == 0) {
+    if (COUNTS && lane < ncols)
+      for (int q = 0; q < 6; ++q) o.counts[(size_t)(c0 + lane) * 6 + q] = 0;
+    return;
+  }
   lo = lo ? lo - 1 : 0;
   for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
     const uint32_t j = j0 + lane;
@@ -296,11 +302,13 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
       const bool live = cand && pos <= p && e > p;
       const uint32_t m = __ballot_sync(0xffffffffu, live);
       if (m == 0) continue;
-      const uint32_t coff = __shfl_sync(0xffffffffu, my_off, ci);
+      const uint32_t coff = COUNTS ? 0 : __shfl_sync(0xffffffffu, my_off, ci);
+      uint32_t base = 0xFFFFFFFFu;
       if (live) {
         const uint64_t slot = chunk_off + coff + __popc(m & lt);
         const uint32_t k = (uint32_t)(p - pos);
-        uint32_t base = '-', qual = 255, qoff;
+        uint32_t qual = 255, qoff;
+        base = '-';
         if (simple) {
           // single M/=/X run: query offset is linear in the column (pileup.d:195-203)
           qoff = qoff0 + k;
@@ -318,14 +326,28 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
           qual = en.qual;
           qoff = en.qoff;
         }
-        o.read_idx[slot] = ri.w;
-        o.base[slot] = (uint8_t)base;
-        o.qual[slot] = (uint8_t)qual;
-        if (o.qoff) o.qoff[slot] = qoff;
+        if (!COUNTS) {
+          o.read_idx[slot] = ri.w;
+          o.base[slot] = (uint8_t)base;
+          o.qual[slot] = (uint8_t)qual;
+          if (o.qoff) o.qoff[slot] = qoff;
+        }
       }
-      if (lane == ci) my_off += __popc(m);
+      if (COUNTS) {
+        const uint32_t a = __popc(__ballot_sync(0xffffffffu, base == 'A')), cc = __popc(__ballot_sync(0xffffffffu, base == 'C'));
+        const uint32_t g = __popc(__ballot_sync(0xffffffffu, base == 'G')), t = __popc(__ballot_sync(0xffffffffu, base == 'T'));
+        const uint32_t d = __popc(__ballot_sync(0xffffffffu, base == '-'));
+        if (lane == ci) {
+          cnt[0] += a; cnt[1] += cc; cnt[2] += g; cnt[3] += t; cnt[5] += d;
+          cnt[4] += __popc(m) - a - cc - g - t - d;
+        }
+      } else if (lane == ci) {
+        my_off += __popc(m);
+      }
     }
   }
+  if (COUNTS && lane < ncols)
+    for (int q = 0; q < 6; ++q) o.counts[(size_t)(c0 + lane) * 6 + q] = cnt[q];
 }
 
 // ---- carry to the next batch ------------------------------------------------------------------------
@@ -449,7 +471,8 @@ void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnS
   if (n_col == 0) return;
   uint32_t warps = (n_col + CHUNK - 1) / CHUNK;
   uint32_t grid = (warps + ENT_WARPS - 1) / ENT_WARPS;
-  entries_kernel<<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
+  if (o.counts) entries_kernel<true><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
+  else entries_kernel<false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
   ++g_kernel_launches;
 }
 

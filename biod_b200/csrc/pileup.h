@@ -65,6 +65,7 @@ struct ColumnOutput {
   uint8_t* base;
   uint8_t* qual;
   uint32_t* qoff;                // or nullptr
+  uint32_t* counts;              // counts_only: [n_col*6] A,C,G,T,other,deletion; entries are then not written
 };
 
 struct CarryOut {

@@ -36,8 +36,8 @@ struct CarryBufs {
 // asynchronous copy on the copy stream.  Two sets alternate so that batch k+1 is computed and copied while
 // the caller still reads batch k.
 struct OutSet {
-  DevBuf d[7];      // col_pos, col_off, nstart, read_idx, base, qual, qoff
-  PinBuf h[6];      // col_pos, col_off, nstart, read_idx, base|qual, qoff
+  DevBuf d[8];      // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts
+  PinBuf h[7];      // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts
   size_t col_cap = 0, ent_cap = 0;
   cudaEvent_t computed = nullptr, done = nullptr;
 };
@@ -174,9 +174,9 @@ static biodb_status load_batch(biodb_pileup* pl) {
   if (pl->sharded && pl->halo_blocks_left && p.blocks.size()) {
     // records that start in the halo blocks: rec_base[h] of the scan workspace (the halo is the head of the first batch)
     uint32_t hb = std::min<uint32_t>(pl->halo_blocks_left, (uint32_t)p.blocks.size());
-    ScanWorkspace w = carve_scan_workspace(p.d_ws.p, (uint32_t)p.blocks.size() + (p.segs.size() > p.blocks.size() ? 1 : 0));
+    const ScanWorkspace& w = p.ws_cur;
     uint64_t* hh = (uint64_t*)pl->h_small.p;
-    PL_TRY(launch_copy_bytes(hh + 8, w.rec_base + hb + (p.segs.size() > p.blocks.size() ? 1 : 0), 8, p.st));
+    PL_TRY(launch_copy_bytes(hh + 8, w.rec_base + hb + p.ws_carry, 8, p.st));
     PL_TRY(cudaStreamSynchronize(p.st));
     pl->index_bias += hh[8];
     pl->shard.n_halo_records = pl->index_bias;
@@ -185,10 +185,10 @@ static biodb_status load_batch(biodb_pileup* pl) {
   if (pl->sharded && p.n) {
     // halo check: largest end among this batch's own records on hi_ref, over all and over those that start before
     // the shard's tail blocks.  Records of the halo (index < bias) may be included: they only raise the bound.
-    const uint32_t off = p.segs.size() > p.blocks.size() ? 1 : 0;
+    const uint32_t off = p.ws_carry;
     uint32_t nbt = 0;
     while (nbt < p.blocks.size() && p.blocks[nbt].coffset < pl->tail_coffset) ++nbt;
-    ScanWorkspace w = carve_scan_workspace(p.d_ws.p, (uint32_t)p.blocks.size() + off);
+    const ScanWorkspace& w = p.ws_cur;
     RecordArrays a = p.arrays(c.n);
     pileup_max_end(a.ref_id, a.pos, a.end_pos, (uint32_t)p.n, w.rec_base + nbt + off, pl->shard.hi_ref,
                    pl->d_maxend.as<int32_t>(), p.st);
@@ -661,15 +661,21 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       s.clo = clo;
       s.chi = chi;
       ColumnScratch c{pl->cs[0].as<int32_t>(), os.d[2].as<uint32_t>(), pl->cs[1].as<uint32_t>(), pl->cs[2].as<uint32_t>()};
-      ColumnOutput o{os.d[0].as<uint64_t>(), os.d[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr};
+      ColumnOutput o{os.d[0].as<uint64_t>(), os.d[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr, nullptr};
       p.stage_begin();
       pileup_phase2(v, g0, g1, n_islands, n_col, s, c, o, st);
       p.stage_end(&p.stats.pileup_ms);
       PL_TRY(launch_copy_bytes(pl->h_small.p, o.col_off + n_col, 8, st));
       PL_TRY(cudaStreamSynchronize(st));
       n_entries = *pl->h_small.as<uint64_t>();
-      const bool want_q = pl->prm.want_query_offset != 0;
-      if (n_entries + 8 > os.ent_cap) {
+      const bool counts_only = pl->prm.counts_only != 0;
+      const bool want_q = pl->prm.want_query_offset != 0 && !counts_only;
+      if (counts_only) {
+        PL_TRY(os.d[7].ensure(os.col_cap * 24, st));
+        if (!p.r->opts.device_output) PL_TRY(os.h[6].ensure(os.col_cap * 24));
+        o.counts = os.d[7].as<uint32_t>();
+      }
+      if (!counts_only && n_entries + 8 > os.ent_cap) {
         size_t cap = (size_t)n_entries + n_entries / 8 + 4096;
         PL_TRY(os.d[3].ensure(cap * 4, st));
         PL_TRY(os.d[4].ensure(cap, st));
@@ -684,9 +690,11 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         PL_TRY(os.d[6].ensure(os.ent_cap * 4, st));
         if (!p.r->opts.device_output) PL_TRY(os.h[5].ensure(os.ent_cap * 4));
       }
-      o.read_idx = os.d[3].as<uint32_t>();
-      o.base = os.d[4].as<uint8_t>();
-      o.qual = os.d[5].as<uint8_t>();
+      if (!counts_only) {
+        o.read_idx = os.d[3].as<uint32_t>();
+        o.base = os.d[4].as<uint8_t>();
+        o.qual = os.d[5].as<uint8_t>();
+      }
       o.qoff = want_q ? os.d[6].as<uint32_t>() : nullptr;
       p.stage_begin();
       pileup_entries(v, n_col, s, c, o, st);
@@ -696,13 +704,17 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       if (!p.r->opts.device_output) {
         cudaStream_t cs = pl->copy_st;
         PL_TRY(cudaStreamWaitEvent(cs, os.computed, 0));
-        p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + n_entries * (6 + (want_q ? 4 : 0));
+        p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + (counts_only ? (uint64_t)n_col * 24 : n_entries * (6 + (want_q ? 4 : 0)));
         PL_TRY(cudaMemcpyAsync(os.h[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
         PL_TRY(cudaMemcpyAsync(os.h[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, cs));
         PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
-        PL_TRY(cudaMemcpyAsync(os.h[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
-        PL_TRY(cudaMemcpyAsync(os.h[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
-        PL_TRY(cudaMemcpyAsync(os.h[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+        if (counts_only) {
+          PL_TRY(cudaMemcpyAsync(os.h[6].p, o.counts, (size_t)n_col * 24, cudaMemcpyDeviceToHost, cs));
+        } else {
+          PL_TRY(cudaMemcpyAsync(os.h[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+        }
         if (want_q) PL_TRY(cudaMemcpyAsync(os.h[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
         PL_TRY(cudaEventRecord(os.done, cs));
       } else {
@@ -768,6 +780,10 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       cols->base = os.d[4].as<uint8_t>();
       cols->qual = os.d[5].as<uint8_t>();
       cols->query_offset = pl->prm.want_query_offset ? os.d[6].as<uint32_t>() : nullptr;
+      if (pl->prm.counts_only) {
+        cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
+        cols->counts = os.d[7].as<uint32_t>();
+      }
       return BIODB_OK;
     }
     cols->position = os.h[0].as<uint64_t>();
@@ -777,6 +793,10 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     cols->base = os.h[4].as<uint8_t>();
     cols->qual = os.h[4].as<uint8_t>() + n_entries;
     cols->query_offset = pl->prm.want_query_offset ? os.h[5].as<uint32_t>() : nullptr;
+    if (pl->prm.counts_only) {
+      cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
+      cols->counts = os.h[6].as<uint32_t>();
+    }
     return BIODB_OK;
   }
 }

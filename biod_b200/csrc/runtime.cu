@@ -318,8 +318,8 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   const bool resident = r->d_file.p != nullptr;
   if (!resident) CUDA_TRY(d_comp.ensure((size_t)(c1 - c0) + 256, st));
   CUDA_TRY(d_u.ensure((size_t)u_len + 256, st));
-  CUDA_TRY(d_status.ensure((size_t)nb * 4 + 16, st));
-  CUDA_TRY(h_status.ensure((size_t)nb * 4 + 16));
+  CUDA_TRY(d_status.ensure((size_t)nb * 8 + 16, st));      // statuses, then (verify_crc) the computed CRCs
+  CUDA_TRY(h_status.ensure((size_t)nb * 8 + 16));
   CUDA_TRY(d_ws.ensure(scan_workspace_bytes(nsb), st));
   if (has_carry)
     CUDA_TRY(launch_copy_bytes(d_u.p, d_carry_tail.p, carry_tail_len, st));
@@ -344,10 +344,27 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     stats.n_blocks += nb;
     stats.compressed_bytes += c1 - c0;
     stats.uncompressed_bytes += off - (has_carry ? carry_tail_len : 0);
-    CUDA_TRY(launch_copy_bytes(h_status.p, d_status.p, (size_t)nb * 4, st));
+    const bool check_crc = r->opts.verify_crc != 0;
+    if (check_crc) {
+      CUDA_TRY(launch_crc32(d_u.as<uint8_t>(), d_outoff, d_isize, nb, d_status.as<uint32_t>() + nb, st));
+    }
+    CUDA_TRY(launch_copy_bytes(h_status.p, d_status.p, (size_t)nb * (check_crc ? 8 : 4), st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    const int32_t* hs = h_status.as<int32_t>();
+    int32_t* hs = h_status.as<int32_t>();
+    if (check_crc) {
+      // block.d:187 `assert(block.crc32 == crc32(0, uncompressed))` — a mismatch is reported like corrupt data
+      const uint32_t* hc = h_status.as<uint32_t>() + nb;
+      for (uint32_t i = 0; i < nb; ++i)
+        if (hs[i] == 0 && hc[i] != blocks[i].crc32) hs[i] = -1003;
+    }
     for (uint32_t i = 0; i < nb; ++i) {
+      if (hs[i] == -1003) {
+        set_error(&pending, BIODB_ERR_ZLIB, -3, blocks[i].coffset, "CRC32 of the inflated BGZF block does not match its footer");
+        u_len = h_outoff[i];
+        blocks.resize(i);
+        last_batch = true;
+        break;
+      }
       if (hs[i] != 0) {
         // the blocks before the faulty one are still delivered; the ZlibException surfaces when the
         // iteration reaches it (test/unittests.d:140-142)
@@ -379,7 +396,10 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   const int eof_semantics = (last_batch && pending.status == 0) ? 1 : 0;
   uint64_t want_rec = std::max<uint64_t>(rec_capacity, u_len / 96 + 1024);
   uint64_t want_cig = std::max<uint64_t>(cigar_capacity, want_rec * 2);
-  ScanWorkspace ws = carve_scan_workspace(d_ws.p, nsb2);
+  // same carving as the one handed to the fused walk (the layout depends on the block count it was carved for)
+  ScanWorkspace ws = carve_scan_workspace(d_ws.p, nsb);
+  ws_cur = ws;
+  ws_carry = has_carry ? 1u : 0u;
   for (int attempt = 0; attempt < 8; ++attempt) {
     if (want_rec != rec_capacity || want_cig != cigar_capacity || rec_front < front_slots) {
       rec_capacity = want_rec;
@@ -761,9 +781,10 @@ float biodb_reads_progress(const biodb_reads* it) {
 biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off, const uint32_t* cdata_size,
                                const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
                                int32_t* status, uint32_t* crc, void* stream) {
-  (void)crc;
   InflateArgs ia{comp, payload_off, cdata_size, out_off, isize, out, status, n_blocks, WalkOut{}};
-  return launch_inflate(ia, (cudaStream_t)stream) == cudaSuccess ? BIODB_OK : BIODB_ERR_CUDA;
+  if (launch_inflate(ia, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
+  if (crc && launch_crc32(out, out_off, isize, n_blocks, crc, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
+  return BIODB_OK;
 }
 
 size_t biodb_dev_scan_workspace_bytes(uint32_t n_blocks) { return scan_workspace_bytes(n_blocks); }

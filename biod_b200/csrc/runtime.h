@@ -105,6 +105,8 @@ struct Pass {
   uint64_t end_coffset_last = 0;
   uint64_t n = 0, n_cigar = 0, tail = 0;
   bool final_slice = false;
+  ScanWorkspace ws_cur{};           // scan workspace of the current slice (rec_base etc.)
+  uint32_t ws_carry = 0;            // 1 when scan block 0 is the carried tail
   bool raw_mode = false;            // header pass: inflate only, no record scan, no carry
   // measurement (biodb_stats)
   biodb_stats stats{};

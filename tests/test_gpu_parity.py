@@ -110,11 +110,17 @@ def test_corrupted_files_raise_the_pinned_classes(name, cls):
     data = fixture_bytes(name)
     with pytest.raises(orc.OracleError) as oe:
         orc.Bam(data).decode()
-    try:
-        rd, g, raws, err = gpu_records(data, blocks_per_batch=2)
-    except Exception as e:  # noqa: BLE001  raised by the constructor
-        err, raws = e, []
-    assert err is not None and type(err).__name__ == cls
+    for bpb in (2, 0, 5):
+        try:
+            rd, g, raws, err = gpu_records(data, blocks_per_batch=bpb)
+        except Exception as e:  # noqa: BLE001  raised by the constructor
+            err, raws = e, []
+        assert err is not None and type(err).__name__ == cls
+        try:
+            n_before = orc.Bam(data).decode(raise_on_error=False).n_records
+        except orc.OracleError:
+            n_before = 0
+        assert len(raws) == n_before, (bpb, len(raws), n_before)
     if cls == "BgzfException":
         assert str(err) == oe.value.msg
     else:
@@ -273,3 +279,105 @@ def test_sharded_pileup_synthetic(skip):
         g = gpu_pileup_sharded(data, n_shards, halo_blocks=4, blocks_per_batch=16, skip_zero_coverage=skip)
         assert g["halo_ok"]
         assert_pileup_equal(g, o.pileup_columns(skip))
+
+
+def test_crc_verification():
+    # block.d:187: debug builds of BioD assert the CRC32 of every inflated block; verify_crc does it on the device
+    import struct
+    from biod_b200 import BamReader
+    data = bytearray(fixture_bytes("ex1_header.bam"))
+    rd = BamReader(bytes(data), verify_crc=True, blocks_per_batch=3)
+    assert sum(1 for _ in rd.reads()) == 3270
+    # corrupt the CRC field of the third block: inflate still succeeds, the check must fail when that block is reached
+    o = orc.Bam(bytes(data)).decode()
+    b = o.blocks[2]
+    crc_at = int(b[6]) + int(b[2])
+    data[crc_at] ^= 0x5A
+    assert sum(1 for _ in BamReader(bytes(data), blocks_per_batch=3).reads()) == 3270     # not checked by default
+    rd = BamReader(bytes(data), verify_crc=True, blocks_per_batch=2)
+    got = 0
+    with pytest.raises(Exception) as ei:
+        for _ in rd.reads():
+            got += 1
+    assert type(ei.value).__name__ == "ZlibException" and "CRC32" in str(ei.value)
+    assert 0 < got < 3270
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "bins.bam", "ion_20_chunk.bam"])
+def test_counts_only_mode(name):
+    # fused consumer view: per-column A,C,G,T,other,deletion counts == histogram of the oracle's bases
+    from biod_b200 import BamReader
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    p = o.pileup_columns()
+    col = np.repeat(np.arange(p.n_columns), np.diff(p.col_off).astype(np.int64))
+    cat = np.full(len(p.base), 4)
+    for k, ch in enumerate(b"ACGT"):
+        cat[p.base == ch] = k
+    cat[p.base == ord("-")] = 5
+    exp = np.zeros((p.n_columns, 6), dtype=np.uint32)
+    np.add.at(exp, (col, cat), 1)
+    rd = BamReader(data, blocks_per_batch=3)
+    got, pos, cov = [], [], []
+    for b in rd.column_batches(False, counts_only=True, copy=True):
+        assert b.read_idx.size == 0
+        got.append(b.counts)
+        pos.append(b.position)
+        cov.append(np.diff(b.col_off))
+    assert np.array_equal(np.concatenate(pos), p.col_pos)
+    assert np.array_equal(np.concatenate(got), exp)
+    assert np.array_equal(np.concatenate(cov), np.diff(p.col_off))
+
+
+@pytest.mark.parametrize("mixed", [False, True])
+def test_large_synthetic_properties(mixed):
+    """Size-independent properties at a scale the oracle does not run at (2 M reads): every live read starts in
+    exactly one column, coverage sums to the sum of reference spans, columns are sorted, entries stay in file
+    order, sharded == unsharded, counts == histogram of bases."""
+    from biod_b200 import BamReader
+    from tools import bamgen
+    n = 2_000_000
+    data = bamgen.generate(n, 2, mixed, level=1)
+    rd = BamReader(data)
+    pos, end = [], []
+    for b in rd.read_batches():
+        pos.append(b.pos.copy())
+        end.append(b.end_pos.copy())
+    pos, end = np.concatenate(pos), np.concatenate(end)
+    assert pos.size == n
+    spans = (end - pos).astype(np.int64)
+    tot_cols = tot_ent = tot_start = 0
+    last_key = (-1, -1)
+    chk = 0
+    for b in rd.column_batches(False):
+        cov = np.diff(b.col_off).astype(np.int64)
+        assert (cov > 0).all()
+        assert (np.diff(b.position.astype(np.int64)) > 0).all()
+        assert (b.ref_id, int(b.position[0])) > last_key
+        last_key = (b.ref_id, int(b.position[-1]))
+        tot_cols += b.n_columns
+        tot_ent += b.n_entries
+        tot_start += int(b.n_starting_here.sum())
+        # file order inside columns: read_idx strictly increasing within each column
+        d = np.diff(b.read_idx.astype(np.int64))
+        ends = (b.col_off[1:-1] - b.col_off[0]).astype(np.int64) - 1      # boundaries between columns
+        mask = np.ones(d.size, dtype=bool)
+        mask[ends] = False
+        assert (d[mask] > 0).all()
+        chk += int(b.base.astype(np.uint64).sum() + 3 * b.qual.astype(np.uint64).sum())
+    assert tot_start == n
+    assert tot_ent == int(spans.sum())
+    # sharded run: same totals and checksum
+    s_cols = s_ent = s_chk = 0
+    for s in range(3):
+        for b in rd.column_batches(False, shard=(s, 3)):
+            s_cols += b.n_columns
+            s_ent += b.n_entries
+            s_chk += int(b.base.astype(np.uint64).sum() + 3 * b.qual.astype(np.uint64).sum())
+    assert (s_cols, s_ent, s_chk) == (tot_cols, tot_ent, chk)
+    # counts mode: per-column counts sum to the coverage
+    c_tot = 0
+    for b in rd.column_batches(False, counts_only=True):
+        assert np.array_equal(b.counts.sum(1), np.diff(b.col_off).astype(np.uint32))
+        c_tot += int(b.counts.sum())
+    assert c_tot == tot_ent
