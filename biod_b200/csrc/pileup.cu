@@ -238,7 +238,10 @@ __device__ __forceinline__ Entry cursor_at(const uint8_t* rec, uint32_t lname, u
 }
 
 constexpr int ENT_WARPS = 8;
-constexpr int CHUNK = 32;            // columns per warp
+#ifndef BIODB_CHUNK
+#define BIODB_CHUNK 32
+#endif
+constexpr int CHUNK = BIODB_CHUNK;   // columns per warp (<= 32)
 
 // 4-bit code -> IUPAC character without a memory lookup: "=ACMGRSV" "TWYHKDBN" packed little-endian (base.d:85)
 __device__ __forceinline__ uint32_t base_char(uint32_t code) {
