@@ -270,11 +270,24 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+    # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (bytes per BGZF block there x
+    # blocks per launch here); None when no capture is committed
+    traffic = None
+    try:
+        for k in json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r1_summary.json"))):
+            if k["kernel"].endswith("inflate_kernel"):
+                def _b(v):
+                    x, u = v.split()
+                    return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                per_block = (_b(k["dram__bytes_read.sum"]) + _b(k["dram__bytes_write.sum"])) / float(k["launch__grid_size"].split()[0])
+                traffic = per_block * s0.n_blocks / max(1, s0.inflate_launches)
+    except Exception:  # noqa: BLE001
+        traffic = None
     infl_ms = np.mean([s[0].inflate_ms for s in steps])
     infl_bytes = s0.compressed_bytes + s0.uncompressed_bytes
     achieved = infl_bytes / (infl_ms * 1e-3) / 1e9
     roofline = {"kernel": "inflate_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": infl_bytes / max(1, s0.inflate_launches),
                 "launches_per_step": int(s0.inflate_launches),
                 "avg_launch_ms": infl_ms / max(1, s0.inflate_launches),
