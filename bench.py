@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--level", type=int, default=-1, help="zlib level of the synthetic file (-1 = BioD writer default)")
     ap.add_argument("--blocks-per-batch", type=int, default=8192)
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
+    ap.add_argument("--straddle", action="store_true", help="htsjdk-style file: records cut across BGZF blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cache-dir", default=os.environ.get("BIODB_BENCH_CACHE", "/dev/shm"))
@@ -63,11 +64,12 @@ def synth_file(args, cfg, n_reads, rank, barrier):
     """Generate (rank 0) or load the synthetic BAM; returns a numpy uint8 array."""
     from tools import bamgen
     os.makedirs(args.cache_dir, exist_ok=True)
-    path = os.path.join(args.cache_dir, f"biod_b200_cfg{args.config}_{n_reads}_l{args.level}.bam")
+    path = os.path.join(args.cache_dir, f"biod_b200_cfg{args.config}_{n_reads}_l{args.level}{'_s' if args.straddle else ''}.bam")
     t0 = time.time()
     made = False
     if rank == 0 and not os.path.exists(path):
-        data = bamgen.generate(n_reads, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + args.config)
+        data = bamgen.generate(n_reads, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + args.config,
+                               straddle=args.straddle)
         tmp = path + ".tmp"
         data.tofile(tmp)
         os.replace(tmp, path)
@@ -164,7 +166,7 @@ def main():
     n_reads = args.reads or cfg["reads"]
     cores = os.cpu_count() or 1
     workload = cfg["name"] + ("" if not args.reads else f" — SCALED to {n_reads} reads by --reads") + \
-        f", zlib level {args.level}"
+        f", zlib level {args.level}" + (", records straddling BGZF blocks (htsjdk layout)" if args.straddle else "")
 
     # ------------------------------------------------------------------ reference arm (CPU) --------------
     if args.impl == "reference":

@@ -308,6 +308,13 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
   const uint32_t win0 = (walking && blk == 0) ? a.walk.in0 : 0;
   uint32_t wnext = win0, wcnt = 0, wncig = 0;
   int wbad = WALK_OK;
+  // Entry point of the chain into this block.  Block 0 of a slice enters at a known offset.  Every other block
+  // first tries offset 0 (files written by BioD / htslib start every block at a record) and otherwise searches
+  // for the first offset where a plausible record starts (htsjdk-style files cut records anywhere).  The guess is
+  // only a speculation: scan_resolve_kernel checks it against the previous block's chain end and repairs it.
+  bool wentry = !walking || (blk == 0 && a.walk.sb_offset == 0);
+  uint32_t wsearch = 0;        // candidates below this offset are ruled out
+  uint64_t win_abs = ~0ull;    // reported entry (absolute); stays "unknown" when no record starts in the block
 #define OPOS() (o - oa)
 
   // pull one 32-bit word from the staging ring (warp-uniform)
@@ -346,8 +353,62 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
     return lds8(ring + (r0 & OMASK)) | (lds8(ring + ((r0 + 1) & OMASK)) << 8) | (lds8(ring + ((r0 + 2) & OMASK)) << 16) |
            (lds8(ring + ((r0 + 3) & OMASK)) << 24);
   };
+  // is a BAM record header plausible at block-relative offset c?  1 yes, 0 no, -1 not enough bytes produced yet
+  auto plausible = [&](uint32_t c, uint32_t avail) -> int {
+    if (c + 36 > avail) return -1;
+    const int32_t bs = (int32_t)ring32(c);
+    if (bs < 34 || bs > (1 << 27)) return 0;
+    const int32_t ref = (int32_t)ring32(c + 4), pos = (int32_t)ring32(c + 8);
+    if (ref < -1 || ref >= a.walk.n_refs || pos < -1) return 0;
+    const uint32_t bin_mq_nl = ring32(c + 12), flag_nc = ring32(c + 16);
+    const int32_t l_seq = (int32_t)ring32(c + 20), nref = (int32_t)ring32(c + 24), npos = (int32_t)ring32(c + 28);
+    const uint32_t lname = bin_mq_nl & 0xFF, nc = flag_nc & 0xFFFF;
+    if (lname == 0 || l_seq < 0 || nref < -1 || nref >= a.walk.n_refs || npos < -1) return 0;
+    const uint64_t need = 32ull + lname + 4ull * nc + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
+    if (need > (uint64_t)bs) return 0;
+    // read name: printable characters closed by a NUL (read.d:984-990)
+    const uint32_t nm = c + 36;
+    if (nm + lname > avail) return -1;
+    if (lds8(ring + ((oa + nm + lname - 1) & OMASK)) != 0) return 0;
+    for (uint32_t k = 0; k + 1 < lname && k < 8; ++k) {
+      const uint32_t ch = lds8(ring + ((oa + nm + k) & OMASK));
+      if (ch < 0x21 || ch > 0x7e) return 0;
+    }
+    return 1;
+  };
+  // find the chain entry: lanes test 32 candidate offsets at a time
+  auto find_entry = [&](uint32_t avail, bool final) {
+    while (!wentry) {
+      const uint32_t c = wsearch + lane;
+      int ok = (c < isize) ? plausible(c, avail) : 0;
+      if (ok == 1) {
+        // a lone plausible header is not enough: the record it announces must be followed by another plausible one
+        // (only when that one is close enough for the candidate itself to stay in the output ring meanwhile)
+        const uint32_t nx = c + 4 + ring32(c);
+        if (nx + 36 <= avail) ok = plausible(nx, avail) == 0 ? 0 : 1;
+        else if (nx + 36 <= isize && nx - c <= 1024 && !final) ok = -1;
+      }
+      const uint32_t yes = __ballot_sync(0xffffffffu, ok == 1), wait = __ballot_sync(0xffffffffu, ok == -1);
+      const uint32_t first_yes = yes ? (uint32_t)__ffs(yes) - 1 : 32, first_wait = wait ? (uint32_t)__ffs(wait) - 1 : 32;
+      if (first_yes < first_wait) {
+        wnext = wsearch + first_yes;
+        win_abs = obase + wnext;
+        wentry = true;
+      } else if (first_wait < 32) {
+        if (!final) { wsearch += first_wait; return; }      // come back when more bytes are there
+        wsearch += first_wait + 1;                          // end of block: what cannot be checked is not an entry
+      } else {
+        wsearch += 32;
+      }
+      if (!wentry && wsearch >= isize) { wnext = isize; wentry = true; }   // no record starts in this block
+    }
+  };
   // follow the block_size chain (readrange.d:118-173) over the records whose 24 leading bytes are already produced
   auto walk_upto = [&](uint32_t avail, bool final) {
+    if (!wentry) {
+      find_entry(avail, final);
+      if (!wentry) return;
+    }
     while (wbad == WALK_OK && wnext < isize) {
       if (wnext + 24 > avail) {
         if (final) wbad = WALK_INCOMPLETE;     // the header straddles the block end: the resolve kernel finishes it
@@ -667,7 +728,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
     if (walking) {
       a.walk.cnt[sb] = wcnt;
       a.walk.ncig[sb] = wncig;
-      a.walk.in[sb] = obase + ((blk == 0) ? a.walk.in0 : 0);
+      a.walk.in[sb] = (blk == 0 && a.walk.sb_offset == 0) ? obase + a.walk.in0 : win_abs;
       a.walk.out[sb] = obase + wnext;
       a.walk.bad[sb] = status ? WALK_TAIL : wbad;
     }

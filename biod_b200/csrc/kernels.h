@@ -28,6 +28,7 @@ struct WalkOut {
   uint32_t sb_offset; // scan-block index of BGZF block 0 (1 when a carried tail forms pseudo block 0)
   uint32_t in0;       // entry offset inside block 0 (bytes of header in front of the first record)
   uint64_t u_len;     // length of the whole slice
+  int32_t n_refs;     // reference count of the file (plausibility of refID fields)
 };
 enum { WALK_OK = 0, WALK_TAIL = 1, WALK_BAD_SIZE = 2, WALK_BAD_FIELDS = 3, WALK_INCOMPLETE = 4 };
 

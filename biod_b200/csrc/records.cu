@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(1024) scan_resolve_kernel(const uint8_t* __res
                                                            const uint64_t* __restrict__ block_uoff, uint32_t n_blocks,
                                                            int final_slice, ScanWorkspace ws, RecordArrays ra,
                                                            uint64_t* __restrict__ result) {
-  __shared__ uint32_t first_fail;
+  constexpr uint32_t FAIL_WORDS = 1024;           // bitmap of inconsistent blocks (32768 blocks)
+  __shared__ uint32_t s_failbits[FAIL_WORDS];
+  __shared__ uint32_t s_nfail;
   __shared__ uint64_t s_scan[2][256];
   __shared__ uint64_t s_carry[2];
   __shared__ uint32_t s_last;     // last block whose records count (the chain stops inside or after it)
@@ -96,56 +98,75 @@ __global__ void __launch_bounds__(1024) scan_resolve_kernel(const uint8_t* __res
     if (t == 0) { result[0] = 0; result[1] = 0; result[2] = 0; result[3] = 0; ra.cigar_off[0] = 0; }
     return;
   }
-  if (t == 0) first_fail = n_blocks;
-  __syncthreads();
-  // block b needs the sequential repair if the chain does not arrive exactly at its start, if the walk of the
-  // previous block stopped early, or if its own (fused) walk could not finish inside the block
+  // phase 0 (parallel): a fused walk stops when the header of its last record straddles the block end — finish
+  // those walks from where they stopped (one record each, common in htsjdk-written files)
   for (uint32_t b = t; b < n_blocks; b += blockDim.x) {
-    bool fail = ws.bad[b] == WALK_INCOMPLETE;
-    if (b > 0 && (ws.out[b - 1] != block_uoff[b] || ws.bad[b - 1] != WALK_OK)) fail = true;
-    if (fail) atomicMin(&first_fail, b);
+    if (ws.bad[b] == WALK_INCOMPLETE) {
+      uint32_t cnt, ncig;
+      uint64_t out;
+      ws.bad[b] = walk_block(u, u_len, ws.out[b], block_uoff[b], block_uoff[b + 1], ws.rel + (size_t)b * SCAN_SLOTS, &cnt, &ncig,
+                             &out, ws.cnt[b], ws.ncig[b]);
+      ws.cnt[b] = cnt; ws.ncig[b] = ncig; ws.out[b] = out;
+    }
+  }
+  for (uint32_t w = t; w < FAIL_WORDS; w += blockDim.x) s_failbits[w] = 0;
+  if (t == 0) { s_nfail = 0; s_carry[0] = 0; s_carry[1] = 0; }
+  __syncthreads();
+  // phase 1 (parallel): block b is inconsistent if the chain of block b-1 does not end exactly where block b's
+  // walk entered, or if that chain stopped early
+  for (uint32_t b = 1 + t; b < n_blocks; b += blockDim.x) {
+    if (ws.out[b - 1] != ws.in[b] || ws.bad[b - 1] != WALK_OK) {
+      if (b < FAIL_WORDS * 32) atomicOr(&s_failbits[b >> 5], 1u << (b & 31));
+      atomicAdd(&s_nfail, 1u);
+    }
   }
   __syncthreads();
+  // phase 2 (one thread, rare): repair the inconsistent blocks in order; a repaired chain usually rejoins the
+  // speculated one at once, so only the flagged blocks are visited
   if (t == 0) {
-    uint32_t b = first_fail;
-    if (b >= n_blocks) {
-      s_last = n_blocks - 1;
-      s_why = ws.bad[n_blocks - 1];
-    } else if (b > 0 && ws.bad[b - 1] != WALK_OK && ws.bad[b - 1] != WALK_INCOMPLETE) {
-      s_last = b - 1;
-      s_why = ws.bad[b - 1];
-    } else {
-      // entry point of block b: where the previous block's chain left off (blocks before b are all consistent)
-      uint64_t in = (b == 0) ? ws.in[0] : ws.out[b - 1];
-      if (b > 0 && ws.bad[b - 1] == WALK_INCOMPLETE) { --b; in = ws.in[b]; }
-      uint32_t last = n_blocks - 1;
-      int why = WALK_OK;
-      for (; b < n_blocks; ++b) {
-        const uint64_t start = block_uoff[b], end = block_uoff[b + 1];
-        if (in >= end) {                       // the whole block lies inside a straddling record
-          ws.cnt[b] = 0; ws.ncig[b] = 0; ws.out[b] = in; ws.in[b] = in; ws.bad[b] = WALK_OK;
-          continue;
+    uint32_t last = n_blocks - 1;
+    int why = ws.bad[n_blocks - 1];
+    if (s_nfail) {
+      auto next_fail = [&](uint32_t from) -> uint32_t {       // first flagged block >= from
+        if (n_blocks > FAIL_WORDS * 32) {                      // bitmap too small: plain scan
+          for (uint32_t b = from; b < n_blocks; ++b)
+            if (b > 0 && (ws.out[b - 1] != ws.in[b] || ws.bad[b - 1] != WALK_OK)) return b;
+          return n_blocks;
         }
-        if (in != ws.in[b]) {                  // walk again from the true entry point
+        for (uint32_t w = from >> 5; w < FAIL_WORDS && w * 32 < n_blocks; ++w) {
+          uint32_t bits = s_failbits[w];
+          if (w == (from >> 5)) bits &= ~0u << (from & 31);
+          if (bits) return w * 32 + (uint32_t)__ffs(bits) - 1;
+        }
+        return n_blocks;
+      };
+      uint32_t b = next_fail(1);
+      bool stopped = false;
+      while (b < n_blocks && !stopped) {
+        if (ws.bad[b - 1] != WALK_OK) { last = b - 1; why = ws.bad[b - 1]; stopped = true; break; }
+        uint64_t in = ws.out[b - 1];
+        // walk forward from b until the chain rejoins the speculated one
+        for (; b < n_blocks; ++b) {
+          const uint64_t start = block_uoff[b], end = block_uoff[b + 1];
+          if (in == ws.in[b]) break;             // rejoined: block b was walked from the right entry
+          if (in >= end) {                       // the whole block lies inside a straddling record
+            ws.cnt[b] = 0; ws.ncig[b] = 0; ws.out[b] = in; ws.in[b] = in; ws.bad[b] = WALK_OK;
+            continue;
+          }
           uint32_t cnt, ncig;
           uint64_t out;
           ws.bad[b] = walk_block(u, u_len, in, start, end, ws.rel + (size_t)b * SCAN_SLOTS, &cnt, &ncig, &out);
           ws.cnt[b] = cnt; ws.ncig[b] = ncig; ws.out[b] = out; ws.in[b] = in;
-        } else if (ws.bad[b] == WALK_INCOMPLETE) {   // finish a walk whose last header straddles the block end
-          uint32_t cnt, ncig;
-          uint64_t out;
-          ws.bad[b] = walk_block(u, u_len, ws.out[b], start, end, ws.rel + (size_t)b * SCAN_SLOTS, &cnt, &ncig, &out,
-                                 ws.cnt[b], ws.ncig[b]);
-          ws.cnt[b] = cnt; ws.ncig[b] = ncig; ws.out[b] = out;
+          if (ws.bad[b] != WALK_OK) { last = b; why = ws.bad[b]; stopped = true; break; }
+          in = out;
         }
-        if (ws.bad[b] != WALK_OK) { last = b; why = ws.bad[b]; break; }
-        in = ws.out[b];
+        if (stopped || b >= n_blocks) break;
+        b = next_fail(b + 1);
       }
-      s_last = last;
-      s_why = why;
+      if (!stopped) { last = n_blocks - 1; why = ws.bad[n_blocks - 1]; }
     }
-    s_carry[0] = 0;
-    s_carry[1] = 0;
+    s_last = last;
+    s_why = why;
   }
   __syncthreads();
   const uint32_t last = s_last;

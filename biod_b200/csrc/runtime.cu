@@ -335,7 +335,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
       // fused record-chain walk: the inflate warps follow the block_size chain of their own block
       ScanWorkspace w0 = carve_scan_workspace(d_ws.p, nsb);
       ia.walk = WalkOut{w0.rel, w0.cnt, w0.ncig, w0.out, w0.in, w0.bad, has_carry ? 1u : 0u,
-                        has_carry ? 0u : (uint32_t)(h_buoff[0]), u_len};
+                        has_carry ? 0u : (uint32_t)(h_buoff[0]), u_len, (int32_t)r->ref_names.size()};
     }
     stage_begin();
     CUDA_TRY(launch_inflate(ia, st));

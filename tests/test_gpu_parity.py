@@ -329,6 +329,15 @@ def test_counts_only_mode(name):
     assert np.array_equal(np.concatenate(cov), np.diff(p.col_off))
 
 
+def test_straddling_layout_matches_oracle():
+    # htsjdk-style files fill every BGZF block regardless of record boundaries: the fused chain walk has to find
+    # its entry point in every block (plausibility search) and the resolve kernel has to confirm it
+    from tools import bamgen
+    data = bamgen.generate(40000, 2, True, level=1, threads=4, straddle=True).tobytes()
+    o = check_records(data, 7)
+    assert_pileup_equal(gpu_pileup(data, False, 5), o.pileup_columns())
+
+
 @pytest.mark.parametrize("mixed", [False, True])
 def test_large_synthetic_properties(mixed):
     """Size-independent properties at a scale the oracle does not run at (2 M reads): every live read starts in

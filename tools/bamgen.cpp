@@ -193,10 +193,12 @@ void bgzf_block(const uint8_t* payload, uint32_t n, int level, std::vector<uint8
   out.resize(at + 18 + c + 8);
 }
 
-void pack_blocks(const std::vector<uint8_t>& raw, const std::vector<uint32_t>& rec_end, int level, std::vector<uint8_t>& out) {
-  // records never straddle a block when they fit (writer.d:259-267)
+void pack_blocks(const std::vector<uint8_t>& raw, const std::vector<uint32_t>& rec_end, int level, std::vector<uint8_t>& out,
+                 bool straddle = false) {
+  // records never straddle a block when they fit (writer.d:259-267) — unless the htsjdk-style layout is asked for,
+  // which fills every block to 0xFF00 bytes wherever that cuts a record
   size_t start = 0, last = 0;
-  for (size_t k = 0; k < rec_end.size(); ++k) {
+  for (size_t k = 0; k < rec_end.size() && !straddle; ++k) {
     if (rec_end[k] - start > BLOCK_PAYLOAD && last > start) {
       bgzf_block(raw.data() + start, (uint32_t)(last - start), level, out);
       start = last;
@@ -223,7 +225,7 @@ uint64_t bamgen_bound(uint64_t n_reads, int mixed) {
 // ref_len_out (may be null) receives the common contig length.
 uint64_t bamgen_generate(uint64_t n_reads, uint32_t n_refs, int mixed, int level, uint64_t seed, int threads, uint8_t* out,
                          uint64_t cap, uint64_t* ref_len_out) {
-  Params P{n_reads, n_refs ? n_refs : 1, mixed, level, seed, 0};
+  Params P{n_reads, n_refs ? n_refs : 1, mixed & 1, level, seed, 0};
   P.reads_per_ref = (n_reads + P.n_refs - 1) / P.n_refs;
   // units never cross a reference
   struct Unit { uint64_t first; uint32_t n; uint32_t ref; int64_t pos0; };
@@ -305,7 +307,7 @@ uint64_t bamgen_generate(uint64_t n_reads, uint32_t n_refs, int mixed, int level
             ends.push_back((uint32_t)raw.size());
           }
           comp[k].clear();
-          pack_blocks(raw, ends, level, comp[k]);
+          pack_blocks(raw, ends, level, comp[k], (mixed & 2) != 0);
         }
       });
     for (auto& x : th) x.join();

@@ -28,7 +28,7 @@ def lib():
     return _L
 
 
-def generate(n_reads, n_refs=1, mixed=False, level=-1, seed=SEED_BASE + 2, threads=None, out=None):
+def generate(n_reads, n_refs=1, mixed=False, level=-1, seed=SEED_BASE + 2, threads=None, out=None, straddle=False):
     """Returns a numpy uint8 array holding a complete BAM file (a view of `out` when given)."""
     L = lib()
     threads = threads or os.cpu_count() or 1
@@ -36,7 +36,8 @@ def generate(n_reads, n_refs=1, mixed=False, level=-1, seed=SEED_BASE + 2, threa
     if out is None:
         out = np.empty(cap, dtype=np.uint8)
     rl = C.c_uint64()
-    n = L.bamgen_generate(n_reads, n_refs, int(mixed), level, seed, threads, out.ctypes.data, out.size, C.byref(rl))
+    n = L.bamgen_generate(n_reads, n_refs, int(mixed) | (2 if straddle else 0), level, seed, threads, out.ctypes.data,
+                          out.size, C.byref(rl))
     if n == 0:
         raise MemoryError("bamgen: output buffer too small")
     return out[:int(n)]
