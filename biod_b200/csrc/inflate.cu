@@ -20,11 +20,9 @@
 //    the next match/flush, so their latency hides behind the literals that follow;
 //  * the ring is flushed to HBM in 512-byte, 16-byte-per-lane aligned vector
 //    stores (ring index == global address mod ring size, so alignment carries).
-#include <cuda_runtime.h>
-#include <stddef.h>
-#include <stdint.h>
+#include <stdlib.h>
 
-#include "kernels.h"
+#include "inflate_common.cuh"
 
 namespace biodb {
 
@@ -39,9 +37,6 @@ namespace {
 #ifndef BIODB_LIT_UNROLL2
 #define BIODB_LIT_UNROLL2 0
 #endif
-#ifndef BIODB_LIT_BITS
-#define BIODB_LIT_BITS 10
-#endif
 constexpr int IN_HALF = BIODB_IN_HALF;    // bytes per TMA chunk
 constexpr int IN_RING = 2 * IN_HALF;
 constexpr int IN_WORDS = IN_RING / 4;
@@ -53,25 +48,6 @@ constexpr int FLUSH = 512;
 constexpr int MAX_PENDING = 2 * FLUSH + 258 + 64;
 constexpr int RING_VALID = OUT_RING - MAX_PENDING - 64;  // any source byte this close to opos is still in the ring
 static_assert(RING_VALID >= 1024, "output ring too small");
-constexpr int LIT_BITS = BIODB_LIT_BITS;
-constexpr int DIST_BITS = 8;
-constexpr int CL_BITS = 7;
-
-// 16-bit LUT entries: [0,8) literal byte / length symbol / distance symbol / code-length symbol,
-// [8,10) kind, [12,16) code length.
-constexpr uint32_t K_LIT = 0, K_LEN = 1, K_EOB = 2, K_SPECIAL = 3;
-constexpr uint32_t ENT_SLOW = K_SPECIAL << 8;           // code longer than the LUT index
-constexpr uint32_t ENT_INVALID = (K_SPECIAL << 8) | 1;  // unused code
-constexpr int Z_DATA = -3;
-constexpr int Z_BUF = -5;
-
-enum { KIND_LITLEN = 0, KIND_DIST = 1, KIND_CODELEN = 2 };
-
-struct Code {               // slow-path side tables of one Huffman code
-  uint16_t cnt[16];         // symbols per code length
-  uint16_t first[16];       // first canonical code of each length
-  uint16_t index[16];       // symbols with shorter codes
-};
 
 struct __align__(16) WarpSmem {
   uint32_t in_ring[IN_WORDS];
@@ -85,161 +61,16 @@ struct __align__(16) WarpSmem {
   unsigned long long mbar[2];
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// explicit shared-space accesses with a 32-bit address: keeps ptxas from rebuilding the shared-window base
-// (S2R SR_CgaCtaId + LEA) inside the hot loop
-__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v));
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-// TMA bulk copy global -> shared (SASS: UBLKCP), completion signalled on the mbarrier.
-__device__ __forceinline__ void tma_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-// length / distance symbol -> (base, extra bits), RFC 1951 §3.2.5
-__device__ __forceinline__ void len_base(uint32_t s /*0..28*/, uint32_t& base, uint32_t& eb) {
-  if (s < 8) { base = 3 + s; eb = 0; }
-  else if (s == 28) { base = 258; eb = 0; }
-  else { eb = (s - 4) >> 2; base = 3 + ((4u + ((s - 4) & 3)) << eb); }
-}
-__device__ __forceinline__ void dist_base(uint32_t d /*0..29*/, uint32_t& base, uint32_t& eb) {
-  if (d < 4) { base = 1 + d; eb = 0; }
-  else { eb = (d - 2) >> 1; base = 1 + ((2u + (d & 1)) << eb); }
-}
-__device__ __forceinline__ uint32_t make_entry(int kind, int sym, int cl) {
-  if (kind == KIND_LITLEN) {
-    if (sym < 256) return ((uint32_t)cl << 12) | (uint32_t)sym;
-    if (sym == 256) return ((uint32_t)cl << 12) | (K_EOB << 8);
-    if (sym > 285) return ENT_INVALID;            // 286/287 exist only in the fixed code and are invalid
-    return ((uint32_t)cl << 12) | (K_LEN << 8) | (uint32_t)(sym - 257);
-  }
-  if (kind == KIND_DIST) return sym > 29 ? ENT_INVALID : (((uint32_t)cl << 12) | (uint32_t)sym);
-  return ((uint32_t)cl << 12) | (uint32_t)sym;     // code-length code
-}
-
-// Warp-cooperative canonical-Huffman table build (RFC 1951 §3.2.2): lane L owns code length L.
-// Returns 0 ok, 1 = empty code (LUT all-invalid), -1 = over-subscribed / incomplete set.
-template <int PB>
-__device__ __noinline__ int build_table(const uint8_t* lens, int n, uint16_t* lut, uint16_t* sorted, Code* code, int kind,
-                                        int lane) {
-  const bool owner = lane >= 1 && lane <= 15;
-  int mycnt = 0;
-  if (owner)
-    for (int i = 0; i < n; ++i) mycnt += (lens[i] == lane);
-  // Kraft sum in units of 2^-15: > 2^15 over-subscribed, < 2^15 incomplete
-  int v = owner ? (mycnt << (15 - lane)) : 0;
-#pragma unroll
-  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-  const uint32_t have = __ballot_sync(0xffffffffu, mycnt > 0);
-  const int maxlen = have ? 31 - __clz(have) : 0;
-  if (v > (1 << 15)) return -1;
-  for (int i = lane; i < (1 << PB); i += 32) lut[i] = (uint16_t)ENT_INVALID;
-  // first canonical code and symbol index of every length (serial recurrence over 15 lengths, warp-uniform)
-  int myfirst = 0, myindex = 0;
-  {
-    int c = 0, idx = 0;
-    for (int L = 1; L <= 15; ++L) {
-      int prev = __shfl_sync(0xffffffffu, mycnt, L - 1);   // lane 0 holds 0
-      c = (c + prev) << 1;
-      idx += prev;
-      if (lane == L) { myfirst = c; myindex = idx; }
-    }
-  }
-  if (lane < 16) {
-    code->cnt[lane] = (uint16_t)mycnt;
-    code->first[lane] = (uint16_t)myfirst;
-    code->index[lane] = (uint16_t)myindex;
-  }
-  __syncwarp();
-  if (maxlen == 0) return 1;
-  if (v < (1 << 15) && (kind == KIND_CODELEN || maxlen != 1)) return -1;
-  if (owner && mycnt) {
-    int c = myfirst, slot = myindex;
-    const int l = lane;
-    for (int sym = 0; sym < n; ++sym) {
-      if (lens[sym] != l) continue;
-      sorted[slot++] = (uint16_t)sym;
-      const uint32_t rev = __brev((uint32_t)c) >> (32 - l);
-      ++c;
-      if (l <= PB) {
-        const uint16_t e = (uint16_t)make_entry(kind, sym, l);
-        for (uint32_t i = rev; i < (1u << PB); i += (1u << l)) lut[i] = e;
-      } else {
-        lut[rev & ((1u << PB) - 1)] = (uint16_t)ENT_SLOW;
-      }
-    }
-  }
-  __syncwarp();
-  return 0;
-}
-
-// Canonical decode of a code longer than PB bits, starting from the PB-bit prefix already known not to be a
-// complete code (RFC 1951 §3.2.2 code assignment run backwards).
-template <int PB>
-__device__ __noinline__ uint32_t slow_decode(uint32_t bits, const Code* code, const uint16_t* sorted, int kind) {
-  uint32_t c = __brev(bits) >> (32 - PB);     // first PB bits of the code, most significant first
-  bits >>= PB;
-  for (int len = PB + 1; len <= 15; ++len) {
-    c = (c << 1) | (bits & 1);
-    bits >>= 1;
-    const uint32_t rel = c - code->first[len];
-    if (rel < code->cnt[len]) return make_entry(kind, sorted[code->index[len] + rel], len);
-  }
-  return ENT_INVALID;
-}
-
 }  // namespace
 
-__global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
+// retry_only != 0: redo only the blocks that inflate_par_kernel gave up on (status == STATUS_RETRY)
+__global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a, int retry_only) {
   __shared__ WarpSmem sm;
   WarpSmem* s = &sm;
   const int lane = threadIdx.x;
   const uint32_t blk = blockIdx.x;
   if (blk >= a.n_blocks) return;
+  if (retry_only && a.status[blk] != STATUS_RETRY) return;
 
   const uint64_t poff = a.payload_off[blk];
   const uint32_t csize = a.cdata_size[blk];
@@ -302,19 +133,9 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
   uint32_t flushed = 0;     // bytes already stored to HBM
   // deferred far match: bytes already requested from L2, to be stored into the ring later
   uint32_t pend_len = 0, pend_o = 0, pv0 = 0, pv1 = 0;
-  // fused record-chain walk (records.cu): next record start inside this block, records / cigar words found so far
-  const bool walking = a.walk.rel != nullptr;
-  const uint32_t sb = blk + a.walk.sb_offset;
-  const uint32_t win0 = (walking && blk == 0) ? a.walk.in0 : 0;
-  uint32_t wnext = win0, wcnt = 0, wncig = 0;
-  int wbad = WALK_OK;
-  // Entry point of the chain into this block.  Block 0 of a slice enters at a known offset.  Every other block
-  // first tries offset 0 (files written by BioD / htslib start every block at a record) and otherwise searches
-  // for the first offset where a plausible record starts (htsjdk-style files cut records anywhere).  The guess is
-  // only a speculation: scan_resolve_kernel checks it against the previous block's chain end and repairs it.
-  bool wentry = !walking || (blk == 0 && a.walk.sb_offset == 0);
-  uint32_t wsearch = 0;        // candidates below this offset are ruled out
-  uint64_t win_abs = ~0ull;    // reported entry (absolute); stays "unknown" when no record starts in the block
+  Walker<OUT_RING> wk;
+  wk.init(a.walk, ring, oa, isize, obase, blk);
+  const bool walking = wk.walking;
 #define OPOS() (o - oa)
 
   // pull one 32-bit word from the staging ring (warp-uniform)
@@ -347,88 +168,6 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
       __syncwarp();
     }
   };
-  // little-endian u32 at block-relative offset x, read from the output ring
-  auto ring32 = [&](uint32_t x) -> uint32_t {
-    const uint32_t r0 = oa + x;
-    return lds8(ring + (r0 & OMASK)) | (lds8(ring + ((r0 + 1) & OMASK)) << 8) | (lds8(ring + ((r0 + 2) & OMASK)) << 16) |
-           (lds8(ring + ((r0 + 3) & OMASK)) << 24);
-  };
-  // is a BAM record header plausible at block-relative offset c?  1 yes, 0 no, -1 not enough bytes produced yet
-  auto plausible = [&](uint32_t c, uint32_t avail) -> int {
-    if (c + 36 > avail) return -1;
-    const int32_t bs = (int32_t)ring32(c);
-    if (bs < 34 || bs > (1 << 27)) return 0;
-    const int32_t ref = (int32_t)ring32(c + 4), pos = (int32_t)ring32(c + 8);
-    if (ref < -1 || ref >= a.walk.n_refs || pos < -1) return 0;
-    const uint32_t bin_mq_nl = ring32(c + 12), flag_nc = ring32(c + 16);
-    const int32_t l_seq = (int32_t)ring32(c + 20), nref = (int32_t)ring32(c + 24), npos = (int32_t)ring32(c + 28);
-    const uint32_t lname = bin_mq_nl & 0xFF, nc = flag_nc & 0xFFFF;
-    if (lname == 0 || l_seq < 0 || nref < -1 || nref >= a.walk.n_refs || npos < -1) return 0;
-    const uint64_t need = 32ull + lname + 4ull * nc + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
-    if (need > (uint64_t)bs) return 0;
-    // read name: printable characters closed by a NUL (read.d:984-990)
-    const uint32_t nm = c + 36;
-    if (nm + lname > avail) return -1;
-    if (lds8(ring + ((oa + nm + lname - 1) & OMASK)) != 0) return 0;
-    for (uint32_t k = 0; k + 1 < lname && k < 8; ++k) {
-      const uint32_t ch = lds8(ring + ((oa + nm + k) & OMASK));
-      if (ch < 0x21 || ch > 0x7e) return 0;
-    }
-    return 1;
-  };
-  // find the chain entry: lanes test 32 candidate offsets at a time
-  auto find_entry = [&](uint32_t avail, bool final) {
-    while (!wentry) {
-      const uint32_t c = wsearch + lane;
-      int ok = (c < isize) ? plausible(c, avail) : 0;
-      if (ok == 1) {
-        // a lone plausible header is not enough: the record it announces must be followed by another plausible one
-        // (only when that one is close enough for the candidate itself to stay in the output ring meanwhile)
-        const uint32_t nx = c + 4 + ring32(c);
-        if (nx + 36 <= avail) ok = plausible(nx, avail) == 0 ? 0 : 1;
-        else if (nx + 36 <= isize && nx - c <= 1024 && !final) ok = -1;
-      }
-      const uint32_t yes = __ballot_sync(0xffffffffu, ok == 1), wait = __ballot_sync(0xffffffffu, ok == -1);
-      const uint32_t first_yes = yes ? (uint32_t)__ffs(yes) - 1 : 32, first_wait = wait ? (uint32_t)__ffs(wait) - 1 : 32;
-      if (first_yes < first_wait) {
-        wnext = wsearch + first_yes;
-        win_abs = obase + wnext;
-        wentry = true;
-      } else if (first_wait < 32) {
-        if (!final) { wsearch += first_wait; return; }      // come back when more bytes are there
-        wsearch += first_wait + 1;                          // end of block: what cannot be checked is not an entry
-      } else {
-        wsearch += 32;
-      }
-      if (!wentry && wsearch >= isize) { wnext = isize; wentry = true; }   // no record starts in this block
-    }
-  };
-  // follow the block_size chain (readrange.d:118-173) over the records whose 24 leading bytes are already produced
-  auto walk_upto = [&](uint32_t avail, bool final) {
-    if (!wentry) {
-      find_entry(avail, final);
-      if (!wentry) return;
-    }
-    while (wbad == WALK_OK && wnext < isize) {
-      if (wnext + 24 > avail) {
-        if (final) wbad = WALK_INCOMPLETE;     // the header straddles the block end: the resolve kernel finishes it
-        break;
-      }
-      const int32_t bs = (int32_t)ring32(wnext);
-      if (bs < 32) { wbad = WALK_BAD_SIZE; break; }
-      if (obase + wnext + 4 + (uint64_t)bs > a.walk.u_len) { wbad = WALK_TAIL; break; }
-      const uint32_t bin_mq_nl = ring32(wnext + 12), flag_nc = ring32(wnext + 16);
-      const int32_t l_seq = (int32_t)ring32(wnext + 20);
-      const uint32_t lname = bin_mq_nl & 0xFF, nc = flag_nc & 0xFFFF;
-      const uint64_t need = 32ull + lname + 4ull * nc + (l_seq > 0 ? ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq : 0);
-      if (l_seq < 0 || need > (uint64_t)bs) { wbad = WALK_BAD_FIELDS; break; }
-      // relative to the chain entry of the block, as scan_extract_kernel expects (block_uoff[0] includes in0)
-      if (lane == 0 && wcnt < (uint32_t)SCAN_SLOTS) a.walk.rel[(size_t)sb * SCAN_SLOTS + wcnt] = (uint16_t)(wnext - win0);
-      ++wcnt;
-      wncig += nc;
-      wnext += 4 + (uint32_t)bs;
-    }
-  };
   auto flush_to = [&](uint32_t fe) {
     // copy ring bytes [flushed, fe) to HBM; 16-byte vector stores where the global address allows
     uint32_t f = flushed;
@@ -455,7 +194,7 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
       if (OPOS() > isize) { status = Z_BUF; return; }
       complete_pending();
       __syncwarp();
-      if (walking) walk_upto(OPOS(), false);
+      if (walking) wk.walk_upto(OPOS(), false, lane);
       const uint32_t fe = OPOS() - (o & (FLUSH - 1));
       if (fe > flushed) flush_to(fe);
     }
@@ -720,18 +459,12 @@ __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a) {
   if (status == 0) {
     complete_pending();
     __syncwarp();
-    if (walking) walk_upto(isize, true);
+    if (walking) wk.walk_upto(isize, true, lane);
     if (OPOS() > flushed) flush_to(OPOS());
   }
   if (lane == 0) {
     a.status[blk] = status;
-    if (walking) {
-      a.walk.cnt[sb] = wcnt;
-      a.walk.ncig[sb] = wncig;
-      a.walk.in[sb] = (blk == 0 && a.walk.sb_offset == 0) ? obase + a.walk.in0 : win_abs;
-      a.walk.out[sb] = obase + wnext;
-      a.walk.bad[sb] = status ? WALK_TAIL : wbad;
-    }
+    wk.store(status);
   }
 #undef REFILL
 #undef DROP
@@ -743,9 +476,26 @@ unsigned long long g_kernel_launches = 0;
 
 size_t inflate_smem_bytes() { return sizeof(WarpSmem); }
 
+// BIODB_INFLATE=serial selects the warp-serial kernel alone (A/B measurements)
+static bool inflate_use_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BIODB_INFLATE");
+    v = (e && e[0] == 's') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st) {
   if (a.n_blocks == 0) return cudaSuccess;
-  inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a);
+  if (!inflate_use_legacy()) {
+    cudaError_t e = launch_inflate_par(a, st);     // lane-parallel kernel; marks the blocks it gives up on
+    if (e != cudaSuccess) return e;
+    inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 1);
+    g_kernel_launches += 2;
+    return cudaGetLastError();
+  }
+  inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 0);
   ++g_kernel_launches;
   return cudaGetLastError();
 }

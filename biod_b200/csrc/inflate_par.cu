@@ -1,0 +1,557 @@
+// BGZF block inflater for sm_100a, lane-parallel: one warp per BGZF block, 32 lanes decode 32 different
+// sub-sequences of the block's DEFLATE bit stream at the same time.
+//
+// Replaces decompressBgzfBlock (bio/core/bgzf/block.d:127-216), i.e. libz's inflateInit2(-15) / inflate(Z_FINISH) /
+// inflateEnd on one <=64 KiB raw-DEFLATE payload.  The algorithm is RFC 1951; nothing here is derived from zlib.
+//
+// Huffman decoding is serial by nature: the start of a code is known only when the one before it has been decoded.
+// inflate.cu therefore lets all 32 lanes of a warp decode the same symbols redundantly (18 warp instructions per
+// output byte).  Here the bit stream of a DEFLATE block is cut into "super-chunks" of 32 sub-sequences of SUB_BITS bits:
+//   1. lane L decodes sub-sequence L from its nominal first bit, which is almost never the start of a code — but
+//      Huffman codes self-synchronise, so after a few codes the lane is usually on the true code chain and the bit
+//      where it crosses into sub-sequence L+1 is the true start of that sub-sequence;
+//   2. every lane whose start differs from its predecessor's end decodes again from there; this repeats until the chain
+//      is consistent from lane 0 (whose start is always known) up to the last lane or the end-of-block code — two
+//      rounds for most super-chunks of BAM data (tools/deflate_sim.py reproduces the statistics);
+//   3. a warp scan of the per-lane output sizes gives every lane its output offset; the lanes decode once more,
+//      storing literals straight into the shared-memory output ring and appending (position, length, distance) of
+//      their LZ77 matches to a list;
+//   4. the matches are copied in stream order by the whole warp (sources in the ring, or — when older than the ring —
+//      in the block's already flushed bytes in L2), the record-chain walker (records.cu) looks at the new bytes, and
+//      the ring is flushed to HBM with 16-byte-per-lane vector stores.
+// The compressed payload is staged through a shared-memory ring by TMA bulk copies (cp.async.bulk + mbarrier), as in
+// inflate.cu.  Tables are built per DEFLATE block by the warp (inflate_common.cuh).
+//
+// Anything unusual — an invalid code, a distance too far back, a stream that does not end exactly at ISIZE, input
+// that runs out — makes the warp give the block up with STATUS_RETRY; launch_inflate() then runs the warp-serial
+// kernel on those blocks, which reproduces zlib's exact return code (Z_DATA_ERROR / Z_BUF_ERROR).  A block this kernel
+// accepts has been decoded completely and consistently: every code valid, every distance inside the block, the final
+// block's end-of-block code reached within the payload, exactly ISIZE bytes produced.
+#include "inflate_common.cuh"
+
+namespace biodb {
+
+namespace {
+
+#ifndef BIODB_PAR_SUB_BITS
+#define BIODB_PAR_SUB_BITS 256
+#endif
+#ifndef BIODB_PAR_OUT_RING
+#define BIODB_PAR_OUT_RING 8192
+#endif
+#ifndef BIODB_PAR_MLIST
+#define BIODB_PAR_MLIST 256
+#endif
+constexpr int SUB_BITS = BIODB_PAR_SUB_BITS;   // bits of one lane's sub-sequence
+constexpr int CH = SUB_BITS * 4;               // bytes per TMA chunk == compressed bytes of one nominal super-chunk
+constexpr int NCH = 4;                         // chunks in the staging ring
+constexpr int PIN_RING = NCH * CH;
+constexpr int PIN_WORDS = PIN_RING / 4;
+constexpr int POUT = BIODB_PAR_OUT_RING;
+constexpr uint32_t POM = POUT - 1;
+// Output bytes one super-chunk may produce.  The ring must keep, besides them, the unflushed tail (< FLUSH_ALIGN), the
+// longest match (258) for the "older than the ring => already flushed" rule, and ~1.1 KB of history for the walker.
+constexpr int OUT_BUDGET = POUT - 2048;
+constexpr int LANE_CAP = 1024;                 // a lane stops taking codes once it has produced this many bytes ...
+constexpr int MLIST = BIODB_PAR_MLIST;         // matches one super-chunk may hold
+constexpr int LANE_MCAP = 32;                  // ... or this many matches (the next lane continues from there)
+constexpr int FLUSH_ALIGN = 128;
+constexpr int STORE_PIECE = 1024;              // stored blocks are copied in pieces of this many bytes
+constexpr int HDR_BYTES = 640;                 // >= longest dynamic block header: 17 + 19*3 + 316*(7+7) bits = 563 bytes
+static_assert(LANE_CAP + 257 <= OUT_BUDGET, "one lane must always fit");
+static_assert(LANE_MCAP <= MLIST, "one lane must always fit");
+static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= STORE_PIECE + 16 && (NCH - 1) * CH >= CH + 32,
+              "staging ring too small");
+static_assert(STORE_PIECE <= OUT_BUDGET, "");
+
+// lane stop reasons
+constexpr uint32_t F_EOB = 1, F_ERR = 2, F_INEND = 3;
+
+struct __align__(16) ParSmem {
+  uint32_t in_ring[PIN_WORDS];
+  uint8_t out_ring[POUT];
+  uint16_t lut_lit[1 << LIT_BITS];
+  uint16_t lut_dist[1 << DIST_BITS];   // also hosts the 128-entry code-length LUT
+  uint16_t sorted_lit[288];
+  uint16_t sorted_dist[32];
+  Code code_lit, code_dist;
+  uint8_t lens[352];                   // [0,19) code-length code, [32,32+316) litlen+dist lengths
+  uint32_t m_ld[MLIST];                // matches of the super-chunk: (length-3) | (distance-1) << 8
+  uint16_t m_pos[MLIST];               //   and their block-relative output offset
+  uint32_t disttab[32];                // distance symbol -> base | extra bits << 16
+  uint16_t lentab[32];                 // length symbol -> base | extra bits << 9
+  unsigned long long mbar[NCH];
+};
+
+struct ParCtx {           // shared-space addresses and limits every lane needs while decoding
+  uint32_t in_ring, ring, lutl, lutd, lentab, disttab, mld, mpos;
+  uint32_t total_bits;
+  const Code* code_lit;
+  const Code* code_dist;
+  const uint16_t* sorted_lit;
+  const uint16_t* sorted_dist;
+};
+
+// 32 bits of the staged stream starting at bit `pos`
+__device__ __forceinline__ uint32_t fetch32(uint32_t in_ring, uint32_t pos) {
+  const uint32_t wi = pos >> 5;
+  const uint32_t lo = lds32(in_ring + ((wi & (PIN_WORDS - 1)) << 2));
+  const uint32_t hi = lds32(in_ring + (((wi + 1) & (PIN_WORDS - 1)) << 2));
+  return __funnelshift_r(lo, hi, pos);
+}
+
+// One lane decodes the codes that start in [t, limit).  WRITE: literals go to the output ring at ring index
+// oring + (bytes produced so far), matches to the list from slot mslot on (output offset opos + bytes produced).
+template <bool WRITE>
+__device__ __forceinline__ void lane_decode(const ParCtx& c, uint32_t t, uint32_t limit, uint32_t oring, uint32_t opos,
+                                            uint32_t mslot, uint32_t& end, uint32_t& out, uint32_t& nm, uint32_t& flag) {
+  uint32_t pos = t, o = 0, m = 0, fl = 0;
+  bool done = false;
+  while (true) {
+    uint32_t e = 0, bits = 0;
+    // literal run: lanes that meet something else wait at the end of this loop, so that the (longer) match path below
+    // runs once for all of them
+    while (true) {
+      if (pos >= limit || o >= (uint32_t)LANE_CAP || m >= (uint32_t)LANE_MCAP) { done = true; break; }
+      if (pos >= c.total_bits) { fl = F_INEND; done = true; break; }
+      bits = fetch32(c.in_ring, pos);
+      e = lds16(c.lutl + ((bits & ((1u << LIT_BITS) - 1)) << 1));
+      if (e & (3u << 8)) break;
+      if (WRITE) sts8(c.ring + ((oring + o) & POM), e);
+      ++o;
+      pos += e >> 12;
+    }
+    if (done) break;
+    if (((e >> 8) & 3) == K_SPECIAL) {
+      if (e == ENT_SLOW) e = slow_decode<LIT_BITS>(bits, c.code_lit, c.sorted_lit, KIND_LITLEN);
+      if (((e >> 8) & 3) == K_SPECIAL) { fl = F_ERR; break; }
+      if (((e >> 8) & 3) == K_LIT) {          // a literal with a long code
+        if (WRITE) sts8(c.ring + ((oring + o) & POM), e);
+        ++o;
+        pos += e >> 12;
+        continue;
+      }
+    }
+    const uint32_t cl = e >> 12;
+    if (((e >> 8) & 3) == K_EOB) { pos += cl; fl = F_EOB; break; }
+    // length / distance pair
+    const uint32_t lb = lds16(c.lentab + ((e & 31) << 1));
+    const uint32_t eb = lb >> 9;
+    const uint32_t len = (lb & 511) + ((bits >> cl) & ((1u << eb) - 1));      // cl + eb <= 20 bits of the 32
+    pos += cl + eb;
+    bits = fetch32(c.in_ring, pos);
+    uint32_t e2 = lds16(c.lutd + ((bits & ((1u << DIST_BITS) - 1)) << 1));
+    if (((e2 >> 8) & 3) == K_SPECIAL) {
+      if (e2 == ENT_SLOW) e2 = slow_decode<DIST_BITS>(bits, c.code_dist, c.sorted_dist, KIND_DIST);
+      if (((e2 >> 8) & 3) == K_SPECIAL) { fl = F_ERR; break; }
+    }
+    const uint32_t cl2 = e2 >> 12;
+    const uint32_t db = lds32(c.disttab + ((e2 & 31) << 2));
+    const uint32_t eb2 = db >> 16;
+    const uint32_t dist = (db & 0xffff) + ((bits >> cl2) & ((1u << eb2) - 1));   // cl2 + eb2 <= 28 bits of the 32
+    pos += cl2 + eb2;
+    if (WRITE) {
+      sts32(c.mld + ((mslot + m) << 2), (len - 3) | ((dist - 1) << 8));
+      sts16(c.mpos + ((mslot + m) << 1), opos + o);
+    }
+    o += len;
+    ++m;
+  }
+  end = pos;
+  out = o;
+  nm = m;
+  flag = fl;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += n;
+  }
+  return v;
+}
+
+}  // namespace
+
+// diagnostics (biodb_debug_inflate_counters): blocks given up, super-chunks, decode rounds, matches read back from L2,
+// matches, DEFLATE blocks
+__device__ unsigned long long g_par_counters[8];
+
+__global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
+  __shared__ ParSmem sm;
+  ParSmem* s = &sm;
+  const int lane = threadIdx.x;
+  const uint32_t blk = blockIdx.x;
+  if (blk >= a.n_blocks) return;
+
+  const uint64_t poff = a.payload_off[blk];
+  const uint32_t csize = a.cdata_size[blk];
+  const uint32_t isize = a.isize[blk];
+  const uint64_t obase = a.out_off[blk];
+  uint8_t* gout = a.out + obase;
+  const uint32_t oa = (uint32_t)(((uintptr_t)gout) & POM);   // ring index of output byte 0
+
+  const uint32_t sbase = smem_u32(s);
+  const uint32_t in_ring = sbase + (uint32_t)offsetof(ParSmem, in_ring);
+  const uint32_t ring = sbase + (uint32_t)offsetof(ParSmem, out_ring);
+  const uint32_t lutd = sbase + (uint32_t)offsetof(ParSmem, lut_dist);
+  const uint32_t mbar = sbase + (uint32_t)offsetof(ParSmem, mbar);
+  ParCtx ctx;
+  ctx.in_ring = in_ring;
+  ctx.ring = ring;
+  ctx.lutl = sbase + (uint32_t)offsetof(ParSmem, lut_lit);
+  ctx.lutd = lutd;
+  ctx.lentab = sbase + (uint32_t)offsetof(ParSmem, lentab);
+  ctx.disttab = sbase + (uint32_t)offsetof(ParSmem, disttab);
+  ctx.mld = sbase + (uint32_t)offsetof(ParSmem, m_ld);
+  ctx.mpos = sbase + (uint32_t)offsetof(ParSmem, m_pos);
+  ctx.code_lit = &s->code_lit;
+  ctx.code_dist = &s->code_dist;
+  ctx.sorted_lit = s->sorted_lit;
+  ctx.sorted_dist = s->sorted_dist;
+
+  if (lane < NCH) mbar_init(mbar + 8 * lane, 1);
+  if (lane == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
+    uint32_t b, eb;
+    if (lane < 29) { len_base((uint32_t)lane, b, eb); s->lentab[lane] = (uint16_t)(b | (eb << 9)); }
+    if (lane < 30) { dist_base((uint32_t)lane, b, eb); s->disttab[lane] = b | (eb << 16); }
+  }
+  __syncwarp();
+
+  // ---- staging of the compressed payload (TMA) -------------------------------------------------------------
+  const uint8_t* pay = a.comp + poff;
+  const uint32_t skip = (uint32_t)(((uintptr_t)pay) & 15);
+  const uint8_t* src = pay - skip;                         // 16-byte aligned start of the staged stream
+  const uint32_t staged = skip + csize;                    // bytes from src that matter
+  uint32_t n_chunks = (staged + CH - 1) / CH;
+  if (n_chunks == 0) n_chunks = 1;
+  uint32_t last_bytes = (staged - (n_chunks - 1) * CH + 15) & ~15u;
+  if (last_bytes == 0) last_bytes = 16;
+  uint32_t issued = 0, waited = 0;
+  auto issue = [&](uint32_t k) {
+    __syncwarp();        // every lane has finished reading the slot being overwritten (calls are warp-uniform)
+    if (lane == 0) {
+      const uint32_t bytes = (k + 1 == n_chunks) ? last_bytes : (uint32_t)CH;
+      const uint32_t bar = mbar + 8 * (k % NCH);
+      mbar_expect_tx(bar, bytes);
+      tma_load(in_ring + (k % NCH) * CH, src + (size_t)k * CH, bytes, bar);
+    }
+    issued = k + 1;
+  };
+  auto wait_chunk = [&](uint32_t k) {
+    mbar_wait(mbar + 8 * (k % NCH), (k / NCH) & 1);
+    waited = k + 1;
+  };
+  // make staged bytes [lo, hi) readable; bytes before lo are not needed any more (the decoder only moves forward)
+  auto ensure_input = [&](uint32_t lo, uint32_t hi) {
+    const uint32_t c0 = lo / CH;
+    uint32_t c1 = (hi - 1) / CH;
+    if (c1 >= n_chunks) c1 = n_chunks - 1;
+    while (issued < n_chunks && issued < c0 + NCH) issue(issued);
+    while (waited <= c1 && waited < issued) wait_chunk(waited);
+  };
+
+  // all bit positions are relative to src
+  uint32_t pos = skip * 8;
+  const uint32_t total_bits = staged * 8;
+  ctx.total_bits = total_bits;
+  int status = 0;
+  uint32_t n_super = 0, n_rounds = 0, n_far = 0, n_matches = 0, n_dblocks = 0;
+  uint32_t o = oa;          // oa + bytes produced: ring index is (o & POM)
+  uint32_t flushed = 0;     // bytes already stored to HBM
+#define OPOS() (o - oa)
+  Walker<POUT> wk;
+  wk.init(a.walk, ring, oa, isize, obase, blk);
+
+  auto flush_to = [&](uint32_t fe) {
+    // copy ring bytes [flushed, fe) to HBM; 16-byte vector stores where the global address allows
+    uint32_t f = flushed;
+    uint32_t head = (16 - ((oa + f) & 15)) & 15;
+    if (head > fe - f) head = fe - f;
+    if (head) {
+      if ((uint32_t)lane < head) gout[f + lane] = (uint8_t)lds8(ring + ((oa + f + lane) & POM));
+      f += head;
+    }
+    const uint32_t n16 = (fe - f) >> 4;
+    for (uint32_t i = lane; i < n16; i += 32) {
+      uint4 v = lds128(ring + ((oa + f + 16 * i) & POM));
+      __stcs(reinterpret_cast<uint4*>(gout + f + 16 * i), v);
+    }
+    f += n16 << 4;
+    const uint32_t tail = fe - f;
+    if ((uint32_t)lane < tail) gout[f + lane] = (uint8_t)lds8(ring + ((oa + f + lane) & POM));
+    flushed = fe;
+    __syncwarp();
+  };
+  // after new bytes are complete in the ring: let the record walker see them, flush whole 128-byte lines
+  auto produced = [&]() {
+    wk.walk_upto(OPOS(), false, lane);
+    const uint32_t fe = OPOS() - (o & (FLUSH_ALIGN - 1));
+    if (fe > flushed && fe <= OPOS()) flush_to(fe);
+  };
+
+  bool last = false;
+  while (!last && status == 0) {
+    // ---- block header (warp-uniform, from a 64-bit register bit buffer) ----------------------------------
+    ensure_input(pos >> 3, (pos >> 3) + HDR_BYTES);
+    ++n_dblocks;
+    uint64_t bb;
+    int bc;
+    uint32_t hw = pos >> 5;
+    {
+      const uint32_t lo = lds32(in_ring + ((hw & (PIN_WORDS - 1)) << 2));
+      const uint32_t hi = lds32(in_ring + (((hw + 1) & (PIN_WORDS - 1)) << 2));
+      bb = (((uint64_t)hi << 32) | lo) >> (pos & 31);
+      bc = 64 - (int)(pos & 31);
+      hw += 2;
+    }
+#define HFILL() do { if (bc <= 32) { bb |= (uint64_t)lds32(in_ring + ((hw & (PIN_WORDS - 1)) << 2)) << bc; bc += 32; ++hw; } } while (0)
+#define HDROP(n) do { bb >>= (n); bc -= (n); } while (0)
+#define HPOS() (hw * 32 - (uint32_t)bc)
+    last = bb & 1;
+    const int btype = (int)((bb >> 1) & 3);
+    HDROP(3);
+    if (btype == 3) { status = STATUS_RETRY; break; }
+
+    if (btype == 0) {
+      // ---- stored block -------------------------------------------------------------
+      pos = (HPOS() + 7) & ~7u;
+      ensure_input(pos >> 3, (pos >> 3) + 4);
+      const uint32_t lw = fetch32(in_ring, pos);
+      const uint32_t len = lw & 0xffff, nlen = lw >> 16;
+      pos += 32;
+      if (pos > total_bits || (len ^ 0xffff) != nlen || pos + len * 8 > total_bits || OPOS() + len > isize) {
+        status = STATUS_RETRY;
+        break;
+      }
+      uint32_t left = len;
+      while (left) {
+        const uint32_t piece = left < (uint32_t)STORE_PIECE ? left : (uint32_t)STORE_PIECE;
+        const uint32_t b0 = pos >> 3;
+        ensure_input(b0, b0 + piece);
+        for (uint32_t i = lane; i < piece; i += 32)
+          sts8(ring + ((o + i) & POM), lds8(in_ring + ((b0 + i) & (PIN_RING - 1))));
+        __syncwarp();
+        o += piece;
+        pos += piece * 8;
+        left -= piece;
+        produced();
+      }
+      continue;
+    }
+
+    if (btype == 1) {
+      // ---- fixed Huffman code (RFC 1951 §3.2.6) ---------------------------------------
+      pos = HPOS();
+      for (int i = lane; i < 288; i += 32) s->lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
+      __syncwarp();
+      build_table<LIT_BITS>(s->lens, 288, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane);
+      __syncwarp();
+      s->lens[lane] = 5;
+      __syncwarp();
+      build_table<DIST_BITS>(s->lens, 32, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane);
+    } else {
+      // ---- dynamic Huffman code (RFC 1951 §3.2.7) --------------------------------------
+      HFILL();
+      const int hlit = (int)(bb & 31) + 257;
+      const int hdist = (int)((bb >> 5) & 31) + 1;
+      const int hclen = (int)((bb >> 10) & 15) + 4;
+      HDROP(14);
+      if (hlit > 286 || hdist > 30) { status = STATUS_RETRY; break; }
+      if (lane < 19) s->lens[lane] = 0;
+      __syncwarp();
+      for (int i = 0; i < hclen; ++i) {
+        HFILL();
+        // order of code-length code lengths, RFC 1951 §3.2.7, packed 5 bits each
+        const uint64_t ord_lo = 16ull | 17ull << 5 | 18ull << 10 | 0ull << 15 | 8ull << 20 | 7ull << 25 | 9ull << 30 |
+                                6ull << 35 | 10ull << 40 | 5ull << 45 | 11ull << 50 | 4ull << 55;
+        const uint64_t ord_hi = 12ull | 3ull << 5 | 13ull << 10 | 2ull << 15 | 14ull << 20 | 1ull << 25 | 15ull << 30;
+        const int sym = i < 12 ? (int)((ord_lo >> (5 * i)) & 31) : (int)((ord_hi >> (5 * (i - 12))) & 31);
+        s->lens[sym] = (uint8_t)(bb & 7);
+        HDROP(3);
+      }
+      __syncwarp();
+      int r = build_table<CL_BITS>(s->lens, 19, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_CODELEN, lane);
+      if (r != 0) { status = STATUS_RETRY; break; }
+      const int total = hlit + hdist;
+      __syncwarp();
+      int idx = 0;
+      int prev = 0;
+      while (idx < total) {
+        HFILL();
+        const uint32_t e = lds16(lutd + (((uint32_t)bb & ((1u << CL_BITS) - 1)) << 1));
+        const int cl = e >> 12;
+        if (cl == 0 || ((e >> 8) & 3) == K_SPECIAL) { status = STATUS_RETRY; break; }
+        const int sym = e & 31;
+        HDROP(cl);
+        if (sym < 16) {
+          if (lane == 0) s->lens[32 + idx] = (uint8_t)sym;
+          prev = sym;
+          ++idx;
+        } else {
+          int rep, val;
+          if (sym == 16) {
+            if (idx == 0) { status = STATUS_RETRY; break; }
+            rep = 3 + (int)(bb & 3);
+            HDROP(2);
+            val = prev;
+          } else if (sym == 17) {
+            rep = 3 + (int)(bb & 7);
+            HDROP(3);
+            val = 0;
+          } else {
+            rep = 11 + (int)(bb & 127);
+            HDROP(7);
+            val = 0;
+          }
+          if (idx + rep > total) { status = STATUS_RETRY; break; }
+          for (int k = lane; k < rep; k += 32) s->lens[32 + idx + k] = (uint8_t)val;
+          prev = val;
+          idx += rep;
+        }
+      }
+      if (status) break;
+      pos = HPOS();
+      if (pos > total_bits) { status = STATUS_RETRY; break; }
+      __syncwarp();
+      if (s->lens[32 + 256] == 0) { status = STATUS_RETRY; break; }   // no end-of-block code
+      __syncwarp();
+      r = build_table<LIT_BITS>(s->lens + 32, hlit, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane);
+      if (r < 0) { status = STATUS_RETRY; break; }
+      r = build_table<DIST_BITS>(s->lens + 32 + hlit, hdist, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane);
+      if (r < 0) { status = STATUS_RETRY; break; }
+    }
+    __syncwarp();
+#undef HFILL
+#undef HDROP
+#undef HPOS
+
+    // ---- the codes of the block, one super-chunk of 32 sub-sequences at a time -------------------------------
+    bool eob = false;
+    while (!eob) {
+      const uint32_t base = pos;
+      ensure_input(base >> 3, (base >> 3) + CH + 24);
+      const uint32_t lim = base + (uint32_t)(lane + 1) * SUB_BITS;
+      uint32_t t = base + (uint32_t)lane * SUB_BITS;
+      uint32_t e_, out_, nm_, fl_;
+      lane_decode<false>(ctx, t, lim, 0, 0, 0, e_, out_, nm_, fl_);
+      ++n_super;
+      ++n_rounds;
+      // repair the chain: lane L must start where lane L-1 ended
+      uint32_t kstop = 32;      // first lane of the consistent prefix that stopped (end of block / fault), or 32
+      while (true) {
+        uint32_t tn = __shfl_up_sync(0xffffffffu, e_, 1);
+        if (lane == 0) tn = base;
+        const bool need = tn != t;
+        const uint32_t needm = __ballot_sync(0xffffffffu, need);
+        const uint32_t stopm = __ballot_sync(0xffffffffu, fl_ != 0);
+        const uint32_t vp = needm ? (uint32_t)__ffs(needm) - 1 : 32;      // lanes [0, vp) form a consistent chain
+        const uint32_t vstop = stopm & (vp >= 32 ? 0xffffffffu : ((1u << vp) - 1));
+        if (vstop) { kstop = (uint32_t)__ffs(vstop) - 1; break; }
+        if (!needm) break;
+        if (need) {
+          t = tn;
+          lane_decode<false>(ctx, t, lim, 0, 0, 0, e_, out_, nm_, fl_);
+        }
+        ++n_rounds;
+        __syncwarp();
+      }
+      // commit the longest prefix of lanes that fits the output ring and the match list
+      const uint32_t ncand = kstop < 32 ? kstop + 1 : 32;
+      const uint32_t inc_out = warp_incl_scan(out_, lane);
+      const uint32_t inc_nm = warp_incl_scan(nm_, lane);
+      const bool fits = (uint32_t)lane < ncand && inc_out <= (uint32_t)OUT_BUDGET && inc_nm <= (uint32_t)MLIST;
+      const uint32_t k = (uint32_t)__popc(__ballot_sync(0xffffffffu, fits));   // >= 1: lane 0 always fits
+      const uint32_t kl = k - 1;
+      const uint32_t chunk_out = __shfl_sync(0xffffffffu, inc_out, kl);
+      const uint32_t n_match = __shfl_sync(0xffffffffu, inc_nm, kl);
+      const uint32_t newpos = __shfl_sync(0xffffffffu, e_, kl);
+      const uint32_t stop_flag = (kl == kstop) ? __shfl_sync(0xffffffffu, fl_, kl) : 0;
+      const uint32_t opos0 = OPOS();
+      if (stop_flag == F_ERR || stop_flag == F_INEND || opos0 + chunk_out > isize) { status = STATUS_RETRY; break; }
+      // write pass: literals into the ring, matches into the list
+      if ((uint32_t)lane < k) {
+        uint32_t e2_, o2_, m2_, f2_;
+        lane_decode<true>(ctx, t, lim, o + (inc_out - out_), opos0 + (inc_out - out_), inc_nm - nm_, e2_, o2_, m2_, f2_);
+      }
+      __syncwarp();
+      // LZ77 copies in stream order, warp-cooperative
+      const uint32_t opos_end = opos0 + chunk_out;
+      const uint32_t ring_lo = opos_end > (uint32_t)POUT ? opos_end - (uint32_t)POUT : 0;   // oldest byte still in the ring
+      bool bad = false;
+      for (uint32_t j = 0; j < n_match; ++j) {
+        const uint32_t ld = lds32(ctx.mld + (j << 2));
+        const uint32_t p = lds16(ctx.mpos + (j << 1));
+        const uint32_t len = (ld & 255) + 3, dist = (ld >> 8) + 1;
+        if (dist > p) { bad = true; break; }                  // distance too far back
+        const uint32_t sp = p - dist;
+        const uint32_t dr = oa + p;                            // ring-relative destination
+        if (sp >= ring_lo) {
+          const uint32_t sr = oa + sp;
+          if (dist >= len) {
+            for (uint32_t i = lane; i < len; i += 32) sts8(ring + ((dr + i) & POM), lds8(ring + ((sr + i) & POM)));
+          } else {
+            uint32_t m = (uint32_t)lane % dist;
+            const uint32_t kk = 32u % dist;
+            for (uint32_t i = lane; i < len; i += 32) {
+              sts8(ring + ((dr + i) & POM), lds8(ring + ((sr + m) & POM)));
+              m += kk;
+              if (m >= dist) m -= dist;
+            }
+          }
+        } else {
+          // older than the ring, therefore already flushed (and dist > len): read the block's own output back from L2
+          const uint8_t* g = gout + sp;
+          ++n_far;
+          for (uint32_t i = lane; i < len; i += 32) sts8(ring + ((dr + i) & POM), __ldcg(g + i));
+        }
+        __syncwarp();
+      }
+      if (bad) { status = STATUS_RETRY; break; }
+      n_matches += n_match;
+      o += chunk_out;
+      pos = newpos;
+      eob = stop_flag == F_EOB;
+      produced();
+    }
+  }
+
+  // drain any TMA chunk still in flight before the CTA (and its shared memory) retires
+  while (waited < issued) wait_chunk(waited);
+
+  if (status == 0 && (OPOS() != isize || pos > total_bits)) status = STATUS_RETRY;
+  if (status == 0) {
+    wk.walk_upto(isize, true, lane);
+    if (OPOS() > flushed) flush_to(OPOS());
+  }
+  if (lane == 0) {
+    a.status[blk] = status;
+    if (status == 0) wk.store(0);
+    if (status) atomicAdd(&g_par_counters[0], 1ull);
+    atomicAdd(&g_par_counters[1], (unsigned long long)n_super);
+    atomicAdd(&g_par_counters[2], (unsigned long long)n_rounds);
+    atomicAdd(&g_par_counters[3], (unsigned long long)n_far);
+    atomicAdd(&g_par_counters[4], (unsigned long long)n_matches);
+    atomicAdd(&g_par_counters[5], (unsigned long long)n_dblocks);
+  }
+#undef OPOS
+}
+
+cudaError_t inflate_par_counters(unsigned long long* out8, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out8, g_par_counters, sizeof(g_par_counters));
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e = cudaMemcpyToSymbol(g_par_counters, z, sizeof(z));
+  }
+  return e;
+}
+
+cudaError_t launch_inflate_par(const InflateArgs& a, cudaStream_t st) {
+  if (a.n_blocks == 0) return cudaSuccess;
+  inflate_par_kernel<<<a.n_blocks, 32, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace biodb

@@ -44,6 +44,11 @@ struct InflateArgs {
   WalkOut walk;
 };
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st);
+// inflate_par.cu: the lane-parallel kernel alone; blocks it cannot finish get status STATUS_RETRY (inflate_common.cuh)
+cudaError_t launch_inflate_par(const InflateArgs& a, cudaStream_t st);
+// diagnostics of the lane-parallel kernel since the last reset: [0] blocks given up (redone by the warp-serial kernel),
+// [1] super-chunks, [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks
+cudaError_t inflate_par_counters(unsigned long long* out8, int reset);
 size_t inflate_smem_bytes();
 
 // ---- crc32.cu ---------------------------------------------------------------------------------

@@ -787,6 +787,15 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
   return BIODB_OK;
 }
 
+biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset) {
+  if (!out8) return BIODB_ERR_ARG;
+  cudaDeviceSynchronize();
+  unsigned long long v[8];
+  if (inflate_par_counters(v, reset) != cudaSuccess) return BIODB_ERR_CUDA;
+  for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  return BIODB_OK;
+}
+
 size_t biodb_dev_scan_workspace_bytes(uint32_t n_blocks) { return scan_workspace_bytes(n_blocks); }
 
 biodb_status biodb_dev_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t* block_uoff, uint32_t n_blocks,

@@ -202,6 +202,11 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
                                const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
                                int32_t* status, uint32_t* crc, void* stream);
 
+/* Diagnostics of the lane-parallel inflate kernel since the last reset (synchronises the device):
+ * out8[0] blocks it gave up on (redone by the warp-serial kernel: malformed or unusual streams), [1] super-chunks,
+ * [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks; [6..7] reserved. */
+biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset);
+
 typedef struct biodb_dev_records {
   uint64_t capacity;     /* in: room (records) in each array below */
   uint64_t cigar_capacity;

@@ -1,0 +1,215 @@
+"""GPU parity of the BGZF inflate stage alone (biodb_dev_inflate, C ABI) against zlib on raw-DEFLATE streams of every
+shape: dynamic / fixed / stored blocks, all levels and strategies, long overlapping matches, distances up to 32 KiB,
+incompressible data, tiny and maximal blocks, corrupted payloads (status parity with inflate(Z_FINISH)).  Also checks
+that the lane-parallel kernel itself (not its warp-serial fallback) decodes every valid stream."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def raw_deflate(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8):
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, mem, strategy)
+    return co.compress(data) + co.flush()
+
+
+def zlib_status(payload, isize):
+    """What inflate(Z_FINISH) into an isize-byte buffer returns (block.d:172): 0 / -3 / -5."""
+    d = zlib.decompressobj(-15)
+    try:
+        out = d.decompress(payload, isize + 1)
+    except zlib.error as e:
+        msg = str(e)
+        return (-3 if "Error -3" in msg else -5), b""
+    if len(out) > isize:
+        return -5, out          # output buffer exhausted
+    if not d.eof:
+        return -5, out          # input exhausted (or output full exactly at a non-final point)
+    if len(out) != isize:
+        return -3, out          # restatement-defined: stream ended short of ISIZE
+    return 0, out
+
+
+def dev_inflate(payloads, isizes, pad_front=0):
+    """Run biodb_dev_inflate on a list of payloads; returns (outputs, statuses, counters)."""
+    torch = _torch()
+    from biod_b200 import _capi
+    L = _capi.lib()
+    n = len(payloads)
+    offs, pos = [], pad_front
+    for p in payloads:
+        offs.append(pos)
+        pos += len(p) + 3          # odd spacing: payloads start at every alignment
+    comp = np.zeros(pos + 64, dtype=np.uint8)
+    for o, p in zip(offs, payloads):
+        comp[o:o + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    out_off = np.zeros(n, dtype=np.uint64)
+    t = 5
+    for i, s in enumerate(isizes):
+        out_off[i] = t
+        t += s + 7
+    dev = torch.device("cuda:0")
+    d_comp = torch.from_numpy(comp).to(dev)
+    d_poff = torch.from_numpy(np.array(offs, dtype=np.int64)).to(dev)
+    d_csz = torch.from_numpy(np.array([len(p) for p in payloads], dtype=np.int32)).to(dev)
+    d_ooff = torch.from_numpy(out_off.astype(np.int64)).to(dev)
+    d_isz = torch.from_numpy(np.array(isizes, dtype=np.int32)).to(dev)
+    d_out = torch.zeros(t + 64, dtype=torch.uint8, device=dev)
+    d_st = torch.full((n,), 77, dtype=torch.int32, device=dev)
+    d_crc = torch.zeros(n, dtype=torch.int32, device=dev)
+    cnt = (C.c_uint64 * 8)()
+    assert L.biodb_debug_inflate_counters(cnt, 1) == 0
+    torch.cuda.synchronize()
+    rc = L.biodb_dev_inflate(d_comp.data_ptr(), d_poff.data_ptr(), d_csz.data_ptr(), d_ooff.data_ptr(), d_isz.data_ptr(),
+                             n, d_out.data_ptr(), d_st.data_ptr(), d_crc.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert L.biodb_debug_inflate_counters(cnt, 1) == 0
+    out = d_out.cpu().numpy()
+    st = d_st.cpu().numpy()
+    crc = d_crc.cpu().numpy().view(np.uint32)
+    outs = [out[int(out_off[i]):int(out_off[i]) + isizes[i]].tobytes() for i in range(n)]
+    return outs, st, crc, list(cnt)
+
+
+def corpus():
+    rng = np.random.default_rng(1234)
+    items = {}
+    items["empty"] = b""
+    items["one"] = b"A"
+    items["short_text"] = b"hello hello hello hello world"
+    items["zeros_64k"] = bytes(65536)
+    items["zeros_65280"] = bytes(65280)
+    items["random_64k"] = rng.integers(0, 256, 65536, dtype=np.uint8).tobytes()
+    items["random_1000"] = rng.integers(0, 256, 1000, dtype=np.uint8).tobytes()
+    items["ramp"] = bytes(range(256)) * 255
+    items["acgt"] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 65280).tobytes()
+    items["quals"] = rng.integers(35, 75, 65280, dtype=np.uint8).tobytes()
+    # repeats at distances up to the 32 KiB window
+    unit = rng.integers(0, 256, 30000, dtype=np.uint8).tobytes()
+    items["far_repeat"] = unit + unit + unit[:5280]
+    unit = rng.integers(0, 256, 700, dtype=np.uint8).tobytes()
+    items["near_repeat"] = (unit * 100)[:65280]
+    items["period3"] = (b"abc" * 30000)[:65536]
+    items["period1_then_text"] = b"x" * 40000 + (b"the quick brown fox jumps over the lazy dog " * 600)[:25000]
+    # BAM-like records: small ints, names, packed bases, uniform quals
+    rec = bytearray()
+    for i in range(230):
+        rec += (279).to_bytes(4, "little") + (0).to_bytes(4, "little") + (1000 + 5 * i).to_bytes(4, "little")
+        rec += b"\x0b\x3c\x49\x12" + b"\x01\x00\x00\x00" + (150).to_bytes(4, "little") + b"\xff" * 8 + bytes(4)
+        rec += b"r%09d\x00" % i + (150 << 4).to_bytes(4, "little")
+        rec += rng.choice(np.frombuffer(b"\x11\x12\x14\x18\x21\x22\x24\x28\x41\x42\x44\x48\x81\x82\x84\x88", dtype=np.uint8), 75).tobytes()
+        rec += rng.integers(2, 42, 150, dtype=np.uint8).tobytes() + b"MDZ150\x00"
+    items["bam_like"] = bytes(rec[:65280])
+    # mixtures that force several DEFLATE blocks of different types inside one stream
+    items["mixed"] = items["random_1000"] * 8 + bytes(20000) + items["quals"][:20000] + items["acgt"][:10000]
+    return items
+
+
+CASES = [
+    (6, zlib.Z_DEFAULT_STRATEGY, 8), (1, zlib.Z_DEFAULT_STRATEGY, 8), (9, zlib.Z_DEFAULT_STRATEGY, 8),
+    (0, zlib.Z_DEFAULT_STRATEGY, 8), (6, zlib.Z_FIXED, 8), (6, zlib.Z_HUFFMAN_ONLY, 8), (6, zlib.Z_RLE, 8),
+    (6, zlib.Z_FILTERED, 8), (9, zlib.Z_DEFAULT_STRATEGY, 1), (4, zlib.Z_DEFAULT_STRATEGY, 9),
+]
+
+
+def test_valid_streams_of_every_shape_match_zlib():
+    items = corpus()
+    payloads, isizes, names = [], [], []
+    for name, data in items.items():
+        for (lv, strat, mem) in CASES:
+            p = raw_deflate(data, lv, strat, mem)
+            if len(p) > 65536:
+                continue
+            payloads.append(p)
+            isizes.append(len(data))
+            names.append((name, lv, strat, mem))
+    # concatenated DEFLATE streams cut by sync flushes (empty stored blocks in the middle)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    data = items["bam_like"]
+    p = co.compress(data[:20000]) + co.flush(zlib.Z_SYNC_FLUSH) + co.compress(data[20000:40000]) + co.flush(zlib.Z_FULL_FLUSH)
+    p += co.compress(data[40000:]) + co.flush()
+    payloads.append(p)
+    isizes.append(len(data))
+    names.append(("flushes", 6, 0, 8))
+    outs, st, crc, cnt = dev_inflate(payloads, isizes)
+    for i, (name, lv, strat, mem) in enumerate(names):
+        data = items["bam_like"] if name == "flushes" else items[name]
+        assert st[i] == 0, (names[i], int(st[i]))
+        assert outs[i] == data, names[i]
+        assert int(crc[i]) == zlib.crc32(data), names[i]
+    # every valid stream is decoded by the lane-parallel kernel itself; the warp-serial kernel is only its fallback
+    assert cnt[0] == 0, cnt
+    assert cnt[1] > 0 and cnt[5] >= len(payloads), cnt
+
+
+@pytest.mark.parametrize("pad", [0, 1, 7, 13])
+def test_payload_alignment(pad):
+    data = corpus()["bam_like"]
+    sizes = (1, 17, 300, 5000, len(data))
+    payloads = [raw_deflate(data[:n], 6) for n in sizes]
+    outs, st, crc, cnt = dev_inflate(payloads, list(sizes), pad_front=pad)
+    assert list(st) == [0] * 5
+    for o, n in zip(outs, sizes):
+        assert o == data[:n]
+    assert cnt[0] == 0
+
+
+def test_corrupted_streams_report_zlib_status():
+    items = corpus()
+    rng = np.random.default_rng(99)
+    payloads, isizes, expect = [], [], []
+    for name in ("bam_like", "mixed", "short_text", "near_repeat", "zeros_64k", "random_1000"):
+        data = items[name]
+        for lv in (6, 0, 1):
+            good = raw_deflate(data, lv)
+            variants = [good[:len(good) // 2], good[:-1], good + b"\x00\x00", good[:max(1, len(good) - 5)]]
+            for _ in range(6):
+                b = bytearray(good)
+                k = int(rng.integers(0, len(b)))
+                b[k] ^= 1 << int(rng.integers(0, 8))
+                variants.append(bytes(b))
+            for v in variants:
+                for isz in (len(data), max(0, len(data) - 1), len(data) + 1):
+                    payloads.append(v)
+                    isizes.append(isz)
+                    expect.append(zlib_status(v, isz))
+    outs, st, crc, cnt = dev_inflate(payloads, isizes)
+    for i in range(len(payloads)):
+        exp_status, exp_out = expect[i]
+        assert int(st[i]) == exp_status, (i, int(st[i]), exp_status, len(payloads[i]), isizes[i])
+        if exp_status == 0:
+            assert outs[i] == exp_out
+
+
+def test_fast_path_takes_all_fixture_blocks():
+    """No block of the reference's own BAM files, nor of the synthetic benchmark files, needs the fallback."""
+    from biod_b200 import _capi
+    from conftest import fixture_bytes
+    from gpu_util import gpu_records
+    from tools import bamgen
+    L = _capi.lib()
+    cnt = (C.c_uint64 * 8)()
+    assert L.biodb_debug_inflate_counters(cnt, 1) == 0
+    n_expected = 0
+    for name in ["ex1_header.bam", "bins.bam", "tags.bam", "b7_295_chunk.bam", "mg1655_chunk.bam", "ion_20_chunk.bam",
+                 "illu_20_chunk.bam", "long_header.bam"]:
+        rd, g, raws, err = gpu_records(fixture_bytes(name))
+        assert err is None
+    for mixed, level, straddle in [(False, -1, False), (True, -1, False), (True, 1, True), (False, 9, False), (False, 0, False)]:
+        data = bamgen.generate(60000, 1, mixed, level, bamgen.SEED_BASE + 2, straddle=straddle)
+        rd, g, raws, err = gpu_records(data.tobytes())
+        assert err is None
+        n_expected += 60000
+        assert len(raws) == 60000
+    assert L.biodb_debug_inflate_counters(cnt, 1) == 0
+    assert cnt[0] == 0, list(cnt)
+    assert cnt[1] > 0 and cnt[2] >= cnt[1], list(cnt)
