@@ -312,6 +312,15 @@ def main():
             "inflate_out_gbs": s0.uncompressed_bytes / (infl_ms * 1e-3) / 1e9,
             "roofline": roofline, "gpu_launches": int(sum(s[0].kernel_launches for s in steps)), "clocks": clocks}
 
+    # diagnostics of the lane-parallel inflate kernel over everything run so far (0 blocks given up = no fallback)
+    try:
+        cnt = (C.c_uint64 * 8)()
+        if L.biodb_debug_inflate_counters(cnt, 0) == 0:
+            line["inflate_counters"] = {"blocks_given_up": int(cnt[0]), "super_chunks": int(cnt[1]), "decode_rounds": int(cnt[2]),
+                                        "matches_from_l2": int(cnt[3]), "matches": int(cnt[4]), "deflate_blocks": int(cnt[5])}
+    except Exception:  # noqa: BLE001
+        pass
+
     # ---- e2e: file in pinned host memory, every column batch copied back inside the timed region -------
     if not args.no_e2e:
         rd = open_reader(False, False, True)   # pin the (possibly shared, mmap-ed) file buffer when the driver allows it

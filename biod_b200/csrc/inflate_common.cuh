@@ -166,6 +166,75 @@ __device__ __noinline__ int build_table(const uint8_t* lens, int n, uint16_t* lu
   return 0;
 }
 
+// Symbol-parallel variant of build_table (same results): lane L takes symbols L, L+32, ...; the rank of a symbol among
+// the symbols of equal code length comes from a warp match, so the canonical codes are assigned 32 symbols at a time
+// and every lane fills the LUT slots of its own symbols.  scratch: 16 words of shared memory.
+template <int PB>
+__device__ __noinline__ int build_table_par(const uint8_t* lens, int n, uint16_t* lut, uint16_t* sorted, Code* code,
+                                            int kind, int lane, uint32_t* scratch) {
+  if (lane < 16) scratch[lane] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const int l = lens[i];
+    if (l) atomicAdd(&scratch[l], 1u);
+  }
+  __syncwarp();
+  const bool owner = lane >= 1 && lane <= 15;
+  const int mycnt = owner ? (int)scratch[lane] : 0;
+  // Kraft sum in units of 2^-15: > 2^15 over-subscribed, < 2^15 incomplete
+  int v = owner ? (mycnt << (15 - lane)) : 0;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const uint32_t have = __ballot_sync(0xffffffffu, mycnt > 0);
+  const int maxlen = have ? 31 - __clz(have) : 0;
+  if (v > (1 << 15)) return -1;
+  int myfirst = 0, myindex = 0;
+  {
+    int c = 0, idx = 0;
+    for (int L = 1; L <= 15; ++L) {
+      int prev = __shfl_sync(0xffffffffu, mycnt, L - 1);   // lane 0 holds 0
+      c = (c + prev) << 1;
+      idx += prev;
+      if (lane == L) { myfirst = c; myindex = idx; }
+    }
+  }
+  __syncwarp();
+  if (lane < 16) {
+    code->cnt[lane] = (uint16_t)mycnt;
+    code->first[lane] = (uint16_t)myfirst;
+    code->index[lane] = (uint16_t)myindex;
+    scratch[lane] = 0;                                     // symbols of this length placed so far
+  }
+  if (v != (1 << 15))                                      // incomplete code: some slots stay unused
+    for (int i = lane; i < (1 << PB); i += 32) lut[i] = (uint16_t)ENT_INVALID;
+  __syncwarp();
+  if (maxlen == 0) return 1;
+  if (v < (1 << 15) && (kind == KIND_CODELEN || maxlen != 1)) return -1;
+  for (int g = 0; g < n; g += 32) {
+    const int sym = g + lane;
+    const int l = sym < n ? (int)lens[sym] : 0;
+    const uint32_t same = __match_any_sync(0xffffffffu, l);
+    const uint32_t rank = (uint32_t)__popc(same & ((1u << lane) - 1));
+    const uint32_t placed = l ? scratch[l] : 0;
+    __syncwarp();
+    if (l) {
+      if (rank == 0) scratch[l] = placed + (uint32_t)__popc(same);
+      const uint32_t k = placed + rank;
+      sorted[code->index[l] + k] = (uint16_t)sym;
+      const uint32_t c = code->first[l] + k;
+      const uint32_t rev = __brev(c) >> (32 - l);
+      if (l <= PB) {
+        const uint16_t e = (uint16_t)make_entry(kind, sym, l);
+        for (uint32_t i = rev; i < (1u << PB); i += (1u << l)) lut[i] = e;
+      } else {
+        lut[rev & ((1u << PB) - 1)] = (uint16_t)ENT_SLOW;
+      }
+    }
+    __syncwarp();
+  }
+  return 0;
+}
+
 // Canonical decode of a code longer than PB bits, starting from the PB-bit prefix already known not to be a
 // complete code (RFC 1951 §3.2.2 code assignment run backwards).
 template <int PB>

@@ -34,33 +34,39 @@ namespace biodb {
 namespace {
 
 #ifndef BIODB_PAR_SUB_BITS
-#define BIODB_PAR_SUB_BITS 256
+#define BIODB_PAR_SUB_BITS 192
 #endif
 #ifndef BIODB_PAR_OUT_RING
-#define BIODB_PAR_OUT_RING 8192
+#define BIODB_PAR_OUT_RING 4096
 #endif
 #ifndef BIODB_PAR_MLIST
-#define BIODB_PAR_MLIST 256
+#define BIODB_PAR_MLIST 192
+#endif
+#ifndef BIODB_PAR_IN_RING
+#define BIODB_PAR_IN_RING 2048
 #endif
 constexpr int SUB_BITS = BIODB_PAR_SUB_BITS;   // bits of one lane's sub-sequence
-constexpr int CH = SUB_BITS * 4;               // bytes per TMA chunk == compressed bytes of one nominal super-chunk
-constexpr int NCH = 4;                         // chunks in the staging ring
+constexpr int SUPER_BYTES = SUB_BITS * 4;      // compressed bytes of one nominal super-chunk
+constexpr int NCH = 8;                         // chunks in the staging ring
+constexpr int CH = BIODB_PAR_IN_RING / NCH;    // bytes per TMA chunk
 constexpr int PIN_RING = NCH * CH;
 constexpr int PIN_WORDS = PIN_RING / 4;
 constexpr int POUT = BIODB_PAR_OUT_RING;
 constexpr uint32_t POM = POUT - 1;
 // Output bytes one super-chunk may produce.  The ring must keep, besides them, the unflushed tail (< FLUSH_ALIGN), the
 // longest match (258) for the "older than the ring => already flushed" rule, and ~1.1 KB of history for the walker.
-constexpr int OUT_BUDGET = POUT - 2048;
-constexpr int LANE_CAP = 1024;                 // a lane stops taking codes once it has produced this many bytes ...
+constexpr int OUT_BUDGET = POUT - 1536;
+constexpr int LANE_CAP = 512;                  // a lane stops taking codes once it has produced this many bytes ...
 constexpr int MLIST = BIODB_PAR_MLIST;         // matches one super-chunk may hold
 constexpr int LANE_MCAP = 32;                  // ... or this many matches (the next lane continues from there)
 constexpr int FLUSH_ALIGN = 128;
 constexpr int STORE_PIECE = 1024;              // stored blocks are copied in pieces of this many bytes
 constexpr int HDR_BYTES = 640;                 // >= longest dynamic block header: 17 + 19*3 + 316*(7+7) bits = 563 bytes
-static_assert(LANE_CAP + 257 <= OUT_BUDGET, "one lane must always fit");
+static_assert(LANE_CAP > SUB_BITS, "literals alone never reach the cap, so it is checked after matches only");
+static_assert(LANE_CAP + SUB_BITS + 257 <= OUT_BUDGET, "one lane must always fit");
 static_assert(LANE_MCAP <= MLIST, "one lane must always fit");
-static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= STORE_PIECE + 16 && (NCH - 1) * CH >= CH + 32,
+static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= STORE_PIECE + 16 &&
+                  (NCH - 1) * CH >= SUPER_BYTES + 32 && CH % 16 == 0,
               "staging ring too small");
 static_assert(STORE_PIECE <= OUT_BUDGET, "");
 
@@ -68,7 +74,7 @@ static_assert(STORE_PIECE <= OUT_BUDGET, "");
 constexpr uint32_t F_EOB = 1, F_ERR = 2, F_INEND = 3;
 
 struct __align__(16) ParSmem {
-  uint32_t in_ring[PIN_WORDS];
+  uint32_t in_ring[PIN_WORDS + 4];     // + guard word (copy of word 0) so that a 64-bit window never wraps
   uint8_t out_ring[POUT];
   uint16_t lut_lit[1 << LIT_BITS];
   uint16_t lut_dist[1 << DIST_BITS];   // also hosts the 128-entry code-length LUT
@@ -78,13 +84,13 @@ struct __align__(16) ParSmem {
   uint8_t lens[352];                   // [0,19) code-length code, [32,32+316) litlen+dist lengths
   uint32_t m_ld[MLIST];                // matches of the super-chunk: (length-3) | (distance-1) << 8
   uint16_t m_pos[MLIST];               //   and their block-relative output offset
-  uint32_t disttab[32];                // distance symbol -> base | extra bits << 16
-  uint16_t lentab[32];                 // length symbol -> base | extra bits << 9
+  uint32_t auxtab[64];                 // [0,32) length symbol, [32,64) distance symbol -> base | extra bits << 16
+  uint32_t scratch[16];                // build_table_par
   unsigned long long mbar[NCH];
 };
 
 struct ParCtx {           // shared-space addresses and limits every lane needs while decoding
-  uint32_t in_ring, ring, lutl, lutd, lentab, disttab, mld, mpos;
+  uint32_t in_ring, ring, lutl, lutd, auxtab, mld, mpos;
   uint32_t total_bits;
   const Code* code_lit;
   const Code* code_dist;
@@ -94,69 +100,70 @@ struct ParCtx {           // shared-space addresses and limits every lane needs 
 
 // 32 bits of the staged stream starting at bit `pos`
 __device__ __forceinline__ uint32_t fetch32(uint32_t in_ring, uint32_t pos) {
-  const uint32_t wi = pos >> 5;
-  const uint32_t lo = lds32(in_ring + ((wi & (PIN_WORDS - 1)) << 2));
-  const uint32_t hi = lds32(in_ring + (((wi + 1) & (PIN_WORDS - 1)) << 2));
+  const uint32_t a = in_ring + ((pos >> 3) & (uint32_t)(PIN_RING - 4));
+  const uint32_t lo = lds32(a);
+  const uint32_t hi = lds32(a + 4);         // the word after the last one of the ring is a copy of word 0 (guard)
   return __funnelshift_r(lo, hi, pos);
 }
 
-// One lane decodes the codes that start in [t, limit).  WRITE: literals go to the output ring at ring index
-// oring + (bytes produced so far), matches to the list from slot mslot on (output offset opos + bytes produced).
+// Every lane with `active` decodes the codes that start in [t, limit) of its own sub-sequence; all 32 lanes must call
+// this together.  WRITE: literals go to the output ring at ring index oring + (bytes produced so far), matches to the
+// list from slot mslot on (output offset opos + bytes produced).
+// One loop trip decodes ONE Huffman code per lane, whichever kind the lane needs next — a literal/length code or the
+// distance code of the length it met in the previous trip — as straight-line, select-based code, so that the lanes
+// stay converged: a length/distance pair costs two trips of the same instructions instead of a divergent side path
+// that stalls the 31 other lanes.
 template <bool WRITE>
-__device__ __forceinline__ void lane_decode(const ParCtx& c, uint32_t t, uint32_t limit, uint32_t oring, uint32_t opos,
-                                            uint32_t mslot, uint32_t& end, uint32_t& out, uint32_t& nm, uint32_t& flag) {
+__device__ __forceinline__ void lane_decode(const ParCtx& c, bool active, uint32_t t, uint32_t limit, uint32_t oring,
+                                            uint32_t opos, uint32_t mslot, uint32_t& end, uint32_t& out, uint32_t& nm,
+                                            uint32_t& flag) {
+  const uint32_t lim = limit < c.total_bits ? limit : c.total_bits;
   uint32_t pos = t, o = 0, m = 0, fl = 0;
-  bool done = false;
-  while (true) {
-    uint32_t e = 0, bits = 0;
-    // literal run: lanes that meet something else wait at the end of this loop, so that the (longer) match path below
-    // runs once for all of them
-    while (true) {
-      if (pos >= limit || o >= (uint32_t)LANE_CAP || m >= (uint32_t)LANE_MCAP) { done = true; break; }
-      if (pos >= c.total_bits) { fl = F_INEND; done = true; break; }
-      bits = fetch32(c.in_ring, pos);
-      e = lds16(c.lutl + ((bits & ((1u << LIT_BITS) - 1)) << 1));
-      if (e & (3u << 8)) break;
-      if (WRITE) sts8(c.ring + ((oring + o) & POM), e);
-      ++o;
-      pos += e >> 12;
-    }
-    if (done) break;
-    if (((e >> 8) & 3) == K_SPECIAL) {
-      if (e == ENT_SLOW) e = slow_decode<LIT_BITS>(bits, c.code_lit, c.sorted_lit, KIND_LITLEN);
-      if (((e >> 8) & 3) == K_SPECIAL) { fl = F_ERR; break; }
-      if (((e >> 8) & 3) == K_LIT) {          // a literal with a long code
-        if (WRITE) sts8(c.ring + ((oring + o) & POM), e);
-        ++o;
-        pos += e >> 12;
-        continue;
+  uint32_t st = 0;          // 0: the next code is a literal/length code, 1: a distance code
+  uint32_t len = 0;
+  uint32_t lut = c.lutl, msk = ((1u << LIT_BITS) - 1) << 1;
+  uint32_t run = (active && pos < lim) ? 1u : 0u;
+  while (__any_sync(0xffffffffu, run)) {
+    const uint32_t bits = fetch32(c.in_ring, pos);
+    uint32_t e = lds16(lut + ((bits << 1) & msk));
+    if (run && (e & (3u << 8)) == (K_SPECIAL << 8)) {      // rare: code longer than the LUT index, or invalid
+      if (e == ENT_SLOW)
+        e = st ? slow_decode<DIST_BITS>(bits, c.code_dist, c.sorted_dist, KIND_DIST)
+               : slow_decode<LIT_BITS>(bits, c.code_lit, c.sorted_lit, KIND_LITLEN);
+      if ((e & (3u << 8)) == (K_SPECIAL << 8)) {
+        fl = F_ERR;
+        run = 0;
       }
     }
     const uint32_t cl = e >> 12;
-    if (((e >> 8) & 3) == K_EOB) { pos += cl; fl = F_EOB; break; }
-    // length / distance pair
-    const uint32_t lb = lds16(c.lentab + ((e & 31) << 1));
-    const uint32_t eb = lb >> 9;
-    const uint32_t len = (lb & 511) + ((bits >> cl) & ((1u << eb) - 1));      // cl + eb <= 20 bits of the 32
-    pos += cl + eb;
-    bits = fetch32(c.in_ring, pos);
-    uint32_t e2 = lds16(c.lutd + ((bits & ((1u << DIST_BITS) - 1)) << 1));
-    if (((e2 >> 8) & 3) == K_SPECIAL) {
-      if (e2 == ENT_SLOW) e2 = slow_decode<DIST_BITS>(bits, c.code_dist, c.sorted_dist, KIND_DIST);
-      if (((e2 >> 8) & 3) == K_SPECIAL) { fl = F_ERR; break; }
+    const uint32_t kind = st ? K_LEN : ((e >> 8) & 3);            // a distance code is handled like a length code
+    const uint32_t aux = lds32(c.auxtab + (((st << 5) | (e & 31)) << 2));   // base | extra bits << 16 (unused for literals)
+    const uint32_t eb = kind == K_LEN ? aux >> 16 : 0;
+    const uint32_t val = (aux & 0xffff) + ((bits >> cl) & ~(0xffffffffu << eb));   // cl + eb <= 28 bits of the 32
+    if (run) {
+      pos += cl + eb;
+      if (kind == K_LIT) {
+        if (WRITE) sts8(c.ring + ((oring + o) & POM), e);
+        ++o;
+      }
+      if (kind == K_EOB) { fl = F_EOB; run = 0; }
+      if (st) {
+        if (WRITE) {
+          sts32(c.mld + ((mslot + m) << 2), (len - 3) | ((val - 1) << 8));
+          sts16(c.mpos + ((mslot + m) << 1), opos + o);
+        }
+        o += len;
+        ++m;
+        if (o >= (uint32_t)LANE_CAP || m >= (uint32_t)LANE_MCAP) run = 0;   // the next lane continues from here
+      }
+      len = val;
+      st = (st ^ 1) & (kind == K_LEN ? 1u : 0u);     // length -> distance next; anything else -> literal/length next
+      lut = st ? c.lutd : c.lutl;
+      msk = st ? ((1u << DIST_BITS) - 1) << 1 : ((1u << LIT_BITS) - 1) << 1;
+      if (!st && pos >= lim) run = 0;                // a lane stops only between codes of the literal/length alphabet
     }
-    const uint32_t cl2 = e2 >> 12;
-    const uint32_t db = lds32(c.disttab + ((e2 & 31) << 2));
-    const uint32_t eb2 = db >> 16;
-    const uint32_t dist = (db & 0xffff) + ((bits >> cl2) & ((1u << eb2) - 1));   // cl2 + eb2 <= 28 bits of the 32
-    pos += cl2 + eb2;
-    if (WRITE) {
-      sts32(c.mld + ((mslot + m) << 2), (len - 3) | ((dist - 1) << 8));
-      sts16(c.mpos + ((mslot + m) << 1), opos + o);
-    }
-    o += len;
-    ++m;
   }
+  if (fl == 0 && active && pos >= c.total_bits && pos < limit) fl = F_INEND;   // ran out of input before its boundary
   end = pos;
   out = o;
   nm = m;
@@ -192,7 +199,9 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
   uint8_t* gout = a.out + obase;
   const uint32_t oa = (uint32_t)(((uintptr_t)gout) & POM);   // ring index of output byte 0
 
-  const uint32_t sbase = smem_u32(s);
+  // shared-window addresses, made opaque so that they live in registers instead of being rebuilt in the hot loops
+  uint32_t sbase = smem_u32(s);
+  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
   const uint32_t in_ring = sbase + (uint32_t)offsetof(ParSmem, in_ring);
   const uint32_t ring = sbase + (uint32_t)offsetof(ParSmem, out_ring);
   const uint32_t lutd = sbase + (uint32_t)offsetof(ParSmem, lut_dist);
@@ -202,8 +211,7 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
   ctx.ring = ring;
   ctx.lutl = sbase + (uint32_t)offsetof(ParSmem, lut_lit);
   ctx.lutd = lutd;
-  ctx.lentab = sbase + (uint32_t)offsetof(ParSmem, lentab);
-  ctx.disttab = sbase + (uint32_t)offsetof(ParSmem, disttab);
+  ctx.auxtab = sbase + (uint32_t)offsetof(ParSmem, auxtab);
   ctx.mld = sbase + (uint32_t)offsetof(ParSmem, m_ld);
   ctx.mpos = sbase + (uint32_t)offsetof(ParSmem, m_pos);
   ctx.code_lit = &s->code_lit;
@@ -215,8 +223,10 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
   if (lane == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   {
     uint32_t b, eb;
-    if (lane < 29) { len_base((uint32_t)lane, b, eb); s->lentab[lane] = (uint16_t)(b | (eb << 9)); }
-    if (lane < 30) { dist_base((uint32_t)lane, b, eb); s->disttab[lane] = b | (eb << 16); }
+    s->auxtab[lane] = 0;
+    s->auxtab[32 + lane] = 0;
+    if (lane < 29) { len_base((uint32_t)lane, b, eb); s->auxtab[lane] = b | (eb << 16); }
+    if (lane < 30) { dist_base((uint32_t)lane, b, eb); s->auxtab[32 + lane] = b | (eb << 16); }
   }
   __syncwarp();
 
@@ -243,6 +253,10 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
   auto wait_chunk = [&](uint32_t k) {
     mbar_wait(mbar + 8 * (k % NCH), (k / NCH) & 1);
     waited = k + 1;
+    if (k % NCH == 0) {      // slot 0 has new bytes: refresh the guard word behind the ring
+      if (lane == 0) sts32(in_ring + PIN_RING, lds32(in_ring));
+      __syncwarp();
+    }
   };
   // make staged bytes [lo, hi) readable; bytes before lo are not needed any more (the decoder only moves forward)
   auto ensure_input = [&](uint32_t lo, uint32_t hi) {
@@ -347,11 +361,11 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
       pos = HPOS();
       for (int i = lane; i < 288; i += 32) s->lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
       __syncwarp();
-      build_table<LIT_BITS>(s->lens, 288, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane);
+      build_table_par<LIT_BITS>(s->lens, 288, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane, s->scratch);
       __syncwarp();
       s->lens[lane] = 5;
       __syncwarp();
-      build_table<DIST_BITS>(s->lens, 32, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane);
+      build_table_par<DIST_BITS>(s->lens, 32, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane, s->scratch);
     } else {
       // ---- dynamic Huffman code (RFC 1951 §3.2.7) --------------------------------------
       HFILL();
@@ -373,7 +387,7 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
         HDROP(3);
       }
       __syncwarp();
-      int r = build_table<CL_BITS>(s->lens, 19, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_CODELEN, lane);
+      int r = build_table_par<CL_BITS>(s->lens, 19, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_CODELEN, lane, s->scratch);
       if (r != 0) { status = STATUS_RETRY; break; }
       const int total = hlit + hdist;
       __syncwarp();
@@ -418,9 +432,9 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
       __syncwarp();
       if (s->lens[32 + 256] == 0) { status = STATUS_RETRY; break; }   // no end-of-block code
       __syncwarp();
-      r = build_table<LIT_BITS>(s->lens + 32, hlit, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane);
+      r = build_table_par<LIT_BITS>(s->lens + 32, hlit, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane, s->scratch);
       if (r < 0) { status = STATUS_RETRY; break; }
-      r = build_table<DIST_BITS>(s->lens + 32 + hlit, hdist, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane);
+      r = build_table_par<DIST_BITS>(s->lens + 32 + hlit, hdist, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane, s->scratch);
       if (r < 0) { status = STATUS_RETRY; break; }
     }
     __syncwarp();
@@ -432,11 +446,11 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
     bool eob = false;
     while (!eob) {
       const uint32_t base = pos;
-      ensure_input(base >> 3, (base >> 3) + CH + 24);
+      ensure_input(base >> 3, (base >> 3) + SUPER_BYTES + 24);
       const uint32_t lim = base + (uint32_t)(lane + 1) * SUB_BITS;
       uint32_t t = base + (uint32_t)lane * SUB_BITS;
       uint32_t e_, out_, nm_, fl_;
-      lane_decode<false>(ctx, t, lim, 0, 0, 0, e_, out_, nm_, fl_);
+      lane_decode<false>(ctx, true, t, lim, 0, 0, 0, e_, out_, nm_, fl_);
       ++n_super;
       ++n_rounds;
       // repair the chain: lane L must start where lane L-1 ended
@@ -451,12 +465,13 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
         const uint32_t vstop = stopm & (vp >= 32 ? 0xffffffffu : ((1u << vp) - 1));
         if (vstop) { kstop = (uint32_t)__ffs(vstop) - 1; break; }
         if (!needm) break;
-        if (need) {
-          t = tn;
-          lane_decode<false>(ctx, t, lim, 0, 0, 0, e_, out_, nm_, fl_);
+        {
+          uint32_t e2_, o2_, m2_, f2_;
+          if (need) t = tn;
+          lane_decode<false>(ctx, need, t, lim, 0, 0, 0, e2_, o2_, m2_, f2_);
+          if (need) { e_ = e2_; out_ = o2_; nm_ = m2_; fl_ = f2_; }
         }
         ++n_rounds;
-        __syncwarp();
       }
       // commit the longest prefix of lanes that fits the output ring and the match list
       const uint32_t ncand = kstop < 32 ? kstop + 1 : 32;
@@ -472,26 +487,61 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
       const uint32_t opos0 = OPOS();
       if (stop_flag == F_ERR || stop_flag == F_INEND || opos0 + chunk_out > isize) { status = STATUS_RETRY; break; }
       // write pass: literals into the ring, matches into the list
-      if ((uint32_t)lane < k) {
+      {
         uint32_t e2_, o2_, m2_, f2_;
-        lane_decode<true>(ctx, t, lim, o + (inc_out - out_), opos0 + (inc_out - out_), inc_nm - nm_, e2_, o2_, m2_, f2_);
+        lane_decode<true>(ctx, (uint32_t)lane < k, t, lim, o + (inc_out - out_), opos0 + (inc_out - out_), inc_nm - nm_,
+                          e2_, o2_, m2_, f2_);
       }
       __syncwarp();
-      // LZ77 copies in stream order, warp-cooperative
+      // LZ77 copies, 32 list entries at a time (one per lane, handed around by shuffles)
       const uint32_t opos_end = opos0 + chunk_out;
       const uint32_t ring_lo = opos_end > (uint32_t)POUT ? opos_end - (uint32_t)POUT : 0;   // oldest byte still in the ring
       bool bad = false;
-      for (uint32_t j = 0; j < n_match; ++j) {
-        const uint32_t ld = lds32(ctx.mld + (j << 2));
-        const uint32_t p = lds16(ctx.mpos + (j << 1));
-        const uint32_t len = (ld & 255) + 3, dist = (ld >> 8) + 1;
-        if (dist > p) { bad = true; break; }                  // distance too far back
-        const uint32_t sp = p - dist;
-        const uint32_t dr = oa + p;                            // ring-relative destination
-        if (sp >= ring_lo) {
-          const uint32_t sr = oa + sp;
+      for (uint32_t j0 = 0; j0 < n_match; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const bool valid = j < n_match;
+        uint32_t ld = 0, myp = 0x10000;
+        if (valid) { ld = lds32(ctx.mld + (j << 2)); myp = lds16(ctx.mpos + (j << 1)); }
+        const uint32_t mylen = (ld & 255) + 3, mydist = (ld >> 8) + 1;
+        if (__any_sync(0xffffffffu, mydist > myp)) { bad = true; break; }      // distance too far back
+        const uint32_t mysp = myp - mydist;
+        const bool far = valid && mysp < ring_lo;
+        // (a) sources older than the ring, therefore already flushed (and dist > len): read the block's own output
+        //     back from L2.  They depend on nothing in flight, so all of them go at once: the bytes of these matches
+        //     are numbered consecutively and dealt out to the lanes, 32 bytes per trip.
+        const uint32_t farm = __ballot_sync(0xffffffffu, far);
+        if (farm) {
+          n_far += (uint32_t)__popc(farm);
+          const uint32_t flen = far ? mylen : 0;
+          const uint32_t incl = warp_incl_scan(flen, lane);
+          const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+          for (uint32_t b0 = 0; b0 < total; b0 += 32) {
+            const uint32_t b = b0 + lane;
+            uint32_t k = 0;                      // number of lanes whose bytes all come before byte b
+#pragma unroll
+            for (uint32_t step = 16; step; step >>= 1) {
+              const uint32_t v = __shfl_sync(0xffffffffu, incl, (k + step - 1) & 31);
+              if (v <= b) k += step;
+            }
+            k &= 31;
+            const uint32_t off = b - (__shfl_sync(0xffffffffu, incl, k) - __shfl_sync(0xffffffffu, flen, k));
+            const uint32_t srcp = __shfl_sync(0xffffffffu, mysp, k) + off;
+            const uint32_t dstp = __shfl_sync(0xffffffffu, myp, k) + off;
+            if (b < total) sts8(ring + ((oa + dstp) & POM), __ldcg(gout + srcp));
+          }
+          __syncwarp();
+        }
+        // (b) sources inside the ring: in stream order, the whole warp on one match
+        uint32_t nearm = __ballot_sync(0xffffffffu, valid && !far);
+        while (nearm) {
+          const uint32_t k = (uint32_t)__ffs(nearm) - 1;
+          nearm &= nearm - 1;
+          const uint32_t len = __shfl_sync(0xffffffffu, mylen, k), dist = __shfl_sync(0xffffffffu, mydist, k);
+          const uint32_t dr = oa + __shfl_sync(0xffffffffu, myp, k);           // ring-relative destination
+          const uint32_t sr = dr - dist;
           if (dist >= len) {
-            for (uint32_t i = lane; i < len; i += 32) sts8(ring + ((dr + i) & POM), lds8(ring + ((sr + i) & POM)));
+            if ((uint32_t)lane < len) sts8(ring + ((dr + lane) & POM), lds8(ring + ((sr + lane) & POM)));
+            for (uint32_t i = lane + 32; i < len; i += 32) sts8(ring + ((dr + i) & POM), lds8(ring + ((sr + i) & POM)));
           } else {
             uint32_t m = (uint32_t)lane % dist;
             const uint32_t kk = 32u % dist;
@@ -501,13 +551,8 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
               if (m >= dist) m -= dist;
             }
           }
-        } else {
-          // older than the ring, therefore already flushed (and dist > len): read the block's own output back from L2
-          const uint8_t* g = gout + sp;
-          ++n_far;
-          for (uint32_t i = lane; i < len; i += 32) sts8(ring + ((dr + i) & POM), __ldcg(g + i));
+          __syncwarp();
         }
-        __syncwarp();
       }
       if (bad) { status = STATUS_RETRY; break; }
       n_matches += n_match;
