@@ -169,9 +169,15 @@ __device__ __noinline__ int build_table(const uint8_t* lens, int n, uint16_t* lu
 // Symbol-parallel variant of build_table (same results): lane L takes symbols L, L+32, ...; the rank of a symbol among
 // the symbols of equal code length comes from a warp match, so the canonical codes are assigned 32 symbols at a time
 // and every lane fills the LUT slots of its own symbols.  scratch: 16 words of shared memory.
+// sub (may be null): pool of sub_cap second-level entries.  Codes longer than PB bits that share their first PB bits
+// get one sub-table of 2^r entries (r = longest such code - PB); the first-level slot then holds
+// K_SPECIAL | r << 12 | offset/2 and the decoder indexes the sub-table with the next r bits.  Canonical codes sorted by
+// (length, symbol) are also sorted by value when left-aligned, so the codes of one sub-table are neighbours in
+// `sorted`.  Codes that do not fit the pool keep ENT_SLOW (slow_decode).
 template <int PB>
 __device__ __noinline__ int build_table_par(const uint8_t* lens, int n, uint16_t* lut, uint16_t* sorted, Code* code,
-                                            int kind, int lane, uint32_t* scratch) {
+                                            int kind, int lane, uint32_t* scratch, uint16_t* sub = nullptr,
+                                            int sub_cap = 0) {
   if (lane < 16) scratch[lane] = 0;
   __syncwarp();
   for (int i = lane; i < n; i += 32) {
@@ -228,6 +234,56 @@ __device__ __noinline__ int build_table_par(const uint8_t* lens, int n, uint16_t
         for (uint32_t i = rev; i < (1u << PB); i += (1u << l)) lut[i] = e;
       } else {
         lut[rev & ((1u << PB) - 1)] = (uint16_t)ENT_SLOW;
+      }
+    }
+    __syncwarp();
+  }
+  if (sub != nullptr && maxlen > PB) {
+    const int k_begin = code->index[PB + 1], k_end = code->index[maxlen] + code->cnt[maxlen];
+    // first PB bits (most significant first) of the k-th code in sorted order
+    auto prefix_of = [&](int k, int& l, uint32_t& c) -> uint32_t {
+      l = lens[sorted[k]];
+      c = code->first[l] + (uint32_t)(k - code->index[l]);
+      return c >> (l - PB);
+    };
+    uint32_t alloc = 0;
+    for (int k0 = k_begin; k0 < k_end; k0 += 32) {        // pass 1: one sub-table per group of equal prefixes
+      const int k = k0 + lane;
+      int l = 0, l2 = 0;
+      uint32_t c = 0, c2 = 0, pre = 0;
+      bool is_last = false;
+      if (k < k_end) {
+        pre = prefix_of(k, l, c);
+        is_last = k + 1 == k_end || prefix_of(k + 1, l2, c2) != pre;
+      }
+      const uint32_t size = is_last ? 1u << (l - PB) : 0;   // lengths grow inside a group: the last code is the longest
+      const uint32_t incl = alloc + [&] {
+        uint32_t v = size;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t u = __shfl_up_sync(0xffffffffu, v, d);
+          if (lane >= d) v += u;
+        }
+        return v;
+      }();
+      if (is_last && incl <= (uint32_t)sub_cap)
+        lut[__brev(pre) >> (32 - PB)] = (uint16_t)((K_SPECIAL << 8) | ((uint32_t)(l - PB) << 12) | ((incl - size) >> 1));
+      alloc = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    for (int k0 = k_begin; k0 < k_end; k0 += 32) {        // pass 2: every long code fills its slots of its sub-table
+      const int k = k0 + lane;
+      if (k < k_end) {
+        int l;
+        uint32_t c;
+        const uint32_t pre = prefix_of(k, l, c);
+        const uint32_t e = lut[__brev(pre) >> (32 - PB)];
+        if (e >> 12) {
+          const uint32_t r = e >> 12, off = (e & 0xff) << 1, w = (uint32_t)(l - PB);
+          const uint32_t rev = __brev(c & ((1u << w) - 1)) >> (32 - w);
+          const uint16_t ent = (uint16_t)make_entry(kind, sorted[k], l);
+          for (uint32_t i = rev; i < (1u << r); i += (1u << w)) sub[off + i] = ent;
+        }
       }
     }
     __syncwarp();

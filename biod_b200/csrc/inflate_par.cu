@@ -34,13 +34,13 @@ namespace biodb {
 namespace {
 
 #ifndef BIODB_PAR_SUB_BITS
-#define BIODB_PAR_SUB_BITS 192
+#define BIODB_PAR_SUB_BITS 224
 #endif
 #ifndef BIODB_PAR_OUT_RING
 #define BIODB_PAR_OUT_RING 4096
 #endif
 #ifndef BIODB_PAR_MLIST
-#define BIODB_PAR_MLIST 192
+#define BIODB_PAR_MLIST 160
 #endif
 #ifndef BIODB_PAR_IN_RING
 #define BIODB_PAR_IN_RING 2048
@@ -60,6 +60,7 @@ constexpr int LANE_CAP = 512;                  // a lane stops taking codes once
 constexpr int MLIST = BIODB_PAR_MLIST;         // matches one super-chunk may hold
 constexpr int LANE_MCAP = 32;                  // ... or this many matches (the next lane continues from there)
 constexpr int FLUSH_ALIGN = 128;
+constexpr int SUB_CAP = 320;                   // >= 308: most second-level entries a complete 286-symbol code needs past 10 bits
 constexpr int STORE_PIECE = 1024;              // stored blocks are copied in pieces of this many bytes
 constexpr int HDR_BYTES = 640;                 // >= longest dynamic block header: 17 + 19*3 + 316*(7+7) bits = 563 bytes
 static_assert(LANE_CAP > SUB_BITS, "literals alone never reach the cap, so it is checked after matches only");
@@ -86,11 +87,12 @@ struct __align__(16) ParSmem {
   uint16_t m_pos[MLIST];               //   and their block-relative output offset
   uint32_t auxtab[64];                 // [0,32) length symbol, [32,64) distance symbol -> base | extra bits << 16
   uint32_t scratch[16];                // build_table_par
+  uint16_t sub_lit[SUB_CAP];           // second-level tables of the literal/length codes longer than LIT_BITS
   unsigned long long mbar[NCH];
 };
 
 struct ParCtx {           // shared-space addresses and limits every lane needs while decoding
-  uint32_t in_ring, ring, lutl, lutd, auxtab, mld, mpos;
+  uint32_t in_ring, ring, lutl, lutd, auxtab, mld, mpos, subl;
   uint32_t total_bits;
   const Code* code_lit;
   const Code* code_dist;
@@ -127,7 +129,9 @@ __device__ __forceinline__ void lane_decode(const ParCtx& c, bool active, uint32
     const uint32_t bits = fetch32(c.in_ring, pos);
     uint32_t e = lds16(lut + ((bits << 1) & msk));
     if (run && (e & (3u << 8)) == (K_SPECIAL << 8)) {      // rare: code longer than the LUT index, or invalid
-      if (e == ENT_SLOW)
+      if (e >> 12)                                         // second-level table of the literal/length code
+        e = lds16(c.subl + ((((e & 0xff) << 1) + ((bits >> LIT_BITS) & ~(0xffffffffu << (e >> 12)))) << 1));
+      else if (e == ENT_SLOW)
         e = st ? slow_decode<DIST_BITS>(bits, c.code_dist, c.sorted_dist, KIND_DIST)
                : slow_decode<LIT_BITS>(bits, c.code_lit, c.sorted_lit, KIND_LITLEN);
       if ((e & (3u << 8)) == (K_SPECIAL << 8)) {
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
   ctx.lutl = sbase + (uint32_t)offsetof(ParSmem, lut_lit);
   ctx.lutd = lutd;
   ctx.auxtab = sbase + (uint32_t)offsetof(ParSmem, auxtab);
+  ctx.subl = sbase + (uint32_t)offsetof(ParSmem, sub_lit);
   ctx.mld = sbase + (uint32_t)offsetof(ParSmem, m_ld);
   ctx.mpos = sbase + (uint32_t)offsetof(ParSmem, m_pos);
   ctx.code_lit = &s->code_lit;
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
       pos = HPOS();
       for (int i = lane; i < 288; i += 32) s->lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
       __syncwarp();
-      build_table_par<LIT_BITS>(s->lens, 288, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane, s->scratch);
+      build_table_par<LIT_BITS>(s->lens, 288, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane, s->scratch, s->sub_lit, SUB_CAP);
       __syncwarp();
       s->lens[lane] = 5;
       __syncwarp();
@@ -432,7 +437,8 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
       __syncwarp();
       if (s->lens[32 + 256] == 0) { status = STATUS_RETRY; break; }   // no end-of-block code
       __syncwarp();
-      r = build_table_par<LIT_BITS>(s->lens + 32, hlit, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane, s->scratch);
+      r = build_table_par<LIT_BITS>(s->lens + 32, hlit, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane, s->scratch,
+                                    s->sub_lit, SUB_CAP);
       if (r < 0) { status = STATUS_RETRY; break; }
       r = build_table_par<DIST_BITS>(s->lens + 32 + hlit, hdist, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane, s->scratch);
       if (r < 0) { status = STATUS_RETRY; break; }
