@@ -44,12 +44,15 @@ extern (C) nothrow @nogc {
     }
     struct biodb_pileup_params {
         int single_ref; int skip_zero_coverage; int use_md_tag; int want_query_offset;
-        ulong start_from; ulong end_at; int counts_only; int[3] reserved;
+        ulong start_from; ulong end_at; int counts_only; int compact_reads; int[2] reserved;
     }
     struct biodb_column_batch {
         ulong n_columns; ulong n_entries; int ref_id; int last_of_pileup;
         const(ulong)* position; const(ulong)* col_off; const(uint)* n_starting_here;
         const(uint)* read_idx; const(ubyte)* base; const(ubyte)* qual; const(uint)* query_offset; const(uint)* counts;
+        // compact_reads: read_idx is null; reads of column c = strag_idx[strag_off[c] .. strag_off[c+1]] followed by
+        // last_read[c] - d for every set bit d = 63..0 of live_mask[c]
+        const(uint)* last_read; const(ulong)* live_mask; const(uint)* strag_off; const(uint)* strag_idx;
     }
     void biodb_default_options(biodb_options*);
     int biodb_open(const(char)* path, const(biodb_options)*, biodb_reader**);
@@ -172,10 +175,19 @@ struct GpuPileupColumn {
     int ref_id() @property const { return _b.ref_id; }
     size_t coverage() @property const { return cast(size_t)(_b.col_off[_c + 1] - _b.col_off[_c]); }
     char reference_base() @property const { return 'N'; }
-    const(uint)[] reads() @property const { return _b.read_idx[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]]; }
+    /// Record indices of the reads of the column, in file order.  With compact_reads the list is rebuilt from
+    /// (stragglers, last_read, live_mask) — see include/biod_b200.h.
+    const(uint)[] reads() @property const {
+        if (_b.read_idx !is null) return _b.read_idx[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]];
+        auto r = new uint[coverage];
+        size_t k = 0;
+        foreach (i; _b.strag_off[_c] .. _b.strag_off[_c + 1]) r[k++] = _b.strag_idx[i];
+        foreach_reverse (d; 0 .. 64) if ((_b.live_mask[_c] >> d) & 1) r[k++] = _b.last_read[_c] - cast(uint)d;
+        return r;
+    }
     const(uint)[] reads_starting_here() @property const {
-        auto e = cast(size_t)_b.col_off[_c + 1];
-        return _b.read_idx[e - _b.n_starting_here[_c] .. e];
+        auto r = reads;
+        return r[$ - _b.n_starting_here[_c] .. $];
     }
     const(char)[] bases() @property const {
         return cast(const(char)[])_b.base[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]];

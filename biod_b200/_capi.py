@@ -44,7 +44,7 @@ class Stats(C.Structure):
 class PileupParams(C.Structure):
     _fields_ = [("single_ref", C.c_int32), ("skip_zero_coverage", C.c_int32), ("use_md_tag", C.c_int32),
                 ("want_query_offset", C.c_int32), ("start_from", C.c_uint64), ("end_at", C.c_uint64),
-                ("counts_only", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("counts_only", C.c_int32), ("compact_reads", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class ShardInfo(C.Structure):
@@ -57,7 +57,8 @@ class ShardInfo(C.Structure):
 class ColumnBatch(C.Structure):
     _fields_ = [("n_columns", C.c_uint64), ("n_entries", C.c_uint64), ("ref_id", C.c_int32),
                 ("last_of_pileup", C.c_int32), ("position", u64p), ("col_off", u64p), ("n_starting_here", u32p),
-                ("read_idx", u32p), ("base", u8p), ("qual", u8p), ("query_offset", u32p), ("counts", u32p)]
+                ("read_idx", u32p), ("base", u8p), ("qual", u8p), ("query_offset", u32p), ("counts", u32p),
+                ("last_read", u32p), ("live_mask", u64p), ("strag_off", u32p), ("strag_idx", u32p)]
 
 
 _lib = None

@@ -262,13 +262,15 @@ class BamReader:
                 yield BamRead(batch, i)
 
     def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
-                       want_query_offset=False, copy=False, shard=None, halo_blocks=8, shard_info=None, counts_only=False):
+                       want_query_offset=False, copy=False, shard=None, halo_blocks=8, shard_info=None, counts_only=False,
+                       compact_reads=False):
         """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015)."""
         L = self._L
         p = capi.PileupParams()
         p.single_ref, p.skip_zero_coverage, p.use_md_tag = int(single_ref), int(skip_zero_coverage), int(use_md_tag)
         p.want_query_offset, p.start_from, p.end_at = int(want_query_offset), start_from, end_at
         p.counts_only = int(counts_only)
+        p.compact_reads = int(compact_reads)
         pl = C.c_void_p()
         if shard is not None:
             st = L.biodb_pileup_begin_shard(self._h, C.byref(p), shard[0], shard[1], halo_blocks, C.byref(pl))
@@ -293,6 +295,31 @@ class BamReader:
             L.biodb_pileup_end(pl)
 
 
+def expand_compact_reads(col_off, last, mask, soff, sidx, n_entries):
+    """read_idx of every entry from the compact representation (include/biod_b200.h, biodb_column_batch)."""
+    nc = len(last)
+    out = np.zeros(n_entries, dtype=np.uint32)
+    if nc == 0:
+        return out
+    cov = np.diff(col_off).astype(np.int64)
+    ns = np.diff(soff).astype(np.int64)
+    # bits of every mask, d = 63..0 (column order = ascending record index = descending d)
+    bits = ((mask[:, None] >> np.arange(63, -1, -1, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
+    assert np.array_equal(bits.sum(axis=1) + ns, cov), "compact read lists do not add up to the coverage"
+    d = np.broadcast_to(np.arange(63, -1, -1, dtype=np.int64)[None, :], bits.shape)[bits]
+    col = np.broadcast_to(np.arange(nc, dtype=np.int64)[:, None], bits.shape)[bits]
+    win = (last[col].astype(np.int64) - d).astype(np.uint32)
+    # place: stragglers first, then the window reads
+    start = col_off[:-1].astype(np.int64)
+    k_in_col = np.arange(len(col), dtype=np.int64) - np.repeat(np.cumsum(bits.sum(axis=1)) - bits.sum(axis=1), bits.sum(axis=1))
+    out[start[col] + ns[col] + k_in_col] = win
+    if len(sidx):
+        scol = np.repeat(np.arange(nc, dtype=np.int64), ns)
+        k = np.arange(len(sidx), dtype=np.int64) - np.repeat(soff[:-1].astype(np.int64), ns)
+        out[start[scol] + k] = sidx
+    return out
+
+
 class ColumnBatch:
     def __init__(self, cb, copy):
         g = (lambda a: a.copy()) if copy else (lambda a: a)
@@ -301,7 +328,19 @@ class ColumnBatch:
         self.position = g(_np(cb.position, nc, np.uint64))
         self.col_off = g(_np(cb.col_off, nc + 1, np.uint64))
         self.n_starting_here = g(_np(cb.n_starting_here, nc, np.uint32))
-        self.read_idx = g(_np(cb.read_idx, ne, np.uint32))
+        self.compact = None
+        if cb.read_idx:
+            self.read_idx = g(_np(cb.read_idx, ne, np.uint32))
+        elif cb.last_read:
+            # compact_reads: (last read, window mask, stragglers) per column -> the same read_idx list
+            last = _np(cb.last_read, nc, np.uint32).copy()
+            mask = _np(cb.live_mask, nc, np.uint64).copy()
+            soff = _np(cb.strag_off, nc + 1, np.uint32).copy()
+            sidx = _np(cb.strag_idx, int(soff[nc]), np.uint32).copy()
+            self.compact = (last, mask, soff, sidx)
+            self.read_idx = expand_compact_reads(self.col_off, last, mask, soff, sidx, ne)
+        else:
+            self.read_idx = np.zeros(0, dtype=np.uint32)
         self.base = g(_np(cb.base, ne, np.uint8))
         self.qual = g(_np(cb.qual, ne, np.uint8))
         self.query_offset = g(_np(cb.query_offset, ne, np.uint32)) if cb.query_offset else None

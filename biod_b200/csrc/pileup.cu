@@ -353,6 +353,41 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
     for (int q = 0; q < 6; ++q) o.counts[(size_t)(c0 + lane) * 6 + q] = cnt[q];
 }
 
+// ---- compact read lists (biodb_pileup_params.compact_reads) -----------------------------------------------
+// The reads of a column are file-ordered, and all but a few long-spanning ones lie within a short window of record
+// indices.  One thread per column turns the column's read_idx list into: the index of its last read, a 64-bit mask
+// (bit d = read `last - d` is in the column) and the number of leading reads older than that window ("stragglers",
+// copied out verbatim by compact_strag_kernel).  12 bytes per column instead of 4 bytes per entry cross PCIe.
+__global__ void compact_mask_kernel(const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ read_idx,
+                                    uint32_t n_col, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > n_col) return;
+  if (c == n_col) { nstrag[c] = 0; return; }
+  const uint64_t b = col_off[c], e = col_off[c + 1];
+  uint32_t last = 0, ns = 0;
+  uint64_t m = 0;
+  if (e > b) {
+    last = read_idx[e - 1];
+    for (uint64_t i = e; i-- > b;) {
+      const uint32_t d = last - read_idx[i];
+      if (d >= 64) { ns = (uint32_t)(i - b + 1); break; }     // ascending order: everything before is older still
+      m |= 1ull << d;
+    }
+  }
+  last_read[c] = last;
+  mask[c] = m;
+  nstrag[c] = ns;
+}
+
+__global__ void compact_strag_kernel(const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ read_idx,
+                                     uint32_t n_col, const uint32_t* __restrict__ strag_off, uint32_t* strag_idx) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_col) return;
+  const uint32_t s0 = strag_off[c], ns = strag_off[c + 1] - s0;
+  const uint64_t b = col_off[c];
+  for (uint32_t i = 0; i < ns; ++i) strag_idx[s0 + i] = read_idx[b + i];
+}
+
 // ---- carry to the next batch ------------------------------------------------------------------------
 __global__ void carry_flag_kernel(uint32_t g0, uint32_t g1, const int32_t* eend, int64_t limit, uint32_t* flag) {
   uint32_t j = g0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -477,6 +512,19 @@ void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnS
   if (o.counts) entries_kernel<true><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
   else entries_kernel<false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
   ++g_kernel_launches;
+}
+
+// Compact read lists, step 1: per-column last read, window mask and straggler offsets (exclusive scan; the total is
+// strag_off[n_col], read by the host after a sync).  Step 2 copies the stragglers.
+void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag,
+                          uint32_t* strag_off, GroupScratch& s, cudaStream_t st) {
+  launch1d(compact_mask_kernel, n_col + 1, st, o.col_off, o.read_idx, n_col, last_read, mask, nstrag);
+  device_scan<false>(nstrag, strag_off, (uint64_t)n_col + 1, s.tmp_u32, OpAdd(), 0u, st);
+}
+
+void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_idx,
+                               cudaStream_t st) {
+  launch1d(compact_strag_kernel, n_col, st, o.col_off, o.read_idx, n_col, strag_off, strag_idx);
 }
 
 // Carry: live reads of [g0,g1) with end > limit, compacted in order into `out`.

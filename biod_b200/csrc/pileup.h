@@ -91,6 +91,10 @@ void pileup_island_cols(uint32_t n_islands, GroupScratch& s, cudaStream_t st);
 void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_islands, uint32_t n_col, GroupScratch& s,
                    ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
 void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
+void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag,
+                          uint32_t* strag_off, GroupScratch& s, cudaStream_t st);
+void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_idx,
+                               cudaStream_t st);
 void pileup_carry(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, int64_t limit, GroupScratch& s,
                   CarryOut& out, cudaStream_t st);
 void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, uint32_t n_carry_out,

@@ -36,8 +36,9 @@ struct CarryBufs {
 // asynchronous copy on the copy stream.  Two sets alternate so that batch k+1 is computed and copied while
 // the caller still reads batch k.
 struct OutSet {
-  DevBuf d[8];      // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts
-  PinBuf h[7];      // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts
+  DevBuf d[12];     // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts, last_read, live_mask, strag_off, strag_idx
+  PinBuf h[11];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, strag_off, strag_idx
+  uint32_t n_strag = 0;
   size_t col_cap = 0, ent_cap = 0;
   cudaEvent_t computed = nullptr, done = nullptr;
 };
@@ -670,6 +671,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       n_entries = *pl->h_small.as<uint64_t>();
       const bool counts_only = pl->prm.counts_only != 0;
       const bool want_q = pl->prm.want_query_offset != 0 && !counts_only;
+      const bool compact = pl->prm.compact_reads != 0 && !counts_only;
       if (counts_only) {
         PL_TRY(os.d[7].ensure(os.col_cap * 24, st));
         if (!p.r->opts.device_output) PL_TRY(os.h[6].ensure(os.col_cap * 24));
@@ -699,19 +701,56 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       p.stage_begin();
       pileup_entries(v, n_col, s, c, o, st);
       p.stage_end(&p.stats.pileup_ms);
+      os.n_strag = 0;
+      if (compact) {
+        // read lists as last read + window mask + stragglers (pileup.cu: compact_mask_kernel)
+        PL_TRY(os.d[8].ensure(os.col_cap * 4, st));
+        PL_TRY(os.d[9].ensure(os.col_cap * 8, st));
+        PL_TRY(os.d[10].ensure((os.col_cap + 1) * 4, st));
+        if (!p.r->opts.device_output) {
+          PL_TRY(os.h[7].ensure(os.col_cap * 4));
+          PL_TRY(os.h[8].ensure(os.col_cap * 8));
+          PL_TRY(os.h[9].ensure((os.col_cap + 1) * 4));
+        }
+        p.stage_begin();
+        pileup_compact_masks(n_col, o, os.d[8].as<uint32_t>(), os.d[9].as<uint64_t>(), pl->cs[0].as<uint32_t>(),
+                             os.d[10].as<uint32_t>(), s, st);
+        p.stage_end(&p.stats.pileup_ms);
+        PL_TRY(launch_copy_bytes(pl->h_small.p, os.d[10].as<uint32_t>() + n_col, 4, st));
+        PL_TRY(cudaStreamSynchronize(st));
+        os.n_strag = *pl->h_small.as<uint32_t>();
+        PL_TRY(os.d[11].ensure((size_t)os.n_strag * 4 + 64, st));
+        if (!p.r->opts.device_output) PL_TRY(os.h[10].ensure((size_t)os.n_strag * 4 + 64));
+        if (os.n_strag) {
+          p.stage_begin();
+          pileup_compact_stragglers(n_col, o, os.d[10].as<uint32_t>(), os.d[11].as<uint32_t>(), st);
+          p.stage_end(&p.stats.pileup_ms);
+        }
+      }
       PL_TRY(cudaEventRecord(os.computed, st));
       // results to the host on the copy stream: overlaps with the carry kernels and the next batch
       if (!p.r->opts.device_output) {
         cudaStream_t cs = pl->copy_st;
         PL_TRY(cudaStreamWaitEvent(cs, os.computed, 0));
-        p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + (counts_only ? (uint64_t)n_col * 24 : n_entries * (6 + (want_q ? 4 : 0)));
+        p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 +
+                             (counts_only ? (uint64_t)n_col * 24
+                                          : n_entries * (2 + (want_q ? 4 : 0)) +
+                                                (compact ? (uint64_t)n_col * 16 + 4 + (uint64_t)os.n_strag * 4 : n_entries * 4));
         PL_TRY(cudaMemcpyAsync(os.h[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
         PL_TRY(cudaMemcpyAsync(os.h[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, cs));
         PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
         if (counts_only) {
           PL_TRY(cudaMemcpyAsync(os.h[6].p, o.counts, (size_t)n_col * 24, cudaMemcpyDeviceToHost, cs));
         } else {
-          PL_TRY(cudaMemcpyAsync(os.h[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+          if (compact) {
+            PL_TRY(cudaMemcpyAsync(os.h[7].p, os.d[8].p, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[8].p, os.d[9].p, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[9].p, os.d[10].p, (size_t)(n_col + 1) * 4, cudaMemcpyDeviceToHost, cs));
+            if (os.n_strag)
+              PL_TRY(cudaMemcpyAsync(os.h[10].p, os.d[11].p, (size_t)os.n_strag * 4, cudaMemcpyDeviceToHost, cs));
+          } else {
+            PL_TRY(cudaMemcpyAsync(os.h[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+          }
           PL_TRY(cudaMemcpyAsync(os.h[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
           PL_TRY(cudaMemcpyAsync(os.h[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
         }
@@ -783,6 +822,12 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       if (pl->prm.counts_only) {
         cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
         cols->counts = os.d[7].as<uint32_t>();
+      } else if (pl->prm.compact_reads) {
+        cols->read_idx = nullptr;
+        cols->last_read = os.d[8].as<uint32_t>();
+        cols->live_mask = os.d[9].as<uint64_t>();
+        cols->strag_off = os.d[10].as<uint32_t>();
+        cols->strag_idx = os.d[11].as<uint32_t>();
       }
       return BIODB_OK;
     }
@@ -796,6 +841,12 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     if (pl->prm.counts_only) {
       cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
       cols->counts = os.h[6].as<uint32_t>();
+    } else if (pl->prm.compact_reads) {
+      cols->read_idx = nullptr;
+      cols->last_read = os.h[7].as<uint32_t>();
+      cols->live_mask = os.h[8].as<uint64_t>();
+      cols->strag_off = os.h[9].as<uint32_t>();
+      cols->strag_idx = os.h[10].as<uint32_t>();
     }
     return BIODB_OK;
   }

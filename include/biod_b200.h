@@ -129,7 +129,9 @@ typedef struct biodb_pileup_params {
   uint64_t start_from;         /* pileup.d:482-489,497-504 (single_ref only) */
   uint64_t end_at;             /* pileup.d:505 (single_ref only); UINT64_MAX = none */
   int32_t counts_only;         /* 1 = per-column A,C,G,T,other,del counts instead of entries */
-  int32_t reserved[3];
+  int32_t compact_reads;       /* 1 = return the reads of each column as last_read / live_mask / stragglers instead of
+                                  read_idx: 12 bytes per column instead of 4 bytes per entry cross PCIe */
+  int32_t reserved[2];
 } biodb_pileup_params;
 
 typedef struct biodb_column_batch {
@@ -145,6 +147,14 @@ typedef struct biodb_column_batch {
   const uint8_t* qual;         /* [n_entries] current_base_quality (255 inside D/N)    pileup.d:127-134 */
   const uint32_t* query_offset;/* [n_entries] or NULL */
   const uint32_t* counts;      /* [n_columns*6] A,C,G,T,other,deletion — only with counts_only */
+  /* compact_reads: read_idx is NULL and the reads of column c, in column (= file) order, are
+   *   strag_idx[strag_off[c] .. strag_off[c+1])  — the few reads more than 63 records older than the column's last read,
+   *   then every d = 63..0 with bit d of live_mask[c] set: record index last_read[c] - d.
+   * (coverage 0: live_mask 0.)  base / qual / query_offset stay per entry, in the same order. */
+  const uint32_t* last_read;   /* [n_columns] */
+  const uint64_t* live_mask;   /* [n_columns] */
+  const uint32_t* strag_off;   /* [n_columns+1] */
+  const uint32_t* strag_idx;   /* [strag_off[n_columns]] */
 } biodb_column_batch;
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);

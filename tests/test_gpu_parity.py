@@ -390,3 +390,29 @@ def test_large_synthetic_properties(mixed):
         assert np.array_equal(b.counts.sum(1), np.diff(b.col_off).astype(np.uint32))
         c_tot += int(b.counts.sum())
     assert c_tot == tot_ent
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "bins.bam", "ion_20_chunk.bam", "b7_295_chunk.bam"])
+@pytest.mark.parametrize("bpb", [0, 2])
+def test_compact_read_lists_match_oracle(name, bpb):
+    """compact_reads (last read + window mask + stragglers per column) carries exactly the explicit read_idx lists."""
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    assert_pileup_equal(gpu_pileup(data, False, bpb, compact_reads=True), o.pileup_columns())
+    assert_pileup_equal(gpu_pileup(data, True, bpb, compact_reads=True, skip_zero_coverage=False),
+                        o.make_pileup(0, 2**64 - 1, False))
+
+
+def test_compact_read_lists_with_stragglers():
+    """Long N-skips keep a read alive across hundreds of later reads: those come back as stragglers."""
+    from biod_b200 import BamReader
+    refs, recs = synthetic(n=6000, seed=11, refs=(("chrA", 100000),))
+    data = make_bam(refs, recs, level=6)
+    o = orc.Bam(data).decode()
+    for bpb in (0, 3):
+        assert_pileup_equal(gpu_pileup(data, False, bpb, compact_reads=True), o.pileup_columns())
+    n_strag = 0
+    for b in BamReader(data).column_batches(False, compact_reads=True, copy=True):
+        assert b.compact is not None
+        n_strag += len(b.compact[3])
+    assert n_strag > 0
