@@ -590,6 +590,13 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
 #undef OPOS
 }
 
+int inflate_resident_blocks(int device) {
+  int per_sm = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_par_kernel, 32, 0) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+  return per_sm * sms;
+}
+
 cudaError_t inflate_par_counters(unsigned long long* out8, int reset) {
   cudaError_t e = cudaMemcpyFromSymbol(out8, g_par_counters, sizeof(g_par_counters));
   if (e == cudaSuccess && reset) {

@@ -50,6 +50,8 @@ cudaError_t launch_inflate_par(const InflateArgs& a, cudaStream_t st);
 // [1] super-chunks, [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks
 cudaError_t inflate_par_counters(unsigned long long* out8, int reset);
 size_t inflate_smem_bytes();
+// BGZF blocks (CTAs of inflate_par_kernel) resident on the whole device at once; 0 if unknown
+int inflate_resident_blocks(int device);
 
 // ---- crc32.cu ---------------------------------------------------------------------------------
 // CRC-32 of each block's inflated bytes (options.verify_crc; BioD asserts it in debug builds, block.d:187)

@@ -479,7 +479,7 @@ const char* biodb_version(void) { return "biod_b200 0.1 (sm_100a)"; }
 void biodb_default_options(biodb_options* o) {
   memset(o, 0, sizeof *o);
   o->device = -1;
-  o->blocks_per_batch = 8192;
+  o->blocks_per_batch = 0;      // = three full waves of the inflate kernel on the device (7992 on a B200)
 }
 
 const biodb_error* biodb_open_error(void) { return &g_open_error; }
@@ -574,7 +574,6 @@ static biodb_status open_common(biodb_reader* r) {
 
 static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biodb_reader** out) {
   if (opts) r->opts = *opts; else biodb_default_options(&r->opts);
-  if (r->opts.blocks_per_batch <= 0) r->opts.blocks_per_batch = 8192;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "no CUDA device: biod_b200 has no CPU fallback");
@@ -583,6 +582,11 @@ static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biod
   }
   if (r->opts.device < 0) { if (cudaGetDevice(&r->device) != cudaSuccess) r->device = 0; }
   else r->device = r->opts.device;
+  if (r->opts.blocks_per_batch <= 0) {
+    // one warp-sized CTA per BGZF block: a batch of a whole number of waves leaves no SM idle behind a partial last wave
+    int slots = inflate_resident_blocks(r->device);
+    r->opts.blocks_per_batch = slots > 0 ? 3 * slots : 8192;
+  }
   biodb_status s = open_common(r);
   if (s != BIODB_OK) {
     g_open_error = r->err;

@@ -55,7 +55,8 @@ typedef struct biodb_error {
 
 typedef struct biodb_options {
   int32_t device;            /* CUDA ordinal; -1 = current device */
-  int32_t blocks_per_batch;  /* BGZF blocks inflated per GPU batch; 0 = default (8192) */
+  int32_t blocks_per_batch;  /* BGZF blocks inflated per GPU batch; 0 = default: three full waves of the inflate
+                                kernel on the device (7992 on a B200) */
   int32_t verify_crc;        /* 1 = check each block's CRC32 on the device (debug builds of BioD assert it, block.d:187) */
   int32_t want_offsets;      /* 1 = fill start/end virtual offsets (withOffsets policy, readrange.d:51-66) */
   int32_t pin_input;         /* 1 = cudaHostRegister the caller's buffer in biodb_open_memory */
