@@ -77,7 +77,7 @@ def synth_file(args, cfg, n_reads, rank, barrier):
         del data
     barrier()
     # N > 1: every rank maps the same file (one copy in the page cache); N = 1: a private copy that can be pinned
-    data = np.fromfile(path, dtype=np.uint8) if world_size() == 1 else np.memmap(path, dtype=np.uint8, mode="r")
+    data = np.fromfile(path, dtype=np.uint8) if world_size() == 1 else np.memmap(path, dtype=np.uint8, mode="c")
     return data, path, time.time() - t0, made
 
 
@@ -325,6 +325,7 @@ def main():
     # ---- e2e: file in pinned host memory, every column batch copied back inside the timed region -------
     if not args.no_e2e:
         rd = open_reader(False, False, True)   # pin the (possibly shared, mmap-ed) file buffer when the driver allows it
+        input_pinned = bool(L.biodb_input_is_pinned(rd))
         run_pass(L, capi, rd, shard, compact=True)
         barrier()
         es = [run_pass(L, capi, rd, shard, compact=True) for _ in range(args.steps)]
@@ -339,7 +340,7 @@ def main():
         e_ms = float(te[0]) / args.steps
         line["e2e"] = {"value": tot_col / (e_ms * 1e-3), "unit": "positions/s", "ms_per_step": e_ms,
                        "h2d_bytes_per_step": int(es[-1][0].h2d_bytes), "d2h_bytes_per_step": int(es[-1][0].d2h_bytes),
-                       "records_per_sec": tot_rec / (e_ms * 1e-3),
+                       "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned,
                        "columns": "position, col_off, n_starting_here per column; base + qual per entry; the reads of a "
                                   "column as last_read + 64-bit window mask + stragglers (compact_reads, lossless)",
                        "with_explicit_read_idx": {"ms_per_step": float(ex[0].total_ms), "d2h_bytes_per_step": int(ex[0].d2h_bytes),

@@ -115,6 +115,8 @@ def lib():
     L.biodb_pileup_stats.argtypes = [vp, C.POINTER(Stats)]
     L.biodb_dev_inflate.restype = C.c_int
     L.biodb_dev_inflate.argtypes = [vp, vp, vp, vp, vp, C.c_uint32, vp, vp, vp, vp]
+    L.biodb_input_is_pinned.restype = C.c_int32
+    L.biodb_input_is_pinned.argtypes = [vp]
     L.biodb_debug_inflate_counters.restype = C.c_int
     L.biodb_debug_inflate_counters.argtypes = [u64p, C.c_int32]
     L.biodb_dev_scan_workspace_bytes.restype = C.c_size_t
@@ -128,7 +130,7 @@ def lib():
 EXPORTS = [
     "biodb_version", "biodb_default_options", "biodb_open", "biodb_open_memory", "biodb_close", "biodb_last_error",
     "biodb_open_error", "biodb_header_text", "biodb_n_refs", "biodb_ref_info", "biodb_reads_start_voffset",
-    "biodb_file_size", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
+    "biodb_file_size", "biodb_input_is_pinned", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters",

@@ -673,6 +673,8 @@ biodb_status biodb_ref_info(const biodb_reader* r, int32_t i, const char** name,
   return BIODB_OK;
 }
 uint64_t biodb_reads_start_voffset(const biodb_reader* r) { return r ? r->reads_start_vo : 0; }
+int32_t biodb_input_is_pinned(const biodb_reader* r) { return r && r->registered ? 1 : 0; }
+
 uint64_t biodb_file_size(const biodb_reader* r) { return r ? r->flen : 0; }
 
 }  // extern "C"

@@ -91,6 +91,8 @@ int32_t biodb_n_refs(const biodb_reader* r);
 biodb_status biodb_ref_info(const biodb_reader* r, int32_t i, const char** name, int32_t* name_len, int32_t* length);
 uint64_t biodb_reads_start_voffset(const biodb_reader* r);   /* reader.d:121-123 */
 uint64_t biodb_file_size(const biodb_reader* r);
+/* 1 if the input buffer of biodb_open_memory was page-locked (options.pin_input succeeded), else 0. */
+int32_t biodb_input_is_pinned(const biodb_reader* r);
 
 /* ---- records ------------------------------------------------------------------------------------------ */
 typedef struct biodb_record_batch {
