@@ -188,55 +188,6 @@ __global__ void colpos_kernel(IslandTable t, const uint32_t* colbase, uint32_t n
 // ---- column entries -------------------------------------------------------------------------------
 struct Entry { uint8_t base, qual; uint32_t qoff; };
 
-// CIGAR cursor of read `rec` at reference offset k from its position (PileupRead ctor + k x incrementPosition,
-// pileup.d:175-222) and the base/quality there (pileup.d:115-134, read.d:364-383, base.d:85).
-__device__ __forceinline__ Entry cursor_at(const uint8_t* rec, uint32_t lname, uint32_t nc, int32_t lseq, uint32_t k) {
-  const uint8_t* cg = rec + 32 + lname;
-  const uint8_t* seq = cg + 4 * nc;
-  const uint8_t* ql = seq + ((uint32_t)lseq + 1) / 2;
-  Entry en;
-  en.base = '-';
-  en.qual = 255;
-  uint32_t qoff = 0, i = 0, raw = 0, t = 0;
-  for (; i < nc; ++i) {
-    raw = ld32u(cg + 4 * i);
-    t = consume(raw);
-    if (t & 2) { if ((raw & 0xF) != 3) break; }
-    else if (t & 1) qoff += raw >> 4;
-  }
-  uint32_t r = k;
-  while (i < nc) {
-    uint32_t len = raw >> 4;
-    uint32_t eff = len ? len : 1;          // a zero-length op still holds the cursor for one position (pileup.d:196-203)
-    if (r < eff) {
-      if (t == 3) {
-        qoff += r;
-        if (qoff < (uint32_t)lseq) {
-          uint8_t byte = __ldg(seq + (qoff >> 1));
-          uint32_t code = (qoff & 1) ? (byte & 0xF) : (byte >> 4);
-          en.base = (uint8_t)"=ACMGRSVTWYHKDBN"[code];
-          en.qual = __ldg(ql + qoff);
-        } else {
-          // SEQ shorter than the CIGAR says (e.g. SEQ '*'): BioD's lazy accessor would raise a RangeError only
-          // if asked for this base; the eager builder marks it with base 0x00 / quality 255 instead.
-          en.base = 0;
-        }
-      }
-      break;
-    }
-    r -= eff;
-    if (t & 1) qoff += eff;
-    for (++i; i < nc; ++i) {
-      raw = ld32u(cg + 4 * i);
-      t = consume(raw);
-      if (t & 2) break;
-      if (t & 1) qoff += raw >> 4;
-    }
-  }
-  en.qoff = qoff;
-  return en;
-}
-
 constexpr int ENT_WARPS = 8;
 #ifndef BIODB_CHUNK
 #define BIODB_CHUNK 32
@@ -247,6 +198,62 @@ constexpr int CHUNK = BIODB_CHUNK;   // columns per warp (<= 32)
 __device__ __forceinline__ uint32_t base_char(uint32_t code) {
   const uint64_t t = (code & 8) ? 0x4E42444B48595754ull : 0x565352474D43413Dull;
   return (uint32_t)(t >> ((code & 7) * 8)) & 0xFF;
+}
+
+// CIGAR cursor of a read at reference offset k from its position (PileupRead ctor + k x incrementPosition,
+// pileup.d:175-222) and the base/quality there (pileup.d:115-134, read.d:364-383, base.d:85).  The cursor is kept alive
+// across the columns a lane visits for one read: columns come in ascending order, so the walk only ever moves
+// forward — amortised O(1) per column instead of a CIGAR walk from the start for every column.
+struct Cursor {
+  uint32_t i, raw, t;   // current reference-consuming operation: index, packed word, consume bits
+  uint32_t k0, q;       // reference offset (from the read's position) and query offset where it starts
+};
+__device__ __forceinline__ void cursor_init(Cursor& c, const uint8_t* cg, uint32_t nc) {
+  c.i = 0; c.raw = 0; c.t = 0; c.k0 = 0; c.q = 0;
+  for (; c.i < nc; ++c.i) {
+    c.raw = ld32u(cg + 4 * c.i);
+    c.t = consume(c.raw);
+    if (c.t & 2) { if ((c.raw & 0xF) != 3) break; }
+    else if (c.t & 1) c.q += c.raw >> 4;
+  }
+}
+__device__ __forceinline__ Entry cursor_eval(Cursor& c, const uint8_t* cg, uint32_t nc, const uint8_t* seq, const uint8_t* ql,
+                                             int32_t lseq, uint32_t k) {
+  Entry en;
+  en.base = '-';
+  en.qual = 255;
+  while (c.i < nc) {
+    const uint32_t len = c.raw >> 4;
+    const uint32_t eff = len ? len : 1;          // a zero-length op still holds the cursor for one position
+    const uint32_t r = k - c.k0;
+    if (r < eff) {
+      uint32_t qoff = c.q;
+      if (c.t == 3) {
+        qoff += r;
+        if (qoff < (uint32_t)lseq) {
+          const uint32_t byte = __ldg(seq + (qoff >> 1));
+          en.base = (uint8_t)base_char((qoff & 1) ? (byte & 0xF) : (byte >> 4));
+          en.qual = __ldg(ql + qoff);
+        } else {
+          // SEQ shorter than the CIGAR says (e.g. SEQ '*'): BioD's lazy accessor would raise a RangeError only
+          // if asked for this base; the eager builder marks it with base 0x00 / quality 255 instead.
+          en.base = 0;
+        }
+      }
+      en.qoff = qoff;
+      return en;
+    }
+    c.k0 += eff;
+    if (c.t & 1) c.q += eff;
+    for (++c.i; c.i < nc; ++c.i) {
+      c.raw = ld32u(cg + 4 * c.i);
+      c.t = consume(c.raw);
+      if (c.t & 2) break;
+      if (c.t & 1) c.q += c.raw >> 4;
+    }
+  }
+  en.qoff = c.q;
+  return en;
 }
 
 // Read-stationary column builder.  A warp owns CHUNK consecutive columns; lane ci keeps column ci's position and
@@ -300,6 +307,8 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
     const uint8_t* ql = seq + (((uint32_t)lseq + 1) >> 1);
     const bool simple = (ri.z & 0x80000000u) != 0;
     const uint32_t qoff0 = ri.z & 0x7fffffffu;
+    Cursor cur;
+    uint32_t cur_nc = 0xffffffffu;          // not initialised yet for this read
     for (uint32_t ci = 0; ci < ncols; ++ci) {
       const int32_t p = __shfl_sync(0xffffffffu, my_p, ci);
       const bool live = cand && pos <= p && e > p;
@@ -320,11 +329,14 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
             base = base_char((qoff & 1) ? (byte & 0xF) : (byte >> 4));
             qual = __ldg(ql + qoff);
           } else {
-            base = 0;      // SEQ shorter than the CIGAR says: see cursor_at
+            base = 0;      // SEQ shorter than the CIGAR says: see cursor_eval
           }
         } else {
-          const uint8_t* rec = record_body(v, j);
-          Entry en = cursor_at(rec, v.bin_mq_nl[j] & 0xFF, v.flag_nc[j] & 0xFFFF, lseq, k);
+          if (cur_nc == 0xffffffffu) {
+            cur_nc = v.flag_nc[j] & 0xFFFF;
+            cursor_init(cur, seq - 4 * cur_nc, cur_nc);
+          }
+          Entry en = cursor_eval(cur, seq - 4 * cur_nc, cur_nc, seq, ql, lseq, k);
           base = en.base;
           qual = en.qual;
           qoff = en.qoff;
