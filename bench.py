@@ -341,8 +341,9 @@ def main():
         line["e2e"] = {"value": tot_col / (e_ms * 1e-3), "unit": "positions/s", "ms_per_step": e_ms,
                        "h2d_bytes_per_step": int(es[-1][0].h2d_bytes), "d2h_bytes_per_step": int(es[-1][0].d2h_bytes),
                        "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned,
-                       "columns": "position, col_off, n_starting_here per column; base + qual per entry; the reads of a "
-                                  "column as last_read + 64-bit window mask + stragglers (compact_reads, lossless)",
+                       "pcie_d2h_gbs": es[-1][0].d2h_bytes / (e_ms * 1e-3) / 1e9,
+                       "columns": "compact_reads (sequential, lossless): positions as runs; per column n_starting_here, "
+                                  "last_read, 64-bit window mask (+ stragglers); per entry base + qual",
                        "with_explicit_read_idx": {"ms_per_step": float(ex[0].total_ms), "d2h_bytes_per_step": int(ex[0].d2h_bytes),
                                                   "value": (tot_col / (float(ex[0].total_ms) * 1e-3)) if world == 1 else None}}
 

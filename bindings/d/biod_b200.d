@@ -50,9 +50,9 @@ extern (C) nothrow @nogc {
         ulong n_columns; ulong n_entries; int ref_id; int last_of_pileup;
         const(ulong)* position; const(ulong)* col_off; const(uint)* n_starting_here;
         const(uint)* read_idx; const(ubyte)* base; const(ubyte)* qual; const(uint)* query_offset; const(uint)* counts;
-        // compact_reads: read_idx is null; reads of column c = strag_idx[strag_off[c] .. strag_off[c+1]] followed by
-        // last_read[c] - d for every set bit d = 63..0 of live_mask[c]
-        const(uint)* last_read; const(ulong)* live_mask; const(uint)* strag_off; const(uint)* strag_idx;
+        // compact_reads: position, col_off and read_idx are null; see include/biod_b200.h for the sequential encoding
+        const(uint)* last_read; const(ulong)* live_mask; ulong n_stragglers; const(uint)* strag_col; const(uint)* strag_idx;
+        ulong n_runs; const(ulong)* run_pos; const(uint)* run_first_col;
     }
     void biodb_default_options(biodb_options*);
     int biodb_open(const(char)* path, const(biodb_options)*, biodb_reader**);
@@ -171,17 +171,20 @@ class GpuBamReader : IBamSamReader {
 struct GpuPileupColumn {
     private const(biodb_column_batch)* _b;
     private size_t _c;
-    ulong position() @property const { return _b.position[_c]; }
+    // where this column sits in the per-entry arrays and in the straggler list; filled by GpuPileup, which walks the
+    // columns in order (the compact encoding of a batch is sequential: see include/biod_b200.h)
+    private ulong _pos;
+    private size_t _off, _cov, _sk, _ns;
+    ulong position() @property const { return _pos; }
     int ref_id() @property const { return _b.ref_id; }
-    size_t coverage() @property const { return cast(size_t)(_b.col_off[_c + 1] - _b.col_off[_c]); }
+    size_t coverage() @property const { return _cov; }
     char reference_base() @property const { return 'N'; }
-    /// Record indices of the reads of the column, in file order.  With compact_reads the list is rebuilt from
-    /// (stragglers, last_read, live_mask) — see include/biod_b200.h.
+    /// Record indices of the reads of the column, in file order.
     const(uint)[] reads() @property const {
-        if (_b.read_idx !is null) return _b.read_idx[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]];
-        auto r = new uint[coverage];
+        if (_b.read_idx !is null) return _b.read_idx[_off .. _off + _cov];
+        auto r = new uint[_cov];
         size_t k = 0;
-        foreach (i; _b.strag_off[_c] .. _b.strag_off[_c + 1]) r[k++] = _b.strag_idx[i];
+        foreach (i; _sk .. _sk + _ns) r[k++] = _b.strag_idx[i];
         foreach_reverse (d; 0 .. 64) if ((_b.live_mask[_c] >> d) & 1) r[k++] = _b.last_read[_c] - cast(uint)d;
         return r;
     }
@@ -189,10 +192,8 @@ struct GpuPileupColumn {
         auto r = reads;
         return r[$ - _b.n_starting_here[_c] .. $];
     }
-    const(char)[] bases() @property const {
-        return cast(const(char)[])_b.base[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]];
-    }
-    const(ubyte)[] base_qualities() @property const { return _b.qual[cast(size_t)_b.col_off[_c] .. cast(size_t)_b.col_off[_c + 1]]; }
+    const(char)[] bases() @property const { return cast(const(char)[])_b.base[_off .. _off + _cov]; }
+    const(ubyte)[] base_qualities() @property const { return _b.qual[_off .. _off + _cov]; }
 }
 
 /// Input range of columns; `makePileup(GpuBamReader, ...)` mirrors pileup.d:683-694, `pileupColumns` pileup.d:509-519.
@@ -202,25 +203,53 @@ struct GpuPileup {
     private biodb_column_batch _b;
     private size_t _c;
     private bool _empty;
-    this(biodb_reader* h, bool single_ref, bool use_md_tag, ulong start_from, ulong end_at, bool skip_zero_coverage) {
+    private GpuPileupColumn _col;      // cursors of the current column
+    private size_t _run;               // current run of consecutive positions (compact encoding)
+    this(biodb_reader* h, bool single_ref, bool use_md_tag, ulong start_from, ulong end_at, bool skip_zero_coverage,
+         bool compact = true) {
         _h = h;
         biodb_pileup_params prm;
         prm.single_ref = single_ref; prm.skip_zero_coverage = skip_zero_coverage; prm.use_md_tag = use_md_tag;
-        prm.start_from = start_from; prm.end_at = end_at;
+        prm.start_from = start_from; prm.end_at = end_at; prm.compact_reads = compact;
         if (biodb_pileup_begin(h, &prm, &_p) != BIODB_OK) raise(biodb_last_error(h));
         fetch();
     }
     ~this() { if (_p !is null) { biodb_pileup_end(_p); _p = null; } }
     @disable this(this);
     bool empty() @property const { return _empty; }
-    GpuPileupColumn front() @property { return GpuPileupColumn(&_b, _c); }
-    void popFront() { if (++_c >= _b.n_columns) fetch(); }
+    GpuPileupColumn front() @property { return _col; }
+    void popFront() {
+        if (++_c >= _b.n_columns) { fetch(); return; }
+        _col._off += _col._cov;
+        _col._sk += _col._ns;
+        place();
+    }
+    // cursors of column _c, given those of column _c - 1
+    private void place() {
+        _col._c = _c;
+        if (_b.read_idx !is null) {                       // explicit table
+            _col._pos = _b.position[_c];
+            _col._off = cast(size_t)_b.col_off[_c];
+            _col._cov = cast(size_t)(_b.col_off[_c + 1] - _b.col_off[_c]);
+            return;
+        }
+        while (_c >= _b.run_first_col[_run + 1]) ++_run;
+        _col._pos = _b.run_pos[_run] + (_c - _b.run_first_col[_run]);
+        size_t ns = 0;
+        while (_col._sk + ns < _b.n_stragglers && _b.strag_col[_col._sk + ns] == _c) ++ns;
+        _col._ns = ns;
+        import core.bitop : popcnt;
+        _col._cov = ns + popcnt(_b.live_mask[_c]);
+    }
     int ref_id() @property { return biodb_pileup_ref_id(_p); }
     private void fetch() {
         auto st = biodb_pileup_next(_p, &_b);
         if (st == BIODB_EOF) { _empty = true; return; }
         if (st != BIODB_OK) raise(biodb_last_error(_h));
         _c = 0;
+        _run = 0;
+        _col = GpuPileupColumn(&_b, 0);
+        place();
     }
 }
 

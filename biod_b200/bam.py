@@ -295,8 +295,35 @@ class BamReader:
             L.biodb_pileup_end(pl)
 
 
+def _popcount64(x):
+    x = x.astype(np.uint64)
+    c = np.zeros(len(x), dtype=np.int64)
+    for k in range(8):
+        c += _POP8[((x >> np.uint64(8 * k)) & np.uint64(0xFF)).astype(np.int64)]
+    return c
+
+
+_POP8 = np.array([bin(i).count("1") for i in range(256)], dtype=np.int64)
+
+
+def expand_compact_columns(n_columns, last, mask, strag_col, strag_idx, run_pos, run_first_col):
+    """The explicit column table (position, col_off, read_idx) from the sequential compact encoding
+    (include/biod_b200.h, biodb_column_batch with compact_reads)."""
+    nc = int(n_columns)
+    position = np.zeros(nc, dtype=np.uint64)
+    for r in range(len(run_pos)):
+        a, b = int(run_first_col[r]), int(run_first_col[r + 1])
+        position[a:b] = np.uint64(run_pos[r]) + np.arange(b - a, dtype=np.uint64)
+    ns = np.bincount(strag_col.astype(np.int64), minlength=nc).astype(np.int64) if nc else np.zeros(0, dtype=np.int64)
+    cov = ns + _popcount64(mask)
+    col_off = np.concatenate([[0], np.cumsum(cov)]).astype(np.uint64)
+    soff = np.concatenate([[0], np.cumsum(ns)]).astype(np.uint32)
+    read_idx = expand_compact_reads(col_off, last, mask, soff, strag_idx, int(col_off[-1]))
+    return position, col_off, read_idx
+
+
 def expand_compact_reads(col_off, last, mask, soff, sidx, n_entries):
-    """read_idx of every entry from the compact representation (include/biod_b200.h, biodb_column_batch)."""
+    """read_idx of every entry from (last read, window mask, straggler offsets / indices) per column."""
     nc = len(last)
     out = np.zeros(n_entries, dtype=np.uint32)
     if nc == 0:
@@ -305,13 +332,14 @@ def expand_compact_reads(col_off, last, mask, soff, sidx, n_entries):
     ns = np.diff(soff).astype(np.int64)
     # bits of every mask, d = 63..0 (column order = ascending record index = descending d)
     bits = ((mask[:, None] >> np.arange(63, -1, -1, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
-    assert np.array_equal(bits.sum(axis=1) + ns, cov), "compact read lists do not add up to the coverage"
+    nb = bits.sum(axis=1)
+    assert np.array_equal(nb + ns, cov), "compact read lists do not add up to the coverage"
     d = np.broadcast_to(np.arange(63, -1, -1, dtype=np.int64)[None, :], bits.shape)[bits]
     col = np.broadcast_to(np.arange(nc, dtype=np.int64)[:, None], bits.shape)[bits]
     win = (last[col].astype(np.int64) - d).astype(np.uint32)
     # place: stragglers first, then the window reads
     start = col_off[:-1].astype(np.int64)
-    k_in_col = np.arange(len(col), dtype=np.int64) - np.repeat(np.cumsum(bits.sum(axis=1)) - bits.sum(axis=1), bits.sum(axis=1))
+    k_in_col = np.arange(len(col), dtype=np.int64) - np.repeat(np.cumsum(nb) - nb, nb)
     out[start[col] + ns[col] + k_in_col] = win
     if len(sidx):
         scol = np.repeat(np.arange(nc, dtype=np.int64), ns)
@@ -325,22 +353,24 @@ class ColumnBatch:
         g = (lambda a: a.copy()) if copy else (lambda a: a)
         nc, ne = int(cb.n_columns), int(cb.n_entries)
         self.n_columns, self.n_entries, self.ref_id = nc, ne, int(cb.ref_id)
-        self.position = g(_np(cb.position, nc, np.uint64))
-        self.col_off = g(_np(cb.col_off, nc + 1, np.uint64))
         self.n_starting_here = g(_np(cb.n_starting_here, nc, np.uint32))
         self.compact = None
-        if cb.read_idx:
-            self.read_idx = g(_np(cb.read_idx, ne, np.uint32))
-        elif cb.last_read:
-            # compact_reads: (last read, window mask, stragglers) per column -> the same read_idx list
+        if cb.last_read:
+            # compact_reads: sequential encoding -> the same explicit table
             last = _np(cb.last_read, nc, np.uint32).copy()
             mask = _np(cb.live_mask, nc, np.uint64).copy()
-            soff = _np(cb.strag_off, nc + 1, np.uint32).copy()
-            sidx = _np(cb.strag_idx, int(soff[nc]), np.uint32).copy()
-            self.compact = (last, mask, soff, sidx)
-            self.read_idx = expand_compact_reads(self.col_off, last, mask, soff, sidx, ne)
+            nst, nr = int(cb.n_stragglers), int(cb.n_runs)
+            scol = _np(cb.strag_col, nst, np.uint32).copy()
+            sidx = _np(cb.strag_idx, nst, np.uint32).copy()
+            rpos = _np(cb.run_pos, nr, np.uint64).copy()
+            rfirst = _np(cb.run_first_col, nr + 1, np.uint32).copy()
+            self.compact = (last, mask, scol, sidx, rpos, rfirst)
+            self.position, self.col_off, self.read_idx = expand_compact_columns(nc, last, mask, scol, sidx, rpos, rfirst)
+            assert int(self.col_off[-1]) == ne
         else:
-            self.read_idx = np.zeros(0, dtype=np.uint32)
+            self.position = g(_np(cb.position, nc, np.uint64))
+            self.col_off = g(_np(cb.col_off, nc + 1, np.uint64))
+            self.read_idx = g(_np(cb.read_idx, ne, np.uint32)) if cb.read_idx else np.zeros(0, dtype=np.uint32)
         self.base = g(_np(cb.base, ne, np.uint8))
         self.qual = g(_np(cb.qual, ne, np.uint8))
         self.query_offset = g(_np(cb.query_offset, ne, np.uint32)) if cb.query_offset else None

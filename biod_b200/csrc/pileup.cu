@@ -392,12 +392,33 @@ __global__ void compact_mask_kernel(const uint64_t* __restrict__ col_off, const 
 }
 
 __global__ void compact_strag_kernel(const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ read_idx,
-                                     uint32_t n_col, const uint32_t* __restrict__ strag_off, uint32_t* strag_idx) {
+                                     uint32_t n_col, const uint32_t* __restrict__ strag_off, uint32_t* strag_col,
+                                     uint32_t* strag_idx) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_col) return;
   const uint32_t s0 = strag_off[c], ns = strag_off[c + 1] - s0;
   const uint64_t b = col_off[c];
-  for (uint32_t i = 0; i < ns; ++i) strag_idx[s0 + i] = read_idx[b + i];
+  for (uint32_t i = 0; i < ns; ++i) {
+    strag_col[s0 + i] = c;
+    strag_idx[s0 + i] = read_idx[b + i];
+  }
+}
+
+// Column positions as runs of consecutive positions (one run per stretch of non-zero coverage, usually one per batch)
+__global__ void run_flag_kernel(const uint64_t* __restrict__ col_pos, uint32_t n_col, uint32_t* flag) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_col) return;
+  flag[c] = (c == 0 || col_pos[c] != col_pos[c - 1] + 1) ? 1u : 0u;
+}
+__global__ void run_scatter_kernel(const uint64_t* __restrict__ col_pos, uint32_t n_col, const uint32_t* __restrict__ flag,
+                                   const uint32_t* __restrict__ incl, uint64_t* run_pos, uint32_t* run_first_col) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_col) return;
+  if (flag[c]) {
+    run_pos[incl[c] - 1] = col_pos[c];
+    run_first_col[incl[c] - 1] = c;
+  }
+  if (c + 1 == n_col) run_first_col[incl[c]] = n_col;
 }
 
 // ---- carry to the next batch ------------------------------------------------------------------------
@@ -534,9 +555,20 @@ void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_
   device_scan<false>(nstrag, strag_off, (uint64_t)n_col + 1, s.tmp_u32, OpAdd(), 0u, st);
 }
 
-void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_idx,
+void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_col,
+                               uint32_t* strag_idx, cudaStream_t st) {
+  launch1d(compact_strag_kernel, n_col, st, o.col_off, o.read_idx, n_col, strag_off, strag_col, strag_idx);
+}
+
+// Position runs: flag + inclusive scan (n_runs = incl[n_col-1], read by the host after a sync), then the scatter.
+void pileup_position_runs_scan(uint32_t n_col, const ColumnOutput& o, uint32_t* flag, uint32_t* incl, GroupScratch& s,
                                cudaStream_t st) {
-  launch1d(compact_strag_kernel, n_col, st, o.col_off, o.read_idx, n_col, strag_off, strag_idx);
+  launch1d(run_flag_kernel, n_col, st, o.col_pos, n_col, flag);
+  device_scan<true>(flag, incl, (uint64_t)n_col, s.tmp_u32b, OpAdd(), 0u, st);
+}
+void pileup_position_runs_scatter(uint32_t n_col, const ColumnOutput& o, const uint32_t* flag, const uint32_t* incl,
+                                  uint64_t* run_pos, uint32_t* run_first_col, cudaStream_t st) {
+  launch1d(run_scatter_kernel, n_col, st, o.col_pos, n_col, flag, incl, run_pos, run_first_col);
 }
 
 // Carry: live reads of [g0,g1) with end > limit, compacted in order into `out`.

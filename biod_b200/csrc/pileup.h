@@ -93,8 +93,12 @@ void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_isla
 void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
 void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag,
                           uint32_t* strag_off, GroupScratch& s, cudaStream_t st);
-void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_idx,
+void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_col,
+                               uint32_t* strag_idx, cudaStream_t st);
+void pileup_position_runs_scan(uint32_t n_col, const ColumnOutput& o, uint32_t* flag, uint32_t* incl, GroupScratch& s,
                                cudaStream_t st);
+void pileup_position_runs_scatter(uint32_t n_col, const ColumnOutput& o, const uint32_t* flag, const uint32_t* incl,
+                                  uint64_t* run_pos, uint32_t* run_first_col, cudaStream_t st);
 void pileup_carry(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, int64_t limit, GroupScratch& s,
                   CarryOut& out, cudaStream_t st);
 void pileup_carry_copy(const ReadsView& v, uint32_t g0, uint32_t g1, const int32_t* block_size, uint32_t n_carry_out,

@@ -36,9 +36,11 @@ struct CarryBufs {
 // asynchronous copy on the copy stream.  Two sets alternate so that batch k+1 is computed and copied while
 // the caller still reads batch k.
 struct OutSet {
-  DevBuf d[12];     // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts, last_read, live_mask, strag_off, strag_idx
-  PinBuf h[11];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, strag_off, strag_idx
-  uint32_t n_strag = 0;
+  DevBuf d[15];     // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts, last_read, live_mask, strag_off,
+                    // strag_idx, strag_col, run_pos, run_first_col
+  PinBuf h[13];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, run_pos,
+                    // strag_idx, strag_col, run_first_col
+  uint32_t n_strag = 0, n_runs = 0;
   size_t col_cap = 0, ent_cap = 0;
   cudaEvent_t computed = nullptr, done = nullptr;
 };
@@ -702,57 +704,76 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       pileup_entries(v, n_col, s, c, o, st);
       p.stage_end(&p.stats.pileup_ms);
       os.n_strag = 0;
+      os.n_runs = 0;
       if (compact) {
-        // read lists as last read + window mask + stragglers (pileup.cu: compact_mask_kernel)
+        // sequential compact encoding (include/biod_b200.h): read lists as last read + window mask + stragglers
+        // (compact_mask_kernel), positions as runs of consecutive positions (run_flag_kernel)
         PL_TRY(os.d[8].ensure(os.col_cap * 4, st));
         PL_TRY(os.d[9].ensure(os.col_cap * 8, st));
         PL_TRY(os.d[10].ensure((os.col_cap + 1) * 4, st));
         if (!p.r->opts.device_output) {
           PL_TRY(os.h[7].ensure(os.col_cap * 4));
           PL_TRY(os.h[8].ensure(os.col_cap * 8));
-          PL_TRY(os.h[9].ensure((os.col_cap + 1) * 4));
         }
+        uint32_t* run_flag = pl->cs[1].as<uint32_t>();      // the candidate windows (lo / hi) are dead after the entries kernel
+        uint32_t* run_incl = pl->cs[2].as<uint32_t>();
         p.stage_begin();
         pileup_compact_masks(n_col, o, os.d[8].as<uint32_t>(), os.d[9].as<uint64_t>(), pl->cs[0].as<uint32_t>(),
                              os.d[10].as<uint32_t>(), s, st);
+        pileup_position_runs_scan(n_col, o, run_flag, run_incl, s, st);
         p.stage_end(&p.stats.pileup_ms);
         PL_TRY(launch_copy_bytes(pl->h_small.p, os.d[10].as<uint32_t>() + n_col, 4, st));
+        PL_TRY(launch_copy_bytes(pl->h_small.as<uint32_t>() + 1, run_incl + (n_col - 1), 4, st));
         PL_TRY(cudaStreamSynchronize(st));
-        os.n_strag = *pl->h_small.as<uint32_t>();
+        os.n_strag = pl->h_small.as<uint32_t>()[0];
+        os.n_runs = pl->h_small.as<uint32_t>()[1];
         PL_TRY(os.d[11].ensure((size_t)os.n_strag * 4 + 64, st));
-        if (!p.r->opts.device_output) PL_TRY(os.h[10].ensure((size_t)os.n_strag * 4 + 64));
-        if (os.n_strag) {
-          p.stage_begin();
-          pileup_compact_stragglers(n_col, o, os.d[10].as<uint32_t>(), os.d[11].as<uint32_t>(), st);
-          p.stage_end(&p.stats.pileup_ms);
+        PL_TRY(os.d[12].ensure((size_t)os.n_strag * 4 + 64, st));
+        PL_TRY(os.d[13].ensure((size_t)os.n_runs * 8 + 64, st));
+        PL_TRY(os.d[14].ensure((size_t)(os.n_runs + 1) * 4 + 64, st));
+        if (!p.r->opts.device_output) {
+          PL_TRY(os.h[9].ensure((size_t)os.n_runs * 8 + 64));
+          PL_TRY(os.h[10].ensure((size_t)os.n_strag * 4 + 64));
+          PL_TRY(os.h[11].ensure((size_t)os.n_strag * 4 + 64));
+          PL_TRY(os.h[12].ensure((size_t)(os.n_runs + 1) * 4 + 64));
         }
+        p.stage_begin();
+        if (os.n_strag)
+          pileup_compact_stragglers(n_col, o, os.d[10].as<uint32_t>(), os.d[12].as<uint32_t>(), os.d[11].as<uint32_t>(), st);
+        pileup_position_runs_scatter(n_col, o, run_flag, run_incl, os.d[13].as<uint64_t>(), os.d[14].as<uint32_t>(), st);
+        p.stage_end(&p.stats.pileup_ms);
       }
       PL_TRY(cudaEventRecord(os.computed, st));
       // results to the host on the copy stream: overlaps with the carry kernels and the next batch
       if (!p.r->opts.device_output) {
         cudaStream_t cs = pl->copy_st;
         PL_TRY(cudaStreamWaitEvent(cs, os.computed, 0));
-        p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 +
-                             (counts_only ? (uint64_t)n_col * 24
-                                          : n_entries * (2 + (want_q ? 4 : 0)) +
-                                                (compact ? (uint64_t)n_col * 16 + 4 + (uint64_t)os.n_strag * 4 : n_entries * 4));
-        PL_TRY(cudaMemcpyAsync(os.h[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
-        PL_TRY(cudaMemcpyAsync(os.h[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, cs));
-        PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
-        if (counts_only) {
-          PL_TRY(cudaMemcpyAsync(os.h[6].p, o.counts, (size_t)n_col * 24, cudaMemcpyDeviceToHost, cs));
-        } else {
-          if (compact) {
-            PL_TRY(cudaMemcpyAsync(os.h[7].p, os.d[8].p, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
-            PL_TRY(cudaMemcpyAsync(os.h[8].p, os.d[9].p, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
-            PL_TRY(cudaMemcpyAsync(os.h[9].p, os.d[10].p, (size_t)(n_col + 1) * 4, cudaMemcpyDeviceToHost, cs));
-            if (os.n_strag)
-              PL_TRY(cudaMemcpyAsync(os.h[10].p, os.d[11].p, (size_t)os.n_strag * 4, cudaMemcpyDeviceToHost, cs));
-          } else {
-            PL_TRY(cudaMemcpyAsync(os.h[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+        if (compact) {
+          p.stats.d2h_bytes += (uint64_t)n_col * 16 + n_entries * (2 + (want_q ? 4 : 0)) + (uint64_t)os.n_strag * 8 +
+                               (uint64_t)os.n_runs * 12 + 4;
+          PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[7].p, os.d[8].p, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[8].p, os.d[9].p, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[9].p, os.d[13].p, (size_t)os.n_runs * 8, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[12].p, os.d[14].p, (size_t)(os.n_runs + 1) * 4, cudaMemcpyDeviceToHost, cs));
+          if (os.n_strag) {
+            PL_TRY(cudaMemcpyAsync(os.h[10].p, os.d[11].p, (size_t)os.n_strag * 4, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[11].p, os.d[12].p, (size_t)os.n_strag * 4, cudaMemcpyDeviceToHost, cs));
           }
           PL_TRY(cudaMemcpyAsync(os.h[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
           PL_TRY(cudaMemcpyAsync(os.h[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+        } else {
+          p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + (counts_only ? (uint64_t)n_col * 24 : n_entries * (6 + (want_q ? 4 : 0)));
+          PL_TRY(cudaMemcpyAsync(os.h[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
+          if (counts_only) {
+            PL_TRY(cudaMemcpyAsync(os.h[6].p, o.counts, (size_t)n_col * 24, cudaMemcpyDeviceToHost, cs));
+          } else {
+            PL_TRY(cudaMemcpyAsync(os.h[3].p, o.read_idx, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+          }
         }
         if (want_q) PL_TRY(cudaMemcpyAsync(os.h[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
         PL_TRY(cudaEventRecord(os.done, cs));
@@ -823,11 +844,15 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
         cols->counts = os.d[7].as<uint32_t>();
       } else if (pl->prm.compact_reads) {
-        cols->read_idx = nullptr;
+        cols->read_idx = nullptr; cols->position = nullptr; cols->col_off = nullptr;
         cols->last_read = os.d[8].as<uint32_t>();
         cols->live_mask = os.d[9].as<uint64_t>();
-        cols->strag_off = os.d[10].as<uint32_t>();
+        cols->n_stragglers = os.n_strag;
         cols->strag_idx = os.d[11].as<uint32_t>();
+        cols->strag_col = os.d[12].as<uint32_t>();
+        cols->n_runs = os.n_runs;
+        cols->run_pos = os.d[13].as<uint64_t>();
+        cols->run_first_col = os.d[14].as<uint32_t>();
       }
       return BIODB_OK;
     }
@@ -842,11 +867,15 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
       cols->counts = os.h[6].as<uint32_t>();
     } else if (pl->prm.compact_reads) {
-      cols->read_idx = nullptr;
+      cols->read_idx = nullptr; cols->position = nullptr; cols->col_off = nullptr;
       cols->last_read = os.h[7].as<uint32_t>();
       cols->live_mask = os.h[8].as<uint64_t>();
-      cols->strag_off = os.h[9].as<uint32_t>();
+      cols->n_stragglers = os.n_strag;
       cols->strag_idx = os.h[10].as<uint32_t>();
+      cols->strag_col = os.h[11].as<uint32_t>();
+      cols->n_runs = os.n_runs;
+      cols->run_pos = os.h[9].as<uint64_t>();
+      cols->run_first_col = os.h[12].as<uint32_t>();
     }
     return BIODB_OK;
   }

@@ -116,7 +116,11 @@ Pass::~Pass() {
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
   }
-  for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b})
+  if (h2d_st) {
+    cudaStreamSynchronize(h2d_st);
+    cudaStreamDestroy(h2d_st);
+  }
+  for (cudaEvent_t e : {ev_begin, ev_end, ev_a, ev_b, pf_done, comp_free[0], comp_free[1]})
     if (e) cudaEventDestroy(e);
   for (const Timed& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
   for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
@@ -178,6 +182,10 @@ biodb_status Pass::init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset) {
   CUDA_TRY(cudaEventCreate(&ev_end));
   CUDA_TRY(cudaEventCreate(&ev_a));
   CUDA_TRY(cudaEventCreate(&ev_b));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h2d_st, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&pf_done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&comp_free[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&comp_free[1], cudaEventDisableTiming));
   next_coffset = coffset;
   first_skip = uoffset;
   CUDA_TRY(h_result.ensure(64));
@@ -189,6 +197,8 @@ void Pass::rewind(uint64_t coffset, uint32_t uoffset) {
   stop_coffset = ~0ull;
   next_coffset = coffset;
   first_skip = uoffset;
+  pf_c0 = pf_c1 = 0;
+  if (h2d_st) cudaStreamSynchronize(h2d_st);
   supplier_done = false;
   memset(&pending, 0, sizeof pending);
   finished = false;
@@ -316,7 +326,27 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   const uint32_t* d_isize = d_cdata + nb;
   // ---- 3. device buffers -------------------------------------------------------------------------------
   const bool resident = r->d_file.p != nullptr;
-  if (!resident) CUDA_TRY(d_comp.ensure((size_t)(c1 - c0) + 256, st));
+  if (!resident && nb) {
+    if (pf_c1 && pf_c0 == c0) {
+      // the start of this batch was prefetched while the previous one was computed: switch buffers, wait for the copy
+      // and top up whatever the guess fell short of
+      comp_cur ^= 1;
+      CUDA_TRY(cudaStreamWaitEvent(st, pf_done, 0));
+      if ((size_t)(c1 - c0) + 256 > d_comp2[comp_cur].cap)
+        CUDA_TRY(d_comp2[comp_cur].ensure((size_t)(c1 - c0) + 256, st, (size_t)(pf_c1 - c0)));
+      if (pf_c1 < c1) {
+        CUDA_TRY(cudaMemcpyAsync(d_comp2[comp_cur].as<uint8_t>() + (pf_c1 - c0), r->file + pf_c1, (size_t)(c1 - pf_c1),
+                                 cudaMemcpyHostToDevice, st));
+        stats.h2d_bytes += c1 - pf_c1;
+      }
+    } else {
+      CUDA_TRY(cudaStreamSynchronize(h2d_st));     // a stale prefetch must not land later
+      CUDA_TRY(d_comp2[comp_cur].ensure((size_t)(c1 - c0) + 256, st));
+      CUDA_TRY(cudaMemcpyAsync(d_comp2[comp_cur].p, r->file + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+      stats.h2d_bytes += c1 - c0;
+    }
+    pf_c1 = 0;
+  }
   CUDA_TRY(d_u.ensure((size_t)u_len + 256, st));
   CUDA_TRY(d_status.ensure((size_t)nb * 8 + 16, st));      // statuses, then (verify_crc) the computed CRCs
   CUDA_TRY(h_status.ensure((size_t)nb * 8 + 16));
@@ -325,11 +355,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     CUDA_TRY(launch_copy_bytes(d_u.p, d_carry_tail.p, carry_tail_len, st));
   CUDA_TRY(cudaMemcpyAsync(d_tab.p, h_tab.p, tab_bytes, cudaMemcpyHostToDevice, st));
   if (nb) {
-    if (!resident) {
-      CUDA_TRY(cudaMemcpyAsync(d_comp.p, r->file + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
-      stats.h2d_bytes += c1 - c0;
-    }
-    const uint8_t* comp = resident ? r->d_file.as<uint8_t>() + c0 : d_comp.as<uint8_t>();
+    const uint8_t* comp = resident ? r->d_file.as<uint8_t>() + c0 : d_comp2[comp_cur].as<uint8_t>();
     InflateArgs ia{comp, d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb, WalkOut{}};
     if (!raw_mode) {
       // fused record-chain walk: the inflate warps follow the block_size chain of their own block
@@ -340,6 +366,24 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     stage_begin();
     CUDA_TRY(launch_inflate(ia, st));
     stage_end(&stats.inflate_ms);
+    if (!resident) {
+      CUDA_TRY(cudaEventRecord(comp_free[comp_cur], st));
+      // prefetch what follows: the next batch starts at c1 and is about as long as this one
+      const uint64_t lim = std::min<uint64_t>(r->flen, stop_coffset == ~0ull ? r->flen : stop_coffset + 65536 + 64);
+      if (!last_batch && c1 < lim) {
+        const uint64_t want = std::min<uint64_t>(lim - c1, (c1 - c0) + (c1 - c0) / 32 + 65536);
+        const int nxt = comp_cur ^ 1;
+        // the other buffer was last read by the inflate kernel of the previous batch, which precedes this batch's
+        // kernels on the compute stream
+        CUDA_TRY(cudaStreamWaitEvent(h2d_st, comp_free[nxt], 0));
+        CUDA_TRY(d_comp2[nxt].ensure((size_t)want + (want >> 4) + 65536 + 256, h2d_st));
+        CUDA_TRY(cudaMemcpyAsync(d_comp2[nxt].p, r->file + c1, (size_t)want, cudaMemcpyHostToDevice, h2d_st));
+        CUDA_TRY(cudaEventRecord(pf_done, h2d_st));
+        stats.h2d_bytes += want;
+        pf_c0 = c1;
+        pf_c1 = c1 + want;
+      }
+    }
     stats.inflate_launches += 1;
     stats.n_blocks += nb;
     stats.compressed_bytes += c1 - c0;

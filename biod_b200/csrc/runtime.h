@@ -94,7 +94,14 @@ struct Pass {
   PinBuf h_tab;                     // per-block tables (payload_off, out_off, cdata, isize, block_uoff)
   PinBuf h_status, h_result;
   // device
-  DevBuf d_comp, d_tab, d_status, d_u, d_carry_tail, d_ws, d_result;
+  DevBuf d_comp2[2], d_tab, d_status, d_u, d_carry_tail, d_ws, d_result;
+  // host->device prefetch of the next batch's compressed bytes (input not resident): while batch k is inflated out of
+  // d_comp2[cur], the bytes that follow it in the file go to d_comp2[cur^1] on their own stream
+  cudaStream_t h2d_st = nullptr;
+  cudaEvent_t pf_done = nullptr;       // the prefetch copy has landed
+  cudaEvent_t comp_free[2] = {nullptr, nullptr};   // the inflate kernel reading d_comp2[i] has finished
+  int comp_cur = 0;
+  uint64_t pf_c0 = 0, pf_c1 = 0;       // file range held by d_comp2[comp_cur^1] (pf_c1 == 0: none)
   DevBuf d_rec[10];                 // RecordArrays columns
   uint64_t rec_capacity = 0, cigar_capacity = 0;
   uint64_t rec_front = 0;           // slots reserved in front of the batch records (pileup carry)

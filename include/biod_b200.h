@@ -132,8 +132,8 @@ typedef struct biodb_pileup_params {
   uint64_t start_from;         /* pileup.d:482-489,497-504 (single_ref only) */
   uint64_t end_at;             /* pileup.d:505 (single_ref only); UINT64_MAX = none */
   int32_t counts_only;         /* 1 = per-column A,C,G,T,other,del counts instead of entries */
-  int32_t compact_reads;       /* 1 = return the reads of each column as last_read / live_mask / stragglers instead of
-                                  read_idx: 12 bytes per column instead of 4 bytes per entry cross PCIe */
+  int32_t compact_reads;       /* 1 = sequential compact encoding of the column table (position runs, read lists as
+                                  last_read / live_mask / stragglers): see biodb_column_batch */
   int32_t reserved[2];
 } biodb_pileup_params;
 
@@ -150,14 +150,23 @@ typedef struct biodb_column_batch {
   const uint8_t* qual;         /* [n_entries] current_base_quality (255 inside D/N)    pileup.d:127-134 */
   const uint32_t* query_offset;/* [n_entries] or NULL */
   const uint32_t* counts;      /* [n_columns*6] A,C,G,T,other,deletion — only with counts_only */
-  /* compact_reads: read_idx is NULL and the reads of column c, in column (= file) order, are
-   *   strag_idx[strag_off[c] .. strag_off[c+1])  — the few reads more than 63 records older than the column's last read,
-   *   then every d = 63..0 with bit d of live_mask[c] set: record index last_read[c] - d.
-   * (coverage 0: live_mask 0.)  base / qual / query_offset stay per entry, in the same order. */
-  const uint32_t* last_read;   /* [n_columns] */
-  const uint64_t* live_mask;   /* [n_columns] */
-  const uint32_t* strag_off;   /* [n_columns+1] */
-  const uint32_t* strag_idx;   /* [strag_off[n_columns]] */
+  /* compact_reads = 1: a sequential, lossless encoding of the same columns that moves 16 bytes per column + 2 bytes
+   * per entry over PCIe instead of 20 + 6.  position, col_off and read_idx are NULL and
+   *  - positions come as n_runs runs of consecutive positions: columns [run_first_col[r], run_first_col[r+1]) have
+   *    positions run_pos[r], run_pos[r]+1, ...  (one run per stretch of non-zero coverage);
+   *  - the reads of column c, in column (= file) order, are its stragglers — the entries k of strag_col[] / strag_idx[]
+   *    with strag_col[k] == c (sorted by column; reads more than 63 records older than the column's last read) —
+   *    followed by record index last_read[c] - d for every d = 63..0 with bit d of live_mask[c] set;
+   *  - coverage(c) = stragglers(c) + popcount(live_mask[c]); the entries of column c in base / qual / query_offset
+   *    start where those of column c-1 end (col_off is the running sum of the coverages). */
+  const uint32_t* last_read;     /* [n_columns] */
+  const uint64_t* live_mask;     /* [n_columns] */
+  uint64_t n_stragglers;
+  const uint32_t* strag_col;     /* [n_stragglers] */
+  const uint32_t* strag_idx;     /* [n_stragglers] */
+  uint64_t n_runs;
+  const uint64_t* run_pos;       /* [n_runs] */
+  const uint32_t* run_first_col; /* [n_runs+1] */
 } biodb_column_batch;
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);

@@ -415,4 +415,5 @@ def test_compact_read_lists_with_stragglers():
     for b in BamReader(data).column_batches(False, compact_reads=True, copy=True):
         assert b.compact is not None
         n_strag += len(b.compact[3])
+        assert len(b.compact[4]) >= 1 and b.compact[5][-1] == b.n_columns
     assert n_strag > 0
