@@ -213,3 +213,68 @@ def test_fast_path_takes_all_fixture_blocks():
     assert L.biodb_debug_inflate_counters(cnt, 1) == 0
     assert cnt[0] == 0, list(cnt)
     assert cnt[1] > 0 and cnt[2] >= cnt[1], list(cnt)
+
+
+def _random_payload(rng):
+    """A buffer of random structure: literal noise, small alphabets, repeats at random distances and lengths."""
+    out = bytearray()
+    target = int(rng.integers(1, 65537))
+    while len(out) < target:
+        kind = int(rng.integers(0, 6))
+        n = int(rng.integers(1, 4000))
+        if kind == 0:
+            out += rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif kind == 1:
+            k = int(rng.integers(1, 40))
+            out += rng.integers(0, k, n, dtype=np.uint8).tobytes()
+        elif kind == 2 and out:
+            d = int(rng.integers(1, min(len(out), 32768) + 1))
+            for _ in range(int(rng.integers(1, 30))):
+                ln = int(rng.integers(3, 300))
+                start = len(out) - d
+                for i in range(ln):
+                    out.append(out[start + i])
+        elif kind == 3:
+            out += bytes([int(rng.integers(0, 256))]) * n
+        elif kind == 4:
+            w = rng.integers(0, 256, int(rng.integers(2, 60)), dtype=np.uint8).tobytes()
+            out += (w * (n // len(w) + 1))[:n]
+        else:
+            out += (b"%d\t" % int(rng.integers(0, 10**9))) * (n // 8 + 1)
+    return bytes(out[:target])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_streams_match_zlib(seed):
+    """Seeded fuzz: ~250 random buffers x random zlib level / strategy / memLevel, valid and corrupted."""
+    rng = np.random.default_rng(1000 + seed)
+    payloads, isizes, expect = [], [], []
+    strategies = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED]
+    while len(payloads) < 250:
+        data = _random_payload(rng)
+        p = raw_deflate(data, int(rng.integers(0, 10)), strategies[int(rng.integers(0, 5))], int(rng.integers(1, 10)))
+        if len(p) > 65536:
+            continue
+        if rng.random() < 0.3:                      # corrupt it: flip a bit, cut it, or lie about ISIZE
+            what = int(rng.integers(0, 3))
+            isz = len(data)
+            if what == 0 and len(p):
+                b = bytearray(p)
+                b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+                p = bytes(b)
+            elif what == 1:
+                p = p[:int(rng.integers(0, len(p) + 1))]
+            else:
+                isz = max(0, len(data) + int(rng.integers(-3, 4)))
+            payloads.append(p)
+            isizes.append(isz)
+            expect.append(zlib_status(p, isz))
+        else:
+            payloads.append(p)
+            isizes.append(len(data))
+            expect.append((0, data))
+    outs, st, crc, cnt = dev_inflate(payloads, isizes, pad_front=int(rng.integers(0, 16)))
+    for i in range(len(payloads)):
+        assert int(st[i]) == expect[i][0], (seed, i, int(st[i]), expect[i][0], len(payloads[i]), isizes[i])
+        if expect[i][0] == 0:
+            assert outs[i] == expect[i][1], (seed, i)
