@@ -60,7 +60,7 @@ constexpr int LANE_CAP = 512;                  // a lane stops taking codes once
 constexpr int MLIST = BIODB_PAR_MLIST;         // matches one super-chunk may hold
 constexpr int LANE_MCAP = 32;                  // ... or this many matches (the next lane continues from there)
 constexpr int FLUSH_ALIGN = 128;
-constexpr int SUB_CAP = 320;                   // >= 308: most second-level entries a complete 286-symbol code needs past 10 bits
+constexpr int SUB_CAP = LIT_BITS >= 10 ? 320 : 352;   // most second-level entries a complete 286-symbol code needs: 308 past 10 bits, 340 past 9
 constexpr int STORE_PIECE = 1024;              // stored blocks are copied in pieces of this many bytes
 constexpr int HDR_BYTES = 640;                 // >= longest dynamic block header: 17 + 19*3 + 316*(7+7) bits = 563 bytes
 static_assert(LANE_CAP > SUB_BITS, "literals alone never reach the cap, so it is checked after matches only");
