@@ -297,6 +297,19 @@ def main():
                 "share_of_step": infl_ms / ms_per_step,
                 "stage_ms": {"inflate": float(infl_ms), "record_scan": float(np.mean([s[0].scan_ms for s in steps])),
                              "pileup": float(np.mean([s[0].pileup_ms for s in steps]))}}
+    # the two other stages against the same HBM peak (algorithmic bytes of SURVEY.md §8d / DESIGN.md §4: 283 B read +
+    # 32 B written per record; 239 B per record + 6 B per entry + 20 B per column)
+    scan_ms = float(np.mean([s[0].scan_ms for s in steps]))
+    pile_ms = float(np.mean([s[0].pileup_ms for s in steps]))
+    scan_bytes = 315.0 * n_rec
+    pile_bytes = 239.0 * n_rec + 6.0 * n_ent + 20.0 * n_col
+    roofline["other_stages"] = {
+        "record_scan": {"bound": "hbm", "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms else None, "unit": "GB/s",
+                        "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak if scan_ms else None,
+                        "algorithmic_bytes": scan_bytes, "ms": scan_ms},
+        "pileup": {"bound": "hbm", "achieved": pile_bytes / (pile_ms * 1e-3) / 1e9 if pile_ms else None, "unit": "GB/s",
+                   "frac": pile_bytes / (pile_ms * 1e-3) / 1e9 / peak if pile_ms else None,
+                   "algorithmic_bytes": pile_bytes, "ms": pile_ms}}
     line = {"metric": "pileup_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "u8",
