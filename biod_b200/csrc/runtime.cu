@@ -198,6 +198,7 @@ void Pass::rewind(uint64_t coffset, uint32_t uoffset) {
   next_coffset = coffset;
   first_skip = uoffset;
   pf_c0 = pf_c1 = 0;
+  pre_valid = false;
   if (h2d_st) cudaStreamSynchronize(h2d_st);
   supplier_done = false;
   memset(&pending, 0, sizeof pending);
@@ -244,6 +245,24 @@ uint64_t Pass::voffset_of(uint64_t x) const {
   return (s.coffset << 16) | (uint64_t)(s.within + (x - s.ustart));
 }
 
+// Host walk of the BSIZE chain: up to max_blocks block headers from next_coffset on (inputstream.d:54-199, 386-424).
+static void walk_headers(const biodb_reader* r, uint64_t stop_coffset, uint32_t max_blocks, std::vector<BlockInfo>& blocks,
+                         uint64_t& next_coffset, bool& supplier_done, biodb_error& pending) {
+  while (blocks.size() < max_blocks && !supplier_done && !pending.status) {
+    if (next_coffset >= stop_coffset) { supplier_done = true; break; }
+    BlockInfo b;
+    int rc = parse_bgzf_header(r->file, r->flen, next_coffset, &b, &pending);
+    if (rc < 0) break;
+    if (rc == 0 || b.isize == 0) { supplier_done = true; break; }     // EOF block ends the stream (inputstream.d:393-394)
+    if (b.isize > 65536) {                                             // block.d:150-152
+      set_error(&pending, BIODB_ERR_FORMAT, 0, b.coffset, "Uncompressed block size must be within 65536 bytes");
+      break;
+    }
+    blocks.push_back(b);
+    next_coffset = b.coffset + b.bsize + 1;
+  }
+}
+
 biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   n = n_cigar = 0;
   if (finished) {
@@ -266,19 +285,16 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   mark_begin();
   // ---- 1. walk the BSIZE chain on the host (18 bytes per block) ----------------------------------
   blocks.clear();
-  while (blocks.size() < max_blocks && !supplier_done && !pending.status) {
-    if (next_coffset >= stop_coffset) { supplier_done = true; break; }
-    BlockInfo b;
-    int rc = parse_bgzf_header(r->file, r->flen, next_coffset, &b, &pending);
-    if (rc < 0) break;
-    if (rc == 0 || b.isize == 0) { supplier_done = true; break; }     // EOF block ends the stream (inputstream.d:393-394)
-    if (b.isize > 65536) {                                             // block.d:150-152
-      set_error(&pending, BIODB_ERR_FORMAT, 0, b.coffset, "Uncompressed block size must be within 65536 bytes");
-      break;
-    }
-    blocks.push_back(b);
-    next_coffset = b.coffset + b.bsize + 1;
+  if (pre_valid && pre_max == max_blocks) {
+    // already walked while the previous batch was being inflated
+    blocks.swap(pre_blocks);
+    next_coffset = pre_next_coffset;
+    supplier_done = pre_supplier_done;
+    pending = pre_pending;
+  } else {
+    walk_headers(r, stop_coffset, max_blocks, blocks, next_coffset, supplier_done, pending);
   }
+  pre_valid = false;
   const uint32_t nb = (uint32_t)blocks.size();
   bool last_batch = supplier_done || pending.status != 0;
   if (nb == 0 && carry_tail_len == 0 && front_slots == 0) {
@@ -388,6 +404,16 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     stats.n_blocks += nb;
     stats.compressed_bytes += c1 - c0;
     stats.uncompressed_bytes += off - (has_carry ? carry_tail_len : 0);
+    if (!last_batch) {
+      // the GPU is busy for milliseconds now: walk the next batch's block headers meanwhile
+      pre_blocks.clear();
+      pre_next_coffset = next_coffset;
+      pre_supplier_done = supplier_done;
+      pre_pending = pending;
+      walk_headers(r, stop_coffset, max_blocks, pre_blocks, pre_next_coffset, pre_supplier_done, pre_pending);
+      pre_max = max_blocks;
+      pre_valid = true;
+    }
     const bool check_crc = r->opts.verify_crc != 0;
     if (check_crc) {
       CUDA_TRY(launch_crc32(d_u.as<uint8_t>(), d_outoff, d_isize, nb, d_status.as<uint32_t>() + nb, st));

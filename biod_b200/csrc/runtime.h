@@ -91,6 +91,13 @@ struct Pass {
   uint64_t n_records_total = 0;
   // host staging
   std::vector<BlockInfo> blocks;    // blocks of the current batch
+  // the BSIZE chain of the NEXT batch, walked on the host while the GPU inflates the current one
+  std::vector<BlockInfo> pre_blocks;
+  bool pre_valid = false;
+  uint32_t pre_max = 0;
+  uint64_t pre_next_coffset = 0;
+  bool pre_supplier_done = false;
+  biodb_error pre_pending{};
   PinBuf h_tab;                     // per-block tables (payload_off, out_off, cdata, isize, block_uoff)
   PinBuf h_status, h_result;
   // device
