@@ -28,6 +28,8 @@ CONFIGS = {
     # BASELINE.json configs[] index -> recipe
     2: dict(name="configs[1]: 100M-read synthetic BAM, 1 contig, 30x, 150bp, CIGAR 150M", reads=100_000_000, refs=1, mixed=0),
     3: dict(name="configs[2]: 100M-read synthetic BAM, 1 contig, 30x, mixed CIGAR (M/I/D/S/N, 5% indel)", reads=100_000_000, refs=1, mixed=1),
+    # configs[3] is 1 G reads (~130 GB compressed): pass --reads to scale it to what the box's /dev/shm holds
+    4: dict(name="configs[3]: 1G-read synthetic BAM, 24 contigs, 30x, mixed CIGAR", reads=1_000_000_000, refs=24, mixed=1),
 }
 
 
