@@ -193,6 +193,7 @@ constexpr int ENT_WARPS = 8;
 #define BIODB_CHUNK 32
 #endif
 constexpr int CHUNK = BIODB_CHUNK;   // columns per warp (<= 32)
+constexpr int CAND_CAP = 128;        // candidate reads gathered per round (a chunk with more takes several rounds)
 
 // 4-bit code -> IUPAC character without a memory lookup: "=ACMGRSV" "TWYHKDBN" packed little-endian (base.d:85)
 __device__ __forceinline__ uint32_t base_char(uint32_t code) {
@@ -288,18 +289,37 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
     return;
   }
   lo = lo ? lo - 1 : 0;
-  for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
-    const uint32_t j = j0 + lane;
+  // The candidate reads of the chunk — alive somewhere between its first and last position — are first gathered, in
+  // file order, into a per-warp list: [lo, hi) also holds reads that ended long ago and, with long N-skips, a few
+  // live reads hundreds of indices before the rest; walking that range 32 reads at a time would run the column loop
+  // for windows with one live lane.
+  __shared__ uint32_t s_list[ENT_WARPS][CAND_CAP];
+  uint32_t* list = s_list[threadIdx.x >> 5];
+  uint32_t jn = lo;
+  while (jn < hi) {
+   uint32_t n_cand = 0;
+   while (jn < hi && n_cand + 32 <= (uint32_t)CAND_CAP) {
+     const uint32_t j = jn + lane;
+     bool cand = false;
+     if (j < hi) {
+       const int32_t e = eend[j];
+       // a chunk may span several islands, so positions are not contiguous: test against its first / last position
+       cand = e != DEAD && e > p_first && v.pos[j] <= p_last;
+     }
+     const uint32_t b = __ballot_sync(0xffffffffu, cand);
+     if (cand) list[n_cand + __popc(b & lt)] = j;
+     n_cand += __popc(b);
+     jn += 32;
+   }
+   __syncwarp();
+   for (uint32_t w0 = 0; w0 < n_cand; w0 += 32) {
+    const bool cand = w0 + lane < n_cand;
+    const uint32_t j = cand ? list[w0 + lane] : 0;
     int32_t e = DEAD, pos = 0, lseq = 0;
     uint4 ri = make_uint4(0, 0, 0, 0);
-    if (j < hi) {
+    if (cand) {
       e = eend[j];
       pos = v.pos[j];
-    }
-    // a chunk may span several islands, so positions are not contiguous: test against its first / last position
-    bool cand = e != DEAD && pos <= p_last && e > p_first;
-    if (!__any_sync(0xffffffffu, cand)) continue;
-    if (cand) {
       ri = rinfo[j];
       lseq = v.l_seq[j];
     }
@@ -360,6 +380,8 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
         my_off += __popc(m);
       }
     }
+   }
+   __syncwarp();
   }
   if (COUNTS && lane < ncols)
     for (int q = 0; q < 6; ++q) o.counts[(size_t)(c0 + lane) * 6 + q] = cnt[q];
