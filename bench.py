@@ -152,6 +152,26 @@ def run_pass(L, capi, reader, shard=None, info=None, compact=False):
     return s, n_rec, nc.value, ne.value
 
 
+def run_reads_pass(L, capi, reader):
+    """One full BamReader.reads pass (inflate + record scan, no pileup).  Returns (stats, n_records)."""
+    it = C.c_void_p()
+    if L.biodb_reads_begin(reader, C.byref(it)) != capi.OK:
+        raise RuntimeError(L.biodb_last_error(reader).contents.message.decode())
+    rb = capi.RecordBatch()
+    n = 0
+    while True:
+        st = L.biodb_reads_next(it, C.byref(rb))
+        if st == capi.EOF:
+            break
+        if st != capi.OK:
+            raise RuntimeError(L.biodb_last_error(reader).contents.message.decode())
+        n += rb.n
+    s = capi.Stats()
+    L.biodb_reads_stats(it, C.byref(s))
+    L.biodb_reads_end(it)
+    return s, n
+
+
 def cpu_reference(args, cfg, threads):
     """Restated BioD CPU path (oracle) on a bounded prefix of the same workload."""
     from oracle import oracle as orc
@@ -347,6 +367,11 @@ def main():
         barrier()
         ex = run_pass(L, capi, rd, shard, compact=False)     # same pass with explicit read_idx lists, for comparison
         barrier()
+        rp = None
+        if world == 1:
+            # BamReader.reads alone: every record (raw bytes + field tables) delivered to host memory
+            run_reads_pass(L, capi, rd)
+            rp = run_reads_pass(L, capi, rd)
         L.biodb_close(rd)
         e_ms = sum(s[0].total_ms for s in es)
         te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
@@ -361,6 +386,11 @@ def main():
                                   "last_read, 64-bit window mask (+ stragglers); per entry base + qual",
                        "with_explicit_read_idx": {"ms_per_step": float(ex[0].total_ms), "d2h_bytes_per_step": int(ex[0].d2h_bytes),
                                                   "value": (tot_col / (float(ex[0].total_ms) * 1e-3)) if world == 1 else None}}
+        if rp is not None:
+            line["reads_pass_e2e"] = {"records_per_sec": rp[1] / (float(rp[0].total_ms) * 1e-3), "ms_per_step": float(rp[0].total_ms),
+                                      "h2d_bytes_per_step": int(rp[0].h2d_bytes), "d2h_bytes_per_step": int(rp[0].d2h_bytes),
+                                      "what": "BamReader.reads through the C ABI: raw record bytes + field / CIGAR tables of every "
+                                              "record copied to host memory (no pileup)"}
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----------------------------------------------
     if not args.no_cpu and rank == 0 and world == 1:

@@ -231,7 +231,9 @@ RecordArrays Pass::arrays(uint64_t front) const {
   return a;
 }
 
-uint64_t Pass::voffset_of(uint64_t x) const {
+uint64_t Pass::voffset_of(uint64_t x) const { return voffset_in(segs, x); }
+
+uint64_t voffset_in(const std::vector<Seg>& segs, uint64_t x) {
   // VirtualOffset (virtualoffset.d:43); an offset that is exactly a block end reports the next
   // block with uoffset 0 (inputstream.d:443-445,516-524).
   size_t lo = 0, hi = segs.size();
@@ -751,10 +753,93 @@ uint64_t biodb_file_size(const biodb_reader* r) { return r ? r->flen : 0; }
 
 // ------------------------------------------------------------------------------------- reads ----
 
+// BamReader.reads iterator.  Batches are read one ahead: while the caller works on batch k (host slot A), batch k+1 is
+// computed, copied device->device into a staging area (so that the pass may reuse its buffers for batch k+2 at once)
+// and from there to host slot B on a copy stream — the PCIe copy of one batch overlaps the kernels of the next.
+struct ReadsSlot {
+  PinBuf h_data, h_arr[10], h_vo[2];
+  cudaEvent_t done = nullptr;        // the device->host copies of this batch have landed
+  uint64_t n = 0, used = 0, n_cigar = 0, first = 0;
+  std::vector<Seg> segs;             // block provenance of the slice, for virtual offsets (readrange.d:55-66)
+};
 struct biodb_reads {
   Pass pass;
-  PinBuf h_data, h_arr[10], h_vo[2];
+  ReadsSlot slot[2];
+  int cur = 0;                       // slot the caller holds
+  bool inflight = false;             // slot[cur ^ 1] holds the batch read ahead
+  bool ahead_done = false;           // the read-ahead hit EOF / an error: ahead_status is returned after the batch in flight
+  biodb_status ahead_status = BIODB_OK;
+  DevBuf d_stage[11];                // device staging: data + the ten record arrays
+  cudaStream_t cs = nullptr;
+  cudaEvent_t computed = nullptr, staged = nullptr;
+  bool staged_valid = false;
+  ~biodb_reads() {
+    if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+    for (cudaEvent_t e : {computed, staged, slot[0].done, slot[1].done})
+      if (e) cudaEventDestroy(e);
+  }
+  void reset() {
+    if (cs) cudaStreamSynchronize(cs);
+    inflight = ahead_done = staged_valid = false;
+    ahead_status = BIODB_OK;
+  }
 };
+
+static const size_t REC_ESZ[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
+
+// Compute the next batch and start its copies into host slot s.  BIODB_OK, BIODB_EOF or the error met.
+static biodb_status reads_produce(biodb_reads* it, int s) {
+  Pass& p = it->pass;
+  if (!it->cs) {
+    if (cudaStreamCreateWithFlags(&it->cs, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&it->computed, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&it->staged, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&it->slot[0].done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&it->slot[1].done, cudaEventDisableTiming) != cudaSuccess)
+      return p.fail(BIODB_ERR_CUDA, 0, 0, "stream / event creation failed");
+  }
+  // the staging copy of the previous batch still reads the pass's buffers
+  if (it->staged_valid && cudaStreamWaitEvent(p.st, it->staged, 0) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "wait failed");
+  const uint64_t first = p.n_records_total;
+  biodb_status st;
+  do {
+    st = p.next((uint32_t)p.r->opts.blocks_per_batch, 0);
+  } while (st == BIODB_OK && p.n == 0 && !p.finished);   // a slice may hold only part of one huge record
+  if (st != BIODB_OK) return st;
+  if (p.n == 0) return p.next(1, 0);                      // finished: raises the pending error or EOF
+  ReadsSlot& sl = it->slot[s];
+  sl.n = p.n;
+  sl.used = p.tail;                                       // bytes of the slice covered by whole records
+  sl.n_cigar = p.n_cigar;
+  sl.first = first;
+  sl.segs = p.segs;
+  cudaStream_t cs = it->cs;
+  bool ok = cudaEventRecord(it->computed, p.st) == cudaSuccess && cudaStreamWaitEvent(cs, it->computed, 0) == cudaSuccess;
+  size_t bytes[11];
+  const void* src[11];
+  bytes[0] = (size_t)sl.used;
+  src[0] = p.d_u.p;
+  for (int a = 0; a < 9; ++a) { bytes[1 + a] = (size_t)(sl.n + (a == 8 ? 1 : 0)) * REC_ESZ[a]; src[1 + a] = p.d_rec[a].p; }
+  bytes[10] = (size_t)sl.n_cigar * 4;
+  src[10] = p.d_rec[9].p;
+  // device -> staging (ordered behind the previous batch's staging -> host copies on the same stream)
+  for (int k = 0; k < 11 && ok; ++k) {
+    ok = it->d_stage[k].ensure(bytes[k] + 16, cs) == cudaSuccess &&
+         (bytes[k] == 0 || cudaMemcpyAsync(it->d_stage[k].p, src[k], bytes[k], cudaMemcpyDeviceToDevice, cs) == cudaSuccess);
+  }
+  ok = ok && cudaEventRecord(it->staged, cs) == cudaSuccess;
+  it->staged_valid = true;
+  // staging -> host slot
+  for (int k = 0; k < 11 && ok; ++k) {
+    PinBuf& h = k == 0 ? sl.h_data : sl.h_arr[k - 1];
+    ok = h.ensure(bytes[k] + 16) == cudaSuccess &&
+         (bytes[k] == 0 || cudaMemcpyAsync(h.p, it->d_stage[k].p, bytes[k], cudaMemcpyDeviceToHost, cs) == cudaSuccess);
+  }
+  ok = ok && cudaEventRecord(sl.done, cs) == cudaSuccess;
+  if (!ok) return p.fail(BIODB_ERR_CUDA, 0, 0, "device to host copy failed");
+  p.stats.d2h_bytes += sl.used + sl.n * 44 + 8 + sl.n_cigar * 4;
+  return BIODB_OK;
+}
 
 extern "C" {
 
@@ -767,6 +852,7 @@ biodb_status biodb_reads_begin(biodb_reader* r, biodb_reads** out) {
     if (!r->reads_pool.empty()) {
       biodb_reads* it = (biodb_reads*)r->reads_pool.back();
       r->reads_pool.pop_back();
+      it->reset();
       it->pass.rewind(r->reads_start_coffset, r->reads_start_uoffset);
       *out = it;
       return BIODB_OK;
@@ -783,48 +869,49 @@ biodb_status biodb_reads_next(biodb_reads* it, biodb_record_batch* batch) {
   if (!it || !batch) return BIODB_ERR_ARG;
   Pass& p = it->pass;
   memset(batch, 0, sizeof *batch);
-  const uint64_t first = p.n_records_total;
-  biodb_status s;
-  do {
-    s = p.next((uint32_t)p.r->opts.blocks_per_batch, 0);
-  } while (s == BIODB_OK && p.n == 0 && !p.finished);   // a slice may hold only part of one huge record
-  if (s != BIODB_OK) return s;
-  if (p.n == 0) return p.next(1, 0);                      // finished: raises the pending error or EOF
-  const uint64_t n = p.n;
-  const uint64_t used = p.tail;                           // bytes of the slice covered by whole records
-  auto pull = [&](PinBuf& h, const void* d, size_t bytes) -> bool {
-    if (h.ensure(bytes + 16) != cudaSuccess) return false;
-    return cudaMemcpyAsync(h.p, d, bytes, cudaMemcpyDeviceToHost, p.st) == cudaSuccess;
-  };
-  static const size_t esz[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
-  bool ok = pull(it->h_data, p.d_u.p, (size_t)used);
-  for (int a = 0; a < 9 && ok; ++a) ok = pull(it->h_arr[a], p.d_rec[a].p, (size_t)(n + (a == 8 ? 1 : 0)) * esz[a]);
-  ok = ok && pull(it->h_arr[9], p.d_rec[9].p, (size_t)p.n_cigar * 4);
-  if (!ok || cudaStreamSynchronize(p.st) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "device to host copy failed");
-  p.stats.d2h_bytes += used + n * 44 + 8 + p.n_cigar * 4;
+  if (!it->inflight && !it->ahead_done) {                 // first call of the pass
+    biodb_status st = reads_produce(it, it->cur ^ 1);
+    if (st != BIODB_OK) { it->ahead_done = true; it->ahead_status = st; return st; }
+    it->inflight = true;
+  }
+  if (!it->inflight) return it->ahead_status;             // EOF / the error, again
+  const int s = it->cur ^ 1;                              // the batch to hand out now
+  bool next_inflight = false;
+  if (!it->ahead_done) {
+    // read ahead into the slot the caller has just released
+    biodb_status st = reads_produce(it, it->cur);
+    if (st == BIODB_OK) next_inflight = true;
+    else { it->ahead_done = true; it->ahead_status = st; }
+  }
+  ReadsSlot& sl = it->slot[s];
+  if (cudaEventSynchronize(sl.done) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "device to host copy failed");
+  it->cur = s;
+  it->inflight = next_inflight;
+  cudaStreamWaitEvent(p.st, sl.done, 0);                  // the pass's clock stops after the copies of what it handed out
   p.mark_end();
+  const uint64_t n = sl.n;
   batch->n = n;
-  batch->first_index = first;
-  batch->data = it->h_data.as<uint8_t>();
-  batch->data_len = used;
-  batch->rec_off = it->h_arr[0].as<uint64_t>();
-  batch->block_size = it->h_arr[1].as<int32_t>();
-  batch->ref_id = it->h_arr[2].as<int32_t>();
-  batch->pos = it->h_arr[3].as<int32_t>();
-  batch->end_pos = it->h_arr[4].as<int32_t>();
-  batch->bin_mq_nl = it->h_arr[5].as<uint32_t>();
-  batch->flag_nc = it->h_arr[6].as<uint32_t>();
-  batch->l_seq = it->h_arr[7].as<int32_t>();
-  batch->cigar_off = it->h_arr[8].as<uint64_t>();
-  batch->cigar = it->h_arr[9].as<uint32_t>();
+  batch->first_index = sl.first;
+  batch->data = sl.h_data.as<uint8_t>();
+  batch->data_len = sl.used;
+  batch->rec_off = sl.h_arr[0].as<uint64_t>();
+  batch->block_size = sl.h_arr[1].as<int32_t>();
+  batch->ref_id = sl.h_arr[2].as<int32_t>();
+  batch->pos = sl.h_arr[3].as<int32_t>();
+  batch->end_pos = sl.h_arr[4].as<int32_t>();
+  batch->bin_mq_nl = sl.h_arr[5].as<uint32_t>();
+  batch->flag_nc = sl.h_arr[6].as<uint32_t>();
+  batch->l_seq = sl.h_arr[7].as<int32_t>();
+  batch->cigar_off = sl.h_arr[8].as<uint64_t>();
+  batch->cigar = sl.h_arr[9].as<uint32_t>();
   if (p.r->opts.want_offsets) {
-    if (it->h_vo[0].ensure((size_t)n * 8 + 8) != cudaSuccess || it->h_vo[1].ensure((size_t)n * 8 + 8) != cudaSuccess)
+    if (sl.h_vo[0].ensure((size_t)n * 8 + 8) != cudaSuccess || sl.h_vo[1].ensure((size_t)n * 8 + 8) != cudaSuccess)
       return p.fail(BIODB_ERR_CUDA, 0, 0, "pinned allocation failed");
-    uint64_t* sv = it->h_vo[0].as<uint64_t>();
-    uint64_t* ev = it->h_vo[1].as<uint64_t>();
+    uint64_t* sv = sl.h_vo[0].as<uint64_t>();
+    uint64_t* ev = sl.h_vo[1].as<uint64_t>();
     for (uint64_t i = 0; i < n; ++i) {
-      sv[i] = p.voffset_of(batch->rec_off[i]);                                  // readrange.d:64-66
-      ev[i] = p.voffset_of(batch->rec_off[i] + 4 + (uint64_t)batch->block_size[i]);   // readrange.d:55-57
+      sv[i] = voffset_in(sl.segs, batch->rec_off[i]);                                  // readrange.d:64-66
+      ev[i] = voffset_in(sl.segs, batch->rec_off[i] + 4 + (uint64_t)batch->block_size[i]);   // readrange.d:55-57
     }
     batch->start_voffset = sv;
     batch->end_voffset = ev;
@@ -836,6 +923,7 @@ void biodb_reads_end(biodb_reads* it) {
   if (!it) return;
   biodb_reader* r = it->pass.r;
   if (it->pass.st) cudaStreamSynchronize(it->pass.st);
+  it->reset();
   {
     std::lock_guard<std::mutex> lk(r->pool_mu);
     if (r->reads_pool.size() < 2) { r->reads_pool.push_back(it); return; }

@@ -149,6 +149,7 @@ struct Pass {
   biodb_status fail(int status, int zerr, uint64_t off, const std::string& msg);
 };
 
+uint64_t voffset_in(const std::vector<Seg>& segs, uint64_t x);
 int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, BlockInfo* b, biodb_error* e);
 
 }  // namespace biodb
