@@ -23,6 +23,7 @@ import contrib.undead.stream : ReadException;
 import std.parallelism : TaskPool, taskPool;
 import std.string : toStringz;
 import std.conv : to;
+import std.range : InputRange, inputRangeObject;
 
 extern (C) nothrow @nogc {
     enum : int {
@@ -158,10 +159,7 @@ class GpuBamReader : IBamSamReader {
     string filename() @property const { return _filename; }
     auto reads(alias IteratePolicy = void)() @property { return GpuBamReadRange!false(_h, this); }
     auto readsWithOffsets() @property { return GpuBamReadRange!true(_h, this); }
-    std.range.InputRange!BamRead allReads() @property {
-        import std.range : inputRangeObject;
-        return inputRangeObject(reads());
-    }
+    InputRange!BamRead allReads() @property { return inputRangeObject(reads()); }
     void assumeSequentialProcessing() {}   // batches already reuse their buffer (reader.d:324)
     package biodb_reader* handle() { return _h; }
 }
