@@ -72,10 +72,18 @@ def synth_file(args, cfg, n_reads, rank, barrier):
     if rank == 0 and not os.path.exists(path):
         data = bamgen.generate(n_reads, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + args.config,
                                straddle=args.straddle)
-        tmp = path + ".tmp"
-        data.tofile(tmp)
-        os.replace(tmp, path)
         made = True
+        tmp = path + ".tmp"
+        try:
+            data.tofile(tmp)
+            os.replace(tmp, path)
+        except OSError:
+            # the cache directory cannot hold the file: one GPU works from memory, several need a shared file
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            if world_size() == 1:
+                return data, None, time.time() - t0, made
+            raise
         del data
     barrier()
     # N > 1: every rank maps the same file (one copy in the page cache); N = 1: a private copy that can be pinned
