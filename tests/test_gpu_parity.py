@@ -417,3 +417,14 @@ def test_compact_read_lists_with_stragglers():
         n_strag += len(b.compact[3])
         assert len(b.compact[4]) >= 1 and b.compact[5][-1] == b.n_columns
     assert n_strag > 0
+
+
+def test_sharded_pileup_with_compact_columns():
+    """Shards deliver the same columns in the compact encoding (what bench.py's e2e leg asks for at N > 1)."""
+    from gpu_util import gpu_pileup_sharded
+    from tools import bamgen
+    data = bamgen.generate(50000, 2, True, level=6, threads=4).tobytes()
+    o = orc.Bam(data).decode()
+    g = gpu_pileup_sharded(data, 3, halo_blocks=4, blocks_per_batch=8, compact_reads=True)
+    assert g["halo_ok"]
+    assert_pileup_equal(g, o.pileup_columns())
