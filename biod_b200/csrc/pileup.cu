@@ -197,8 +197,10 @@ constexpr int CAND_CAP = 128;        // candidate reads gathered per round (a ch
 
 // 4-bit code -> IUPAC character without a memory lookup: "=ACMGRSV" "TWYHKDBN" packed little-endian (base.d:85)
 __device__ __forceinline__ uint32_t base_char(uint32_t code) {
-  const uint64_t t = (code & 8) ? 0x4E42444B48595754ull : 0x565352474D43413Dull;
-  return (uint32_t)(t >> ((code & 7) * 8)) & 0xFF;
+  // two byte permutes over the 8-byte halves of the table, selected by bit 3 of the code
+  const uint32_t lo = __byte_perm(0x4D43413Du, 0x56535247u, code & 7);     // "=ACM" "GRSV"
+  const uint32_t hi = __byte_perm(0x48595754u, 0x4E42444Bu, code & 7);     // "TWYH" "KDBN"
+  return ((code & 8) ? hi : lo) & 0xFF;
 }
 
 // CIGAR cursor of a read at reference offset k from its position (PileupRead ctor + k x incrementPosition,
@@ -262,7 +264,7 @@ __device__ __forceinline__ Entry cursor_eval(Cursor& c, const uint8_t* cg, uint3
 // taken 32 at a time, one per lane, their cursor data loaded ONCE; then for every column of the chunk the lanes
 // whose read is live there are balloted, ranked (popc of lower lanes = file order, pileup.d:351-359,381-383)
 // and write read_idx / base / qual at consecutive slots.
-template <bool COUNTS>
+template <bool COUNTS, bool WANT_Q>
 __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, const int32_t* __restrict__ eend,
                                                                  const uint4* __restrict__ rinfo, ColumnScratch c,
                                                                  ColumnOutput o, uint32_t n_col, int32_t* info) {
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
           o.read_idx[slot] = ri.w;
           o.base[slot] = (uint8_t)base;
           o.qual[slot] = (uint8_t)qual;
-          if (o.qoff) o.qoff[slot] = qoff;
+          if (WANT_Q) o.qoff[slot] = qoff;
         }
       }
       if (COUNTS) {
@@ -564,8 +566,9 @@ void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnS
   if (n_col == 0) return;
   uint32_t warps = (n_col + CHUNK - 1) / CHUNK;
   uint32_t grid = (warps + ENT_WARPS - 1) / ENT_WARPS;
-  if (o.counts) entries_kernel<true><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
-  else entries_kernel<false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
+  if (o.counts) entries_kernel<true, false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
+  else if (o.qoff) entries_kernel<false, true><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
+  else entries_kernel<false, false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
   ++g_kernel_launches;
 }
 
