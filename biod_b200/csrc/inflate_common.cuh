@@ -173,7 +173,7 @@ __device__ __noinline__ int build_table(const uint8_t* lens, int n, uint16_t* lu
 // get one sub-table of 2^r entries (r = longest such code - PB); the first-level slot then holds
 // K_SPECIAL | r << 12 | offset/2 and the decoder indexes the sub-table with the next r bits.  Canonical codes sorted by
 // (length, symbol) are also sorted by value when left-aligned, so the codes of one sub-table are neighbours in
-// `sorted`.  Codes that do not fit the pool keep ENT_SLOW (slow_decode).
+// `sorted`.  Returns 2 when the pool is too small (the caller then gives the block to the warp-serial kernel).
 template <int PB>
 __device__ __noinline__ int build_table_par(const uint8_t* lens, int n, uint16_t* lut, uint16_t* sorted, Code* code,
                                             int kind, int lane, uint32_t* scratch, uint16_t* sub = nullptr,
@@ -271,6 +271,7 @@ __device__ __noinline__ int build_table_par(const uint8_t* lens, int n, uint16_t
       alloc = __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
+    if (alloc > (uint32_t)sub_cap) return 2;              // pool too small: cannot happen for a complete code of <= 286 symbols
     for (int k0 = k_begin; k0 < k_end; k0 += 32) {        // pass 2: every long code fills its slots of its sub-table
       const int k = k0 + lane;
       if (k < k_end) {

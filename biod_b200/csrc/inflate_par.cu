@@ -70,6 +70,7 @@ static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= STORE_PIECE 
                   (NCH - 1) * CH >= SUPER_BYTES + 32 && CH % 16 == 0,
               "staging ring too small");
 static_assert(STORE_PIECE <= OUT_BUDGET, "");
+static_assert(MLIST * 6 >= 288 * 2 + 352, "the match list lives where the table-building scratch was");
 
 // lane stop reasons
 constexpr uint32_t F_EOB = 1, F_ERR = 2, F_INEND = 3;
@@ -79,12 +80,18 @@ struct __align__(16) ParSmem {
   uint8_t out_ring[POUT];
   uint16_t lut_lit[1 << LIT_BITS];
   uint16_t lut_dist[1 << DIST_BITS];   // also hosts the 128-entry code-length LUT
-  uint16_t sorted_lit[288];
   uint16_t sorted_dist[32];
   Code code_lit, code_dist;
-  uint8_t lens[352];                   // [0,19) code-length code, [32,32+316) litlen+dist lengths
-  uint32_t m_ld[MLIST];                // matches of the super-chunk: (length-3) | (distance-1) << 8
-  uint16_t m_pos[MLIST];               //   and their block-relative output offset
+  union {                              // table building and decoding never overlap in time:
+    struct {
+      uint16_t sorted_lit[288];        //   literal/length symbols in canonical order (build_table_par only)
+      uint8_t lens[352];               //   [0,19) code-length code, [32,32+316) litlen+dist lengths
+    };
+    struct {
+      uint32_t m_ld[MLIST];            //   matches of the super-chunk: (length-3) | (distance-1) << 8
+      uint16_t m_pos[MLIST];           //   and their block-relative output offset
+    };
+  };
   uint32_t auxtab[64];                 // [0,32) length symbol, [32,64) distance symbol -> base | extra bits << 16
   uint32_t scratch[16];                // build_table_par
   uint16_t sub_lit[SUB_CAP];           // second-level tables of the literal/length codes longer than LIT_BITS
@@ -131,9 +138,8 @@ __device__ __forceinline__ void lane_decode(const ParCtx& c, bool active, uint32
     if (run && (e & (3u << 8)) == (K_SPECIAL << 8)) {      // rare: code longer than the LUT index, or invalid
       if (e >> 12)                                         // second-level table of the literal/length code
         e = lds16(c.subl + ((((e & 0xff) << 1) + ((bits >> LIT_BITS) & ~(0xffffffffu << (e >> 12)))) << 1));
-      else if (e == ENT_SLOW)
-        e = st ? slow_decode<DIST_BITS>(bits, c.code_dist, c.sorted_dist, KIND_DIST)
-               : slow_decode<LIT_BITS>(bits, c.code_lit, c.sorted_lit, KIND_LITLEN);
+      else if (e == ENT_SLOW && st)                        // (every long literal/length code has a second-level table)
+        e = slow_decode<DIST_BITS>(bits, c.code_dist, c.sorted_dist, KIND_DIST);
       if ((e & (3u << 8)) == (K_SPECIAL << 8)) {
         fl = F_ERR;
         run = 0;
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
       __syncwarp();
       r = build_table_par<LIT_BITS>(s->lens + 32, hlit, s->lut_lit, s->sorted_lit, &s->code_lit, KIND_LITLEN, lane, s->scratch,
                                     s->sub_lit, SUB_CAP);
-      if (r < 0) { status = STATUS_RETRY; break; }
+      if (r != 0) { status = STATUS_RETRY; break; }
       r = build_table_par<DIST_BITS>(s->lens + 32 + hlit, hdist, s->lut_dist, s->sorted_dist, &s->code_dist, KIND_DIST, lane, s->scratch);
       if (r < 0) { status = STATUS_RETRY; break; }
     }
