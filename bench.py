@@ -346,7 +346,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "reads_per_gpu": n_rec, "positions_per_gpu": n_col, "entries_per_gpu": n_ent,
                        "total_reads": tot_rec, "total_positions": tot_col, "halo_check_passed": halo_ok,
-                       "compressed_bytes": int(data.size), "blocks_per_batch": args.blocks_per_batch or "library default: 3 full waves of the inflate kernel (7992 on a B200)",
+                       "compressed_bytes": int(data.size), "blocks_per_batch": args.blocks_per_batch or "library default: 3 full waves of the inflate kernel (8436 on a B200)",
                        "cache": "inputs larger than L2: 12 GB compressed / 28 GB inflated per pass vs 126 MB L2",
                        "parallelism": ("1 GPU, whole file" if world == 1 else
                                        f"{world} block-range shards of ONE file (one per GPU, halo of 8 blocks, no data-path "

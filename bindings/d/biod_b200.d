@@ -54,6 +54,7 @@ extern (C) nothrow @nogc {
         // compact_reads: position, col_off and read_idx are null; see include/biod_b200.h for the sequential encoding
         const(uint)* last_read; const(ulong)* live_mask; ulong n_stragglers; const(uint)* strag_col; const(uint)* strag_idx;
         ulong n_runs; const(ulong)* run_pos; const(uint)* run_first_col;
+        const(ubyte)* base4; ulong n_special; const(uint)* special_entry; const(ubyte)* special_base;
     }
     void biodb_default_options(biodb_options*);
     int biodb_open(const(char)* path, const(biodb_options)*, biodb_reader**);
@@ -172,7 +173,7 @@ struct GpuPileupColumn {
     // where this column sits in the per-entry arrays and in the straggler list; filled by GpuPileup, which walks the
     // columns in order (the compact encoding of a batch is sequential: see include/biod_b200.h)
     private ulong _pos;
-    private size_t _off, _cov, _sk, _ns;
+    private size_t _off, _cov, _sk, _ns, _sp;
     ulong position() @property const { return _pos; }
     int ref_id() @property const { return _b.ref_id; }
     size_t coverage() @property const { return _cov; }
@@ -190,7 +191,20 @@ struct GpuPileupColumn {
         auto r = reads;
         return r[$ - _b.n_starting_here[_c] .. $];
     }
-    const(char)[] bases() @property const { return cast(const(char)[])_b.base[_off .. _off + _cov]; }
+    /// Bases of the column's reads (pileup.d:277-279).  The compact encoding packs them two per byte and lists the
+    /// entries that are not a base ('-' in a deletion, 0 past l_seq) apart; `_sp` is the cursor into that list.
+    const(char)[] bases() @property const {
+        if (_b.base !is null) return cast(const(char)[])_b.base[_off .. _off + _cov];
+        auto r = new char[_cov];
+        size_t sp = _sp;
+        foreach (k; 0 .. _cov) {
+            auto e = _off + k;
+            if (sp < _b.n_special && _b.special_entry[sp] == e) { r[k] = cast(char)_b.special_base[sp++]; continue; }
+            auto b = _b.base4[e >> 1];
+            r[k] = "=ACMGRSVTWYHKDBN"[(e & 1) ? (b & 15) : (b >> 4)];
+        }
+        return r;
+    }
     const(ubyte)[] base_qualities() @property const { return _b.qual[_off .. _off + _cov]; }
 }
 
@@ -220,6 +234,7 @@ struct GpuPileup {
         if (++_c >= _b.n_columns) { fetch(); return; }
         _col._off += _col._cov;
         _col._sk += _col._ns;
+        while (_col._sp < _b.n_special && _b.special_entry[_col._sp] < _col._off) ++_col._sp;
         place();
     }
     // cursors of column _c, given those of column _c - 1

@@ -59,7 +59,8 @@ class ColumnBatch(C.Structure):
                 ("last_of_pileup", C.c_int32), ("position", u64p), ("col_off", u64p), ("n_starting_here", u32p),
                 ("read_idx", u32p), ("base", u8p), ("qual", u8p), ("query_offset", u32p), ("counts", u32p),
                 ("last_read", u32p), ("live_mask", u64p), ("n_stragglers", C.c_uint64), ("strag_col", u32p), ("strag_idx", u32p),
-                ("n_runs", C.c_uint64), ("run_pos", u64p), ("run_first_col", u32p)]
+                ("n_runs", C.c_uint64), ("run_pos", u64p), ("run_first_col", u32p),
+                ("base4", u8p), ("n_special", C.c_uint64), ("special_entry", u32p), ("special_base", u8p)]
 
 
 _lib = None

@@ -371,7 +371,18 @@ class ColumnBatch:
             self.position = g(_np(cb.position, nc, np.uint64))
             self.col_off = g(_np(cb.col_off, nc + 1, np.uint64))
             self.read_idx = g(_np(cb.read_idx, ne, np.uint32)) if cb.read_idx else np.zeros(0, dtype=np.uint32)
-        self.base = g(_np(cb.base, ne, np.uint8))
+        if cb.base4 and not cb.base:
+            # compact_reads: bases two per byte + the few entries that are not a base
+            b4 = _np(cb.base4, (ne + 1) // 2, np.uint8)
+            codes = np.empty(2 * len(b4), dtype=np.uint8)
+            codes[0::2] = b4 >> 4
+            codes[1::2] = b4 & 15
+            self.base = BASE_CHARS[codes[:ne]]
+            nsp = int(cb.n_special)
+            if nsp:
+                self.base[_np(cb.special_entry, nsp, np.uint32).astype(np.int64)] = _np(cb.special_base, nsp, np.uint8)
+        else:
+            self.base = g(_np(cb.base, ne, np.uint8))
         self.qual = g(_np(cb.qual, ne, np.uint8))
         self.query_offset = g(_np(cb.query_offset, ne, np.uint32)) if cb.query_offset else None
         self.counts = g(_np(cb.counts, nc * 6, np.uint32)).reshape(nc, 6) if cb.counts else None

@@ -428,6 +428,56 @@ __global__ void compact_strag_kernel(const uint64_t* __restrict__ col_off, const
   }
 }
 
+// Bases of the column entries, two per byte (4-bit codes of "=ACMGRSVTWYHKDBN", first entry in the high nibble — the
+// packing of BAM's own SEQ field, read.d:364-383).  The two byte values that are not a base — '-' inside a deletion /
+// reference skip, 0 for a base asked past l_seq — become code 0 and are listed apart ("special" entries): pass 1
+// packs and counts them per thread block, pass 2 (only when there are any) writes the list in entry order.
+__device__ __forceinline__ uint32_t base_code(uint32_t ch) {
+  // (ch & 31) is unique over the 16 IUPAC characters (= A B C D G H K M N R S T V W Y -> 29 1 2 3 4 7 8 11 13 14 18 19
+  // 20 22 23 25): nibble k of lo (k < 16) / nibble k-16 of hi holds the code of the character with (ch & 31) == k
+  const uint64_t lo = 0xf30c00b400d2e10ull, hi = 0xa097086500ull;
+  const uint32_t k = ch & 31;
+  return (uint32_t)(((k & 16) ? hi : lo) >> ((k & 15) * 4)) & 15;
+}
+constexpr int PACK_THREADS = 256;
+__global__ void __launch_bounds__(PACK_THREADS) pack_base_kernel(const uint8_t* __restrict__ base, uint64_t n_entries,
+                                                                 uint8_t* base4, uint32_t* block_special) {
+  const uint64_t i = (uint64_t)blockIdx.x * PACK_THREADS + threadIdx.x;     // entries 2i, 2i+1
+  uint32_t nsp = 0;
+  if (2 * i < n_entries) {
+    const uint32_t b0 = base[2 * i];
+    const uint32_t b1 = 2 * i + 1 < n_entries ? base[2 * i + 1] : 'N';
+    const bool s0 = b0 == '-' || b0 == 0, s1 = 2 * i + 1 < n_entries && (b1 == '-' || b1 == 0);
+    base4[i] = (uint8_t)(((s0 ? 0 : base_code(b0)) << 4) | ((s1 || 2 * i + 1 >= n_entries) ? 0 : base_code(b1)));
+    nsp = (s0 ? 1u : 0u) + (s1 ? 1u : 0u);
+  }
+  __shared__ uint32_t total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  if (nsp) atomicAdd(&total, nsp);
+  __syncthreads();
+  if (threadIdx.x == 0) block_special[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(PACK_THREADS) special_scatter_kernel(const uint8_t* __restrict__ base, uint64_t n_entries,
+                                                                       const uint32_t* __restrict__ block_off,
+                                                                       uint32_t* special_entry, uint8_t* special_base) {
+  const uint32_t n_here = block_off[blockIdx.x + 1] - block_off[blockIdx.x];
+  if (n_here == 0) return;
+  // rare path: thread 0 of a block that has special entries walks its 512 entries in order
+  if (threadIdx.x != 0) return;
+  uint32_t out = block_off[blockIdx.x];
+  const uint64_t e0 = (uint64_t)blockIdx.x * PACK_THREADS * 2;
+  const uint64_t e1 = e0 + PACK_THREADS * 2 < n_entries ? e0 + PACK_THREADS * 2 : n_entries;
+  for (uint64_t e = e0; e < e1; ++e) {
+    const uint32_t b = base[e];
+    if (b == '-' || b == 0) {
+      special_entry[out] = (uint32_t)e;
+      special_base[out] = (uint8_t)b;
+      ++out;
+    }
+  }
+}
+
 // Column positions as runs of consecutive positions (one run per stretch of non-zero coverage, usually one per batch)
 __global__ void run_flag_kernel(const uint64_t* __restrict__ col_pos, uint32_t n_col, uint32_t* flag) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -583,6 +633,25 @@ void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_
 void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_col,
                                uint32_t* strag_idx, cudaStream_t st) {
   launch1d(compact_strag_kernel, n_col, st, o.col_off, o.read_idx, n_col, strag_off, strag_col, strag_idx);
+}
+
+// Packed bases: pass 1 (base4 + special counts per block, then their exclusive scan: block_off[n_blocks] = total).
+uint32_t pileup_pack_blocks(uint64_t n_entries) { return (uint32_t)((n_entries + 2 * PACK_THREADS - 1) / (2 * PACK_THREADS)); }
+void pileup_pack_bases(uint64_t n_entries, const uint8_t* base, uint8_t* base4, uint32_t* block_special, uint32_t* block_off,
+                       GroupScratch& s, uint32_t* scan_tmp, cudaStream_t st) {
+  const uint32_t nb = pileup_pack_blocks(n_entries);
+  if (nb == 0) return;
+  pack_base_kernel<<<nb, PACK_THREADS, 0, st>>>(base, n_entries, base4, block_special);
+  ++g_kernel_launches;
+  cudaMemsetAsync(block_special + nb, 0, 4, st);
+  device_scan<false>(block_special, block_off, (uint64_t)nb + 1, scan_tmp, OpAdd(), 0u, st);
+}
+void pileup_pack_specials(uint64_t n_entries, const uint8_t* base, const uint32_t* block_off, uint32_t* special_entry,
+                          uint8_t* special_base, cudaStream_t st) {
+  const uint32_t nb = pileup_pack_blocks(n_entries);
+  if (nb == 0) return;
+  special_scatter_kernel<<<nb, PACK_THREADS, 0, st>>>(base, n_entries, block_off, special_entry, special_base);
+  ++g_kernel_launches;
 }
 
 // Position runs: flag + inclusive scan (n_runs = incl[n_col-1], read by the host after a sync), then the scatter.

@@ -95,6 +95,11 @@ void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_
                           uint32_t* strag_off, GroupScratch& s, cudaStream_t st);
 void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_col,
                                uint32_t* strag_idx, cudaStream_t st);
+uint32_t pileup_pack_blocks(uint64_t n_entries);
+void pileup_pack_bases(uint64_t n_entries, const uint8_t* base, uint8_t* base4, uint32_t* block_special, uint32_t* block_off,
+                       GroupScratch& s, uint32_t* scan_tmp, cudaStream_t st);
+void pileup_pack_specials(uint64_t n_entries, const uint8_t* base, const uint32_t* block_off, uint32_t* special_entry,
+                          uint8_t* special_base, cudaStream_t st);
 void pileup_position_runs_scan(uint32_t n_col, const ColumnOutput& o, uint32_t* flag, uint32_t* incl, GroupScratch& s,
                                cudaStream_t st);
 void pileup_position_runs_scatter(uint32_t n_col, const ColumnOutput& o, const uint32_t* flag, const uint32_t* incl,

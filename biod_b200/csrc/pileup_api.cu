@@ -36,11 +36,11 @@ struct CarryBufs {
 // asynchronous copy on the copy stream.  Two sets alternate so that batch k+1 is computed and copied while
 // the caller still reads batch k.
 struct OutSet {
-  DevBuf d[15];     // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts, last_read, live_mask, strag_off,
-                    // strag_idx, strag_col, run_pos, run_first_col
-  PinBuf h[13];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, run_pos,
-                    // strag_idx, strag_col, run_first_col
-  uint32_t n_strag = 0, n_runs = 0;
+  DevBuf d[20];     // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts, last_read, live_mask, strag_off,
+                    // strag_idx, strag_col, run_pos, run_first_col, base4, block_special, block_off, special_entry, special_base
+  PinBuf h[16];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, run_pos,
+                    // strag_idx, strag_col, run_first_col, base4, special_entry, special_base
+  uint32_t n_strag = 0, n_runs = 0, n_special = 0;
   size_t col_cap = 0, ent_cap = 0;
   cudaEvent_t computed = nullptr, done = nullptr;
 };
@@ -71,6 +71,7 @@ struct biodb_pileup {
   uint64_t index_bias = 0;           // records of the halo: read_idx counts from the shard's first own record
   uint64_t tail_coffset = 0;         // first block of the shard's last `halo_blocks` blocks
   DevBuf d_maxend;                   // [2] int32 maxima + u64 scratch
+  DevBuf pack_tmp;                   // scan scratch of the base packing (compact_reads)
   // single_ref state
   bool started = false, done = false;
   int32_t target_ref = -1;
@@ -705,6 +706,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       p.stage_end(&p.stats.pileup_ms);
       os.n_strag = 0;
       os.n_runs = 0;
+      os.n_special = 0;
       if (compact) {
         // sequential compact encoding (include/biod_b200.h): read lists as last read + window mask + stragglers
         // (compact_mask_kernel), positions as runs of consecutive positions (run_flag_kernel)
@@ -721,12 +723,29 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         pileup_compact_masks(n_col, o, os.d[8].as<uint32_t>(), os.d[9].as<uint64_t>(), pl->cs[0].as<uint32_t>(),
                              os.d[10].as<uint32_t>(), s, st);
         pileup_position_runs_scan(n_col, o, run_flag, run_incl, s, st);
+        // bases two per byte + the list of entries that are not a base ('-' in D / N, 0 past l_seq)
+        const uint32_t npb = pileup_pack_blocks(n_entries);
+        PL_TRY(os.d[15].ensure((size_t)(n_entries + 1) / 2 + 64, st));
+        PL_TRY(os.d[16].ensure((size_t)(npb + 2) * 4, st));
+        PL_TRY(os.d[17].ensure((size_t)(npb + 2) * 4, st));
+        PL_TRY(pl->pack_tmp.ensure((scan_temp_elems((uint64_t)npb + 2) + 8) * 4, st));
+        if (!p.r->opts.device_output) PL_TRY(os.h[13].ensure((size_t)(n_entries + 1) / 2 + 64));
+        pileup_pack_bases(n_entries, o.base, os.d[15].as<uint8_t>(), os.d[16].as<uint32_t>(), os.d[17].as<uint32_t>(), s,
+                          pl->pack_tmp.as<uint32_t>(), st);
         p.stage_end(&p.stats.pileup_ms);
         PL_TRY(launch_copy_bytes(pl->h_small.p, os.d[10].as<uint32_t>() + n_col, 4, st));
         PL_TRY(launch_copy_bytes(pl->h_small.as<uint32_t>() + 1, run_incl + (n_col - 1), 4, st));
+        if (npb) PL_TRY(launch_copy_bytes(pl->h_small.as<uint32_t>() + 2, os.d[17].as<uint32_t>() + npb, 4, st));
         PL_TRY(cudaStreamSynchronize(st));
         os.n_strag = pl->h_small.as<uint32_t>()[0];
         os.n_runs = pl->h_small.as<uint32_t>()[1];
+        os.n_special = npb ? pl->h_small.as<uint32_t>()[2] : 0;
+        PL_TRY(os.d[18].ensure((size_t)os.n_special * 4 + 64, st));
+        PL_TRY(os.d[19].ensure((size_t)os.n_special + 64, st));
+        if (!p.r->opts.device_output) {
+          PL_TRY(os.h[14].ensure((size_t)os.n_special * 4 + 64));
+          PL_TRY(os.h[15].ensure((size_t)os.n_special + 64));
+        }
         PL_TRY(os.d[11].ensure((size_t)os.n_strag * 4 + 64, st));
         PL_TRY(os.d[12].ensure((size_t)os.n_strag * 4 + 64, st));
         PL_TRY(os.d[13].ensure((size_t)os.n_runs * 8 + 64, st));
@@ -741,6 +760,8 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         if (os.n_strag)
           pileup_compact_stragglers(n_col, o, os.d[10].as<uint32_t>(), os.d[12].as<uint32_t>(), os.d[11].as<uint32_t>(), st);
         pileup_position_runs_scatter(n_col, o, run_flag, run_incl, os.d[13].as<uint64_t>(), os.d[14].as<uint32_t>(), st);
+        if (os.n_special)
+          pileup_pack_specials(n_entries, o.base, os.d[17].as<uint32_t>(), os.d[18].as<uint32_t>(), os.d[19].as<uint8_t>(), st);
         p.stage_end(&p.stats.pileup_ms);
       }
       PL_TRY(cudaEventRecord(os.computed, st));
@@ -749,8 +770,8 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         cudaStream_t cs = pl->copy_st;
         PL_TRY(cudaStreamWaitEvent(cs, os.computed, 0));
         if (compact) {
-          p.stats.d2h_bytes += (uint64_t)n_col * 16 + n_entries * (2 + (want_q ? 4 : 0)) + (uint64_t)os.n_strag * 8 +
-                               (uint64_t)os.n_runs * 12 + 4;
+          p.stats.d2h_bytes += (uint64_t)n_col * 16 + n_entries + (n_entries + 1) / 2 + n_entries * (want_q ? 4 : 0) +
+                               (uint64_t)os.n_strag * 8 + (uint64_t)os.n_runs * 12 + 4 + (uint64_t)os.n_special * 5;
           PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
           PL_TRY(cudaMemcpyAsync(os.h[7].p, os.d[8].p, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
           PL_TRY(cudaMemcpyAsync(os.h[8].p, os.d[9].p, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
@@ -760,7 +781,11 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
             PL_TRY(cudaMemcpyAsync(os.h[10].p, os.d[11].p, (size_t)os.n_strag * 4, cudaMemcpyDeviceToHost, cs));
             PL_TRY(cudaMemcpyAsync(os.h[11].p, os.d[12].p, (size_t)os.n_strag * 4, cudaMemcpyDeviceToHost, cs));
           }
-          PL_TRY(cudaMemcpyAsync(os.h[4].p, o.base, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
+          PL_TRY(cudaMemcpyAsync(os.h[13].p, os.d[15].p, (size_t)(n_entries + 1) / 2, cudaMemcpyDeviceToHost, cs));
+          if (os.n_special) {
+            PL_TRY(cudaMemcpyAsync(os.h[14].p, os.d[18].p, (size_t)os.n_special * 4, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[15].p, os.d[19].p, (size_t)os.n_special, cudaMemcpyDeviceToHost, cs));
+          }
           PL_TRY(cudaMemcpyAsync(os.h[4].as<uint8_t>() + n_entries, o.qual, (size_t)n_entries, cudaMemcpyDeviceToHost, cs));
         } else {
           p.stats.d2h_bytes += (uint64_t)n_col * 20 + 8 + (counts_only ? (uint64_t)n_col * 24 : n_entries * (6 + (want_q ? 4 : 0)));
@@ -844,7 +869,11 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
         cols->counts = os.d[7].as<uint32_t>();
       } else if (pl->prm.compact_reads) {
-        cols->read_idx = nullptr; cols->position = nullptr; cols->col_off = nullptr;
+        cols->read_idx = nullptr; cols->position = nullptr; cols->col_off = nullptr; cols->base = nullptr;
+        cols->base4 = os.d[15].as<uint8_t>();
+        cols->n_special = os.n_special;
+        cols->special_entry = os.d[18].as<uint32_t>();
+        cols->special_base = os.d[19].as<uint8_t>();
         cols->last_read = os.d[8].as<uint32_t>();
         cols->live_mask = os.d[9].as<uint64_t>();
         cols->n_stragglers = os.n_strag;
@@ -867,7 +896,11 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
       cols->counts = os.h[6].as<uint32_t>();
     } else if (pl->prm.compact_reads) {
-      cols->read_idx = nullptr; cols->position = nullptr; cols->col_off = nullptr;
+      cols->read_idx = nullptr; cols->position = nullptr; cols->col_off = nullptr; cols->base = nullptr;
+      cols->base4 = os.h[13].as<uint8_t>();
+      cols->n_special = os.n_special;
+      cols->special_entry = os.h[14].as<uint32_t>();
+      cols->special_base = os.h[15].as<uint8_t>();
       cols->last_read = os.h[7].as<uint32_t>();
       cols->live_mask = os.h[8].as<uint64_t>();
       cols->n_stragglers = os.n_strag;

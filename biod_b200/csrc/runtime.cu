@@ -551,7 +551,7 @@ const char* biodb_version(void) { return "biod_b200 0.1 (sm_100a)"; }
 void biodb_default_options(biodb_options* o) {
   memset(o, 0, sizeof *o);
   o->device = -1;
-  o->blocks_per_batch = 0;      // = three full waves of the inflate kernel on the device (7992 on a B200)
+  o->blocks_per_batch = 0;      // = three full waves of the inflate kernel on the device (8436 on a B200)
 }
 
 const biodb_error* biodb_open_error(void) { return &g_open_error; }

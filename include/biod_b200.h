@@ -56,7 +56,7 @@ typedef struct biodb_error {
 typedef struct biodb_options {
   int32_t device;            /* CUDA ordinal; -1 = current device */
   int32_t blocks_per_batch;  /* BGZF blocks inflated per GPU batch; 0 = default: three full waves of the inflate
-                                kernel on the device (7992 on a B200) */
+                                kernel on the device (8436 on a B200) */
   int32_t verify_crc;        /* 1 = check each block's CRC32 on the device (debug builds of BioD assert it, block.d:187) */
   int32_t want_offsets;      /* 1 = fill start/end virtual offsets (withOffsets policy, readrange.d:51-66) */
   int32_t pin_input;         /* 1 = cudaHostRegister the caller's buffer in biodb_open_memory */
@@ -150,15 +150,19 @@ typedef struct biodb_column_batch {
   const uint8_t* qual;         /* [n_entries] current_base_quality (255 inside D/N)    pileup.d:127-134 */
   const uint32_t* query_offset;/* [n_entries] or NULL */
   const uint32_t* counts;      /* [n_columns*6] A,C,G,T,other,deletion — only with counts_only */
-  /* compact_reads = 1: a sequential, lossless encoding of the same columns that moves 16 bytes per column + 2 bytes
+  /* compact_reads = 1: a sequential, lossless encoding of the same columns that moves 16 bytes per column + 1.5 bytes
    * per entry over PCIe instead of 20 + 6.  position, col_off and read_idx are NULL and
    *  - positions come as n_runs runs of consecutive positions: columns [run_first_col[r], run_first_col[r+1]) have
    *    positions run_pos[r], run_pos[r]+1, ...  (one run per stretch of non-zero coverage);
    *  - the reads of column c, in column (= file) order, are its stragglers — the entries k of strag_col[] / strag_idx[]
    *    with strag_col[k] == c (sorted by column; reads more than 63 records older than the column's last read) —
    *    followed by record index last_read[c] - d for every d = 63..0 with bit d of live_mask[c] set;
-   *  - coverage(c) = stragglers(c) + popcount(live_mask[c]); the entries of column c in base / qual / query_offset
-   *    start where those of column c-1 end (col_off is the running sum of the coverages). */
+   *  - coverage(c) = stragglers(c) + popcount(live_mask[c]); the entries of column c in base4 / qual / query_offset
+   *    start where those of column c-1 end (col_off is the running sum of the coverages);
+   *  - base is NULL: entry e's base is "=ACMGRSVTWYHKDBN"[code], code = high nibble of base4[e/2] for even e, low
+   *    nibble for odd e (BAM's SEQ packing, read.d:364-383) — except for the n_special entries listed, in ascending
+   *    order, in special_entry[] (index e within the batch), whose base is special_base[]: '-' inside a deletion /
+   *    reference skip (pileup.d:115-122), 0 for a base asked past l_seq. */
   const uint32_t* last_read;     /* [n_columns] */
   const uint64_t* live_mask;     /* [n_columns] */
   uint64_t n_stragglers;
@@ -167,6 +171,10 @@ typedef struct biodb_column_batch {
   uint64_t n_runs;
   const uint64_t* run_pos;       /* [n_runs] */
   const uint32_t* run_first_col; /* [n_runs+1] */
+  const uint8_t* base4;          /* [(n_entries+1)/2] */
+  uint64_t n_special;
+  const uint32_t* special_entry; /* [n_special] */
+  const uint8_t* special_base;   /* [n_special] */
 } biodb_column_batch;
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);
