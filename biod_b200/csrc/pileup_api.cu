@@ -725,11 +725,11 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         pileup_position_runs_scan(n_col, o, run_flag, run_incl, s, st);
         // bases two per byte + the list of entries that are not a base ('-' in D / N, 0 past l_seq)
         const uint32_t npb = pileup_pack_blocks(n_entries);
-        PL_TRY(os.d[15].ensure((size_t)(n_entries + 1) / 2 + 64, st));
-        PL_TRY(os.d[16].ensure((size_t)(npb + 2) * 4, st));
-        PL_TRY(os.d[17].ensure((size_t)(npb + 2) * 4, st));
-        PL_TRY(pl->pack_tmp.ensure((scan_temp_elems((uint64_t)npb + 2) + 8) * 4, st));
-        if (!p.r->opts.device_output) PL_TRY(os.h[13].ensure((size_t)(n_entries + 1) / 2 + 64));
+        PL_TRY(os.d[15].ensure(os.ent_cap / 2 + 64, st));            // sized like the entry arrays (headroom included)
+        PL_TRY(os.d[16].ensure((size_t)(pileup_pack_blocks(os.ent_cap) + 2) * 4, st));
+        PL_TRY(os.d[17].ensure((size_t)(pileup_pack_blocks(os.ent_cap) + 2) * 4, st));
+        PL_TRY(pl->pack_tmp.ensure((scan_temp_elems((uint64_t)pileup_pack_blocks(os.ent_cap) + 2) + 8) * 4, st));
+        if (!p.r->opts.device_output) PL_TRY(os.h[13].ensure(os.ent_cap / 2 + 64));
         pileup_pack_bases(n_entries, o.base, os.d[15].as<uint8_t>(), os.d[16].as<uint32_t>(), os.d[17].as<uint32_t>(), s,
                           pl->pack_tmp.as<uint32_t>(), st);
         p.stage_end(&p.stats.pileup_ms);

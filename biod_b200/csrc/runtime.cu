@@ -824,7 +824,9 @@ static biodb_status reads_produce(biodb_reads* it, int s) {
   src[10] = p.d_rec[9].p;
   // device -> staging (ordered behind the previous batch's staging -> host copies on the same stream)
   for (int k = 0; k < 11 && ok; ++k) {
-    ok = it->d_stage[k].ensure(bytes[k] + 16, cs) == cudaSuccess &&
+    // (grow with headroom: the two host slots and the staging area see batches of slightly different sizes, and a
+    //  re-allocation of half a gigabyte of pinned memory costs hundreds of milliseconds)
+    ok = (bytes[k] + 16 <= it->d_stage[k].cap || it->d_stage[k].ensure(bytes[k] + bytes[k] / 8 + 4096, cs) == cudaSuccess) &&
          (bytes[k] == 0 || cudaMemcpyAsync(it->d_stage[k].p, src[k], bytes[k], cudaMemcpyDeviceToDevice, cs) == cudaSuccess);
   }
   ok = ok && cudaEventRecord(it->staged, cs) == cudaSuccess;
@@ -832,7 +834,7 @@ static biodb_status reads_produce(biodb_reads* it, int s) {
   // staging -> host slot
   for (int k = 0; k < 11 && ok; ++k) {
     PinBuf& h = k == 0 ? sl.h_data : sl.h_arr[k - 1];
-    ok = h.ensure(bytes[k] + 16) == cudaSuccess &&
+    ok = (bytes[k] + 16 <= h.cap || h.ensure(bytes[k] + bytes[k] / 8 + 4096) == cudaSuccess) &&
          (bytes[k] == 0 || cudaMemcpyAsync(h.p, it->d_stage[k].p, bytes[k], cudaMemcpyDeviceToHost, cs) == cudaSuccess);
   }
   ok = ok && cudaEventRecord(sl.done, cs) == cudaSuccess;
