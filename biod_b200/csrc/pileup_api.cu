@@ -675,6 +675,8 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       const bool counts_only = pl->prm.counts_only != 0;
       const bool want_q = pl->prm.want_query_offset != 0 && !counts_only;
       const bool compact = pl->prm.compact_reads != 0 && !counts_only;
+      if (compact && n_entries >= 0xfffffff0ull)      // special_entry[] indexes entries with 32 bits
+        return pl->fail(BIODB_ERR_NOMEM, "too many column entries in one batch for the compact encoding; lower blocks_per_batch");
       if (counts_only) {
         PL_TRY(os.d[7].ensure(os.col_cap * 24, st));
         if (!p.r->opts.device_output) PL_TRY(os.h[6].ensure(os.col_cap * 24));
