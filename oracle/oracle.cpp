@@ -372,6 +372,185 @@ int decode_records(Bam* s) {
 
 // ---------------------------------------------------------------- pileup ----
 
+// ---- reference bases from MD tags (oracle only so far: the CUDA path is the next step) ----
+// Base16(char) -> char: bio/core/base.d:39-62 (_char2code) and :85 (_code2char)
+inline char norm16(uint8_t ch) {
+  static const uint8_t low[128] = {
+      15,15,15,15,15,15,15,15,15,15,15,15,15,15,15,15, 15,15,15,15,15,15,15,15,15,15,15,15,15,15,15,15,
+      15,15,15,15,15,15,15,15,15,15,15,15,15,15,15,15,  1, 2, 4, 8,15,15,15,15,15,15,15,15,15, 0,15,15,
+      15, 1,14, 2,13,15,15, 4,11,15,15,12,15, 3,15,15, 15,15, 5, 6, 8,15, 7, 9,15,10,15,15,15,15,15,15,
+      15, 1,14, 2,13,15,15, 4,11,15,15,12,15, 3,15,15, 15,15, 5, 6, 8,15, 7, 9,15,10,15,15,15,15,15,15};
+  return "=ACMGRSVTWYHKDBN"[ch < 128 ? low[ch] : 15];
+}
+
+// BamRead["MD"] as a string: TagStorage.opIndex / skipValue (read.d:1070-1087, 1219-1230), charToSizeof
+// (tagvalue.d:106-119).  Restatement-defined: a value that is not of type Z, or a tag area that ends inside a value,
+// gives "no MD tag" (BioD would throw or read out of bounds).
+bool find_md(const Bam* s, uint32_t r, std::string* md) {
+  const uint8_t* rec = s->u.data() + s->rec_off[r] + 4;
+  const uint64_t bs = (uint64_t)s->block_size[r];
+  const uint64_t lseq = (uint64_t)std::max(0, s->l_seq[r]);
+  uint64_t off = 32ull + s->l_read_name[r] + 4ull * s->n_cigar[r] + (lseq + 1) / 2 + lseq;
+  if (off > bs) return false;
+  const uint8_t* t = rec + off;
+  const uint64_t n = bs - off;
+  if (n < 4) return false;
+  uint64_t o = 0;
+  auto size_of = [](char c) -> int {
+    switch (c) { case 'A': case 'c': case 'C': return 1; case 's': case 'S': return 2; case 'i': case 'I': case 'f': return 4; default: return -1; }
+  };
+  while (o + 1 < n) {
+    const bool hit = t[o] == 'M' && t[o + 1] == 'D';
+    o += 2;
+    if (o >= n) return false;
+    const char type = (char)t[o++];
+    if (type == 'Z' || type == 'H') {
+      const uint64_t b = o;
+      while (o < n && t[o] != 0) ++o;
+      if (o >= n) return false;
+      if (hit) { if (type != 'Z') return false; md->assign((const char*)t + b, (size_t)(o - b)); return true; }
+      ++o;
+    } else if (type == 'B') {
+      if (o + 5 > n) return false;
+      const int es = size_of((char)t[o]);
+      if (es < 0) return false;
+      const uint64_t cnt = le32(t + o + 1);
+      o += 5 + (uint64_t)es * cnt;
+      if (hit || o > n) return false;
+    } else {
+      const int es = size_of(type);
+      if (es < 0 || hit) return false;
+      o += (uint64_t)es;
+    }
+  }
+  return false;
+}
+
+struct MdOp { int type; uint32_t match; char mismatch; std::string del; };   // md/operation.d: 0 Match, 1 Mismatch, 2 Deletion
+
+// mdOperations (md/parse.d:13-143), literally: a bidirectional range that parses its first operation from the front of
+// the string and caches its LAST operation from the back at construction; forward iteration therefore yields the
+// operations parsed from the front of what is left, then the cached back one.  Zero-length matches are filtered the
+// way std.algorithm.filterBidirectional does (from both ends at construction, then at every popFront).
+struct MdRange {
+  std::string md;
+  MdOp f{}, b{};
+  uint8_t rem = 255;
+  static bool up(char c) { return c >= 'A' && c <= 'Z'; }
+  static bool dig(char c) { return c >= '0' && c <= '9'; }
+  static uint32_t to_uint(const std::string& x) {        // to!uint; restatement-defined: saturates instead of throwing
+    uint64_t v = 0;
+    for (char c : x) { v = v * 10 + (uint64_t)(c - '0'); if (v > 0xffffffffull) v = 0xffffffffull; }
+    return (uint32_t)v;
+  }
+  bool cache_front() {
+    if (md.empty()) return false;
+    if (md[0] == '^') {
+      md.erase(0, 1);
+      size_t len = 0;
+      while (len < md.size() && up(md[len])) ++len;
+      f = MdOp{2, 0, 0, md.substr(0, len)};
+      md.erase(0, len);
+    } else if (dig(md[0])) {
+      size_t len = 0;
+      while (len < md.size() && dig(md[len])) ++len;
+      f = MdOp{0, to_uint(md.substr(0, len)), 0, ""};
+      md.erase(0, len);
+    } else {
+      f = MdOp{1, 0, md[0], ""};
+      md.erase(0, 1);
+    }
+    return true;
+  }
+  bool cache_back() {
+    if (md.empty()) return false;
+    const size_t n = md.size();
+    if (dig(md[n - 1])) {
+      size_t len = 0;
+      while (len < n && dig(md[n - 1 - len])) ++len;
+      b = MdOp{0, to_uint(md.substr(n - len)), 0, ""};
+      md.erase(n - len);
+    } else if (n == 1 || dig(md[n - 2])) {
+      b = MdOp{1, 0, md[n - 1], ""};
+      md.erase(n - 1);
+    } else {
+      size_t len = 0;                                        // countUntil!"a == '^'"(retro(_md)); restatement-defined: no '^' = whole string
+      while (len < n && md[n - 1 - len] != '^') ++len;
+      b = MdOp{2, 0, 0, md.substr(n - len)};
+      md.erase(len < n ? n - len - 1 : 0);
+    }
+    return true;
+  }
+  explicit MdRange(const std::string& m) : md(m) {
+    if (!cache_front()) rem = 0;
+    else if (!cache_back()) { b = f; rem = 1; }
+  }
+  bool empty() const { return rem == 0; }
+  void pop_front() {
+    if (md.empty()) { if (rem == 255) { f = b; rem = 1; } else rem = 0; }
+    else if (!cache_front()) rem = 0;
+  }
+  void pop_back() {
+    if (md.empty()) { if (rem == 255) { b = f; rem = 1; } else rem = 0; }
+    else if (!cache_back()) rem = 0;
+  }
+};
+inline bool zero_match(const MdOp& o) { return o.type == 0 && o.match == 0; }
+std::vector<MdOp> md_operations(const std::string& md) {
+  MdRange r(md);
+  while (!r.empty() && zero_match(r.f)) r.pop_front();
+  while (!r.empty() && zero_match(r.b)) r.pop_back();
+  std::vector<MdOp> out;
+  while (!r.empty()) {
+    out.push_back(r.f);
+    do { r.pop_front(); } while (!r.empty() && zero_match(r.f));
+  }
+  return out;
+}
+
+// dna(read) (md/reconstruct.d:38-214): reference bases over the read's M/=/X and deleted positions, from SEQ + MD.
+// Restatement-defined: where BioD's lazy range gets stuck (a match / mismatch operation with the query bases used up:
+// popFront returns without advancing, :143-156) or reads an empty range, the sequence simply ends.
+std::string dna_of_read(const Bam* s, uint32_t r) {
+  const uint8_t* rec = s->u.data() + s->rec_off[r] + 4;
+  const uint32_t lname = s->l_read_name[r], nc = s->n_cigar[r];
+  const int64_t lseq = s->l_seq[r];
+  const uint8_t* seq = rec + 32 + lname + 4 * nc;
+  std::string q;                                              // joiner of the SEQ chunks of M/=/X operations (:87-92,:196-198)
+  int64_t qoff = 0;
+  const uint32_t* cg = s->cigar.data() + s->cigar_off[r];
+  for (uint32_t k = 0; k < nc; ++k) {
+    const uint32_t raw = cg[k], len = raw >> 4;
+    if (!op_query(raw)) continue;
+    if (op_ref(raw))
+      for (int64_t i = qoff; i < qoff + (int64_t)len && i < lseq; ++i) {
+        const uint8_t byte = seq[i >> 1];
+        q.push_back("=ACMGRSVTWYHKDBN"[(i & 1) ? (byte & 0xF) : (byte >> 4)]);
+      }
+    qoff += len;
+  }
+  std::string md;
+  find_md(s, r, &md);
+  const std::vector<MdOp> ops = md_operations(md);
+  std::string out;
+  size_t qi = 0, k = 0, di = 0;
+  if (ops.empty()) return out;
+  MdOp cur = ops[k++];
+  while (true) {
+    if (cur.type == 2) {
+      if (di >= cur.del.size()) { if (k >= ops.size()) break; cur = ops[k++]; di = 0; continue; }   // (empty deletion)
+      out.push_back(norm16((uint8_t)cur.del[di]));
+      if (++di >= cur.del.size()) { if (k >= ops.size()) break; cur = ops[k++]; di = 0; }
+    } else {
+      if (qi >= q.size()) break;                             // _qseqIsSuddenlyEmpty
+      out.push_back(cur.type == 0 ? q[qi] : norm16((uint8_t)cur.mismatch));
+      ++qi;
+      if (cur.type == 1 || --cur.match == 0) { if (k >= ops.size()) break; cur = ops[k++]; di = 0; }
+    }
+  }
+  return out;
+}
+
 struct Cursor {              // PileupRead — bam/pileup.d:86-230
   uint32_t read;             // index into the record table
   int32_t end_position;      // EagerBamRead (read.d:1380-1383)
@@ -387,6 +566,7 @@ struct Pileup {
   std::vector<uint32_t> n_start;
   std::vector<uint32_t> read_idx, qoff, op_index, op_offset;
   std::vector<uint8_t> base, qual;
+  std::vector<uint8_t> ref_base;      // PileupColumn.reference_base, one per column ('N' unless use_md_tag)
 };
 
 struct PileupSim {
@@ -399,6 +579,36 @@ struct PileupSim {
   int32_t ref = -1;
   size_t n_starting = 0;
   bool skip_zero;
+  // PileupRangeUsingMdTag (pileup.d:522-654)
+  bool use_md = false;
+  std::string chunk;             // _chunk: reference bases reconstructed from the current provider
+  size_t chunk_i = 0;
+  uint32_t chunk_end = 0;        // _chunk_end_position
+  uint32_t provider = 0;         // _next_chunk_provider
+  bool has_provider = false;
+  uint64_t prev_cov = 0;         // _prev_coverage
+  int32_t curr_ref = -1;         // _curr_ref_id
+  uint8_t ref_base = 'N';        // _column._reference_base (PileupColumn default 'N')
+  bool chunk_empty() const { return chunk_i >= chunk.size(); }
+  void take_front() {            // _column._reference_base = _chunk.front; _chunk.popFront();
+    // restatement-defined: `front` of an exhausted chunk (BioD reads an empty range) gives 'N'
+    if (chunk_empty()) { ref_base = 'N'; return; }
+    ref_base = (uint8_t)chunk[chunk_i++];
+  }
+  void md_add(uint32_t r) {      // override add :563-596, after super.add(read)
+    const bool had_zero = prev_cov == 0;
+    if (s->ref_id[r] != curr_ref) {
+      curr_ref = s->ref_id[r];
+      has_provider = true;
+      provider = r;
+      return;
+    }
+    if ((uint32_t)s->pos[r] > chunk_end && !had_zero) return;
+    if ((uint32_t)s->end_pos[r] > chunk_end) {
+      if (!has_provider) { has_provider = true; provider = r; }
+      else if (s->end_pos[r] > s->end_pos[provider]) provider = r;
+    }
+  }
 
   const uint32_t* cig(uint32_t r) const { return s->cigar.data() + s->cigar_off[r]; }
   uint32_t ncig(uint32_t r) const { return (uint32_t)(s->cigar_off[r + 1] - s->cigar_off[r]); }
@@ -429,6 +639,7 @@ struct PileupSim {
       out->msg = "Invalid read - CIGAR has no usable reference-consuming operation (record " + std::to_string(r) + ")";
     }
     buf.push_back(c);
+    if (use_md) md_add(r);
   }
 
   void increment(Cursor& c) {   // incrementPosition :195-222
@@ -448,7 +659,22 @@ struct PileupSim {
     }
   }
 
-  void init_new_reference() {   // :399-424
+  void init_new_reference() {   // PileupRangeUsingMdTag.initNewReference :598-611 (virtual: the base class calls this one)
+    if (!use_md) { base_init_new_reference(); return; }
+    prev_cov = 0;
+    base_init_new_reference();
+    if (has_provider) {
+      chunk = dna_of_read(s, provider);
+      chunk_i = 0;
+      chunk_end = (uint32_t)s->end_pos[provider];
+      has_provider = false;
+      take_front();
+    } else {
+      ref_base = 'N';
+    }
+  }
+
+  void base_init_new_reference() {   // :399-424
     uint32_t r = reads[next];
     position = (uint64_t)(int64_t)s->pos[r];
     ref = s->ref_id[r];
@@ -465,7 +691,24 @@ struct PileupSim {
 
   bool empty() const { return reads_empty() && buf.empty(); }   // :340-342
 
-  void pop_front() {            // :345-397
+  void pop_front() {            // PileupRangeUsingMdTag.popFront :614-653
+    if (!use_md) { base_pop_front(); return; }
+    if (!chunk_empty()) ref_base = (uint8_t)chunk[chunk_i++];
+    else ref_base = 'N';
+    prev_cov = buf.size();
+    base_pop_front();           // may call init_new_reference() above
+    if (chunk_empty() && has_provider) {
+      chunk = dna_of_read(s, provider);
+      chunk_i = 0;
+      chunk_end = (uint32_t)s->end_pos[provider];
+      has_provider = false;
+      const uint64_t skip = position - (uint64_t)(int64_t)s->pos[provider];     // _chunk.popFrontN(...)
+      chunk_i = (size_t)std::min<uint64_t>(skip, chunk.size());
+      take_front();
+    }
+  }
+
+  void base_pop_front() {       // :345-397
     uint64_t pos = ++position;
     size_t survived = 0;
     for (size_t i = 0; i < buf.size(); ++i) {
@@ -497,6 +740,7 @@ struct PileupSim {
     out->col_ref.push_back(ref);
     out->col_pos.push_back(position);
     out->n_start.push_back((uint32_t)n_starting);
+    out->ref_base.push_back(ref_base);
     for (const Cursor& c : buf) {
       const uint8_t* rec = s->u.data() + s->rec_off[c.read] + 4;
       uint32_t lname = s->l_read_name[c.read];
@@ -533,13 +777,14 @@ struct PileupSim {
 // makePileup / pileupInstance (pileup.d:480-507, 683-694) when single_ref != 0,
 // pileupColumns (pileup.d:509-519) otherwise.
 Pileup* run_pileup(const Bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero,
-                   int64_t rec_begin, int64_t rec_end) {
+                   int64_t rec_begin, int64_t rec_end, int use_md = 0) {
   Pileup* out = new Pileup;
   out->col_off.push_back(0);
   PileupSim sim;
   sim.s = s;
   sim.out = out;
   sim.skip_zero = skip_zero != 0;
+  sim.use_md = use_md != 0;
   int64_t n = (int64_t)s->rec_off.size();
   if (rec_end < 0 || rec_end > n) rec_end = n;
   if (rec_begin < 0) rec_begin = 0;
@@ -643,6 +888,18 @@ orc_pileup* orc_pileup_run_range(orc_bam* s, int single_ref, uint64_t start_from
   decode_records(s);
   return run_pileup(s, single_ref, start_from, end_at, skip_zero, rec_begin, rec_end);
 }
+// the same with use_md_tag = true: every column also gets its reference_base (pileup.d:522-654)
+orc_pileup* orc_pileup_run_md(orc_bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero) {
+  decode_records(s);
+  return run_pileup(s, single_ref, start_from, end_at, skip_zero, 0, -1, 1);
+}
+// dna(read) of one record (md/reconstruct.d:38-214); returns its length, copies at most cap bytes
+uint64_t orc_dna_of_read(orc_bam* s, uint64_t r, char* out, uint64_t cap) {
+  decode_records(s);
+  const std::string d = dna_of_read(s, (uint32_t)r);
+  memcpy(out, d.data(), (size_t)std::min<uint64_t>(cap, d.size()));
+  return d.size();
+}
 void orc_pileup_free(orc_pileup* p) { delete p; }
 int orc_pileup_status(const orc_pileup* p) { return p->status; }
 const char* orc_pileup_errmsg(const orc_pileup* p) { return p->msg.c_str(); }
@@ -660,6 +917,7 @@ ORC_PARR(op_index, uint32_t, op_index)
 ORC_PARR(op_offset, uint32_t, op_offset)
 ORC_PARR(base, uint8_t, base)
 ORC_PARR(qual, uint8_t, qual)
+ORC_PARR(ref_base, uint8_t, ref_base)
 
 // ------------------------------------------------------- CPU baseline legs ----
 // "Restated BioD CPU path (libz, g++ -O3), not the D binary" (BASELINE.md §2):

@@ -56,6 +56,10 @@ def lib():
             fn.argtypes = [C.c_void_p]
         L.orc_pileup_run.restype = C.c_void_p
         L.orc_pileup_run.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int]
+        L.orc_pileup_run_md.restype = C.c_void_p
+        L.orc_pileup_run_md.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int]
+        L.orc_dna_of_read.restype = u64
+        L.orc_dna_of_read.argtypes = [C.c_void_p, u64, C.c_char_p, u64]
         L.orc_pileup_run_range.restype = C.c_void_p
         L.orc_pileup_run_range.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int, C.c_int64, C.c_int64]
         L.orc_pileup_free.argtypes = [C.c_void_p]
@@ -68,7 +72,7 @@ def lib():
         for f in ("orc_pileup_n_columns", "orc_pileup_n_entries"):
             getattr(L, f).restype = u64
             getattr(L, f).argtypes = [C.c_void_p]
-        for name in list(_PILEUP_ARRAYS) + ["col_off"]:
+        for name in list(_PILEUP_ARRAYS) + ["col_off", "ref_base"]:
             fn = getattr(L, "orc_pileup_" + name)
             fn.restype = C.c_void_p
             fn.argtypes = [C.c_void_p]
@@ -118,6 +122,7 @@ class Pileup:
             n = nc if name in ("col_ref", "col_pos", "n_start") else ne
             setattr(self, name, _arr(getattr(L, "orc_pileup_" + name)(h), n, dt))
         self.col_off = _arr(L.orc_pileup_col_off(h), nc + 1, np.uint64)
+        self.ref_base = _arr(L.orc_pileup_ref_base(h), nc, np.uint8)     # PileupColumn.reference_base ('N' unless use_md_tag)
         L.orc_pileup_free(h)
 
     def bases(self, c):
@@ -225,11 +230,19 @@ class Bam:
         return r[o:].tobytes()
 
     # -- pileup ------------------------------------------------------------
-    def make_pileup(self, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True):
-        return Pileup(self._L, self._L.orc_pileup_run(self._h, 1, start_from, end_at, int(skip_zero_coverage)))
+    def make_pileup(self, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True, use_md_tag=False):
+        run = self._L.orc_pileup_run_md if use_md_tag else self._L.orc_pileup_run
+        return Pileup(self._L, run(self._h, 1, start_from, end_at, int(skip_zero_coverage)))
 
-    def pileup_columns(self, skip_zero_coverage=True):
-        return Pileup(self._L, self._L.orc_pileup_run(self._h, 0, 0, 2**64 - 1, int(skip_zero_coverage)))
+    def pileup_columns(self, skip_zero_coverage=True, use_md_tag=False):
+        run = self._L.orc_pileup_run_md if use_md_tag else self._L.orc_pileup_run
+        return Pileup(self._L, run(self._h, 0, 0, 2**64 - 1, int(skip_zero_coverage)))
+
+    def dna(self, i):
+        """dna(read) of record i: reference bases over its aligned and deleted positions (md/reconstruct.d:38-214)."""
+        buf = C.create_string_buffer(1 << 16)
+        n = int(self._L.orc_dna_of_read(self._h, i, buf, len(buf)))
+        return buf.raw[:min(n, len(buf))].decode("latin1")
 
     def make_pileup_range(self, rec_begin, rec_end, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
                           single_ref=True):

@@ -242,3 +242,99 @@ def test_bins_bam_all_cigar_ops():
     assert {0, 1, 2, 3, 7, 8} <= ops
     p = b.pileup_columns()
     assert p.status == 0 and p.n_entries > 0
+
+
+# ---- reference bases from MD tags (oracle restatement of pileup.d:522-654) --------------
+def _py_reference_of(seq, cigar, md):
+    """Independent, plain reconstruction of the reference bases a well-formed read covers: {ref offset: base}."""
+    import re
+    ops = [(int(n), o) for n, o in re.findall(r"(\d+)([MIDNSHP=X])", cigar)]
+    aligned, q = [], 0                    # query bases of M/=/X in order
+    for n, o in ops:
+        if o in "M=X":
+            aligned += list(seq[q:q + n])
+        if o in "MIS=X":
+            q += n
+    toks = re.findall(r"\d+|\^[A-Z]+|[A-Z]", md)
+    ref, k = [], 0
+    for t in toks:
+        if t[0].isdigit():
+            ref += aligned[k:k + int(t)]
+            k += int(t)
+        elif t[0] == "^":
+            ref += list(t[1:])
+        else:
+            ref.append(t)
+            k += 1
+    # lay the string over reference offsets: M/=/X and D consume it, N consumes reference without bases
+    out, off, i = {}, 0, 0
+    for n, o in ops:
+        if o in "M=XD":
+            for _ in range(n):
+                out[off] = ref[i]
+                off += 1
+                i += 1
+        elif o == "N":
+            off += n
+    assert i == len(ref)
+    return out
+
+
+def _expected_reference(positions, seqs, cigars, mds):
+    exp = {}
+    for p, s_, c, m in zip(positions, seqs, cigars, mds):
+        for off, b in _py_reference_of(s_, c, m).items():
+            assert exp.setdefault(p + off, b) == b, "reads disagree on the reference"
+    return exp
+
+
+def test_reference_bases_unit_vector():
+    # bam/pileup.d:776-786: column.reference_base == dna(reads)[column.position - first_read_position]
+    b = orc.Bam(pileup_vector_bam()).decode()
+    exp = _expected_reference(POSITIONS, SEQS, CIGARS, MDS)
+    for args in ((796, 849, False), (0, 2**64 - 1, False), (0, 2**64 - 1, True)):
+        p = b.make_pileup(*args, use_md_tag=True)
+        assert p.status == 0 and p.n_columns > 0
+        got = "".join(chr(x) for x in p.ref_base)
+        want = "".join(exp.get(int(pos), "N") for pos in p.col_pos)
+        assert got == want
+    # dna(read) itself, read by read (md/reconstruct.d:216-260 checks the same function on other vectors)
+    for i in range(10):
+        d = _py_reference_of(SEQS[i], CIGARS[i], MDS[i])
+        assert b.dna(i) == "".join(d[k] for k in sorted(d))
+    # without the flag every column keeps PileupColumn's default (pileup.d:240)
+    assert set(b.make_pileup(796, 849, False).ref_base.tolist()) == {ord("N")}
+
+
+def test_reference_bases_zero_coverage_vector():
+    # bam/pileup.d:830-856: equal(dna(reads), map!(c => c.reference_base)(makePileup(reads, true, 0, ulong.max, false)))
+    seqs = ["CCCACATAGAAAGCTTGCTGTTTCTCTGTGGGAAGTTTTAACTTAGGTCAGCTT",
+            "TAGAAAGCTTGCTGTTTCTCTGTGGGAAGTTTTAACTTAGGTTAGCTTCATCTA",
+            "TTTTTCTTTCTTTCTTTGAAGAAGGCAGATTCCTGGTCCTGCCACTCAAATTTT",
+            "TTTCTTTCTTTCTTTGAAGAAGGCAGATTCCTGGTCCTGCCACTCAAATTTTCA"]
+    pos = [979, 985, 1046, 1048]
+    mds = ["54", "42C7C3", "54", "54"]
+    recs = [bam_record(f"r{i + 1}", seqs[i], "54M", pos[i], tags=tag_z("MD", mds[i])) for i in range(4)]
+    b = orc.Bam(make_bam([("20", 63025520)], recs)).decode()
+    exp = _expected_reference(pos, seqs, ["54M"] * 4, mds)
+    p = b.make_pileup(0, 2**64 - 1, False, use_md_tag=True)
+    got = "".join(chr(x) for x in p.ref_base)
+    want = "".join(exp.get(q, "N") for q in range(979, 1048 + 54))     # dna(reads): 'N' where no read covers (reconstruct.d:262-270)
+    assert got == want
+    q = b.make_pileup(0, 2**64 - 1, True, use_md_tag=True)
+    assert "".join(chr(x) for x in q.ref_base) == "".join(exp[int(x)] for x in q.col_pos)
+
+
+def test_md_operations_and_missing_tags():
+    # md/parse.d:148-182 vectors go through dna(read): matches, mismatches, deletions, zero matches are skipped
+    recs = [bam_record("a", "ACGTACGTAC", "10M", 10, tags=tag_z("MD", "3A0C5")),
+            bam_record("b", "ACGTACGTAC", "4M2D6M", 10, tags=tag_z("MD", "4^GG6")),
+            bam_record("c", "ACGTACGTAC", "2S4M1I3M", 12, tags=tag_z("XX", "zz") + tag_z("MD", "0T6")),
+            bam_record("d", "ACGTACGTAC", "10M", 14)]                      # no MD tag: empty dna
+    b = orc.Bam(make_bam([("r", 1000)], recs)).decode()
+    assert b.dna(0) == "ACG" + "A" + "C" + "CGTAC"        # 3 matches, mismatch A, (0 skipped), mismatch C, 5 matches
+    assert b.dna(1) == "ACGT" + "GG" + "ACGTAC"           # the deleted bases come from the tag
+    assert b.dna(2) == "T" + "TAC" + "TAC"                # soft clip and insertion are not reference positions
+    assert b.dna(3) == ""
+    p = b.pileup_columns(use_md_tag=True)
+    assert p.status == 0 and len(p.ref_base) == p.n_columns
