@@ -1,5 +1,6 @@
 // Host runtime + C ABI of libbiod_b200.so (see include/biod_b200.h and runtime.h).
 #include "runtime.h"
+#include "md_chain.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -951,6 +952,23 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
   if (launch_inflate(ia, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
   if (crc && launch_crc32(out, out_off, isize, n_blocks, crc, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
   return BIODB_OK;
+}
+
+// Host-only: MdChain (md_chain.h) over n reads; returns the number of segments, writes at most cap of them as
+// (first, count, read, offset) quadruples of int64.
+int64_t biodb_debug_md_chain(const int32_t* ref_id, const int64_t* pos, const int64_t* end, const int64_t* dna_len, uint64_t n,
+                             int32_t skip_zero_coverage, int64_t* seg4, uint64_t cap) {
+  MdChain chain(skip_zero_coverage != 0);
+  std::vector<MdSegment> segs;
+  for (uint64_t i = 0; i < n; ++i) chain.admit(i, ref_id[i], pos[i], end[i], dna_len[i], &segs);
+  chain.finish(&segs);
+  for (uint64_t k = 0; k < segs.size() && k < cap; ++k) {
+    seg4[4 * k] = segs[k].first;
+    seg4[4 * k + 1] = segs[k].count;
+    seg4[4 * k + 2] = (int64_t)segs[k].read;
+    seg4[4 * k + 3] = segs[k].offset;
+  }
+  return (int64_t)segs.size();
 }
 
 biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset) {
