@@ -10,7 +10,7 @@
 // and every column position outside all segments has reference_base 'N'.  The device then only has to replay the
 // providers' dna() strings into the column table ("N1 on the device").
 //
-// Nothing here touches the GPU; tests/test_md_chain.py checks it against the oracle's column-by-column restatement.
+// Nothing here touches the GPU; tests/test_md_chain.py checks it against a column-by-column restatement of the sweep.
 #pragma once
 #include <stdint.h>
 
