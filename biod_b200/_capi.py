@@ -122,7 +122,9 @@ def lib():
     L.biodb_debug_inflate_counters.restype = C.c_int
     L.biodb_debug_inflate_counters.argtypes = [u64p, C.c_int32]
     L.biodb_debug_md_chain.restype = C.c_int64
-    L.biodb_debug_md_chain.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int32, vp, C.c_uint64]
+    L.biodb_debug_md_chain.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_uint64, vp, C.c_uint64]
+    L.biodb_debug_md_dna.restype = C.c_int64
+    L.biodb_debug_md_dna.argtypes = [vp, C.c_int64, vp, C.c_uint64]
     L.biodb_dev_scan_workspace_bytes.restype = C.c_size_t
     L.biodb_dev_scan_workspace_bytes.argtypes = [C.c_uint32]
     L.biodb_dev_scan_records.restype = C.c_int
@@ -138,4 +140,5 @@ EXPORTS = [
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
+    "biodb_debug_md_dna",
 ]

@@ -65,6 +65,37 @@ class MdChain {
     started_ = false;
   }
 
+  // The reference of the reads admitted so far is complete (the batch pipeline knows that before the first read of the
+  // next reference shows up): emit everything up to its last column now.  The admit() that follows finds it done.
+  void finish_reference(std::vector<MdSegment>* out) {
+    if (started_) finish_island(out);
+  }
+
+  // Streaming use: more reads of this reference will follow, none of them in front of `limit` — the position of the
+  // last read admitted, which is where the batch pipeline stops emitting columns.  Emits the segments of every column
+  // position below `limit`; afterwards no later segment reaches below it.
+  void drain(int64_t limit, std::vector<MdSegment>* out) {
+    if (!started_ || fin_) return;
+    if (!pending_.empty() && !adm_init_ && limit == adm_pos_) run_to(limit, out);   // what flush_admissions() will do first
+    if (seg_open_ && seg_first_ < limit) {
+      const int64_t span = limit - seg_first_;
+      const int64_t n = std::min<int64_t>(chunk_.len - seg_off_, span);
+      if (n > 0) out->push_back(MdSegment{seg_first_, n, chunk_.id, seg_off_});
+      seg_first_ = limit;
+      seg_off_ += span;
+      if (seg_off_ >= chunk_.len) seg_open_ = false;
+    }
+  }
+
+  // The reads whose dna() may still be asked for by later segments: the current chunk's (if bases are left) and the
+  // pending provider's.  Returns how many of ids[0..2) / lens[0..2) were filled.
+  int live_providers(uint64_t* ids, int64_t* lens) const {
+    int n = 0;
+    if (have_chunk_ && !chunk_empty()) { ids[n] = chunk_.id; lens[n] = chunk_.len; ++n; }
+    if (has_provider_ && !(n == 1 && ids[0] == provider_.id)) { ids[n] = provider_.id; lens[n] = provider_.len; ++n; }
+    return n;
+  }
+
  private:
   struct Rd { uint64_t id; int64_t pos, end, len; };
 
@@ -90,6 +121,7 @@ class MdChain {
   std::vector<Rd> pending_;
   int64_t adm_pos_ = 0;
   bool adm_init_ = false, adm_had_zero_ = false;
+  bool fin_ = false;          // finish_island() has run and no read has been admitted since
 
   bool chunk_empty() const { return !have_chunk_ || ci_ >= chunk_.len; }
 
@@ -187,12 +219,15 @@ class MdChain {
     adm_pos_ = r.pos;
     adm_init_ = true;
     adm_had_zero_ = true;
+    fin_ = false;
     pending_.clear();
     pending_.push_back(r);     // (max_end_ is updated when the admissions are flushed)
   }
 
   // the sweep runs on to the last covered position of the stretch; then (skip_zero_coverage or a new reference) it jumps
   void finish_island(std::vector<MdSegment>* out) {
+    if (fin_) return;
+    fin_ = true;
     flush_admissions(out);
     const int64_t end = max_end_;                 // columns exist up to max_end_ - 1
     run_to(end, out);

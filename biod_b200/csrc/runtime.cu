@@ -1,6 +1,7 @@
 // Host runtime + C ABI of libbiod_b200.so (see include/biod_b200.h and runtime.h).
 #include "runtime.h"
 #include "md_chain.h"
+#include "md_walk.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -955,12 +956,23 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
 }
 
 // Host-only: MdChain (md_chain.h) over n reads; returns the number of segments, writes at most cap of them as
-// (first, count, read, offset) quadruples of int64.
+// (first, count, read, offset) quadruples of int64.  batch_reads > 0 drives it the way the batch pipeline does: after
+// every batch_reads reads the columns below the last read's position are drained (a marker quadruple
+// (limit, -1, ref, 0) follows the segments of each drain), and a reference is finished as soon as its last read is in.
 int64_t biodb_debug_md_chain(const int32_t* ref_id, const int64_t* pos, const int64_t* end, const int64_t* dna_len, uint64_t n,
-                             int32_t skip_zero_coverage, int64_t* seg4, uint64_t cap) {
+                             int32_t skip_zero_coverage, uint64_t batch_reads, int64_t* seg4, uint64_t cap) {
   MdChain chain(skip_zero_coverage != 0);
   std::vector<MdSegment> segs;
-  for (uint64_t i = 0; i < n; ++i) chain.admit(i, ref_id[i], pos[i], end[i], dna_len[i], &segs);
+  for (uint64_t i = 0; i < n; ++i) {
+    chain.admit(i, ref_id[i], pos[i], end[i], dna_len[i], &segs);
+    if (!batch_reads) continue;
+    if (i + 1 == n || ref_id[i + 1] != ref_id[i]) {
+      chain.finish_reference(&segs);
+    } else if ((i + 1) % batch_reads == 0) {
+      chain.drain(pos[i], &segs);
+      segs.push_back(MdSegment{pos[i], -1, (uint64_t)(int64_t)ref_id[i], 0});
+    }
+  }
   chain.finish(&segs);
   for (uint64_t k = 0; k < segs.size() && k < cap; ++k) {
     seg4[4 * k] = segs[k].first;
@@ -969,6 +981,18 @@ int64_t biodb_debug_md_chain(const int32_t* ref_id, const int64_t* pos, const in
     seg4[4 * k + 3] = segs[k].offset;
   }
   return (int64_t)segs.size();
+}
+
+// Host-only: DnaWalk (md_walk.h) over one raw record body (the bytes after block_size); returns the length of
+// dna(read) and writes at most cap of its characters.
+int64_t biodb_debug_md_dna(const uint8_t* body, int64_t block_size, uint8_t* out, uint64_t cap) {
+  if (!body || block_size < 32) return -1;
+  DnaWalk w;
+  w.init(body, block_size);
+  int64_t n = 0;
+  for (int c; (c = w.next()) >= 0; ++n)
+    if ((uint64_t)n < cap && out) out[n] = (uint8_t)c;
+  return n;
 }
 
 biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset) {

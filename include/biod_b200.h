@@ -237,13 +237,19 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
  * [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks; [6..7] reserved. */
 biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset);
 
-/* Host-only building block of the MD-tag reference bases (row N1 of the plan, pileup.d:522-654; csrc/md_chain.h): which
- * read's dna() string supplies PileupColumn.reference_base at which positions.  Input: the n reads a pileup keeps, in
- * file order (reference id, position, end position, length of dna(read)).  Output: segments (first position, count,
- * read index, offset into that read's dna()) as int64 quadruples; positions outside every segment read 'N'.
- * Returns the number of segments (which may exceed cap).  Needs no GPU. */
+/* Host-only building blocks of the MD-tag reference bases (row N1 of the plan, pileup.d:522-654), exported so that the
+ * CPU test suite can check them against the oracle.  Neither needs a GPU.
+ * biodb_debug_md_chain (csrc/md_chain.h): which read's dna() string supplies PileupColumn.reference_base at which
+ * positions.  Input: the n reads a pileup keeps, in file order (reference id, position, end position, length of
+ * dna(read)).  Output: segments (first position, count, read index, offset into that read's dna()) as int64 quadruples;
+ * positions outside every segment read 'N'.  batch_reads > 0 drains the chain every batch_reads reads the way the batch
+ * pipeline does and marks each drain with a quadruple (limit, -1, ref, 0).  Returns the number of quadruples (which
+ * may exceed cap).
+ * biodb_debug_md_dna (csrc/md_walk.h): dna(read) (md/reconstruct.d:38-214) of one raw record body (the block_size bytes
+ * that follow the block_size field); returns its length and writes at most cap characters. */
 int64_t biodb_debug_md_chain(const int32_t* ref_id, const int64_t* pos, const int64_t* end, const int64_t* dna_len, uint64_t n,
-                             int32_t skip_zero_coverage, int64_t* seg4, uint64_t cap);
+                             int32_t skip_zero_coverage, uint64_t batch_reads, int64_t* seg4, uint64_t cap);
+int64_t biodb_debug_md_dna(const uint8_t* body, int64_t block_size, uint8_t* out, uint64_t cap);
 
 typedef struct biodb_dev_records {
   uint64_t capacity;     /* in: room (records) in each array below */

@@ -1,7 +1,13 @@
-"""MdChain (biod_b200/csrc/md_chain.h, C ABI hook biodb_debug_md_chain — host code, no GPU): the read-by-read scan that
-says which read's dna() supplies PileupColumn.reference_base where, checked against the oracle's column-by-column
-restatement of PileupRangeUsingMdTag (pileup.d:522-654) on the reference's own vectors and on random pileups."""
+"""Host halves of the MD-tag reference bases (row N1), checked on the CPU against the oracle:
+MdChain (biod_b200/csrc/md_chain.h, C ABI hook biodb_debug_md_chain): the read-by-read scan that says which read's dna()
+supplies PileupColumn.reference_base where, against the oracle's column-by-column restatement of PileupRangeUsingMdTag
+(pileup.d:522-654) on the reference's own vectors and on random pileups — in one go and drained batch by batch the way
+the pipeline does;
+DnaWalk (biod_b200/csrc/md_walk.h, hook biodb_debug_md_dna): the allocation-free generator of dna(read) that the CUDA
+kernels run per thread, compiled for the host here, against the oracle's string-based dna_of_read on the fixtures, on
+random reads and on malformed MD strings / tag areas."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -10,7 +16,7 @@ from bamutil import bam_record, make_bam, tag_z
 from oracle import oracle as orc
 
 
-def chain_reference(b, skip_zero, single_ref, start_from=0):
+def chain_reference(b, skip_zero, single_ref, start_from=0, batch_reads=0):
     """reference_base per (ref, position) from MdChain + the oracle's dna(read) strings."""
     from biod_b200 import _capi
     L = _capi.lib()
@@ -31,14 +37,20 @@ def chain_reference(b, skip_zero, single_ref, start_from=0):
     pos = np.array([b.pos[i] for i in keep], dtype=np.int64)
     end = np.array([b.end_pos[i] for i in keep], dtype=np.int64)
     ln = np.array([len(d) for d in dna], dtype=np.int64)
-    seg = np.zeros(4 * (4 * n + 8), dtype=np.int64)
+    seg = np.zeros(4 * (8 * n + 8), dtype=np.int64)
     m = L.biodb_debug_md_chain(ref.ctypes.data, pos.ctypes.data, end.ctypes.data, ln.ctypes.data, n, int(skip_zero),
-                               seg.ctypes.data, len(seg) // 4)
+                               batch_reads, seg.ctypes.data, len(seg) // 4)
     assert 0 <= m <= len(seg) // 4
     out = {}
+    settled = {}                     # per reference: columns below this position were handed out by an earlier drain
     for k in range(m):
         first, count, r, off = (int(x) for x in seg[4 * k:4 * k + 4])
+        if count == -1:              # a drain marker (limit, -1, ref, 0)
+            assert first >= settled.get(r, -1 << 62)
+            settled[r] = first
+            continue
         assert count > 0 and off >= 0 and off + count <= len(dna[r])
+        assert first >= settled.get(int(ref[r]), -1 << 62), "a segment reaches below an earlier drain"
         for q in range(count):
             key = (int(ref[r]), first + q)
             assert key not in out, "segments overlap"
@@ -51,10 +63,11 @@ def check(data, skip_zero, single_ref, start_from=0, end_at=2**64 - 1):
     p = (b.make_pileup(start_from, end_at, skip_zero, use_md_tag=True) if single_ref
          else b.pileup_columns(skip_zero, use_md_tag=True))
     assert p.status == 0
-    got = chain_reference(b, skip_zero, single_ref, start_from)
     want = "".join(chr(x) for x in p.ref_base)
-    mine = "".join(got.get((int(r), int(q)), "N") for r, q in zip(p.col_ref, p.col_pos))
-    assert mine == want
+    for batch_reads in (0, 1, 7, 64):
+        got = chain_reference(b, skip_zero, single_ref, start_from, batch_reads)
+        mine = "".join(got.get((int(r), int(q)), "N") for r, q in zip(p.col_ref, p.col_pos))
+        assert mine == want, batch_reads
     return p.n_columns
 
 
@@ -139,3 +152,99 @@ def test_random_pileups(seed, consistent):
         assert check(data, skip, False) > 0
         assert check(data, skip, True) > 0
         assert check(data, skip, True, start_from=int(rng.integers(50, 600))) > 0
+
+
+# ---- DnaWalk --------------------------------------------------------------------------------------------------------
+DATA = os.path.join(os.path.dirname(__file__), "golden", "biod_test_data")
+
+
+def walk_dna(body):
+    from biod_b200 import _capi
+    L = _capi.lib()
+    a = np.frombuffer(bytes(body) + b"\0" * 8, dtype=np.uint8)
+    out = np.zeros(1 << 16, dtype=np.uint8)
+    n = L.biodb_debug_md_dna(a.ctypes.data, len(body), out.ctypes.data, len(out))
+    assert 0 <= n <= len(out)
+    return out[:n].tobytes().decode("latin1")
+
+
+def check_dna(data, max_records=None):
+    b = orc.Bam(data).decode()
+    n = b.n_records if max_records is None else min(b.n_records, max_records)
+    some = 0
+    for i in range(n):
+        want = b.dna(i)
+        assert walk_dna(b.record_bytes(i)) == want, (i, b.tags_raw(i))
+        some += bool(want)
+    return some
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "illu_20_chunk.bam", "tags.bam", "bins.bam", "mg1655_chunk.bam"])
+def test_dna_walk_fixtures(name):
+    path = os.path.join(DATA, name)
+    if not os.path.exists(path):
+        pytest.skip("fixture not present")
+    with open(path, "rb") as f:
+        check_dna(f.read(), 1500)
+
+
+def test_dna_walk_reference_vectors():
+    from test_oracle_golden import pileup_vector_bam
+    assert check_dna(pileup_vector_bam()) > 0
+
+
+@pytest.mark.parametrize("consistent", [True, False])
+def test_dna_walk_random_reads(consistent):
+    rng = np.random.default_rng(7)
+    assert check_dna(random_pileup(rng, 600, refs=2, consistent=consistent)) > 0
+
+
+def test_dna_walk_malformed_md_strings():
+    """MD values no aligner writes: the bidirectional quirks of mdOperations (last operation parsed from the back),
+    zero-length matches at either end, deletions without '^', every byte value as a mismatch character, huge counts."""
+    rng = np.random.default_rng(11)
+    alphabet = "0123456789^ACGTNacgtn=RYKMxz*"
+    mds = ["", "0", "00", "10", "5A", "A", "^", "^A", "^AC", "0A0", "0^AC0", "3^AC", "^AC3", "AC", "ACGT", "3AC", "3^", "^3",
+           "3^^A2", "2A^", "1^A^C1", "99999999999", "4294967296", "0A0C0G0T0", "5^acgt5", "=5", "5=", "3a2", "A^C", "^C^", "1A1^",
+           "12^^", "0^0", "10^AC^GT10", "z", "*5", "5*", "1 2", "1\x80\xff2", "\x01"]
+    for _ in range(400):
+        mds.append("".join(alphabet[k] for k in rng.integers(0, len(alphabet), int(rng.integers(1, 12)))))
+    for v in range(1, 256):
+        if v not in (0,):
+            mds.append("2" + chr(v) + "2")
+    recs = []
+    for k, md in enumerate(mds):
+        cig = ["12M", "4S8M", "3M2I4M1D5M", "5M10N5M2S", "2=1X9M", "6M6D6M"][k % 6]
+        lq = sum(l for l, o in [(int(x[:-1]), x[-1]) for x in __import__("re").findall(r"\d+[A-Z=]", cig)] if o in "MIS=X")
+        seq = "".join("ACGT"[x] for x in rng.integers(0, 4, lq))
+        tags = tag_z("XA", "q") + b"MDZ" + md.encode("latin1") + b"\0" + b"NMC\x01"
+        recs.append(bam_record(f"m{k}", seq, cig, 10 + k, tags=tags))
+    assert check_dna(make_bam([("c0", 100000)], recs)) > 0
+
+
+def test_dna_walk_tag_areas():
+    """The tag walk in front of MD: every value type, arrays, an MD that is not a string, truncated areas, SEQ '*'."""
+    import struct
+    arr = b"XBB" + b"s" + struct.pack("<I", 3) + struct.pack("<3h", 1, -2, 3)
+    areas = [
+        b"",
+        b"MD",
+        b"MDZ",
+        b"MDZ5",
+        b"MDZ5\0",
+        b"XAA!" + b"XcC\x07" + b"XsS\x01\x02" + b"XiI\x01\x02\x03\x04" + b"Xff\0\0\x80\x3f" + arr + b"XHH1AE3\0" + b"MDZ3A2\0",
+        b"MDi\x05\0\0\0" + b"MDZ6\0",
+        b"MDH0A\0",
+        b"XB" + b"B" + b"q" + struct.pack("<I", 1) + b"\0" + b"MDZ6\0",
+        b"XBBi" + struct.pack("<I", 1000) + b"MDZ6\0",
+        b"XZZunterminated",
+        b"X?!\0MDZ6\0",
+        b"MDBc" + struct.pack("<I", 2) + b"\x01\x02" + b"MDZ6\0",
+        b"XAAqMDZ2^AC4\0XBA!",
+    ]
+    recs = []
+    for k, t in enumerate(areas):
+        recs.append(bam_record(f"t{k}", "ACGTAC", "6M", 5 + k, tags=t))
+    recs.append(bam_record("star", "", "6M", 40, tags=b"MDZ6\0"))                    # SEQ '*' with a CIGAR
+    recs.append(bam_record("long", "ACGTACGTAC", "10M", 41, tags=b"MDZ4^ACGT6A20\0"))   # MD longer than the read
+    assert check_dna(make_bam([("c0", 100000)], recs)) > 0
