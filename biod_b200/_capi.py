@@ -60,7 +60,8 @@ class ColumnBatch(C.Structure):
                 ("read_idx", u32p), ("base", u8p), ("qual", u8p), ("query_offset", u32p), ("counts", u32p),
                 ("last_read", u32p), ("live_mask", u64p), ("n_stragglers", C.c_uint64), ("strag_col", u32p), ("strag_idx", u32p),
                 ("n_runs", C.c_uint64), ("run_pos", u64p), ("run_first_col", u32p),
-                ("base4", u8p), ("n_special", C.c_uint64), ("special_entry", u32p), ("special_base", u8p)]
+                ("base4", u8p), ("n_special", C.c_uint64), ("special_entry", u32p), ("special_base", u8p),
+                ("reference_base", u8p)]
 
 
 _lib = None

@@ -276,6 +276,8 @@ class BamReader:
             st = L.biodb_pileup_begin_shard(self._h, C.byref(p), shard[0], shard[1], halo_blocks, C.byref(pl))
         else:
             st = L.biodb_pileup_begin(self._h, C.byref(p), C.byref(pl))
+        if st == capi.ERR_ARG:
+            raise ValueError("biodb_pileup_begin: invalid arguments (use_md_tag is not available for shards)")
         if st != capi.OK:
             self._err()
         try:
@@ -386,6 +388,8 @@ class ColumnBatch:
         self.qual = g(_np(cb.qual, ne, np.uint8))
         self.query_offset = g(_np(cb.query_offset, ne, np.uint32)) if cb.query_offset else None
         self.counts = g(_np(cb.counts, nc * 6, np.uint32)).reshape(nc, 6) if cb.counts else None
+        # use_md_tag: PileupColumn.reference_base per column (pileup.d:252-254)
+        self.reference_base = g(_np(cb.reference_base, nc, np.uint8)) if cb.reference_base else None
 
 
 class PileupColumn:
@@ -401,7 +405,12 @@ class PileupColumn:
 
     position = property(lambda s: int(s._b.position[s._c]))
     ref_id = property(lambda s: s._b.ref_id)
-    reference_base = "N"
+
+    @property
+    def reference_base(self):
+        """pileup.d:252-254; 'N' unless the pileup was made with use_md_tag (PileupColumn's default, pileup.d:239)."""
+        rb = self._b.reference_base
+        return "N" if rb is None else chr(int(rb[self._c]))
 
     @property
     def coverage(self):

@@ -7,7 +7,7 @@
 //
 // DnaWalk is a generator with O(1) state that works directly on the raw record bytes — no strings, no allocation —
 // so the same code runs in a CUDA thread (csrc/mdtag.cu) and on the host (biodb_debug_md_dna, used by the CPU tests to
-// check it against the oracle's string-based restatement before any GPU is involved).
+// check it against the test suite's CPU restatement before any GPU is involved).
 #pragma once
 #include <stdint.h>
 
@@ -203,23 +203,25 @@ struct DnaWalk {
   bool done;
 
   BIODB_HD void init(const uint8_t* body, int64_t block_size) {
+    k = 0;
+    nc = 0;
+    lseq = qoff = qi = qend = 0;
+    di = 0;
+    done = true;
+    cg = seq = nullptr;
+    ops.lo = ops.hi = nullptr;
+    ops.rem = 0;
+    ops.f = ops.b = cur = MdOpV{0, 0, 0, nullptr, 0};
+    if (block_size < 32) return;
     const uint32_t lname = body[8];
     nc = (uint32_t)body[12] | ((uint32_t)body[13] << 8);
     lseq = (int32_t)md_le32(body + 16);
     cg = body + 32 + lname;
     seq = cg + 4ull * nc;
-    k = 0;
-    qoff = 0;
-    qi = qend = 0;
-    di = 0;
-    done = true;
-    ops.lo = ops.hi = nullptr;
-    ops.rem = 0;
-    ops.f = ops.b = cur = MdOpV{0, 0, 0, nullptr, 0};
     const uint64_t ls = lseq > 0 ? (uint64_t)lseq : 0;
     const uint64_t off = 32ull + lname + 4ull * nc + (ls + 1) / 2 + ls;
     const uint8_t *vb = nullptr, *ve = nullptr;
-    if (block_size < 0 || off > (uint64_t)block_size) return;
+    if (off > (uint64_t)block_size) return;
     if (!md_find_tag(body + off, (uint64_t)block_size - off, &vb, &ve)) return;
     ops.init(vb, ve);
     done = !ops.take(&cur);

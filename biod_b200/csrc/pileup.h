@@ -81,6 +81,26 @@ struct CarryOut {
   uint8_t* data;
 };
 
+// ---- mdtag.cu: reference bases from MD tags (row N1) ------------------------------------------------------------
+struct MdSeg {                   // = MdSegment of md_chain.h: reference_base[P] = dna(read)[offset + (P - first)], P in [first, first+count)
+  int64_t first, count;
+  uint64_t read;                 // file-order index of the provider
+  int64_t offset;
+};
+struct MdKeep {                  // dna() strings of providers that outlive the record bytes of their batch
+  uint64_t id[2];                // file-order index, ~0 = empty slot
+  uint32_t len[2];
+  const uint8_t* data[2];
+};
+// dna_len[j] = length of dna(read j) for the live reads of [a0, g1), 0 for the others
+void md_dna_lengths(const ReadsView& v, const int32_t* block_size, const int32_t* eend, uint32_t a0, uint32_t g1,
+                    int32_t* dna_len, cudaStream_t st);
+// ref_base[c] (preset to 'N') of the columns covered by the segments
+void md_replay(const ReadsView& v, const int32_t* block_size, const MdSeg* segs, uint32_t n_segs, const MdKeep& keep,
+               const uint64_t* col_pos, uint32_t n_col, uint8_t* ref_base, cudaStream_t st);
+// materialise the dna() of new_keep.id[k] (len[k] characters) into new_keep.data[k]
+void md_keep(const ReadsView& v, const int32_t* block_size, const MdKeep& old_keep, const MdKeep& new_keep, cudaStream_t st);
+
 void pileup_max_end(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, uint32_t n, const uint64_t* n_head_ptr,
                     int32_t ref, int32_t* out, cudaStream_t st);
 void pileup_find_groups(const ReadsView& v, uint32_t* boundaries, uint32_t* n_boundaries, uint32_t cap, cudaStream_t st);

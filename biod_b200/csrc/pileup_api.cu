@@ -11,6 +11,9 @@
 #include <thread>
 #include <vector>
 
+#include <memory>
+
+#include "md_chain.h"
 #include "runtime.h"
 #include "scan.cuh"
 
@@ -36,10 +39,11 @@ struct CarryBufs {
 // asynchronous copy on the copy stream.  Two sets alternate so that batch k+1 is computed and copied while
 // the caller still reads batch k.
 struct OutSet {
-  DevBuf d[20];     // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts, last_read, live_mask, strag_off,
-                    // strag_idx, strag_col, run_pos, run_first_col, base4, block_special, block_off, special_entry, special_base
-  PinBuf h[16];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, run_pos,
-                    // strag_idx, strag_col, run_first_col, base4, special_entry, special_base
+  DevBuf d[21];     // col_pos, col_off, nstart, read_idx, base, qual, qoff, counts, last_read, live_mask, strag_off,
+                    // strag_idx, strag_col, run_pos, run_first_col, base4, block_special, block_off, special_entry, special_base,
+                    // reference_base
+  PinBuf h[17];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, run_pos,
+                    // strag_idx, strag_col, run_first_col, base4, special_entry, special_base, reference_base
   uint32_t n_strag = 0, n_runs = 0, n_special = 0;
   size_t col_cap = 0, ent_cap = 0;
   cudaEvent_t computed = nullptr, done = nullptr;
@@ -72,6 +76,13 @@ struct biodb_pileup {
   uint64_t tail_coffset = 0;         // first block of the shard's last `halo_blocks` blocks
   DevBuf d_maxend;                   // [2] int32 maxima + u64 scratch
   DevBuf pack_tmp;                   // scan scratch of the base packing (compact_reads)
+  // reference bases from MD tags (use_md_tag; mdtag.cu, md_chain.h)
+  std::unique_ptr<MdChain> md;       // which read's dna() serves which positions; its state runs across batches
+  std::vector<MdSegment> md_segs;    // segments of the group being produced
+  DevBuf md_len, md_dsegs, md_keep_buf[2][2];
+  PinBuf md_h, md_hsegs;
+  MdKeep md_keep{{~0ull, ~0ull}, {0, 0}, {nullptr, nullptr}};   // providers materialised by the previous batch
+  int md_keep_set = 0;
   // single_ref state
   bool started = false, done = false;
   int32_t target_ref = -1;
@@ -291,6 +302,10 @@ void biodb_pileup::reset(const biodb_pileup_params* p) {
   memset(&shard, 0, sizeof shard);
   halo_blocks_left = 0;
   index_bias = 0;
+  md.reset(prm.use_md_tag ? new MdChain(prm.skip_zero_coverage != 0) : nullptr);
+  md_segs.clear();
+  md_keep.id[0] = md_keep.id[1] = ~0ull;
+  md_keep_set = 0;
 }
 
 static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* cols);
@@ -374,6 +389,8 @@ static biodb_status peek_first_record(biodb_reader* r, uint64_t coffset, int32_t
 biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
                                       uint32_t halo_blocks, biodb_pileup** out) {
   if (!r || !out || n_shards == 0 || shard >= n_shards) return BIODB_ERR_ARG;
+  // the chain of MD providers depends on every read since the start of the reference: a shard cannot know it
+  if (prm && prm->use_md_tag) return BIODB_ERR_ARG;
   biodb_pileup_params p2;
   if (prm) p2 = *prm; else { memset(&p2, 0, sizeof p2); p2.skip_zero_coverage = 1; }
   p2.single_ref = 0;                       // pileupColumns semantics
@@ -590,6 +607,24 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     p.stage_begin();
     pileup_phase1(v, g0, g1, drop_before, skip_zero, clo, chi, s, st);
     p.stage_end(&p.stats.pileup_ms);
+    // use_md_tag: length of dna(read) of the reads that are new in this batch (carried ones were fed to the chain by
+    // the batch they came with), brought to the host with their positions by the sync below
+    const bool use_md = pl->md != nullptr;
+    const uint32_t md_a0 = std::max(g0, pl->n_carry_view);
+    const size_t md_n = (use_md && md_a0 < g1) ? g1 - md_a0 : 0;
+    if (md_n) {
+      RecordArrays a = p.arrays(0);
+      PL_TRY(pl->md_len.ensure(pl->read_cap * 4, st));
+      PL_TRY(pl->md_h.ensure(md_n * 12 + 64));
+      p.stage_begin();
+      md_dna_lengths(v, a.block_size, s.eend, md_a0, g1, pl->md_len.as<int32_t>(), st);
+      p.stage_end(&p.stats.pileup_ms);
+      int32_t* hm = pl->md_h.as<int32_t>();
+      PL_TRY(launch_copy_bytes(hm, v.pos + md_a0, md_n * 4, st));
+      PL_TRY(launch_copy_bytes(hm + md_n, s.eend + md_a0, md_n * 4, st));
+      PL_TRY(launch_copy_bytes(hm + 2 * md_n, pl->md_len.as<int32_t>() + md_a0, md_n * 4, st));
+      p.stats.d2h_bytes += md_n * 12;
+    }
     const uint32_t ng = g1 - g0;
     const uint32_t t_reads = (uint32_t)((ng + SCAN_TILE - 1) / SCAN_TILE);
     PL_TRY(launch_copy_bytes(h, s.tmp_u32 + t_reads, 4, st));           // n_islands
@@ -615,6 +650,20 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       PL_TRY(cudaStreamSynchronize(st));
       E = h[0];
       chi = std::min(chi, E);
+    }
+    if (use_md) {
+      // the chain over the new reads: segments "positions [first, first+count) read dna(read)[offset...]".  A group that
+      // later batches continue is drained up to E, the position its columns stop at; a complete one is finished.
+      pl->md_segs.clear();
+      const int32_t* hm = pl->md_h.as<int32_t>();
+      const uint64_t id0 = pl->first_index + (md_a0 - pl->n_carry_view);
+      for (size_t k = 0; k < md_n; ++k) {
+        const int32_t e = hm[md_n + k];
+        if (e == INT32_MIN) continue;                                  // not a read of the pileup
+        pl->md->admit(id0 + k, ref, hm[k], e, hm[2 * md_n + k], &pl->md_segs);
+      }
+      if (trailing) pl->md->drain(E, &pl->md_segs);
+      else pl->md->finish_reference(&pl->md_segs);
     }
     s.clo = clo;
     s.chi = chi;
@@ -706,6 +755,26 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       p.stage_begin();
       pileup_entries(v, n_col, s, c, o, st);
       p.stage_end(&p.stats.pileup_ms);
+      if (use_md) {
+        // reference_base: 'N' everywhere, then the providers' dna() replayed over the columns their segments cover
+        static_assert(sizeof(MdSegment) == sizeof(MdSeg), "MdSegment is uploaded as MdSeg");
+        const size_t nseg = pl->md_segs.size();
+        PL_TRY(os.d[20].ensure(os.col_cap, st));
+        if (!p.r->opts.device_output) PL_TRY(os.h[16].ensure(os.col_cap));
+        PL_TRY(cudaMemsetAsync(os.d[20].p, 'N', n_col, st));
+        if (nseg) {
+          RecordArrays a = p.arrays(0);
+          PL_TRY(pl->md_dsegs.ensure(nseg * sizeof(MdSeg), st));
+          PL_TRY(pl->md_hsegs.ensure(nseg * sizeof(MdSeg)));
+          memcpy(pl->md_hsegs.p, pl->md_segs.data(), nseg * sizeof(MdSeg));
+          PL_TRY(launch_copy_bytes(pl->md_dsegs.p, pl->md_hsegs.p, nseg * sizeof(MdSeg), st));
+          p.stats.h2d_bytes += nseg * sizeof(MdSeg);
+          p.stage_begin();
+          md_replay(v, a.block_size, pl->md_dsegs.as<MdSeg>(), (uint32_t)nseg, pl->md_keep, o.col_pos, n_col,
+                    os.d[20].as<uint8_t>(), st);
+          p.stage_end(&p.stats.pileup_ms);
+        }
+      }
       os.n_strag = 0;
       os.n_runs = 0;
       os.n_special = 0;
@@ -803,6 +872,10 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
           }
         }
         if (want_q) PL_TRY(cudaMemcpyAsync(os.h[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
+        if (use_md) {
+          PL_TRY(cudaMemcpyAsync(os.h[16].p, os.d[20].p, (size_t)n_col, cudaMemcpyDeviceToHost, cs));
+          p.stats.d2h_bytes += n_col;
+        }
         PL_TRY(cudaEventRecord(os.done, cs));
       } else {
         PL_TRY(cudaEventRecord(os.done, st));
@@ -810,6 +883,28 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       PL_TRY(launch_copy_bytes(h + 8, s.info, 4, st));
       PL_TRY(cudaStreamSynchronize(st));
       if (h[8] != 0) return pl->fail(h[8], "Invalid read - query offset beyond the sequence while building a column");
+    }
+    if (use_md) {
+      // providers whose dna() later batches may still ask for: write the strings out now, while the records are here
+      MdKeep nk{{~0ull, ~0ull}, {0, 0}, {nullptr, nullptr}};
+      if (trailing) {
+        uint64_t ids[2];
+        int64_t lens[2];
+        const int np = pl->md->live_providers(ids, lens);
+        const int set = pl->md_keep_set ^ 1;
+        for (int k = 0; k < np; ++k) {
+          nk.id[k] = ids[k];
+          nk.len[k] = (uint32_t)std::min<int64_t>(std::max<int64_t>(lens[k], 0), 0x7fffffff);
+          PL_TRY(pl->md_keep_buf[set][k].ensure((size_t)nk.len[k] + 16, st));
+          nk.data[k] = pl->md_keep_buf[set][k].as<uint8_t>();
+        }
+        if (np) {
+          RecordArrays a = p.arrays(0);
+          md_keep(v, a.block_size, pl->md_keep, nk, st);
+        }
+        pl->md_keep_set = set;
+      }
+      pl->md_keep = nk;
     }
     // ---- carry reads that reach past this batch ---------------------------------------------------------------
     bool stop_after = false;
@@ -885,6 +980,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         cols->run_pos = os.d[13].as<uint64_t>();
         cols->run_first_col = os.d[14].as<uint32_t>();
       }
+      cols->reference_base = use_md ? os.d[20].as<uint8_t>() : nullptr;
       return BIODB_OK;
     }
     cols->position = os.h[0].as<uint64_t>();
@@ -912,6 +1008,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       cols->run_pos = os.h[9].as<uint64_t>();
       cols->run_first_col = os.h[12].as<uint32_t>();
     }
+    cols->reference_base = use_md ? os.h[16].as<uint8_t>() : nullptr;
     return BIODB_OK;
   }
 }

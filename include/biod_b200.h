@@ -127,7 +127,8 @@ float biodb_reads_progress(const biodb_reads* it);
 typedef struct biodb_pileup_params {
   int32_t single_ref;          /* 1 = makePileup (first reference only, pileup.d:490-494); 0 = pileupColumns */
   int32_t skip_zero_coverage;  /* pileup.d:389-392 */
-  int32_t use_md_tag;          /* accepted; reference bases are reconstructed by the host binding (next row N1) */
+  int32_t use_md_tag;          /* 1 = also reconstruct PileupColumn.reference_base from the reads' MD tags
+                                  (PileupRangeUsingMdTag, pileup.d:522-654); not available for shards */
   int32_t want_query_offset;   /* 1 = also return PileupRead.query_offset per entry (pileup.d:146-149) */
   uint64_t start_from;         /* pileup.d:482-489,497-504 (single_ref only) */
   uint64_t end_at;             /* pileup.d:505 (single_ref only); UINT64_MAX = none */
@@ -175,6 +176,9 @@ typedef struct biodb_column_batch {
   uint64_t n_special;
   const uint32_t* special_entry; /* [n_special] */
   const uint8_t* special_base;   /* [n_special] */
+  /* use_md_tag = 1 (any encoding): PileupColumn.reference_base per column (pileup.d:252-254,614-653), 'N' where no
+   * read's MD tag supplies it; NULL otherwise (BioD's default column has 'N', pileup.d:239). */
+  const uint8_t* reference_base; /* [n_columns] */
 } biodb_column_batch;
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);

@@ -32,8 +32,12 @@ def gpu_records(data, blocks_per_batch=0, want_offsets=True):
 
 def gpu_pileup(data, single_ref, blocks_per_batch=0, **kw):
     rd = BamReader(data, blocks_per_batch=blocks_per_batch)
-    pos, ref, cov, nstart, ridx, base, qual, qoff = [], [], [], [], [], [], [], []
+    pos, ref, cov, nstart, ridx, base, qual, qoff, refb = [], [], [], [], [], [], [], [], []
     for b in rd.column_batches(single_ref, want_query_offset=True, copy=True, **kw):
+        if b.reference_base is not None:
+            refb.append(b.reference_base)
+        else:
+            assert not kw.get("use_md_tag"), "use_md_tag batches must carry reference_base"
         pos.append(b.position)
         ref.append(np.full(b.n_columns, b.ref_id, dtype=np.int32))
         cov.append(np.diff(b.col_off).astype(np.uint64))
@@ -47,7 +51,7 @@ def gpu_pileup(data, single_ref, blocks_per_batch=0, **kw):
     return dict(col_pos=cat(pos, np.uint64), col_ref=cat(ref, np.int32), cov=cov,
                 col_off=np.concatenate([[0], np.cumsum(cov)]).astype(np.uint64), n_start=cat(nstart, np.uint32),
                 read_idx=cat(ridx, np.uint32), base=cat(base, np.uint8), qual=cat(qual, np.uint8),
-                qoff=cat(qoff, np.uint32))
+                qoff=cat(qoff, np.uint32), ref_base=cat(refb, np.uint8))
 
 
 def assert_pileup_equal(g, o):

@@ -79,7 +79,7 @@ def test_reference_vectors():
         assert check(pileup_vector_bam(), skip, False) > 0
 
 
-def random_pileup(rng, n_reads, refs=2, consistent=True, gap_p=0.02, dup_p=0.15):
+def random_pileup(rng, n_reads, refs=2, consistent=True, gap_p=0.02, dup_p=0.15, **bam_kw):
     """Reads with M / I / D / S / N operations and MD tags written against a random reference."""
     recs = []
     for rid in range(refs):
@@ -140,7 +140,7 @@ def random_pileup(rng, n_reads, refs=2, consistent=True, gap_p=0.02, dup_p=0.15)
                     tags = tag_z("MD", mds + "A7")                    # longer than the read
             cig = "".join(f"{n}{o}" for n, o in ops)
             recs.append(bam_record(f"r{rid}_{k}", "".join(seq), cig, pos, ref_id=rid, tags=tags))
-    return make_bam([(f"c{i}", 100000) for i in range(refs)], recs)
+    return make_bam([(f"c{i}", 100000) for i in range(refs)], recs, **bam_kw)
 
 
 @pytest.mark.parametrize("seed", range(6))
