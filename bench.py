@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--straddle", action="store_true", help="htsjdk-style file: records cut across BGZF blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--md", action="store_true",
+                    help="also time the pass with use_md_tag (reference bases from MD tags, row N1); 1 GPU only")
     ap.add_argument("--cache-dir", default=os.environ.get("BIODB_BENCH_CACHE", "/dev/shm"))
     return ap.parse_args()
 
@@ -125,12 +127,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_pass(L, capi, reader, shard=None, info=None, compact=False):
+def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False):
     """One full pileup pass (pileupColumns); shard=(rank, world) runs this rank's block-range shard of it.
     Returns (stats, n_records, n_cols, n_entries)."""
     p = capi.PileupParams()
     p.single_ref, p.skip_zero_coverage, p.end_at = 0, 1, 2**64 - 1
     p.compact_reads = int(compact)
+    p.use_md_tag = int(use_md)
     pl = C.c_void_p()
     if shard is not None and shard[1] > 1:
         st = L.biodb_pileup_begin_shard(reader, C.byref(p), shard[0], shard[1], 8, C.byref(pl))
@@ -275,6 +278,11 @@ def main():
     barrier()
     wall = time.time() - t0
     clocks = sampler.stop()
+    md_steps = None
+    if args.md and world == 1:
+        # the same device-resident pass with PileupColumn.reference_base rebuilt from the MD tags (use_md_tag)
+        run_pass(L, capi, rd, shard, use_md=True)
+        md_steps = [run_pass(L, capi, rd, shard, use_md=True) for _ in range(args.steps)]
     L.biodb_close(rd)
     dev_ms = sum(s[0].total_ms for s in steps)
     tt = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
@@ -356,6 +364,14 @@ def main():
             "inflate_out_gbs": s0.uncompressed_bytes / (infl_ms * 1e-3) / 1e9,
             "roofline": roofline, "gpu_launches": int(sum(s[0].kernel_launches for s in steps)), "clocks": clocks}
 
+    if md_steps:
+        md_ms = float(np.mean([s[0].total_ms for s in md_steps]))
+        line["md_reference_bases"] = {
+            "value": md_steps[-1][2] / (md_ms * 1e-3), "unit": "positions/s", "ms_per_step": md_ms,
+            "pileup_stage_ms": float(np.mean([s[0].pileup_ms for s in md_steps])),
+            "d2h_bytes_per_step": int(md_steps[-1][0].d2h_bytes), "h2d_bytes_per_step": int(md_steps[-1][0].h2d_bytes),
+            "what": "same device-resident pass with use_md_tag: dna() length per read on the GPU, provider chain on the host "
+                    "(12 B per read device->host), segment replay into reference_base[] on the GPU"}
     # diagnostics of the lane-parallel inflate kernel over everything run so far (0 blocks given up = no fallback)
     try:
         cnt = (C.c_uint64 * 8)()

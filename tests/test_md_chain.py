@@ -83,7 +83,7 @@ def random_pileup(rng, n_reads, refs=2, consistent=True, gap_p=0.02, dup_p=0.15,
     """Reads with M / I / D / S / N operations and MD tags written against a random reference."""
     recs = []
     for rid in range(refs):
-        genome = "".join("ACGT"[k] for k in rng.integers(0, 4, 6000))
+        genome = "".join("ACGT"[k] for k in rng.integers(0, 4, 6000 + 12 * n_reads))
         pos = int(rng.integers(0, 30))
         for k in range(n_reads // refs):
             if rng.random() > dup_p:
