@@ -55,6 +55,7 @@ extern (C) nothrow @nogc {
         const(uint)* last_read; const(ulong)* live_mask; ulong n_stragglers; const(uint)* strag_col; const(uint)* strag_idx;
         ulong n_runs; const(ulong)* run_pos; const(uint)* run_first_col;
         const(ubyte)* base4; ulong n_special; const(uint)* special_entry; const(ubyte)* special_base;
+        const(ubyte)* reference_base;   // use_md_tag: one per column (pileup.d:252-254), else null
     }
     void biodb_default_options(biodb_options*);
     int biodb_open(const(char)* path, const(biodb_options)*, biodb_reader**);
@@ -177,7 +178,8 @@ struct GpuPileupColumn {
     ulong position() @property const { return _pos; }
     int ref_id() @property const { return _b.ref_id; }
     size_t coverage() @property const { return _cov; }
-    char reference_base() @property const { return 'N'; }
+    /// pileup.d:252-254; 'N' (PileupColumn's default, pileup.d:239) unless the pileup was made with use_md_tag
+    char reference_base() @property const { return _b.reference_base is null ? 'N' : cast(char)_b.reference_base[_c]; }
     /// Record indices of the reads of the column, in file order.
     const(uint)[] reads() @property const {
         if (_b.read_idx !is null) return _b.read_idx[_off .. _off + _cov];
