@@ -38,7 +38,8 @@ enum {
   ORC_ERR_FORMAT = -3,  // plain Exception (bam/reader.d:113, bgzf/block.d:150)
   ORC_ERR_TRUNC = -4,   // ReadException from readExact (bam/readrange.d:169)
   ORC_ERR_CIGAR = -7,   // PileupRead.assertCigarIndexIsValid (bam/pileup.d:224-228)
-  ORC_ERR_UNSORTED = -8 // not a reference error: input order the engine assumes
+  ORC_ERR_UNSORTED = -8, // not a reference error: input order the engine assumes
+  ORC_ERR_ARG = -9      // enforce() on arguments (randomaccessmanager.d:206-208)
 };
 
 const uint32_t BGZF_MAX_BLOCK_SIZE = 65536;  // bio/core/bgzf/constants.d:60
@@ -816,6 +817,215 @@ Pileup* run_pileup(const Bam* s, int single_ref, uint64_t start_from, uint64_t e
 
 }  // namespace
 
+
+// ----------------------------------------------------- BAI random access ----
+// SURVEY.md §8f row N2 (oracle side).  BaiFile.parse (bam/baifile.d:126-169), Index.getMinimumOffset (:77-82),
+// Bin.canOverlapWith (bai/bin.d:49-78), RandomAccessManager.getChunks / appendChunks (randomaccessmanager.d:211-244),
+// nonOverlapping (core/utils/algo.d:95-162), StreamChunksSupplier (bgzf/inputstream.d:257-345) feeding the record
+// framing of readrange.d:118-173, BamReadFilter (randomaccessmanager.d:366-462), getReadsBetween (:186-196).
+namespace {
+
+struct BaiBin { uint32_t id; std::vector<std::pair<uint64_t, uint64_t>> chunks; };
+struct BaiIndex { std::vector<BaiBin> bins; std::vector<uint64_t> ioffsets; };
+struct Bai {
+  int status = 0;
+  std::string msg;
+  std::vector<BaiIndex> idx;
+};
+
+inline uint64_t le64(const uint8_t* p) { return (uint64_t)le32(p) | ((uint64_t)le32(p + 4) << 32); }
+
+Bai* bai_parse(const uint8_t* d, uint64_t n) {            // baifile.d:126-169
+  Bai* b = new Bai;
+  uint64_t o = 0;
+  auto need = [&](uint64_t k) {
+    if (b->status) return false;
+    if (n - o < k || o > n) { b->status = ORC_ERR_TRUNC; b->msg = "not enough data in stream"; return false; }   // Stream.readExact
+    return true;
+  };
+  if (!need(4)) return b;
+  if (memcmp(d, "BAI\1", 4) != 0) { b->status = ORC_ERR_FORMAT; b->msg = "Invalid file format: expected BAI\\1"; return b; }
+  o = 4;
+  if (!need(4)) return b;
+  const int32_t n_ref = (int32_t)le32(d + o);
+  o += 4;
+  for (int32_t i = 0; i < n_ref && !b->status; ++i) {
+    BaiIndex ix;
+    if (!need(4)) break;
+    const int32_t n_bin = (int32_t)le32(d + o);
+    o += 4;
+    for (int32_t j = 0; j < n_bin; ++j) {
+      if (!need(8)) break;
+      BaiBin bin;
+      bin.id = le32(d + o);
+      const int32_t n_chunk = (int32_t)le32(d + o + 4);
+      o += 8;
+      for (int32_t k = 0; k < n_chunk; ++k) {
+        if (!need(16)) break;
+        bin.chunks.push_back({le64(d + o), le64(d + o + 8)});
+        o += 16;
+      }
+      if (b->status) break;
+      ix.bins.push_back(std::move(bin));
+    }
+    if (b->status || !need(4)) break;
+    const int32_t n_intv = (int32_t)le32(d + o);
+    o += 4;
+    for (int32_t j = 0; j < n_intv; ++j) {
+      if (!need(8)) break;
+      ix.ioffsets.push_back(le64(d + o));
+      o += 8;
+    }
+    if (b->status) break;
+    b->idx.push_back(std::move(ix));
+  }
+  return b;
+}
+
+bool bin_can_overlap(uint32_t id, int32_t begin, int32_t end) {      // bai/bin.d:49-78
+  if (id == 0) return true;
+  if (id > 37449) return false;                                       // BAI_MAX_BIN_ID
+  if (begin < 0) begin = 0;
+  int32_t magic = 4681;
+  int32_t b = begin >> 14, e = end >> 14;
+  while (true) {
+    const uint32_t delta = id - (uint32_t)magic;                      // uint - int in D: unsigned arithmetic and comparisons
+    if ((uint32_t)b <= delta && delta <= (uint32_t)e) return true;
+    magic >>= 3;
+    if (magic == 0) return false;
+    b >>= 3;
+    e >>= 3;
+  }
+}
+
+typedef std::pair<uint64_t, uint64_t> Chunk;    // (beg, end) virtual offsets; compares like Chunk.opCmp (bgzf/chunk.d:34-40)
+
+std::vector<Chunk> region_chunks(const Bai* bai, uint32_t ref_id, uint32_t beg, uint32_t end, int* status) {   // :222-244
+  std::vector<Chunk> out;
+  if (ref_id >= bai->idx.size()) { *status = ORC_ERR_ARG; return out; }          // "Invalid reference sequence index"
+  const BaiIndex& ix = bai->idx[ref_id];
+  // getMinimumOffset(int position), baifile.d:77-82
+  const int32_t pos = std::max(0, (int32_t)beg);
+  const int32_t i = std::min(pos / 16384, (int32_t)ix.ioffsets.size() - 1);
+  const uint64_t min_offset = i == -1 ? 0 : ix.ioffsets[(size_t)i];
+  for (const BaiBin& b : ix.bins) {
+    if (!bin_can_overlap(b.id, (int32_t)beg, (int32_t)end)) continue;
+    for (const Chunk& c : b.chunks)                                              // appendChunks :211-220
+      if (c.second > min_offset) out.push_back({std::max(c.first, min_offset), c.second});
+  }
+  std::sort(out.begin(), out.end());
+  std::vector<Chunk> merged;                                                     // algo.d:95-140
+  for (const Chunk& c : out) {
+    if (!merged.empty() && merged.back().second >= c.first) merged.back().second = std::max(merged.back().second, c.second);
+    else merged.push_back(c);
+  }
+  return merged;
+}
+
+struct RegionRead { int64_t index; uint64_t start_vo, end_vo; int32_t ref_id, pos, end_pos; };
+
+// The byte stream StreamChunksSupplier + BgzfInputStream present for a chunk list, framed into records.
+// `until_vo`: getReadsBetween's `until!offsetTooBig` (records whose end offset is beyond it are cut off), ~0 = none.
+int chunk_stream_reads(Bam* s, std::vector<Chunk> chunks, uint64_t until_vo, std::vector<RegionRead>* out) {
+  decode_records(s);            // the whole file: block table + the record table the indices refer to
+  struct Piece { uint64_t cat, coffset, cend; uint32_t within, len; };
+  std::vector<uint8_t> cat;
+  std::vector<Piece> pieces;
+  auto block_at = [&](uint64_t coffset) -> const Block* {
+    size_t lo = 0, hi = s->blocks.size();
+    while (lo < hi) { size_t m = (lo + hi) / 2; if (s->blocks[m].coffset < coffset) lo = m + 1; else hi = m; }
+    return (lo < s->blocks.size() && s->blocks[lo].coffset == coffset) ? &s->blocks[lo] : nullptr;
+  };
+  size_t ci = 0;
+  uint64_t cur_beg = 0, cur_end = 0, next_off = 0;
+  auto move_to_next_chunk = [&]() {                                             // inputstream.d:262-277
+    if (ci >= chunks.size()) return;
+    const uint64_t beg = chunks[ci].first;
+    size_t i = ci + 1;
+    for (; i < chunks.size(); ++i)
+      if ((chunks[i].first >> 16) > (chunks[ci].first >> 16)) break;
+    ci = i - 1;
+    chunks[ci].first = beg;
+    cur_beg = chunks[ci].first;
+    cur_end = chunks[ci].second;
+    next_off = cur_beg >> 16;
+  };
+  move_to_next_chunk();
+  bool eof = false;
+  while (ci < chunks.size() && !eof) {
+    // getNextBgzfBlock :285-338 (a block that is not in the table — EOF block, end of file, garbage — ends the stream)
+    const Block* b = block_at(next_off);
+    if (!b) break;
+    const uint64_t offset = b->coffset;
+    next_off = b->coffset + b->bsize + 1;
+    const uint32_t skip_start = offset == (cur_beg >> 16) ? (uint32_t)(cur_beg & 0xFFFF) : 0;
+    const int64_t skip_end = offset == (cur_end >> 16) ? (int64_t)b->isize - (int64_t)(cur_end & 0xFFFF) : 0;
+    if (offset >= (cur_end >> 16)) { ++ci; move_to_next_chunk(); }
+    if (b->isize > 0 && skip_end == (int64_t)b->isize) continue;                // the chunk ended on the edge of two blocks
+    const int64_t from = skip_start, to = (int64_t)b->isize - (int64_t)(uint16_t)skip_end;
+    if (to <= from) { eof = true; break; }                                      // setupReadBuffer :432-435 (restatement-defined for to < from)
+    pieces.push_back(Piece{cat.size(), b->coffset, b->coffset + b->bsize + 1, (uint32_t)from, (uint32_t)(to - from)});
+    cat.insert(cat.end(), s->u.begin() + b->uoffset + from, s->u.begin() + b->uoffset + to);
+  }
+  auto vo_of = [&](uint64_t x) -> uint64_t {                                     // _current_vo bookkeeping :438-445,516-524
+    size_t lo = 0, hi = pieces.size();
+    while (lo < hi) { size_t m = (lo + hi) / 2; if (pieces[m].cat <= x) lo = m + 1; else hi = m; }
+    if (lo == 0) return 0;
+    const Piece& p = pieces[lo - 1];
+    if (x - p.cat >= p.len) {
+      // end of a piece: the next block's start, or (skip_end > 0) the cut position inside this block
+      const Block* b = block_at(p.coffset);
+      if (b && p.within + p.len < b->isize) return (p.coffset << 16) | (p.within + p.len);
+      return p.cend << 16;
+    }
+    return (p.coffset << 16) | (p.within + (x - p.cat));
+  };
+  uint64_t p = 0;
+  const uint64_t avail = cat.size();
+  while (p < avail && avail - p >= 4) {                                          // readrange.d:118-173
+    const int32_t bs = (int32_t)le32(cat.data() + p);
+    if (bs < 32 || (uint64_t)bs > avail - p - 4) return ORC_ERR_TRUNC;
+    const uint8_t* r = cat.data() + p + 4;
+    RegionRead rr;
+    rr.start_vo = vo_of(p);
+    rr.end_vo = vo_of(p + 4 + (uint64_t)bs);
+    if (until_vo != ~0ull && rr.end_vo > until_vo) break;                        // randomaccessmanager.d:190-195
+    rr.ref_id = (int32_t)le32(r);
+    rr.pos = (int32_t)le32(r + 4);
+    const uint32_t bin_mq_nl = le32(r + 8), flag_nc = le32(r + 12);
+    const uint32_t lname = bin_mq_nl & 0xFF, nc = flag_nc & 0xFFFF;
+    if (32ull + lname + 4ull * nc > (uint64_t)bs) return ORC_ERR_TRUNC;
+    uint32_t covered = 0;
+    for (uint32_t k = 0; k < nc; ++k) {
+      const uint32_t raw = le32(r + 32 + lname + 4 * k);
+      if (op_ref(raw)) covered += raw >> 4;
+    }
+    if ((flag_nc >> 16) & 0x4) covered = 0;
+    rr.end_pos = (int32_t)((uint32_t)rr.pos + covered);
+    const auto it = std::lower_bound(s->start_vo.begin(), s->start_vo.end(), rr.start_vo);
+    rr.index = (it != s->start_vo.end() && *it == rr.start_vo) ? (int64_t)(it - s->start_vo.begin()) : -1;
+    out->push_back(rr);
+    p += 4 + (uint64_t)bs;
+  }
+  return 0;
+}
+
+// BamReadFilter.findNext for one region (randomaccessmanager.d:396-450)
+void region_filter(const std::vector<RegionRead>& in, uint32_t ref_id, uint32_t start, uint32_t end, std::vector<RegionRead>* out) {
+  for (const RegionRead& r : in) {
+    const uint32_t cur = (uint32_t)r.ref_id;
+    if (cur > ref_id) return;                                   // no more records for this reference (-1 compares as uint.max)
+    if (cur < ref_id) continue;
+    // _current_read.position (int) against region.end / region.start (uint): D compares them as unsigned
+    if ((uint32_t)r.pos >= end) return;
+    if ((uint32_t)r.pos > start) { out->push_back(r); continue; }
+    if ((uint32_t)(r.pos + (r.end_pos - r.pos)) <= start) continue;     // position + basesCovered() <= region.start
+    out->push_back(r);
+  }
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------ C API ----
 extern "C" {
 
@@ -918,6 +1128,53 @@ ORC_PARR(op_offset, uint32_t, op_offset)
 ORC_PARR(base, uint8_t, base)
 ORC_PARR(qual, uint8_t, qual)
 ORC_PARR(ref_base, uint8_t, ref_base)
+
+
+typedef struct Bai orc_bai;
+orc_bai* orc_bai_open(const uint8_t* data, uint64_t len) { return bai_parse(data, len); }
+void orc_bai_close(orc_bai* b) { delete b; }
+int orc_bai_status(const orc_bai* b) { return b->status; }
+const char* orc_bai_errmsg(const orc_bai* b) { return b->msg.c_str(); }
+uint64_t orc_bai_n_refs(const orc_bai* b) { return b->idx.size(); }
+uint64_t orc_bai_n_bins(const orc_bai* b, uint64_t ref) { return ref < b->idx.size() ? b->idx[ref].bins.size() : 0; }
+uint64_t orc_bai_n_intervals(const orc_bai* b, uint64_t ref) { return ref < b->idx.size() ? b->idx[ref].ioffsets.size() : 0; }
+// getChunks(BamRegion) — writes at most cap (beg, end) pairs, returns their number (-1: invalid reference index)
+int64_t orc_region_chunks(const orc_bai* b, uint32_t ref_id, uint32_t beg, uint32_t end, uint64_t* out2, uint64_t cap) {
+  int st = 0;
+  const std::vector<Chunk> c = region_chunks(b, ref_id, beg, end, &st);
+  if (st) return -1;
+  for (uint64_t k = 0; k < c.size() && k < cap; ++k) { out2[2 * k] = c[k].first; out2[2 * k + 1] = c[k].second; }
+  return (int64_t)c.size();
+}
+// bam[ref][beg .. end) = getReads(BamRegion) (:300-305): record indices (into the whole-file record table; -1 for a
+// record the sequential walk does not know) and their virtual offsets.  Returns the count, or -(status) on error.
+int64_t orc_region_reads(orc_bam* s, const orc_bai* b, uint32_t ref_id, uint32_t beg, uint32_t end, int64_t* index,
+                         uint64_t* start_vo, uint64_t* end_vo, uint64_t cap) {
+  int st = 0;
+  const std::vector<Chunk> c = region_chunks(b, ref_id, beg, end, &st);
+  if (st) return st;
+  std::vector<RegionRead> all, keep;
+  st = chunk_stream_reads(s, c, ~0ull, &all);
+  if (st) return st;
+  region_filter(all, ref_id, beg, end, &keep);
+  for (uint64_t k = 0; k < keep.size() && k < cap; ++k) {
+    index[k] = keep[k].index;
+    if (start_vo) start_vo[k] = keep[k].start_vo;
+    if (end_vo) end_vo[k] = keep[k].end_vo;
+  }
+  return (int64_t)keep.size();
+}
+// getReadsBetween(from, to) (:186-196)
+int64_t orc_reads_between(orc_bam* s, uint64_t from_vo, uint64_t to_vo, int64_t* index, uint64_t cap) {
+  // createStreamStartingFrom(from): every block from from.coffset on, the first one cut at from.uoffset
+  decode_records(s);
+  std::vector<Chunk> c{{from_vo, s->end_coffset << 16}};
+  std::vector<RegionRead> all;
+  const int st = chunk_stream_reads(s, c, to_vo, &all);
+  if (st) return st;
+  for (uint64_t k = 0; k < all.size() && k < cap; ++k) index[k] = all[k].index;
+  return (int64_t)all.size();
+}
 
 // ------------------------------------------------------- CPU baseline legs ----
 // "Restated BioD CPU path (libz, g++ -O3), not the D binary" (BASELINE.md §2):

@@ -76,6 +76,25 @@ def lib():
             fn = getattr(L, "orc_pileup_" + name)
             fn.restype = C.c_void_p
             fn.argtypes = [C.c_void_p]
+        L.orc_bai_open.restype = C.c_void_p
+        L.orc_bai_open.argtypes = [C.c_void_p, u64]
+        L.orc_bai_close.argtypes = [C.c_void_p]
+        L.orc_bai_status.restype = C.c_int
+        L.orc_bai_status.argtypes = [C.c_void_p]
+        L.orc_bai_errmsg.restype = C.c_char_p
+        L.orc_bai_errmsg.argtypes = [C.c_void_p]
+        for f in ("orc_bai_n_bins", "orc_bai_n_intervals"):
+            getattr(L, f).restype = u64
+            getattr(L, f).argtypes = [C.c_void_p, u64]
+        L.orc_bai_n_refs.restype = u64
+        L.orc_bai_n_refs.argtypes = [C.c_void_p]
+        L.orc_region_chunks.restype = C.c_int64
+        L.orc_region_chunks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, u64]
+        L.orc_region_reads.restype = C.c_int64
+        L.orc_region_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, u64]
+        L.orc_reads_between.restype = C.c_int64
+        L.orc_reads_between.argtypes = [C.c_void_p, u64, u64, C.c_void_p, u64]
         L.orc_cpu_baseline.restype = C.c_int
         L.orc_cpu_baseline.argtypes = [C.c_void_p, u64, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3 + \
             [C.POINTER(u64)] * 4
@@ -248,6 +267,54 @@ class Bam:
                           single_ref=True):
         return Pileup(self._L, self._L.orc_pileup_run_range(self._h, int(single_ref), start_from, end_at,
                                                             int(skip_zero_coverage), rec_begin, rec_end))
+
+
+class Bai:
+    """BaiFile (bam/baifile.d:85-169) + RandomAccessManager.getChunks (randomaccessmanager.d:222-244)."""
+
+    def __init__(self, data: bytes):
+        self._L = lib()
+        self._buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        self._h = self._L.orc_bai_open(self._buf.ctypes.data, len(self._buf))
+        st = self._L.orc_bai_status(self._h)
+        if st:
+            raise OracleError(st, self._L.orc_bai_errmsg(self._h).decode())
+        self.n_refs = int(self._L.orc_bai_n_refs(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_bai_close(self._h)
+            self._h = None
+
+    def chunks(self, ref_id, beg, end):
+        out = np.zeros(2 * 4096, dtype=np.uint64)
+        n = int(self._L.orc_region_chunks(self._h, ref_id, beg, end, out.ctypes.data, len(out) // 2))
+        if n < 0:
+            raise OracleError(-9, "Invalid reference sequence index")
+        assert n <= len(out) // 2
+        return [(int(out[2 * k]), int(out[2 * k + 1])) for k in range(n)]
+
+
+def region_reads(bam, bai, ref_id, beg, end):
+    """bam[ref][beg .. end) (reference.d:76-81): (record indices, start voffsets, end voffsets)."""
+    cap = max(16, bam.n_records + 16)
+    idx = np.zeros(cap, dtype=np.int64)
+    sv = np.zeros(cap, dtype=np.uint64)
+    ev = np.zeros(cap, dtype=np.uint64)
+    n = int(bam._L.orc_region_reads(bam._h, bai._h, ref_id, beg, end, idx.ctypes.data, sv.ctypes.data, ev.ctypes.data, cap))
+    if n < 0:
+        raise OracleError(n, "region read failed")
+    return idx[:n].copy(), sv[:n].copy(), ev[:n].copy()
+
+
+def reads_between(bam, from_vo, to_vo):
+    """getReadsBetween (randomaccessmanager.d:186-196): record indices."""
+    cap = max(16, bam.n_records + 16)
+    idx = np.zeros(cap, dtype=np.int64)
+    n = int(bam._L.orc_reads_between(bam._h, from_vo, to_vo, idx.ctypes.data, cap))
+    if n < 0:
+        raise OracleError(n, "reads between failed")
+    return idx[:n].copy()
 
 
 def cpu_baseline(data, threads, do_pileup=True):

@@ -338,3 +338,91 @@ def test_md_operations_and_missing_tags():
     assert b.dna(3) == ""
     p = b.pileup_columns(use_md_tag=True)
     assert p.status == 0 and len(p.ref_base) == p.n_columns
+
+
+# ---- BAI random access --------------------------------------------------------------------
+BINS_REGIONS = [(1400, 1500), (10, 123), (135, 1236), (1350, 3612), (643, 1732), (267, 1463), (0, 30), (1363, 1612),
+                (361, 1231), (322, 612), (912, 938), (0, 3000), (0, 100), (0, 1000), (0, 1900), (1, 279)] + \
+               [(i, i + 100) for i in range(50_000, 1_000_000, 50_000)]
+
+
+def naive_region(b, ref_id, beg, end):
+    # test/unittests.d:151-156: ref matches, position < end, position + basesCovered() > beg
+    return [i for i in range(b.n_records)
+            if b.ref_id[i] == ref_id and b.pos[i] < end and b.end_pos[i] > beg]
+
+
+def test_bai_region_reads_equal_the_naive_filter():
+    # test/unittests.d:145-185: bf["large"][beg .. end] == filter over all reads, for every listed interval
+    data = fixture_bytes("bins.bam")
+    b = orc.Bam(data).decode()
+    bai = orc.Bai(fixture_bytes("bins.bam.bai"))
+    assert bai.n_refs == len(b.ref_names)
+    large = b.ref_names.index("large")
+    for beg, end in BINS_REGIONS:
+        idx, sv, ev = orc.region_reads(b, bai, large, beg, end)
+        assert list(idx) == naive_region(b, large, beg, end), (beg, end)
+        assert np.array_equal(sv, b.start_vo[idx])
+        # end offsets: as in the sequential walk, except that after the last record of a chunk the stream has already
+        # moved on to the next chunk (inputstream.d:516-524), whose start is what virtualTell reports
+        begs = {a for a, _ in bai.chunks(large, beg, end)}
+        assert all(int(e) == int(w) or int(e) in begs for e, w in zip(ev, b.end_vo[idx]))
+    # every reference, whole and in parts
+    for name in b.ref_names:
+        r = b.ref_names.index(name)
+        ln = b.ref_lens[r]
+        for beg, end in [(0, ln), (0, 1), (ln // 2, ln // 2 + 1), (ln - 1, ln), (ln // 3, 2 * ln // 3)]:
+            if beg < end:
+                assert list(orc.region_reads(b, bai, r, beg, end)[0]) == naive_region(b, r, beg, end), (name, beg, end)
+
+
+def test_bai_first_reads_of_references():
+    # test/unittests.d:193-205: getReadAt(bf[name].startVirtualOffset()).name
+    data = fixture_bytes("bins.bam")
+    b = orc.Bam(data).decode()
+    bai = orc.Bai(fixture_bytes("bins.bam.bai"))
+    for name in ("tiny", "small", "large"):
+        r = b.ref_names.index(name)
+        idx, sv, _ = orc.region_reads(b, bai, r, 0, b.ref_lens[r])
+        assert b.name(int(idx[0])) == f"{name}:r1:0..1:len1:bin4681:hexbin0x1249"
+        # getReadAt: the first record of the stream that starts at that virtual offset
+        assert int(orc.reads_between(b, int(sv[0]), int(b.end_vo[int(idx[0])]))[0]) == int(idx[0])
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "tags.bam"])
+def test_bai_other_fixtures(name):
+    data = fixture_bytes(name)
+    b = orc.Bam(data).decode()
+    bai = orc.Bai(fixture_bytes(name + ".bai"))
+    rng = np.random.default_rng(5)
+    for r in range(len(b.ref_names)):
+        ln = b.ref_lens[r]
+        regions = [(0, ln)] + [tuple(sorted(int(x) for x in rng.integers(0, ln, 2))) for _ in range(25)]
+        for beg, end in regions:
+            if beg < end:
+                # (no reference test pins these files; placed-but-unmapped reads need not be in the index's chunks)
+                got = [int(i) for i in orc.region_reads(b, bai, r, beg, end)[0]]
+                naive = naive_region(b, r, beg, end)
+                assert got == [i for i in naive if i in set(got)], (name, r, beg, end)
+                assert all(b.flag[i] & 4 for i in set(naive) - set(got)), (name, r, beg, end)
+
+
+def test_reads_between_virtual_offsets():
+    # getReadsBetween (randomaccessmanager.d:186-196): records from `from` on whose end offset is not beyond `to`
+    data = fixture_bytes("ex1_header.bam")
+    b = orc.Bam(data).decode()
+    n = b.n_records
+    for a, z in [(0, n), (0, 1), (5, 6), (100, 1500), (n - 3, n), (700, 701), (1234, 3000)]:
+        got = orc.reads_between(b, int(b.start_vo[a]), int(b.end_vo[z - 1]))
+        assert list(got) == list(range(a, z)), (a, z)
+
+
+def test_bai_parse_errors():
+    good = fixture_bytes("bins.bam.bai")
+    with pytest.raises(orc.OracleError):
+        orc.Bai(b"BAM\1" + good[4:])
+    with pytest.raises(orc.OracleError):
+        orc.Bai(good[:len(good) // 2])
+    bai = orc.Bai(good)
+    with pytest.raises(orc.OracleError):
+        bai.chunks(bai.n_refs, 0, 10)          # "Invalid reference sequence index"
