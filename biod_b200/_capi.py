@@ -124,6 +124,15 @@ def lib():
     L.biodb_debug_inflate_counters.argtypes = [u64p, C.c_int32]
     L.biodb_debug_md_chain.restype = C.c_int64
     L.biodb_debug_md_chain.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_uint64, vp, C.c_uint64]
+    L.biodb_index_open.restype = C.c_int
+    L.biodb_index_open.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.biodb_index_close.argtypes = [vp]
+    L.biodb_index_n_refs.restype = C.c_int32
+    L.biodb_index_n_refs.argtypes = [vp]
+    L.biodb_index_chunks.restype = C.c_int64
+    L.biodb_index_chunks.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64]
+    L.biodb_reads_begin_region.restype = C.c_int
+    L.biodb_reads_begin_region.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.biodb_debug_md_dna.restype = C.c_int64
     L.biodb_debug_md_dna.argtypes = [vp, C.c_int64, vp, C.c_uint64]
     L.biodb_dev_scan_workspace_bytes.restype = C.c_size_t
@@ -141,5 +150,6 @@ EXPORTS = [
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
-    "biodb_debug_md_dna",
+    "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks",
+    "biodb_reads_begin_region",
 ]

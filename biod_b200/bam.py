@@ -10,6 +10,7 @@ argument meaning and error classes, every byte of work done by the CUDA library.
     for column in pileupColumns(bam): ...          # pileup.d:509-519
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -144,6 +145,9 @@ class BamRead:
     sequence_length = property(lambda s: int(s._b.l_seq[s._i]))
     index = property(lambda s: s._b.first_index + s._i)
     is_unmapped = property(lambda s: bool(s.flag & 4))
+    # BamReadBlock (readrange.d:38-48); None unless the reader was opened with want_offsets
+    start_virtual_offset = property(lambda s: None if s._b.start_voffset is None else int(s._b.start_voffset[s._i]))
+    end_virtual_offset = property(lambda s: None if s._b.end_voffset is None else int(s._b.end_voffset[s._i]))
     is_reverse_strand = property(lambda s: bool(s.flag & 16))
 
     def basesCovered(self):
@@ -187,10 +191,86 @@ class BamRead:
         return self.raw[self._seq_off() + (n + 1) // 2 + n:].tobytes()
 
 
+class BaiFile:
+    """bam/baifile.d:85-169: a parsed BAI index.  `source` is the bytes of the .bai file, its path, or the path of the
+    BAM file (then `<bam>.bai` and `<bam without extension>.bai` are tried, baifile.d:95-113).  Host only."""
+
+    def __init__(self, source):
+        self._L = L = capi.lib()
+        if isinstance(source, (bytes, bytearray, memoryview, np.ndarray)):
+            data = bytes(source)
+        else:
+            path = str(source)
+            if not path.endswith(".bai"):
+                first, second = path + ".bai", path[:path.rfind(".") + 1] + "bai"
+                if os.path.exists(first):
+                    path = first
+                elif os.path.exists(second):
+                    path = second
+                else:
+                    raise Exception(f"searched for {first} or {second}, found neither")
+            with open(path, "rb") as f:
+                data = f.read()
+        self._buf = np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        st = L.biodb_index_open(self._buf.ctypes.data, self._buf.size, C.byref(h))
+        if st != capi.OK:
+            _raise(L.biodb_open_error().contents)
+        self._h = h
+        self.n_refs = int(L.biodb_index_n_refs(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.biodb_index_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def chunks(self, ref_id, beg, end):
+        """RandomAccessManager.getChunks (randomaccessmanager.d:222-244): [(beg voffset, end voffset), ...]."""
+        n = int(self._L.biodb_index_chunks(self._h, ref_id, beg, end, None, 0))
+        if n < 0:
+            raise Exception("Invalid reference sequence index")
+        out = np.zeros(2 * max(n, 1), dtype=np.uint64)
+        self._L.biodb_index_chunks(self._h, ref_id, beg, end, out.ctypes.data, n)
+        return [(int(out[2 * k]), int(out[2 * k + 1])) for k in range(n)]
+
+
+class ReferenceSequence:
+    """bam/reference.d:37-160: `reader["chr1"]`; slicing it gives the reads that overlap [start, end)."""
+
+    def __init__(self, reader, ref_id, info):
+        self._reader, self.id, self.name, self.length = reader, ref_id, info.name, info.length
+
+    def __getitem__(self, sl):
+        start = 0 if sl.start is None else sl.start
+        end = self.length if sl.stop is None else sl.stop
+        return self._reader.region_reads(self.id, start, end)
+
+    def reads(self):
+        return self[0:self.length]
+
+    def startVirtualOffset(self):
+        """reference.d:96-102 (the EOF fallback for references without reads is not mirrored)."""
+        for r in self.reads():
+            return r.start_virtual_offset
+        return None
+
+    def firstPosition(self):
+        for r in self.reads():
+            return r.position
+        return -1
+
+
 class BamReader:
     """bam/reader.d:80-598 — the subset on the hot path."""
 
-    def __init__(self, source, blocks_per_batch=0, want_offsets=False, device=-1, task_pool=None, verify_crc=False):
+    def __init__(self, source, blocks_per_batch=0, want_offsets=False, device=-1, task_pool=None, verify_crc=False,
+                 index=None):
         # task_pool is accepted and ignored (reader.d:100-101): the device is the pool
         self._L = L = capi.lib()
         o = capi.Options()
@@ -220,6 +300,54 @@ class BamReader:
             L.biodb_ref_info(h, i, C.byref(nm), C.byref(nl), C.byref(ln))
             self.reference_sequences.append(ReferenceSequenceInfo(C.string_at(nm, nl.value).decode("latin-1"), ln.value))
         self.reads_start_voffset = int(L.biodb_reads_start_voffset(h))
+        # random access (reader.d:424-447): an index given explicitly, or looked for next to the file on first use
+        self._index = index if (index is None or isinstance(index, BaiFile)) else BaiFile(index)
+
+    def _bai(self):
+        if self._index is None:
+            if self.filename is None:
+                raise Exception("BAM index file (.bai) must be provided")      # randomaccessmanager.d:202-204
+            self._index = BaiFile(self.filename)
+        return self._index
+
+    def __getitem__(self, ref_name):
+        """reader.d:424-429"""
+        for i, r in enumerate(self.reference_sequences):
+            if r.name == ref_name:
+                return ReferenceSequence(self, i, r)
+        raise Exception(f"Reference with name {ref_name} does not exist")
+
+    def reference(self, ref_id):
+        """reader.d:435-440"""
+        return ReferenceSequence(self, ref_id, self.reference_sequences[ref_id])
+
+    def region_batches(self, ref_id, start, end, copy=False):
+        """Batches holding the reads of reference ref_id that overlap [start, end) (randomaccessmanager.d:300-305)."""
+        if not start < end:
+            raise Exception("start must be less than end")                       # reference.d:77
+        L = self._L
+        it = C.c_void_p()
+        st = L.biodb_reads_begin_region(self._h, self._bai()._h, ref_id, start, end, C.byref(it))
+        if st == capi.ERR_ARG:
+            raise Exception(L.biodb_last_error(self._h).contents.message.decode("latin-1"))
+        if st != capi.OK:
+            self._err()
+        try:
+            while True:
+                b = capi.RecordBatch()
+                st = L.biodb_reads_next(it, C.byref(b))
+                if st == capi.EOF:
+                    return
+                if st != capi.OK:
+                    self._err()
+                yield RecordBatch(b, copy)
+        finally:
+            L.biodb_reads_end(it)
+
+    def region_reads(self, ref_id, start, end):
+        for batch in self.region_batches(ref_id, start, end, copy=True):
+            for i in range(batch.n):
+                yield BamRead(batch, i)
 
     def close(self):
         if getattr(self, "_h", None):

@@ -92,4 +92,13 @@ cudaError_t launch_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t
                                 uint32_t n_walk, int final_slice, const RecordArrays& out, uint64_t* result,
                                 const ScanWorkspace& ws, cudaStream_t st);
 
+// ---- region.cu -------------------------------------------------------------------------------
+// BamReadFilter (randomaccessmanager.d:366-462) for one region + compaction of the record tables: `out` receives the
+// kept records in order (cigar_off rebased to its own cigar array).  scratch: region_scratch_elems(n) u32;
+// info (device, 4 x u32): [0] index of the first read that ends the range (0xffffffff = none), [1] reads kept,
+// [2] their CIGAR words.
+size_t region_scratch_elems(uint64_t n);
+cudaError_t launch_region_filter(const RecordArrays& in, uint64_t n, uint32_t ref, uint32_t beg, uint32_t end,
+                                 const RecordArrays& out, uint32_t* scratch, uint32_t* info, cudaStream_t st);
+
 }  // namespace biodb

@@ -1,5 +1,6 @@
 // Host runtime + C ABI of libbiod_b200.so (see include/biod_b200.h and runtime.h).
 #include "runtime.h"
+#include "bai.h"
 #include "md_chain.h"
 #include "md_walk.h"
 
@@ -197,6 +198,7 @@ biodb_status Pass::init(biodb_reader* rd, uint64_t coffset, uint32_t uoffset) {
 
 void Pass::rewind(uint64_t coffset, uint32_t uoffset) {
   stop_coffset = ~0ull;
+  stop_uoffset = 0;
   next_coffset = coffset;
   first_skip = uoffset;
   pf_c0 = pf_c1 = 0;
@@ -250,10 +252,10 @@ uint64_t voffset_in(const std::vector<Seg>& segs, uint64_t x) {
 }
 
 // Host walk of the BSIZE chain: up to max_blocks block headers from next_coffset on (inputstream.d:54-199, 386-424).
-static void walk_headers(const biodb_reader* r, uint64_t stop_coffset, uint32_t max_blocks, std::vector<BlockInfo>& blocks,
-                         uint64_t& next_coffset, bool& supplier_done, biodb_error& pending) {
+static void walk_headers(const biodb_reader* r, uint64_t stop_coffset, uint32_t stop_uoffset, uint32_t max_blocks,
+                         std::vector<BlockInfo>& blocks, uint64_t& next_coffset, bool& supplier_done, biodb_error& pending) {
   while (blocks.size() < max_blocks && !supplier_done && !pending.status) {
-    if (next_coffset >= stop_coffset) { supplier_done = true; break; }
+    if (next_coffset > stop_coffset || (next_coffset == stop_coffset && stop_uoffset == 0)) { supplier_done = true; break; }
     BlockInfo b;
     int rc = parse_bgzf_header(r->file, r->flen, next_coffset, &b, &pending);
     if (rc < 0) break;
@@ -296,7 +298,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     supplier_done = pre_supplier_done;
     pending = pre_pending;
   } else {
-    walk_headers(r, stop_coffset, max_blocks, blocks, next_coffset, supplier_done, pending);
+    walk_headers(r, stop_coffset, stop_uoffset, max_blocks, blocks, next_coffset, supplier_done, pending);
   }
   pre_valid = false;
   const uint32_t nb = (uint32_t)blocks.size();
@@ -338,6 +340,12 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   if (!has_carry && nb) h_buoff[0] += first_skip;         // the first record of the file sits behind the header
   first_skip = 0;
   u_len = off;
+  if (nb && stop_uoffset && blocks[nb - 1].coffset == stop_coffset) {
+    // the stream ends inside this block (end of a BAI chunk): the block is inflated whole, but the record scan sees
+    // only its first stop_uoffset bytes
+    u_len = h_outoff[nb - 1] + std::min<uint32_t>(stop_uoffset, blocks[nb - 1].isize);
+    h_buoff[k] = u_len;
+  }
   uint8_t* dp = d_tab.as<uint8_t>();
   const uint64_t* d_payload = (const uint64_t*)dp;
   const uint64_t* d_outoff = d_payload + nb;
@@ -367,7 +375,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     }
     pf_c1 = 0;
   }
-  CUDA_TRY(d_u.ensure((size_t)u_len + 256, st));
+  CUDA_TRY(d_u.ensure((size_t)off + 256, st));
   CUDA_TRY(d_status.ensure((size_t)nb * 8 + 16, st));      // statuses, then (verify_crc) the computed CRCs
   CUDA_TRY(h_status.ensure((size_t)nb * 8 + 16));
   CUDA_TRY(d_ws.ensure(scan_workspace_bytes(nsb), st));
@@ -414,7 +422,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
       pre_next_coffset = next_coffset;
       pre_supplier_done = supplier_done;
       pre_pending = pending;
-      walk_headers(r, stop_coffset, max_blocks, pre_blocks, pre_next_coffset, pre_supplier_done, pre_pending);
+      walk_headers(r, stop_coffset, stop_uoffset, max_blocks, pre_blocks, pre_next_coffset, pre_supplier_done, pre_pending);
       pre_max = max_blocks;
       pre_valid = true;
     }
@@ -763,9 +771,26 @@ struct ReadsSlot {
   cudaEvent_t done = nullptr;        // the device->host copies of this batch have landed
   uint64_t n = 0, used = 0, n_cigar = 0, first = 0;
   std::vector<Seg> segs;             // block provenance of the slice, for virtual offsets (readrange.d:55-66)
+  // region mode: where the chunk of this batch ends and the next one begins (0 = there is none)
+  uint64_t chunk_end_vo = 0, next_chunk_beg_vo = 0;
 };
+struct biodb_index {
+  BaiIndex bai;
+};
+
 struct biodb_reads {
   Pass pass;
+  // region mode (biodb_reads_begin_region): the chunks the index names are read one after the other, each as a pass of
+  // its own from chunk.beg to chunk.end, and every batch goes through the region filter (region.cu)
+  bool region = false;
+  bool region_done = false;            // a read beyond the region was met: nothing further can overlap it
+  std::vector<VoChunk> chunks;
+  size_t chunk_i = 0;                  // chunk being read
+  uint32_t reg_ref = 0, reg_beg = 0, reg_end = 0;
+  DevBuf d_sel[10], d_scratch, d_info;
+  PinBuf h_info;
+  uint64_t sel_cap = 0, sel_cig_cap = 0;
+  uint64_t sel_n = 0, sel_cig = 0;
   ReadsSlot slot[2];
   int cur = 0;                       // slot the caller holds
   bool inflight = false;             // slot[cur ^ 1] holds the batch read ahead
@@ -784,8 +809,65 @@ struct biodb_reads {
     if (cs) cudaStreamSynchronize(cs);
     inflight = ahead_done = staged_valid = false;
     ahead_status = BIODB_OK;
+    region = region_done = false;
+    chunks.clear();
+    chunk_i = 0;
   }
 };
+
+// Point the pass at chunk k of a region read: from chunk.beg to chunk.end (virtual offsets).
+static void region_seek(biodb_reads* it, size_t k) {
+  const VoChunk& c = it->chunks[k];
+  it->pass.rewind(c.beg >> 16, (uint32_t)(c.beg & 0xFFFF));
+  it->pass.stop_coffset = c.end >> 16;
+  it->pass.stop_uoffset = (uint32_t)(c.end & 0xFFFF);
+}
+
+// Region mode: the next batch that holds at least one read of the region, filtered and compacted into it->d_sel.
+static biodb_status region_next(biodb_reads* it) {
+  Pass& p = it->pass;
+  cudaStream_t st = p.st;
+  while (true) {
+    if (it->region_done || it->chunk_i >= it->chunks.size()) return BIODB_EOF;
+    biodb_status s = p.next((uint32_t)p.r->opts.blocks_per_batch, 0);
+    if (s == BIODB_EOF) {
+      if (++it->chunk_i >= it->chunks.size()) return BIODB_EOF;
+      region_seek(it, it->chunk_i);
+      continue;
+    }
+    if (s != BIODB_OK) return s;
+    if (p.n == 0) continue;
+    if (p.n > 0xfffffff0ull) return p.fail(BIODB_ERR_NOMEM, 0, 0, "too many records in one batch; lower blocks_per_batch");
+    // room for the compacted tables
+    if (p.n + 8 > it->sel_cap || p.n_cigar + 8 > it->sel_cig_cap) {
+      it->sel_cap = std::max<uint64_t>(it->sel_cap, p.n + p.n / 8 + 1024);
+      it->sel_cig_cap = std::max<uint64_t>(it->sel_cig_cap, p.n_cigar + p.n_cigar / 8 + 1024);
+      static const size_t esz[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
+      for (int a = 0; a < 9; ++a)
+        if (it->d_sel[a].ensure((size_t)(it->sel_cap + 2) * esz[a], st) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "allocation failed");
+      if (it->d_sel[9].ensure((size_t)(it->sel_cig_cap + 2) * 4, st) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "allocation failed");
+    }
+    if (it->d_scratch.ensure(region_scratch_elems(p.n) * 4, st) != cudaSuccess || it->d_info.ensure(64, st) != cudaSuccess ||
+        it->h_info.ensure(64) != cudaSuccess)
+      return p.fail(BIODB_ERR_CUDA, 0, 0, "allocation failed");
+    RecordArrays in = p.arrays(0);
+    RecordArrays out{it->d_sel[0].as<uint64_t>(), it->d_sel[1].as<int32_t>(), it->d_sel[2].as<int32_t>(), it->d_sel[3].as<int32_t>(),
+                     it->d_sel[4].as<int32_t>(), it->d_sel[5].as<uint32_t>(), it->d_sel[6].as<uint32_t>(), it->d_sel[7].as<int32_t>(),
+                     it->d_sel[8].as<uint64_t>(), it->d_sel[9].as<uint32_t>(), it->sel_cap, it->sel_cig_cap};
+    p.stage_begin();
+    cudaError_t e = launch_region_filter(in, p.n, it->reg_ref, it->reg_beg, it->reg_end, out, it->d_scratch.as<uint32_t>(),
+                                         it->d_info.as<uint32_t>(), st);
+    p.stage_end(&p.stats.scan_ms);
+    if (e != cudaSuccess || launch_copy_bytes(it->h_info.p, it->d_info.p, 12, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+      return p.fail(BIODB_ERR_CUDA, 0, 0, "region filter failed");
+    const uint32_t* hi = it->h_info.as<uint32_t>();
+    if (hi[0] != 0xffffffffu) it->region_done = true;
+    it->sel_n = hi[1];
+    it->sel_cig = hi[2];
+    if (it->sel_n) return BIODB_OK;
+  }
+}
 
 static const size_t REC_ESZ[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
 
@@ -804,26 +886,39 @@ static biodb_status reads_produce(biodb_reads* it, int s) {
   if (it->staged_valid && cudaStreamWaitEvent(p.st, it->staged, 0) != cudaSuccess) return p.fail(BIODB_ERR_CUDA, 0, 0, "wait failed");
   const uint64_t first = p.n_records_total;
   biodb_status st;
-  do {
-    st = p.next((uint32_t)p.r->opts.blocks_per_batch, 0);
-  } while (st == BIODB_OK && p.n == 0 && !p.finished);   // a slice may hold only part of one huge record
-  if (st != BIODB_OK) return st;
-  if (p.n == 0) return p.next(1, 0);                      // finished: raises the pending error or EOF
+  if (it->region) {
+    st = region_next(it);
+    if (st != BIODB_OK) return st;
+  } else {
+    do {
+      st = p.next((uint32_t)p.r->opts.blocks_per_batch, 0);
+    } while (st == BIODB_OK && p.n == 0 && !p.finished);   // a slice may hold only part of one huge record
+    if (st != BIODB_OK) return st;
+    if (p.n == 0) return p.next(1, 0);                      // finished: raises the pending error or EOF
+  }
   ReadsSlot& sl = it->slot[s];
-  sl.n = p.n;
+  sl.n = it->region ? it->sel_n : p.n;
   sl.used = p.tail;                                       // bytes of the slice covered by whole records
-  sl.n_cigar = p.n_cigar;
-  sl.first = first;
+  sl.n_cigar = it->region ? it->sel_cig : p.n_cigar;
+  sl.first = it->region ? 0 : first;
   sl.segs = p.segs;
+  sl.chunk_end_vo = sl.next_chunk_beg_vo = 0;
+  if (it->region && it->chunk_i < it->chunks.size()) {
+    sl.chunk_end_vo = it->chunks[it->chunk_i].end;
+    if (it->chunk_i + 1 < it->chunks.size()) sl.next_chunk_beg_vo = it->chunks[it->chunk_i + 1].beg;
+  }
   cudaStream_t cs = it->cs;
   bool ok = cudaEventRecord(it->computed, p.st) == cudaSuccess && cudaStreamWaitEvent(cs, it->computed, 0) == cudaSuccess;
   size_t bytes[11];
   const void* src[11];
   bytes[0] = (size_t)sl.used;
   src[0] = p.d_u.p;
-  for (int a = 0; a < 9; ++a) { bytes[1 + a] = (size_t)(sl.n + (a == 8 ? 1 : 0)) * REC_ESZ[a]; src[1 + a] = p.d_rec[a].p; }
+  for (int a = 0; a < 9; ++a) {
+    bytes[1 + a] = (size_t)(sl.n + (a == 8 ? 1 : 0)) * REC_ESZ[a];
+    src[1 + a] = it->region ? it->d_sel[a].p : p.d_rec[a].p;
+  }
   bytes[10] = (size_t)sl.n_cigar * 4;
-  src[10] = p.d_rec[9].p;
+  src[10] = it->region ? it->d_sel[9].p : p.d_rec[9].p;
   // device -> staging (ordered behind the previous batch's staging -> host copies on the same stream)
   for (int k = 0; k < 11 && ok; ++k) {
     // (grow with headroom: the two host slots and the staging area see batches of slightly different sizes, and a
@@ -866,6 +961,65 @@ biodb_status biodb_reads_begin(biodb_reader* r, biodb_reads** out) {
   biodb_status s = it->pass.init(r, r->reads_start_coffset, r->reads_start_uoffset);
   if (s != BIODB_OK) { delete it; return s; }
   *out = it;
+  return BIODB_OK;
+}
+
+biodb_status biodb_index_open(const void* bai, size_t len, biodb_index** out) {
+  if (!bai || !out) return BIODB_ERR_ARG;
+  biodb_index* ix = new biodb_index;
+  std::string msg;
+  const int rc = ix->bai.parse((const uint8_t*)bai, len, &msg);
+  if (rc != 0) {
+    delete ix;
+    set_error(&g_open_error, rc == -3 ? BIODB_ERR_FORMAT : BIODB_ERR_TRUNCATED, 0, 0, msg);
+    return (biodb_status)g_open_error.status;
+  }
+  *out = ix;
+  return BIODB_OK;
+}
+void biodb_index_close(biodb_index* ix) { delete ix; }
+int32_t biodb_index_n_refs(const biodb_index* ix) { return ix ? (int32_t)ix->bai.refs.size() : 0; }
+int64_t biodb_index_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end, uint64_t* out2, uint64_t cap) {
+  if (!ix) return -1;
+  std::vector<VoChunk> c;
+  if (!ix->bai.region_chunks(ref_id, beg, end, &c)) return -1;
+  for (uint64_t k = 0; k < c.size() && k < cap && out2; ++k) { out2[2 * k] = c[k].beg; out2[2 * k + 1] = c[k].end; }
+  return (int64_t)c.size();
+}
+
+biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
+                                      biodb_reads** out) {
+  if (!r || !ix || !out) return BIODB_ERR_ARG;
+  std::vector<VoChunk> c;
+  if (beg >= end) {                                        // reference.d:77
+    set_error(&r->err, BIODB_ERR_ARG, 0, 0, "start must be less than end");
+    return BIODB_ERR_ARG;
+  }
+  if (!ix->bai.region_chunks(ref_id, beg, end, &c)) {      // randomaccessmanager.d:206-208
+    set_error(&r->err, BIODB_ERR_ARG, 0, 0, "Invalid reference sequence index");
+    return BIODB_ERR_ARG;
+  }
+  // StreamChunksSupplier.moveToNextChunk (inputstream.d:262-277): chunks that begin in the same BGZF block are read
+  // as one stretch, from the first one's start to the last one's end
+  std::vector<VoChunk> merged;
+  for (size_t k = 0; k < c.size();) {
+    size_t i = k + 1;
+    while (i < c.size() && (c[i].beg >> 16) <= (c[k].beg >> 16)) ++i;
+    merged.push_back(VoChunk{c[k].beg, c[i - 1].end});
+    k = i;
+  }
+  c.swap(merged);
+  biodb_status s = biodb_reads_begin(r, out);
+  if (s != BIODB_OK) return s;
+  biodb_reads* it = *out;
+  it->region = true;
+  it->region_done = false;
+  it->chunks.swap(c);
+  it->chunk_i = 0;
+  it->reg_ref = ref_id;
+  it->reg_beg = beg;
+  it->reg_end = end;
+  if (!it->chunks.empty()) region_seek(it, 0);
   return BIODB_OK;
 }
 
@@ -916,6 +1070,9 @@ biodb_status biodb_reads_next(biodb_reads* it, biodb_record_batch* batch) {
     for (uint64_t i = 0; i < n; ++i) {
       sv[i] = voffset_in(sl.segs, batch->rec_off[i]);                                  // readrange.d:64-66
       ev[i] = voffset_in(sl.segs, batch->rec_off[i] + 4 + (uint64_t)batch->block_size[i]);   // readrange.d:55-57
+      // after the last record of a chunk BioD's stream has already moved on to the next chunk, whose start is what
+      // virtualTell reports (inputstream.d:516-524)
+      if (sl.next_chunk_beg_vo && ev[i] == sl.chunk_end_vo) ev[i] = sl.next_chunk_beg_vo;
     }
     batch->start_voffset = sv;
     batch->end_voffset = ev;

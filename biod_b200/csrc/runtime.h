@@ -84,6 +84,8 @@ struct Pass {
   // position in the file
   uint64_t next_coffset = 0;
   uint64_t stop_coffset = ~0ull;      // shard end: blocks at or beyond it are not read
+  uint32_t stop_uoffset = 0;          // > 0: the block AT stop_coffset is read too, but only its first stop_uoffset bytes
+                                      // belong to the stream (the skip_end of a BAI chunk, inputstream.d:316-322)
   uint32_t first_skip = 0;          // bytes of the first block that precede the first record
   bool supplier_done = false;       // EOF block / end of file reached (inputstream.d:393-394)
   biodb_error pending{};            // error to raise once the blocks before it are consumed

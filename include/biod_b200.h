@@ -123,6 +123,25 @@ void biodb_reads_end(biodb_reads* it);
 /* Progress in [0,1] by compressed bytes consumed (readsWithProgress, reader.d:233-279). */
 float biodb_reads_progress(const biodb_reads* it);
 
+/* ---- BAI random access: bam["chr"][beg .. end) -------------------------------------- */
+/* BaiFile (bio/std/hts/bam/baifile.d:85-169): parse the bytes of a .bai file.  Host only (needs no GPU).
+ * BIODB_ERR_FORMAT ("Invalid file format: expected BAI\1") / BIODB_ERR_TRUNCATED, message in biodb_open_error(). */
+typedef struct biodb_index biodb_index;
+biodb_status biodb_index_open(const void* bai, size_t len, biodb_index** out);
+void biodb_index_close(biodb_index* ix);
+int32_t biodb_index_n_refs(const biodb_index* ix);
+/* RandomAccessManager.getChunks (randomaccessmanager.d:222-244): the merged (beg, end) virtual-offset pairs that hold
+ * every read overlapping [beg, end) of reference ref_id.  Writes at most cap pairs into out2 (may be NULL), returns
+ * their number, -1 for an invalid reference index. */
+int64_t biodb_index_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end, uint64_t* out2, uint64_t cap);
+/* ReferenceSequence.opSlice(beg, end) = RandomAccessManager.getReads(BamRegion) (reference.d:76-81,
+ * randomaccessmanager.d:300-305): an iterator over the reads of reference ref_id that overlap [beg, end) — the chunks
+ * are inflated and scanned like any other stretch of the file, then filtered on the device (BamReadFilter, :366-462).
+ * Batches come from biodb_reads_next as usual and hold only the reads of the region (first_index is 0; data is the
+ * whole slice the reads lie in).  BIODB_ERR_ARG: beg >= end or invalid reference index. */
+biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
+                                      biodb_reads** out);
+
 /* ---- pileup -------------------------------------------------------------------------------------------- */
 typedef struct biodb_pileup_params {
   int32_t single_ref;          /* 1 = makePileup (first reference only, pileup.d:490-494); 0 = pileupColumns */

@@ -1,0 +1,69 @@
+"""BAI index on the host (row N2; csrc/bai.h through biodb_index_*): parse + getChunks against the oracle's
+restatement (randomaccessmanager.d:222-244) on the reference's .bai files and on an index built for a synthetic BAM.
+No GPU involved."""
+import numpy as np
+import pytest
+
+from baiutil import build_bai
+from conftest import fixture_bytes
+from oracle import oracle as orc
+
+
+def product_chunks(bai_bytes, ref, beg, end):
+    from biod_b200 import BaiFile
+    ix = BaiFile(bai_bytes)
+    try:
+        return ix.n_refs, ix.chunks(ref, beg, end)
+    finally:
+        ix.close()
+
+
+@pytest.mark.parametrize("name", ["bins.bam.bai", "ex1_header.bam.bai", "tags.bam.bai"])
+def test_chunks_match_oracle(name):
+    from biod_b200 import BaiFile
+    raw = fixture_bytes(name)
+    o = orc.Bai(raw)
+    ix = BaiFile(raw)
+    assert ix.n_refs == o.n_refs
+    rng = np.random.default_rng(3)
+    regions = [(0, 1), (0, 2**31 - 1), (0, 2**32 - 1), (16383, 16385), (2**29 - 1, 2**29 + 5), (1400, 1500), (50_000, 50_100)]
+    regions += [tuple(sorted(int(x) for x in rng.integers(0, 1 << int(rng.integers(4, 31)), 2))) for _ in range(300)]
+    some = 0
+    for r in range(o.n_refs):
+        for beg, end in regions:
+            if beg < end:
+                want = o.chunks(r, beg, end)
+                assert ix.chunks(r, beg, end) == want, (name, r, beg, end)
+                some += len(want)
+    assert some > 0
+    with pytest.raises(Exception):
+        ix.chunks(o.n_refs, 0, 10)
+
+
+def test_index_of_a_synthetic_bam():
+    from test_md_chain import random_pileup
+    data = random_pileup(np.random.default_rng(9), 3000, refs=3, block_size=2500)
+    b = orc.Bam(data).decode()
+    raw = build_bai(b)
+    o = orc.Bai(raw)
+    rng = np.random.default_rng(4)
+    for r in range(3):
+        for _ in range(40):
+            beg, end = sorted(int(x) for x in rng.integers(0, 30000, 2))
+            if beg < end:
+                assert product_chunks(raw, r, beg, end)[1] == o.chunks(r, beg, end)
+                # the index is a valid one: the oracle's region read through it equals the naive filter
+                got = [int(i) for i in orc.region_reads(b, o, r, beg, end)[0]]
+                assert got == [i for i in range(b.n_records) if b.ref_id[i] == r and b.pos[i] < end and b.end_pos[i] > beg
+                               and (b.pos[i] > beg or b.end_pos[i] > beg)]
+
+
+def test_parse_errors():
+    from biod_b200 import BaiFile, BamFormatException, ReadException
+    good = fixture_bytes("bins.bam.bai")
+    with pytest.raises(BamFormatException):
+        BaiFile(b"BAM\1" + good[4:])
+    with pytest.raises(ReadException):
+        BaiFile(good[:len(good) // 2])
+    with pytest.raises(ReadException):
+        BaiFile(good[:6])

@@ -1,0 +1,114 @@
+"""GPU parity of BAI random access: reader["chr"][beg:end] — the index's chunks inflated and
+scanned on the device, then BamReadFilter (randomaccessmanager.d:366-462) as a device-side filter + compaction —
+against the oracle's restatement: the same reads, in the same order, with the same raw bytes, fields, CIGAR words and
+virtual offsets.  Regions of test/unittests.d:145-185 on bins.bam, the other indexed fixtures, and a synthetic file
+whose chunks end in the middle of BGZF blocks and span several batches."""
+import numpy as np
+import pytest
+
+from baiutil import build_bai
+from conftest import fixture_bytes
+from oracle import oracle as orc
+from test_oracle_golden import BINS_REGIONS
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_region(rd, ref, beg, end):
+    raws, sv, ev, fields, cig = [], [], [], [], []
+    for b in rd.region_batches(ref, beg, end, copy=True):
+        assert b.n > 0
+        for i in range(b.n):
+            o = int(b.rec_off[i]) + 4
+            raws.append(b.data[o:o + int(b.block_size[i])].tobytes())
+            fields.append((int(b.ref_id[i]), int(b.pos[i]), int(b.end_pos[i]), int(b.bin_mq_nl[i]), int(b.flag_nc[i]), int(b.l_seq[i])))
+            cig.append(b.cigar[int(b.cigar_off[i]):int(b.cigar_off[i + 1])].tolist())
+        sv += b.start_voffset.tolist()
+        ev += b.end_voffset.tolist()
+    return raws, sv, ev, fields, cig
+
+
+def check_region(rd, o, bai, ref, beg, end):
+    idx, wsv, wev = orc.region_reads(o, bai, ref, beg, end)
+    raws, sv, ev, fields, cig = gpu_region(rd, ref, beg, end)
+    assert len(raws) == len(idx), (ref, beg, end, len(raws), len(idx))
+    for k, i in enumerate(idx):
+        i = int(i)
+        assert raws[k] == o.record_bytes(i).tobytes(), (ref, beg, end, k)
+        assert fields[k] == (int(o.ref_id[i]), int(o.pos[i]), int(o.end_pos[i]),
+                             (int(o.bin[i]) << 16) | (int(o.mapq[i]) << 8) | int(o.l_read_name[i]),
+                             (int(o.flag[i]) << 16) | int(o.n_cigar[i]), int(o.l_seq[i]))
+        assert cig[k] == o.cigar[int(o.cigar_off[i]):int(o.cigar_off[i + 1])].tolist()
+    assert sv == wsv.tolist(), (ref, beg, end)
+    assert ev == wev.tolist(), (ref, beg, end)
+    return len(idx)
+
+
+@pytest.mark.parametrize("bpb", [0, 1])
+def test_bins_bam_regions(bpb):
+    # test/unittests.d:145-185
+    from biod_b200 import BamReader
+    data = fixture_bytes("bins.bam")
+    o = orc.Bam(data).decode()
+    bai = orc.Bai(fixture_bytes("bins.bam.bai"))
+    rd = BamReader(data, blocks_per_batch=bpb, want_offsets=True, index=fixture_bytes("bins.bam.bai"))
+    large = o.ref_names.index("large")
+    total = sum(check_region(rd, o, bai, large, beg, end) for beg, end in BINS_REGIONS)
+    assert total > 0
+    for name in o.ref_names:
+        r = o.ref_names.index(name)
+        assert check_region(rd, o, bai, r, 0, o.ref_lens[r]) > 0
+        # test/unittests.d:193-205
+        first = next(iter(rd[name][0:o.ref_lens[r]]))
+        assert first.name == f"{name}:r1:0..1:len1:bin4681:hexbin0x1249"
+        assert rd[name].firstPosition() == 0
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "tags.bam"])
+def test_other_indexed_fixtures(name):
+    from biod_b200 import BamReader
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    raw = fixture_bytes(name + ".bai")
+    bai = orc.Bai(raw)
+    rd = BamReader(data, blocks_per_batch=2, want_offsets=True, index=raw)
+    rng = np.random.default_rng(8)
+    for r in range(len(o.ref_names)):
+        ln = o.ref_lens[r]
+        for beg, end in [(0, ln), (0, 1), (ln - 1, ln)] + [tuple(sorted(int(x) for x in rng.integers(0, ln, 2))) for _ in range(12)]:
+            if beg < end:
+                check_region(rd, o, bai, r, beg, end)
+
+
+def test_synthetic_chunks_across_batches():
+    from biod_b200 import BamReader
+    from test_md_chain import random_pileup
+    data = random_pileup(np.random.default_rng(21), 4000, refs=3, block_size=1800)
+    o = orc.Bam(data).decode()
+    raw = build_bai(o)
+    bai = orc.Bai(raw)
+    rng = np.random.default_rng(6)
+    total = 0
+    for bpb in (0, 1, 3):
+        rd = BamReader(data, blocks_per_batch=bpb, want_offsets=True, index=raw)
+        for r in range(3):
+            for beg, end in [(0, 100000), (0, 1), (5000, 5001)] + [tuple(sorted(int(x) for x in rng.integers(0, 12000, 2))) for _ in range(10)]:
+                if beg < end:
+                    total += check_region(rd, o, bai, r, beg, end)
+    assert total > 0
+
+
+def test_region_argument_errors():
+    from biod_b200 import BamReader
+    data = fixture_bytes("bins.bam")
+    rd = BamReader(data, index=fixture_bytes("bins.bam.bai"))
+    with pytest.raises(Exception, match="start must be less than end"):
+        list(rd["large"][10:10])
+    with pytest.raises(Exception, match="does not exist"):
+        rd["nope"]
+    with pytest.raises(Exception, match="Invalid reference sequence index"):
+        list(rd.region_reads(99, 0, 10))
+    with pytest.raises(Exception, match="must be provided"):
+        list(BamReader(data)["large"][0:10])
+    # a sequential pass after region reads on the same reader is unaffected
+    assert sum(b.n for b in rd.read_batches()) == orc.Bam(data).decode().n_records
