@@ -23,6 +23,7 @@ import contrib.undead.stream : ReadException;
 import std.parallelism : TaskPool, taskPool;
 import std.string : toStringz;
 import std.conv : to;
+import std.exception : enforce;
 import std.range : InputRange, inputRangeObject;
 
 extern (C) nothrow @nogc {
@@ -75,6 +76,13 @@ extern (C) nothrow @nogc {
     int biodb_pileup_next(biodb_pileup*, biodb_column_batch*);
     void biodb_pileup_end(biodb_pileup*);
     int biodb_pileup_ref_id(const(biodb_pileup)*);
+    // BAI random access (row N2)
+    struct biodb_index;
+    int biodb_index_open(const(void)* bai, size_t len, biodb_index**);
+    void biodb_index_close(biodb_index*);
+    int biodb_index_n_refs(const(biodb_index)*);
+    long biodb_index_chunks(const(biodb_index)*, uint ref_id, uint beg, uint end, ulong* out2, ulong cap);
+    int biodb_reads_begin_region(biodb_reader*, const(biodb_index)*, uint ref_id, uint beg, uint end, biodb_reads**);
 }
 
 /// Maps a status + error record to the exception classes BioD's tests pin (test/unittests.d:132-142).
@@ -101,6 +109,12 @@ struct GpuBamReadRange(bool withOffsets = false) {
     this(biodb_reader* h, IBamSamReader reader) {
         _h = h; _reader = reader;
         if (biodb_reads_begin(h, &_it) != BIODB_OK) raise(biodb_last_error(h));
+        fetch();
+    }
+    /// the reads of reference ref_id overlapping [beg, end): RandomAccessManager.getReads (randomaccessmanager.d:300-305)
+    this(biodb_reader* h, IBamSamReader reader, const(biodb_index)* ix, uint ref_id, uint beg, uint end) {
+        _h = h; _reader = reader;
+        if (biodb_reads_begin_region(h, ix, ref_id, beg, end, &_it) != BIODB_OK) raise(biodb_last_error(h));
         fetch();
     }
     ~this() { if (_it !is null) { biodb_reads_end(_it); _it = null; } }
@@ -132,6 +146,25 @@ struct GpuBamReadRange(bool withOffsets = false) {
     }
 }
 
+/// `bam["chr1"]` (bam/reference.d:37-160): slicing gives the reads that overlap [start, end), fetched through the BAI
+/// index — chunks inflated and scanned on the GPU, BamReadFilter (randomaccessmanager.d:366-462) as a device-side filter.
+struct GpuReferenceSequence {
+    private GpuBamReader _bam;
+    private int _ref_id;
+    private ReferenceSequenceInfo _info;
+    string name() @property const { return _info.name; }
+    int length() @property const { return _info.length; }
+    int id() @property const { return _ref_id; }
+    auto opSlice(uint start, uint end) {
+        enforce(start < end, "start must be less than end");                      // reference.d:77
+        enforce(_ref_id >= 0, "invalid reference id");
+        return GpuBamReadRange!true(_bam.handle, _bam, _bam.index, cast(uint)_ref_id, start, end);
+    }
+    auto opSlice() { return opSlice(0, length); }
+    VirtualOffset startVirtualOffset() { auto r = opSlice(); enforce(!r.empty); return r.front.start_virtual_offset; }
+    int firstPosition() { auto r = opSlice(); return r.empty ? -1 : r.front.read.position; }
+}
+
 /// Drop-in for BamReader on the streaming path (bam/reader.d:80-598).
 class GpuBamReader : IBamSamReader {
     private biodb_reader* _h;
@@ -154,7 +187,7 @@ class GpuBamReader : IBamSamReader {
             _refs ~= ReferenceSequenceInfo(nm[0 .. nl].idup, len);
         }
     }
-    ~this() { if (_h !is null) biodb_close(_h); }
+    ~this() { if (_ix !is null) biodb_index_close(_ix); if (_h !is null) biodb_close(_h); }
 
     SamHeader header() @property { if (_header is null) _header = new SamHeader(_headertext); return _header; }
     const(ReferenceSequenceInfo)[] reference_sequences() @property const nothrow { return _refs; }
@@ -164,6 +197,24 @@ class GpuBamReader : IBamSamReader {
     InputRange!BamRead allReads() @property { return inputRangeObject(reads()); }
     void assumeSequentialProcessing() {}   // batches already reuse their buffer (reader.d:324)
     package biodb_reader* handle() { return _h; }
+
+    // random access (reader.d:424-447): the index is looked for next to the file, as BaiFile does (baifile.d:95-113)
+    private biodb_index* _ix;
+    package const(biodb_index)* index() {
+        if (_ix is null) {
+            import std.file : exists, read;
+            auto first = _filename ~ ".bai";
+            enforce(exists(first), "BAM index file (.bai) must be provided");     // randomaccessmanager.d:202-204
+            auto bytes = cast(ubyte[])read(first);
+            if (biodb_index_open(bytes.ptr, bytes.length, &_ix) != BIODB_OK) raise(biodb_open_error());
+        }
+        return _ix;
+    }
+    GpuReferenceSequence opIndex(string ref_name) {                               // reader.d:424-429
+        foreach (i, r; _refs) if (r.name == ref_name) return GpuReferenceSequence(this, cast(int)i, r);
+        throw new Exception("Reference with name " ~ ref_name ~ " does not exist");
+    }
+    GpuReferenceSequence reference(int ref_id) { return GpuReferenceSequence(this, ref_id, _refs[ref_id]); }   // reader.d:435-440
 }
 
 /// Pileup column over a GPU column batch; same surface as PileupColumn (pileup.d:236-290) for the fields
