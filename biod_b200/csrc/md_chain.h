@@ -42,7 +42,12 @@ class MdChain {
       return;
     }
     if (pos == adm_pos_) {                    // admitted in the same column as the previous read
-      pending_.push_back(r);
+      if (settled_) {                         // (its step is already simulated and cannot end in a switch: see below)
+        md_add(r, adm_had_zero_);
+        max_end_ = std::max(max_end_, r.end);
+      } else {
+        pending_.push_back(r);
+      }
       return;
     }
     flush_admissions(out);                    // columns up to and including the previous admission position are settled
@@ -55,6 +60,18 @@ class MdChain {
     adm_pos_ = pos;
     adm_init_ = false;
     adm_had_zero_ = max_end_ < pos;           // coverage of the previous column was 0 (only without skip_zero_coverage)
+    // Fast path (nearly every read of a deep pileup): the chunk has bases left beyond this column, so neither the steps
+    // up to it nor the step at it can end in a switch, whatever else is admitted at this position — the step can be
+    // simulated right away instead of waiting for the next position to show up.
+    if (have_chunk_ && ci_ + (pos - cur_) < chunk_.len) {
+      ci_ += pos - cur_;
+      cur_ = pos;
+      md_add(r, adm_had_zero_);
+      max_end_ = std::max(max_end_, r.end);
+      settled_ = true;
+      return;
+    }
+    settled_ = false;
     pending_.push_back(r);
   }
 
@@ -122,6 +139,7 @@ class MdChain {
   int64_t adm_pos_ = 0;
   bool adm_init_ = false, adm_had_zero_ = false;
   bool fin_ = false;          // finish_island() has run and no read has been admitted since
+  bool settled_ = false;      // the step at adm_pos_ has been simulated already (fast path of admit())
 
   bool chunk_empty() const { return !have_chunk_ || ci_ >= chunk_.len; }
 
@@ -220,6 +238,7 @@ class MdChain {
     adm_init_ = true;
     adm_had_zero_ = true;
     fin_ = false;
+    settled_ = false;
     pending_.clear();
     pending_.push_back(r);     // (max_end_ is updated when the admissions are flushed)
   }
