@@ -75,6 +75,53 @@ class MdChain {
     pending_.push_back(r);
   }
 
+  // The live reads of one reference group of a batch, in file order: read k has index id0 + k, position pos[k], end
+  // position end[k] (INT32_MIN = not a read of the pileup: skipped) and dna() length len[k].  Same result as admit()
+  // read by read; runs of reads that fall inside the stretch the current chunk still serves — where nothing can happen
+  // but the pending provider being replaced — go through a tight loop.
+  void admit_many(uint64_t id0, int32_t ref_id, const int32_t* pos, const int32_t* end, const int32_t* len, size_t n,
+                  std::vector<MdSegment>* out) {
+    size_t k = 0;
+    while (k < n) {
+      if (end[k] == INT32_MIN) { ++k; continue; }
+      if (started_ && !fin_ && ref_id == ref_ && curr_ref_ == ref_ && settled_ && pending_.empty() && have_chunk_ && ci_ < chunk_.len &&
+          pos[k] >= cur_) {
+        // positions up to last_safe are served by the chunk with bases to spare: no step there ends in a switch
+        const int64_t last_safe = cur_ + (chunk_.len - ci_) - 1;
+        int64_t at = cur_;                 // position of the last read taken
+        bool hz = adm_had_zero_;
+        const size_t k0 = k;
+        for (; k < n; ++k) {
+          const int32_t e = end[k];
+          if (e == INT32_MIN) continue;
+          const int64_t p = pos[k];
+          if (p > last_safe) break;
+          if (p != at) {
+            if (skip_zero_ && max_end_ < p) break;                   // the sweep jumps: the general path handles it
+            hz = max_end_ < p;
+            at = p;
+          }
+          if ((uint32_t)p > chunk_end_) break;                       // (the rare rule of pileup.d:579: general path)
+          if ((uint32_t)e > chunk_end_ && (!has_provider_ || e > (int32_t)provider_.end))
+            provider_ = Rd{id0 + k, p, e, len[k]};
+          if ((uint32_t)e > chunk_end_) has_provider_ = true;
+          if (e > max_end_) max_end_ = e;
+        }
+        if (at != cur_ || k != k0) {
+          ci_ += at - cur_;
+          cur_ = at;
+          adm_pos_ = at;
+          adm_init_ = false;
+          adm_had_zero_ = hz;
+          settled_ = true;
+        }
+        if (k != k0) continue;
+      }
+      admit(id0 + k, ref_id, pos[k], end[k], len[k], out);
+      ++k;
+    }
+  }
+
   // End of the pileup (or of the batch range that will ever be simulated): settle what is pending.
   void finish(std::vector<MdSegment>* out) {
     if (!started_) return;

@@ -657,11 +657,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       pl->md_segs.clear();
       const int32_t* hm = pl->md_h.as<int32_t>();
       const uint64_t id0 = pl->first_index + (md_a0 - pl->n_carry_view);
-      for (size_t k = 0; k < md_n; ++k) {
-        const int32_t e = hm[md_n + k];
-        if (e == INT32_MIN) continue;                                  // not a read of the pileup
-        pl->md->admit(id0 + k, ref, hm[k], e, hm[2 * md_n + k], &pl->md_segs);
-      }
+      pl->md->admit_many(id0, ref, hm, hm + md_n, hm + 2 * md_n, md_n, &pl->md_segs);   // (end INT32_MIN = not a read of the pileup)
       if (trailing) pl->md->drain(E, &pl->md_segs);
       else pl->md->finish_reference(&pl->md_segs);
     }

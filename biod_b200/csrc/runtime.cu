@@ -1120,14 +1120,25 @@ int64_t biodb_debug_md_chain(const int32_t* ref_id, const int64_t* pos, const in
                              int32_t skip_zero_coverage, uint64_t batch_reads, int64_t* seg4, uint64_t cap) {
   MdChain chain(skip_zero_coverage != 0);
   std::vector<MdSegment> segs;
-  for (uint64_t i = 0; i < n; ++i) {
-    chain.admit(i, ref_id[i], pos[i], end[i], dna_len[i], &segs);
-    if (!batch_reads) continue;
-    if (i + 1 == n || ref_id[i + 1] != ref_id[i]) {
-      chain.finish_reference(&segs);
-    } else if ((i + 1) % batch_reads == 0) {
-      chain.drain(pos[i], &segs);
-      segs.push_back(MdSegment{pos[i], -1, (uint64_t)(int64_t)ref_id[i], 0});
+  if (!batch_reads) {
+    for (uint64_t i = 0; i < n; ++i) chain.admit(i, ref_id[i], pos[i], end[i], dna_len[i], &segs);
+  } else {
+    std::vector<int32_t> p32, e32, l32;
+    for (uint64_t i = 0; i < n;) {
+      // one reference group of one batch, the unit the pipeline hands to admit_many
+      uint64_t j = i + 1;
+      while (j < n && ref_id[j] == ref_id[i] && j % batch_reads != 0) ++j;
+      p32.assign(pos + i, pos + j);
+      e32.assign(end + i, end + j);
+      l32.assign(dna_len + i, dna_len + j);
+      chain.admit_many(i, ref_id[i], p32.data(), e32.data(), l32.data(), (size_t)(j - i), &segs);
+      if (j == n || ref_id[j] != ref_id[i]) {
+        chain.finish_reference(&segs);
+      } else {
+        chain.drain(pos[j - 1], &segs);
+        segs.push_back(MdSegment{pos[j - 1], -1, (uint64_t)(int64_t)ref_id[i], 0});
+      }
+      i = j;
     }
   }
   chain.finish(&segs);

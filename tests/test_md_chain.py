@@ -64,7 +64,7 @@ def check(data, skip_zero, single_ref, start_from=0, end_at=2**64 - 1):
          else b.pileup_columns(skip_zero, use_md_tag=True))
     assert p.status == 0
     want = "".join(chr(x) for x in p.ref_base)
-    for batch_reads in (0, 1, 7, 64):
+    for batch_reads in (0, 1, 7, 64, 10**9):
         got = chain_reference(b, skip_zero, single_ref, start_from, batch_reads)
         mine = "".join(got.get((int(r), int(q)), "N") for r, q in zip(p.col_ref, p.col_pos))
         assert mine == want, batch_reads
