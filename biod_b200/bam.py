@@ -344,6 +344,34 @@ class BamReader:
         finally:
             L.biodb_reads_end(it)
 
+    def getReadsBetween(self, from_voffset, to_voffset=None, max_blocks=0):
+        """reader.d:350-356: the reads from one virtual offset (the start of a record) to another (the end of one;
+        None = the end of the file)."""
+        L = self._L
+        it = C.c_void_p()
+        to = 2**64 - 1 if to_voffset is None else int(to_voffset)
+        if L.biodb_reads_begin_between(self._h, int(from_voffset), to, max_blocks, C.byref(it)) != capi.OK:
+            self._err()
+        try:
+            while True:
+                b = capi.RecordBatch()
+                st = L.biodb_reads_next(it, C.byref(b))
+                if st == capi.EOF:
+                    return
+                if st != capi.OK:
+                    self._err()
+                batch = RecordBatch(b, True)
+                for i in range(batch.n):
+                    yield BamRead(batch, i)
+        finally:
+            L.biodb_reads_end(it)
+
+    def getReadAt(self, voffset):
+        """reader.d:336-339: the read that starts at a virtual offset."""
+        for r in self.getReadsBetween(voffset, None, max_blocks=2):
+            return r
+        raise ReadException("not enough data in stream")
+
     def region_reads(self, ref_id, start, end):
         for batch in self.region_batches(ref_id, start, end, copy=True):
             for i in range(batch.n):

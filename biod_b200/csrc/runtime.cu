@@ -782,7 +782,9 @@ struct biodb_reads {
   Pass pass;
   // region mode (biodb_reads_begin_region): the chunks the index names are read one after the other, each as a pass of
   // its own from chunk.beg to chunk.end, and every batch goes through the region filter (region.cu)
-  bool region = false;
+  bool region = false;                 // chunk mode: the pass reads it->chunks one after the other
+  bool filter = false;                 // ... and every batch goes through the region filter
+  uint32_t chunk_blocks = 0;           // blocks per batch in chunk mode (0 = the reader's option)
   bool region_done = false;            // a read beyond the region was met: nothing further can overlap it
   std::vector<VoChunk> chunks;
   size_t chunk_i = 0;                  // chunk being read
@@ -809,7 +811,8 @@ struct biodb_reads {
     if (cs) cudaStreamSynchronize(cs);
     inflight = ahead_done = staged_valid = false;
     ahead_status = BIODB_OK;
-    region = region_done = false;
+    region = region_done = filter = false;
+    chunk_blocks = 0;
     chunks.clear();
     chunk_i = 0;
   }
@@ -829,7 +832,7 @@ static biodb_status region_next(biodb_reads* it) {
   cudaStream_t st = p.st;
   while (true) {
     if (it->region_done || it->chunk_i >= it->chunks.size()) return BIODB_EOF;
-    biodb_status s = p.next((uint32_t)p.r->opts.blocks_per_batch, 0);
+    biodb_status s = p.next(it->chunk_blocks ? it->chunk_blocks : (uint32_t)p.r->opts.blocks_per_batch, 0);
     if (s == BIODB_EOF) {
       if (++it->chunk_i >= it->chunks.size()) return BIODB_EOF;
       region_seek(it, it->chunk_i);
@@ -837,6 +840,7 @@ static biodb_status region_next(biodb_reads* it) {
     }
     if (s != BIODB_OK) return s;
     if (p.n == 0) continue;
+    if (!it->filter) return BIODB_OK;                     // getReadsBetween: every record of the stretch
     if (p.n > 0xfffffff0ull) return p.fail(BIODB_ERR_NOMEM, 0, 0, "too many records in one batch; lower blocks_per_batch");
     // room for the compacted tables
     if (p.n + 8 > it->sel_cap || p.n_cigar + 8 > it->sel_cig_cap) {
@@ -897,9 +901,9 @@ static biodb_status reads_produce(biodb_reads* it, int s) {
     if (p.n == 0) return p.next(1, 0);                      // finished: raises the pending error or EOF
   }
   ReadsSlot& sl = it->slot[s];
-  sl.n = it->region ? it->sel_n : p.n;
+  sl.n = it->filter ? it->sel_n : p.n;
   sl.used = p.tail;                                       // bytes of the slice covered by whole records
-  sl.n_cigar = it->region ? it->sel_cig : p.n_cigar;
+  sl.n_cigar = it->filter ? it->sel_cig : p.n_cigar;
   sl.first = it->region ? 0 : first;
   sl.segs = p.segs;
   sl.chunk_end_vo = sl.next_chunk_beg_vo = 0;
@@ -915,10 +919,10 @@ static biodb_status reads_produce(biodb_reads* it, int s) {
   src[0] = p.d_u.p;
   for (int a = 0; a < 9; ++a) {
     bytes[1 + a] = (size_t)(sl.n + (a == 8 ? 1 : 0)) * REC_ESZ[a];
-    src[1 + a] = it->region ? it->d_sel[a].p : p.d_rec[a].p;
+    src[1 + a] = it->filter ? it->d_sel[a].p : p.d_rec[a].p;
   }
   bytes[10] = (size_t)sl.n_cigar * 4;
-  src[10] = it->region ? it->d_sel[9].p : p.d_rec[9].p;
+  src[10] = it->filter ? it->d_sel[9].p : p.d_rec[9].p;
   // device -> staging (ordered behind the previous batch's staging -> host copies on the same stream)
   for (int k = 0; k < 11 && ok; ++k) {
     // (grow with headroom: the two host slots and the staging area see batches of slightly different sizes, and a
@@ -1013,6 +1017,7 @@ biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, ui
   if (s != BIODB_OK) return s;
   biodb_reads* it = *out;
   it->region = true;
+  it->filter = true;
   it->region_done = false;
   it->chunks.swap(c);
   it->chunk_i = 0;
@@ -1020,6 +1025,27 @@ biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, ui
   it->reg_beg = beg;
   it->reg_end = end;
   if (!it->chunks.empty()) region_seek(it, 0);
+  return BIODB_OK;
+}
+
+biodb_status biodb_reads_begin_between(biodb_reader* r, uint64_t from_voffset, uint64_t to_voffset, uint32_t max_blocks,
+                                       biodb_reads** out) {
+  if (!r || !out) return BIODB_ERR_ARG;
+  biodb_status s = biodb_reads_begin(r, out);
+  if (s != BIODB_OK) return s;
+  biodb_reads* it = *out;
+  it->region = true;
+  it->filter = false;
+  it->chunk_blocks = max_blocks;
+  it->chunks.assign(1, VoChunk{from_voffset, to_voffset});
+  it->chunk_i = 0;
+  if (to_voffset == ~0ull) {
+    it->pass.rewind(from_voffset >> 16, (uint32_t)(from_voffset & 0xFFFF));     // to the end of the file
+  } else if (to_voffset <= from_voffset) {
+    it->chunks.clear();
+  } else {
+    region_seek(it, 0);
+  }
   return BIODB_OK;
 }
 

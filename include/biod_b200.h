@@ -142,6 +142,15 @@ int64_t biodb_index_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg,
 biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
                                       biodb_reads** out);
 
+/* getReadsBetween(from, to) (reader.d:350-356, randomaccessmanager.d:186-196): the records from virtual offset `from`
+ * (which must point at the start of a record) up to virtual offset `to` — the end offset of some record, or
+ * UINT64_MAX for "to the end of the file".  getReadAt(offset) (reader.d:336-339) is its first record; max_blocks > 0
+ * bounds the BGZF blocks inflated per batch for such point reads (0 = options.blocks_per_batch).
+ * Restatement-defined: a `to` inside a record is a BIODB_ERR_TRUNCATED after the whole records in front of it (BioD
+ * stops silently). */
+biodb_status biodb_reads_begin_between(biodb_reader* r, uint64_t from_voffset, uint64_t to_voffset, uint32_t max_blocks,
+                                       biodb_reads** out);
+
 /* ---- pileup -------------------------------------------------------------------------------------------- */
 typedef struct biodb_pileup_params {
   int32_t single_ref;          /* 1 = makePileup (first reference only, pileup.d:490-494); 0 = pileupColumns */

@@ -112,3 +112,28 @@ def test_region_argument_errors():
         list(BamReader(data)["large"][0:10])
     # a sequential pass after region reads on the same reader is unaffected
     assert sum(b.n for b in rd.read_batches()) == orc.Bam(data).decode().n_records
+
+
+def test_reads_between_and_read_at():
+    # getReadsBetween (reader.d:350-356) and getReadAt (reader.d:336-339, test/unittests.d:193-205)
+    from biod_b200 import BamReader
+    data = fixture_bytes("ex1_header.bam")
+    o = orc.Bam(data).decode()
+    n = o.n_records
+    for bpb in (0, 2):
+        rd = BamReader(data, blocks_per_batch=bpb, want_offsets=True)
+        for a, z in [(0, n), (0, 1), (5, 6), (100, 1500), (n - 3, n), (700, 701), (1234, 3000)]:
+            want = [int(i) for i in orc.reads_between(o, int(o.start_vo[a]), int(o.end_vo[z - 1]))]
+            assert want == list(range(a, z))
+            got = list(rd.getReadsBetween(int(o.start_vo[a]), int(o.end_vo[z - 1])))
+            assert [r.raw.tobytes() for r in got] == [o.record_bytes(i).tobytes() for i in want], (a, z)
+            assert [r.start_virtual_offset for r in got] == o.start_vo[a:z].tolist()
+        assert len(list(rd.getReadsBetween(int(o.start_vo[n - 10])))) == 10          # to the end of the file
+        assert list(rd.getReadsBetween(int(o.start_vo[5]), int(o.start_vo[5]))) == []
+        for i in (0, 1, 777, n - 1):
+            r = rd.getReadAt(int(o.start_vo[i]))
+            assert r.raw.tobytes() == o.record_bytes(i).tobytes() and r.start_virtual_offset == int(o.start_vo[i])
+    data = fixture_bytes("bins.bam")
+    rd = BamReader(data, want_offsets=True, index=fixture_bytes("bins.bam.bai"))
+    for name in ("tiny", "small", "large"):
+        assert rd.getReadAt(rd[name].startVirtualOffset()).name == f"{name}:r1:0..1:len1:bin4681:hexbin0x1249"
