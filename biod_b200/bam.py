@@ -240,6 +240,19 @@ class BaiFile:
         return [(int(out[2 * k]), int(out[2 * k + 1])) for k in range(n)]
 
 
+class RegionReads:
+    """The range `bam["chr"][start .. end)` (reference.d:76-81): iterating it yields the reads of the region; handing it
+    to makePileup / pileupColumns gives the pileup of exactly these reads (examples/read_bam_file.d:22-25)."""
+
+    def __init__(self, reader, ref_id, start, end):
+        if not start < end:
+            raise Exception("start must be less than end")                       # reference.d:77
+        self.reader, self.ref_id, self.start, self.end = reader, ref_id, start, end
+
+    def __iter__(self):
+        return self.reader.region_reads(self.ref_id, self.start, self.end)
+
+
 class ReferenceSequence:
     """bam/reference.d:37-160: `reader["chr1"]`; slicing it gives the reads that overlap [start, end)."""
 
@@ -249,7 +262,7 @@ class ReferenceSequence:
     def __getitem__(self, sl):
         start = 0 if sl.start is None else sl.start
         end = self.length if sl.stop is None else sl.stop
-        return self._reader.region_reads(self.id, start, end)
+        return RegionReads(self._reader, self.id, start, end)
 
     def reads(self):
         return self[0:self.length]
@@ -419,8 +432,9 @@ class BamReader:
 
     def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
                        want_query_offset=False, copy=False, shard=None, halo_blocks=8, shard_info=None, counts_only=False,
-                       compact_reads=False):
-        """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015)."""
+                       compact_reads=False, region=None):
+        """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015);
+        region=(ref_id, start, end) piles up the reads of bam[ref][start .. end) only (read_idx then counts those)."""
         L = self._L
         p = capi.PileupParams()
         p.single_ref, p.skip_zero_coverage, p.use_md_tag = int(single_ref), int(skip_zero_coverage), int(use_md_tag)
@@ -428,7 +442,9 @@ class BamReader:
         p.counts_only = int(counts_only)
         p.compact_reads = int(compact_reads)
         pl = C.c_void_p()
-        if shard is not None:
+        if region is not None:
+            st = L.biodb_pileup_begin_region(self._h, self._bai()._h, region[0], region[1], region[2], C.byref(p), C.byref(pl))
+        elif shard is not None:
             st = L.biodb_pileup_begin_shard(self._h, C.byref(p), shard[0], shard[1], halo_blocks, C.byref(pl))
         else:
             st = L.biodb_pileup_begin(self._h, C.byref(p), C.byref(pl))
@@ -595,6 +611,9 @@ class PileupColumn:
 
 
 def _columns(reader, single_ref, **kw):
+    if isinstance(reader, RegionReads):                      # makePileup(bam["chr"][a .. b), ...)
+        kw["region"] = (reader.ref_id, reader.start, reader.end)
+        reader = reader.reader
     for batch in reader.column_batches(single_ref, copy=True, **kw):
         for c in range(batch.n_columns):
             yield PileupColumn(batch, c)

@@ -13,6 +13,7 @@
 
 #include <memory>
 
+#include "bai.h"
 #include "md_chain.h"
 #include "runtime.h"
 #include "scan.cuh"
@@ -83,6 +84,15 @@ struct biodb_pileup {
   PinBuf md_h, md_hsegs;
   MdKeep md_keep{{~0ull, ~0ull}, {0, 0}, {nullptr, nullptr}};   // providers materialised by the previous batch
   int md_keep_set = 0;
+  // region mode (biodb_pileup_begin_region): the reads are those of bam[ref][beg .. end) — the index's chunks read one
+  // after the other, every batch reduced to the reads of the region (region.cu) before the pileup sees it
+  bool region = false, region_done = false;
+  std::vector<VoChunk> chunks;
+  size_t chunk_i = 0;
+  uint32_t reg_ref = 0, reg_beg = 0, reg_end = 0;
+  uint64_t region_index = 0;         // reads of the region handed to the pileup so far (read_idx counts these)
+  DevBuf d_sel[10], d_rscratch, d_rinfo;
+  uint64_t sel_cap = 0, sel_cig_cap = 0;
   // single_ref state
   bool started = false, done = false;
   int32_t target_ref = -1;
@@ -179,13 +189,79 @@ static GroupScratch scratch(biodb_pileup* pl) {
   return s;
 }
 
+// Region mode: reduce the batch the pass has just produced to the reads of the region (BamReadFilter,
+// randomaccessmanager.d:366-462), in place, so that the pileup kernels see nothing else.
+static biodb_status region_reduce(biodb_pileup* pl, uint64_t front) {
+  Pass& p = pl->pass;
+  cudaStream_t st = p.st;
+  const bool more_chunks = pl->chunk_i + 1 < pl->chunks.size();
+  if (p.n) {
+    if (p.n > 0xfffffff0ull) return pl->fail(BIODB_ERR_NOMEM, "too many records in one batch; lower blocks_per_batch");
+    if (p.n + 8 > pl->sel_cap || p.n_cigar + 8 > pl->sel_cig_cap) {
+      pl->sel_cap = std::max<uint64_t>(pl->sel_cap, p.n + p.n / 8 + 1024);
+      pl->sel_cig_cap = std::max<uint64_t>(pl->sel_cig_cap, p.n_cigar + p.n_cigar / 8 + 1024);
+      static const size_t esz[10] = {8, 4, 4, 4, 4, 4, 4, 4, 8, 4};
+      for (int a = 0; a < 9; ++a) PL_TRY(pl->d_sel[a].ensure((size_t)(pl->sel_cap + 2) * esz[a], st));
+      PL_TRY(pl->d_sel[9].ensure((size_t)(pl->sel_cig_cap + 2) * 4, st));
+    }
+    PL_TRY(pl->d_rscratch.ensure(region_scratch_elems(p.n) * 4, st));
+    PL_TRY(pl->d_rinfo.ensure(64, st));
+    RecordArrays in = p.arrays(front);
+    RecordArrays out{pl->d_sel[0].as<uint64_t>(), pl->d_sel[1].as<int32_t>(), pl->d_sel[2].as<int32_t>(), pl->d_sel[3].as<int32_t>(),
+                     pl->d_sel[4].as<int32_t>(), pl->d_sel[5].as<uint32_t>(), pl->d_sel[6].as<uint32_t>(), pl->d_sel[7].as<int32_t>(),
+                     pl->d_sel[8].as<uint64_t>(), pl->d_sel[9].as<uint32_t>(), pl->sel_cap, pl->sel_cig_cap};
+    p.stage_begin();
+    PL_TRY(launch_region_filter(in, p.n, pl->reg_ref, pl->reg_beg, pl->reg_end, out, pl->d_rscratch.as<uint32_t>(),
+                                pl->d_rinfo.as<uint32_t>(), st));
+    p.stage_end(&p.stats.scan_ms);
+    uint32_t* hi = pl->h_small.as<uint32_t>() + 32;
+    PL_TRY(launch_copy_bytes(hi, pl->d_rinfo.p, 12, st));
+    PL_TRY(cudaStreamSynchronize(st));
+    const uint64_t n_keep = hi[1], n_cig = hi[2];
+    if (hi[0] != 0xffffffffu) pl->region_done = true;       // a read beyond the region: nothing further can overlap it
+    // the kept records take the place of the batch's records
+    static const size_t esz[8] = {8, 4, 4, 4, 4, 4, 4, 4};
+    void* dst[8] = {in.rec_off, in.block_size, in.ref_id, in.pos, in.end_pos, in.bin_mq_nl, in.flag_nc, in.l_seq};
+    for (int a = 0; a < 8; ++a)
+      if (n_keep) PL_TRY(launch_copy_bytes(dst[a], pl->d_sel[a].p, (size_t)n_keep * esz[a], st));
+    PL_TRY(launch_copy_bytes(in.cigar_off, pl->d_sel[8].p, (size_t)(n_keep + 1) * 8, st));
+    if (n_cig) PL_TRY(launch_copy_bytes(in.cigar, pl->d_sel[9].p, (size_t)n_cig * 4, st));
+    p.n = n_keep;
+    p.n_cigar = n_cig;
+    pl->region_index += n_keep;
+  }
+  if (pl->region_done) {
+    // the rest of this chunk and the chunks behind it are not read
+    p.finished = true;
+    p.final_slice = true;
+    pl->chunk_i = pl->chunks.size();
+  } else if (p.final_slice && more_chunks && !p.pending.status) {
+    p.final_slice = false;                                  // the next chunk goes on with reads of the same reference
+  }
+  return BIODB_OK;
+}
+
 // Fetch the next batch of records and lay the carried reads in front of it.
 static biodb_status load_batch(biodb_pileup* pl) {
   Pass& p = pl->pass;
   CarryBufs& c = pl->carry[pl->cur];
-  const uint64_t first = p.n_records_total;
+  uint64_t first = p.n_records_total;
+  if (pl->region) {
+    // a chunk's pass is over: go on with the next chunk (the pass then hands out that chunk's first batch)
+    while (p.finished && !p.pending.status && !pl->region_done && pl->chunk_i + 1 < pl->chunks.size()) {
+      const VoChunk& ch = pl->chunks[++pl->chunk_i];
+      p.rewind(ch.beg >> 16, (uint32_t)(ch.beg & 0xFFFF));
+      p.stop_coffset = ch.end >> 16;
+      p.stop_uoffset = (uint32_t)(ch.end & 0xFFFF);
+    }
+    first = pl->region_index;
+  }
   biodb_status s = p.next((uint32_t)p.r->opts.blocks_per_batch, c.n);
   if (s != BIODB_OK) return s;
+  if (pl->region) {
+    biodb_status rs = region_reduce(pl, c.n);
+    if (rs != BIODB_OK) return rs;
+  }
   if (pl->sharded && pl->halo_blocks_left && p.blocks.size()) {
     // records that start in the halo blocks: rec_base[h] of the scan workspace (the halo is the head of the first batch)
     uint32_t hb = std::min<uint32_t>(pl->halo_blocks_left, (uint32_t)p.blocks.size());
@@ -302,6 +378,10 @@ void biodb_pileup::reset(const biodb_pileup_params* p) {
   memset(&shard, 0, sizeof shard);
   halo_blocks_left = 0;
   index_bias = 0;
+  region = region_done = false;
+  chunks.clear();
+  chunk_i = 0;
+  region_index = 0;
   md.reset(prm.use_md_tag ? new MdChain(prm.skip_zero_coverage != 0) : nullptr);
   md_segs.clear();
   md_keep.id[0] = md_keep.id[1] = ~0ull;
@@ -365,6 +445,33 @@ biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, b
     if (s == BIODB_OK && (cudaEventCreate(&o.computed) != cudaSuccess || cudaEventCreate(&o.done) != cudaSuccess)) s = BIODB_ERR_CUDA;
   if (s != BIODB_OK) { delete pl; return s; }
   *out = pl;
+  return BIODB_OK;
+}
+
+// makePileup(bam[ref][beg .. end), ...) (examples/read_bam_file.d:22-25): the pileup of the reads that overlap a region,
+// fetched through the BAI index.  read_idx counts the reads of the region (the order biodb_reads_begin_region yields).
+biodb_status biodb_pileup_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
+                                       const biodb_pileup_params* prm, biodb_pileup** out) {
+  if (!r || !ix || !out || beg >= end) return BIODB_ERR_ARG;
+  std::vector<VoChunk> c;
+  if (biodb_index_region_chunks(ix, ref_id, beg, end, &c) != BIODB_OK) return BIODB_ERR_ARG;
+  biodb_status s = biodb_pileup_begin(r, prm, out);
+  if (s != BIODB_OK) return s;
+  biodb_pileup* pl = *out;
+  pl->region = true;
+  pl->chunks.swap(c);
+  pl->chunk_i = 0;
+  pl->reg_ref = ref_id;
+  pl->reg_beg = beg;
+  pl->reg_end = end;
+  if (pl->chunks.empty()) {
+    pl->done = true;                                        // no chunk can hold a read of the region
+  } else {
+    const VoChunk& ch = pl->chunks[0];
+    pl->pass.rewind(ch.beg >> 16, (uint32_t)(ch.beg & 0xFFFF));
+    pl->pass.stop_coffset = ch.end >> 16;
+    pl->pass.stop_uoffset = (uint32_t)(ch.end & 0xFFFF);
+  }
   return BIODB_OK;
 }
 
@@ -476,7 +583,7 @@ void biodb_pileup_stats(const biodb_pileup* pl, biodb_stats* out) {
 int32_t biodb_pileup_ref_id(const biodb_pileup* pl) { return pl ? pl->target_ref : -1; }
 void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* n_columns, uint64_t* n_entries) {
   if (!pl) return;
-  if (n_records) *n_records = pl->pass.n_records_total;
+  if (n_records) *n_records = pl->region ? pl->region_index : pl->pass.n_records_total;
   if (n_columns) *n_columns = pl->tot_cols;
   if (n_entries) *n_entries = pl->tot_entries;
 }
@@ -535,7 +642,9 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     if (pl->done) return BIODB_EOF;
     if (!pl->have_batch || pl->gi + 1 >= pl->bounds.size()) {
       pl->have_batch = false;
-      if (p.finished && (pl->carry[pl->cur].n == 0 || p.pending.status != 0)) {
+      // (region mode: a finished pass is only the end of a chunk while further chunks wait)
+      const bool more_chunks = pl->region && !pl->region_done && !p.pending.status && pl->chunk_i + 1 < pl->chunks.size();
+      if (p.finished && !more_chunks && (pl->carry[pl->cur].n == 0 || p.pending.status != 0)) {
         biodb_status s = p.next(1, 0);          // raises the pending error, or EOF
         if (s == BIODB_EOF) pl->done = true;
         return s;

@@ -991,6 +991,27 @@ int64_t biodb_index_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg,
   return (int64_t)c.size();
 }
 
+}  // extern "C"
+
+// The stretches of the file a region read goes through: getChunks, then StreamChunksSupplier.moveToNextChunk
+// (inputstream.d:262-277): chunks that begin in the same BGZF block are read as one stretch, from the first one's
+// start to the last one's end.
+biodb_status biodb_index_region_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
+                                       std::vector<biodb::VoChunk>* out) {
+  std::vector<VoChunk> c;
+  out->clear();
+  if (!ix || !ix->bai.region_chunks(ref_id, beg, end, &c)) return BIODB_ERR_ARG;
+  for (size_t k = 0; k < c.size();) {
+    size_t i = k + 1;
+    while (i < c.size() && (c[i].beg >> 16) <= (c[k].beg >> 16)) ++i;
+    out->push_back(VoChunk{c[k].beg, c[i - 1].end});
+    k = i;
+  }
+  return BIODB_OK;
+}
+
+extern "C" {
+
 biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
                                       biodb_reads** out) {
   if (!r || !ix || !out) return BIODB_ERR_ARG;
@@ -999,20 +1020,10 @@ biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, ui
     set_error(&r->err, BIODB_ERR_ARG, 0, 0, "start must be less than end");
     return BIODB_ERR_ARG;
   }
-  if (!ix->bai.region_chunks(ref_id, beg, end, &c)) {      // randomaccessmanager.d:206-208
+  if (biodb_index_region_chunks(ix, ref_id, beg, end, &c) != BIODB_OK) {      // randomaccessmanager.d:206-208
     set_error(&r->err, BIODB_ERR_ARG, 0, 0, "Invalid reference sequence index");
     return BIODB_ERR_ARG;
   }
-  // StreamChunksSupplier.moveToNextChunk (inputstream.d:262-277): chunks that begin in the same BGZF block are read
-  // as one stretch, from the first one's start to the last one's end
-  std::vector<VoChunk> merged;
-  for (size_t k = 0; k < c.size();) {
-    size_t i = k + 1;
-    while (i < c.size() && (c[i].beg >> 16) <= (c[k].beg >> 16)) ++i;
-    merged.push_back(VoChunk{c[k].beg, c[i - 1].end});
-    k = i;
-  }
-  c.swap(merged);
   biodb_status s = biodb_reads_begin(r, out);
   if (s != BIODB_OK) return s;
   biodb_reads* it = *out;

@@ -75,6 +75,12 @@ struct biodb_reader {
   biodb_status build_block_index();
 };
 
+namespace biodb { struct VoChunk; }
+struct biodb_index;
+// chunk list of a region read (defined in runtime.cu next to biodb_index)
+biodb_status biodb_index_region_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
+                                       std::vector<biodb::VoChunk>* out);
+
 namespace biodb {
 
 // One sequential pass over the BGZF blocks of a reader: owns a CUDA stream and all buffers.

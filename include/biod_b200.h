@@ -234,6 +234,13 @@ typedef struct biodb_shard_info {
 biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* p, uint32_t shard, uint32_t n_shards,
                                       uint32_t halo_blocks, biodb_pileup** out);
 void biodb_pileup_shard_info(const biodb_pileup* pl, biodb_shard_info* out);
+/* makePileup(bam[ref][beg .. end), use_md_tag, start_from, end_at, skip_zero_coverage) — "any range of reads is
+ * acceptable" (examples/read_bam_file.d:22-25, transverse_multiple_bam_files.d:15): the pileup of the reads of
+ * reference ref_id that overlap [beg, end), fetched through the BAI index (biodb_reads_begin_region's reads, reduced on
+ * the device before the pileup kernels see the batch).  read_idx counts the reads of the region, in the order
+ * biodb_reads_begin_region yields them.  BIODB_ERR_ARG: beg >= end or invalid reference index. */
+biodb_status biodb_pileup_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
+                                       const biodb_pileup_params* p, biodb_pileup** out);
 biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols);
 void biodb_pileup_end(biodb_pileup* pl);
 /* Reference id of the pileup (AbstractPileup.ref_id, pileup.d:455-457); valid after the first _next. */

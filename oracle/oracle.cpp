@@ -778,7 +778,8 @@ struct PileupSim {
 // makePileup / pileupInstance (pileup.d:480-507, 683-694) when single_ref != 0,
 // pileupColumns (pileup.d:509-519) otherwise.
 Pileup* run_pileup(const Bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero,
-                   int64_t rec_begin, int64_t rec_end, int use_md = 0) {
+                   int64_t rec_begin, int64_t rec_end, int use_md = 0, const int64_t* rec_list = nullptr,
+                   uint64_t n_list = 0) {
   Pileup* out = new Pileup;
   out->col_off.push_back(0);
   PileupSim sim;
@@ -789,6 +790,13 @@ Pileup* run_pileup(const Bam* s, int single_ref, uint64_t start_from, uint64_t e
   int64_t n = (int64_t)s->rec_off.size();
   if (rec_end < 0 || rec_end > n) rec_end = n;
   if (rec_begin < 0) rec_begin = 0;
+  if (rec_list) {
+    // the reads of an arbitrary range (e.g. bam[ref][beg .. end), examples/read_bam_file.d:22-25), given by index
+    for (uint64_t k = 0; k < n_list; ++k) {
+      const int64_t r = rec_list[k];
+      if (r >= 0 && r < n && s->end_pos[r] - s->pos[r] > 0) sim.reads.push_back((uint32_t)r);
+    }
+  } else
   for (int64_t r = rec_begin; r < rec_end; ++r)
     if (s->end_pos[r] - s->pos[r] > 0) sim.reads.push_back((uint32_t)r);   // filter basesCovered()>0 (:481,:510)
   if (single_ref) {
@@ -1097,6 +1105,13 @@ orc_pileup* orc_pileup_run_range(orc_bam* s, int single_ref, uint64_t start_from
                                  int64_t rec_begin, int64_t rec_end) {
   decode_records(s);
   return run_pileup(s, single_ref, start_from, end_at, skip_zero, rec_begin, rec_end);
+}
+// pileup over the reads whose record indices are listed (any range of reads is acceptable to makePileup:
+// examples/read_bam_file.d:22-25 feeds it bam["chr2"][150 .. 160])
+orc_pileup* orc_pileup_run_list(orc_bam* s, const int64_t* rec_list, uint64_t n_list, int single_ref, uint64_t start_from,
+                                uint64_t end_at, int skip_zero, int use_md) {
+  decode_records(s);
+  return run_pileup(s, single_ref, start_from, end_at, skip_zero, 0, -1, use_md, rec_list, n_list);
 }
 // the same with use_md_tag = true: every column also gets its reference_base (pileup.d:522-654)
 orc_pileup* orc_pileup_run_md(orc_bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero) {

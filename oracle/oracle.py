@@ -60,6 +60,8 @@ def lib():
         L.orc_pileup_run_md.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int]
         L.orc_dna_of_read.restype = u64
         L.orc_dna_of_read.argtypes = [C.c_void_p, u64, C.c_char_p, u64]
+        L.orc_pileup_run_list.restype = C.c_void_p
+        L.orc_pileup_run_list.argtypes = [C.c_void_p, C.c_void_p, u64, C.c_int, u64, u64, C.c_int, C.c_int]
         L.orc_pileup_run_range.restype = C.c_void_p
         L.orc_pileup_run_range.argtypes = [C.c_void_p, C.c_int, u64, u64, C.c_int, C.c_int64, C.c_int64]
         L.orc_pileup_free.argtypes = [C.c_void_p]
@@ -256,6 +258,13 @@ class Bam:
     def pileup_columns(self, skip_zero_coverage=True, use_md_tag=False):
         run = self._L.orc_pileup_run_md if use_md_tag else self._L.orc_pileup_run
         return Pileup(self._L, run(self._h, 0, 0, 2**64 - 1, int(skip_zero_coverage)))
+
+    def make_pileup_of(self, indices, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True, use_md_tag=False,
+                       single_ref=True):
+        """makePileup over the reads with the given record indices (any range of reads: examples/read_bam_file.d:22-25)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        return Pileup(self._L, self._L.orc_pileup_run_list(self._h, idx.ctypes.data, len(idx), int(single_ref), start_from,
+                                                           end_at, int(skip_zero_coverage), int(use_md_tag)))
 
     def dna(self, i):
         """dna(read) of record i: reference bases over its aligned and deleted positions (md/reconstruct.d:38-214)."""

@@ -137,3 +137,77 @@ def test_reads_between_and_read_at():
     rd = BamReader(data, want_offsets=True, index=fixture_bytes("bins.bam.bai"))
     for name in ("tiny", "small", "large"):
         assert rd.getReadAt(rd[name].startVirtualOffset()).name == f"{name}:r1:0..1:len1:bin4681:hexbin0x1249"
+
+
+def check_region_pileup(rd, o, bai, ref, beg, end, **kw):
+    """makePileup(bam[ref][beg .. end), ...) on the GPU against the oracle's pileup of the same reads."""
+    from gpu_util import assert_pileup_equal
+    idx = orc.region_reads(o, bai, ref, beg, end)[0]
+    okw = dict(start_from=kw.get("start_from", 0), end_at=kw.get("end_at", 2**64 - 1),
+               skip_zero_coverage=kw.get("skip_zero_coverage", True), use_md_tag=kw.get("use_md_tag", False))
+    want = o.make_pileup_of(idx, **okw)
+    assert want.status == 0
+    g = dict(col_pos=[], col_ref=[], cov=[], n_start=[], read_idx=[], base=[], qual=[], qoff=[], ref_base=[])
+    for b in rd.column_batches(True, want_query_offset=True, copy=True, region=(ref, beg, end), **kw):
+        g["col_pos"].append(b.position)
+        g["col_ref"].append(np.full(b.n_columns, b.ref_id, dtype=np.int32))
+        g["cov"].append(np.diff(b.col_off).astype(np.uint64))
+        g["n_start"].append(b.n_starting_here)
+        g["read_idx"].append(b.read_idx)
+        g["base"].append(b.base)
+        g["qual"].append(b.qual)
+        g["qoff"].append(b.query_offset)
+        if b.reference_base is not None:
+            g["ref_base"].append(b.reference_base)
+    dts = dict(col_pos=np.uint64, col_ref=np.int32, cov=np.uint64, n_start=np.uint32, read_idx=np.uint32, base=np.uint8,
+               qual=np.uint8, qoff=np.uint32, ref_base=np.uint8)
+    g = {k: (np.concatenate(v) if v else np.zeros(0, dtype=dts[k])) for k, v in g.items()}
+    g["col_off"] = np.concatenate([[0], np.cumsum(g["cov"])]).astype(np.uint64)
+    # read_idx counts the reads of the region: map it to the record index of the whole file the oracle reports
+    g["read_idx"] = idx[g["read_idx"].astype(np.int64)].astype(np.uint32) if len(g["read_idx"]) else g["read_idx"]
+    assert_pileup_equal(g, want)
+    if kw.get("use_md_tag"):
+        assert g["ref_base"].tobytes() == np.asarray(want.ref_base, dtype=np.uint8).tobytes()
+    return want.n_columns
+
+
+def test_region_pileup_example():
+    # examples/read_bam_file.d:21-25: makePileup(bam["chr2"][150 .. 160], false, 155, 158)
+    from biod_b200 import BamReader, makePileup
+    data = fixture_bytes("ex1_header.bam")
+    raw = fixture_bytes("ex1_header.bam.bai")
+    o = orc.Bam(data).decode()
+    bai = orc.Bai(raw)
+    rd = BamReader(data, index=raw)
+    chr2 = o.ref_names.index("chr2")
+    assert check_region_pileup(rd, o, bai, chr2, 150, 160, start_from=155, end_at=158) == 3
+    cols = list(makePileup(rd["chr2"][150:160], start_from=155, end_at=158))
+    assert [c.position for c in cols] == [155, 156, 157] and [c.coverage for c in cols] == [11, 10, 8]
+    rng = np.random.default_rng(12)
+    for bpb in (0, 1):
+        rd = BamReader(data, blocks_per_batch=bpb, index=raw)
+        for r in range(2):
+            ln = o.ref_lens[r]
+            for beg, end in [(0, ln), (100, 101)] + [tuple(sorted(int(x) for x in rng.integers(0, ln, 2))) for _ in range(6)]:
+                if beg < end:
+                    check_region_pileup(rd, o, bai, r, beg, end)
+                    check_region_pileup(rd, o, bai, r, beg, end, start_from=beg, end_at=end, skip_zero_coverage=False)
+
+
+def test_region_pileup_across_chunks_and_batches():
+    from biod_b200 import BamReader
+    from test_md_chain import random_pileup
+    data = random_pileup(np.random.default_rng(33), 3000, refs=2, block_size=1500)
+    o = orc.Bam(data).decode()
+    raw = build_bai(o)
+    bai = orc.Bai(raw)
+    rng = np.random.default_rng(2)
+    total = 0
+    for bpb in (0, 1, 2):
+        rd = BamReader(data, blocks_per_batch=bpb, index=raw)
+        for r in range(2):
+            for beg, end in [(0, 100000), (3000, 3001)] + [tuple(sorted(int(x) for x in rng.integers(0, 14000, 2))) for _ in range(5)]:
+                if beg < end:
+                    total += check_region_pileup(rd, o, bai, r, beg, end)
+                    total += check_region_pileup(rd, o, bai, r, beg, end, use_md_tag=True, skip_zero_coverage=False)
+    assert total > 0
