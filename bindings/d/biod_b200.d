@@ -83,6 +83,9 @@ extern (C) nothrow @nogc {
     int biodb_index_n_refs(const(biodb_index)*);
     long biodb_index_chunks(const(biodb_index)*, uint ref_id, uint beg, uint end, ulong* out2, ulong cap);
     int biodb_reads_begin_region(biodb_reader*, const(biodb_index)*, uint ref_id, uint beg, uint end, biodb_reads**);
+    int biodb_reads_begin_between(biodb_reader*, ulong from_voffset, ulong to_voffset, uint max_blocks, biodb_reads**);
+    int biodb_pileup_begin_region(biodb_reader*, const(biodb_index)*, uint ref_id, uint beg, uint end,
+                                  const(biodb_pileup_params)*, biodb_pileup**);
 }
 
 /// Maps a status + error record to the exception classes BioD's tests pin (test/unittests.d:132-142).
@@ -161,6 +164,8 @@ struct GpuReferenceSequence {
         return GpuBamReadRange!true(_bam.handle, _bam, _bam.index, cast(uint)_ref_id, start, end);
     }
     auto opSlice() { return opSlice(0, length); }
+    /// the same region as a value makePileup accepts (a D range cannot be told apart from any other range of reads)
+    GpuRegion region(uint start, uint end) { enforce(start < end, "start must be less than end"); return GpuRegion(_bam, cast(uint)_ref_id, start, end); }
     VirtualOffset startVirtualOffset() { auto r = opSlice(); enforce(!r.empty); return r.front.start_virtual_offset; }
     int firstPosition() { auto r = opSlice(); return r.empty ? -1 : r.front.read.position; }
 }
@@ -279,6 +284,16 @@ struct GpuPileup {
         if (biodb_pileup_begin(h, &prm, &_p) != BIODB_OK) raise(biodb_last_error(h));
         fetch();
     }
+    /// the pileup of the reads of a region: makePileup(bam["chr2"][150 .. 160], ...) (examples/read_bam_file.d:21-25)
+    this(biodb_reader* h, const(biodb_index)* ix, uint ref_id, uint beg, uint end, bool use_md_tag, ulong start_from,
+         ulong end_at, bool skip_zero_coverage, bool compact = true) {
+        _h = h;
+        biodb_pileup_params prm;
+        prm.single_ref = true; prm.skip_zero_coverage = skip_zero_coverage; prm.use_md_tag = use_md_tag;
+        prm.start_from = start_from; prm.end_at = end_at; prm.compact_reads = compact;
+        if (biodb_pileup_begin_region(h, ix, ref_id, beg, end, &prm, &_p) != BIODB_OK) raise(biodb_last_error(h));
+        fetch();
+    }
     ~this() { if (_p !is null) { biodb_pileup_end(_p); _p = null; } }
     @disable this(this);
     bool empty() @property const { return _empty; }
@@ -322,6 +337,12 @@ struct GpuPileup {
 auto makePileup(GpuBamReader bam, bool use_md_tag = false, ulong start_from = 0, ulong end_at = ulong.max,
                 bool skip_zero_coverage = true) {
     return GpuPileup(bam.handle, true, use_md_tag, start_from, end_at, skip_zero_coverage);
+}
+/// makePileup over a region's reads: `makePileup(bam["chr2"].region(150, 160), false, 155, 158)`
+struct GpuRegion { GpuBamReader bam; uint ref_id, start, end; }
+auto makePileup(GpuRegion r, bool use_md_tag = false, ulong start_from = 0, ulong end_at = ulong.max,
+                bool skip_zero_coverage = true) {
+    return GpuPileup(r.bam.handle, r.bam.index, r.ref_id, r.start, r.end, use_md_tag, start_from, end_at, skip_zero_coverage);
 }
 auto pileupColumns(GpuBamReader bam, bool use_md_tag = false, bool skip_zero_coverage = true) {
     return GpuPileup(bam.handle, false, use_md_tag, 0, ulong.max, skip_zero_coverage);
