@@ -131,6 +131,8 @@ def lib():
     L.biodb_index_n_refs.argtypes = [vp]
     L.biodb_index_chunks.restype = C.c_int64
     L.biodb_index_chunks.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64]
+    L.biodb_index_last_linear_offset.restype = C.c_int32
+    L.biodb_index_last_linear_offset.argtypes = [vp, C.c_int32, u64p]
     L.biodb_reads_begin_region.restype = C.c_int
     L.biodb_reads_begin_region.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.biodb_pileup_begin_region.restype = C.c_int
@@ -154,6 +156,6 @@ EXPORTS = [
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
-    "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks",
+    "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region",
 ]

@@ -385,6 +385,38 @@ class BamReader:
             return r
         raise ReadException("not enough data in stream")
 
+    BGZF_EOF = bytes([31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+
+    def eofVirtualOffset(self):
+        """reader.d:177-179, randomaccessmanager.d:113-137: the start of the EOF block if the file ends with one, else the
+        physical end of the file."""
+        if self.filename is None:
+            size, tail = int(self._buf.size), bytes(self._buf[-28:])
+        else:
+            size = os.path.getsize(self.filename)
+            with open(self.filename, "rb") as f:
+                f.seek(max(0, size - 28))
+                tail = f.read()
+        return ((size - 28) << 16) if tail == self.BGZF_EOF else (size << 16)
+
+    def unmappedReads(self):
+        """reader.d:369-390: the reads at the end of a coordinate-sorted, indexed file whose reference id is -1."""
+        bai = self._bai()
+        start = self.eofVirtualOffset()
+        try:
+            if self.getReadAt(self.reads_start_voffset).ref_id == -1:
+                start = self.reads_start_voffset
+        except ReadException:
+            pass                                                                # no reads at all
+        off = C.c_uint64()
+        if self._L.biodb_index_last_linear_offset(bai._h, len(self.reference_sequences), C.byref(off)):
+            start = int(off.value)
+        started = False
+        for r in self.getReadsBetween(start, None):
+            if started or r.ref_id == -1:
+                started = True
+                yield r
+
     def region_reads(self, ref_id, start, end):
         for batch in self.region_batches(ref_id, start, end, copy=True):
             for i in range(batch.n):

@@ -983,6 +983,14 @@ biodb_status biodb_index_open(const void* bai, size_t len, biodb_index** out) {
 }
 void biodb_index_close(biodb_index* ix) { delete ix; }
 int32_t biodb_index_n_refs(const biodb_index* ix) { return ix ? (int32_t)ix->bai.refs.size() : 0; }
+int32_t biodb_index_last_linear_offset(const biodb_index* ix, int32_t n_refs, uint64_t* out) {
+  // reader.d:380-383: the last entry of the last non-empty linear index among references [0, n_refs)
+  if (!ix || !out) return 0;
+  const int32_t n = std::min<int32_t>(n_refs, (int32_t)ix->bai.refs.size());
+  for (int32_t r = n - 1; r >= 0; --r)
+    if (!ix->bai.refs[(size_t)r].ioffsets.empty()) { *out = ix->bai.refs[(size_t)r].ioffsets.back(); return 1; }
+  return 0;
+}
 int64_t biodb_index_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end, uint64_t* out2, uint64_t cap) {
   if (!ix) return -1;
   std::vector<VoChunk> c;

@@ -134,6 +134,9 @@ int32_t biodb_index_n_refs(const biodb_index* ix);
  * every read overlapping [beg, end) of reference ref_id.  Writes at most cap pairs into out2 (may be NULL), returns
  * their number, -1 for an invalid reference index. */
 int64_t biodb_index_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end, uint64_t* out2, uint64_t cap);
+/* The last entry of the last non-empty linear index among references [0, n_refs): where BamReader.unmappedReads starts
+ * looking for the reads without a reference (reader.d:369-390).  Returns 1 and writes *out, or 0 if there is none. */
+int32_t biodb_index_last_linear_offset(const biodb_index* ix, int32_t n_refs, uint64_t* out);
 /* ReferenceSequence.opSlice(beg, end) = RandomAccessManager.getReads(BamRegion) (reference.d:76-81,
  * randomaccessmanager.d:300-305): an iterator over the reads of reference ref_id that overlap [beg, end) — the chunks
  * are inflated and scanned like any other stretch of the file, then filtered on the device (BamReadFilter, :366-462).

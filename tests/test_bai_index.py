@@ -67,3 +67,32 @@ def test_parse_errors():
         BaiFile(good[:len(good) // 2])
     with pytest.raises(ReadException):
         BaiFile(good[:6])
+
+
+def test_last_linear_offset():
+    # reader.d:380-383 (what unmappedReads starts from): the last entry of the last non-empty linear index
+    import ctypes as C
+    import struct
+    from biod_b200 import BaiFile, _capi
+    L = _capi.lib()
+    for name in ("bins.bam.bai", "ex1_header.bam.bai", "tags.bam.bai"):
+        raw = fixture_bytes(name)
+        # a plain walk of the file format (SAM spec 5.2)
+        o, n_ref = 8, struct.unpack_from("<i", raw, 4)[0]
+        last = []
+        for _ in range(n_ref):
+            n_bin = struct.unpack_from("<i", raw, o)[0]
+            o += 4
+            for _ in range(n_bin):
+                n_chunk = struct.unpack_from("<i", raw, o + 4)[0]
+                o += 8 + 16 * n_chunk
+            n_intv = struct.unpack_from("<i", raw, o)[0]
+            o += 4
+            last.append(struct.unpack_from("<Q", raw, o + 8 * (n_intv - 1))[0] if n_intv else None)
+            o += 8 * n_intv
+        ix = BaiFile(raw)
+        for n in range(n_ref + 2):
+            want = next((v for v in reversed(last[:n]) if v is not None), None)
+            out = C.c_uint64()
+            got = L.biodb_index_last_linear_offset(ix._h, n, C.byref(out))
+            assert (int(out.value) if got else None) == want, (name, n)

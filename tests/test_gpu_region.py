@@ -211,3 +211,21 @@ def test_region_pileup_across_chunks_and_batches():
                     total += check_region_pileup(rd, o, bai, r, beg, end)
                     total += check_region_pileup(rd, o, bai, r, beg, end, use_md_tag=True, skip_zero_coverage=False)
     assert total > 0
+
+
+def test_unmapped_reads_and_eof_offset():
+    # reader.d:369-390 (unmappedReads), :177-179 (eofVirtualOffset)
+    from biod_b200 import BamReader
+    data = fixture_bytes("bins.bam")
+    o = orc.Bam(data).decode()
+    rd = BamReader(data, want_offsets=True, index=fixture_bytes("bins.bam.bai"))
+    assert rd.eofVirtualOffset() == (len(data) - 28) << 16 == int(o.end_vo[-1])
+    want = [i for i in range(o.n_records) if o.ref_id[i] == -1]
+    assert want and want == list(range(want[0], o.n_records))        # they sit at the end of the file
+    got = list(rd.unmappedReads())
+    assert [r.raw.tobytes() for r in got] == [o.record_bytes(i).tobytes() for i in want]
+    assert [r.start_virtual_offset for r in got] == o.start_vo[want].tolist()
+    # a file without unmapped reads
+    data = fixture_bytes("ex1_header.bam")
+    rd = BamReader(data, want_offsets=True, index=fixture_bytes("ex1_header.bam.bai"))
+    assert list(rd.unmappedReads()) == []
