@@ -139,6 +139,12 @@ def lib():
     L.biodb_pileup_begin_region.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(PileupParams), C.POINTER(vp)]
     L.biodb_reads_begin_between.restype = C.c_int
     L.biodb_reads_begin_between.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(vp)]
+    L.biodb_bgzf_compress_bound.restype = C.c_size_t
+    L.biodb_bgzf_compress_bound.argtypes = [C.c_size_t]
+    L.biodb_bgzf_compress.restype = C.c_int
+    L.biodb_bgzf_compress.argtypes = [C.c_int32, vp, C.c_size_t, C.c_int32, C.c_int32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.biodb_debug_deflate_block.restype = C.c_int64
+    L.biodb_debug_deflate_block.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_int32]
     L.biodb_debug_md_dna.restype = C.c_int64
     L.biodb_debug_md_dna.argtypes = [vp, C.c_int64, vp, C.c_uint64]
     L.biodb_dev_scan_workspace_bytes.restype = C.c_size_t
@@ -157,5 +163,6 @@ EXPORTS = [
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
     "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset",
-    "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region",
+    "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",
+    "biodb_debug_deflate_block",
 ]

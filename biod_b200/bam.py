@@ -660,3 +660,52 @@ def makePileup(reader, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_ze
 def pileupColumns(reader, use_md_tag=False, skip_zero_coverage=True):
     """bam/pileup.d:509-519"""
     return _columns(reader, False, use_md_tag=use_md_tag, skip_zero_coverage=skip_zero_coverage)
+
+
+# ---- BGZF compression (bgzf/compress.d, bgzf/outputstream.d) --------------------------------------------------------
+def bgzf_compress(data, level=-1, eof=True, device=-1):
+    """The BGZF stream of `data`: one block per 0xFF00 bytes (outputstream.d:50-223), each compressed on the GPU the way
+    bgzfCompress frames it (compress.d:43-103), plus the EOF block of close() when eof is true."""
+    L = capi.lib()
+    if not -1 <= level <= 9:
+        raise ValueError("level must be within -1 .. 9")                         # compress.d:46-48
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    cap = int(L.biodb_bgzf_compress_bound(buf.size))
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_size_t()
+    st = L.biodb_bgzf_compress(device, buf.ctypes.data if buf.size else None, buf.size, level, int(eof), out.ctypes.data, cap,
+                               C.byref(n))
+    if st == capi.ERR_CUDA:
+        raise CudaUnavailable("biodb_bgzf_compress needs a CUDA device: biod_b200 has no CPU fallback")
+    if st != capi.OK:
+        raise RuntimeError(f"biodb_bgzf_compress: status {st}")
+    return out[:n.value].tobytes()
+
+
+class BgzfOutputStream:
+    """bgzf/outputstream.d:50-223 over a file-like sink: bytes written are cut into BGZF blocks and compressed on the
+    GPU at flush() / close(); close() appends the EOF block (:218-221)."""
+
+    def __init__(self, sink, compression_level=-1):
+        self._sink, self._level, self._buf, self._open = sink, compression_level, bytearray(), True
+
+    def write(self, data):
+        assert self._open, "stream is closed"
+        self._buf += data
+        return len(data)
+
+    writeExact = write
+
+    def flush(self):
+        if self._buf:
+            self._sink.write(bgzf_compress(self._buf, self._level, eof=False))
+            self._buf = bytearray()
+
+    def addEofBlock(self):
+        self._sink.write(bytes(BamReader.BGZF_EOF))
+
+    def close(self):
+        if self._open:
+            self.flush()
+            self.addEofBlock()
+            self._open = False

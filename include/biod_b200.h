@@ -251,6 +251,21 @@ int32_t biodb_pileup_ref_id(const biodb_pileup* pl);
 /* Totals over the whole pass so far (for benches and checks). */
 void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* n_columns, uint64_t* n_entries);
 
+/* ---- BGZF compression (first part) -------------------------------------------------- */
+/* bgzfCompress (bio/core/bgzf/compress.d:43-103) over a whole buffer, cut like BgzfOutputStream does
+ * (bgzf/outputstream.d:50-223): one BGZF block per 0xFF00 bytes, compressed on the device, plus the 28-byte EOF block
+ * when add_eof != 0 (close(), :218-221).  level: -1..9 as for zlib; 0 stores, every other value selects the one
+ * effort this encoder has (greedy LZ77, fixed Huffman codes).  The compressed bytes are valid DEFLATE but not zlib's —
+ * the reference asks for the round trip only (outputstream.d:225-247).  device < 0: the current device.
+ * BIODB_ERR_NOMEM when cap < what is needed (biodb_bgzf_compress_bound(len) always suffices); BIODB_ERR_CUDA without
+ * a device (no CPU fallback). */
+size_t biodb_bgzf_compress_bound(size_t len);
+biodb_status biodb_bgzf_compress(int32_t device, const void* data, size_t len, int32_t level, int32_t add_eof, void* out,
+                                 size_t cap, size_t* out_len);
+/* Host-only test hook: the device's DEFLATE encoder (csrc/deflate_enc.h) compiled for the CPU; raw DEFLATE of one
+ * chunk of at most 65535 bytes.  Returns the size, 0 if cap is too small. */
+int64_t biodb_debug_deflate_block(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, int32_t level);
+
 /* ---- measurement ---------------------------------------------------------------------------------------- */
 typedef struct biodb_stats {
   double total_ms;        /* CUDA-event time from the first to the last operation of the pass, on its stream */
