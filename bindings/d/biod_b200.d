@@ -86,6 +86,20 @@ extern (C) nothrow @nogc {
     int biodb_reads_begin_between(biodb_reader*, ulong from_voffset, ulong to_voffset, uint max_blocks, biodb_reads**);
     int biodb_pileup_begin_region(biodb_reader*, const(biodb_index)*, uint ref_id, uint beg, uint end,
                                   const(biodb_pileup_params)*, biodb_pileup**);
+    // BGZF compression (row N4, first part)
+    size_t biodb_bgzf_compress_bound(size_t len);
+    int biodb_bgzf_compress(int device, const(void)* data, size_t len, int level, int add_eof, void* out_, size_t cap,
+                            size_t* out_len);
+}
+
+/// The BGZF stream of `data` (bgzf/outputstream.d:50-223 over a complete buffer): blocks of 0xFF00 bytes compressed on
+/// the GPU and framed like bgzfCompress frames them (bgzf/compress.d:43-103), plus the EOF block when `eof`.
+ubyte[] gpuBgzfCompress(const(ubyte)[] data, int level = -1, bool eof = true) {
+    auto buf = new ubyte[biodb_bgzf_compress_bound(data.length)];
+    size_t n;
+    auto st = biodb_bgzf_compress(-1, data.ptr, data.length, level, eof, buf.ptr, buf.length, &n);
+    enforce(st == BIODB_OK, "biodb_bgzf_compress failed");
+    return buf[0 .. n];
 }
 
 /// Maps a status + error record to the exception classes BioD's tests pin (test/unittests.d:132-142).

@@ -248,3 +248,33 @@ def test_dna_walk_tag_areas():
     recs.append(bam_record("star", "", "6M", 40, tags=b"MDZ6\0"))                    # SEQ '*' with a CIGAR
     recs.append(bam_record("long", "ACGTACGTAC", "10M", 41, tags=b"MDZ4^ACGT6A20\0"))   # MD longer than the read
     assert check_dna(make_bam([("c0", 100000)], recs)) > 0
+
+
+def test_admit_many_equals_admit_on_large_inputs():
+    """The tight loop of admit_many against the read-by-read path on 200 k reads per shape: identical segment lists."""
+    from biod_b200 import _capi
+    L = _capi.lib()
+    rng = np.random.default_rng(77)
+    shapes = [dict(p=0.2, span=(150, 151), slack=(0, 1)),            # the benchmark's shape: 150M, 30x
+              dict(p=0.5, span=(20, 400), slack=(-30, 30)),          # ragged spans, dna() longer / shorter than the span
+              dict(p=0.02, span=(5, 60), slack=(-5, 1)),             # sparse: islands and zero-coverage gaps
+              dict(p=0.9, span=(1, 3000), slack=(0, 1))]             # long N-skip-like spans over many short reads
+    for sh in shapes:
+        n = 200_000
+        ref = np.sort(rng.integers(0, 3, n)).astype(np.int32)
+        pos = np.zeros(n, dtype=np.int64)
+        for r in range(3):
+            m = ref == r
+            pos[m] = np.cumsum(rng.geometric(sh["p"], int(m.sum())) - 1)
+        span = rng.integers(*sh["span"], n)
+        end = pos + span
+        ln = np.maximum(0, span + rng.integers(*sh["slack"], n)).astype(np.int64)
+        for skip in (1, 0):
+            res = []
+            for batch in (0, 10**9):
+                seg = np.zeros(4 * (4 * n + 64), dtype=np.int64)
+                k = L.biodb_debug_md_chain(ref.ctypes.data, pos.ctypes.data, end.ctypes.data, ln.ctypes.data, n, skip, batch,
+                                           seg.ctypes.data, len(seg) // 4)
+                assert 0 < k <= len(seg) // 4
+                res.append(seg[:4 * k].reshape(k, 4))
+            assert np.array_equal(res[0], res[1]), (sh, skip)
