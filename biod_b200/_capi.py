@@ -143,6 +143,21 @@ def lib():
     L.biodb_bgzf_compress_bound.argtypes = [C.c_size_t]
     L.biodb_bgzf_compress.restype = C.c_int
     L.biodb_bgzf_compress.argtypes = [C.c_int32, vp, C.c_size_t, C.c_int32, C.c_int32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.biodb_writer_begin.restype = C.c_int
+    L.biodb_writer_begin.argtypes = [C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.biodb_writer_header.restype = C.c_int
+    L.biodb_writer_header.argtypes = [vp, C.c_char_p, C.c_size_t, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
+    L.biodb_writer_records.restype = C.c_int
+    L.biodb_writer_records.argtypes = [vp, vp, C.c_size_t]
+    L.biodb_writer_flush.restype = C.c_int
+    L.biodb_writer_flush.argtypes = [vp]
+    L.biodb_writer_finish.restype = C.c_int
+    L.biodb_writer_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.biodb_writer_layout.restype = C.c_int
+    L.biodb_writer_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.biodb_writer_error.restype = C.c_char_p
+    L.biodb_writer_error.argtypes = [vp]
+    L.biodb_writer_end.argtypes = [vp]
     L.biodb_debug_deflate_block.restype = C.c_int64
     L.biodb_debug_deflate_block.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_int32]
     L.biodb_debug_md_dna.restype = C.c_int64
@@ -164,5 +179,6 @@ EXPORTS = [
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
     "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",
-    "biodb_debug_deflate_block",
+    "biodb_debug_deflate_block", "biodb_writer_begin", "biodb_writer_header", "biodb_writer_records", "biodb_writer_flush",
+    "biodb_writer_finish", "biodb_writer_layout", "biodb_writer_error", "biodb_writer_end",
 ]

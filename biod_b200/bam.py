@@ -709,3 +709,78 @@ class BgzfOutputStream:
             self.flush()
             self.addEofBlock()
             self._open = False
+
+
+class BamWriter:
+    """bam/writer.d:67-300 (without the automatic index): collects header and records the way BamWriter lays them out
+    and compresses the BGZF blocks on the GPU at finish().  `sink` is a file-like object or a path."""
+
+    def __init__(self, sink, compression_level=-1, task_pool=None, device=-1):
+        self._L = L = capi.lib()
+        if not -1 <= compression_level <= 9:
+            raise ValueError("compression level must be within -1 .. 9")
+        self._sink = open(sink, "wb") if isinstance(sink, (str, os.PathLike)) else sink
+        self._own = self._sink is not sink
+        h = C.c_void_p()
+        if L.biodb_writer_begin(device, compression_level, C.byref(h)) != capi.OK:
+            raise RuntimeError("biodb_writer_begin failed")
+        self._h = h
+
+    def _check(self, st):
+        if st == capi.ERR_CUDA:
+            raise CudaUnavailable("BamWriter needs a CUDA device: biod_b200 has no CPU fallback")
+        if st != capi.OK:
+            raise Exception(self._L.biodb_writer_error(self._h).decode("latin-1") or f"biod_b200 status {st}")
+
+    def writeSamHeader(self, header_text):
+        self._text = header_text if isinstance(header_text, bytes) else header_text.encode("latin-1")
+
+    def writeReferenceSequenceInfo(self, reference_sequences):
+        """writer.d:151-181; reference_sequences: objects with .name and .length (or (name, length) pairs)."""
+        refs = [(r.name, r.length) if hasattr(r, "name") else r for r in reference_sequences]
+        names = (C.c_char_p * max(1, len(refs)))(*[n.encode("latin-1") for n, _ in refs])
+        lens = (C.c_int32 * max(1, len(refs)))(*[int(l) for _, l in refs])
+        text = getattr(self, "_text", b"")
+        self._check(self._L.biodb_writer_header(self._h, text, len(text), len(refs), names, lens))
+
+    def writeRecord(self, read):
+        """writer.d:244-268; `read` is a BamRead, or the raw bytes of a record (with or without its block_size prefix)."""
+        raw = read.raw.tobytes() if hasattr(read, "raw") else bytes(read)
+        if hasattr(read, "raw") or len(raw) < 4 or int.from_bytes(raw[:4], "little", signed=True) != len(raw) - 4:
+            raw = len(raw).to_bytes(4, "little") + raw
+        self.writeRecords(raw)
+
+    def writeRecords(self, records):
+        """Any number of records, back to back, each with its block_size prefix."""
+        buf = np.frombuffer(bytes(records), dtype=np.uint8)
+        self._check(self._L.biodb_writer_records(self._h, buf.ctypes.data if buf.size else None, buf.size))
+
+    def flush(self):
+        self._check(self._L.biodb_writer_flush(self._h))
+
+    def layout(self):
+        """(uncompressed bytes, block starts) chosen so far — host only."""
+        d, n, c, k = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+        self._check(self._L.biodb_writer_layout(self._h, C.byref(d), C.byref(n), C.byref(c), C.byref(k)))
+        data = C.string_at(d, n.value) if n.value else b""
+        cuts = list(np.frombuffer(C.string_at(c, 8 * k.value), dtype=np.uint64).astype(np.int64))
+        return data, cuts
+
+    def finish(self):
+        d, n = C.c_void_p(), C.c_size_t()
+        self._check(self._L.biodb_writer_finish(self._h, C.byref(d), C.byref(n)))
+        self._sink.write(C.string_at(d, n.value))
+        if self._own:
+            self._sink.close()
+        self.close()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.biodb_writer_end(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -262,6 +262,26 @@ void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* 
 size_t biodb_bgzf_compress_bound(size_t len);
 biodb_status biodb_bgzf_compress(int32_t device, const void* data, size_t len, int32_t level, int32_t add_eof, void* out,
                                  size_t cap, size_t* out_len);
+/* BamWriter (bio/std/hts/bam/writer.d:67-300) over that compressor.  The writer collects the uncompressed stream on the
+ * host exactly as BamWriter + BgzfOutputStream lay it out — "BAM\1", header text, reference table, a block boundary,
+ * then the records, where a record that would not fit into the current block starts a new one (writer.d:259-267) and
+ * a record longer than a block is cut every 0xFF00 bytes (outputstream.d:107-132) — and compresses all blocks on the
+ * device at finish.  The index a BamWriter creates for coordinate-sorted output (bai/indexing.d) is not built.
+ *  _header : writeSamHeader + writeReferenceSequenceInfo (names are NUL-terminated strings); once, before records
+ *  _records: writeRecord for every record of the buffer (block_size prefix + body, back to back); the bin field is
+ *            recalculated (read.d:1028-1030); BIODB_ERR_ARG "Read reference ID is out of range" (writer.d:245-246)
+ *  _flush  : ends the current block;  _finish: the whole file (valid until _end), EOF block included
+ *  _layout : host-only view of the uncompressed bytes and the block starts chosen so far (for tests) */
+typedef struct biodb_writer biodb_writer;
+biodb_status biodb_writer_begin(int32_t device, int32_t level, biodb_writer** out);
+biodb_status biodb_writer_header(biodb_writer* w, const char* text, size_t text_len, int32_t n_refs, const char* const* names,
+                                 const int32_t* lengths);
+biodb_status biodb_writer_records(biodb_writer* w, const uint8_t* records, size_t len);
+biodb_status biodb_writer_flush(biodb_writer* w);
+biodb_status biodb_writer_finish(biodb_writer* w, const uint8_t** data, size_t* len);
+biodb_status biodb_writer_layout(const biodb_writer* w, const uint8_t** data, size_t* len, const uint64_t** cuts, size_t* n_cuts);
+const char* biodb_writer_error(const biodb_writer* w);
+void biodb_writer_end(biodb_writer* w);
 /* Host-only test hook: the device's DEFLATE encoder (csrc/deflate_enc.h) compiled for the CPU; raw DEFLATE of one
  * chunk of at most 65535 bytes.  Returns the size, 0 if cap is too small. */
 int64_t biodb_debug_deflate_block(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, int32_t level);
