@@ -87,6 +87,14 @@ extern (C) nothrow @nogc {
     int biodb_pileup_begin_region(biodb_reader*, const(biodb_index)*, uint ref_id, uint beg, uint end,
                                   const(biodb_pileup_params)*, biodb_pileup**);
     // BGZF compression (row N4, first part)
+    struct biodb_writer;
+    int biodb_writer_begin(int device, int level, biodb_writer**);
+    int biodb_writer_header(biodb_writer*, const(char)* text, size_t text_len, int n_refs, const(char*)* names, const(int)* lengths);
+    int biodb_writer_records(biodb_writer*, const(ubyte)* records, size_t len);
+    int biodb_writer_flush(biodb_writer*);
+    int biodb_writer_finish(biodb_writer*, const(ubyte)** data, size_t* len);
+    const(char)* biodb_writer_error(const(biodb_writer)*);
+    void biodb_writer_end(biodb_writer*);
     size_t biodb_bgzf_compress_bound(size_t len);
     int biodb_bgzf_compress(int device, const(void)* data, size_t len, int level, int add_eof, void* out_, size_t cap,
                             size_t* out_len);
