@@ -27,6 +27,7 @@ namespace {
 constexpr uint32_t BGZF_CHUNK = 0xFF00;       // BGZF_BLOCK_SIZE (bgzf/constants.d:61)
 constexpr uint32_t SLOT = 65536;              // BGZF_MAX_BLOCK_SIZE (:60)
 constexpr uint32_t SLAB_BLOCKS = 4096;        // blocks per round trip to the device (256 MiB of slots)
+constexpr size_t BLOCK_SCRATCH = (DEFL_HASH_SIZE * 2 + sizeof(DeflWork) + 255) & ~(size_t)255;   // per block, in global memory
 
 __global__ void __launch_bounds__(64) deflate_blocks_kernel(const uint8_t* __restrict__ in, uint64_t in_len, uint32_t n_blocks,
                                                             uint8_t* __restrict__ slots, uint64_t* __restrict__ in_off,
@@ -34,10 +35,12 @@ __global__ void __launch_bounds__(64) deflate_blocks_kernel(const uint8_t* __res
                                                             uint16_t* __restrict__ htabs, int level) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
-  uint16_t* htab = htabs + (size_t)b * DEFL_HASH_SIZE;      // 8 KiB of scratch per block (global: L2-resident)
+  // scratch of the block (global memory, L2-resident): the hash table, then the encoder's work area
+  uint16_t* htab = (uint16_t*)((uint8_t*)htabs + (size_t)b * BLOCK_SCRATCH);
+  DeflWork* work = (DeflWork*)(htab + DEFL_HASH_SIZE);
   const uint64_t off = (uint64_t)b * BGZF_CHUNK;
   const uint32_t n = (uint32_t)(in_len - off < BGZF_CHUNK ? in_len - off : BGZF_CHUNK);
-  const uint32_t len = deflate_block(in + off, n, slots + (size_t)b * SLOT + 18, SLOT - 26, htab, level);
+  const uint32_t len = deflate_block(in + off, n, slots + (size_t)b * SLOT + 18, SLOT - 26, htab, level, work);
   in_off[b] = off;
   isize[b] = n;
   total[b] = len + 26;                        // header 18 + payload + footer 8 (compress.d:88)
@@ -51,10 +54,11 @@ __global__ void __launch_bounds__(64) deflate_chunks_kernel(const uint8_t* __res
                                                             uint32_t* __restrict__ total, uint16_t* __restrict__ htabs, int level) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
-  uint16_t* htab = htabs + (size_t)b * DEFL_HASH_SIZE;
+  uint16_t* htab = (uint16_t*)((uint8_t*)htabs + (size_t)b * BLOCK_SCRATCH);
+  DeflWork* work = (DeflWork*)(htab + DEFL_HASH_SIZE);
   const uint64_t off = chunk_off[b] - chunk_off[0];
   const uint32_t n = (uint32_t)(chunk_off[b + 1] - chunk_off[b]);
-  const uint32_t len = deflate_block(in + off, n, slots + (size_t)b * SLOT + 18, SLOT - 26, htab, level);
+  const uint32_t len = deflate_block(in + off, n, slots + (size_t)b * SLOT + 18, SLOT - 26, htab, level, work);
   in_off[b] = off;
   isize[b] = n;
   total[b] = len + 26;
@@ -95,7 +99,8 @@ size_t biodb_bgzf_compress_bound(size_t len) {
 int64_t biodb_debug_deflate_block(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, int32_t level) {
   if ((!in && n) || !out) return -1;
   uint16_t htab[DEFL_HASH_SIZE];
-  return (int64_t)deflate_block(in, n, out, cap, htab, level);
+  DeflWork work;
+  return (int64_t)deflate_block(in, n, out, cap, htab, level, &work);
 }
 
 biodb_status biodb_bgzf_compress(int32_t device, const void* data, size_t len, int32_t level, int32_t add_eof, void* out,
@@ -122,7 +127,7 @@ biodb_status biodb_bgzf_compress(int32_t device, const void* data, size_t len, i
                 d_total.ensure((size_t)(nb + 1) * 4, st) == cudaSuccess && d_crc.ensure((size_t)nb * 4, st) == cudaSuccess &&
                 d_ooff.ensure((size_t)(nb + 1) * 8, st) == cudaSuccess &&
                 d_tmp.ensure((scan_temp_elems(nb + 1) + 8) * 8, st) == cudaSuccess &&
-                d_htab.ensure((size_t)nb * DEFL_HASH_SIZE * 2, st) == cudaSuccess;
+                d_htab.ensure((size_t)nb * BLOCK_SCRATCH, st) == cudaSuccess;
       ok = ok && cudaMemcpyAsync(d_in.p, src + in0, in_len, cudaMemcpyHostToDevice, st) == cudaSuccess;
       if (ok) {
         deflate_blocks_kernel<<<(nb + 63) / 64, 64, 0, st>>>(d_in.as<uint8_t>(), in_len, nb, d_slots.as<uint8_t>(),
@@ -190,7 +195,7 @@ biodb_status compress_chunks(int32_t device, const uint8_t* data, const uint64_t
                 d_isize.ensure((size_t)nb * 4, st) == cudaSuccess && d_total.ensure((size_t)(nb + 1) * 4, st) == cudaSuccess &&
                 d_crc.ensure((size_t)nb * 4, st) == cudaSuccess && d_ooff.ensure((size_t)(nb + 1) * 8, st) == cudaSuccess &&
                 d_tmp.ensure((scan_temp_elems(nb + 1) + 8) * 8, st) == cudaSuccess &&
-                d_htab.ensure((size_t)nb * DEFL_HASH_SIZE * 2, st) == cudaSuccess;
+                d_htab.ensure((size_t)nb * BLOCK_SCRATCH, st) == cudaSuccess;
       ok = ok && cudaMemcpyAsync(d_in.p, data + in0, (size_t)in_len, cudaMemcpyHostToDevice, st) == cudaSuccess &&
            cudaMemcpyAsync(d_coff.p, chunk_off + b0, (size_t)(nb + 1) * 8, cudaMemcpyHostToDevice, st) == cudaSuccess;
       if (ok) {
