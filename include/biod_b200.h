@@ -255,7 +255,7 @@ void biodb_pileup_totals(const biodb_pileup* pl, uint64_t* n_records, uint64_t* 
 /* bgzfCompress (bio/core/bgzf/compress.d:43-103) over a whole buffer, cut like BgzfOutputStream does
  * (bgzf/outputstream.d:50-223): one BGZF block per 0xFF00 bytes, compressed on the device, plus the 28-byte EOF block
  * when add_eof != 0 (close(), :218-221).  level: -1..9 as for zlib; 0 stores, every other value selects the one
- * effort this encoder has (greedy LZ77, fixed Huffman codes).  The compressed bytes are valid DEFLATE but not zlib's —
+ * effort this encoder has (greedy LZ77; dynamic or fixed Huffman codes, whichever is shorter).  The compressed bytes are valid DEFLATE but not zlib's —
  * the reference asks for the round trip only (outputstream.d:225-247).  device < 0: the current device.
  * BIODB_ERR_NOMEM when cap < what is needed (biodb_bgzf_compress_bound(len) always suffices); BIODB_ERR_CUDA without
  * a device (no CPU fallback). */

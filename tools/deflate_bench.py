@@ -39,7 +39,7 @@ def main():
                       "zlib_written_file_ratio": len(bam) / len(u),
                       "zlib_level1_one_core": {"ratio": z / zn, "gb_per_s_in": zn / tz / 1e9},
                       "what": "wall clock of biodb_bgzf_compress through the Python mirror (H2D, one thread per BGZF block: greedy "
-                              "LZ77 + fixed Huffman, CRC32, pack, D2H; plus the mirror's own byte copies)"}))
+                              "LZ77, dynamic or fixed Huffman codes, CRC32, pack, D2H; plus the mirror's own byte copies)"}))
 
 
 if __name__ == "__main__":
