@@ -4,5 +4,5 @@ Everything is computed by libbiod_b200.so (hand-written sm_100a CUDA, C ABI in i
 Importing the package does not need a GPU; opening a reader does, and fails loudly without one.
 """
 from . import _capi  # noqa: F401
-from .bam import (BaiFile, BamFormatException, BamWriter, BgzfOutputStream, bgzf_compress, BamRead, BamReader, BgzfException, CudaUnavailable, PileupColumn,  # noqa: F401
+from .bam import (BaiFile, BamFormatException, BamWriter, IndexBuilder, createIndex, BgzfOutputStream, bgzf_compress, BamRead, BamReader, BgzfException, CudaUnavailable, PileupColumn,  # noqa: F401
                   PileupException, ReadException, ZlibException, makePileup, pileupColumns)

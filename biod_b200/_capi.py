@@ -133,6 +133,15 @@ def lib():
     L.biodb_index_chunks.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64]
     L.biodb_index_last_linear_offset.restype = C.c_int32
     L.biodb_index_last_linear_offset.argtypes = [vp, C.c_int32, u64p]
+    L.biodb_index_builder_begin.restype = C.c_int
+    L.biodb_index_builder_begin.argtypes = [C.c_int32, C.c_int32, C.POINTER(vp)]
+    L.biodb_index_builder_put.restype = C.c_int
+    L.biodb_index_builder_put.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, vp, vp]
+    L.biodb_index_builder_finish.restype = C.c_int
+    L.biodb_index_builder_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.biodb_index_builder_error.restype = C.c_char_p
+    L.biodb_index_builder_error.argtypes = [vp]
+    L.biodb_index_builder_end.argtypes = [vp]
     L.biodb_reads_begin_region.restype = C.c_int
     L.biodb_reads_begin_region.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.biodb_pileup_begin_region.restype = C.c_int
@@ -177,7 +186,8 @@ EXPORTS = [
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
-    "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset",
+    "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",
+    "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",
     "biodb_debug_deflate_block", "biodb_writer_begin", "biodb_writer_header", "biodb_writer_records", "biodb_writer_flush",
     "biodb_writer_finish", "biodb_writer_layout", "biodb_writer_error", "biodb_writer_end",

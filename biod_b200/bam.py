@@ -784,3 +784,56 @@ class BamWriter:
             self.close()
         except Exception:
             pass
+
+
+class IndexBuilder:
+    """bam/bai/indexing.d:56-351 over the C ABI (host only): put() batches of reads in file order, finish() returns the
+    bytes of the .bai file."""
+
+    def __init__(self, n_refs, check_bins=False):
+        self._L = L = capi.lib()
+        h = C.c_void_p()
+        if L.biodb_index_builder_begin(n_refs, int(check_bins), C.byref(h)) != capi.OK:
+            raise RuntimeError("biodb_index_builder_begin failed")
+        self._h = h
+
+    def put(self, batch):
+        """batch: a RecordBatch of a reader opened with want_offsets (or any object with the same arrays)."""
+        if batch.start_voffset is None:
+            raise Exception("the index needs virtual offsets: open the reader with want_offsets=True")
+        arrs = [np.ascontiguousarray(getattr(batch, f), dtype=dt) for f, dt in
+                (("ref_id", np.int32), ("pos", np.int32), ("end_pos", np.int32), ("bin_mq_nl", np.uint32),
+                 ("flag_nc", np.uint32), ("start_voffset", np.uint64), ("end_voffset", np.uint64))]
+        st = self._L.biodb_index_builder_put(self._h, len(arrs[0]), *[a.ctypes.data for a in arrs])
+        if st != capi.OK:
+            raise Exception(self._L.biodb_index_builder_error(self._h).decode("latin-1"))
+
+    def finish(self):
+        d, n = C.c_void_p(), C.c_size_t()
+        st = self._L.biodb_index_builder_finish(self._h, C.byref(d), C.byref(n))
+        if st != capi.OK:
+            raise Exception(self._L.biodb_index_builder_error(self._h).decode("latin-1"))
+        return C.string_at(d, n.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.biodb_index_builder_end(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def createIndex(reader, check_bins=False):
+    """bam/bai/indexing.d:356-366: the BAI index of a coordinate-sorted file, as bytes.  The reads and their virtual
+    offsets come from a GPU pass over the file (the reader must have been opened with want_offsets=True)."""
+    b = IndexBuilder(len(reader.reference_sequences), check_bins)
+    try:
+        for batch in reader.read_batches(copy=True):
+            b.put(batch)
+        return b.finish()
+    finally:
+        b.close()

@@ -1,6 +1,7 @@
 // Host runtime + C ABI of libbiod_b200.so (see include/biod_b200.h and runtime.h).
 #include "runtime.h"
 #include "bai.h"
+#include "bai_build.h"
 #include "md_chain.h"
 #include "md_walk.h"
 
@@ -777,6 +778,11 @@ struct ReadsSlot {
 struct biodb_index {
   BaiIndex bai;
 };
+struct biodb_index_builder {
+  BaiBuilder b;
+  biodb_status failed = BIODB_OK;
+  bool finished = false;
+};
 
 struct biodb_reads {
   Pass pass;
@@ -967,6 +973,39 @@ biodb_status biodb_reads_begin(biodb_reader* r, biodb_reads** out) {
   *out = it;
   return BIODB_OK;
 }
+
+// ---- IndexBuilder (bai/indexing.d) behind the C ABI: host only ------------------------------------------------------
+biodb_status biodb_index_builder_begin(int32_t n_refs, int32_t check_bins, biodb_index_builder** out) {
+  if (!out || n_refs < 0) return BIODB_ERR_ARG;
+  biodb_index_builder* b = new biodb_index_builder;
+  b->b.begin(n_refs, check_bins != 0);
+  *out = b;
+  return BIODB_OK;
+}
+biodb_status biodb_index_builder_put(biodb_index_builder* b, uint64_t n, const int32_t* ref_id, const int32_t* pos,
+                                     const int32_t* end_pos, const uint32_t* bin_mq_nl, const uint32_t* flag_nc,
+                                     const uint64_t* start_voffset, const uint64_t* end_voffset) {
+  if (!b || (n && (!ref_id || !pos || !end_pos || !bin_mq_nl || !flag_nc || !start_voffset || !end_voffset))) return BIODB_ERR_ARG;
+  if (b->failed) return b->failed;
+  for (uint64_t i = 0; i < n; ++i) {
+    const bool unm = ((flag_nc[i] >> 16) & 4) != 0;
+    if (!b->b.put(ref_id[i], pos[i], end_pos[i], bin_mq_nl[i] >> 16, unm, start_voffset[i], end_voffset[i])) {
+      b->failed = b->b.err.rfind("BAM file is not", 0) == 0 ? BIODB_ERR_UNSORTED : BIODB_ERR_FORMAT;
+      return b->failed;
+    }
+  }
+  return BIODB_OK;
+}
+biodb_status biodb_index_builder_finish(biodb_index_builder* b, const uint8_t** data, size_t* len) {
+  if (!b || !data || !len) return BIODB_ERR_ARG;
+  if (b->failed) return b->failed;
+  if (!b->finished) { b->b.finish(); b->finished = true; }
+  *data = b->b.out.data();
+  *len = b->b.out.size();
+  return BIODB_OK;
+}
+const char* biodb_index_builder_error(const biodb_index_builder* b) { return b ? b->b.err.c_str() : ""; }
+void biodb_index_builder_end(biodb_index_builder* b) { delete b; }
 
 biodb_status biodb_index_open(const void* bai, size_t len, biodb_index** out) {
   if (!bai || !out) return BIODB_ERR_ARG;

@@ -137,6 +137,20 @@ int64_t biodb_index_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t beg,
 /* The last entry of the last non-empty linear index among references [0, n_refs): where BamReader.unmappedReads starts
  * looking for the reads without a reference (reader.d:369-390).  Returns 1 and writes *out, or 0 if there is none. */
 int32_t biodb_index_last_linear_offset(const biodb_index* ix, int32_t n_refs, uint64_t* out);
+/* IndexBuilder / createIndex (bio/std/hts/bam/bai/indexing.d:56-366): builds the bytes of a .bai file from the reads of
+ * a coordinate-sorted file, given in file order, batch by batch, as the arrays a biodb_record_batch holds (reader opened
+ * with options.want_offsets).  Host only.  check_bins: verify every read's bin (indexing.d:236-246).
+ * BIODB_ERR_UNSORTED ("BAM file is not coordinate-sorted ...") / BIODB_ERR_FORMAT ("Bin in read ... is set
+ * incorrectly"), message in _error.  _finish: the file's bytes, valid until _end.  Bins are written in ascending order
+ * (the reference's order is that of a D associative array). */
+typedef struct biodb_index_builder biodb_index_builder;
+biodb_status biodb_index_builder_begin(int32_t n_refs, int32_t check_bins, biodb_index_builder** out);
+biodb_status biodb_index_builder_put(biodb_index_builder* b, uint64_t n, const int32_t* ref_id, const int32_t* pos,
+                                     const int32_t* end_pos, const uint32_t* bin_mq_nl, const uint32_t* flag_nc,
+                                     const uint64_t* start_voffset, const uint64_t* end_voffset);
+biodb_status biodb_index_builder_finish(biodb_index_builder* b, const uint8_t** data, size_t* len);
+const char* biodb_index_builder_error(const biodb_index_builder* b);
+void biodb_index_builder_end(biodb_index_builder* b);
 /* ReferenceSequence.opSlice(beg, end) = RandomAccessManager.getReads(BamRegion) (reference.d:76-81,
  * randomaccessmanager.d:300-305): an iterator over the reads of reference ref_id that overlap [beg, end) — the chunks
  * are inflated and scanned like any other stretch of the file, then filtered on the device (BamReadFilter, :366-462).
