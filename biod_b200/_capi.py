@@ -164,6 +164,10 @@ def lib():
     L.biodb_writer_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.biodb_writer_layout.restype = C.c_int
     L.biodb_writer_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.biodb_writer_index.restype = C.c_int
+    L.biodb_writer_index.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.biodb_writer_debug_set_output.restype = C.c_int
+    L.biodb_writer_debug_set_output.argtypes = [vp, vp, C.c_size_t]
     L.biodb_writer_error.restype = C.c_char_p
     L.biodb_writer_error.argtypes = [vp]
     L.biodb_writer_end.argtypes = [vp]
@@ -190,5 +194,5 @@ EXPORTS = [
     "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",
     "biodb_debug_deflate_block", "biodb_writer_begin", "biodb_writer_header", "biodb_writer_records", "biodb_writer_flush",
-    "biodb_writer_finish", "biodb_writer_layout", "biodb_writer_error", "biodb_writer_end",
+    "biodb_writer_finish", "biodb_writer_layout", "biodb_writer_index", "biodb_writer_debug_set_output", "biodb_writer_error", "biodb_writer_end",
 ]

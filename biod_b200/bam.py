@@ -766,13 +766,33 @@ class BamWriter:
         cuts = list(np.frombuffer(C.string_at(c, 8 * k.value), dtype=np.uint64).astype(np.int64))
         return data, cuts
 
-    def finish(self):
+    def index(self):
+        """The BAI index of the finished file (call between finish_keep() and close(); writer.d:139-195)."""
+        d, n = C.c_void_p(), C.c_size_t()
+        self._check(self._L.biodb_writer_index(self._h, C.byref(d), C.byref(n)))
+        return C.string_at(d, n.value)
+
+    def finish(self, want_index=None):
+        """writer.d:276-280.  Like BamWriter, creates `<file>.bai` next to a coordinate-sorted `.bam` written to a path
+        (writer.d:139-146,171-175); want_index=True returns the index bytes whatever the sink is."""
         d, n = C.c_void_p(), C.c_size_t()
         self._check(self._L.biodb_writer_finish(self._h, C.byref(d), C.byref(n)))
         self._sink.write(C.string_at(d, n.value))
+        path = self._sink.name if self._own else None
+        auto = bool(path) and str(path).endswith(".bam") and b"SO:coordinate" in getattr(self, "_text", b"") and \
+            not getattr(self, "_no_index", False)
+        bai = self.index() if (want_index or (auto and want_index is None)) else None
+        if auto and bai is not None:
+            with open(str(path) + ".bai", "wb") as f:
+                f.write(bai)
         if self._own:
             self._sink.close()
         self.close()
+        return bai
+
+    def disableAutoIndexCreation(self):
+        """writer.d:108-110"""
+        self._no_index = True
 
     def close(self):
         if getattr(self, "_h", None):

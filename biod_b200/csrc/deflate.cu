@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "bai_build.h"
 #include "deflate_enc.h"
 #include "runtime.h"
 #include "scan.cuh"
@@ -257,7 +258,11 @@ struct biodb_writer {
   int32_t n_refs = 0;
   bool header_done = false;
   std::vector<uint8_t> out;            // the finished file
+  std::vector<uint8_t> index;          // its BAI index (biodb_writer_index)
   std::string err;
+  // what the index needs to know of every record written (writer.d:150-195 parses it back out of the blocks)
+  struct Rec { uint64_t at; uint32_t size; int32_t ref_id, pos, end_pos; uint32_t bin; bool unmapped; };
+  std::vector<Rec> recs;
 
   void flush_current_block() {         // outputstream.d:136-161
     if (stream_cur == 0) return;
@@ -355,9 +360,11 @@ biodb_status biodb_writer_records(biodb_writer* w, const uint8_t* records, size_
     const size_t read_size = rec.size();                                   // size_in_bytes (read.d:609-611)
     if (read_size + w->rec_cur > BGZF_CHUNK) {
       w->flush_current_block();
+      w->recs.push_back(biodb_writer::Rec{w->bytes.size(), (uint32_t)read_size, ref_id, pos, (int32_t)((uint32_t)pos + covered), bin, (flag & 4) != 0});
       w->write(rec.data(), rec.size());
       w->rec_cur = read_size;
     } else {
+      w->recs.push_back(biodb_writer::Rec{w->bytes.size(), (uint32_t)read_size, ref_id, pos, (int32_t)((uint32_t)pos + covered), bin, (flag & 4) != 0});
       w->write(rec.data(), rec.size());
       w->rec_cur += read_size;
     }
@@ -395,6 +402,48 @@ biodb_status biodb_writer_finish(biodb_writer* w, const uint8_t** data, size_t* 
   w->out.insert(w->out.end(), EOF_BLOCK, EOF_BLOCK + 28);
   *data = w->out.data();
   *len = w->out.size();
+  return BIODB_OK;
+}
+
+// Host-only test hook: take `data` for the finished file (a BGZF stream with exactly the writer's block layout, e.g.
+// compressed by zlib), so that biodb_writer_index can be checked without a device.
+biodb_status biodb_writer_debug_set_output(biodb_writer* w, const uint8_t* data, size_t len) {
+  if (!w || (!data && len)) return BIODB_ERR_ARG;
+  w->flush_current_block();
+  w->out.assign(data, data + len);
+  return BIODB_OK;
+}
+
+// The BAI index of the finished file — what BamWriter builds while writing coordinate-sorted output (writer.d:139-195,
+// 171-175: IndexBuilder with check_bins, fed with every record and the virtual offsets it got in the file).  Call after
+// biodb_writer_finish.  BIODB_ERR_UNSORTED if the records were not in coordinate order.
+biodb_status biodb_writer_index(biodb_writer* w, const uint8_t** data, size_t* len) {
+  if (!w || !data || !len || w->out.empty()) return BIODB_ERR_ARG;
+  // where the blocks of the layout begin in the file: the BSIZE chain of the finished stream
+  const size_t nb = w->cuts.size() - 1;
+  std::vector<uint64_t> cb;
+  size_t p = 0;
+  while (p + 18 <= w->out.size() && cb.size() <= nb) {
+    cb.push_back(p);
+    p += ((size_t)w->out[p + 16] | ((size_t)w->out[p + 17] << 8)) + 1;
+  }
+  if (cb.size() != nb + 1) { w->err = "the finished file does not have the writer's block layout"; return BIODB_ERR_FORMAT; }
+  auto voffset = [&](uint64_t x) -> uint64_t {                    // of byte x of the uncompressed stream
+    const size_t i = (size_t)(std::upper_bound(w->cuts.begin(), w->cuts.end(), x) - w->cuts.begin()) - 1;   // cuts[i] <= x
+    return (cb[i] << 16) | (x - w->cuts[i]);                       // (x == the end of the stream: the EOF block, offset 0)
+  };
+  BaiBuilder b;
+  b.begin(w->n_refs, true);
+  for (const biodb_writer::Rec& r : w->recs) {
+    if (!b.put(r.ref_id, r.pos, r.end_pos, r.bin, r.unmapped, voffset(r.at), voffset(r.at + r.size))) {
+      w->err = b.err;
+      return b.err.rfind("BAM file is not", 0) == 0 ? BIODB_ERR_UNSORTED : BIODB_ERR_FORMAT;
+    }
+  }
+  b.finish();
+  w->index.swap(b.out);
+  *data = w->index.data();
+  *len = w->index.size();
   return BIODB_OK;
 }
 

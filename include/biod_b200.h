@@ -294,6 +294,12 @@ biodb_status biodb_writer_records(biodb_writer* w, const uint8_t* records, size_
 biodb_status biodb_writer_flush(biodb_writer* w);
 biodb_status biodb_writer_finish(biodb_writer* w, const uint8_t** data, size_t* len);
 biodb_status biodb_writer_layout(const biodb_writer* w, const uint8_t** data, size_t* len, const uint64_t** cuts, size_t* n_cuts);
+/* The BAI index of the finished file: what BamWriter builds while it writes coordinate-sorted output (writer.d:139-195:
+ * IndexBuilder with check_bins, every record with the virtual offsets it got).  After _finish; valid until _end.
+ * BIODB_ERR_UNSORTED when the records were not in coordinate order. */
+biodb_status biodb_writer_index(biodb_writer* w, const uint8_t** data, size_t* len);
+/* Host-only test hook: use `data` (a BGZF stream with the writer's block layout) as the finished file. */
+biodb_status biodb_writer_debug_set_output(biodb_writer* w, const uint8_t* data, size_t len);
 const char* biodb_writer_error(const biodb_writer* w);
 void biodb_writer_end(biodb_writer* w);
 /* Host-only test hook: the device's DEFLATE encoder (csrc/deflate_enc.h) compiled for the CPU; raw DEFLATE of one

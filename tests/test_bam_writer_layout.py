@@ -129,3 +129,32 @@ def test_writer_argument_errors():
         w.writeRecords(b"\x50\x00\x00\x00abc")                            # truncated
     with pytest.raises(ValueError):
         BamWriter(io.BytesIO(), compression_level=12)
+
+
+def test_index_of_the_written_file():
+    """biodb_writer_index (writer.d:139-195): the index BamWriter builds while writing == IndexBuilder over the reads
+    and virtual offsets the finished file really has.  The file is compressed by zlib here (debug hook), so no GPU."""
+    import ctypes as C
+    from baiutil import build_bai_biod
+    from biod_b200 import _capi
+    L = _capi.lib()
+    for name in ("ex1_header.bam", "bins.bam", "mg1655_chunk.bam"):
+        o = orc.Bam(fixture_bytes(name)).decode()
+        w = write_like(o)
+        w.writeRecords(b"".join(struct.pack("<i", int(o.block_size[i])) + o.record_bytes(i).tobytes()
+                                for i in range(o.n_records)))
+        parts, stream = layout_stream(w)
+        buf = np.frombuffer(stream, dtype=np.uint8)
+        assert L.biodb_writer_debug_set_output(w._h, buf.ctypes.data, buf.size) == 0
+        bai = w.index()
+        o2 = orc.Bam(stream).decode()
+        assert bai == build_bai_biod(o2, check_bins=True), name
+    # unsorted records: the writer writes them, the index refuses
+    w = write_like(o)
+    w.writeRecord(bam_record("a", "ACGT", "4M", 100))
+    w.writeRecord(bam_record("b", "ACGT", "4M", 50))
+    parts, stream = layout_stream(w)
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    assert L.biodb_writer_debug_set_output(w._h, buf.ctypes.data, buf.size) == 0
+    with pytest.raises(Exception, match="not coordinate-sorted"):
+        w.index()

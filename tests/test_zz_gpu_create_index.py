@@ -29,3 +29,27 @@ def test_create_index(name, bpb):
                 want = orc.region_reads(o, bai, r, beg, end)[0]
                 got = [x.raw.tobytes() for x in rd.region_reads(r, beg, end)]
                 assert got == [o.record_bytes(int(i)).tobytes() for i in want], (name, r, beg, end)
+
+
+def test_writer_creates_the_index(tmp_path):
+    # writer.d:139-146,171-175: a coordinate-sorted file written to a path ending in .bam gets its .bai beside it
+    import struct
+    from biod_b200 import BamReader, BamWriter
+    o = orc.Bam(fixture_bytes("ex1_header.bam")).decode()
+    assert "SO:coordinate" in o.header_text
+    path = tmp_path / "out.bam"
+    w = BamWriter(str(path))
+    w.writeSamHeader(o.header_text)
+    w.writeReferenceSequenceInfo(list(zip(o.ref_names, o.ref_lens)))
+    w.writeRecords(b"".join(struct.pack("<i", int(o.block_size[i])) + o.record_bytes(i).tobytes() for i in range(o.n_records)))
+    bai = w.finish()
+    written = path.read_bytes()
+    o2 = orc.Bam(written).decode()
+    assert o2.n_records == o.n_records
+    assert bai == build_bai_biod(o2, check_bins=True) == (tmp_path / "out.bam.bai").read_bytes()
+    # and the reader finds it next to the file (baifile.d:95-113)
+    rd = BamReader(str(path))
+    chr2 = o.ref_names.index("chr2")
+    got = [x.raw.tobytes() for x in rd["chr2"][150:160]]
+    want = [i for i in range(o2.n_records) if o2.ref_id[i] == chr2 and o2.pos[i] < 160 and o2.end_pos[i] > 150]
+    assert got == [o2.record_bytes(i).tobytes() for i in want]
