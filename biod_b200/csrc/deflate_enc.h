@@ -204,20 +204,27 @@ BIODB_HD void defl_code_lengths(const uint16_t* freq, uint32_t n, uint32_t max_l
     len[first == 0 ? 1 : 0] = 1;
     return;
   }
-  // leaves 0..used-1 (in symbol order), internal nodes after them
+  // leaves in order of rising weight (insertion sort: at most 286 symbols), internal nodes after them; the nodes a
+  // join creates come out in rising weight too, so the two lightest roots are always at the front of one of the two
+  // queues (no search)
+  for (uint32_t i = 1; i < used; ++i) {
+    const uint16_t v = order[i];
+    uint32_t j = i;
+    while (j > 0 && freq[order[j - 1]] > freq[v]) { order[j] = order[j - 1]; --j; }
+    order[j] = v;
+  }
   for (uint32_t k = 0; k < used; ++k) { weight[k] = freq[order[k]]; parent[k] = 0xFFFF; }
-  uint32_t nodes = used;
+  uint32_t li = 0, qi = used, qn = used;
   for (uint32_t m = 0; m + 1 < used; ++m) {
-    uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu;          // the two lightest roots (a <= b)
-    for (uint32_t k = 0; k < nodes; ++k) {
-      if (parent[k] != 0xFFFF) continue;
-      if (a == 0xFFFFFFFFu || weight[k] < weight[a]) { b = a; a = k; }
-      else if (b == 0xFFFFFFFFu || weight[k] < weight[b]) b = k;
+    uint32_t pick[2];
+    for (int t = 0; t < 2; ++t) {
+      if (li < used && (qi >= qn || weight[li] <= weight[qi])) pick[t] = li++;
+      else pick[t] = qi++;
     }
-    weight[nodes] = weight[a] + weight[b];
-    parent[nodes] = 0xFFFF;
-    parent[a] = parent[b] = (uint16_t)nodes;
-    ++nodes;
+    weight[qn] = weight[pick[0]] + weight[pick[1]];
+    parent[qn] = 0xFFFF;
+    parent[pick[0]] = parent[pick[1]] = (uint16_t)qn;
+    ++qn;
   }
   uint32_t hist[33];
   for (int k = 0; k < 33; ++k) hist[k] = 0;
@@ -237,16 +244,10 @@ BIODB_HD void defl_code_lengths(const uint16_t* freq, uint32_t n, uint32_t max_l
       if (hist[l]) { --hist[l]; hist[l + 1] += 2; break; }
     --total;
   }
-  // symbols by falling frequency (stable: ties keep symbol order) get the lengths shortest first
-  for (uint32_t i = 1; i < used; ++i) {
-    const uint16_t v = order[i];
-    uint32_t j = i;
-    while (j > 0 && freq[order[j - 1]] < freq[v]) { order[j] = order[j - 1]; --j; }
-    order[j] = v;
-  }
-  uint32_t k = 0;
+  // the most frequent symbols (the end of `order`) get the shortest lengths
+  uint32_t k = used;
   for (uint32_t l = 1; l <= max_len; ++l)
-    for (uint32_t c = 0; c < hist[l]; ++c) len[order[k++]] = (uint8_t)l;
+    for (uint32_t c = 0; c < hist[l]; ++c) len[order[--k]] = (uint8_t)l;
 }
 
 // canonical codes (RFC 1951 §3.2.2), already bit-reversed for the LSB-first writer
