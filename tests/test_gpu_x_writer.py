@@ -9,7 +9,7 @@ import pytest
 
 from conftest import fixture_bytes
 from oracle import oracle as orc
-from test_gpu_deflate import bgzf_read
+from test_gpu_x_deflate import bgzf_read
 
 pytestmark = pytest.mark.gpu
 
