@@ -743,10 +743,15 @@ class BamWriter:
         text = getattr(self, "_text", b"")
         self._check(self._L.biodb_writer_header(self._h, text, len(text), len(refs), names, lens))
 
-    def writeRecord(self, read):
-        """writer.d:244-268; `read` is a BamRead, or the raw bytes of a record (with or without its block_size prefix)."""
+    def writeRecord(self, read, prefixed=False):
+        """writer.d:244-268; `read` is a BamRead, or the raw bytes of one record BODY (what follows the block_size field) —
+        the block_size prefix is always prepended here.  Bytes that already carry their prefix are passed with
+        prefixed=True (or through writeRecords); nothing is guessed from the bytes themselves."""
         raw = read.raw.tobytes() if hasattr(read, "raw") else bytes(read)
-        if hasattr(read, "raw") or len(raw) < 4 or int.from_bytes(raw[:4], "little", signed=True) != len(raw) - 4:
+        if prefixed and not hasattr(read, "raw"):
+            if len(raw) < 4 or int.from_bytes(raw[:4], "little", signed=True) != len(raw) - 4:
+                raise Exception("malformed record: the block_size prefix does not match the length of the bytes given")
+        else:
             raw = len(raw).to_bytes(4, "little") + raw
         self.writeRecords(raw)
 
@@ -776,18 +781,22 @@ class BamWriter:
         """writer.d:276-280.  Like BamWriter, creates `<file>.bai` next to a coordinate-sorted `.bam` written to a path
         (writer.d:139-146,171-175); want_index=True returns the index bytes whatever the sink is."""
         d, n = C.c_void_p(), C.c_size_t()
-        self._check(self._L.biodb_writer_finish(self._h, C.byref(d), C.byref(n)))
-        self._sink.write(C.string_at(d, n.value))
-        path = self._sink.name if self._own else None
-        auto = bool(path) and str(path).endswith(".bam") and b"SO:coordinate" in getattr(self, "_text", b"") and \
-            not getattr(self, "_no_index", False)
-        bai = self.index() if (want_index or (auto and want_index is None)) else None
-        if auto and bai is not None:
-            with open(str(path) + ".bai", "wb") as f:
-                f.write(bai)
-        if self._own:
-            self._sink.close()
-        self.close()
+        try:
+            self._check(self._L.biodb_writer_finish(self._h, C.byref(d), C.byref(n)))
+            self._sink.write(C.string_at(d, n.value))
+            path = self._sink.name if self._own else None
+            auto = bool(path) and str(path).endswith(".bam") and b"SO:coordinate" in getattr(self, "_text", b"") and \
+                not getattr(self, "_no_index", False)
+            # (unsorted records under an SO:coordinate header, or a wrong bin, make index() raise — the reference fails at
+            #  writeRecord time; either way the file and the native handle are released below)
+            bai = self.index() if (want_index or (auto and want_index is None)) else None
+            if auto and bai is not None:
+                with open(str(path) + ".bai", "wb") as f:
+                    f.write(bai)
+        finally:
+            if self._own:
+                self._sink.close()
+            self.close()
         return bai
 
     def disableAutoIndexCreation(self):

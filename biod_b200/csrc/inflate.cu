@@ -476,27 +476,58 @@ unsigned long long g_kernel_launches = 0;
 
 size_t inflate_smem_bytes() { return sizeof(WarpSmem); }
 
-// BIODB_INFLATE=serial selects the warp-serial kernel alone (A/B measurements)
-static bool inflate_use_legacy() {
+// Which kernel inflates: the two-warp kernel (inflate_duo.cu) unless BIODB_INFLATE says otherwise —
+// "par" = the one-warp lane-parallel kernel (inflate_par.cu), "serial" = the warp-serial kernel alone (A/B measurements).
+enum { MODE_DUO = 0, MODE_PAR = 1, MODE_SERIAL = 2 };
+static int inflate_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("BIODB_INFLATE");
-    v = (e && e[0] == 's') ? 1 : 0;
+    v = (e && e[0] == 's') ? MODE_SERIAL : (e && e[0] == 'p') ? MODE_PAR : MODE_DUO;
   }
-  return v == 1;
+  return v;
+}
+
+int inflate_resident_blocks(int device) {
+  return inflate_mode() == MODE_DUO ? inflate_duo_resident_blocks(device) : inflate_par_resident_blocks(device);
+}
+
+size_t inflate_token_bytes(uint32_t n_blocks) { return inflate_mode() == MODE_DUO ? inflate_duo_token_bytes(n_blocks) : 0; }
+
+cudaError_t inflate_counters(unsigned long long* out8, int reset) {
+  unsigned long long p[8], d[8];
+  cudaError_t e = inflate_par_counters(p, reset);
+  if (e == cudaSuccess) e = inflate_duo_counters(d, reset);
+  if (e == cudaSuccess)
+    for (int i = 0; i < 8; ++i) out8[i] = p[i] + d[i];
+  return e;
 }
 
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st) {
   if (a.n_blocks == 0) return cudaSuccess;
-  if (!inflate_use_legacy()) {
-    cudaError_t e = launch_inflate_par(a, st);     // lane-parallel kernel; marks the blocks it gives up on
-    if (e != cudaSuccess) return e;
-    inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 1);
-    g_kernel_launches += 2;
+  const int mode = inflate_mode();
+  if (mode == MODE_SERIAL) {
+    inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 0);
+    ++g_kernel_launches;
     return cudaGetLastError();
   }
-  inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 0);
-  ++g_kernel_launches;
+  cudaError_t e;
+  if (mode == MODE_DUO) {
+    InflateArgs b = a;
+    void* tmp = nullptr;
+    if (!b.tok) {                                  // callers without a token area of their own (the device-resident stage API)
+      e = cudaMallocAsync(&tmp, inflate_duo_token_bytes(a.n_blocks), st);
+      if (e != cudaSuccess) return e;
+      b.tok = (uint16_t*)tmp;
+    }
+    e = launch_inflate_duo(b, st);                 // two-warp kernel; marks the blocks it gives up on
+    if (tmp) cudaFreeAsync(tmp, st);
+  } else {
+    e = launch_inflate_par(a, st);                 // one-warp lane-parallel kernel; marks the blocks it gives up on
+  }
+  if (e != cudaSuccess) return e;
+  inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 1);
+  g_kernel_launches += 2;
   return cudaGetLastError();
 }
 

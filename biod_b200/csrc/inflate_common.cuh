@@ -99,16 +99,27 @@ __device__ __forceinline__ void dist_base(uint32_t d /*0..29*/, uint32_t& base, 
   if (d < 4) { base = 1 + d; eb = 0; }
   else { eb = (d - 2) >> 1; base = 1 + ((2u + (d & 1)) << eb); }
 }
+// number of extra bits of a length / distance symbol, RFC 1951 §3.2.5 (the closed forms of len_base / dist_base)
+__device__ __forceinline__ uint32_t len_extra_bits(uint32_t s /*0..28*/) { return (s < 8 || s == 28) ? 0u : (s - 4) >> 2; }
+__device__ __forceinline__ uint32_t dist_extra_bits(uint32_t d /*0..29*/) { return d < 4 ? 0u : (d - 2) >> 1; }
+// Length and distance entries also carry the symbol's extra-bit count: bits [5,8) its low three bits, bit 10 its
+// fourth (distances only) — so that a decoder can advance over a code without a second table lookup
+// (ENTRY_EXTRA_BITS).  Readers of the symbol mask it with 31.
 __device__ __forceinline__ uint32_t make_entry(int kind, int sym, int cl) {
   if (kind == KIND_LITLEN) {
     if (sym < 256) return ((uint32_t)cl << 12) | (uint32_t)sym;
     if (sym == 256) return ((uint32_t)cl << 12) | (K_EOB << 8);
     if (sym > 285) return ENT_INVALID;            // 286/287 exist only in the fixed code and are invalid
-    return ((uint32_t)cl << 12) | (K_LEN << 8) | (uint32_t)(sym - 257);
+    return ((uint32_t)cl << 12) | (K_LEN << 8) | (len_extra_bits((uint32_t)(sym - 257)) << 5) | (uint32_t)(sym - 257);
   }
-  if (kind == KIND_DIST) return sym > 29 ? ENT_INVALID : (((uint32_t)cl << 12) | (uint32_t)sym);
+  if (kind == KIND_DIST) {
+    if (sym > 29) return ENT_INVALID;
+    const uint32_t eb = dist_extra_bits((uint32_t)sym);
+    return ((uint32_t)cl << 12) | ((eb & 8) << 7) | ((eb & 7) << 5) | (uint32_t)sym;
+  }
   return ((uint32_t)cl << 12) | (uint32_t)sym;     // code-length code
 }
+#define ENTRY_EXTRA_BITS(e) ((((e) >> 5) & 7u) | (((e) >> 7) & 8u))
 
 // Warp-cooperative canonical-Huffman table build (RFC 1951 §3.2.2): lane L owns code length L.
 // Returns 0 ok, 1 = empty code (LUT all-invalid), -1 = over-subscribed / incomplete set.

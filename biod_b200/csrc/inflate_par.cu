@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(32) inflate_par_kernel(InflateArgs a) {
 #undef OPOS
 }
 
-int inflate_resident_blocks(int device) {
+int inflate_par_resident_blocks(int device) {
   int per_sm = 0, sms = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_par_kernel, 32, 0) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;

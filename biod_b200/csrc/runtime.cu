@@ -385,7 +385,11 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   CUDA_TRY(cudaMemcpyAsync(d_tab.p, h_tab.p, tab_bytes, cudaMemcpyHostToDevice, st));
   if (nb) {
     const uint8_t* comp = resident ? r->d_file.as<uint8_t>() + c0 : d_comp2[comp_cur].as<uint8_t>();
-    InflateArgs ia{comp, d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb, WalkOut{}};
+    InflateArgs ia{comp, d_payload, d_cdata, d_outoff, d_isize, d_u.as<uint8_t>(), d_status.as<int32_t>(), nb, WalkOut{}, nullptr};
+    if (const size_t tb = inflate_token_bytes(nb)) {
+      CUDA_TRY(d_tok.ensure(tb, st));
+      ia.tok = d_tok.as<uint16_t>();
+    }
     if (!raw_mode) {
       // fused record-chain walk: the inflate warps follow the block_size chain of their own block
       ScanWorkspace w0 = carve_scan_workspace(d_ws.p, nsb);
@@ -1190,7 +1194,7 @@ float biodb_reads_progress(const biodb_reads* it) {
 biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off, const uint32_t* cdata_size,
                                const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
                                int32_t* status, uint32_t* crc, void* stream) {
-  InflateArgs ia{comp, payload_off, cdata_size, out_off, isize, out, status, n_blocks, WalkOut{}};
+  InflateArgs ia{comp, payload_off, cdata_size, out_off, isize, out, status, n_blocks, WalkOut{}, nullptr};
   if (launch_inflate(ia, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
   if (crc && launch_crc32(out, out_off, isize, n_blocks, crc, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
   return BIODB_OK;
@@ -1251,7 +1255,7 @@ biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset) {
   if (!out8) return BIODB_ERR_ARG;
   cudaDeviceSynchronize();
   unsigned long long v[8];
-  if (inflate_par_counters(v, reset) != cudaSuccess) return BIODB_ERR_CUDA;
+  if (inflate_counters(v, reset) != cudaSuccess) return BIODB_ERR_CUDA;
   for (int i = 0; i < 8; ++i) out8[i] = v[i];
   return BIODB_OK;
 }

@@ -109,7 +109,7 @@ struct Pass {
   PinBuf h_tab;                     // per-block tables (payload_off, out_off, cdata, isize, block_uoff)
   PinBuf h_status, h_result;
   // device
-  DevBuf d_comp2[2], d_tab, d_status, d_u, d_carry_tail, d_ws, d_result;
+  DevBuf d_comp2[2], d_tab, d_status, d_u, d_carry_tail, d_ws, d_result, d_tok;
   // host->device prefetch of the next batch's compressed bytes (input not resident): while batch k is inflated out of
   // d_comp2[cur], the bytes that follow it in the file go to d_comp2[cur^1] on their own stream
   cudaStream_t h2d_st = nullptr;

@@ -48,7 +48,7 @@ def test_rewritten_fixture_reads_back(name):
     recs = [struct.pack("<i", int(o.block_size[i])) + o.record_bytes(i).tobytes() for i in range(o.n_records)]
     w.writeRecords(b"".join(recs[:o.n_records // 2]))
     for r in recs[o.n_records // 2:]:
-        w.writeRecord(r)
+        w.writeRecord(r, prefixed=True)
     parts, stream = layout_stream(w)
     o2 = orc.Bam(stream).decode()
     assert o2.header_text == o.header_text and o2.ref_names == o.ref_names and o2.ref_lens == o.ref_lens
@@ -123,8 +123,8 @@ def test_writer_argument_errors():
     w.writeSamHeader("@HD\tVN:1.6\n")
     w.writeReferenceSequenceInfo([("c0", 1000)])
     with pytest.raises(Exception, match="Read reference ID is out of range"):
-        w.writeRecord(bam_record("x", "ACGT", "4M", 5, ref_id=1))
-    w.writeRecord(bam_record("u", "ACGT", "", -1, ref_id=-1, flag=4))      # unmapped reads are fine
+        w.writeRecord(bam_record("x", "ACGT", "4M", 5, ref_id=1), prefixed=True)
+    w.writeRecord(bam_record("u", "ACGT", "", -1, ref_id=-1, flag=4), prefixed=True)      # unmapped reads are fine
     with pytest.raises(Exception):
         w.writeRecords(b"\x50\x00\x00\x00abc")                            # truncated
     with pytest.raises(ValueError):
@@ -151,10 +151,29 @@ def test_index_of_the_written_file():
         assert bai == build_bai_biod(o2, check_bins=True), name
     # unsorted records: the writer writes them, the index refuses
     w = write_like(o)
-    w.writeRecord(bam_record("a", "ACGT", "4M", 100))
-    w.writeRecord(bam_record("b", "ACGT", "4M", 50))
+    w.writeRecord(bam_record("a", "ACGT", "4M", 100), prefixed=True)
+    w.writeRecord(bam_record("b", "ACGT", "4M", 50), prefixed=True)
     parts, stream = layout_stream(w)
     buf = np.frombuffer(stream, dtype=np.uint8)
     assert L.biodb_writer_debug_set_output(w._h, buf.ctypes.data, buf.size) == 0
     with pytest.raises(Exception, match="not coordinate-sorted"):
         w.index()
+
+
+def test_write_record_never_guesses_the_prefix():
+    """A record body whose ref_id happens to equal len(body) - 4 (plausible with hundreds of contigs) used to be taken
+    for bytes that already carry their block_size prefix; writeRecord(bytes) now always means a body."""
+    from biod_b200 import BamWriter
+    import io
+    rec = bam_record("q", "ACGTACGT", "8M", 7, ref_id=0)
+    body = bytearray(rec[4:])
+    L = len(body)
+    body[0:4] = struct.pack("<i", L - 4)                    # ref_id == len - 4
+    w = BamWriter(io.BytesIO())
+    w.writeSamHeader("@HD\tVN:1.6\n")
+    w.writeReferenceSequenceInfo([("c%d" % i, 1000) for i in range(L)])
+    w.writeRecord(bytes(body))
+    data, cuts = w.layout()
+    assert data[cuts[-1]:][:8] == struct.pack("<ii", L, L - 4) and data.endswith(bytes(body)[12:])   # (the bin is recalculated)
+    with pytest.raises(Exception, match="block_size prefix"):
+        w.writeRecord(bytes(body)[:-1], prefixed=True)      # said to be prefixed, but the prefix does not fit
