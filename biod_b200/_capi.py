@@ -48,10 +48,9 @@ class PileupParams(C.Structure):
 
 
 class ShardInfo(C.Structure):
-    _fields_ = [("first_coffset", C.c_uint64), ("end_coffset", C.c_uint64), ("halo_coffset", C.c_uint64),
+    _fields_ = [("first_voffset", C.c_uint64), ("end_voffset", C.c_uint64), ("halo_voffset", C.c_uint64),
                 ("lo_ref", C.c_int32), ("hi_ref", C.c_int32), ("lo_pos", C.c_int64), ("hi_pos", C.c_int64),
-                ("n_halo_records", C.c_uint64), ("n_own_records", C.c_uint64),
-                ("max_end_all", C.c_int64), ("max_end_outside_tail", C.c_int64)]
+                ("n_halo_records", C.c_uint64), ("n_own_records", C.c_uint64)]
 
 
 class ColumnBatch(C.Structure):
@@ -108,6 +107,14 @@ def lib():
     L.biodb_pileup_begin_shard.restype = C.c_int
     L.biodb_pileup_begin_shard.argtypes = [vp, C.POINTER(PileupParams), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
     L.biodb_pileup_shard_info.argtypes = [vp, C.POINTER(ShardInfo)]
+    L.biodb_pileup_begin_shard_at.restype = C.c_int
+    L.biodb_pileup_begin_shard_at.argtypes = [vp, C.POINTER(PileupParams), C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(vp)]
+    L.biodb_pileup_shard_reach.argtypes = [vp, u64p]
+    L.biodb_shard_cuts.restype = C.c_int
+    L.biodb_shard_cuts.argtypes = [vp, C.c_uint32, u64p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
+    L.biodb_pileup_begin_range.restype = C.c_int
+    L.biodb_pileup_begin_range.argtypes = [vp, C.POINTER(PileupParams), C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_int32,
+                                           C.c_int64, C.POINTER(vp)]
     L.biodb_pileup_next.restype = C.c_int
     L.biodb_pileup_next.argtypes = [vp, C.POINTER(ColumnBatch)]
     L.biodb_pileup_end.argtypes = [vp]
@@ -122,6 +129,8 @@ def lib():
     L.biodb_input_is_pinned.argtypes = [vp]
     L.biodb_debug_inflate_counters.restype = C.c_int
     L.biodb_debug_inflate_counters.argtypes = [u64p, C.c_int32]
+    L.biodb_debug_inflate_cycles.restype = C.c_int
+    L.biodb_debug_inflate_cycles.argtypes = [u64p, C.c_int32]
     L.biodb_debug_md_chain.restype = C.c_int64
     L.biodb_debug_md_chain.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_uint64, vp, C.c_uint64]
     L.biodb_index_open.restype = C.c_int
@@ -188,8 +197,9 @@ EXPORTS = [
     "biodb_open_error", "biodb_header_text", "biodb_n_refs", "biodb_ref_info", "biodb_reads_start_voffset",
     "biodb_file_size", "biodb_input_is_pinned", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
-    "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_shard_info",
-    "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
+    "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_begin_shard_at", "biodb_pileup_shard_info",
+    "biodb_pileup_shard_reach", "biodb_shard_cuts", "biodb_pileup_begin_range",
+    "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_inflate_cycles", "biodb_debug_md_chain",
     "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",
     "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",

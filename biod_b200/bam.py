@@ -463,10 +463,14 @@ class BamReader:
                 yield BamRead(batch, i)
 
     def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
-                       want_query_offset=False, copy=False, shard=None, halo_blocks=8, shard_info=None, counts_only=False,
-                       compact_reads=False, region=None):
-        """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015);
-        region=(ref_id, start, end) piles up the reads of bam[ref][start .. end) only (read_idx then counts those)."""
+                       want_query_offset=False, copy=False, shard=None, halo_blocks=8, halo_voffset=None, shard_info=None,
+                       counts_only=False, compact_reads=False, region=None, record_range=None):
+        """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015): its halo
+        starts halo_blocks BGZF blocks in front of it (a guess) or at the record at halo_voffset; shard_info receives
+        the biodb_shard_info fields plus "reach" (see biod_b200.stitch.exact_halos).
+        region=(ref_id, start, end) piles up the reads of bam[ref][start .. end) only (read_idx then counts those).
+        record_range=(from_voffset, to_voffset, lo_ref, lo_pos, hi_ref, hi_pos): the records that start in
+        [from, to), columns clipped to the keys [lo, hi) (biodb_pileup_begin_range)."""
         L = self._L
         p = capi.PileupParams()
         p.single_ref, p.skip_zero_coverage, p.use_md_tag = int(single_ref), int(skip_zero_coverage), int(use_md_tag)
@@ -476,12 +480,16 @@ class BamReader:
         pl = C.c_void_p()
         if region is not None:
             st = L.biodb_pileup_begin_region(self._h, self._bai()._h, region[0], region[1], region[2], C.byref(p), C.byref(pl))
+        elif record_range is not None:
+            st = L.biodb_pileup_begin_range(self._h, C.byref(p), *[int(x) for x in record_range], C.byref(pl))
+        elif shard is not None and halo_voffset is not None:
+            st = L.biodb_pileup_begin_shard_at(self._h, C.byref(p), shard[0], shard[1], int(halo_voffset), C.byref(pl))
         elif shard is not None:
             st = L.biodb_pileup_begin_shard(self._h, C.byref(p), shard[0], shard[1], halo_blocks, C.byref(pl))
         else:
             st = L.biodb_pileup_begin(self._h, C.byref(p), C.byref(pl))
         if st == capi.ERR_ARG:
-            raise ValueError("biodb_pileup_begin: invalid arguments (use_md_tag is not available for shards)")
+            raise ValueError("biodb_pileup_begin: invalid arguments")
         if st != capi.OK:
             self._err()
         try:
@@ -493,12 +501,42 @@ class BamReader:
                         si = capi.ShardInfo()
                         L.biodb_pileup_shard_info(pl, C.byref(si))
                         shard_info.update({f: getattr(si, f) for f, _ in si._fields_})
+                        if shard is not None:
+                            reach = (C.c_uint64 * shard[1])()
+                            L.biodb_pileup_shard_reach(pl, reach)
+                            shard_info["reach"] = [int(x) for x in reach]
                     return
                 if st != capi.OK:
                     self._err()
                 yield ColumnBatch(cb, copy)
         finally:
             L.biodb_pileup_end(pl)
+
+    def shard_cuts(self, n_shards):
+        """(voffset, ref_id, position) of the n_shards + 1 cuts of a sharded pileup (biodb_shard_cuts)."""
+        vo = (C.c_uint64 * (n_shards + 1))()
+        rf = (C.c_int32 * (n_shards + 1))()
+        ps = (C.c_int64 * (n_shards + 1))()
+        if self._L.biodb_shard_cuts(self._h, n_shards, vo, rf, ps) != capi.OK:
+            self._err()
+        return [(int(vo[k]), int(rf[k]), int(ps[k])) for k in range(n_shards + 1)]
+
+    def sharded_column_batches(self, n_shards, halo_blocks=8, shard_infos=None, **kw):
+        """All shards of a sharded pileup, one after the other on this GPU, with EXACT halos: shard t's halo starts at
+        the first record of an earlier shard that reaches into its columns (the minimum of the earlier shards'
+        "reach" reports — known by the time shard t runs, so nothing is run twice here; across GPUs the shards run
+        at once from a guess and biod_b200.stitch.exact_halos says which to run again).  Yields (shard, batch)."""
+        need = [2**64 - 1] * n_shards
+        cuts = self.shard_cuts(n_shards)
+        for s in range(n_shards):
+            info = {}
+            hv = min(need[s], cuts[s][0])
+            for b in self.column_batches(False, shard=(s, n_shards), halo_voffset=hv, shard_info=info, **kw):
+                yield s, b
+            for t in range(s + 1, n_shards):
+                need[t] = min(need[t], info["reach"][t])
+            if shard_infos is not None:
+                shard_infos.append(info)
 
 
 def _popcount64(x):
@@ -660,6 +698,118 @@ def makePileup(reader, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_ze
 def pileupColumns(reader, use_md_tag=False, skip_zero_coverage=True):
     """bam/pileup.d:509-519"""
     return _columns(reader, False, use_md_tag=use_md_tag, skip_zero_coverage=skip_zero_coverage)
+
+
+# ---- pileupChunks (bam/pileup.d:859-1015, bam/splitter.d:66-101) ---------------------------------------------------
+def chunk_plan(ref_id, pos, end_pos, rec_size, block_size=16_384_000, start_from=0, end_at=2**64 - 1):
+    """Where BioD's pileupChunks cuts a range of reads, from the per-read tables alone (host arithmetic, no GPU):
+    chunksConsumingLessThan (splitter.d:72-90: a chunk takes reads while the bytes taken so far are <= block_size and the
+    reference stays that of its first read; size_in_bytes = 4 + block_size of the record, read.d:609-611) and
+    PileupChunkRange's constructor / front / popFront (pileup.d:876-940).  Returns a list of dicts
+    (first, last, halo, ref_id, start_position, end_position): the chunk's reads [first, last), the first read of its
+    halo, and its column interval.  The halo is EXACT — the first earlier read of the reference that reaches beyond the
+    interval's start — where BioD keeps the previous chunk's reads from 2 x the median read length before it
+    (pileup.d:941-985, an approximation that loses longer reads)."""
+    n = len(ref_id)
+    size = rec_size.astype(np.int64) + 4
+    cum = np.concatenate([[0], np.cumsum(size)])
+    chunks = []
+    i = 0
+    while i < n:
+        # getNextChunk: the first read always; then reads while total_size <= block_size (checked before each is added)
+        j = int(np.searchsorted(cum, cum[i] + block_size, side="right"))     # first j with cum[j] - cum[i] > block_size
+        j = max(i + 1, min(j, n))
+        other = np.nonzero(ref_id[i + 1:j] != ref_id[i])[0]
+        if other.size:
+            j = i + 1 + int(other[0])
+        chunks.append((i, j))
+        i = j
+    # exact halos: per reference run, the running maximum of the end positions (non-decreasing, so "the first read
+    # that reaches beyond x" is a binary search)
+    run_start = np.zeros(n, dtype=np.int64)
+    pm = np.zeros(n, dtype=np.int64)
+    if n:
+        edges = np.concatenate([[0], np.flatnonzero(np.diff(ref_id)) + 1, [n]])
+        for a, b in zip(edges[:-1], edges[1:]):
+            run_start[a:b] = a
+            pm[a:b] = np.maximum.accumulate(end_pos[a:b].astype(np.int64))
+    plan = []
+    started = False
+    prev = None                                    # (first, last) of the previous chunk handed out
+    for k, (i, j) in enumerate(chunks):
+        rid = int(ref_id[i])
+        if rid < 0:
+            continue
+        right_end = int(end_pos[i:j].max())
+        if not started:
+            beg = int(pos[i])
+            if beg >= end_at:
+                break
+            if right_end <= start_from:
+                continue
+            started = True
+            halo = i
+        else:
+            if prev is not None and int(ref_id[prev[1] - 1]) == rid:
+                beg = int(pos[prev[1] - 1])
+            else:
+                beg = int(pos[i])
+                prev = None
+            halo = i
+            if prev is not None:
+                # the first earlier read of this reference that covers a position beyond beg
+                r0 = int(run_start[i])
+                halo = min(i, r0 + int(np.searchsorted(pm[r0:i], beg, side="right")))
+        # front: up to the position of the chunk's last read, or — when the next chunk of the range (whatever its
+        # reference id) is on another reference, or there is none — to the right end of the chunk's reads
+        nxt = chunks[k + 1] if k + 1 < len(chunks) else None
+        end = int(pos[j - 1])
+        if nxt is None or int(ref_id[nxt[0]]) != int(ref_id[j - 1]):
+            end = right_end
+        plan.append(dict(first=i, last=j, halo=halo, ref_id=rid, start_position=max(beg, start_from), end_position=min(end, end_at)))
+        prev = (i, j)
+    return plan
+
+
+class PileupChunk:
+    """One element of pileupChunks: the pileup of a chunk's reads and its halo over [start_position, end_position)
+    (makePileup(chain(prev_chunk, chunk), use_md_tag, beg, end), pileup.d:905-913).  Chunks are independent of one
+    another: any number may be iterated at the same time, on one GPU or several."""
+
+    def __init__(self, reader, plan, from_vo, to_vo, use_md_tag):
+        self._reader, self._from, self._to, self._md = reader, from_vo, to_vo, use_md_tag
+        self.ref_id, self.start_position, self.end_position = plan["ref_id"], plan["start_position"], plan["end_position"]
+        self.first_read_index = plan["halo"]          # read_idx of the columns counts from this read of the file
+        self.reads = (plan["first"], plan["last"])
+
+    def column_batches(self, **kw):
+        if self.start_position >= self.end_position:
+            return iter(())
+        return self._reader.column_batches(False, use_md_tag=self._md,
+                                           record_range=(self._from, self._to, self.ref_id, self.start_position, self.ref_id,
+                                                         self.end_position), **kw)
+
+    def __iter__(self):
+        for batch in self.column_batches(copy=True):
+            for c in range(batch.n_columns):
+                yield PileupColumn(batch, c)
+
+
+def pileupChunks(reader, use_md_tag=False, block_size=16_384_000, start_from=0, end_at=2**64 - 1):
+    """bam/pileup.d:1011-1015: non-overlapping consecutive pileups that can be processed in parallel.  One pass over the
+    records (GPU: inflate + record scan, field tables only) finds the cuts; every chunk is then a range pileup of its
+    own (biodb_pileup_begin_range).  The reader must have been opened with want_offsets=True."""
+    ref, pos, end, size, vo = [], [], [], [], []
+    for b in reader.read_batches():
+        if b.start_voffset is None:
+            raise Exception("pileupChunks needs virtual offsets: open the reader with want_offsets=True")
+        ref.append(b.ref_id.copy()); pos.append(b.pos.copy()); end.append(b.end_pos.copy())
+        size.append(b.block_size.copy()); vo.append(b.start_voffset.copy())
+    cat = lambda v, dt: np.concatenate(v) if v else np.zeros(0, dtype=dt)  # noqa: E731
+    ref, pos, end, size, vo = cat(ref, np.int32), cat(pos, np.int32), cat(end, np.int32), cat(size, np.int32), cat(vo, np.uint64)
+    for pl in chunk_plan(ref, pos, end, size, block_size, start_from, end_at):
+        to_vo = int(vo[pl["last"]]) if pl["last"] < len(vo) else 2**64 - 1
+        yield PileupChunk(reader, pl, int(vo[pl["halo"]]), to_vo, use_md_tag)
 
 
 # ---- BGZF compression (bgzf/compress.d, bgzf/outputstream.d) --------------------------------------------------------

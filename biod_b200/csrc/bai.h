@@ -44,19 +44,26 @@ struct BaiIndex {
       return true;
     };
     const char* cut = "not enough data in stream";
+    // a count read as a negative int32 is a corrupt index, never "an empty table" (BioD: uninitializedArray with a
+    // negative length throws); a count larger than what the file still holds ends as "not enough data" below
+    auto bad_count = [&](uint32_t v, size_t) { return (int32_t)v < 0; };
+    const char* neg = "Invalid BAI file: negative table size";
     if (n < 4) { *msg = cut; return -4; }
     if (memcmp(d, "BAI\1", 4) != 0) { *msg = "Invalid file format: expected BAI\\1"; return -3; }
     o = 4;
     uint32_t n_ref;
     if (!u32(&n_ref)) { *msg = cut; return -4; }
+    if (bad_count(n_ref, 8)) { *msg = neg; return -3; }
     refs.clear();
     for (int32_t r = 0; r < (int32_t)n_ref; ++r) {
       BaiRef ref;
       uint32_t n_bin;
       if (!u32(&n_bin)) { *msg = cut; return -4; }
+      if (bad_count(n_bin, 8)) { *msg = neg; return -3; }
       for (int32_t b = 0; b < (int32_t)n_bin; ++b) {
         uint32_t id, n_chunk;
         if (!u32(&id) || !u32(&n_chunk)) { *msg = cut; return -4; }
+        if (bad_count(n_chunk, 16)) { *msg = neg; return -3; }
         ref.bin_id.push_back(id);
         ref.bin_first.push_back((uint32_t)ref.chunks.size());
         for (int32_t c = 0; c < (int32_t)n_chunk; ++c) {
@@ -68,6 +75,7 @@ struct BaiIndex {
       ref.bin_first.push_back((uint32_t)ref.chunks.size());
       uint32_t n_intv;
       if (!u32(&n_intv)) { *msg = cut; return -4; }
+      if (bad_count(n_intv, 8)) { *msg = neg; return -3; }
       for (int32_t k = 0; k < (int32_t)n_intv; ++k) {
         uint64_t v;
         if (!u64(&v)) { *msg = cut; return -4; }

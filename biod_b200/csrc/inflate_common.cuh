@@ -354,7 +354,7 @@ struct Walker {
     sb = blk + w.sb_offset;
     win0 = (walking && blk == 0) ? w.in0 : 0;
     wnext = win0; wcnt = 0; wncig = 0; wbad = WALK_OK;
-    wentry = !walking || (blk == 0 && w.sb_offset == 0);
+    wentry = !walking || (blk == 0 && w.sb_offset == 0 && !w.search0);
     wsearch = 0;
     win_abs = ~0ull;
   }
@@ -448,7 +448,7 @@ struct Walker {
     if (!walking) return;
     wk.cnt[sb] = wcnt;
     wk.ncig[sb] = wncig;
-    wk.in[sb] = (blk == 0 && wk.sb_offset == 0) ? obase + wk.in0 : win_abs;
+    wk.in[sb] = (blk == 0 && wk.sb_offset == 0 && !wk.search0) ? obase + wk.in0 : win_abs;
     wk.out[sb] = obase + wnext;
     wk.bad[sb] = status ? WALK_TAIL : wbad;
   }

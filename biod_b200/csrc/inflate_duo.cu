@@ -14,7 +14,7 @@
 //     is counted).  From round 2 on a lane decodes from where its predecessor ended and RECORDS what it decodes as 16-bit
 //     tokens — literal / length / distance, one per loop trip — in a per-block scratch area in global memory (8 KB per
 //     block, L2-resident, written 64 contiguous bytes per warp store).  When the chain of lanes is consistent the
-//     per-lane byte / match / token counts go to shared memory and the resolver is signalled (mbarrier); the decoder
+//     per-lane byte / match / token counts go to shared memory and the resolver is signalled (named barrier); the decoder
 //     goes straight on to the next super-chunk.
 //   * RESOLVER (warp 1): scans the counts into output offsets, REPLAYS the tokens (literals into the shared-memory
 //     output ring, matches into a list: ~10 instructions per token instead of a Huffman decode), releases the token
@@ -53,7 +53,7 @@ constexpr uint32_t POM = POUT - 1;
 constexpr int OUT_BUDGET = POUT - 1536;
 constexpr int LANE_CAP = 512;                  // a lane stops taking codes once it has produced this many bytes ...
 constexpr int MLIST = BIODB_DUO_MLIST;         // matches one super-chunk may hold
-constexpr int LANE_MCAP = 32;                  // ... or this many matches ...
+constexpr int LANE_MCAP = DUO_TOK_TRIPS / 2;   // (a lane stops after DUO_TOK_TRIPS - 1 tokens: at most this many matches)
 constexpr int FLUSH_ALIGN = 128;
 constexpr int SUB_CAP = LIT_BITS >= 10 ? 320 : 352;
 constexpr int STORE_PIECE = 1024;              // stored blocks are copied in pieces of this many bytes
@@ -69,7 +69,7 @@ static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= STORE_PIECE 
 static_assert(STORE_PIECE <= OUT_BUDGET, "");
 
 // tokens (16 bits, one per decode trip of a lane)
-constexpr uint32_t TOK_LEN = 0x4000, TOK_DIST = 0x8000, TOK_EOB = 0x2000;
+constexpr uint32_t TOK_LEN = K_LEN << 13, TOK_EOB = K_EOB << 13, TOK_DIST = 0x8000;   // literal: the byte itself
 // lane stop reasons
 constexpr uint32_t F_EOB = 1, F_ERR = 2, F_INEND = 3;
 // decoder -> resolver messages
@@ -89,8 +89,6 @@ struct __align__(16) DuoSmem {
   uint16_t sub_lit[SUB_CAP];           // second-level tables of the literal/length codes longer than LIT_BITS
   unsigned long long mbar[NCH];        // TMA completion, one per staging chunk
   // ---- decoder -> resolver ----
-  unsigned long long bar_full;         // a message (and its tokens) is ready
-  unsigned long long bar_free;         // the resolver has consumed the message, its tokens and (stored) its input bytes
   uint32_t msg_kind, msg_a, msg_b, r_bad;
   uint32_t msg_lane[32];               // MSG_CHUNK: bytes | matches << 16 | tokens << 24 of every lane
   // ---- resolver warp ----
@@ -107,8 +105,17 @@ struct DCtx {             // shared-space addresses and limits every decoder lan
   uint16_t* tok;          // this block's token area + lane
 };
 
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+// Decoder <-> resolver hand-over on two named barriers (bar.arrive by the 32 lanes of the signalling warp + bar.sync by
+// the 32 lanes of the waiting warp = 64 arrivals): a warp blocked in bar.sync is descheduled by the hardware and costs no
+// issue slots.  (A first version polled an mbarrier with try_wait: the idle resolver warps then spent 18 % of the
+// kernel's instructions spinning — ncu, profiles/ — and the kernel was no faster than its one-warp predecessor.)
+constexpr int BAR_FULL = 1, BAR_FREE = 2;
+__device__ __forceinline__ void bar_signal(int id) {
+  __threadfence_block();                        // tokens (global) and message (shared) before the arrival
+  asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
+__device__ __forceinline__ void bar_await(int id) {
+  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
 }
 
 // 32 bits of the staged stream starting at bit `pos`
@@ -135,6 +142,9 @@ __device__ __forceinline__ void lane_decode(const DCtx& c, bool active, uint32_t
   uint32_t lut = c.lutl, msk = ((1u << LIT_BITS) - 1) << 1;
   uint32_t run = (active && pos < lim) ? 1u : 0u;
   uint16_t* tp = c.tok;
+  // The body is written with selects on 0/1 flags, not with if/else: whatever nvcc turns into branches here runs
+  // divergently (a lane with a literal, a lane with a length, a lane with a distance) and costs every path's instructions.
+  // A stopped lane (run == 0) keeps computing on its last position; nothing it computes is kept.
   while (__any_sync(0xffffffffu, run)) {
     const uint32_t bits = fetch32(c.in_ring, pos);
     uint32_t e = lds16(lut + ((bits << 1) & msk));
@@ -149,30 +159,33 @@ __device__ __forceinline__ void lane_decode(const DCtx& c, bool active, uint32_t
       }
     }
     const uint32_t cl = e >> 12;
-    const uint32_t kind = st ? K_LEN : ((e >> 8) & 3);            // a distance code is handled like a length code
-    const uint32_t eb = kind == K_LEN ? ENTRY_EXTRA_BITS(e) : 0;  // cl + eb <= 28 bits of the 32
-    uint32_t val = 0;
-    if (RECORD) val = lds32(c.auxtab + (((st << 5) | (e & 31)) << 2)) + ((bits >> cl) & ~(0xffffffffu << eb));
-    if (run) {
-      pos += cl + eb;
-      if (RECORD) {
-        const uint32_t tk = st ? (TOK_DIST | (val - 1)) : kind == K_LEN ? (TOK_LEN | (val - 3)) : kind == K_EOB ? TOK_EOB : (e & 0xff);
-        *tp = (uint16_t)tk;
-        ++trips;
-        if (kind == K_LIT) ++o;
-        if (st) { o += len; ++m; }
-        len = val;
-      }
-      if (kind == K_EOB) { fl = F_EOB; run = 0; }
-      st = (st ^ 1) & (kind == K_LEN ? 1u : 0u);     // length -> distance next; anything else -> literal/length next
-      lut = st ? c.lutd : c.lutl;
-      msk = st ? ((1u << DIST_BITS) - 1) << 1 : ((1u << LIT_BITS) - 1) << 1;
-      if (!st) {                                     // a lane stops only between codes of the literal/length alphabet
-        if (pos >= lim) run = 0;
-        if (RECORD && (o >= (uint32_t)LANE_CAP || m >= (uint32_t)LANE_MCAP || trips >= (uint32_t)DUO_TOK_TRIPS - 1)) run = 0;
-      }
+    const uint32_t kraw = (e >> 8) & 3;                            // kind of a literal/length entry (distance entries: 0)
+    const uint32_t is_len = st | (kraw == K_LEN ? 1u : 0u);        // a distance code is handled like a length code
+    const uint32_t eb = is_len ? ENTRY_EXTRA_BITS(e) : 0u;         // cl + eb <= 28 bits of the 32
+    const uint32_t adv = cl + eb;
+    pos += run ? adv : 0u;
+    if (RECORD) {
+      const uint32_t val = lds32(c.auxtab + (((st << 5) | (e & 31)) << 2)) + ((bits >> cl) & ~(0xffffffffu << eb));
+      const uint32_t tk = (st ? TOK_DIST : (kraw << 13)) | (is_len ? val - (st ? 1u : 3u) : (e & 0xffu));
+      if (run) *tp = (uint16_t)tk;
+      tp += 32;
+      trips += run;
+      const uint32_t lit = (is_len | kraw) ? 0u : run;             // a literal: one byte
+      const uint32_t mat = st & run;                               // a distance: the match is complete
+      o += lit + (mat ? len : 0u);
+      m += mat;
+      len = val;
     }
-    if (RECORD) tp += 32;
+    const uint32_t eob = (st ? 0u : (kraw == K_EOB ? 1u : 0u)) & run;
+    fl = eob ? F_EOB : fl;
+    st = (st ^ 1u) & is_len;                         // length -> distance next; anything else -> literal/length next
+    lut = st ? c.lutd : c.lutl;
+    msk = st ? ((1u << DIST_BITS) - 1) << 1 : ((1u << LIT_BITS) - 1) << 1;
+    // a lane stops only between codes of the literal/length alphabet: at its boundary, or (RECORD) when it has produced
+    // LANE_CAP bytes or DUO_TOK_TRIPS - 1 tokens (hence at most LANE_MCAP matches) — the next lane continues from there
+    uint32_t stop = pos >= lim ? 1u : 0u;
+    if (RECORD) stop |= (o >= (uint32_t)LANE_CAP ? 1u : 0u) | (trips >= (uint32_t)DUO_TOK_TRIPS - 1 ? 1u : 0u);
+    run &= ~(eob | (st ? 0u : stop));
   }
   if (fl == 0 && active && pos >= c.total_bits && pos < limit) fl = F_INEND;   // ran out of input before its boundary
   end = pos;
@@ -191,6 +204,23 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
+// -DBIODB_DUO_TIMING: cycles per phase, summed over blocks (lane 0 of each warp), read back through
+// biodb_debug_inflate_counters slots of inflate_duo_cycles(): decoder [0] round 1, [1] waiting for the resolver,
+// [2] rounds >= 2, [3] headers + tables, [4] waiting for input (TMA), [5] total; resolver [8] waiting for the decoder,
+// [9] replay, [10] matches, [11] walker + flush, [12] total.
+#ifdef BIODB_DUO_TIMING
+__device__ unsigned long long g_duo_cycles[16];
+#define T_DECL(n) long long _t_##n = 0
+#define T_ON(n) _t_##n -= clock64()
+#define T_OFF(n) _t_##n += clock64()
+#define T_PUT(n, slot) atomicAdd(&g_duo_cycles[slot], (unsigned long long)_t_##n)
+#else
+#define T_DECL(n)
+#define T_ON(n)
+#define T_OFF(n)
+#define T_PUT(n, slot)
+#endif
+
 // ====================================================================================== decoder warp ====
 __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const uint32_t blk, const int lane,
                                          unsigned long long* counters) {
@@ -203,8 +233,6 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
   const uint32_t in_ring = sbase + (uint32_t)offsetof(DuoSmem, in_ring);
   const uint32_t lutd = sbase + (uint32_t)offsetof(DuoSmem, lut_dist);
   const uint32_t mbar = sbase + (uint32_t)offsetof(DuoSmem, mbar);
-  const uint32_t bar_full = sbase + (uint32_t)offsetof(DuoSmem, bar_full);
-  const uint32_t bar_free = sbase + (uint32_t)offsetof(DuoSmem, bar_free);
   DCtx ctx;
   ctx.in_ring = in_ring;
   ctx.lutl = sbase + (uint32_t)offsetof(DuoSmem, lut_lit);
@@ -254,21 +282,15 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
 
   // ---- messages to the resolver ---------------------------------------------------------------------------------
   bool owe = false;         // a message is out whose consumption has not been waited for
-  uint32_t fpar = 0;
   auto wait_free = [&]() {
     if (owe) {
-      mbar_wait(bar_free, fpar);
-      fpar ^= 1;
+      bar_await(BAR_FREE);
       owe = false;
     }
   };
   auto send = [&](uint32_t kind, uint32_t x, uint32_t y) {     // msg_lane[] (if any) is already written
     if (lane == 0) { s->msg_kind = kind; s->msg_a = x; s->msg_b = y; }
-    __syncwarp();
-    if (lane == 0) {
-      __threadfence_block();
-      mbar_arrive(bar_full);
-    }
+    bar_signal(BAR_FULL);
     owe = true;
   };
 
@@ -280,10 +302,15 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
   uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0;
   uint32_t produced = 0;    // bytes handed to the resolver so far
 
+  T_DECL(r1); T_DECL(wf); T_DECL(r2); T_DECL(hd); T_DECL(in); T_DECL(tot);
+  T_ON(tot);
   bool last = false;
   while (!last && status == 0) {
     // ---- block header (warp-uniform, from a 64-bit register bit buffer) ----------------------------------
+    T_ON(in);
     ensure_input(pos >> 3, (pos >> 3) + HDR_BYTES);
+    T_OFF(in);
+    T_ON(hd);
     ++n_dblocks;
     uint64_t bb;
     int bc;
@@ -301,9 +328,10 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
     last = bb & 1;
     const int btype = (int)((bb >> 1) & 3);
     HDROP(3);
-    if (btype == 3) { status = STATUS_RETRY; break; }
+    if (btype == 3) { status = STATUS_RETRY; T_OFF(hd); break; }
 
     if (btype == 0) {
+      T_OFF(hd);
       // ---- stored block: the resolver copies the bytes out of the staging ring, piece by piece -----------
       pos = (HPOS() + 7) & ~7u;
       ensure_input(pos >> 3, (pos >> 3) + 4);
@@ -412,6 +440,7 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
       if (r < 0) { status = STATUS_RETRY; break; }
     }
     __syncwarp();
+    T_OFF(hd);
 #undef HFILL
 #undef HDROP
 #undef HPOS
@@ -421,15 +450,22 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
     while (!eob) {
       if (s->r_bad) { status = STATUS_RETRY; break; }        // the resolver met a distance that reaches before the block
       const uint32_t base = pos;
+      T_ON(in);
       ensure_input(base >> 3, (base >> 3) + SUPER_BYTES + 24);
+      T_OFF(in);
       const uint32_t lim = base + (uint32_t)(lane + 1) * SUB_BITS;
       uint32_t t = base + (uint32_t)lane * SUB_BITS;
       uint32_t e_, out_, nm_, nt_, fl_;
       // round 1: where does the chain cross into each sub-sequence?  (bit positions only)
+      T_ON(r1);
       lane_decode<false>(ctx, true, t, lim, e_, out_, nm_, nt_, fl_);
+      T_OFF(r1);
       ++n_super;
       // round 2: every lane from where its predecessor ended, recording tokens — the token area must be free
+      T_ON(wf);
       wait_free();
+      T_OFF(wf);
+      T_ON(r2);
       {
         uint32_t tn = __shfl_up_sync(0xffffffffu, e_, 1);
         if (lane == 0) tn = base;
@@ -459,6 +495,7 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
         }
         ++rounds;
       }
+      T_OFF(r2);
       n_rounds += rounds;
       // commit the longest prefix of lanes that fits the output ring and the match list
       const uint32_t ncand = kstop < 32 ? kstop + 1 : vcut;
@@ -483,9 +520,13 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
   while (waited < issued) wait_chunk(waited);
 
   if (status == 0 && (produced != isize || pos > total_bits)) status = STATUS_RETRY;
+  T_ON(wf);
   wait_free();
+  T_OFF(wf);
   send(MSG_DONE, (uint32_t)status, 0);
+  T_OFF(tot);
   if (lane == 0) {
+    T_PUT(r1, 0); T_PUT(wf, 1); T_PUT(r2, 2); T_PUT(hd, 3); T_PUT(in, 4); T_PUT(tot, 5);
     atomicAdd(&counters[1], (unsigned long long)n_super);
     atomicAdd(&counters[2], (unsigned long long)n_rounds);
     atomicAdd(&counters[5], (unsigned long long)n_dblocks);
@@ -506,8 +547,6 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
   const uint32_t in_ring = sbase + (uint32_t)offsetof(DuoSmem, in_ring);
   const uint32_t mld = sbase + (uint32_t)offsetof(DuoSmem, m_ld);
   const uint32_t mpos = sbase + (uint32_t)offsetof(DuoSmem, m_pos);
-  const uint32_t bar_full = sbase + (uint32_t)offsetof(DuoSmem, bar_full);
-  const uint32_t bar_free = sbase + (uint32_t)offsetof(DuoSmem, bar_free);
   const uint16_t* tok = a.tok + (size_t)blk * (DUO_TOK_TRIPS * 32) + lane;
 
   uint32_t o = oa;          // oa + bytes produced: ring index is (o & POM)
@@ -542,18 +581,17 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
     const uint32_t fe = OPOS() - (o & (FLUSH_ALIGN - 1));
     if (fe > flushed && fe <= OPOS()) flush_to(fe);
   };
-  auto release = [&]() {                      // message, tokens and stored input bytes are consumed
-    __syncwarp();
-    if (lane == 0) mbar_arrive(bar_free);
-  };
+  auto release = [&]() { bar_signal(BAR_FREE); };   // message, tokens and stored input bytes are consumed
 
-  uint32_t par = 0;
   uint32_t n_far = 0, n_matches = 0;
   bool bad = false;
   int dstatus = 0;
+  T_DECL(wm); T_DECL(rp); T_DECL(mt); T_DECL(fw); T_DECL(rt);
+  T_ON(rt);
   while (true) {
-    mbar_wait(bar_full, par);
-    par ^= 1;
+    T_ON(wm);
+    bar_await(BAR_FULL);
+    T_OFF(wm);
     const uint32_t kind = s->msg_kind, ma = s->msg_a, mb = s->msg_b;
     if (kind == MSG_DONE) { dstatus = (int)ma; break; }
     if (kind == MSG_STORED) {
@@ -576,6 +614,7 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
     const uint32_t n_match = __shfl_sync(0xffffffffu, inc_nm, 31);
     const uint32_t max_nt = __reduce_max_sync(0xffffffffu, nt_);
     const uint32_t opos0 = OPOS();
+    T_ON(rp);
     if (!bad) {
       // replay: literals into the ring, matches into the list
       uint32_t oo = o + (inc_out - out_);               // ring-relative position of this lane's next byte
@@ -603,6 +642,8 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
       }
     }
     release();
+    T_OFF(rp);
+    T_ON(mt);
     if (!bad) {
       // LZ77 copies, 32 list entries at a time (one per lane, handed around by shuffles)
       const uint32_t opos_end = opos0 + chunk_out;
@@ -667,9 +708,13 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
       if (bad && lane == 0) s->r_bad = 1;      // the decoder stops at its next super-chunk
       n_matches += n_match;
     }
+    T_OFF(mt);
     o += chunk_out;
+    T_ON(fw);
     if (!bad) produced();
+    T_OFF(fw);
   }
+  T_OFF(rt);
 
   const int status = (dstatus != 0 || bad) ? STATUS_RETRY : 0;
   if (status == 0) {
@@ -682,6 +727,7 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
     if (status) atomicAdd(&counters[0], 1ull);
     atomicAdd(&counters[3], (unsigned long long)n_far);
     atomicAdd(&counters[4], (unsigned long long)n_matches);
+    T_PUT(wm, 8); T_PUT(rp, 9); T_PUT(mt, 10); T_PUT(fw, 11); T_PUT(rt, 12);
   }
 #undef OPOS
 }
@@ -697,11 +743,7 @@ __global__ void __launch_bounds__(64, BIODB_DUO_MIN_CTAS) inflate_duo_kernel(Inf
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t blk = blockIdx.x;
   if (blk >= a.n_blocks) return;
-  if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&s->bar_full), 1);
-    mbar_init(smem_u32(&s->bar_free), 1);
-    s->r_bad = 0;
-  }
+  if (threadIdx.x == 0) s->r_bad = 0;
   if (threadIdx.x < NCH) mbar_init(smem_u32(&s->mbar[threadIdx.x]), 1);
   if (warp == 0) {
     uint32_t b, eb;
@@ -730,6 +772,21 @@ cudaError_t inflate_duo_counters(unsigned long long* out8, int reset) {
     e = cudaMemcpyToSymbol(g_duo_counters, z, sizeof(z));
   }
   return e;
+}
+
+// phase cycle counters of a -DBIODB_DUO_TIMING build (zeros otherwise)
+cudaError_t inflate_duo_cycles(unsigned long long* out16, int reset) {
+#ifdef BIODB_DUO_TIMING
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_duo_cycles, sizeof(g_duo_cycles));
+  if (e == cudaSuccess && reset) {
+    unsigned long long z[16] = {0};
+    e = cudaMemcpyToSymbol(g_duo_cycles, z, sizeof(z));
+  }
+  return e;
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  return cudaSuccess;
+#endif
 }
 
 size_t inflate_duo_token_bytes(uint32_t n_blocks) { return (size_t)n_blocks * DUO_TOK_TRIPS * 32 * sizeof(uint16_t); }

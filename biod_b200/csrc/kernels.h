@@ -29,6 +29,8 @@ struct WalkOut {
   uint32_t in0;       // entry offset inside block 0 (bytes of header in front of the first record)
   uint64_t u_len;     // length of the whole slice
   int32_t n_refs;     // reference count of the file (plausibility of refID fields)
+  int32_t search0;    // 1 = the chain's entry into block 0 is not known either (a pass that starts at a block boundary of
+                      // a file whose records straddle blocks): block 0 searches for it like every later block
 };
 enum { WALK_OK = 0, WALK_TAIL = 1, WALK_BAD_SIZE = 2, WALK_BAD_FIELDS = 3, WALK_INCOMPLETE = 4 };
 
@@ -55,6 +57,7 @@ cudaError_t launch_inflate_duo(const InflateArgs& a, cudaStream_t st);
 size_t inflate_duo_token_bytes(uint32_t n_blocks);
 int inflate_duo_resident_blocks(int device);
 cudaError_t inflate_duo_counters(unsigned long long* out8, int reset);
+cudaError_t inflate_duo_cycles(unsigned long long* out16, int reset);
 int inflate_par_resident_blocks(int device);
 // inflate_par.cu: the lane-parallel kernel alone; blocks it cannot finish get status STATUS_RETRY (inflate_common.cuh)
 cudaError_t launch_inflate_par(const InflateArgs& a, cudaStream_t st);

@@ -540,15 +540,36 @@ __global__ void carry_copy_kernel(ReadsView v, uint32_t g0, const int32_t* block
   for (uint32_t i = lane; i < n; i += 32) out.data[dst + i] = src[i];
 }
 
-// shard halo check: max end_pos over records [0, *n_all) / [0, *n_head) with the given reference
-__global__ void max_end_kernel(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, uint32_t n_all,
-                               const uint64_t* n_head_ptr, int32_t ref, int32_t* out /*[2]*/) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_all) return;
-  int32_t e = end_pos[i];
-  if (ref_id[i] != ref || e <= pos[i]) return;
-  atomicMax(&out[0], e);
-  if ((uint64_t)i < *n_head_ptr) atomicMax(&out[1], e);
+// shard bookkeeping: number of records of the batch that start before slice offset x (rec_off ascends)
+__global__ void count_below_kernel(const uint64_t* __restrict__ rec_off, uint32_t n, uint64_t x, uint64_t* out) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t m = (lo + hi) >> 1;
+    if (rec_off[m] < x) lo = m + 1; else hi = m;
+  }
+  *out = lo;
+}
+
+// Exact halos (include/biod_b200.h, biodb_pileup_shard_reach): for each of the nk later shard boundaries (ascending
+// (ref, pos) keys), the smallest slice offset of an own record [first, n) that reaches across it — same reference and
+// end_position beyond the boundary's position.  A read that does not reach boundary k reaches no later one.
+__global__ void reach_kernel(const int32_t* __restrict__ ref_id, const int32_t* __restrict__ pos,
+                             const int32_t* __restrict__ end_pos, const uint64_t* __restrict__ rec_off, uint32_t first, uint32_t n,
+                             const int32_t* __restrict__ kref, const int64_t* __restrict__ kpos, uint32_t nk,
+                             unsigned long long* reach) {
+  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t e = end_pos[i], r = ref_id[i];
+  if (e <= pos[i] || r < 0) return;                 // covers no position: not a read of any pileup
+  for (uint32_t k = 0; k < nk; ++k) {
+    const int32_t br = kref[k];
+    if (br == r) {
+      if ((int64_t)e > kpos[k]) atomicMin(&reach[k], (unsigned long long)rec_off[i]);
+      else break;
+    } else if (br < 0 || br > r) {
+      break;                                        // boundary on a later reference (or among the unmapped reads)
+    }
+  }
 }
 
 template <typename K, typename... A>
@@ -565,9 +586,15 @@ void pileup_find_groups(const ReadsView& v, uint32_t* boundaries, uint32_t* n_bo
   if (v.n > 1) launch1d(find_groups_kernel, v.n - 1, st, v, boundaries, n_boundaries, cap);
 }
 
-void pileup_max_end(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, uint32_t n, const uint64_t* n_head_ptr,
-                    int32_t ref, int32_t* out, cudaStream_t st) {
-  launch1d(max_end_kernel, n, st, ref_id, pos, end_pos, n, n_head_ptr, ref, out);
+void pileup_count_below(const uint64_t* rec_off, uint32_t n, uint64_t x, uint64_t* out, cudaStream_t st) {
+  count_below_kernel<<<1, 1, 0, st>>>(rec_off, n, x, out);
+  ++g_kernel_launches;
+}
+
+void pileup_reach(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, const uint64_t* rec_off, uint32_t first,
+                  uint32_t n, const int32_t* kref, const int64_t* kpos, uint32_t nk, unsigned long long* reach, cudaStream_t st) {
+  if (first >= n || nk == 0) return;
+  launch1d(reach_kernel, n - first, st, ref_id, pos, end_pos, rec_off, first, n, kref, kpos, nk, reach);
 }
 
 void pileup_first_kept(const ReadsView& v, uint32_t g0, uint32_t g1, uint64_t start_from, uint32_t* first, cudaStream_t st) {

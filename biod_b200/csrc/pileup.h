@@ -101,8 +101,9 @@ void md_replay(const ReadsView& v, const int32_t* block_size, const MdSeg* segs,
 // materialise the dna() of new_keep.id[k] (len[k] characters) into new_keep.data[k]
 void md_keep(const ReadsView& v, const int32_t* block_size, const MdKeep& old_keep, const MdKeep& new_keep, cudaStream_t st);
 
-void pileup_max_end(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, uint32_t n, const uint64_t* n_head_ptr,
-                    int32_t ref, int32_t* out, cudaStream_t st);
+void pileup_count_below(const uint64_t* rec_off, uint32_t n, uint64_t x, uint64_t* out, cudaStream_t st);
+void pileup_reach(const int32_t* ref_id, const int32_t* pos, const int32_t* end_pos, const uint64_t* rec_off, uint32_t first,
+                  uint32_t n, const int32_t* kref, const int64_t* kpos, uint32_t nk, unsigned long long* reach, cudaStream_t st);
 void pileup_find_groups(const ReadsView& v, uint32_t* boundaries, uint32_t* n_boundaries, uint32_t cap, cudaStream_t st);
 void pileup_first_kept(const ReadsView& v, uint32_t g0, uint32_t g1, uint64_t start_from, uint32_t* first, cudaStream_t st);
 void pileup_phase1(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t drop_before, int skip_zero, int64_t clo,

@@ -72,10 +72,14 @@ struct biodb_pileup {
   // shard mode (biodb_pileup_begin_shard)
   bool sharded = false;
   biodb_shard_info shard{};
-  uint32_t halo_blocks_left = 0;     // halo blocks not yet seen by the scanner
-  uint64_t index_bias = 0;           // records of the halo: read_idx counts from the shard's first own record
-  uint64_t tail_coffset = 0;         // first block of the shard's last `halo_blocks` blocks
-  DevBuf d_maxend;                   // [2] int32 maxima + u64 scratch
+  bool own_reached = false;          // the first own record has been met: index_bias is final
+  uint64_t index_bias = 0;           // records of the halo: read_idx counts from the first record read
+  uint32_t shard_index = 0, shard_count = 0;
+  std::vector<int32_t> later_ref;    // (ref, pos) of the cuts behind this shard, i.e. of shards shard_index+1 ...
+  std::vector<int64_t> later_pos;
+  std::vector<uint64_t> reach;       // [shard_count] first own record reaching into each later shard (voffset), ~0 = none
+  DevBuf d_later, d_reach;           // the keys / the per-batch minima on the device
+  PinBuf h_reach;
   DevBuf pack_tmp;                   // scan scratch of the base packing (compact_reads)
   // reference bases from MD tags (use_md_tag; mdtag.cu, md_chain.h)
   std::unique_ptr<MdChain> md;       // which read's dna() serves which positions; its state runs across batches
@@ -262,27 +266,46 @@ static biodb_status load_batch(biodb_pileup* pl) {
     biodb_status rs = region_reduce(pl, c.n);
     if (rs != BIODB_OK) return rs;
   }
-  if (pl->sharded && pl->halo_blocks_left && p.blocks.size()) {
-    // records that start in the halo blocks: rec_base[h] of the scan workspace (the halo is the head of the first batch)
-    uint32_t hb = std::min<uint32_t>(pl->halo_blocks_left, (uint32_t)p.blocks.size());
-    const ScanWorkspace& w = p.ws_cur;
-    uint64_t* hh = (uint64_t*)pl->h_small.p;
-    PL_TRY(launch_copy_bytes(hh + 8, w.rec_base + hb + p.ws_carry, 8, p.st));
-    PL_TRY(cudaStreamSynchronize(p.st));
-    pl->index_bias += hh[8];
-    pl->shard.n_halo_records = pl->index_bias;
-    pl->halo_blocks_left -= hb;
-  }
   if (pl->sharded && p.n) {
-    // halo check: largest end among this batch's own records on hi_ref, over all and over those that start before
-    // the shard's tail blocks.  Records of the halo (index < bias) may be included: they only raise the bound.
-    const uint32_t off = p.ws_carry;
-    uint32_t nbt = 0;
-    while (nbt < p.blocks.size() && p.blocks[nbt].coffset < pl->tail_coffset) ++nbt;
-    const ScanWorkspace& w = p.ws_cur;
-    RecordArrays a = p.arrays(c.n);
-    pileup_max_end(a.ref_id, a.pos, a.end_pos, (uint32_t)p.n, w.rec_base + nbt + off, pl->shard.hi_ref,
-                   pl->d_maxend.as<int32_t>(), p.st);
+    // which of this batch's records are the shard's own (start at or after its first voffset)?
+    uint64_t first_own = 0;                                  // index within the batch
+    if (!pl->own_reached) {
+      const uint64_t oc = pl->shard.first_voffset >> 16, ou = pl->shard.first_voffset & 0xFFFF;
+      uint64_t x = ~0ull;                                    // slice offset of the first own byte
+      for (const Seg& sg : p.segs) {
+        if (sg.coffset > oc) { x = sg.ustart; break; }       // (only when the voffset was a block end)
+        if (sg.coffset == oc && ou >= sg.within && ou < (uint64_t)sg.within + sg.len) { x = sg.ustart + (ou - sg.within); break; }
+      }
+      if (x == ~0ull) {
+        first_own = p.n;                                     // the whole batch is halo
+      } else {
+        uint64_t* hh = (uint64_t*)pl->h_small.p;
+        RecordArrays a = p.arrays(c.n);
+        pileup_count_below(a.rec_off, (uint32_t)p.n, x, (uint64_t*)pl->info.p + 4, p.st);
+        PL_TRY(launch_copy_bytes(hh + 8, (uint64_t*)pl->info.p + 4, 8, p.st));
+        PL_TRY(cudaStreamSynchronize(p.st));
+        first_own = hh[8];
+        pl->own_reached = true;
+      }
+      pl->index_bias += first_own;
+      pl->shard.n_halo_records = pl->index_bias;
+    }
+    // exact halos: the first own record that reaches across each later cut
+    const uint32_t nk = (uint32_t)pl->later_ref.size();
+    if (nk && first_own < p.n) {
+      RecordArrays a = p.arrays(c.n);
+      PL_TRY(cudaMemsetAsync(pl->d_reach.p, 0xff, (size_t)nk * 8, p.st));
+      pileup_reach(a.ref_id, a.pos, a.end_pos, a.rec_off, (uint32_t)first_own, (uint32_t)p.n, pl->d_later.as<int32_t>(),
+                   (const int64_t*)(pl->d_later.as<uint8_t>() + (((size_t)nk * 4 + 7) & ~(size_t)7)), nk,
+                   pl->d_reach.as<unsigned long long>(), p.st);
+      PL_TRY(launch_copy_bytes(pl->h_reach.p, pl->d_reach.p, (size_t)nk * 8, p.st));
+      PL_TRY(cudaStreamSynchronize(p.st));
+      const uint64_t* hr = pl->h_reach.as<uint64_t>();
+      for (uint32_t k = 0; k < nk; ++k) {
+        uint64_t& slot = pl->reach[pl->shard_index + 1 + k];
+        if (hr[k] != ~0ull && slot == ~0ull) slot = p.voffset_of(hr[k]);   // batches come in file order: the first hit is the minimum
+      }
+    }
   }
   pl->first_index = first;      // shard mode: counted from the first halo record; the stitch subtracts n_halo_records
   pl->n_carry_view = c.n;
@@ -376,8 +399,12 @@ void biodb_pileup::reset(const biodb_pileup_params* p) {
   last_done = nullptr;
   sharded = false;
   memset(&shard, 0, sizeof shard);
-  halo_blocks_left = 0;
+  own_reached = false;
   index_bias = 0;
+  shard_index = shard_count = 0;
+  later_ref.clear();
+  later_pos.clear();
+  reach.clear();
   region = region_done = false;
   chunks.clear();
   chunk_i = 0;
@@ -475,95 +502,190 @@ biodb_status biodb_pileup_begin_region(biodb_reader* r, const biodb_index* ix, u
   return BIODB_OK;
 }
 
-// (ref, pos) of the first record that starts in the block at `coffset` (assumed to be a record boundary).
-static biodb_status peek_first_record(biodb_reader* r, uint64_t coffset, int32_t* ref, int64_t* pos) {
+// The first record that starts in or after the BGZF block at `coffset`: its virtual offset, reference and position.
+// In a file whose records straddle blocks the chain's entry into the block is searched for (Pass::entry_search).
+// *vo = ~0 when no record follows.
+static biodb_status peek_first_record(biodb_reader* r, uint64_t coffset, uint64_t* vo, int32_t* ref, int64_t* pos) {
+  *vo = ~0ull; *ref = -1; *pos = INT64_MAX;
   Pass p;
-  biodb_status s = p.init(r, coffset, 0);
+  const bool at_start = coffset == r->reads_start_coffset;
+  biodb_status s = p.init(r, coffset, at_start ? r->reads_start_uoffset : 0);
   if (s != BIODB_OK) return s;
-  s = p.next(1, 0);
-  if (s != BIODB_OK) return s;
-  if (p.n == 0) { *ref = -1; *pos = 0; return BIODB_OK; }
-  int32_t h[2];
+  p.entry_search = !at_start;
+  for (int tries = 0; tries < 64; ++tries) {
+    s = p.next(4, 0);
+    if (s == BIODB_EOF) return BIODB_OK;
+    if (s != BIODB_OK) return s;
+    if (p.n) break;
+    if (p.finished) return BIODB_OK;
+  }
+  if (p.n == 0) return BIODB_OK;
   RecordArrays a = p.arrays(0);
+  int32_t h[2];
+  uint64_t off = 0;
   if (cudaMemcpy(&h[0], a.ref_id, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
-      cudaMemcpy(&h[1], a.pos, 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+      cudaMemcpy(&h[1], a.pos, 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      cudaMemcpy(&off, a.rec_off, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
     return p.fail(BIODB_ERR_CUDA, 0, 0, "peek failed");
+  *vo = p.voffset_of(off);
   *ref = h[0];
   *pos = h[1];
   return BIODB_OK;
 }
 
-biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
-                                      uint32_t halo_blocks, biodb_pileup** out) {
-  if (!r || !out || n_shards == 0 || shard >= n_shards) return BIODB_ERR_ARG;
-  // the chain of MD providers depends on every read since the start of the reference: a shard cannot know it
-  if (prm && prm->use_md_tag) return BIODB_ERR_ARG;
+// biodb_shard_cuts: cut k = the first record in or after the block at compressed-byte fraction k/n of the data blocks
+static biodb_status shard_cuts(biodb_reader* r, uint32_t n_shards, const biodb_reader::ShardCuts** out) {
+  for (const auto& c : r->shard_cuts)
+    if (c.n == n_shards) { *out = &c; return BIODB_OK; }
+  biodb_status s = r->build_block_index();
+  if (s != BIODB_OK) return s;
+  const std::vector<uint64_t>& bi = r->block_index;
+  const size_t nb = bi.size();
+  const uint64_t end_vo = r->data_end_coffset << 16;
+  biodb_reader::ShardCuts c;
+  c.n = n_shards;
+  for (uint32_t k = 0; k <= n_shards; ++k) {
+    uint64_t vo = end_vo;
+    int32_t ref = -1;
+    int64_t pos = INT64_MAX;
+    if (k < n_shards && nb) {
+      size_t b = 0;
+      if (k > 0) {
+        const uint64_t a = bi[0], z = r->data_end_coffset;
+        const uint64_t target = a + (uint64_t)((double)(z - a) * k / n_shards);
+        b = (size_t)(std::lower_bound(bi.begin(), bi.end(), target) - bi.begin());
+      }
+      if (b < nb) {
+        s = peek_first_record(r, bi[b], &vo, &ref, &pos);
+        if (s != BIODB_OK) return s;
+        if (vo == ~0ull) { vo = end_vo; ref = -1; pos = INT64_MAX; }
+      }
+    }
+    if (!c.vo.empty() && vo < c.vo.back()) vo = c.vo.back();      // (cuts never run backwards)
+    c.vo.push_back(vo);
+    c.ref.push_back(ref);
+    c.pos.push_back(pos);
+  }
+  r->shard_cuts.push_back(std::move(c));
+  *out = &r->shard_cuts.back();
+  return BIODB_OK;
+}
+
+biodb_status biodb_shard_cuts(biodb_reader* r, uint32_t n_shards, uint64_t* cut_voffset, int32_t* cut_ref, int64_t* cut_pos) {
+  if (!r || n_shards == 0) return BIODB_ERR_ARG;
+  const biodb_reader::ShardCuts* c = nullptr;
+  biodb_status s = shard_cuts(r, n_shards, &c);
+  if (s != BIODB_OK) return s;
+  for (uint32_t k = 0; k <= n_shards; ++k) {
+    if (cut_voffset) cut_voffset[k] = c->vo[k];
+    if (cut_ref) cut_ref[k] = c->ref[k];
+    if (cut_pos) cut_pos[k] = c->pos[k];
+  }
+  return BIODB_OK;
+}
+
+// common part of the shard / range passes: read [from_vo, to_vo), own records from own_vo on, columns in [lo, hi)
+static biodb_status begin_clipped(biodb_reader* r, const biodb_pileup_params* prm, uint64_t from_vo, uint64_t own_vo, uint64_t to_vo,
+                                  int32_t lo_ref, int64_t lo_pos, int32_t hi_ref, int64_t hi_pos, biodb_pileup** out) {
   biodb_pileup_params p2;
   if (prm) p2 = *prm; else { memset(&p2, 0, sizeof p2); p2.skip_zero_coverage = 1; }
   p2.single_ref = 0;                       // pileupColumns semantics
   p2.start_from = 0;
   p2.end_at = ~0ull;
-  biodb_status s = r->build_block_index();
-  if (s != BIODB_OK) return s;
-  const std::vector<uint64_t>& bi = r->block_index;
-  const size_t nb = bi.size();
-  // cut points at equal compressed-byte fractions of the data blocks
-  auto cut = [&](uint32_t k) -> size_t {
-    if (k == 0) return 0;
-    if (k >= n_shards || nb == 0) return nb;
-    const uint64_t a = bi[0], z = r->data_end_coffset;
-    const uint64_t target = a + (uint64_t)((double)(z - a) * k / n_shards);
-    return (size_t)(std::lower_bound(bi.begin(), bi.end(), target) - bi.begin());
-  };
-  const size_t b0 = cut(shard), b1 = cut(shard + 1);
-  biodb_shard_info sh{};
-  sh.first_coffset = b0 < nb ? bi[b0] : r->data_end_coffset;
-  sh.end_coffset = b1 < nb ? bi[b1] : r->data_end_coffset;
-  const size_t hb = (shard == 0) ? 0 : std::min<size_t>(halo_blocks, b0);
-  sh.halo_coffset = (b0 - hb) < nb ? bi[b0 - hb] : r->data_end_coffset;
-  sh.lo_ref = 0;
-  sh.lo_pos = INT64_MIN;
-  sh.hi_ref = -1;
-  sh.hi_pos = INT64_MAX;
-  if (shard > 0 && b0 < nb) {
-    s = peek_first_record(r, bi[b0], &sh.lo_ref, &sh.lo_pos);
-    if (s != BIODB_OK) return s;
-  } else if (shard > 0) {
-    sh.lo_ref = -1;                        // empty shard at the end of the file
-    sh.lo_pos = INT64_MAX;
-  }
-  if (b1 < nb) {
-    s = peek_first_record(r, bi[b1], &sh.hi_ref, &sh.hi_pos);
-    if (s != BIODB_OK) return s;
-  }
-  s = biodb_pileup_begin(r, &p2, out);
+  biodb_status s = biodb_pileup_begin(r, &p2, out);
   if (s != BIODB_OK) return s;
   biodb_pileup* pl = *out;
   pl->sharded = true;
+  biodb_shard_info sh{};
+  sh.first_voffset = own_vo;
+  sh.end_voffset = to_vo;
+  sh.halo_voffset = from_vo;
+  sh.lo_ref = lo_ref; sh.lo_pos = lo_pos; sh.hi_ref = hi_ref; sh.hi_pos = hi_pos;
   pl->shard = sh;
-  pl->halo_blocks_left = (uint32_t)hb;
-  {
-    const size_t tb = b1 > halo_blocks ? b1 - halo_blocks : 0;
-    pl->tail_coffset = tb < nb ? bi[std::max(tb, b0)] : r->data_end_coffset;
-    int32_t init[2] = {INT32_MIN, INT32_MIN};
-    if (pl->d_maxend.ensure(64) != cudaSuccess || cudaMemcpy(pl->d_maxend.p, init, 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+  pl->own_reached = own_vo <= from_vo;
+  pl->pass.rewind(from_vo >> 16, (uint32_t)(from_vo & 0xFFFF));
+  if (to_vo != ~0ull) {
+    pl->pass.stop_coffset = to_vo >> 16;
+    pl->pass.stop_uoffset = (uint32_t)(to_vo & 0xFFFF);
+  }
+  if (to_vo != ~0ull && to_vo <= from_vo) pl->done = true;     // nothing to read
+  return BIODB_OK;
+}
+
+biodb_status biodb_pileup_begin_range(biodb_reader* r, const biodb_pileup_params* prm, uint64_t from_voffset, uint64_t to_voffset,
+                                      int32_t lo_ref, int64_t lo_pos, int32_t hi_ref, int64_t hi_pos, biodb_pileup** out) {
+  if (!r || !out) return BIODB_ERR_ARG;
+  return begin_clipped(r, prm, from_voffset, from_voffset, to_voffset, lo_ref, lo_pos, hi_ref, hi_pos, out);
+}
+
+static biodb_status begin_shard_common(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
+                                       bool by_blocks, uint32_t halo_blocks, uint64_t halo_vo, biodb_pileup** out) {
+  if (!r || !out || n_shards == 0 || shard >= n_shards) return BIODB_ERR_ARG;
+  const biodb_reader::ShardCuts* c = nullptr;
+  biodb_status s = shard_cuts(r, n_shards, &c);
+  if (s != BIODB_OK) return s;
+  const uint64_t own = c->vo[shard], end = c->vo[shard + 1];
+  uint64_t from = own;
+  if (shard > 0 && by_blocks && halo_blocks) {
+    // a guess: the halo starts halo_blocks BGZF blocks in front of the block the shard's first record starts in
+    const std::vector<uint64_t>& bi = r->block_index;
+    size_t b = (size_t)(std::upper_bound(bi.begin(), bi.end(), own >> 16) - bi.begin());   // blocks at or before own's
+    b = b ? b - 1 : 0;
+    const size_t hb = b > halo_blocks ? b - halo_blocks : 0;
+    if (hb < bi.size() && bi[hb] < (own >> 16)) {
+      int32_t rf; int64_t ps;
+      s = peek_first_record(r, bi[hb], &from, &rf, &ps);
+      if (s != BIODB_OK) return s;
+      if (from > own) from = own;
+    }
+  } else if (shard > 0 && !by_blocks) {
+    from = std::min(halo_vo, own);
+  }
+  // shard 0 also owns whatever precedes its first record's position; the last shard everything to the end
+  const int32_t lo_ref = shard == 0 ? 0 : c->ref[shard];
+  const int64_t lo_pos = shard == 0 ? INT64_MIN : c->pos[shard];
+  s = begin_clipped(r, prm, from, own, end, lo_ref, lo_pos, c->ref[shard + 1], c->pos[shard + 1], out);
+  if (s != BIODB_OK) return s;
+  biodb_pileup* pl = *out;
+  pl->shard_index = shard;
+  pl->shard_count = n_shards;
+  pl->reach.assign(n_shards, ~0ull);
+  for (uint32_t t = shard + 1; t < n_shards; ++t) { pl->later_ref.push_back(c->ref[t]); pl->later_pos.push_back(c->pos[t]); }
+  const size_t nk = pl->later_ref.size();
+  if (nk) {
+    const size_t poff = (nk * 4 + 7) & ~(size_t)7;
+    std::vector<uint8_t> buf(poff + nk * 8);
+    memcpy(buf.data(), pl->later_ref.data(), nk * 4);
+    memcpy(buf.data() + poff, pl->later_pos.data(), nk * 8);
+    if (pl->d_later.ensure(buf.size()) != cudaSuccess || pl->d_reach.ensure(nk * 8) != cudaSuccess ||
+        pl->h_reach.ensure(nk * 8) != cudaSuccess ||
+        cudaMemcpy(pl->d_later.p, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
       biodb_pileup_end(pl);
       return BIODB_ERR_CUDA;
     }
   }
-  pl->pass.rewind(sh.halo_coffset, sh.halo_coffset == r->reads_start_coffset ? r->reads_start_uoffset : 0);
-  pl->pass.stop_coffset = sh.end_coffset;
   return BIODB_OK;
+}
+
+biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
+                                      uint32_t halo_blocks, biodb_pileup** out) {
+  return begin_shard_common(r, prm, shard, n_shards, true, halo_blocks, 0, out);
+}
+
+biodb_status biodb_pileup_begin_shard_at(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
+                                         uint64_t halo_voffset, biodb_pileup** out) {
+  return begin_shard_common(r, prm, shard, n_shards, false, 0, halo_voffset, out);
 }
 
 void biodb_pileup_shard_info(const biodb_pileup* pl, biodb_shard_info* out) {
   if (!pl || !out) return;
   *out = pl->shard;
   out->n_own_records = pl->pass.n_records_total - pl->index_bias;
-  int32_t m[2] = {INT32_MIN, INT32_MIN};
-  if (pl->d_maxend.p) cudaMemcpy(m, pl->d_maxend.p, 8, cudaMemcpyDeviceToHost);
-  out->max_end_all = m[0] == INT32_MIN ? INT64_MIN : m[0];
-  out->max_end_outside_tail = m[1] == INT32_MIN ? INT64_MIN : m[1];
+}
+
+void biodb_pileup_shard_reach(const biodb_pileup* pl, uint64_t* reach) {
+  if (!pl || !reach) return;
+  for (uint32_t t = 0; t < pl->shard_count; ++t) reach[t] = t < pl->reach.size() ? pl->reach[t] : ~0ull;
 }
 
 void biodb_pileup_end(biodb_pileup* pl) {

@@ -202,6 +202,7 @@ void Pass::rewind(uint64_t coffset, uint32_t uoffset) {
   stop_uoffset = 0;
   next_coffset = coffset;
   first_skip = uoffset;
+  entry_search = false;
   pf_c0 = pf_c1 = 0;
   pre_valid = false;
   if (h2d_st) cudaStreamSynchronize(h2d_st);
@@ -394,7 +395,9 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
       // fused record-chain walk: the inflate warps follow the block_size chain of their own block
       ScanWorkspace w0 = carve_scan_workspace(d_ws.p, nsb);
       ia.walk = WalkOut{w0.rel, w0.cnt, w0.ncig, w0.out, w0.in, w0.bad, has_carry ? 1u : 0u,
-                        has_carry ? 0u : (uint32_t)(h_buoff[0]), u_len, (int32_t)r->ref_names.size()};
+                        has_carry ? 0u : (uint32_t)(h_buoff[0]), u_len, (int32_t)r->ref_names.size(),
+                        (entry_search && !has_carry) ? 1 : 0};
+      entry_search = false;
     }
     stage_begin();
     CUDA_TRY(launch_inflate(ia, st));
@@ -1257,6 +1260,15 @@ biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset) {
   unsigned long long v[8];
   if (inflate_counters(v, reset) != cudaSuccess) return BIODB_ERR_CUDA;
   for (int i = 0; i < 8; ++i) out8[i] = v[i];
+  return BIODB_OK;
+}
+
+biodb_status biodb_debug_inflate_cycles(uint64_t* out16, int32_t reset) {
+  if (!out16) return BIODB_ERR_ARG;
+  cudaDeviceSynchronize();
+  unsigned long long v[16];
+  if (inflate_duo_cycles(v, reset) != cudaSuccess) return BIODB_ERR_CUDA;
+  for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return BIODB_OK;
 }
 

@@ -73,6 +73,9 @@ struct biodb_reader {
   std::vector<uint64_t> block_index;
   uint64_t data_end_coffset = 0;
   biodb_status build_block_index();
+  // cuts of the file into n shards (biodb_shard_cuts), kept per n
+  struct ShardCuts { uint32_t n = 0; std::vector<uint64_t> vo; std::vector<int32_t> ref; std::vector<int64_t> pos; };
+  std::vector<ShardCuts> shard_cuts;
 };
 
 namespace biodb { struct VoChunk; }
@@ -93,6 +96,8 @@ struct Pass {
   uint32_t stop_uoffset = 0;          // > 0: the block AT stop_coffset is read too, but only its first stop_uoffset bytes
                                       // belong to the stream (the skip_end of a BAI chunk, inputstream.d:316-322)
   uint32_t first_skip = 0;          // bytes of the first block that precede the first record
+  bool entry_search = false;        // the pass starts at a block boundary that need not be a record boundary: the first
+                                    // block searches for the record chain's entry like every later one (Walker)
   bool supplier_done = false;       // EOF block / end of file reached (inputstream.d:393-394)
   biodb_error pending{};            // error to raise once the blocks before it are consumed
   bool finished = false;

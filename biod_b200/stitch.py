@@ -23,17 +23,31 @@ def stitch_counts(n_columns, n_entries, n_records, device="cpu"):
                 per_rank=[tuple(int(x) for x in row) for row in table])
 
 
-def halo_sufficient(shards):
-    """Exactness check of a sharded pileup (see biodb_shard_info): `shards` = list of shard-info dicts in shard order.
-    True iff no read outside a shard's halo reaches into its column range."""
-    for s in range(1, len(shards)):
-        lo_ref, lo_pos = shards[s]["lo_ref"], shards[s]["lo_pos"]
-        for q in range(s):
-            if shards[q]["hi_ref"] != lo_ref:
-                continue
-            if shards[s]["halo_coffset"] <= shards[q]["first_coffset"]:
-                continue                      # the halo re-reads all of shard q
-            m = shards[q]["max_end_outside_tail"] if q == s - 1 else shards[q]["max_end_all"]
-            if m > lo_pos:
-                return False
-    return True
+NONE = 2**64 - 1
+
+
+def exact_halos(reach_rows, halo_used):
+    """The exact halo check of a sharded pileup (include/biod_b200.h, biodb_pileup_shard_reach).
+    reach_rows[j][t] = virtual offset of shard j's first own record that reaches into shard t's columns (NONE if none);
+    halo_used[t] = where shard t's halo started.  Returns (need, redo): need[t] = the exact start of shard t's halo
+    (NONE when no earlier read reaches it), redo = the shards whose halo started behind that and must be run again with
+    biodb_pileup_begin_shard_at(need[t])."""
+    n = len(halo_used)
+    need = [min([reach_rows[j][t] for j in range(t)], default=NONE) for t in range(n)]
+    redo = [t for t in range(n) if need[t] < halo_used[t]]
+    return need, redo
+
+
+def gather_reach(reach_row, halo_voffset, device="cpu"):
+    """All-gather of every rank's reach row and halo start (one row of world + 1 integers per rank); returns
+    (reach_rows, halo_used) for exact_halos.  Offsets travel as int64 (NONE = -1)."""
+    enc = lambda v: -1 if v >= NONE else int(v)  # noqa: E731
+    dec = lambda v: NONE if v < 0 else int(v)  # noqa: E731
+    mine = torch.tensor([enc(v) for v in reach_row] + [enc(halo_voffset)], dtype=torch.int64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        allv = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(allv, mine)
+        table = torch.stack(allv).cpu().tolist()
+    else:
+        table = [mine.cpu().tolist()]
+    return [[dec(v) for v in row[:-1]] for row in table], [dec(row[-1]) for row in table]

@@ -173,7 +173,7 @@ typedef struct biodb_pileup_params {
   int32_t single_ref;          /* 1 = makePileup (first reference only, pileup.d:490-494); 0 = pileupColumns */
   int32_t skip_zero_coverage;  /* pileup.d:389-392 */
   int32_t use_md_tag;          /* 1 = also reconstruct PileupColumn.reference_base from the reads' MD tags
-                                  (PileupRangeUsingMdTag, pileup.d:522-654); not available for shards */
+                                  (PileupRangeUsingMdTag, pileup.d:522-654) */
   int32_t want_query_offset;   /* 1 = also return PileupRead.query_offset per entry (pileup.d:146-149) */
   uint64_t start_from;         /* pileup.d:482-489,497-504 (single_ref only) */
   uint64_t end_at;             /* pileup.d:505 (single_ref only); UINT64_MAX = none */
@@ -227,30 +227,53 @@ typedef struct biodb_column_batch {
 } biodb_column_batch;
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);
-/* Sharded pileup (pileupChunks semantics, pileup.d:859-1015): shard `shard` of `n_shards` reads a
- * contiguous range of BGZF blocks (cut at equal compressed-byte fractions, which must be record boundaries — true for
- * files written by BioD / htslib unless a record exceeds a block) plus a halo of `halo_blocks` trailing blocks of the
- * previous shard, and emits exactly the columns from the position of its own first read up to (not including) the
- * position of the next shard's first read.  Concatenating the shards' batches in shard order gives the columns of an
- * unsharded biodb_pileup_begin pass; read_idx counts from the first record the shard reads (its first halo record):
- * global index = read_idx - n_halo_records + (records owned by all earlier shards), the base the stitch provides.
- * pileupColumns semantics only. */
+/* Sharded pileup (pileupChunks semantics, pileup.d:859-1015).  The records of the file are cut into
+ * n_shards consecutive ranges at equal compressed-byte fractions: cut k is the first record that starts in or after the
+ * BGZF block at fraction k/n (found by inflating that block and — in files whose records straddle blocks — searching
+ * for the record chain's entry, as the sequential reader does).  Shard s owns the records that start in
+ * [cut s, cut s+1) and emits exactly the columns from the position of its first record up to (not including) the
+ * position of the next shard's first record; it reads, besides its own records, a HALO of earlier records, from
+ * `halo_voffset` on, because reads that start before the shard's first record can reach into its columns.
+ * Concatenating the shards' batches in shard order gives the columns of an unsharded biodb_pileup_begin pass; read_idx
+ * counts from the first record the shard reads (its first halo record): global index = read_idx - n_halo_records +
+ * (records owned by all earlier shards), the base the stitch provides.  pileupColumns semantics; use_md_tag is allowed —
+ * the chain of MD providers then starts at the halo's first read, exactly as BioD's own chunks start theirs at the first
+ * read of makePileup(chain(prev_chunk, chunk), ...) (pileup.d:905-913).
+ *
+ * The halo is EXACT, in two steps (BioD approximates it by 2 x the median read length, pileup.d:941-985):
+ *  1. _begin_shard starts the halo `halo_blocks` BGZF blocks in front of the shard, a guess;
+ *  2. every shard reports, for every LATER shard t, the first of its own records that reaches into t's columns
+ *     (biodb_pileup_shard_reach: same reference as cut t and end_position > cut t's position).  The minimum over the
+ *     earlier shards is the exact start of shard t's halo; a shard whose guess began later than that is run again with
+ *     _begin_shard_at(that voffset).  biod_b200.stitch.run_shards / exact_halos do this (one all-gather of n_shards
+ *     offsets per rank across GPUs). */
 typedef struct biodb_shard_info {
-  uint64_t first_coffset, end_coffset;   /* own block range */
-  uint64_t halo_coffset;                 /* where reading starts */
+  uint64_t first_voffset, end_voffset;   /* own records: those that start in [first, end) */
+  uint64_t halo_voffset;                 /* where reading starts (the start of a record, <= first_voffset) */
   int32_t lo_ref, hi_ref;                /* column keys (ref, pos): [lo, hi) ; ref -1 sorts last */
   int64_t lo_pos, hi_pos;
-  uint64_t n_halo_records;               /* records in the halo blocks (valid after the first batch) */
+  uint64_t n_halo_records;               /* records read in front of the first own one (valid once it has been met) */
   uint64_t n_own_records;                /* records starting in the own range (valid at EOF) */
-  /* halo check (valid at EOF): largest end position among this shard's own reads on reference hi_ref — over all of
-   * them, and over those outside its last `halo_blocks` blocks (which the next shard re-reads as its halo).  The
-   * sharded result equals the sequential one iff, for every later shard s that starts on the same reference,
-   * max_end_outside_tail (previous shard) / max_end_all (earlier shards) <= s.lo_pos.  INT64_MIN when none. */
-  int64_t max_end_all, max_end_outside_tail;
 } biodb_shard_info;
+/* The n_shards + 1 cuts: virtual offset, reference id and position of the record each cut falls on (cut n_shards = the
+ * end of the data: ref -1, position INT64_MAX).  Arrays of n_shards + 1 elements; any may be NULL. */
+biodb_status biodb_shard_cuts(biodb_reader* r, uint32_t n_shards, uint64_t* cut_voffset, int32_t* cut_ref, int64_t* cut_pos);
 biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* p, uint32_t shard, uint32_t n_shards,
                                       uint32_t halo_blocks, biodb_pileup** out);
+/* The same shard with its halo starting at the record at halo_voffset (<= the shard's first record). */
+biodb_status biodb_pileup_begin_shard_at(biodb_reader* r, const biodb_pileup_params* p, uint32_t shard, uint32_t n_shards,
+                                         uint64_t halo_voffset, biodb_pileup** out);
 void biodb_pileup_shard_info(const biodb_pileup* pl, biodb_shard_info* out);
+/* reach[t], t in (shard, n_shards): virtual offset of the first OWN record of this shard that reaches into the columns
+ * of shard t, UINT64_MAX if none does; entries t <= shard are UINT64_MAX.  Valid at EOF.  `reach` has n_shards elements. */
+void biodb_pileup_shard_reach(const biodb_pileup* pl, uint64_t* reach);
+/* The pileup (pileupColumns semantics, use_md_tag allowed) of the records that start in [from_voffset, to_voffset) —
+ * from_voffset the start of a record, to_voffset the start of a record or UINT64_MAX for the end of the file — clipped to
+ * the columns with (ref, position) in [(lo_ref, lo_pos), (hi_ref, hi_pos)); ref -1 sorts last.  This is one element of
+ * BioD's pileupChunks: makePileup(chain(prev_chunk, chunk), use_md_tag, beg, end) (pileup.d:905-913) with from_voffset
+ * the first halo read and [lo, hi) the chunk's column interval.  read_idx counts from the record at from_voffset. */
+biodb_status biodb_pileup_begin_range(biodb_reader* r, const biodb_pileup_params* p, uint64_t from_voffset, uint64_t to_voffset,
+                                      int32_t lo_ref, int64_t lo_pos, int32_t hi_ref, int64_t hi_pos, biodb_pileup** out);
 /* makePileup(bam[ref][beg .. end), use_md_tag, start_from, end_at, skip_zero_coverage) — "any range of reads is
  * acceptable" (examples/read_bam_file.d:22-25, transverse_multiple_bam_files.d:15): the pileup of the reads of
  * reference ref_id that overlap [beg, end), fetched through the BAI index (biodb_reads_begin_region's reads, reduced on
@@ -333,6 +356,9 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
  * out8[0] blocks it gave up on (redone by the warp-serial kernel: malformed or unusual streams), [1] super-chunks,
  * [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks; [6..7] reserved. */
 biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset);
+/* Cycles per phase of the two-warp inflate kernel, summed over blocks — all zero unless the library was built with
+ * -DBIODB_DUO_TIMING (a measurement build; csrc/inflate_duo.cu lists the 16 slots). */
+biodb_status biodb_debug_inflate_cycles(uint64_t* out16, int32_t reset);
 
 /* Host-only building blocks of the MD-tag reference bases (row N1 of the plan, pileup.d:522-654), exported so that the
  * CPU test suite can check them against the oracle.  Neither needs a GPU.

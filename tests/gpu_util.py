@@ -67,16 +67,19 @@ def assert_pileup_equal(g, o):
     assert np.array_equal(g["qoff"], o.qoff)
 
 
-def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, **kw):
+def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, exact=True, **kw):
     """Run every shard of a sharded pileup (one after the other on this GPU) and stitch the column tables the way
-    biod_b200.stitch does across ranks: concatenate in shard order, rebase read_idx by the record counts."""
+    biod_b200.stitch does across ranks: concatenate in shard order, rebase read_idx by the record counts.
+    exact=True: the shards run the way several GPUs run them — all from the halo_blocks guess, then exact_halos says which
+    halos were too short and those shards run again from the exact offset (res["redone"]).  exact=False: the guess only."""
+    from biod_b200.stitch import exact_halos
     rd = BamReader(data, blocks_per_batch=blocks_per_batch)
-    parts, infos = [], []
-    for s in range(n_shards):
-        pos, ref, cov, nstart, ridx, base, qual, qoff = [], [], [], [], [], [], [], []
+
+    def run(s, halo_voffset=None):
+        pos, ref, cov, nstart, ridx, base, qual, qoff, refb = [], [], [], [], [], [], [], [], []
         info = {}
         for b in rd.column_batches(False, want_query_offset=True, copy=True, shard=(s, n_shards), halo_blocks=halo_blocks,
-                                   shard_info=info, **kw):
+                                   halo_voffset=halo_voffset, shard_info=info, **kw):
             pos.append(b.position)
             ref.append(np.full(b.n_columns, b.ref_id, dtype=np.int32))
             cov.append(np.diff(b.col_off).astype(np.uint64))
@@ -85,12 +88,24 @@ def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, **kw):
             base.append(b.base)
             qual.append(b.qual)
             qoff.append(b.query_offset)
-        parts.append((pos, ref, cov, nstart, ridx, base, qual, qoff))
+            if b.reference_base is not None:
+                refb.append(b.reference_base)
+        return (pos, ref, cov, nstart, ridx, base, qual, qoff, refb), info
+
+    parts, infos = [], []
+    for s in range(n_shards):
+        part, info = run(s)
+        parts.append(part)
         infos.append(info)
+    need, redo = exact_halos([i["reach"] for i in infos], [i["halo_voffset"] for i in infos])
+    if exact:
+        for t in redo:
+            parts[t], infos[t] = run(t, need[t])
+            assert infos[t]["halo_voffset"] == need[t]
     rec_base = np.concatenate([[0], np.cumsum([i["n_own_records"] for i in infos])]).astype(np.uint64)
     cat = lambda v, dt: np.concatenate(v) if v else np.zeros(0, dtype=dt)  # noqa: E731
-    out = {k: [] for k in ("col_pos", "col_ref", "cov", "n_start", "read_idx", "base", "qual", "qoff")}
-    for s, (pos, ref, cov, nstart, ridx, base, qual, qoff) in enumerate(parts):
+    out = {k: [] for k in ("col_pos", "col_ref", "cov", "n_start", "read_idx", "base", "qual", "qoff", "ref_base")}
+    for s, (pos, ref, cov, nstart, ridx, base, qual, qoff, refb) in enumerate(parts):
         out["col_pos"] += pos
         out["col_ref"] += ref
         out["cov"] += cov
@@ -100,11 +115,12 @@ def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, **kw):
         out["base"] += base
         out["qual"] += qual
         out["qoff"] += qoff
+        out["ref_base"] += refb
     dts = dict(col_pos=np.uint64, col_ref=np.int32, cov=np.uint64, n_start=np.uint32, read_idx=np.uint32, base=np.uint8,
-               qual=np.uint8, qoff=np.uint32)
+               qual=np.uint8, qoff=np.uint32, ref_base=np.uint8)
     res = {k: cat(v, dts[k]) for k, v in out.items()}
     res["col_off"] = np.concatenate([[0], np.cumsum(res["cov"])]).astype(np.uint64)
     res["shards"] = infos
-    from biod_b200.stitch import halo_sufficient
-    res["halo_ok"] = halo_sufficient(infos)
+    res["redone"] = redo
+    res["halo_ok"] = not redo or exact
     return res

@@ -67,6 +67,11 @@ def test_parse_errors():
         BaiFile(good[:len(good) // 2])
     with pytest.raises(ReadException):
         BaiFile(good[:6])
+    # negative counts are a corrupt index, not an empty table (n_ref, then the first reference's n_bin)
+    import struct
+    for off in (4, 8):
+        with pytest.raises(BamFormatException, match="negative"):
+            BaiFile(good[:off] + struct.pack("<i", -3) + good[off + 4:])
 
 
 def test_last_linear_offset():

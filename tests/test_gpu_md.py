@@ -91,11 +91,3 @@ def test_reference_bases_with_other_encodings():
     assert cols and all(c.reference_base == "N" for c in cols[:50])
     cols = list(pileupColumns(BamReader(data, blocks_per_batch=1), use_md_tag=True))
     assert "".join(c.reference_base for c in cols) == exp
-
-
-def test_shards_refuse_md_tags():
-    from biod_b200 import BamReader
-    rng = np.random.default_rng(3)
-    rd = BamReader(random_pileup(rng, 300, refs=1, block_size=900))
-    with pytest.raises(ValueError):
-        list(rd.column_batches(False, use_md_tag=True, shard=(0, 2)))

@@ -250,23 +250,26 @@ def test_make_pileup_example_invariant_on_gpu():
     assert starting == list(range(29))
 
 
-@pytest.mark.parametrize("name", ["ex1_header.bam", "bins.bam", "b7_295_chunk.bam", "ion_20_chunk.bam"])
-@pytest.mark.parametrize("n_shards,halo", [(2, 8), (3, 2), (5, 8)])
+@pytest.mark.parametrize("name", ["ex1_header.bam", "bins.bam", "b7_295_chunk.bam", "ion_20_chunk.bam", "mg1655_chunk.bam"])
+@pytest.mark.parametrize("n_shards,halo", [(2, 8), (3, 2), (5, 8), (4, 0)])
 def test_sharded_pileup_equals_unsharded(name, n_shards, halo):
-    # shards by BGZF block range + halo; concatenated shard outputs == one sequential pass
+    """SURVEY.md §8e / pileup.d:859-1015: shards + EXACT halos; concatenated shard outputs == one sequential pass.
+    bins.bam holds reads spanning megabases and the *_chunk files pile hundreds of reads on one spot, so a guessed halo
+    of a few blocks is too short there: the shards' reach reports must say so and the re-run from the exact offset must
+    be right — no halo size is ever chosen by hand.  mg1655_chunk.bam is htsjdk-written: its records straddle BGZF
+    blocks, so every cut has to find the record chain's entry first."""
     from gpu_util import gpu_pileup_sharded
     data = fixture_bytes(name)
     o = orc.Bam(data).decode()
     g = gpu_pileup_sharded(data, n_shards, halo_blocks=halo, blocks_per_batch=3)
     assert sum(i["n_own_records"] for i in g["shards"]) == o.n_records
-    if not g["halo_ok"]:
-        # bins.bam holds reads spanning megabases and the *_chunk files pile hundreds of reads on one spot: the
-        # stitch check must notice that a small halo is not enough, and a halo reaching back to the start of
-        # the file must then be exact
-        assert name != "ex1_header.bam"
-        g = gpu_pileup_sharded(data, n_shards, halo_blocks=10**6, blocks_per_batch=3)
-        assert g["halo_ok"]
     assert_pileup_equal(g, o.pileup_columns())
+    if halo == 0 and name != "mg1655_chunk.bam":
+        # without any halo every shard whose first column is covered by an earlier read must have been run again
+        cuts = [(i["lo_ref"], i["lo_pos"]) for i in g["shards"]]
+        covered = [t for t in range(1, n_shards) if g["shards"][t]["n_own_records"] and
+                   np.any((o.ref_id == cuts[t][0]) & (o.pos < cuts[t][1]) & (o.end_pos > cuts[t][1]) & (o.end_pos > o.pos))]
+        assert set(covered) <= set(g["redone"])
 
 
 @pytest.mark.parametrize("skip", [True, False])
@@ -277,8 +280,62 @@ def test_sharded_pileup_synthetic(skip):
     o = orc.Bam(data).decode()
     for n_shards in (2, 4, 7):
         g = gpu_pileup_sharded(data, n_shards, halo_blocks=4, blocks_per_batch=16, skip_zero_coverage=skip)
-        assert g["halo_ok"]
         assert_pileup_equal(g, o.pileup_columns(skip))
+
+
+def test_sharded_pileup_of_a_straddling_file():
+    """htsjdk layout at scale: records cut across BGZF blocks, mixed CIGARs with long N-skips, 6 shards, halo guessed
+    at one block — cuts enter through the plausibility search, exact halos repair the guess."""
+    from gpu_util import gpu_pileup_sharded
+    from tools import bamgen
+    data = bamgen.generate(50000, 2, True, level=1, threads=4, straddle=True).tobytes()
+    o = orc.Bam(data).decode()
+    g = gpu_pileup_sharded(data, 6, halo_blocks=1, blocks_per_batch=7)
+    assert sum(i["n_own_records"] for i in g["shards"]) == o.n_records
+    assert_pileup_equal(g, o.pileup_columns())
+    # the sequential helper of the mirror (exact halos known up front, nothing run twice) gives the same columns
+    from biod_b200 import BamReader
+    rd = BamReader(data, blocks_per_batch=7)
+    n_col = n_ent = 0
+    for _, b in rd.sharded_column_batches(6):
+        n_col += b.n_columns
+        n_ent += b.n_entries
+    p = o.pileup_columns()
+    assert (n_col, n_ent) == (p.n_columns, p.n_entries)
+
+
+def _oracle_shard_with_md(o, info, first_index, skip=True):
+    """What BioD computes for one chunk (pileup.d:905-913): makePileup over the halo reads + the chunk's reads with
+    use_md_tag, clipped to the chunk's column interval."""
+    lo, hi = (info["lo_ref"], info["lo_pos"]), (info["hi_ref"], info["hi_pos"])
+    a = first_index - info["n_halo_records"]
+    b = first_index + info["n_own_records"]
+    p = o.make_pileup_of(np.arange(a, b), 0, 2**64 - 1, skip, use_md_tag=True, single_ref=False)
+    key = lambda r, x: (2**40 if r < 0 else int(r), int(x))  # noqa: E731
+    keep = np.array([key(*lo) <= key(r, x) < key(*hi) for r, x in zip(p.col_ref, p.col_pos.astype(np.int64))], dtype=bool)
+    return p, keep
+
+
+@pytest.mark.parametrize("name", ["illu_20_chunk.bam", "ex1_header.bam", "mg1655_chunk.bam"])
+def test_sharded_pileup_with_md_tags(name):
+    """use_md_tag in shards: every shard's reference bases are those of BioD's own chunk — the provider chain starts
+    at the first halo read (makePileup(chain(prev_chunk, chunk), use_md_tag, beg, end))."""
+    from gpu_util import gpu_pileup_sharded
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    n_shards = 3
+    g = gpu_pileup_sharded(data, n_shards, halo_blocks=1, blocks_per_batch=2, use_md_tag=True)
+    assert_pileup_equal(g, o.pileup_columns())
+    first, want = 0, []
+    for info in g["shards"]:
+        p, keep = _oracle_shard_with_md(o, info, first)
+        want.append(p.ref_base[keep])
+        first += info["n_own_records"]
+    want = np.concatenate(want)
+    assert len(g["ref_base"]) == len(want) == o.pileup_columns().n_columns
+    assert g["ref_base"].tobytes() == want.tobytes()
+    if name == "illu_20_chunk.bam":
+        assert set(want.tobytes()) - {ord("N")}
 
 
 def test_crc_verification():
@@ -426,5 +483,4 @@ def test_sharded_pileup_with_compact_columns():
     data = bamgen.generate(50000, 2, True, level=6, threads=4).tobytes()
     o = orc.Bam(data).decode()
     g = gpu_pileup_sharded(data, 3, halo_blocks=4, blocks_per_batch=8, compact_reads=True)
-    assert g["halo_ok"]
     assert_pileup_equal(g, o.pileup_columns())

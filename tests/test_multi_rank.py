@@ -54,3 +54,45 @@ def test_stitch_single_process():
     from biod_b200.stitch import stitch_counts
     r = stitch_counts(10, 300, 7)
     assert r["world"] == 1 and r["col_base"] == 0 and r["totals"] == (10, 300, 7)
+
+
+def _reach_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from biod_b200.stitch import NONE, exact_halos, gather_reach
+    # rank 0's read at voffset 0x5000 reaches into shard 1, whose halo was guessed at 0x9000: too late
+    reach = [NONE, 0x5000] if rank == 0 else [NONE, NONE]
+    rows, used = gather_reach(reach, 0 if rank == 0 else 0x9000)
+    out.put((rank, exact_halos(rows, used)))
+    dist.destroy_process_group()
+
+
+def test_exact_halo_exchange_two_ranks():
+    """The second collective of the path (include/biod_b200.h, biodb_pileup_shard_reach): every rank learns where the
+    halo of every shard must start, and which shards have to be run again."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_reach_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0] == res[1]
+    need, redo = res[0]
+    assert need[1] == 0x5000 and redo == [1]
+
+
+def test_exact_halos_single_process():
+    sys.path.insert(0, ROOT)
+    from biod_b200.stitch import NONE, exact_halos, gather_reach
+    rows, used = gather_reach([NONE, NONE, NONE], 0)
+    assert rows == [[NONE, NONE, NONE]] and used == [0]
+    # three shards: shard 0 reaches shards 1 and 2, shard 1 reaches shard 2 from further on; shard 2's guess was too short
+    need, redo = exact_halos([[NONE, 100, 120], [NONE, NONE, 300], [NONE, NONE, NONE]], [0, 90, 250])
+    assert need == [NONE, 100, 120] and redo == [2]
