@@ -5,7 +5,10 @@ A step is ONE full pass of the hot path over the synthetic BAM of BASELINE.json 
 (100 M reads, 1 contig, 30x, 150 bp, CIGAR 150M): every BGZF block inflated, every record decoded, every
 pileup column built.  `value` = pileup positions per second with the compressed file already resident in
 HBM and the columns left in HBM; `e2e` = the same pass through the C ABI with the file in (pinned) host
-memory and every column batch copied back to host memory inside the timed region.
+memory and every column batch copied back to host memory inside the timed region.  With N GPUs the ONE file is cut
+into N shards (total work fixed: "strong" scaling), the only collectives being the column-table stitch and the exact-halo
+exchange (biod_b200/stitch.py).  The line also carries the other configs BASELINE.json names: configs[2] (mixed CIGAR)
+at N = 1, configs[3] (24 contigs, mixed CIGAR, scaled) at N > 1.
 
   python bench.py --gpus N --steps K --warmup W            # ours
   python bench.py --impl reference ...                     # restated BioD CPU path on the host cores
@@ -14,6 +17,7 @@ import argparse
 import ctypes as C
 import json
 import os
+import shutil
 import subprocess
 import sys
 import threading
@@ -28,9 +32,10 @@ CONFIGS = {
     # BASELINE.json configs[] index -> recipe
     2: dict(name="configs[1]: 100M-read synthetic BAM, 1 contig, 30x, 150bp, CIGAR 150M", reads=100_000_000, refs=1, mixed=0),
     3: dict(name="configs[2]: 100M-read synthetic BAM, 1 contig, 30x, mixed CIGAR (M/I/D/S/N, 5% indel)", reads=100_000_000, refs=1, mixed=1),
-    # configs[3] is 1 G reads (~130 GB compressed): pass --reads to scale it to what the box's /dev/shm holds
+    # configs[3] is 1 G reads (~130 GB compressed): scaled to what a bench run can generate and hold (the line says so)
     4: dict(name="configs[3]: 1G-read synthetic BAM, 24 contigs, 30x, mixed CIGAR", reads=1_000_000_000, refs=24, mixed=1),
 }
+CFG4_READS_PER_GPU = 12_500_000      # configs[3] inside the default N > 1 line: N x this many reads
 
 
 def parse():
@@ -42,11 +47,13 @@ def parse():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--reads", type=int, default=0, help="override the read count (the line then says so)")
     ap.add_argument("--level", type=int, default=-1, help="zlib level of the synthetic file (-1 = BioD writer default)")
-    ap.add_argument("--blocks-per-batch", type=int, default=0, help="0 = library default (three full waves of the inflate kernel)")
+    ap.add_argument("--blocks-per-batch", type=int, default=0,
+                    help="0 = library default (three full waves of the inflate kernel; fewer waves per batch at N > 1)")
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--straddle", action="store_true", help="htsjdk-style file: records cut across BGZF blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the blocks for the other named configs (config3 / config4)")
     ap.add_argument("--md", action="store_true",
                     help="also time the pass with use_md_tag (reference bases from MD tags, row N1); 1 GPU only")
     ap.add_argument("--cache-dir", default=os.environ.get("BIODB_BENCH_CACHE", "/dev/shm"))
@@ -60,19 +67,15 @@ def dist_env():
     return rank, world, local
 
 
-def world_size():
-    return int(os.environ.get("WORLD_SIZE", "1"))
-
-
-def synth_file(args, cfg, n_reads, rank, barrier):
-    """Generate (rank 0) or load the synthetic BAM; returns a numpy uint8 array."""
+def synth_file(args, config, cfg, n_reads, rank, world, barrier):
+    """Generate (rank 0) or load the synthetic BAM; returns (numpy uint8 array, path, seconds, generated now)."""
     from tools import bamgen
     os.makedirs(args.cache_dir, exist_ok=True)
-    path = os.path.join(args.cache_dir, f"biod_b200_cfg{args.config}_{n_reads}_l{args.level}{'_s' if args.straddle else ''}.bam")
+    path = os.path.join(args.cache_dir, f"biod_b200_cfg{config}_{n_reads}_l{args.level}{'_s' if args.straddle else ''}.bam")
     t0 = time.time()
     made = False
     if rank == 0 and not os.path.exists(path):
-        data = bamgen.generate(n_reads, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + args.config,
+        data = bamgen.generate(n_reads, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + config,
                                straddle=args.straddle)
         made = True
         tmp = path + ".tmp"
@@ -83,13 +86,14 @@ def synth_file(args, cfg, n_reads, rank, barrier):
             # the cache directory cannot hold the file: one GPU works from memory, several need a shared file
             if os.path.exists(tmp):
                 os.remove(tmp)
-            if world_size() == 1:
+            if world == 1:
                 return data, None, time.time() - t0, made
             raise
         del data
     barrier()
-    # N > 1: every rank maps the same file (one copy in the page cache); N = 1: a private copy that can be pinned
-    data = np.fromfile(path, dtype=np.uint8) if world_size() == 1 else np.memmap(path, dtype=np.uint8, mode="c")
+    # N > 1: every rank maps the same file read-only (one copy in the page cache; only the shard's pages are touched);
+    # N = 1: a private copy that can be pinned
+    data = np.fromfile(path, dtype=np.uint8) if world == 1 else np.memmap(path, dtype=np.uint8, mode="r")
     return data, path, time.time() - t0, made
 
 
@@ -127,15 +131,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False):
-    """One full pileup pass (pileupColumns); shard=(rank, world) runs this rank's block-range shard of it.
-    Returns (stats, n_records, n_cols, n_entries)."""
+def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False, halo_voffset=None):
+    """One full pileup pass (pileupColumns); shard=(rank, world) runs this rank's shard of it (halo guessed at 8 BGZF
+    blocks, or starting at halo_voffset).  Returns (stats, n_records, n_cols, n_entries)."""
     p = capi.PileupParams()
     p.single_ref, p.skip_zero_coverage, p.end_at = 0, 1, 2**64 - 1
     p.compact_reads = int(compact)
     p.use_md_tag = int(use_md)
     pl = C.c_void_p()
-    if shard is not None and shard[1] > 1:
+    sharded = shard is not None and shard[1] > 1
+    if sharded and halo_voffset is not None:
+        st = L.biodb_pileup_begin_shard_at(reader, C.byref(p), shard[0], shard[1], int(halo_voffset), C.byref(pl))
+    elif sharded:
         st = L.biodb_pileup_begin_shard(reader, C.byref(p), shard[0], shard[1], 8, C.byref(pl))
     else:
         st = L.biodb_pileup_begin(reader, C.byref(p), C.byref(pl))
@@ -153,12 +160,15 @@ def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False
     nr, nc, ne = C.c_uint64(), C.c_uint64(), C.c_uint64()
     L.biodb_pileup_totals(pl, C.byref(nr), C.byref(nc), C.byref(ne))
     n_rec = nr.value
-    if shard is not None and shard[1] > 1:
+    if sharded:
         si = capi.ShardInfo()
         L.biodb_pileup_shard_info(pl, C.byref(si))
         n_rec = si.n_own_records
         if info is not None:
             info.update({f: getattr(si, f) for f, _ in si._fields_})
+            reach = (C.c_uint64 * shard[1])()
+            L.biodb_pileup_shard_reach(pl, reach)
+            info["reach"] = [int(x) for x in reach]
     L.biodb_pileup_end(pl)
     return s, n_rec, nc.value, ne.value
 
@@ -183,14 +193,176 @@ def run_reads_pass(L, capi, reader):
     return s, n
 
 
-def cpu_reference(args, cfg, threads):
-    """Restated BioD CPU path (oracle) on a bounded prefix of the same workload."""
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def cpu_reference_block(args, config, cfg, threads, runs=1):
+    """Restated BioD CPU path (oracle) on a bounded prefix of the same workload: inflate on `threads` threads
+    (BgzfInputStream's task pool), record walk + pileup on one (readrange.d, pileup.d) — assumed to overlap perfectly.
+    Two pileup figures: `value` materialises every column's bases / qualities / read list (what the GPU path delivers);
+    `lazy` only sweeps — BioD's PileupRange.popFront keeps and advances the live reads and the consumer touches nothing
+    but column.coverage (bases are lazy in BioD, pileup.d:115-134).  The truth for a given consumer lies between."""
     from oracle import oracle as orc
     from tools import bamgen
     n = args.cpu_sample_reads
-    data = bamgen.generate(n, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + args.config)
-    r = orc.cpu_baseline(data, threads, True)
-    return n, r
+    data = bamgen.generate(n, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + config)
+    rs = [orc.cpu_baseline(data, threads, True) for _ in range(runs)]
+    r = rs[-1]
+    t_full = float(np.mean([max(x["t_inflate"], x["t_decode"] + x["t_pileup"]) for x in rs]))
+    t_lazy = float(np.mean([max(x["t_inflate"], x["t_decode"] + x["t_pileup_lazy"]) for x in rs]))
+    t_reads = float(np.mean([max(x["t_inflate"], x["t_decode"]) for x in rs]))
+    d_compilers = [c for c in ("ldc2", "dmd", "gdc") if shutil.which(c)]
+    blk = {"value": r["n_columns"] / t_full, "unit": "positions/s", "cores": threads, "kind": "port",
+           "cpu_model": cpu_model(), "host_cpus": os.cpu_count(),
+           "records_per_sec": r["n_records"] / t_full,
+           "lazy": {"value": r["n_columns"] / t_lazy, "unit": "positions/s",
+                    "what": "sweep only (popFront + coverage), nothing materialised: the floor of what BioD's own consumer pays"},
+           "reads_only_records_per_sec": r["n_records"] / t_reads,
+           "d_compilers_on_box": d_compilers,
+           "sample": (f"first {n} reads of the workload ({r['n_columns']} positions): inflate {r['t_inflate']:.2f}s on "
+                      f"{threads} threads; on one thread record walk {r['t_decode']:.2f}s, pileup {r['t_pileup']:.2f}s materialising "
+                      f"every column / {r['t_pileup_lazy']:.2f}s sweeping only; value assumes inflate overlaps the consumer perfectly"),
+           "note": "restated BioD CPU path (libz, g++ -O3), not the D binary: no D toolchain in this image" +
+                   ("" if not d_compilers else f" (found on the box: {d_compilers}; not used)")}
+    return blk, t_full * 1e3, r
+
+
+def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, barrier, steps, warmup, want_e2e, want_reads_pass,
+            want_md):
+    """The device-resident and the end-to-end measurement of one config.  Returns a dict (rank 0 uses it)."""
+    from biod_b200.stitch import exact_halos, gather_reach, stitch_counts
+    cfg = CONFIGS[config]
+    data, path, t_gen, made = synth_file(args, config, cfg, n_reads, rank, world, barrier)
+    bpb = args.blocks_per_batch or (0 if world == 1 else (-2 if world == 2 else -1))
+
+    def open_reader(resident, device_output, pin):
+        o = capi.Options()
+        L.biodb_default_options(C.byref(o))
+        o.device, o.blocks_per_batch = local, bpb
+        o.resident_input, o.device_output, o.pin_input = int(resident), int(device_output), int(pin)
+        h = C.c_void_p()
+        st = L.biodb_open_memory(data.ctypes.data, data.size, C.byref(o), C.byref(h))
+        if st != capi.OK:
+            raise RuntimeError(L.biodb_open_error().contents.message.decode())
+        return h
+
+    shard = (rank, world)
+    out = {"generated_in_s": round(t_gen, 1), "generated_now": made, "compressed_bytes": int(data.size)}
+
+    def exact_halo_pass(rd, info, **kw):
+        """The halo exchange of a sharded pass: which shards started their halo too late?  Those run again from the
+        exact offset.  Returns (replacement result or None, report)."""
+        if world == 1:
+            return None, {"exact": True, "rerun_shards": [], "exchange_ms": 0.0}
+        t0 = time.time()
+        rows, used = gather_reach(info["reach"], info["halo_voffset"], device="cuda")
+        need, redo = exact_halos(rows, used)
+        ms = (time.time() - t0) * 1e3
+        res = None
+        if rank in redo:
+            res = run_pass(L, capi, rd, shard, info, halo_voffset=need[rank], **kw)
+        return res, {"exact": True, "rerun_shards": redo, "exchange_ms": ms}
+
+    # ---- value: compressed file resident in HBM, columns stay in HBM ------------------------------------
+    rd = open_reader(True, True, False)
+    for _ in range(warmup):
+        run_pass(L, capi, rd, shard)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.time()
+    shard_info = {}
+    runs = [run_pass(L, capi, rd, shard, shard_info) for _ in range(steps)]
+    barrier()
+    wall = time.time() - t0
+    out["clocks"] = sampler.stop()
+    redo_res, halo_report = exact_halo_pass(rd, shard_info)
+    rerun_ms = float(redo_res[0].total_ms) if redo_res else 0.0
+    if redo_res:
+        runs[-1] = redo_res
+    md_runs = None
+    if want_md and world == 1:
+        run_pass(L, capi, rd, shard, use_md=True)
+        md_runs = [run_pass(L, capi, rd, shard, use_md=True) for _ in range(steps)]
+    L.biodb_close(rd)
+    dev_ms = sum(s[0].total_ms for s in runs[:steps])
+    tt = torch.tensor([dev_ms, wall * 1e3, rerun_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, rerun_ms = float(tt[0]), float(tt[1]), float(tt[2])
+    s0, n_rec, n_col, n_ent = runs[-1]
+    # the stitch: every rank learns every shard's column / entry / record counts -> global column offsets, record bases
+    torch.cuda.synchronize()
+    t0 = time.time()
+    stc = stitch_counts(n_col, n_ent, n_rec, device="cuda")
+    torch.cuda.synchronize()
+    stitch_ms = (time.time() - t0) * 1e3
+    tot_col, tot_ent, tot_rec = stc["totals"]
+    # shards re-run for an exact halo count as part of every step (they are rare: a read must span the whole guess)
+    ms_per_step = dev_ms / steps + rerun_ms
+    out.update(ms_per_step=ms_per_step, wall_ms_per_step=wall_ms / steps, value=tot_col / (ms_per_step * 1e-3),
+               records_per_sec=tot_rec / (ms_per_step * 1e-3), totals=(tot_col, tot_ent, tot_rec),
+               per_gpu=(n_rec, n_col, n_ent), stats=s0, runs=runs[:steps],
+               stitch={"stitch_counts_ms": stitch_ms, "halo_exchange_ms": halo_report["exchange_ms"],
+                       "what": "all-gather of 3 counts per rank (column / entry / record bases) + all-gather of the reach rows; "
+                               "outside the timed passes, stated here"},
+               halo=dict(halo_report, rerun_ms=rerun_ms))
+    if md_runs:
+        md_ms = float(np.mean([s[0].total_ms for s in md_runs]))
+        out["md"] = {"value": md_runs[-1][2] / (md_ms * 1e-3), "unit": "positions/s", "ms_per_step": md_ms,
+                     "pileup_stage_ms": float(np.mean([s[0].pileup_ms for s in md_runs])),
+                     "d2h_bytes_per_step": int(md_runs[-1][0].d2h_bytes), "h2d_bytes_per_step": int(md_runs[-1][0].h2d_bytes),
+                     "what": "same device-resident pass with use_md_tag: dna() length per read on the GPU, provider chain on the "
+                             "host (12 B per read device->host), segment replay into reference_base[] on the GPU"}
+
+    # ---- e2e: file in pinned host memory, every column batch copied back inside the timed region -------
+    if want_e2e:
+        # N = 1: the private copy of the file is page-locked whole; N > 1: every rank maps the shared file and page-locks
+        # only the byte range of its own shard (+ halo), on demand
+        rd = open_reader(False, False, 1 if world == 1 else 2)
+        input_pinned = bool(L.biodb_input_is_pinned(rd))
+        einfo = {}
+        run_pass(L, capi, rd, shard, einfo, compact=True)
+        barrier()
+        es = [run_pass(L, capi, rd, shard, einfo, compact=True) for _ in range(steps)]
+        barrier()
+        eredo, _ = exact_halo_pass(rd, einfo, compact=True)
+        e_rerun = float(eredo[0].total_ms) if eredo else 0.0
+        ex = run_pass(L, capi, rd, shard, compact=False)     # same pass with explicit read_idx lists, for comparison
+        barrier()
+        rp = None
+        if want_reads_pass and world == 1:
+            # BamReader.reads alone: every record (raw bytes + field tables) delivered to host memory
+            run_reads_pass(L, capi, rd)
+            rp = run_reads_pass(L, capi, rd)
+        L.biodb_close(rd)
+        e_ms = sum(s[0].total_ms for s in es)
+        te = torch.tensor([e_ms, e_rerun], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_ms = float(te[0]) / steps + float(te[1])
+        out["e2e"] = {"value": tot_col / (e_ms * 1e-3), "unit": "positions/s", "ms_per_step": e_ms,
+                      "h2d_bytes_per_step": int(es[-1][0].h2d_bytes), "d2h_bytes_per_step": int(es[-1][0].d2h_bytes),
+                      "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned,
+                      "pcie_d2h_gbs": es[-1][0].d2h_bytes / (e_ms * 1e-3) / 1e9,
+                      "columns": "compact_reads (sequential, lossless): positions as runs; per column n_starting_here, "
+                                 "last_read, 64-bit window mask (+ stragglers); per entry base + qual",
+                      "with_explicit_read_idx": {"ms_per_step": float(ex[0].total_ms), "d2h_bytes_per_step": int(ex[0].d2h_bytes),
+                                                 "value": (tot_col / (float(ex[0].total_ms) * 1e-3)) if world == 1 else None}}
+        if rp is not None:
+            out["reads_pass_e2e"] = {"records_per_sec": rp[1] / (float(rp[0].total_ms) * 1e-3), "ms_per_step": float(rp[0].total_ms),
+                                     "h2d_bytes_per_step": int(rp[0].h2d_bytes), "d2h_bytes_per_step": int(rp[0].d2h_bytes),
+                                     "what": "BamReader.reads through the C ABI: raw record bytes + field / CIGAR tables of "
+                                             "every record copied to host memory (no pileup)"}
+    del data
+    return out
 
 
 def main():
@@ -199,39 +371,29 @@ def main():
     cfg = CONFIGS[args.config]
     n_reads = args.reads or cfg["reads"]
     cores = os.cpu_count() or 1
-    workload = cfg["name"] + ("" if not args.reads else f" — SCALED to {n_reads} reads by --reads") + \
-        f", zlib level {args.level}" + (", records straddling BGZF blocks (htsjdk layout)" if args.straddle else "")
+
+    def workload_name(c, n, full):
+        return c["name"] + ("" if n == full else f" — SCALED to {n} reads") + \
+            f", zlib level {args.level}" + (", records straddling BGZF blocks (htsjdk layout)" if args.straddle else "")
+
+    workload = workload_name(cfg, n_reads, cfg["reads"])
 
     # ------------------------------------------------------------------ reference arm (CPU) --------------
     if args.impl == "reference":
         if rank != 0:
             return
         threads = max(1, cores - 1)   # default taskPool = totalCPUs-1 inflate workers (bgzf/inputstream.d:456,467)
-        vals, rec = [], None
-        from oracle import oracle as orc
-        from tools import bamgen
-        n = args.cpu_sample_reads
-        data = bamgen.generate(n, cfg["refs"], bool(cfg["mixed"]), args.level, bamgen.SEED_BASE + args.config)
-        for i in range(args.warmup + args.steps):
-            r = orc.cpu_baseline(data, threads, True)
-            t = max(r["t_inflate"], r["t_decode"] + r["t_pileup"])
-            if i >= args.warmup:
-                vals.append((r["n_columns"] / t, t, r))
-        v = float(np.mean([x[0] for x in vals]))
-        t = float(np.mean([x[1] for x in vals]))
-        r = vals[-1][2]
-        sample = (f"first {n} reads of the workload ({r['n_columns']} positions); inflate on {threads} threads "
-                  f"{r['t_inflate']:.2f}s, record walk {r['t_decode']:.2f}s + pileup {r['t_pileup']:.2f}s on 1 thread; "
-                  "value assumes the reference overlaps inflate with its consumer thread perfectly")
-        line = {"impl": "reference", "metric": "pileup_positions_per_sec", "value": v, "unit": "positions/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": workload, "sample_reads": n},
-                "records_per_sec": r["n_records"] / t,
-                "cpu_baseline": {"value": v, "unit": "positions/s", "cores": threads, "kind": "port", "sample": sample},
-                "e2e": {"value": v, "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        blk, t_ms, r = cpu_reference_block(args, args.config, cfg, threads, runs=args.warmup + args.steps)
+        blk_runs = args.warmup + args.steps
+        line = {"impl": "reference", "metric": "pileup_positions_per_sec", "value": blk["value"], "unit": "positions/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": workload, "sample_reads": args.cpu_sample_reads, "runs_averaged": blk_runs},
+                "records_per_sec": blk["records_per_sec"],
+                "cpu_baseline": blk,
+                "e2e": {"value": blk["value"], "unit": "positions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0,
-                "note": "restated BioD CPU path (libz, g++ -O3), not the D binary: no D toolchain in this image"}
+                "note": blk["note"]}
         print(json.dumps(line))
         return
 
@@ -251,59 +413,13 @@ def main():
 
     from biod_b200 import _capi as capi
     L = capi.lib()
-    data, path, t_gen, made = synth_file(args, cfg, n_reads, rank, barrier)
-
-    def open_reader(resident, device_output, pin):
-        o = capi.Options()
-        L.biodb_default_options(C.byref(o))
-        o.device, o.blocks_per_batch = local, args.blocks_per_batch
-        o.resident_input, o.device_output, o.pin_input = int(resident), int(device_output), int(pin)
-        h = C.c_void_p()
-        st = L.biodb_open_memory(data.ctypes.data, data.size, C.byref(o), C.byref(h))
-        if st != capi.OK:
-            raise RuntimeError(L.biodb_open_error().contents.message.decode())
-        return h
-
-    # ---- value: compressed file resident in HBM, columns stay in HBM ------------------------------------
-    shard = (rank, world)
-    rd = open_reader(True, True, False)
-    for _ in range(args.warmup):
-        run_pass(L, capi, rd, shard)
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    t0 = time.time()
-    shard_info = {}
-    steps = [run_pass(L, capi, rd, shard, shard_info) for _ in range(args.steps)]
-    barrier()
-    wall = time.time() - t0
-    clocks = sampler.stop()
-    md_steps = None
-    if args.md and world == 1:
-        # the same device-resident pass with PileupColumn.reference_base rebuilt from the MD tags (use_md_tag)
-        run_pass(L, capi, rd, shard, use_md=True)
-        md_steps = [run_pass(L, capi, rd, shard, use_md=True) for _ in range(args.steps)]
-    L.biodb_close(rd)
-    dev_ms = sum(s[0].total_ms for s in steps)
-    tt = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms = float(tt[0]), float(tt[1])
-    s0, n_rec, n_col, n_ent = steps[-1]
-    # the stitch (the only collective of the path): every rank learns every shard's column / entry / record counts
-    # -> global column offsets and record bases; plus the halo exactness check of the shard boundaries
-    from biod_b200.stitch import halo_sufficient, stitch_counts
-    stc = stitch_counts(n_col, n_ent, n_rec, device="cuda")
-    tot_col, tot_ent, tot_rec = stc["totals"]
-    halo_ok = True
-    if world > 1:
-        keys = ["first_coffset", "halo_coffset", "lo_ref", "hi_ref", "lo_pos", "max_end_all", "max_end_outside_tail"]
-        mine = torch.tensor([int(shard_info[k]) for k in keys], dtype=torch.int64, device="cuda")
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        halo_ok = halo_sufficient([dict(zip(keys, (int(x) for x in v))) for v in allv])
-    ms_per_step = dev_ms / args.steps
-    value = tot_col / (ms_per_step * 1e-3)
+    m = measure(args, L, capi, torch, dist, args.config, n_reads, rank, world, local, barrier, args.steps, args.warmup,
+                not args.no_e2e, True, args.md)
+    s0 = m["stats"]
+    runs = m["runs"]
+    n_rec, n_col, n_ent = m["per_gpu"]
+    tot_col, tot_ent, tot_rec = m["totals"]
+    ms_per_step = m["ms_per_step"]
     # roofline of the dominant kernel (inflate): algorithmic bytes = compressed in + uncompressed out
     peaks = {}
     try:
@@ -313,65 +429,73 @@ def main():
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
     # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (bytes per BGZF block there x
     # blocks per launch here); None when no capture is committed
-    traffic = None
-    try:
-        for k in json.load(open(os.path.join(ROOT, "profiles", "ncu_full_r1_summary.json"))):
-            if k["kernel"].endswith("inflate_par_kernel"):
-                def _b(v):
-                    x, u = v.split()
-                    return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-                per_block = (_b(k["dram__bytes_read.sum"]) + _b(k["dram__bytes_write.sum"])) / float(k["launch__grid_size"].split()[0])
-                traffic = per_block * s0.n_blocks / max(1, s0.inflate_launches)
-    except Exception:  # noqa: BLE001
-        traffic = None
-    infl_ms = np.mean([s[0].inflate_ms for s in steps])
+    traffic, traffic_src = None, None
+    for fn in ("ncu_full_r2_summary.json", "ncu_full_r1_summary.json"):
+        try:
+            per_block = 0.0
+            for k in json.load(open(os.path.join(ROOT, "profiles", fn))):
+                if "inflate" in k["kernel"] and k.get("dominant_inflate"):
+                    def _b(v):
+                        x, u = v.split()
+                        return float(x) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+                    per_block += (_b(k["dram__bytes_read.sum"]) + _b(k["dram__bytes_write.sum"])) / float(k["launch__grid_size"].split()[0])
+            if per_block:
+                traffic, traffic_src = per_block * s0.n_blocks / max(1, s0.inflate_launches), fn
+                break
+        except Exception:  # noqa: BLE001
+            continue
+    infl_ms = np.mean([s[0].inflate_ms for s in runs])
     infl_bytes = s0.compressed_bytes + s0.uncompressed_bytes
     achieved = infl_bytes / (infl_ms * 1e-3) / 1e9
-    roofline = {"kernel": "inflate_par_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+    roofline = {"kernel": "inflate (decode + resolve kernels)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": infl_bytes / max(1, s0.inflate_launches),
                 "launches_per_step": int(s0.inflate_launches),
                 "avg_launch_ms": infl_ms / max(1, s0.inflate_launches),
                 "share_of_step": infl_ms / ms_per_step,
-                "stage_ms": {"inflate": float(infl_ms), "record_scan": float(np.mean([s[0].scan_ms for s in steps])),
-                             "pileup": float(np.mean([s[0].pileup_ms for s in steps]))}}
+                "stage_ms": {"inflate": float(infl_ms), "record_scan": float(np.mean([s[0].scan_ms for s in runs])),
+                             "pileup": float(np.mean([s[0].pileup_ms for s in runs]))}}
     # the two other stages against the same HBM peak (algorithmic bytes of SURVEY.md §8d / DESIGN.md §4: 283 B read +
     # 32 B written per record; 239 B per record + 6 B per entry + 20 B per column)
-    scan_ms = float(np.mean([s[0].scan_ms for s in steps]))
-    pile_ms = float(np.mean([s[0].pileup_ms for s in steps]))
+    scan_ms = float(np.mean([s[0].scan_ms for s in runs]))
+    pile_ms = float(np.mean([s[0].pileup_ms for s in runs]))
     scan_bytes = 315.0 * n_rec
     pile_bytes = 239.0 * n_rec + 6.0 * n_ent + 20.0 * n_col
     roofline["other_stages"] = {
         "record_scan": {"bound": "hbm", "achieved": scan_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms else None, "unit": "GB/s",
                         "frac": scan_bytes / (scan_ms * 1e-3) / 1e9 / peak if scan_ms else None,
-                        "algorithmic_bytes": scan_bytes, "ms": scan_ms},
+                        "algorithmic_bytes": scan_bytes, "ms": scan_ms,
+                        "note": "algorithmic (283 B + 32 B per record); the kernel itself touches ~182 B per record (no SEQ / QUAL) "
+                                "and its chain walk is fused into the inflate kernel — from compressed bytes the decode runs at "
+                                "records_per_sec, ~1 % of HBM"},
         "pileup": {"bound": "hbm", "achieved": pile_bytes / (pile_ms * 1e-3) / 1e9 if pile_ms else None, "unit": "GB/s",
                    "frac": pile_bytes / (pile_ms * 1e-3) / 1e9 / peak if pile_ms else None,
                    "algorithmic_bytes": pile_bytes, "ms": pile_ms}}
-    line = {"metric": "pileup_positions_per_sec", "value": value, "unit": "positions/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "u8",
+    line = {"metric": "pileup_positions_per_sec", "value": m["value"], "unit": "positions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "wall_ms_per_step": m["wall_ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": workload, "reads_per_gpu": n_rec, "positions_per_gpu": n_col, "entries_per_gpu": n_ent,
-                       "total_reads": tot_rec, "total_positions": tot_col, "halo_check_passed": halo_ok,
-                       "compressed_bytes": int(data.size), "blocks_per_batch": args.blocks_per_batch or "library default: 3 full waves of the inflate kernel (8436 on a B200)",
+                       "total_reads": tot_rec, "total_positions": tot_col, "halo": m["halo"],
+                       "halo_check_passed": True,
+                       "compressed_bytes": m["compressed_bytes"],
+                       "blocks_per_batch": args.blocks_per_batch or ("library default: 3 full waves of the inflate kernel" if world == 1
+                                                                     else f"{2 if world == 2 else 1} full wave(s) of the inflate kernel"),
                        "cache": "inputs larger than L2: 12 GB compressed / 28 GB inflated per pass vs 126 MB L2",
                        "parallelism": ("1 GPU, whole file" if world == 1 else
-                                       f"{world} block-range shards of ONE file (one per GPU, halo of 8 blocks, no data-path "
-                                       "collective), NCCL all-gather of counts + halo check for the column stitch"),
-                       "generated_in_s": round(t_gen, 1), "generated_now": made},
-            "records_per_sec": tot_rec / (ms_per_step * 1e-3),
+                                       f"{world} shards of ONE file (one per GPU: total work fixed, 'strong' scaling), halos read from "
+                                       "the file, no data-path collective; NCCL all-gathers of counts (stitch) and reach rows (exact halos)"),
+                       "generated_in_s": m["generated_in_s"], "generated_now": m["generated_now"]},
+            "records_per_sec": m["records_per_sec"],
             "inflate_out_gbs": s0.uncompressed_bytes / (infl_ms * 1e-3) / 1e9,
-            "roofline": roofline, "gpu_launches": int(sum(s[0].kernel_launches for s in steps)), "clocks": clocks}
-
-    if md_steps:
-        md_ms = float(np.mean([s[0].total_ms for s in md_steps]))
-        line["md_reference_bases"] = {
-            "value": md_steps[-1][2] / (md_ms * 1e-3), "unit": "positions/s", "ms_per_step": md_ms,
-            "pileup_stage_ms": float(np.mean([s[0].pileup_ms for s in md_steps])),
-            "d2h_bytes_per_step": int(md_steps[-1][0].d2h_bytes), "h2d_bytes_per_step": int(md_steps[-1][0].h2d_bytes),
-            "what": "same device-resident pass with use_md_tag: dna() length per read on the GPU, provider chain on the host "
-                    "(12 B per read device->host), segment replay into reference_base[] on the GPU"}
+            "stitch": m["stitch"],
+            "roofline": roofline, "gpu_launches": int(sum(s[0].kernel_launches for s in runs)), "clocks": m["clocks"]}
+    if "md" in m:
+        line["md_reference_bases"] = m["md"]
+    if "e2e" in m:
+        line["e2e"] = m["e2e"]
+    if "reads_pass_e2e" in m:
+        line["reads_pass_e2e"] = m["reads_pass_e2e"]
     # diagnostics of the lane-parallel inflate kernel over everything run so far (0 blocks given up = no fallback)
     try:
         cnt = (C.c_uint64 * 8)()
@@ -381,52 +505,28 @@ def main():
     except Exception:  # noqa: BLE001
         pass
 
-    # ---- e2e: file in pinned host memory, every column batch copied back inside the timed region -------
-    if not args.no_e2e:
-        rd = open_reader(False, False, True)   # pin the (possibly shared, mmap-ed) file buffer when the driver allows it
-        input_pinned = bool(L.biodb_input_is_pinned(rd))
-        run_pass(L, capi, rd, shard, compact=True)
-        barrier()
-        es = [run_pass(L, capi, rd, shard, compact=True) for _ in range(args.steps)]
-        barrier()
-        ex = run_pass(L, capi, rd, shard, compact=False)     # same pass with explicit read_idx lists, for comparison
-        barrier()
-        rp = None
-        if world == 1:
-            # BamReader.reads alone: every record (raw bytes + field tables) delivered to host memory
-            run_reads_pass(L, capi, rd)
-            rp = run_reads_pass(L, capi, rd)
-        L.biodb_close(rd)
-        e_ms = sum(s[0].total_ms for s in es)
-        te = torch.tensor([e_ms], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e_ms = float(te[0]) / args.steps
-        line["e2e"] = {"value": tot_col / (e_ms * 1e-3), "unit": "positions/s", "ms_per_step": e_ms,
-                       "h2d_bytes_per_step": int(es[-1][0].h2d_bytes), "d2h_bytes_per_step": int(es[-1][0].d2h_bytes),
-                       "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned,
-                       "pcie_d2h_gbs": es[-1][0].d2h_bytes / (e_ms * 1e-3) / 1e9,
-                       "columns": "compact_reads (sequential, lossless): positions as runs; per column n_starting_here, "
-                                  "last_read, 64-bit window mask (+ stragglers); per entry base + qual",
-                       "with_explicit_read_idx": {"ms_per_step": float(ex[0].total_ms), "d2h_bytes_per_step": int(ex[0].d2h_bytes),
-                                                  "value": (tot_col / (float(ex[0].total_ms) * 1e-3)) if world == 1 else None}}
-        if rp is not None:
-            line["reads_pass_e2e"] = {"records_per_sec": rp[1] / (float(rp[0].total_ms) * 1e-3), "ms_per_step": float(rp[0].total_ms),
-                                      "h2d_bytes_per_step": int(rp[0].h2d_bytes), "d2h_bytes_per_step": int(rp[0].d2h_bytes),
-                                      "what": "BamReader.reads through the C ABI: raw record bytes + field / CIGAR tables of every "
-                                              "record copied to host memory (no pileup)"}
+    # ---- the other configs BASELINE.json names, as blocks of the same line --------------------------------
+    if not args.no_extra and args.config == 2 and not args.reads:
+        xc = 3 if world == 1 else 4
+        xn = CONFIGS[3]["reads"] if world == 1 else CFG4_READS_PER_GPU * world
+        try:
+            x = measure(args, L, capi, torch, dist, xc, xn, rank, world, local, barrier, max(1, min(2, args.steps)), 1,
+                        not args.no_e2e, False, False)
+            line["config3" if xc == 3 else "config4"] = {
+                "workload": workload_name(CONFIGS[xc], xn, CONFIGS[xc]["reads"]), "value": x["value"], "unit": "positions/s",
+                "ms_per_step": x["ms_per_step"], "records_per_sec": x["records_per_sec"],
+                "total_reads": x["totals"][2], "total_positions": x["totals"][0], "halo": x["halo"],
+                "e2e": x.get("e2e"), "stitch": x["stitch"], "generated_in_s": x["generated_in_s"],
+                "stage_ms": {"inflate": float(np.mean([s[0].inflate_ms for s in x["runs"]])),
+                             "record_scan": float(np.mean([s[0].scan_ms for s in x["runs"]])),
+                             "pileup": float(np.mean([s[0].pileup_ms for s in x["runs"]]))}}
+        except Exception as e:  # noqa: BLE001 - the headline must survive a failure of the extra block
+            line["config3" if xc == 3 else "config4"] = {"error": repr(e)[:300]}
 
     # ---- CPU baseline on the host cores (rank 0, N=1 only) ----------------------------------------------
     if not args.no_cpu and rank == 0 and world == 1:
-        threads = max(1, cores - 1)
-        n, r = cpu_reference(args, cfg, threads)
-        t = max(r["t_inflate"], r["t_decode"] + r["t_pileup"])
-        line["cpu_baseline"] = {
-            "value": r["n_columns"] / t, "unit": "positions/s", "cores": threads, "kind": "port",
-            "records_per_sec": r["n_records"] / t,
-            "sample": (f"first {n} reads of the workload ({r['n_columns']} positions): inflate {r['t_inflate']:.2f}s on "
-                       f"{threads} threads, record walk {r['t_decode']:.2f}s + pileup {r['t_pileup']:.2f}s single-threaded "
-                       "(as BioD does); value assumes perfect overlap of the two")}
+        blk, _, _ = cpu_reference_block(args, args.config, cfg, max(1, cores - 1))
+        line["cpu_baseline"] = blk
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -22,6 +22,8 @@
 //    stores (ring index == global address mod ring size, so alignment carries).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "inflate_common.cuh"
 
 namespace biodb {
@@ -476,31 +478,45 @@ unsigned long long g_kernel_launches = 0;
 
 size_t inflate_smem_bytes() { return sizeof(WarpSmem); }
 
-// Which kernel inflates: the two-warp kernel (inflate_duo.cu) unless BIODB_INFLATE says otherwise —
-// "par" = the one-warp lane-parallel kernel (inflate_par.cu), "serial" = the warp-serial kernel alone (A/B measurements).
-enum { MODE_DUO = 0, MODE_PAR = 1, MODE_SERIAL = 2 };
+// Which kernels inflate: the decode + resolve pair (inflate_tok.cu) unless BIODB_INFLATE says otherwise — "duo" = one
+// kernel with a decoder and a resolver warp per block (inflate_duo.cu), "par" = the one-warp lane-parallel kernel
+// (inflate_par.cu), "serial" = the warp-serial kernel alone (A/B measurements).
+enum { MODE_TOK = 0, MODE_DUO = 1, MODE_PAR = 2, MODE_SERIAL = 3 };
 static int inflate_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("BIODB_INFLATE");
-    v = (e && e[0] == 's') ? MODE_SERIAL : (e && e[0] == 'p') ? MODE_PAR : MODE_DUO;
+    v = (e && e[0] == 's') ? MODE_SERIAL : (e && e[0] == 'p') ? MODE_PAR : (e && e[0] == 'd') ? MODE_DUO : MODE_TOK;
   }
   return v;
 }
 
 int inflate_resident_blocks(int device) {
-  return inflate_mode() == MODE_DUO ? inflate_duo_resident_blocks(device) : inflate_par_resident_blocks(device);
+  const int m = inflate_mode();
+  return m == MODE_TOK ? inflate_tok_resident_blocks(device) : m == MODE_DUO ? inflate_duo_resident_blocks(device)
+                                                                             : inflate_par_resident_blocks(device);
 }
 
-size_t inflate_token_bytes(uint32_t n_blocks) { return inflate_mode() == MODE_DUO ? inflate_duo_token_bytes(n_blocks) : 0; }
+size_t inflate_token_bytes(uint32_t n_blocks) {
+  const int m = inflate_mode();
+  return m == MODE_TOK ? inflate_tok_token_bytes(n_blocks) : m == MODE_DUO ? inflate_duo_token_bytes(n_blocks) : 0;
+}
 
 cudaError_t inflate_counters(unsigned long long* out8, int reset) {
-  unsigned long long p[8], d[8];
+  unsigned long long p[8], d[8], t[8];
   cudaError_t e = inflate_par_counters(p, reset);
   if (e == cudaSuccess) e = inflate_duo_counters(d, reset);
+  if (e == cudaSuccess) e = inflate_tok_counters(t, reset);
   if (e == cudaSuccess)
-    for (int i = 0; i < 8; ++i) out8[i] = p[i] + d[i];
+    for (int i = 0; i < 8; ++i) out8[i] = p[i] + d[i] + t[i];
   return e;
+}
+
+static InflateArgs slice_args(const InflateArgs& a, uint32_t b0, uint32_t n) {
+  InflateArgs s = a;
+  s.payload_off += b0; s.cdata_size += b0; s.out_off += b0; s.isize += b0; s.status += b0;
+  s.n_blocks = n;
+  return s;
 }
 
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st) {
@@ -511,23 +527,31 @@ cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st) {
     ++g_kernel_launches;
     return cudaGetLastError();
   }
-  cudaError_t e;
-  if (mode == MODE_DUO) {
-    InflateArgs b = a;
-    void* tmp = nullptr;
-    if (!b.tok) {                                  // callers without a token area of their own (the device-resident stage API)
-      e = cudaMallocAsync(&tmp, inflate_duo_token_bytes(a.n_blocks), st);
-      if (e != cudaSuccess) return e;
-      b.tok = (uint16_t*)tmp;
-    }
-    e = launch_inflate_duo(b, st);                 // two-warp kernel; marks the blocks it gives up on
-    if (tmp) cudaFreeAsync(tmp, st);
-  } else {
+  cudaError_t e = cudaSuccess;
+  if (mode == MODE_PAR) {
     e = launch_inflate_par(a, st);                 // one-warp lane-parallel kernel; marks the blocks it gives up on
+    g_kernel_launches += 1;
+  } else if (a.tok) {
+    e = mode == MODE_TOK ? launch_inflate_tok(a, st) : launch_inflate_duo(a, st);
+    g_kernel_launches += mode == MODE_TOK ? 2 : 1;
+  } else {
+    // callers without a token area of their own (the device-resident stage API, no fused record walk): one is allocated
+    // for the call (stream-ordered) and the blocks go through it slab by slab
+    const uint32_t slab = std::min<uint32_t>(a.n_blocks, 8192);
+    void* tmp = nullptr;
+    e = cudaMallocAsync(&tmp, inflate_token_bytes(slab), st);
+    if (e != cudaSuccess) return e;
+    for (uint32_t b0 = 0; b0 < a.n_blocks && e == cudaSuccess; b0 += slab) {
+      InflateArgs s = slice_args(a, b0, std::min<uint32_t>(slab, a.n_blocks - b0));
+      s.tok = (uint16_t*)tmp;
+      e = mode == MODE_TOK ? launch_inflate_tok(s, st) : launch_inflate_duo(s, st);
+      g_kernel_launches += mode == MODE_TOK ? 2 : 1;
+    }
+    cudaFreeAsync(tmp, st);
   }
   if (e != cudaSuccess) return e;
   inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 1);
-  g_kernel_launches += 2;
+  g_kernel_launches += 1;
   return cudaGetLastError();
 }
 

@@ -1,46 +1,53 @@
-// BGZF block inflater for sm_100a, two warps per BGZF block: a DECODER warp that turns the DEFLATE bit stream into
-// tokens and a RESOLVER warp that turns tokens into bytes, working on consecutive pieces of the stream at the same time.
+// BGZF block inflater for sm_100a in two kernels: DECODE turns the DEFLATE bit stream of every block into tokens,
+// RESOLVE turns the tokens into bytes.
 //
 // Replaces decompressBgzfBlock (bio/core/bgzf/block.d:127-216), i.e. libz's inflateInit2(-15) / inflate(Z_FINISH) /
 // inflateEnd on one <=64 KiB raw-DEFLATE payload.  The algorithm is RFC 1951; nothing here is derived from zlib.
 //
-// inflate_par.cu (one warp per block) showed where the time goes: every code was decoded 3.24 times — a speculative
-// round that finds where the lanes' sub-sequences really start, 1.24 repair rounds, and one more full Huffman decode
-// whose only job was to write the bytes now that the output offsets were known — and decoding and LZ77 copying
-// alternated in the one warp.  Here:
-//   * DECODER (warp 0): TMA staging of the payload, block headers, Huffman tables, and the lane-parallel decode of
-//     "super-chunks" of 32 sub-sequences of SUB_BITS bits (see inflate_par.cu for the idea).  Round 1 only looks for the
-//     synchronisation points (code lengths alone: the LUT entry carries the extra-bit count, no value is computed, nothing
-//     is counted).  From round 2 on a lane decodes from where its predecessor ended and RECORDS what it decodes as 16-bit
-//     tokens — literal / length / distance, one per loop trip — in a per-block scratch area in global memory (8 KB per
-//     block, L2-resident, written 64 contiguous bytes per warp store).  When the chain of lanes is consistent the
-//     per-lane byte / match / token counts go to shared memory and the resolver is signalled (named barrier); the decoder
-//     goes straight on to the next super-chunk.
-//   * RESOLVER (warp 1): scans the counts into output offsets, REPLAYS the tokens (literals into the shared-memory
-//     output ring, matches into a list: ~10 instructions per token instead of a Huffman decode), releases the token
-//     area, copies the LZ77 matches (in-ring sources in stream order, older sources read back from L2 all at once),
-//     lets the record-chain walker (records.cu) look at the new bytes and flushes whole 128-byte lines to HBM.
-// Anything unusual makes the block a STATUS_RETRY, redone by the warp-serial kernel (inflate.cu), which also produces
-// zlib's exact error code — as in inflate_par.cu.
+// Why two kernels.  Huffman decoding is one long dependency chain per warp: measured on the B200, a warp of the decode
+// loop issues one instruction every ~10 cycles whatever else the SM does, so the throughput of an SM is the number of
+// RESIDENT DECODING WARPS times that rate until the four schedulers saturate near 36-40 warps.  inflate_par.cu (one
+// warp per block doing everything: 11 KB of shared memory, 19 warps per SM, every code decoded 3.24 times) and
+// inflate_duo.cu (a decoder and a resolver warp per block, 16-18 blocks per SM, the resolver idle half of the time) both
+// ran at ~55-65 % of the issue slots for that reason.  Here
+//   * inflate_decode_kernel (one warp per block) keeps only what decoding needs in shared memory — the TMA staging ring,
+//     the Huffman tables — ~7 KB, so 28 blocks are resident per SM.  It decodes "super-chunks" of 32 sub-sequences of
+//     SUB_BITS bits lane-parallel (see inflate_par.cu for the idea): round 1 only looks for the points where the
+//     sub-sequences synchronise (code lengths alone: the LUT entry carries the extra-bit count); from round 2 on a lane
+//     decodes from where its predecessor ended and RECORDS what it decodes as 16-bit tokens — literal / length /
+//     distance, one per loop trip — straight into the block's record stream in global memory (64 contiguous bytes per warp
+//     store).  When the chain of lanes is consistent it appends the super-chunk's header (lanes committed, per-lane byte /
+//     match / token counts) and goes on; it never waits for anybody.
+//   * inflate_resolve_kernel (one warp per block, ~5 KB of shared memory: 32 blocks per SM) walks the record stream:
+//     scans the counts into output offsets, REPLAYS the tokens (literals into the shared-memory output ring, matches
+//     into a list: ~10 instructions per token instead of a Huffman decode), copies the LZ77 matches (in-ring sources in
+//     stream order, older sources read back from L2 all at once), lets the record-chain walker (records.cu) look at the
+//     new bytes and flushes whole 128-byte lines to HBM.  Stored blocks are copied by this kernel straight from the
+//     compressed payload.
+// The price is the record stream: ~2 bytes per token written and read once (~2.4 x the block's own bytes for BAM data),
+// on a kernel pair that uses a few per cent of the HBM bandwidth.
+// Anything unusual — an invalid code, a distance too far back, a stream that does not end exactly at ISIZE, input that
+// runs out, a record stream that outgrows its arena — makes the block a STATUS_RETRY, redone by the warp-serial kernel
+// (inflate.cu), which also produces zlib's exact error code.
 #include "inflate_common.cuh"
 
 namespace biodb {
 
 namespace {
 
-#ifndef BIODB_DUO_SUB_BITS
-#define BIODB_DUO_SUB_BITS 224
+#ifndef BIODB_TOK_SUB_BITS
+#define BIODB_TOK_SUB_BITS 224
 #endif
-#ifndef BIODB_DUO_MIN_CTAS
-#define BIODB_DUO_MIN_CTAS 16
+#ifndef BIODB_TOK_MLIST
+#define BIODB_TOK_MLIST 128
 #endif
-#ifndef BIODB_DUO_MLIST
-#define BIODB_DUO_MLIST 128
+#ifndef BIODB_TOK_MAX_ROUNDS
+#define BIODB_TOK_MAX_ROUNDS 5
 #endif
-#ifndef BIODB_DUO_MAX_ROUNDS
-#define BIODB_DUO_MAX_ROUNDS 5
+#ifndef BIODB_TOK_DECODE_CTAS
+#define BIODB_TOK_DECODE_CTAS 28
 #endif
-constexpr int SUB_BITS = BIODB_DUO_SUB_BITS;   // bits of one lane's sub-sequence
+constexpr int SUB_BITS = BIODB_TOK_SUB_BITS;   // bits of one lane's sub-sequence
 constexpr int SUPER_BYTES = SUB_BITS * 4;      // compressed bytes of one nominal super-chunk
 constexpr int NCH = 8;                         // chunks in the staging ring
 constexpr int PIN_RING = 2048;
@@ -48,35 +55,44 @@ constexpr int CH = PIN_RING / NCH;             // bytes per TMA chunk
 constexpr int PIN_WORDS = PIN_RING / 4;
 constexpr int POUT = 4096;
 constexpr uint32_t POM = POUT - 1;
-// Output bytes one super-chunk may produce.  The ring must keep, besides them, the unflushed tail (< FLUSH_ALIGN), the
-// longest match (258) for the "older than the ring => already flushed" rule, and ~1.1 KB of history for the walker.
+// Output bytes one super-chunk may produce.  The resolver's ring must keep, besides them, the unflushed tail
+// (< FLUSH_ALIGN), the longest match (258) for the "older than the ring => already flushed" rule, and ~1.1 KB of history
+// for the walker.
 constexpr int OUT_BUDGET = POUT - 1536;
 constexpr int LANE_CAP = 512;                  // a lane stops taking codes once it has produced this many bytes ...
-constexpr int MLIST = BIODB_DUO_MLIST;         // matches one super-chunk may hold
-constexpr int LANE_MCAP = DUO_TOK_TRIPS / 2;   // (a lane stops after DUO_TOK_TRIPS - 1 tokens: at most this many matches)
+constexpr int MLIST = BIODB_TOK_MLIST;         // matches one super-chunk may hold
+constexpr int TOK_TRIPS = DUO_TOK_TRIPS;       // ... or TOK_TRIPS - 1 tokens
+constexpr int LANE_MCAP = TOK_TRIPS / 2;       // (hence at most this many matches)
 constexpr int FLUSH_ALIGN = 128;
 constexpr int SUB_CAP = LIT_BITS >= 10 ? 320 : 352;
 constexpr int STORE_PIECE = 1024;              // stored blocks are copied in pieces of this many bytes
 constexpr int HDR_BYTES = 640;                 // >= longest dynamic block header
-constexpr int MAX_ROUNDS = BIODB_DUO_MAX_ROUNDS;   // decode rounds per super-chunk before the consistent prefix is committed as it is
+constexpr int MAX_ROUNDS = BIODB_TOK_MAX_ROUNDS;   // decode rounds per super-chunk before the consistent prefix is committed as it is
 static_assert(LANE_CAP > SUB_BITS, "literals alone never reach the cap, so it is checked between codes only");
 static_assert(LANE_CAP + SUB_BITS + 257 <= OUT_BUDGET, "one lane must always fit");
 static_assert(LANE_MCAP <= MLIST, "one lane must always fit");
-static_assert(DUO_TOK_TRIPS >= 64 && DUO_TOK_TRIPS <= 255, "token count of a lane travels in 8 bits");   // ... or DUO_TOK_TRIPS - 1 tokens
-static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= STORE_PIECE + 16 &&
-                  (NCH - 1) * CH >= SUPER_BYTES + 32 && CH % 16 == 0,
-              "staging ring too small");
+static_assert(TOK_TRIPS >= 64 && TOK_TRIPS <= 255, "token count of a lane travels in 8 bits");
+static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= SUPER_BYTES + 32 && CH % 16 == 0, "staging ring too small");
 static_assert(STORE_PIECE <= OUT_BUDGET, "");
 
-// tokens (16 bits, one per decode trip of a lane)
-constexpr uint32_t TOK_LEN = K_LEN << 13, TOK_EOB = K_EOB << 13, TOK_DIST = 0x8000;   // literal: the byte itself
+// tokens (16 bits, one per decode trip of a lane); a literal is the byte itself
+constexpr uint32_t TOK_LEN = K_LEN << 13, TOK_EOB = K_EOB << 13, TOK_DIST = 0x8000;
 // lane stop reasons
 constexpr uint32_t F_EOB = 1, F_ERR = 2, F_INEND = 3;
-// decoder -> resolver messages
-enum { MSG_CHUNK = 0, MSG_STORED = 1, MSG_DONE = 2 };
 
-struct __align__(16) DuoSmem {
-  // ---- decoder warp ----
+// The record stream of a block: 16-bit words in its arena of TOK_ARENA_WORDS, records back to back, each a multiple of 32
+// words (64 bytes).
+//   REC_CHUNK : head[32] = {REC_CHUNK, lanes committed, token rows, ...}; lane[32] x u32 = bytes | matches << 16 |
+//               tokens << 24 of every lane; then `rows` rows of 32 tokens (row t = trip t of lanes 0..31)
+//   REC_STORED: head[32] = {REC_STORED, -, -, -, offset lo, offset hi, length lo, length hi}: `length` bytes at `offset`
+//               of the block's compressed payload
+//   REC_DONE  : head[32] = {REC_DONE, status != 0}
+enum { REC_CHUNK = 1, REC_STORED = 2, REC_DONE = 3 };
+constexpr uint32_t REC_HEAD = 32, REC_LANES = 64;
+constexpr uint32_t ARENA = TOK_ARENA_WORDS;
+static_assert(ARENA % 64 == 0, "");
+
+struct __align__(16) DecSmem {
   uint32_t in_ring[PIN_WORDS + 4];     // + guard word (copy of word 0) so that a 64-bit window never wraps
   uint16_t lut_lit[1 << LIT_BITS];
   uint16_t lut_dist[1 << DIST_BITS];   // also hosts the 128-entry code-length LUT
@@ -88,11 +104,9 @@ struct __align__(16) DuoSmem {
   uint32_t scratch[16];                // build_table_par
   uint16_t sub_lit[SUB_CAP];           // second-level tables of the literal/length codes longer than LIT_BITS
   unsigned long long mbar[NCH];        // TMA completion, one per staging chunk
-  // ---- decoder -> resolver ----
-  uint32_t msg_kind, msg_a, msg_b, r_bad;
-  uint32_t dwarp;                      // which of the CTA's two warps decodes (see inflate_duo_kernel)
-  uint32_t msg_lane[32];               // MSG_CHUNK: bytes | matches << 16 | tokens << 24 of every lane
-  // ---- resolver warp ----
+};
+
+struct __align__(16) ResSmem {
   alignas(16) uint8_t out_ring[POUT];  // (flushed with 16-byte shared-memory loads)
   uint32_t m_ld[MLIST];                // matches of the super-chunk: (length-3) | (distance-1) << 8
   uint16_t m_pos[MLIST];               // and their block-relative output offset
@@ -103,21 +117,8 @@ struct DCtx {             // shared-space addresses and limits every decoder lan
   uint32_t total_bits;
   const Code* code_dist;
   const uint16_t* sorted_dist;
-  uint16_t* tok;          // this block's token area + lane
+  uint16_t* tok;          // row 0 of the super-chunk being decoded + lane
 };
-
-// Decoder <-> resolver hand-over on two named barriers (bar.arrive by the 32 lanes of the signalling warp + bar.sync by
-// the 32 lanes of the waiting warp = 64 arrivals): a warp blocked in bar.sync is descheduled by the hardware and costs no
-// issue slots.  (A first version polled an mbarrier with try_wait: the idle resolver warps then spent 18 % of the
-// kernel's instructions spinning — ncu, profiles/ — and the kernel was no faster than its one-warp predecessor.)
-constexpr int BAR_FULL = 1, BAR_FREE = 2;
-__device__ __forceinline__ void bar_signal(int id) {
-  __threadfence_block();                        // tokens (global) and message (shared) before the arrival
-  asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
-}
-__device__ __forceinline__ void bar_await(int id) {
-  asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory");
-}
 
 // 32 bits of the staged stream starting at bit `pos`
 __device__ __forceinline__ uint32_t fetch32(uint32_t in_ring, uint32_t pos) {
@@ -183,9 +184,9 @@ __device__ __forceinline__ void lane_decode(const DCtx& c, bool active, uint32_t
     lut = st ? c.lutd : c.lutl;
     msk = st ? ((1u << DIST_BITS) - 1) << 1 : ((1u << LIT_BITS) - 1) << 1;
     // a lane stops only between codes of the literal/length alphabet: at its boundary, or (RECORD) when it has produced
-    // LANE_CAP bytes or DUO_TOK_TRIPS - 1 tokens (hence at most LANE_MCAP matches) — the next lane continues from there
+    // LANE_CAP bytes or TOK_TRIPS - 1 tokens (hence at most LANE_MCAP matches) — the next lane continues from there
     uint32_t stop = pos >= lim ? 1u : 0u;
-    if (RECORD) stop |= (o >= (uint32_t)LANE_CAP ? 1u : 0u) | (trips >= (uint32_t)DUO_TOK_TRIPS - 1 ? 1u : 0u);
+    if (RECORD) stop |= (o >= (uint32_t)LANE_CAP ? 1u : 0u) | (trips >= (uint32_t)TOK_TRIPS - 1 ? 1u : 0u);
     run &= ~(eob | (st ? 0u : stop));
   }
   if (fl == 0 && active && pos >= c.total_bits && pos < limit) fl = F_INEND;   // ran out of input before its boundary
@@ -205,44 +206,48 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
-// -DBIODB_DUO_TIMING: cycles per phase, summed over blocks (lane 0 of each warp), read back through
-// biodb_debug_inflate_counters slots of inflate_duo_cycles(): decoder [0] round 1, [1] waiting for the resolver,
-// [2] rounds >= 2, [3] headers + tables, [4] waiting for input (TMA), [5] total; resolver [8] waiting for the decoder,
-// [9] replay, [10] matches, [11] walker + flush, [12] total.
-#ifdef BIODB_DUO_TIMING
-__device__ unsigned long long g_duo_cycles[16];
-#define T_DECL(n) long long _t_##n = 0
-#define T_ON(n) _t_##n -= clock64()
-#define T_OFF(n) _t_##n += clock64()
-#define T_PUT(n, slot) atomicAdd(&g_duo_cycles[slot], (unsigned long long)_t_##n)
-#else
-#define T_DECL(n)
-#define T_ON(n)
-#define T_OFF(n)
-#define T_PUT(n, slot)
-#endif
+}  // namespace
 
-// ====================================================================================== decoder warp ====
-__device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const uint32_t blk, const int lane,
-                                         unsigned long long* counters) {
+// diagnostics (biodb_debug_inflate_counters), same slots as inflate_par.cu's
+__device__ unsigned long long g_tok_counters[8];
+
+// ===================================================================================== decode kernel ====
+__global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kernel(InflateArgs a) {
+  __shared__ DecSmem sm;
+  DecSmem* s = &sm;
+  const int lane = threadIdx.x;
+  const uint32_t blk = blockIdx.x;
+  if (blk >= a.n_blocks) return;
   const uint64_t poff = a.payload_off[blk];
   const uint32_t csize = a.cdata_size[blk];
   const uint32_t isize = a.isize[blk];
+  uint16_t* const arena = a.tok + (size_t)blk * ARENA;
 
   uint32_t sbase = smem_u32(s);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));           // opaque: keeps the addresses in registers
-  const uint32_t in_ring = sbase + (uint32_t)offsetof(DuoSmem, in_ring);
-  const uint32_t lutd = sbase + (uint32_t)offsetof(DuoSmem, lut_dist);
-  const uint32_t mbar = sbase + (uint32_t)offsetof(DuoSmem, mbar);
+  const uint32_t in_ring = sbase + (uint32_t)offsetof(DecSmem, in_ring);
+  const uint32_t lutd = sbase + (uint32_t)offsetof(DecSmem, lut_dist);
+  const uint32_t mbar = sbase + (uint32_t)offsetof(DecSmem, mbar);
   DCtx ctx;
   ctx.in_ring = in_ring;
-  ctx.lutl = sbase + (uint32_t)offsetof(DuoSmem, lut_lit);
+  ctx.lutl = sbase + (uint32_t)offsetof(DecSmem, lut_lit);
   ctx.lutd = lutd;
-  ctx.auxtab = sbase + (uint32_t)offsetof(DuoSmem, auxtab);
-  ctx.subl = sbase + (uint32_t)offsetof(DuoSmem, sub_lit);
+  ctx.auxtab = sbase + (uint32_t)offsetof(DecSmem, auxtab);
+  ctx.subl = sbase + (uint32_t)offsetof(DecSmem, sub_lit);
   ctx.code_dist = &s->code_dist;
   ctx.sorted_dist = s->sorted_dist;
-  ctx.tok = a.tok + (size_t)blk * (DUO_TOK_TRIPS * 32) + lane;
+  ctx.tok = arena;
+
+  if (lane < NCH) mbar_init(mbar + 8 * lane, 1);
+  if (lane == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  {
+    uint32_t b, eb;
+    s->auxtab[lane] = 0;
+    s->auxtab[32 + lane] = 0;
+    if (lane < 29) { len_base((uint32_t)lane, b, eb); s->auxtab[lane] = b; }
+    if (lane < 30) { dist_base((uint32_t)lane, b, eb); s->auxtab[32 + lane] = b; }
+  }
+  __syncwarp();
 
   // ---- staging of the compressed payload (TMA) -------------------------------------------------------------
   const uint8_t* pay = a.comp + poff;
@@ -281,20 +286,6 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
     while (waited <= c1 && waited < issued) wait_chunk(waited);
   };
 
-  // ---- messages to the resolver ---------------------------------------------------------------------------------
-  bool owe = false;         // a message is out whose consumption has not been waited for
-  auto wait_free = [&]() {
-    if (owe) {
-      bar_await(BAR_FREE);
-      owe = false;
-    }
-  };
-  auto send = [&](uint32_t kind, uint32_t x, uint32_t y) {     // msg_lane[] (if any) is already written
-    if (lane == 0) { s->msg_kind = kind; s->msg_a = x; s->msg_b = y; }
-    bar_signal(BAR_FULL);
-    owe = true;
-  };
-
   // all bit positions are relative to src
   uint32_t pos = skip * 8;
   const uint32_t total_bits = staged * 8;
@@ -302,16 +293,14 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
   int status = 0;
   uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0;
   uint32_t produced = 0;    // bytes handed to the resolver so far
+  uint32_t cur = 0;         // next free word of the arena
+  // room a record may need, plus the closing REC_DONE
+  constexpr uint32_t CHUNK_MAX = REC_HEAD + REC_LANES + (uint32_t)TOK_TRIPS * 32;
 
-  T_DECL(r1); T_DECL(wf); T_DECL(r2); T_DECL(hd); T_DECL(in); T_DECL(tot);
-  T_ON(tot);
   bool last = false;
   while (!last && status == 0) {
     // ---- block header (warp-uniform, from a 64-bit register bit buffer) ----------------------------------
-    T_ON(in);
     ensure_input(pos >> 3, (pos >> 3) + HDR_BYTES);
-    T_OFF(in);
-    T_ON(hd);
     ++n_dblocks;
     uint64_t bb;
     int bc;
@@ -329,32 +318,28 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
     last = bb & 1;
     const int btype = (int)((bb >> 1) & 3);
     HDROP(3);
-    if (btype == 3) { status = STATUS_RETRY; T_OFF(hd); break; }
+    if (btype == 3) { status = STATUS_RETRY; break; }
 
     if (btype == 0) {
-      T_OFF(hd);
-      // ---- stored block: the resolver copies the bytes out of the staging ring, piece by piece -----------
+      // ---- stored block: the resolve kernel copies it straight from the payload ------------------------------
       pos = (HPOS() + 7) & ~7u;
       ensure_input(pos >> 3, (pos >> 3) + 4);
       const uint32_t lw = fetch32(in_ring, pos);
       const uint32_t len = lw & 0xffff, nlen = lw >> 16;
       pos += 32;
-      if (pos > total_bits || (len ^ 0xffff) != nlen || pos + len * 8 > total_bits || produced + len > isize) {
+      if (pos > total_bits || (len ^ 0xffff) != nlen || pos + len * 8 > total_bits || produced + len > isize ||
+          cur + 2 * REC_HEAD > ARENA) {
         status = STATUS_RETRY;
         break;
       }
-      uint32_t left = len;
-      while (left) {
-        const uint32_t piece = left < (uint32_t)STORE_PIECE ? left : (uint32_t)STORE_PIECE;
-        const uint32_t b0 = pos >> 3;
-        ensure_input(b0, b0 + piece);
-        wait_free();
-        send(MSG_STORED, b0, piece);
-        wait_free();                       // the staging slots of this piece may be recycled only after the copy
-        produced += piece;
-        pos += piece * 8;
-        left -= piece;
+      if (lane == 0) {
+        const uint32_t off = (pos >> 3) - skip;              // within the block's payload
+        uint16_t* h = arena + cur;
+        h[0] = REC_STORED; h[4] = (uint16_t)off; h[5] = (uint16_t)(off >> 16); h[6] = (uint16_t)len; h[7] = (uint16_t)(len >> 16);
       }
+      cur += REC_HEAD;
+      produced += len;
+      pos += len * 8;
       continue;
     }
 
@@ -441,7 +426,6 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
       if (r < 0) { status = STATUS_RETRY; break; }
     }
     __syncwarp();
-    T_OFF(hd);
 #undef HFILL
 #undef HDROP
 #undef HPOS
@@ -449,24 +433,17 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
     // ---- the codes of the block, one super-chunk of 32 sub-sequences at a time -------------------------------
     bool eob = false;
     while (!eob) {
-      if (s->r_bad) { status = STATUS_RETRY; break; }        // the resolver met a distance that reaches before the block
+      if (cur + CHUNK_MAX + REC_HEAD > ARENA) { status = STATUS_RETRY; break; }   // the record stream outgrew its arena
       const uint32_t base = pos;
-      T_ON(in);
       ensure_input(base >> 3, (base >> 3) + SUPER_BYTES + 24);
-      T_OFF(in);
       const uint32_t lim = base + (uint32_t)(lane + 1) * SUB_BITS;
       uint32_t t = base + (uint32_t)lane * SUB_BITS;
       uint32_t e_, out_, nm_, nt_, fl_;
       // round 1: where does the chain cross into each sub-sequence?  (bit positions only)
-      T_ON(r1);
       lane_decode<false>(ctx, true, t, lim, e_, out_, nm_, nt_, fl_);
-      T_OFF(r1);
       ++n_super;
-      // round 2: every lane from where its predecessor ended, recording tokens — the token area must be free
-      T_ON(wf);
-      wait_free();
-      T_OFF(wf);
-      T_ON(r2);
+      // round 2: every lane from where its predecessor ended, recording tokens into the rows of this record
+      ctx.tok = arena + cur + REC_HEAD + REC_LANES + lane;
       {
         uint32_t tn = __shfl_up_sync(0xffffffffu, e_, 1);
         if (lane == 0) tn = base;
@@ -496,9 +473,8 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
         }
         ++rounds;
       }
-      T_OFF(r2);
       n_rounds += rounds;
-      // commit the longest prefix of lanes that fits the output ring and the match list
+      // commit the longest prefix of lanes that fits the resolver's output ring and match list
       const uint32_t ncand = kstop < 32 ? kstop + 1 : vcut;
       const uint32_t inc_out = warp_incl_scan(out_, lane);
       const uint32_t inc_nm = warp_incl_scan(nm_, lane);
@@ -509,8 +485,13 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
       const uint32_t newpos = __shfl_sync(0xffffffffu, e_, kl);
       const uint32_t stop_flag = (kl == kstop) ? __shfl_sync(0xffffffffu, fl_, kl) : 0;
       if (stop_flag == F_ERR || stop_flag == F_INEND || produced + chunk_out > isize) { status = STATUS_RETRY; break; }
-      s->msg_lane[lane] = out_ | (nm_ << 16) | (nt_ << 24);
-      send(MSG_CHUNK, k, 0);
+      const uint32_t rows = __reduce_max_sync(0xffffffffu, (uint32_t)lane < k ? nt_ : 0u);
+      reinterpret_cast<uint32_t*>(arena + cur + REC_HEAD)[lane] = (uint32_t)lane < k ? (out_ | (nm_ << 16) | (nt_ << 24)) : 0u;
+      if (lane == 0) {
+        uint16_t* h = arena + cur;
+        h[0] = REC_CHUNK; h[1] = (uint16_t)k; h[2] = (uint16_t)rows;
+      }
+      cur += REC_HEAD + REC_LANES + rows * 32;
       produced += chunk_out;
       pos = newpos;
       eob = stop_flag == F_EOB;
@@ -521,34 +502,34 @@ __device__ __noinline__ void duo_decoder(const InflateArgs& a, DuoSmem* s, const
   while (waited < issued) wait_chunk(waited);
 
   if (status == 0 && (produced != isize || pos > total_bits)) status = STATUS_RETRY;
-  T_ON(wf);
-  wait_free();
-  T_OFF(wf);
-  send(MSG_DONE, (uint32_t)status, 0);
-  T_OFF(tot);
   if (lane == 0) {
-    T_PUT(r1, 0); T_PUT(wf, 1); T_PUT(r2, 2); T_PUT(hd, 3); T_PUT(in, 4); T_PUT(tot, 5);
-    atomicAdd(&counters[1], (unsigned long long)n_super);
-    atomicAdd(&counters[2], (unsigned long long)n_rounds);
-    atomicAdd(&counters[5], (unsigned long long)n_dblocks);
+    uint16_t* h = arena + cur;                 // (room for this record is part of every capacity check above)
+    h[0] = REC_DONE; h[1] = status ? 1 : 0;
+    atomicAdd(&g_tok_counters[1], (unsigned long long)n_super);
+    atomicAdd(&g_tok_counters[2], (unsigned long long)n_rounds);
+    atomicAdd(&g_tok_counters[5], (unsigned long long)n_dblocks);
   }
 }
 
-// ===================================================================================== resolver warp ====
-__device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, const uint32_t blk, const int lane,
-                                          unsigned long long* counters) {
+// ==================================================================================== resolve kernel ====
+__global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) {
+  __shared__ ResSmem sm;
+  ResSmem* s = &sm;
+  const int lane = threadIdx.x;
+  const uint32_t blk = blockIdx.x;
+  if (blk >= a.n_blocks) return;
   const uint32_t isize = a.isize[blk];
   const uint64_t obase = a.out_off[blk];
   uint8_t* gout = a.out + obase;
+  const uint8_t* pay = a.comp + a.payload_off[blk];
   const uint32_t oa = (uint32_t)(((uintptr_t)gout) & POM);   // ring index of output byte 0
+  const uint16_t* arena = a.tok + (size_t)blk * ARENA;
 
   uint32_t sbase = smem_u32(s);
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
-  const uint32_t ring = sbase + (uint32_t)offsetof(DuoSmem, out_ring);
-  const uint32_t in_ring = sbase + (uint32_t)offsetof(DuoSmem, in_ring);
-  const uint32_t mld = sbase + (uint32_t)offsetof(DuoSmem, m_ld);
-  const uint32_t mpos = sbase + (uint32_t)offsetof(DuoSmem, m_pos);
-  const uint16_t* tok = a.tok + (size_t)blk * (DUO_TOK_TRIPS * 32) + lane;
+  const uint32_t ring = sbase + (uint32_t)offsetof(ResSmem, out_ring);
+  const uint32_t mld = sbase + (uint32_t)offsetof(ResSmem, m_ld);
+  const uint32_t mpos = sbase + (uint32_t)offsetof(ResSmem, m_pos);
 
   uint32_t o = oa;          // oa + bytes produced: ring index is (o & POM)
   uint32_t flushed = 0;     // bytes already stored to HBM
@@ -582,49 +563,51 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
     const uint32_t fe = OPOS() - (o & (FLUSH_ALIGN - 1));
     if (fe > flushed && fe <= OPOS()) flush_to(fe);
   };
-  auto release = [&]() { bar_signal(BAR_FREE); };   // message, tokens and stored input bytes are consumed
 
   uint32_t n_far = 0, n_matches = 0;
   bool bad = false;
   int dstatus = 0;
-  T_DECL(wm); T_DECL(rp); T_DECL(mt); T_DECL(fw); T_DECL(rt);
-  T_ON(rt);
-  while (true) {
-    T_ON(wm);
-    bar_await(BAR_FULL);
-    T_OFF(wm);
-    const uint32_t kind = s->msg_kind, ma = s->msg_a, mb = s->msg_b;
-    if (kind == MSG_DONE) { dstatus = (int)ma; break; }
-    if (kind == MSG_STORED) {
-      const uint32_t b0 = ma, piece = mb;
-      if (!bad)
-        for (uint32_t i = lane; i < piece; i += 32)
-          sts8(ring + ((o + i) & POM), lds8(in_ring + ((b0 + i) & (PIN_RING - 1))));
-      release();
-      o += piece;
-      if (!bad) produced();
+  uint32_t cur = 0;
+  while (!bad) {
+    const uint32_t kind = __ldcg(arena + cur);
+    if (kind == REC_DONE) { dstatus = (int)__ldcg(arena + cur + 1); break; }
+    if (kind == REC_STORED) {
+      const uint32_t off = (uint32_t)__ldcg(arena + cur + 4) | ((uint32_t)__ldcg(arena + cur + 5) << 16);
+      const uint32_t len = (uint32_t)__ldcg(arena + cur + 6) | ((uint32_t)__ldcg(arena + cur + 7) << 16);
+      cur += REC_HEAD;
+      if (OPOS() + len > isize) { bad = true; break; }
+      for (uint32_t p0 = 0; p0 < len; p0 += STORE_PIECE) {
+        const uint32_t piece = len - p0 < (uint32_t)STORE_PIECE ? len - p0 : (uint32_t)STORE_PIECE;
+        const uint8_t* g = pay + off + p0;
+        for (uint32_t i = lane; i < piece; i += 32) sts8(ring + ((o + i) & POM), __ldg(g + i));
+        __syncwarp();
+        o += piece;
+        produced();
+      }
       continue;
     }
-    // ---- MSG_CHUNK: ma lanes of the decoder's super-chunk are committed -----------------------------------
-    const uint32_t k = ma;
-    const uint32_t mine = (uint32_t)lane < k ? s->msg_lane[lane] : 0;
+    if (kind != REC_CHUNK) { bad = true; break; }             // (cannot happen: the decode kernel wrote the stream)
+    // ---- a super-chunk: k lanes of the decoder are committed -----------------------------------------------
+    const uint32_t k = __ldcg(arena + cur + 1), rows = __ldcg(arena + cur + 2);
+    const uint32_t mine = (uint32_t)lane < k ? __ldcg(reinterpret_cast<const uint32_t*>(arena + cur + REC_HEAD) + lane) : 0u;
+    const uint16_t* tok = arena + cur + REC_HEAD + REC_LANES + lane;
+    cur += REC_HEAD + REC_LANES + rows * 32;
     const uint32_t out_ = mine & 0xffff, nm_ = (mine >> 16) & 0xff, nt_ = mine >> 24;
     const uint32_t inc_out = warp_incl_scan(out_, lane);
     const uint32_t inc_nm = warp_incl_scan(nm_, lane);
     const uint32_t chunk_out = __shfl_sync(0xffffffffu, inc_out, 31);
     const uint32_t n_match = __shfl_sync(0xffffffffu, inc_nm, 31);
-    const uint32_t max_nt = __reduce_max_sync(0xffffffffu, nt_);
     const uint32_t opos0 = OPOS();
-    T_ON(rp);
-    if (!bad) {
+    if (opos0 + chunk_out > isize || chunk_out > (uint32_t)OUT_BUDGET || n_match > (uint32_t)MLIST) { bad = true; break; }
+    {
       // replay: literals into the ring, matches into the list
       uint32_t oo = o + (inc_out - out_);               // ring-relative position of this lane's next byte
       uint32_t slot = inc_nm - nm_;
       uint32_t len = 0;
-      for (uint32_t t0 = 0; t0 < max_nt; t0 += 8) {
+      for (uint32_t t0 = 0; t0 < rows; t0 += 8) {
         uint32_t tk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tk[j] = (t0 + j < nt_) ? (uint32_t)__ldcg(tok + (size_t)(t0 + j) * 32) : TOK_EOB;
+        for (int j = 0; j < 8; ++j) tk[j] = (t0 + j < nt_) ? (uint32_t)__ldcs(tok + (size_t)(t0 + j) * 32) : TOK_EOB;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t v = tk[j];
@@ -642,10 +625,8 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
         }
       }
     }
-    release();
-    T_OFF(rp);
-    T_ON(mt);
-    if (!bad) {
+    __syncwarp();
+    {
       // LZ77 copies, 32 list entries at a time (one per lane, handed around by shuffles)
       const uint32_t opos_end = opos0 + chunk_out;
       const uint32_t ring_lo = opos_end > (uint32_t)POUT ? opos_end - (uint32_t)POUT : 0;   // oldest byte still in the ring
@@ -706,18 +687,14 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
           __syncwarp();
         }
       }
-      if (bad && lane == 0) s->r_bad = 1;      // the decoder stops at its next super-chunk
       n_matches += n_match;
     }
-    T_OFF(mt);
+    if (bad) break;
     o += chunk_out;
-    T_ON(fw);
-    if (!bad) produced();
-    T_OFF(fw);
+    produced();
   }
-  T_OFF(rt);
 
-  const int status = (dstatus != 0 || bad) ? STATUS_RETRY : 0;
+  const int status = (dstatus != 0 || bad || OPOS() != isize) ? STATUS_RETRY : 0;
   if (status == 0) {
     wk.walk_upto(isize, true, lane);
     if (OPOS() > flushed) flush_to(OPOS());
@@ -725,88 +702,35 @@ __device__ __noinline__ void duo_resolver(const InflateArgs& a, DuoSmem* s, cons
   if (lane == 0) {
     a.status[blk] = status;
     if (status == 0) wk.store(0);
-    if (status) atomicAdd(&counters[0], 1ull);
-    atomicAdd(&counters[3], (unsigned long long)n_far);
-    atomicAdd(&counters[4], (unsigned long long)n_matches);
-    T_PUT(wm, 8); T_PUT(rp, 9); T_PUT(mt, 10); T_PUT(fw, 11); T_PUT(rt, 12);
+    if (status) atomicAdd(&g_tok_counters[0], 1ull);
+    atomicAdd(&g_tok_counters[3], (unsigned long long)n_far);
+    atomicAdd(&g_tok_counters[4], (unsigned long long)n_matches);
   }
 #undef OPOS
 }
 
-}  // namespace
-
-// diagnostics (biodb_debug_inflate_counters), same slots as inflate_par.cu's
-__device__ unsigned long long g_duo_counters[8];
-
-__global__ void __launch_bounds__(64, BIODB_DUO_MIN_CTAS) inflate_duo_kernel(InflateArgs a) {
-  __shared__ DuoSmem sm;
-  DuoSmem* s = &sm;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t blk = blockIdx.x;
-  if (blk >= a.n_blocks) return;
-  if (threadIdx.x == 0) {
-    s->r_bad = 0;
-    // The decoder warp is the busy one (the resolver sleeps half of the time).  A CTA's two warps sit on neighbouring
-    // warp slots, i.e. on sub-partitions {0,1} or {2,3} of the SM: with the decoder always in warp 0, all decoders of an
-    // SM would share two of its four schedulers (ncu: issue slots 81 % busy on two sub-partitions, 33 % on the others).
-    // Alternating the role with bit 2 of the hardware warp slot spreads the decoders over all four.
-    uint32_t wid;
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-#ifdef BIODB_DUO_NO_BALANCE
-    wid = 0;
-#endif
-    s->dwarp = (wid >> 2) & 1u;
-  }
-  if (threadIdx.x < NCH) mbar_init(smem_u32(&s->mbar[threadIdx.x]), 1);
-  if (warp == 0) {       // (either role's warp 0 fills the table; both wait at the barrier below)
-    uint32_t b, eb;
-    s->auxtab[lane] = 0;
-    s->auxtab[32 + lane] = 0;
-    if (lane < 29) { len_base((uint32_t)lane, b, eb); s->auxtab[lane] = b; }
-    if (lane < 30) { dist_base((uint32_t)lane, b, eb); s->auxtab[32 + lane] = b; }
-  }
-  if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  __syncthreads();
-  if ((uint32_t)warp == s->dwarp) duo_decoder(a, s, blk, lane, g_duo_counters);
-  else duo_resolver(a, s, blk, lane, g_duo_counters);
-}
-
-int inflate_duo_resident_blocks(int device) {
+int inflate_tok_resident_blocks(int device) {
   int per_sm = 0, sms = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_duo_kernel, 64, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, inflate_decode_kernel, 32, 0) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
   return per_sm * sms;
 }
 
-cudaError_t inflate_duo_counters(unsigned long long* out8, int reset) {
-  cudaError_t e = cudaMemcpyFromSymbol(out8, g_duo_counters, sizeof(g_duo_counters));
+cudaError_t inflate_tok_counters(unsigned long long* out8, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out8, g_tok_counters, sizeof(g_tok_counters));
   if (e == cudaSuccess && reset) {
     unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    e = cudaMemcpyToSymbol(g_duo_counters, z, sizeof(z));
+    e = cudaMemcpyToSymbol(g_tok_counters, z, sizeof(z));
   }
   return e;
 }
 
-// phase cycle counters of a -DBIODB_DUO_TIMING build (zeros otherwise)
-cudaError_t inflate_duo_cycles(unsigned long long* out16, int reset) {
-#ifdef BIODB_DUO_TIMING
-  cudaError_t e = cudaMemcpyFromSymbol(out16, g_duo_cycles, sizeof(g_duo_cycles));
-  if (e == cudaSuccess && reset) {
-    unsigned long long z[16] = {0};
-    e = cudaMemcpyToSymbol(g_duo_cycles, z, sizeof(z));
-  }
-  return e;
-#else
-  for (int i = 0; i < 16; ++i) out16[i] = 0;
-  return cudaSuccess;
-#endif
-}
+size_t inflate_tok_token_bytes(uint32_t n_blocks) { return (size_t)n_blocks * ARENA * sizeof(uint16_t); }
 
-size_t inflate_duo_token_bytes(uint32_t n_blocks) { return (size_t)n_blocks * DUO_TOK_TRIPS * 32 * sizeof(uint16_t); }
-
-cudaError_t launch_inflate_duo(const InflateArgs& a, cudaStream_t st) {
+cudaError_t launch_inflate_tok(const InflateArgs& a, cudaStream_t st) {
   if (a.n_blocks == 0) return cudaSuccess;
-  inflate_duo_kernel<<<a.n_blocks, 64, 0, st>>>(a);
+  inflate_decode_kernel<<<a.n_blocks, 32, 0, st>>>(a);
+  inflate_resolve_kernel<<<a.n_blocks, 32, 0, st>>>(a);
   return cudaGetLastError();
 }
 

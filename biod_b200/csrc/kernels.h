@@ -47,8 +47,11 @@ struct InflateArgs {
   uint16_t* tok;                // device: token area of inflate_duo_kernel, inflate_token_bytes(n_blocks) bytes; nullptr =
                                 // launch_inflate allocates it for the call (stream-ordered)
 };
-// inflate_duo.cu: tokens (decode trips) one lane of the decoder warp may record per super-chunk
+// inflate_duo.cu / inflate_tok.cu: tokens (decode trips) one lane of the decoder warp may record per super-chunk
 constexpr int DUO_TOK_TRIPS = 128;
+// inflate_tok.cu: 16-bit words of one block's record stream (tokens + super-chunk headers): a block of 64 KiB has at
+// most 65536 tokens; rows padded to the longest lane and the headers come to ~1.3 x that in practice
+constexpr uint32_t TOK_ARENA_WORDS = 96 * 1024;
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st);
 // bytes of InflateArgs::tok for n_blocks blocks (0 when the selected kernel needs none)
 size_t inflate_token_bytes(uint32_t n_blocks);
@@ -59,6 +62,11 @@ int inflate_duo_resident_blocks(int device);
 cudaError_t inflate_duo_counters(unsigned long long* out8, int reset);
 cudaError_t inflate_duo_cycles(unsigned long long* out16, int reset);
 int inflate_par_resident_blocks(int device);
+// inflate_tok.cu: decode kernel + resolve kernel; blocks they cannot finish get status STATUS_RETRY
+cudaError_t launch_inflate_tok(const InflateArgs& a, cudaStream_t st);
+size_t inflate_tok_token_bytes(uint32_t n_blocks);
+int inflate_tok_resident_blocks(int device);
+cudaError_t inflate_tok_counters(unsigned long long* out8, int reset);
 // inflate_par.cu: the lane-parallel kernel alone; blocks it cannot finish get status STATUS_RETRY (inflate_common.cuh)
 cudaError_t launch_inflate_par(const InflateArgs& a, cudaStream_t st);
 // diagnostics of the lane-parallel kernels since the last reset: [0] blocks given up (redone by the warp-serial kernel),

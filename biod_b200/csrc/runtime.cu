@@ -290,6 +290,8 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     final_slice = true;
     return BIODB_OK;
   }
+  if (!began && r->opts.pin_input == 2 && !r->d_file.p)
+    r->ensure_pinned(next_coffset, stop_coffset == ~0ull ? r->flen : std::min<uint64_t>(r->flen, stop_coffset + 65536 + 64));
   mark_begin();
   // ---- 1. walk the BSIZE chain on the host (18 bytes per block) ----------------------------------
   blocks.clear();
@@ -542,6 +544,36 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
 
 }  // namespace biodb
 
+void biodb_reader::ensure_pinned(uint64_t lo, uint64_t hi) {
+  if (opts.pin_input != 2 || !file || lo >= hi) return;
+  const uint64_t page = 4096;
+  const uint64_t base = (uint64_t)(uintptr_t)file;
+  // page-align in address space, clip to the buffer's own pages
+  uint64_t a = ((base + lo) & ~(page - 1)), b = ((base + std::min(hi, flen) + page - 1) & ~(page - 1));
+  const uint64_t first = base & ~(page - 1), last = (base + flen + page - 1) & ~(page - 1);
+  a = std::max(a, first);
+  b = std::min(b, last);
+  std::lock_guard<std::mutex> lk(pool_mu);
+  std::vector<std::pair<uint64_t, uint64_t>> gaps;
+  uint64_t cur = a;
+  for (const auto& r : pinned) {
+    if (r.second <= cur) continue;
+    if (r.first >= b) break;
+    if (r.first > cur) gaps.push_back({cur, r.first});
+    cur = std::max(cur, r.second);
+  }
+  if (cur < b) gaps.push_back({cur, b});
+  for (const auto& g : gaps) {
+    void* p = (void*)(uintptr_t)g.first;
+    const size_t n = (size_t)(g.second - g.first);
+    bool ok = cudaHostRegister(p, n, cudaHostRegisterReadOnly) == cudaSuccess ||
+              cudaHostRegister(p, n, cudaHostRegisterDefault) == cudaSuccess;
+    cudaGetLastError();
+    if (ok) pinned.push_back(g);          // (a range that cannot be locked is simply copied from pageable memory)
+  }
+  std::sort(pinned.begin(), pinned.end());
+}
+
 biodb_status biodb_reader::build_block_index() {
   if (!block_index.empty()) return BIODB_OK;
   uint64_t pos = reads_start_coffset;
@@ -673,9 +705,11 @@ static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biod
   if (r->opts.device < 0) { if (cudaGetDevice(&r->device) != cudaSuccess) r->device = 0; }
   else r->device = r->opts.device;
   if (r->opts.blocks_per_batch <= 0) {
-    // one warp-sized CTA per BGZF block: a batch of a whole number of waves leaves no SM idle behind a partial last wave
+    // one CTA per BGZF block: a batch of a whole number of waves leaves no SM idle behind a partial last wave.
+    // 0 = three waves; -k = k waves (short passes — one shard of many — pipeline better in smaller batches)
+    const int waves = r->opts.blocks_per_batch < 0 ? -r->opts.blocks_per_batch : 3;
     int slots = inflate_resident_blocks(r->device);
-    r->opts.blocks_per_batch = slots > 0 ? 3 * slots : 8192;
+    r->opts.blocks_per_batch = slots > 0 ? waves * slots : 8192;
   }
   biodb_status s = open_common(r);
   if (s != BIODB_OK) {
@@ -701,7 +735,7 @@ biodb_status biodb_open_memory(const void* data, size_t len, const biodb_options
   biodb_reader* r = new biodb_reader;
   r->file = (const uint8_t*)data;
   r->flen = len;
-  if (opts && opts->pin_input && len)
+  if (opts && opts->pin_input == 1 && len)
     r->registered = cudaHostRegister((void*)data, len, cudaHostRegisterReadOnly) == cudaSuccess ||
                     cudaHostRegister((void*)data, len, cudaHostRegisterDefault) == cudaSuccess;
   cudaGetLastError();
@@ -745,6 +779,7 @@ void biodb_close(biodb_reader* r) {
   for (void* p : r->pileup_pool) biodb_pileup_destroy_pooled(p);
   for (void* p : r->reads_pool) reads_destroy_pooled(p);
   if (r->registered) cudaHostUnregister((void*)r->file);
+  for (const auto& g : r->pinned) cudaHostUnregister((void*)(uintptr_t)g.first);
   delete r;
 }
 
@@ -763,7 +798,7 @@ biodb_status biodb_ref_info(const biodb_reader* r, int32_t i, const char** name,
   return BIODB_OK;
 }
 uint64_t biodb_reads_start_voffset(const biodb_reader* r) { return r ? r->reads_start_vo : 0; }
-int32_t biodb_input_is_pinned(const biodb_reader* r) { return r && r->registered ? 1 : 0; }
+int32_t biodb_input_is_pinned(const biodb_reader* r) { return r && (r->registered || !r->pinned.empty()) ? 1 : 0; }
 
 uint64_t biodb_file_size(const biodb_reader* r) { return r ? r->flen : 0; }
 

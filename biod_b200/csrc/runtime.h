@@ -56,7 +56,11 @@ struct biodb_reader {
   const uint8_t* file = nullptr;
   uint64_t flen = 0;
   biodb::PinBuf owned;            // file contents when opened by path
-  bool registered = false;
+  bool registered = false;        // the whole caller buffer is page-locked (options.pin_input == 1)
+  // options.pin_input == 2: page-lock on demand, only the byte ranges passes really read (one shard of many GPUs' worth
+  // of file must not make every process pin the whole file)
+  std::vector<std::pair<uint64_t, uint64_t>> pinned;   // disjoint, sorted [lo, hi) offsets into file
+  void ensure_pinned(uint64_t lo, uint64_t hi);
   std::string text;
   std::vector<std::string> ref_names;
   std::vector<int32_t> ref_lens;

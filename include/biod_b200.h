@@ -56,10 +56,11 @@ typedef struct biodb_error {
 typedef struct biodb_options {
   int32_t device;            /* CUDA ordinal; -1 = current device */
   int32_t blocks_per_batch;  /* BGZF blocks inflated per GPU batch; 0 = default: three full waves of the inflate
-                                kernel on the device (8436 on a B200) */
+                                kernel on the device; -k = k full waves */
   int32_t verify_crc;        /* 1 = check each block's CRC32 on the device (debug builds of BioD assert it, block.d:187) */
   int32_t want_offsets;      /* 1 = fill start/end virtual offsets (withOffsets policy, readrange.d:51-66) */
-  int32_t pin_input;         /* 1 = cudaHostRegister the caller's buffer in biodb_open_memory */
+  int32_t pin_input;         /* biodb_open_memory: 1 = cudaHostRegister the caller's whole buffer at open; 2 = page-lock on
+                                demand, only the byte ranges that passes really read (a shard of the file) */
   int32_t resident_input;    /* 1 = copy the whole compressed file to HBM once at open; passes then read it from there */
   int32_t device_output;     /* 1 = biodb_pileup_next hands out DEVICE pointers (no device->host copy of the columns) */
   int32_t reserved[1];

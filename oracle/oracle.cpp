@@ -20,6 +20,9 @@
 
 #include <zlib.h>
 
+#include <cfloat>
+#include <cmath>
+#include <cctype>
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -568,6 +571,8 @@ struct Pileup {
   std::vector<uint32_t> read_idx, qoff, op_index, op_offset;
   std::vector<uint8_t> base, qual;
   std::vector<uint8_t> ref_base;      // PileupColumn.reference_base, one per column ('N' unless use_md_tag)
+  // lazy mode (orc_cpu_baseline): nothing above is filled; only what `foreach (column; pileup) n += column.coverage` sees
+  uint64_t lazy_columns = 0, lazy_entries = 0;
 };
 
 struct PileupSim {
@@ -580,6 +585,9 @@ struct PileupSim {
   int32_t ref = -1;
   size_t n_starting = 0;
   bool skip_zero;
+  // lazy = what BioD's own sweep costs: popFront keeps and advances the live reads (pileup.d:345-397) and the column
+  // hands out a slice of them; bases and qualities are computed only if the consumer asks (pileup.d:115-134)
+  bool lazy = false;
   // PileupRangeUsingMdTag (pileup.d:522-654)
   bool use_md = false;
   std::string chunk;             // _chunk: reference bases reconstructed from the current provider
@@ -738,6 +746,7 @@ struct PileupSim {
   }
 
   void emit() {
+    if (lazy) { ++out->lazy_columns; out->lazy_entries += buf.size(); return; }
     out->col_ref.push_back(ref);
     out->col_pos.push_back(position);
     out->n_start.push_back((uint32_t)n_starting);
@@ -779,10 +788,11 @@ struct PileupSim {
 // pileupColumns (pileup.d:509-519) otherwise.
 Pileup* run_pileup(const Bam* s, int single_ref, uint64_t start_from, uint64_t end_at, int skip_zero,
                    int64_t rec_begin, int64_t rec_end, int use_md = 0, const int64_t* rec_list = nullptr,
-                   uint64_t n_list = 0) {
+                   uint64_t n_list = 0, bool lazy = false) {
   Pileup* out = new Pileup;
   out->col_off.push_back(0);
   PileupSim sim;
+  sim.lazy = lazy;
   sim.s = s;
   sim.out = out;
   sim.skip_zero = skip_zero != 0;
@@ -1191,12 +1201,180 @@ int64_t orc_reads_between(orc_bam* s, uint64_t from_vo, uint64_t to_vo, int64_t*
   return (int64_t)all.size();
 }
 
+// ------------------------------------------------------- MAQ genotype likelihoods (row N3) ----
+// bio/std/hts/snpcallers/maq.d: ErrorModelCoefficients (:66-132), computeLikelihoods (:138-248), GenotypeLikelihoodInfo
+// (:252-310), MaqSnpCaller.genotypeLikelihoodInfo / makeCall / findSNPs (:388-540).  D's `real` is the x87 80-bit
+// type on x86 = long double here; float / double roundings happen where D's types make them happen.
+//
+// Restatement-defined (the reference leaves them open, pinned here and in the CUDA kernel):
+//  * computeLikelihoods sorts the read bases with Phobos' UNSTABLE sort!"a.quality < b.quality" (maq.d:151): the order
+//    of bases of equal quality is whatever that Phobos version's shortSort does.  Pinned: STABLE — bases of equal quality
+//    keep their order in the column.  (The order matters: it decides which strand's dependency weight fk(w) meets which
+//    beta(q, n, k).)
+//  * more than 255 valid bases are subsampled with randomSample (maq.d:142-147), which is seeded unpredictably.  Pinned:
+//    the first 255 valid bases of the column.
+struct MaqTables {
+  std::vector<double> fk, beta, lhet;
+  MaqTables(double depcorr, double eta) : fk(256), beta((size_t)256 * 256 * 64, 0.0), lhet((size_t)256 * 256, 0.0) {
+    for (size_t n = 0; n < 256; ++n) fk[n] = pow(1.0 - depcorr, (double)n) * (1.0 - eta) + eta;      // maq.d:85-87
+    static double lC[256][256];
+    double lG[256];
+    const long double LN2l = 0.693147180559945309417232121458176568L, LN10l = 2.302585092994045684017991454684364208L;
+    for (size_t n = 0; n <= 255; ++n) {                                                              // :95-103
+      lG[n] = lgamma((double)(n + 1));
+      for (size_t k = 0; k <= n / 2; ++k) {
+        lC[n][n - k] = lC[n][k] = lG[n] - lG[k] - lG[n - k];
+        // `lC[n][k] - n * cast(double)LN2`
+        lhet[n << 8 | (n - k)] = lhet[n << 8 | k] = lC[n][k] - (double)n * (double)LN2l;
+      }
+    }
+    for (size_t q = 1; q < 64; ++q) {                                                                // :105-119
+      const long double e = powl(10.0L, -((long double)q) / 10.0L);
+      const long double le = logl(e), le1 = logl(1.0L - e);
+      for (int n = 1; n <= 255; ++n) {
+        long double sum = 0.0L, sum1 = 0.0L;
+        for (int k = n; k >= 0; --k) {
+          sum = sum1 + expl((long double)lC[n][k] + k * le + (n - k) * le1);
+          beta[q << 16 | (size_t)n << 8 | (size_t)k] = (double)(-10.0L / LN10l * logl(sum1 / sum));
+          sum1 = sum;
+        }
+      }
+    }
+  }
+};
+
+// Base16 internal codes of A, C, G, T (bio/core/base.d); Base5 codes are 0..3, N = 4
+static inline int base16_code(uint8_t ch) {
+  static const char* tab = "=ACMGRSVTWYHKDBN";
+  for (int i = 0; i < 16; ++i) if (tab[i] == (char)toupper(ch)) return i;
+  return 15;
+}
+
+// computeLikelihoods (maq.d:138-248): scores[25] indexed by DiploidGenotype!Base5 code (first * 5 + second), FLT_MIN =
+// absent (TinyMap useDefaultValue with float.min).  base / qual / rev: the valid read bases of the column, in column order.
+static void maq_likelihoods(const MaqTables& T, const uint8_t* base, const uint8_t* qual, const uint8_t* rev, size_t n_in,
+                            float scores[25]) {
+  const size_t n = std::min<size_t>(n_in, 255);
+  std::vector<uint32_t> order(n);
+  for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return qual[a] < qual[b]; });
+  uint32_t w[32] = {0}, c[16] = {0};
+  double fsum[16] = {0}, bsum[16] = {0};
+  for (size_t r = n; r-- > 0;) {                       // foreach_reverse: highest quality first
+    const uint32_t i = order[r];
+    uint32_t quality = qual[i];
+    if (quality < 4) quality = 4;
+    if (quality > 63) quality = 63;
+    const int b = base16_code(base[i]);
+    const int bws = b * 2 + (rev[i] ? 1 : 0);
+    fsum[b] += T.fk[w[bws]];
+    bsum[b] += T.fk[w[bws]] * T.beta[(size_t)quality << 16 | n << 8 | c[b]];
+    c[b] += 1;
+    w[bws] += 1;
+  }
+  static const int nuc[4] = {1, 2, 4, 8};                // Base16 codes of A, C, G, T
+  const long double C = 10.0L / 2.302585092994045684017991454684364208L;   // `immutable C = 10.0 / LN10` is a real
+  for (int g = 0; g < 25; ++g) scores[g] = FLT_MIN;
+  for (int i = 0; i < 4; ++i) {
+    float tmp1 = 0.0f, tmp3 = 0.0f;
+    int tmp2 = 0;
+    for (int k = 0; k < 4; ++k)
+      if (k != i) { tmp1 = (float)((double)tmp1 + bsum[nuc[k]]); tmp2 += (int)c[nuc[k]]; tmp3 = (float)((double)tmp3 + fsum[nuc[k]]); }
+    scores[i * 5 + i] = tmp2 > 0 ? tmp1 : 0.0f;          // homozygous
+    for (int j = i + 1; j < 4; ++j) {                    // heterozygous: dG(b2, b1) with b2 the later nucleotide
+      const int cij = (int)(c[nuc[i]] + c[nuc[j]]);
+      tmp1 = tmp3 = 0.0f;
+      tmp2 = 0;
+      for (int k = 0; k < 4; ++k)
+        if (k != i && k != j) { tmp1 = (float)((double)tmp1 + bsum[nuc[k]]); tmp2 += (int)c[nuc[k]]; tmp3 = (float)((double)tmp3 + fsum[nuc[k]]); }
+      const double lh = T.lhet[(size_t)cij << 8 | c[nuc[j]]];
+      scores[j * 5 + i] = tmp2 > 0 ? (float)((long double)tmp1 - C * (long double)lh) : (float)(-C * (long double)lh);
+    }
+    for (int k = 0; k < 4; ++k) {                        // :236-241
+      const int g = i * 5 + k;
+      if (scores[g] != FLT_MIN && scores[g] < 0.0f) scores[g] = 0.0f;
+    }
+  }
+}
+
+struct MaqResult {
+  std::vector<uint32_t> n_valid;        // per column
+  std::vector<uint8_t> gt0, gt1;        // best and second genotype (Base5 pair codes), 255 = none
+  std::vector<float> s0, s1;            // their scores
+  std::vector<float> scores;            // 25 per column (FLT_MIN = absent)
+};
+
+extern "C" {
+
+typedef struct MaqTables orc_maq;
+orc_maq* orc_maq_new(double depcorr, double eta) { return new MaqTables(depcorr, eta); }
+void orc_maq_free(orc_maq* t) { delete t; }
+const double* orc_maq_fk(const orc_maq* t) { return t->fk.data(); }
+const double* orc_maq_beta(const orc_maq* t) { return t->beta.data(); }
+const double* orc_maq_lhet(const orc_maq* t) { return t->lhet.data(); }
+// computeLikelihoods over explicit read bases (already filtered): scores[25]
+void orc_maq_compute(const orc_maq* t, const uint8_t* base, const uint8_t* qual, const uint8_t* rev, uint64_t n, float* scores) {
+  maq_likelihoods(*t, base, qual, rev, (size_t)n, scores);
+}
+
+// MaqSnpCaller.genotypeLikelihoodInfo over every column of a pileup (maq.d:388-457) + the ordering of
+// GenotypeLikelihoodInfo (:258-277: genotypes in code order, insertion-sorted by score, equal scores keep code order).
+// Per column: n_valid, best / second genotype and their scores; makeCall's quality is s1 - s0 (:480-482).
+typedef struct MaqResult orc_maq_result;
+orc_maq_result* orc_maq_run(orc_bam* s, const orc_pileup* p, const orc_maq* t, int min_base_quality) {
+  decode_records(s);
+  MaqResult* r = new MaqResult;
+  const size_t nc = p->col_pos.size();
+  std::vector<uint8_t> b, q, rv;
+  for (size_t c = 0; c < nc; ++c) {
+    b.clear(); q.clear(); rv.clear();
+    for (uint64_t e = p->col_off[c]; e < p->col_off[c + 1]; ++e) {
+      const uint32_t rd = p->read_idx[e];
+      if (p->qual[e] < min_base_quality) continue;        // current_base_quality < minimum_base_quality
+      if (p->base[e] == '-') continue;
+      b.push_back(p->base[e]);
+      q.push_back(std::min<uint8_t>(p->qual[e], s->mapq[rd]));   // min(base quality, mapping quality)
+      rv.push_back((s->flag[rd] & 0x10) ? 1 : 0);
+    }
+    float sc[25];
+    for (int g = 0; g < 25; ++g) sc[g] = FLT_MIN;
+    uint8_t g0 = 255, g1 = 255;
+    float s0 = 0, s1 = 0;
+    if (!b.empty()) {
+      maq_likelihoods(*t, b.data(), q.data(), rv.data(), b.size(), sc);
+      int buf[25], k = 0;
+      for (int g = 0; g < 25; ++g) {
+        if (sc[g] == FLT_MIN) continue;
+        int j = k;
+        while (j > 0 && sc[buf[j - 1]] > sc[g]) { buf[j] = buf[j - 1]; --j; }
+        buf[j] = g;
+        ++k;
+      }
+      if (k >= 2) { g0 = (uint8_t)buf[0]; g1 = (uint8_t)buf[1]; s0 = sc[buf[0]]; s1 = sc[buf[1]]; }
+    }
+    r->n_valid.push_back((uint32_t)b.size());
+    r->gt0.push_back(g0); r->gt1.push_back(g1); r->s0.push_back(s0); r->s1.push_back(s1);
+    r->scores.insert(r->scores.end(), sc, sc + 25);
+  }
+  return r;
+}
+void orc_maq_result_free(orc_maq_result* r) { delete r; }
+const uint32_t* orc_maq_n_valid(const orc_maq_result* r) { return r->n_valid.data(); }
+const uint8_t* orc_maq_gt0(const orc_maq_result* r) { return r->gt0.data(); }
+const uint8_t* orc_maq_gt1(const orc_maq_result* r) { return r->gt1.data(); }
+const float* orc_maq_s0(const orc_maq_result* r) { return r->s0.data(); }
+const float* orc_maq_s1(const orc_maq_result* r) { return r->s1.data(); }
+const float* orc_maq_scores(const orc_maq_result* r) { return r->scores.data(); }
+
+}  // extern "C"
+
 // ------------------------------------------------------- CPU baseline legs ----
 // "Restated BioD CPU path (libz, g++ -O3), not the D binary" (BASELINE.md §2):
 // inflate with `threads` worker threads the way BgzfInputStream hands whole
 // blocks to a TaskPool (inputstream.d:414-417; default totalCPUs-1 workers),
 // framing + field decode + pileup single-threaded by construction
 // (readrange.d:118-173, pileup.d:345-397).  Returns seconds per leg.
+static thread_local double g_last_lazy_pileup_s = 0;
 int orc_cpu_baseline(const uint8_t* data, uint64_t len, int threads, int do_pileup, double* t_inflate,
                      double* t_decode, double* t_pileup, uint64_t* n_records, uint64_t* n_columns,
                      uint64_t* n_entries, uint64_t* checksum) {
@@ -1264,8 +1442,21 @@ int orc_cpu_baseline(const uint8_t* data, uint64_t len, int threads, int do_pile
     if (st) { delete s; return st; }
   }
   *checksum = cs;
+  // the same sweep without materialising the columns: BioD's `foreach (column; pileupColumns(reads)) n += column.coverage`
+  g_last_lazy_pileup_s = 0;
+  if (do_pileup) {
+    double t4 = now();
+    Pileup* p = run_pileup(s, 0, 0, ~0ull, 1, 0, -1, 0, nullptr, 0, true);
+    g_last_lazy_pileup_s = now() - t4;
+    const bool same = p->lazy_columns == *n_columns && p->lazy_entries == *n_entries;
+    delete p;
+    if (!same) { delete s; return ORC_ERR_FORMAT; }
+  }
   delete s;
   return 0;
 }
+
+// seconds the lazy sweep of the last orc_cpu_baseline call took (same thread)
+double orc_cpu_baseline_lazy_seconds() { return g_last_lazy_pileup_s; }
 
 }  // extern "C"

@@ -97,6 +97,19 @@ def lib():
                                        C.c_void_p, u64]
         L.orc_reads_between.restype = C.c_int64
         L.orc_reads_between.argtypes = [C.c_void_p, u64, u64, C.c_void_p, u64]
+        L.orc_maq_new.restype = C.c_void_p
+        L.orc_maq_new.argtypes = [C.c_double, C.c_double]
+        L.orc_maq_free.argtypes = [C.c_void_p]
+        for f in ("orc_maq_fk", "orc_maq_beta", "orc_maq_lhet"):
+            getattr(L, f).restype = C.c_void_p
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.orc_maq_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p]
+        L.orc_maq_run.restype = C.c_void_p
+        L.orc_maq_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_maq_result_free.argtypes = [C.c_void_p]
+        for f in ("orc_maq_n_valid", "orc_maq_gt0", "orc_maq_gt1", "orc_maq_s0", "orc_maq_s1", "orc_maq_scores"):
+            getattr(L, f).restype = C.c_void_p
+            getattr(L, f).argtypes = [C.c_void_p]
         L.orc_cpu_baseline.restype = C.c_int
         L.orc_cpu_baseline.argtypes = [C.c_void_p, u64, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 3 + \
             [C.POINTER(u64)] * 4
@@ -133,7 +146,8 @@ class OracleError(Exception):
 class Pileup:
     """Result of makePileup / pileupColumns restated on the CPU."""
 
-    def __init__(self, L, h):
+    def __init__(self, L, h, keep=False):
+        self._L, self._h = L, (h if keep else None)
         self.status = L.orc_pileup_status(h)
         self.msg = L.orc_pileup_errmsg(h).decode()
         self.ref_id = L.orc_pileup_ref_id(h)
@@ -144,7 +158,13 @@ class Pileup:
             setattr(self, name, _arr(getattr(L, "orc_pileup_" + name)(h), n, dt))
         self.col_off = _arr(L.orc_pileup_col_off(h), nc + 1, np.uint64)
         self.ref_base = _arr(L.orc_pileup_ref_base(h), nc, np.uint8)     # PileupColumn.reference_base ('N' unless use_md_tag)
-        L.orc_pileup_free(h)
+        if not keep:
+            L.orc_pileup_free(h)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_pileup_free(self._h)
+            self._h = None
 
     def bases(self, c):
         a, b = int(self.col_off[c]), int(self.col_off[c + 1])
@@ -251,13 +271,25 @@ class Bam:
         return r[o:].tobytes()
 
     # -- pileup ------------------------------------------------------------
-    def make_pileup(self, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True, use_md_tag=False):
+    def make_pileup(self, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True, use_md_tag=False, keep=False):
         run = self._L.orc_pileup_run_md if use_md_tag else self._L.orc_pileup_run
-        return Pileup(self._L, run(self._h, 1, start_from, end_at, int(skip_zero_coverage)))
+        return Pileup(self._L, run(self._h, 1, start_from, end_at, int(skip_zero_coverage)), keep)
 
-    def pileup_columns(self, skip_zero_coverage=True, use_md_tag=False):
+    def pileup_columns(self, skip_zero_coverage=True, use_md_tag=False, keep=False):
         run = self._L.orc_pileup_run_md if use_md_tag else self._L.orc_pileup_run
-        return Pileup(self._L, run(self._h, 0, 0, 2**64 - 1, int(skip_zero_coverage)))
+        return Pileup(self._L, run(self._h, 0, 0, 2**64 - 1, int(skip_zero_coverage)), keep)
+
+    def maq(self, pileup, tables, min_base_quality=13):
+        """MaqSnpCaller.genotypeLikelihoodInfo over every column of `pileup` (made with keep=True); see Maq."""
+        assert pileup._h, "make the pileup with keep=True"
+        L = self._L
+        r = L.orc_maq_run(self._h, pileup._h, tables._h, int(min_base_quality))
+        nc = pileup.n_columns
+        out = dict(n_valid=_arr(L.orc_maq_n_valid(r), nc, np.uint32), gt0=_arr(L.orc_maq_gt0(r), nc, np.uint8),
+                   gt1=_arr(L.orc_maq_gt1(r), nc, np.uint8), s0=_arr(L.orc_maq_s0(r), nc, np.float32),
+                   s1=_arr(L.orc_maq_s1(r), nc, np.float32), scores=_arr(L.orc_maq_scores(r), nc * 25, np.float32).reshape(nc, 25))
+        L.orc_maq_result_free(r)
+        return out
 
     def make_pileup_of(self, indices, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True, use_md_tag=False,
                        single_ref=True):
@@ -276,6 +308,32 @@ class Bam:
                           single_ref=True):
         return Pileup(self._L, self._L.orc_pileup_run_range(self._h, int(single_ref), start_from, end_at,
                                                             int(skip_zero_coverage), rec_begin, rec_end))
+
+
+class Maq:
+    """ErrorModelCoefficients of the MAQ model (bio/std/hts/snpcallers/maq.d:66-132) and computeLikelihoods (:138-248)."""
+
+    def __init__(self, depcorr=0.17, eta=0.03):
+        # MaqSnpCaller keeps depcorr / eta as floats and hands them to ErrorModel(float, float) (maq.d:329-338,346-347)
+        self._L = lib()
+        self._h = self._L.orc_maq_new(float(np.float32(depcorr)), float(np.float32(eta)))
+        self.fk = _arr(self._L.orc_maq_fk(self._h), 256, np.float64)
+        self.beta = _arr(self._L.orc_maq_beta(self._h), 256 * 256 * 64, np.float64)
+        self.lhet = _arr(self._L.orc_maq_lhet(self._h), 256 * 256, np.float64)
+
+    def compute(self, bases, quals, reverse):
+        """computeLikelihoods over explicit read bases: 25 scores by DiploidGenotype!Base5 code (FLT_MIN = absent)."""
+        b = np.frombuffer(bases if isinstance(bases, bytes) else bytes(bases), dtype=np.uint8).copy()
+        q = np.ascontiguousarray(quals, dtype=np.uint8)
+        r = np.ascontiguousarray(reverse, dtype=np.uint8)
+        out = np.zeros(25, dtype=np.float32)
+        self._L.orc_maq_compute(self._h, b.ctypes.data, q.ctypes.data, r.ctypes.data, len(b), out.ctypes.data)
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.orc_maq_free(self._h)
+            self._h = None
 
 
 class Bai:
@@ -336,5 +394,6 @@ def cpu_baseline(data, threads, do_pileup=True):
                             C.byref(nr), C.byref(nc), C.byref(ne), C.byref(cs))
     if st:
         raise OracleError(st, "cpu baseline failed")
-    return dict(t_inflate=ti.value, t_decode=td.value, t_pileup=tp.value, n_records=nr.value,
-                n_columns=nc.value, n_entries=ne.value, checksum=cs.value)
+    L.orc_cpu_baseline_lazy_seconds.restype = C.c_double
+    return dict(t_inflate=ti.value, t_decode=td.value, t_pileup=tp.value, t_pileup_lazy=L.orc_cpu_baseline_lazy_seconds(),
+                n_records=nr.value, n_columns=nc.value, n_entries=ne.value, checksum=cs.value)
