@@ -352,6 +352,9 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
                       "h2d_bytes_per_step": int(es[-1][0].h2d_bytes), "d2h_bytes_per_step": int(es[-1][0].d2h_bytes),
                       "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned,
                       "pcie_d2h_gbs": es[-1][0].d2h_bytes / (e_ms * 1e-3) / 1e9,
+                      "stage_ms": {"inflate": float(np.mean([s[0].inflate_ms for s in es])),
+                                   "record_scan": float(np.mean([s[0].scan_ms for s in es])),
+                                   "pileup": float(np.mean([s[0].pileup_ms for s in es]))},
                       "columns": "compact_reads (sequential, lossless): positions as runs; per column n_starting_here, "
                                  "last_read, 64-bit window mask (+ stragglers); per entry base + qual",
                       "with_explicit_read_idx": {"ms_per_step": float(ex[0].total_ms), "d2h_bytes_per_step": int(ex[0].d2h_bytes),

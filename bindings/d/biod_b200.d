@@ -46,7 +46,12 @@ extern (C) nothrow @nogc {
     }
     struct biodb_pileup_params {
         int single_ref; int skip_zero_coverage; int use_md_tag; int want_query_offset;
-        ulong start_from; ulong end_at; int counts_only; int compact_reads; int[2] reserved;
+        ulong start_from; ulong end_at; int counts_only; int compact_reads; int maq_mode; int[1] reserved;
+    }
+    struct biodb_maq_params { float depcorr = 0.17f; float eta = 0.03f; float minimum_call_quality = 6.0f; int minimum_base_quality = 13; }
+    struct biodb_shard_info {
+        ulong first_voffset, end_voffset, halo_voffset; int lo_ref, hi_ref; long lo_pos, hi_pos;
+        ulong n_halo_records, n_own_records;
     }
     struct biodb_column_batch {
         ulong n_columns; ulong n_entries; int ref_id; int last_of_pileup;
@@ -57,6 +62,10 @@ extern (C) nothrow @nogc {
         ulong n_runs; const(ulong)* run_pos; const(uint)* run_first_col;
         const(ubyte)* base4; ulong n_special; const(uint)* special_entry; const(ubyte)* special_base;
         const(ubyte)* reference_base;   // use_md_tag: one per column (pileup.d:252-254), else null
+        // maq_mode: the calls of MaqSnpCaller.findSNPs among the batch's columns; mode 2: the two best genotypes per column
+        ulong n_calls; const(uint)* call_col; const(ulong)* call_pos; const(ubyte)* call_gt; const(ubyte)* call_ref;
+        const(float)* call_qual;
+        const(ubyte)* maq_gt0; const(ubyte)* maq_gt1; const(float)* maq_s0; const(float)* maq_s1; const(ushort)* maq_n_valid;
     }
     void biodb_default_options(biodb_options*);
     int biodb_open(const(char)* path, const(biodb_options)*, biodb_reader**);
@@ -74,6 +83,16 @@ extern (C) nothrow @nogc {
     float biodb_reads_progress(const(biodb_reads)*);
     int biodb_pileup_begin(biodb_reader*, const(biodb_pileup_params)*, biodb_pileup**);
     int biodb_pileup_next(biodb_pileup*, biodb_column_batch*);
+    int biodb_pileup_maq_params(biodb_pileup*, const(biodb_maq_params)*);
+    // shards / chunks (pileupChunks semantics, pileup.d:859-1015) with exact halos: see include/biod_b200.h
+    int biodb_shard_cuts(biodb_reader*, uint n_shards, ulong* cut_voffset, int* cut_ref, long* cut_pos);
+    int biodb_pileup_begin_shard(biodb_reader*, const(biodb_pileup_params)*, uint shard, uint n_shards, uint halo_blocks, biodb_pileup**);
+    int biodb_pileup_begin_shard_at(biodb_reader*, const(biodb_pileup_params)*, uint shard, uint n_shards, ulong halo_voffset,
+                                    biodb_pileup**);
+    void biodb_pileup_shard_info(const(biodb_pileup)*, biodb_shard_info*);
+    void biodb_pileup_shard_reach(const(biodb_pileup)*, ulong* reach);
+    int biodb_pileup_begin_range(biodb_reader*, const(biodb_pileup_params)*, ulong from_voffset, ulong to_voffset,
+                                 int lo_ref, long lo_pos, int hi_ref, long hi_pos, biodb_pileup**);
     void biodb_pileup_end(biodb_pileup*);
     int biodb_pileup_ref_id(const(biodb_pileup)*);
     // BAI random access (row N2)
@@ -316,6 +335,21 @@ struct GpuPileup {
         if (biodb_pileup_begin_region(h, ix, ref_id, beg, end, &prm, &_p) != BIODB_OK) raise(biodb_last_error(h));
         fetch();
     }
+    /// one element of pileupChunks: the records that start in [from_voffset, to_voffset), columns [beg, end) of ref_id
+    /// (makePileup(chain(prev_chunk, chunk), use_md_tag, beg, end), pileup.d:905-913)
+    this(biodb_reader* h, ulong from_voffset, ulong to_voffset, int ref_id, ulong beg, ulong end, bool use_md_tag) {
+        _h = h;
+        biodb_pileup_params prm;
+        prm.skip_zero_coverage = true; prm.use_md_tag = use_md_tag; prm.compact_reads = true;
+        if (biodb_pileup_begin_range(h, &prm, from_voffset, to_voffset, ref_id, cast(long)beg, ref_id, cast(long)end, &_p) != BIODB_OK)
+            raise(biodb_last_error(h));
+        _start = beg; _end = end; _ref = ref_id;
+        fetch();
+    }
+    private ulong _start, _end; private int _ref = -1;
+    /// AbstractPileup.start_position / end_position (pileup.d:440-452) of a chunk
+    ulong start_position() @property const { return _start; }
+    ulong end_position() @property const { return _end; }
     ~this() { if (_p !is null) { biodb_pileup_end(_p); _p = null; } }
     @disable this(this);
     bool empty() @property const { return _empty; }
@@ -368,4 +402,79 @@ auto makePileup(GpuRegion r, bool use_md_tag = false, ulong start_from = 0, ulon
 }
 auto pileupColumns(GpuBamReader bam, bool use_md_tag = false, bool skip_zero_coverage = true) {
     return GpuPileup(bam.handle, false, use_md_tag, 0, ulong.max, skip_zero_coverage);
+}
+
+/// pileupChunks(reads, use_md_tag, block_size, start_from, end_at) (pileup.d:1011-1015): non-overlapping consecutive
+/// pileups that can be processed in parallel — here each one is a range pileup on the GPU, independent of the others.
+/// The cuts follow chunksConsumingLessThan (splitter.d:66-90) and PileupChunkRange (pileup.d:876-940) over the record
+/// tables of one reads pass (reader opened with want_offsets); the halo of a chunk is EXACT (the first earlier read of
+/// the reference that reaches beyond the chunk's first column) where BioD keeps 2 x the median read length.
+/// biod_b200/bam.py: chunk_plan is the same arithmetic, checked against a line-by-line simulation of the D code.
+struct GpuChunkPlan { size_t first, last, halo; int ref_id; ulong start_position, end_position; }
+
+GpuChunkPlan[] chunkPlan(const(int)[] ref_id, const(int)[] pos, const(int)[] end_pos, const(int)[] rec_size,
+                         size_t block_size = 16_384_000, ulong start_from = 0, ulong end_at = ulong.max) {
+    import std.algorithm : max, min;
+    GpuChunkPlan[] plan;
+    const n = ref_id.length;
+    size_t[2][] chunks;
+    for (size_t i = 0; i < n;) {
+        size_t total = 4 + rec_size[i], j = i + 1;
+        while (total <= block_size && j < n && ref_id[j] == ref_id[i]) { total += 4 + rec_size[j]; ++j; }
+        chunks ~= [i, j];
+        i = j;
+    }
+    bool started = false, have_prev = false;
+    size_t prev_last;
+    foreach (k, ch; chunks) {
+        const i = ch[0], j = ch[1];
+        const rid = ref_id[i];
+        if (rid < 0) continue;
+        long right_end = long.min;
+        foreach (r; i .. j) right_end = max(right_end, end_pos[r]);
+        long beg;
+        size_t halo = i;
+        if (!started) {
+            beg = pos[i];
+            if (cast(ulong)beg >= end_at) break;
+            if (right_end <= cast(long)start_from) continue;
+            started = true;
+        } else if (have_prev && ref_id[prev_last - 1] == rid) {
+            beg = pos[prev_last - 1];
+            size_t r0 = i;
+            while (r0 > 0 && ref_id[r0 - 1] == rid) --r0;
+            foreach (r; r0 .. i) if (end_pos[r] > beg) { halo = r; break; }
+        } else {
+            beg = pos[i];
+        }
+        long end = pos[j - 1];
+        if (k + 1 >= chunks.length || ref_id[chunks[k + 1][0]] != ref_id[j - 1]) end = right_end;
+        plan ~= GpuChunkPlan(i, j, halo, rid, max(cast(ulong)beg, start_from), min(cast(ulong)end, end_at));
+        have_prev = true;
+        prev_last = j;
+    }
+    return plan;
+}
+
+/// MaqSnpCaller.findSNPs over the GPU pileup (maq.d:489-540): the likelihoods are computed on the device, only the
+/// calls come back.  Genotype codes are DiploidGenotype!Base5's (first * 5 + second).
+struct GpuSnpCall { int ref_id; ulong position; char reference_base; ubyte genotype; float quality; }
+
+GpuSnpCall[] findSNPs(GpuBamReader bam, biodb_maq_params mp = biodb_maq_params.init, bool single_ref = true) {
+    biodb_pileup_params prm;
+    prm.single_ref = single_ref; prm.skip_zero_coverage = true; prm.use_md_tag = true; prm.end_at = ulong.max; prm.maq_mode = 1;
+    biodb_pileup* p;
+    if (biodb_pileup_begin(bam.handle, &prm, &p) != BIODB_OK) raise(biodb_last_error(bam.handle));
+    scope (exit) biodb_pileup_end(p);
+    enforce(biodb_pileup_maq_params(p, &mp) == BIODB_OK, "invalid MAQ parameters");
+    GpuSnpCall[] calls;
+    biodb_column_batch b;
+    while (true) {
+        const st = biodb_pileup_next(p, &b);
+        if (st == BIODB_EOF) break;
+        if (st != BIODB_OK) raise(biodb_last_error(bam.handle));
+        foreach (k; 0 .. cast(size_t)b.n_calls)
+            calls ~= GpuSnpCall(b.ref_id, b.call_pos[k], cast(char)b.call_ref[k], b.call_gt[k], b.call_qual[k]);
+    }
+    return calls;
 }

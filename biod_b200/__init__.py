@@ -5,4 +5,4 @@ Importing the package does not need a GPU; opening a reader does, and fails loud
 """
 from . import _capi  # noqa: F401
 from .bam import (BaiFile, BamFormatException, BamWriter, IndexBuilder, createIndex, BgzfOutputStream, bgzf_compress, BamRead, BamReader, BgzfException, CudaUnavailable, PileupColumn,  # noqa: F401
-                  PileupException, ReadException, ZlibException, makePileup, pileupColumns, pileupChunks, PileupChunk, chunk_plan)
+                  PileupException, ReadException, ZlibException, makePileup, pileupColumns, pileupChunks, PileupChunk, chunk_plan, MaqSnpCaller, DiploidCall5)

@@ -44,7 +44,12 @@ class Stats(C.Structure):
 class PileupParams(C.Structure):
     _fields_ = [("single_ref", C.c_int32), ("skip_zero_coverage", C.c_int32), ("use_md_tag", C.c_int32),
                 ("want_query_offset", C.c_int32), ("start_from", C.c_uint64), ("end_at", C.c_uint64),
-                ("counts_only", C.c_int32), ("compact_reads", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("counts_only", C.c_int32), ("compact_reads", C.c_int32), ("maq_mode", C.c_int32), ("reserved", C.c_int32 * 1)]
+
+
+class MaqParams(C.Structure):
+    _fields_ = [("depcorr", C.c_float), ("eta", C.c_float), ("minimum_call_quality", C.c_float),
+                ("minimum_base_quality", C.c_int32)]
 
 
 class ShardInfo(C.Structure):
@@ -60,7 +65,11 @@ class ColumnBatch(C.Structure):
                 ("last_read", u32p), ("live_mask", u64p), ("n_stragglers", C.c_uint64), ("strag_col", u32p), ("strag_idx", u32p),
                 ("n_runs", C.c_uint64), ("run_pos", u64p), ("run_first_col", u32p),
                 ("base4", u8p), ("n_special", C.c_uint64), ("special_entry", u32p), ("special_base", u8p),
-                ("reference_base", u8p)]
+                ("reference_base", u8p),
+                ("n_calls", C.c_uint64), ("call_col", u32p), ("call_pos", u64p), ("call_gt", u8p), ("call_ref", u8p),
+                ("call_qual", C.POINTER(C.c_float)),
+                ("maq_gt0", u8p), ("maq_gt1", u8p), ("maq_s0", C.POINTER(C.c_float)), ("maq_s1", C.POINTER(C.c_float)),
+                ("maq_n_valid", C.POINTER(C.c_uint16))]
 
 
 _lib = None
@@ -115,6 +124,8 @@ def lib():
     L.biodb_pileup_begin_range.restype = C.c_int
     L.biodb_pileup_begin_range.argtypes = [vp, C.POINTER(PileupParams), C.c_uint64, C.c_uint64, C.c_int32, C.c_int64, C.c_int32,
                                            C.c_int64, C.POINTER(vp)]
+    L.biodb_pileup_maq_params.restype = C.c_int
+    L.biodb_pileup_maq_params.argtypes = [vp, C.POINTER(MaqParams)]
     L.biodb_pileup_next.restype = C.c_int
     L.biodb_pileup_next.argtypes = [vp, C.POINTER(ColumnBatch)]
     L.biodb_pileup_end.argtypes = [vp]
@@ -198,7 +209,7 @@ EXPORTS = [
     "biodb_file_size", "biodb_input_is_pinned", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_begin_shard_at", "biodb_pileup_shard_info",
-    "biodb_pileup_shard_reach", "biodb_shard_cuts", "biodb_pileup_begin_range",
+    "biodb_pileup_shard_reach", "biodb_shard_cuts", "biodb_pileup_begin_range", "biodb_pileup_maq_params",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_inflate_cycles", "biodb_debug_md_chain",
     "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",
     "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",

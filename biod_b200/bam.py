@@ -464,7 +464,7 @@ class BamReader:
 
     def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
                        want_query_offset=False, copy=False, shard=None, halo_blocks=8, halo_voffset=None, shard_info=None,
-                       counts_only=False, compact_reads=False, region=None, record_range=None):
+                       counts_only=False, compact_reads=False, region=None, record_range=None, maq=None, maq_mode=0):
         """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015): its halo
         starts halo_blocks BGZF blocks in front of it (a guess) or at the record at halo_voffset; shard_info receives
         the biodb_shard_info fields plus "reach" (see biod_b200.stitch.exact_halos).
@@ -477,6 +477,7 @@ class BamReader:
         p.want_query_offset, p.start_from, p.end_at = int(want_query_offset), start_from, end_at
         p.counts_only = int(counts_only)
         p.compact_reads = int(compact_reads)
+        p.maq_mode = int(maq_mode)
         pl = C.c_void_p()
         if region is not None:
             st = L.biodb_pileup_begin_region(self._h, self._bai()._h, region[0], region[1], region[2], C.byref(p), C.byref(pl))
@@ -492,6 +493,11 @@ class BamReader:
             raise ValueError("biodb_pileup_begin: invalid arguments")
         if st != capi.OK:
             self._err()
+        if maq_mode and maq is not None:
+            mp = capi.MaqParams(maq.depcorr, maq.eta, maq.minimum_call_quality, maq.minimum_base_quality)
+            if L.biodb_pileup_maq_params(pl, C.byref(mp)) != capi.OK:
+                L.biodb_pileup_end(pl)
+                raise ValueError("biodb_pileup_maq_params: invalid arguments")
         try:
             while True:
                 cb = capi.ColumnBatch()
@@ -597,8 +603,25 @@ class ColumnBatch:
         g = (lambda a: a.copy()) if copy else (lambda a: a)
         nc, ne = int(cb.n_columns), int(cb.n_entries)
         self.n_columns, self.n_entries, self.ref_id = nc, ne, int(cb.ref_id)
-        self.n_starting_here = g(_np(cb.n_starting_here, nc, np.uint32))
         self.compact = None
+        # maq_mode: the calls of findSNPs, and (mode 2) the two best genotypes of every column
+        ncall = int(cb.n_calls)
+        self.calls = None
+        if cb.call_pos or cb.maq_gt0:
+            self.calls = dict(col=g(_np(cb.call_col, ncall, np.uint32)), pos=g(_np(cb.call_pos, ncall, np.uint64)),
+                              gt=g(_np(cb.call_gt, ncall, np.uint8)), ref=g(_np(cb.call_ref, ncall, np.uint8)),
+                              qual=g(_np(cb.call_qual, ncall, np.float32)))
+        self.maq = None
+        if cb.maq_gt0:
+            self.maq = dict(gt0=g(_np(cb.maq_gt0, nc, np.uint8)), gt1=g(_np(cb.maq_gt1, nc, np.uint8)),
+                            s0=g(_np(cb.maq_s0, nc, np.float32)), s1=g(_np(cb.maq_s1, nc, np.float32)),
+                            n_valid=g(_np(cb.maq_n_valid, nc, np.uint16)))
+        if self.calls is not None and not cb.position:
+            # maq_mode 1: nothing but the calls leaves the device
+            self.position = self.col_off = self.n_starting_here = self.read_idx = self.base = self.qual = None
+            self.query_offset = self.counts = self.reference_base = None
+            return
+        self.n_starting_here = g(_np(cb.n_starting_here, nc, np.uint32))
         if cb.last_read:
             # compact_reads: sequential encoding -> the same explicit table
             last = _np(cb.last_read, nc, np.uint32).copy()
@@ -626,8 +649,8 @@ class ColumnBatch:
             if nsp:
                 self.base[_np(cb.special_entry, nsp, np.uint32).astype(np.int64)] = _np(cb.special_base, nsp, np.uint8)
         else:
-            self.base = g(_np(cb.base, ne, np.uint8))
-        self.qual = g(_np(cb.qual, ne, np.uint8))
+            self.base = g(_np(cb.base, ne, np.uint8)) if cb.base else None
+        self.qual = g(_np(cb.qual, ne, np.uint8)) if cb.qual else None
         self.query_offset = g(_np(cb.query_offset, ne, np.uint32)) if cb.query_offset else None
         self.counts = g(_np(cb.counts, nc * 6, np.uint32)).reshape(nc, 6) if cb.counts else None
         # use_md_tag: PileupColumn.reference_base per column (pileup.d:252-254)
@@ -698,6 +721,62 @@ def makePileup(reader, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_ze
 def pileupColumns(reader, use_md_tag=False, skip_zero_coverage=True):
     """bam/pileup.d:509-519"""
     return _columns(reader, False, use_md_tag=use_md_tag, skip_zero_coverage=skip_zero_coverage)
+
+
+# ---- MAQ SNP caller (bio/std/hts/snpcallers/maq.d) ---------------------------------------------------------------------
+_BASE5 = "ACGTN"
+
+
+class DiploidCall5:
+    """bio/core/call.d:29-92 (Call!(DiploidGenotype, Base5)): what MaqSnpCaller.makeCall / findSNPs hand out."""
+
+    __slots__ = ("sample", "chromosome", "position", "reference_base", "genotype_code", "quality")
+
+    def __init__(self, sample, chromosome, position, reference_base, genotype_code, quality):
+        self.sample, self.chromosome, self.position = sample, chromosome, int(position)
+        self.reference_base, self.genotype_code, self.quality = reference_base, int(genotype_code), float(quality)
+
+    base1 = property(lambda s: _BASE5[s.genotype_code // 5])             # genotype.d:53-60
+    base2 = property(lambda s: _BASE5[s.genotype_code % 5])
+    is_heterozygous = property(lambda s: s.base1 != s.base2)
+    is_homozygous = property(lambda s: s.base1 == s.base2)
+    genotype = property(lambda s: s.base1 + "|" + s.base2)              # genotype.d:73-75
+
+    @property
+    def is_variant(self):                                                # call.d:88-90
+        r = self.reference_base.upper()
+        r = r if r in "ACGT" else "N"
+        return (self.base1, self.base2) != (r, r)
+
+
+class MaqSnpCaller:
+    """bio/std/hts/snpcallers/maq.d:319-540.  The likelihoods are computed on the GPU over the columns of the pileup it
+    builds (maq_mode of biodb_pileup_params): only calls — or, for genotypeLikelihoods, 12 bytes per column — come back."""
+
+    def __init__(self, depcorr=0.17, eta=0.03, minimum_call_quality=6.0, minimum_base_quality=13):
+        self.depcorr, self.eta = depcorr, eta
+        self.minimum_call_quality, self.minimum_base_quality = minimum_call_quality, minimum_base_quality
+
+    def findSNPs(self, reads, reference="", sample="", single_ref=True, **kw):
+        """maq.d:489-540: the calls that differ from the reference base (from the reads' MD tags) and whose quality exceeds
+        minimum_call_quality.  `reads`: a BamReader or bam["chr"][a:b]; single_ref=True is makePileup(reads, true)."""
+        region = None
+        if isinstance(reads, RegionReads):
+            region, reads = (reads.ref_id, reads.start, reads.end), reads.reader
+        for b in reads.column_batches(single_ref, use_md_tag=True, region=region, maq=self, maq_mode=1, copy=True, **kw):
+            chrom = reference or (reads.reference_sequences[b.ref_id].name if 0 <= b.ref_id < len(reads.reference_sequences) else "")
+            c = b.calls
+            for k in range(len(c["pos"])):
+                yield DiploidCall5(sample, chrom, c["pos"][k], chr(int(c["ref"][k])), c["gt"][k], c["qual"][k])
+
+    def genotypeLikelihoods(self, reads, single_ref=True, use_md_tag=True, **kw):
+        """genotypeLikelihoodInfo / makeCall of every column (maq.d:388-486), batch by batch: yields ColumnBatch objects
+        whose .maq holds gt0 / gt1 / s0 / s1 / n_valid per column (the call's quality is s1 - s0) next to position,
+        col_off, n_starting_here and reference_base."""
+        region = None
+        if isinstance(reads, RegionReads):
+            region, reads = (reads.ref_id, reads.start, reads.end), reads.reader
+        yield from reads.column_batches(single_ref, use_md_tag=use_md_tag, region=region, maq=self, maq_mode=2, copy=True, **kw)
 
 
 # ---- pileupChunks (bam/pileup.d:859-1015, bam/splitter.d:66-101) ---------------------------------------------------

@@ -222,11 +222,15 @@ __device__ __noinline__ int build_table_par(const uint8_t* lens, int n, uint16_t
     code->index[lane] = (uint16_t)myindex;
     scratch[lane] = 0;                                     // symbols of this length placed so far
   }
-  if (v != (1 << 15))                                      // incomplete code: some slots stay unused
-    for (int i = lane; i < (1 << PB); i += 32) lut[i] = (uint16_t)ENT_INVALID;
+  if (lane < 2) lut[lane] = (uint16_t)ENT_INVALID;        // (an incomplete code leaves slots unused: they inherit this)
   __syncwarp();
-  if (maxlen == 0) return 1;
+  if (maxlen == 0) {
+    for (int i = lane; i < (1 << PB); i += 32) lut[i] = (uint16_t)ENT_INVALID;
+    __syncwarp();
+    return 1;
+  }
   if (v < (1 << 15) && (kind == KIND_CODELEN || maxlen != 1)) return -1;
+  // canonical order: sorted[index[l] + k] = k-th symbol of code length l
   for (int g = 0; g < n; g += 32) {
     const int sym = g + lane;
     const int l = sym < n ? (int)lens[sym] : 0;
@@ -236,19 +240,31 @@ __device__ __noinline__ int build_table_par(const uint8_t* lens, int n, uint16_t
     __syncwarp();
     if (l) {
       if (rank == 0) scratch[l] = placed + (uint32_t)__popc(same);
-      const uint32_t k = placed + rank;
-      sorted[code->index[l] + k] = (uint16_t)sym;
-      const uint32_t c = code->first[l] + k;
-      const uint32_t rev = __brev(c) >> (32 - l);
-      if (l <= PB) {
-        const uint16_t e = (uint16_t)make_entry(kind, sym, l);
-        for (uint32_t i = rev; i < (1u << PB); i += (1u << l)) lut[i] = e;
-      } else {
-        lut[rev & ((1u << PB) - 1)] = (uint16_t)ENT_SLOW;
-      }
+      sorted[code->index[l] + placed + rank] = (uint16_t)sym;
     }
     __syncwarp();
   }
+  // The LUT, level by level: a code of length k sits at its bit-reversed value (< 2^k); copying [0, 2^k) onto
+  // [2^k, 2^(k+1)) then repeats every code of length <= k with its period.  One store per symbol and one pass of
+  // doublings (2^PB / 32 warp stores) instead of 2^(PB - k) stores per symbol.
+#pragma unroll 1
+  for (int k = 1; k <= PB; ++k) {
+    const int c0 = code->index[k], cn = code->cnt[k];
+    const uint32_t f = code->first[k];
+    for (int i = lane; i < cn; i += 32)
+      lut[__brev(f + (uint32_t)i) >> (32 - k)] = (uint16_t)make_entry(kind, sorted[c0 + i], k);
+    __syncwarp();
+    if (k < PB) {
+      for (int i = lane; i < (1 << k); i += 32) lut[(1 << k) + i] = lut[i];
+      __syncwarp();
+    }
+  }
+  for (int l = PB + 1; l <= maxlen; ++l) {                 // codes longer than the index: marked, resolved elsewhere
+    const int cn = code->cnt[l];
+    const uint32_t f = code->first[l];
+    for (int i = lane; i < cn; i += 32) lut[(__brev(f + (uint32_t)i) >> (32 - l)) & ((1u << PB) - 1)] = (uint16_t)ENT_SLOW;
+  }
+  __syncwarp();
   if (sub != nullptr && maxlen > PB) {
     const int k_begin = code->index[PB + 1], k_end = code->index[maxlen] + code->cnt[maxlen];
     // first PB bits (most significant first) of the k-th code in sorted order

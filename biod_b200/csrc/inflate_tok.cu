@@ -75,20 +75,22 @@ static_assert(TOK_TRIPS >= 64 && TOK_TRIPS <= 255, "token count of a lane travel
 static_assert((NCH - 1) * CH >= HDR_BYTES + 16 && (NCH - 1) * CH >= SUPER_BYTES + 32 && CH % 16 == 0, "staging ring too small");
 static_assert(STORE_PIECE <= OUT_BUDGET, "");
 
-// tokens (16 bits, one per decode trip of a lane); a literal is the byte itself
-constexpr uint32_t TOK_LEN = K_LEN << 13, TOK_EOB = K_EOB << 13, TOK_DIST = 0x8000;
+// tokens (16 bits): bit 15 = a distance (15 bits of distance - 1); else bits 13-14 = literal (the byte itself) / length
+// (8 bits of length - 3) / end of block / none.  A decode trip of a lane yields two: its code, and the literal/length
+// code behind it if the first was a literal (else TOK_NONE).
+constexpr uint32_t TOK_LEN = K_LEN << 13, TOK_EOB = K_EOB << 13, TOK_NONE = 3u << 13, TOK_DIST = 0x8000;
 // lane stop reasons
 constexpr uint32_t F_EOB = 1, F_ERR = 2, F_INEND = 3;
 
 // The record stream of a block: 16-bit words in its arena of TOK_ARENA_WORDS, records back to back, each a multiple of 32
 // words (64 bytes).
 //   REC_CHUNK : head[32] = {REC_CHUNK, lanes committed, token rows, ...}; lane[32] x u32 = bytes | matches << 16 |
-//               tokens << 24 of every lane; then `rows` rows of 32 tokens (row t = trip t of lanes 0..31)
+//               rows << 24 of every lane; then `rows` rows of 32 x u32 (row t = the two tokens of trip t of lanes 0..31)
 //   REC_STORED: head[32] = {REC_STORED, -, -, -, offset lo, offset hi, length lo, length hi}: `length` bytes at `offset`
 //               of the block's compressed payload
 //   REC_DONE  : head[32] = {REC_DONE, status != 0}
 enum { REC_CHUNK = 1, REC_STORED = 2, REC_DONE = 3 };
-constexpr uint32_t REC_HEAD = 32, REC_LANES = 64;
+constexpr uint32_t REC_HEAD = 32, REC_LANES = 64, ROW_WORDS = 64;
 constexpr uint32_t ARENA = TOK_ARENA_WORDS;
 static_assert(ARENA % 64 == 0, "");
 
@@ -129,21 +131,24 @@ __device__ __forceinline__ uint32_t fetch32(uint32_t in_ring, uint32_t pos) {
 }
 
 // Every lane with `active` decodes the codes that start in [t, limit) of its own sub-sequence; all 32 lanes of the
-// decoder warp must call this together.  One loop trip decodes ONE Huffman code per lane, whichever kind the lane needs
-// next — a literal/length code or the distance code of the length it met in the previous trip — as straight-line,
-// select-based code, so that the lanes stay converged.
+// decoder warp must call this together.  One loop trip decodes one Huffman code per lane, whichever kind the lane needs
+// next — a literal/length code or the distance code of the length it met in the previous trip — and, when that code
+// was a plain literal (nine codes in ten of BAM data are), the literal/length code behind it as well: both come out of
+// the same 32-bit window (<= 15 + 10 + 5 bits), so the second one costs a table lookup but no second fetch, vote or
+// loop turn.  Everything is straight-line, select-based code, so that the lanes stay converged.
 // RECORD = false: only the bit position moves (round 1: where do the sub-sequences synchronise?).
-// RECORD = true: the lane also counts the bytes and matches it produces and writes one token per trip.
+// RECORD = true: the lane also counts the bytes and matches it produces and writes one row entry (two tokens) per trip.
 template <bool RECORD>
 __device__ __forceinline__ void lane_decode(const DCtx& c, bool active, uint32_t t, uint32_t limit, uint32_t& end,
                                             uint32_t& out, uint32_t& nm, uint32_t& nt, uint32_t& flag) {
   const uint32_t lim = limit < c.total_bits ? limit : c.total_bits;
+  constexpr uint32_t LITMSK = ((1u << LIT_BITS) - 1) << 1;
   uint32_t pos = t, o = 0, m = 0, fl = 0, trips = 0;
   uint32_t st = 0;          // 0: the next code is a literal/length code, 1: a distance code
   uint32_t len = 0;
-  uint32_t lut = c.lutl, msk = ((1u << LIT_BITS) - 1) << 1;
+  uint32_t lut = c.lutl, msk = LITMSK;
   uint32_t run = (active && pos < lim) ? 1u : 0u;
-  uint16_t* tp = c.tok;
+  uint32_t* tp = reinterpret_cast<uint32_t*>(c.tok);
   // The body is written with selects on 0/1 flags, not with if/else: whatever nvcc turns into branches here runs
   // divergently (a lane with a literal, a lane with a length, a lane with a distance) and costs every path's instructions.
   // A stopped lane (run == 0) keeps computing on its last position; nothing it computes is kept.
@@ -163,28 +168,38 @@ __device__ __forceinline__ void lane_decode(const DCtx& c, bool active, uint32_t
     const uint32_t cl = e >> 12;
     const uint32_t kraw = (e >> 8) & 3;                            // kind of a literal/length entry (distance entries: 0)
     const uint32_t is_len = st | (kraw == K_LEN ? 1u : 0u);        // a distance code is handled like a length code
-    const uint32_t eb = is_len ? ENTRY_EXTRA_BITS(e) : 0u;         // cl + eb <= 28 bits of the 32
-    const uint32_t adv = cl + eb;
+    const uint32_t eb = is_len ? ENTRY_EXTRA_BITS(e) : 0u;
+    // the code behind a plain literal: taken if it starts inside the lane's range and the first-level table knows it
+    const uint32_t lit1 = (st | kraw) ? 0u : 1u;
+    const uint32_t bits2 = bits >> cl;
+    const uint32_t e2 = lds16(c.lutl + ((bits2 << 1) & LITMSK));
+    const uint32_t k2 = (e2 >> 8) & 3, cl2 = e2 >> 12;
+    uint32_t ok2 = lit1 & (k2 != K_SPECIAL ? 1u : 0u) & (pos + cl < lim ? 1u : 0u);
+    if (RECORD) ok2 &= (o + 1 < (uint32_t)LANE_CAP ? 1u : 0u);     // (the byte cap is checked between codes)
+    const uint32_t eb2 = k2 == K_LEN ? ENTRY_EXTRA_BITS(e2) : 0u;
+    const uint32_t adv = cl + eb + (ok2 ? cl2 + eb2 : 0u);         // <= 15 + 10 + 5 bits of the 32
     pos += run ? adv : 0u;
     if (RECORD) {
       const uint32_t val = lds32(c.auxtab + (((st << 5) | (e & 31)) << 2)) + ((bits >> cl) & ~(0xffffffffu << eb));
-      const uint32_t tk = (st ? TOK_DIST : (kraw << 13)) | (is_len ? val - (st ? 1u : 3u) : (e & 0xffu));
-      if (run) *tp = (uint16_t)tk;
+      const uint32_t val2 = lds32(c.auxtab + ((e2 & 31) << 2)) + ((bits2 >> cl2) & ~(0xffffffffu << eb2));
+      const uint32_t tk1 = (st ? TOK_DIST : (kraw << 13)) | (is_len ? val - (st ? 1u : 3u) : (e & 0xffu));
+      const uint32_t tk2 = ok2 ? ((k2 << 13) | (k2 == K_LEN ? val2 - 3u : (e2 & 0xffu))) : TOK_NONE;
+      if (run) *tp = tk1 | (tk2 << 16);
       tp += 32;
       trips += run;
-      const uint32_t lit = (is_len | kraw) ? 0u : run;             // a literal: one byte
       const uint32_t mat = st & run;                               // a distance: the match is complete
-      o += lit + (mat ? len : 0u);
+      o += (lit1 & run) + (mat ? len : 0u) + ((ok2 & run & (k2 == K_LIT ? 1u : 0u)));
       m += mat;
-      len = val;
+      len = ok2 ? val2 : val;
     }
-    const uint32_t eob = (st ? 0u : (kraw == K_EOB ? 1u : 0u)) & run;
+    const uint32_t klast = ok2 ? k2 : (st ? 0u : kraw);            // kind of the last literal/length code of the trip
+    const uint32_t eob = (klast == K_EOB ? 1u : 0u) & run;
     fl = eob ? F_EOB : fl;
-    st = (st ^ 1u) & is_len;                         // length -> distance next; anything else -> literal/length next
+    st = ok2 ? (k2 == K_LEN ? 1u : 0u) : ((st ^ 1u) & is_len);     // length -> distance next; anything else -> literal/length
     lut = st ? c.lutd : c.lutl;
-    msk = st ? ((1u << DIST_BITS) - 1) << 1 : ((1u << LIT_BITS) - 1) << 1;
+    msk = st ? ((1u << DIST_BITS) - 1) << 1 : LITMSK;
     // a lane stops only between codes of the literal/length alphabet: at its boundary, or (RECORD) when it has produced
-    // LANE_CAP bytes or TOK_TRIPS - 1 tokens (hence at most LANE_MCAP matches) — the next lane continues from there
+    // LANE_CAP bytes or TOK_TRIPS - 1 rows (hence at most LANE_MCAP matches) — the next lane continues from there
     uint32_t stop = pos >= lim ? 1u : 0u;
     if (RECORD) stop |= (o >= (uint32_t)LANE_CAP ? 1u : 0u) | (trips >= (uint32_t)TOK_TRIPS - 1 ? 1u : 0u);
     run &= ~(eob | (st ? 0u : stop));
@@ -294,8 +309,9 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
   uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0;
   uint32_t produced = 0;    // bytes handed to the resolver so far
   uint32_t cur = 0;         // next free word of the arena
+  uint32_t sub_bits = SUB_BITS;   // bits per lane of the next super-chunk (adapts to the stream, see below)
   // room a record may need, plus the closing REC_DONE
-  constexpr uint32_t CHUNK_MAX = REC_HEAD + REC_LANES + (uint32_t)TOK_TRIPS * 32;
+  constexpr uint32_t CHUNK_MAX = REC_HEAD + REC_LANES + (uint32_t)TOK_TRIPS * ROW_WORDS;
 
   bool last = false;
   while (!last && status == 0) {
@@ -339,6 +355,10 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
       }
       cur += REC_HEAD;
       produced += len;
+      // the decoder only skips the bytes, but the staging ring has to pass them: its chunks are issued and waited for
+      // strictly in order (the mbarrier parities count every chunk), at most NCH in flight
+      for (uint32_t b = pos >> 3, e = (pos >> 3) + len; b < e; b += (NCH - 2) * CH)
+        ensure_input(b, (b + (NCH - 2) * CH < e ? b + (NCH - 2) * CH : e));
       pos += len * 8;
       continue;
     }
@@ -436,14 +456,14 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
       if (cur + CHUNK_MAX + REC_HEAD > ARENA) { status = STATUS_RETRY; break; }   // the record stream outgrew its arena
       const uint32_t base = pos;
       ensure_input(base >> 3, (base >> 3) + SUPER_BYTES + 24);
-      const uint32_t lim = base + (uint32_t)(lane + 1) * SUB_BITS;
-      uint32_t t = base + (uint32_t)lane * SUB_BITS;
+      const uint32_t lim = base + (uint32_t)(lane + 1) * sub_bits;
+      uint32_t t = base + (uint32_t)lane * sub_bits;
       uint32_t e_, out_, nm_, nt_, fl_;
       // round 1: where does the chain cross into each sub-sequence?  (bit positions only)
       lane_decode<false>(ctx, true, t, lim, e_, out_, nm_, nt_, fl_);
       ++n_super;
       // round 2: every lane from where its predecessor ended, recording tokens into the rows of this record
-      ctx.tok = arena + cur + REC_HEAD + REC_LANES + lane;
+      ctx.tok = arena + cur + REC_HEAD + REC_LANES + 2 * lane;
       {
         uint32_t tn = __shfl_up_sync(0xffffffffu, e_, 1);
         if (lane == 0) tn = base;
@@ -491,7 +511,12 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
         uint16_t* h = arena + cur;
         h[0] = REC_CHUNK; h[1] = (uint16_t)k; h[2] = (uint16_t)rows;
       }
-      cur += REC_HEAD + REC_LANES + rows * 32;
+      cur += REC_HEAD + REC_LANES + rows * ROW_WORDS;
+      // Streams that expand a lot (long matches, one-bit codes) fill the resolver's ring with fewer than 32 lanes: the
+      // other lanes' decoding — and their rows of the record stream — would be thrown away super-chunk after super-chunk.
+      // Shorter sub-sequences make 32 lanes fit again; they grow back when the output gets small.
+      if (k < ncand) sub_bits = max(64u, (sub_bits * k / 32u) & ~7u);
+      else if (k == 32 && 2 * chunk_out < (uint32_t)OUT_BUDGET && sub_bits < (uint32_t)SUB_BITS) sub_bits = min((uint32_t)SUB_BITS, 2 * sub_bits);
       produced += chunk_out;
       pos = newpos;
       eob = stop_flag == F_EOB;
@@ -590,8 +615,8 @@ __global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) 
     // ---- a super-chunk: k lanes of the decoder are committed -----------------------------------------------
     const uint32_t k = __ldcg(arena + cur + 1), rows = __ldcg(arena + cur + 2);
     const uint32_t mine = (uint32_t)lane < k ? __ldcg(reinterpret_cast<const uint32_t*>(arena + cur + REC_HEAD) + lane) : 0u;
-    const uint16_t* tok = arena + cur + REC_HEAD + REC_LANES + lane;
-    cur += REC_HEAD + REC_LANES + rows * 32;
+    const uint32_t* tok = reinterpret_cast<const uint32_t*>(arena + cur + REC_HEAD + REC_LANES) + lane;
+    cur += REC_HEAD + REC_LANES + rows * ROW_WORDS;
     const uint32_t out_ = mine & 0xffff, nm_ = (mine >> 16) & 0xff, nt_ = mine >> 24;
     const uint32_t inc_out = warp_incl_scan(out_, lane);
     const uint32_t inc_nm = warp_incl_scan(nm_, lane);
@@ -607,20 +632,24 @@ __global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) 
       for (uint32_t t0 = 0; t0 < rows; t0 += 8) {
         uint32_t tk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tk[j] = (t0 + j < nt_) ? (uint32_t)__ldcs(tok + (size_t)(t0 + j) * 32) : TOK_EOB;
+        for (int j = 0; j < 8; ++j) tk[j] = (t0 + j < nt_) ? __ldcs(tok + (size_t)(t0 + j) * 32) : (TOK_NONE | (TOK_NONE << 16));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t v = tk[j];
-          if (v & TOK_DIST) {
-            sts32(mld + (slot << 2), (len - 3) | ((v & 0x7fffu) << 8));
-            sts16(mpos + (slot << 1), oo - oa);
-            ++slot;
-            oo += len;
-          } else if (v & TOK_LEN) {
-            len = (v & 0xff) + 3;
-          } else if (!(v & TOK_EOB)) {
-            sts8(ring + (oo & POM), v);
-            ++oo;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t v = h ? tk[j] >> 16 : tk[j] & 0xffffu;
+            const uint32_t kind = (v >> 13) & 3;
+            if (v & TOK_DIST) {
+              sts32(mld + (slot << 2), (len - 3) | ((v & 0x7fffu) << 8));
+              sts16(mpos + (slot << 1), oo - oa);
+              ++slot;
+              oo += len;
+            } else if (kind == K_LEN) {
+              len = (v & 0xff) + 3;
+            } else if (kind == K_LIT) {
+              sts8(ring + (oo & POM), v);
+              ++oo;
+            }
           }
         }
       }

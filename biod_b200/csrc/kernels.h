@@ -49,9 +49,10 @@ struct InflateArgs {
 };
 // inflate_duo.cu / inflate_tok.cu: tokens (decode trips) one lane of the decoder warp may record per super-chunk
 constexpr int DUO_TOK_TRIPS = 128;
-// inflate_tok.cu: 16-bit words of one block's record stream (tokens + super-chunk headers): a block of 64 KiB has at
-// most 65536 tokens; rows padded to the longest lane and the headers come to ~1.3 x that in practice
-constexpr uint32_t TOK_ARENA_WORDS = 96 * 1024;
+// inflate_tok.cu: 16-bit words of one block's record stream (token rows + super-chunk headers).  A block of 64 KiB has
+// at most 65536 tokens; rows hold two tokens per lane and are padded to the longest lane: BAM data needs ~57 K words,
+// an all-literal block ~85 K.  A stream that outgrows the arena goes to the warp-serial kernel.
+constexpr uint32_t TOK_ARENA_WORDS = 144 * 1024;
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st);
 // bytes of InflateArgs::tok for n_blocks blocks (0 when the selected kernel needs none)
 size_t inflate_token_bytes(uint32_t n_blocks);

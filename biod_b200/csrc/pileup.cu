@@ -264,15 +264,20 @@ __device__ __forceinline__ Entry cursor_eval(Cursor& c, const uint8_t* cg, uint3
 // taken 32 at a time, one per lane, their cursor data loaded ONCE; then for every column of the chunk the lanes
 // whose read is live there are balloted, ranked (popc of lower lanes = file order, pileup.d:351-359,381-383)
 // and write read_idx / base / qual at consecutive slots.
-template <bool COUNTS, bool WANT_Q>
+// MAQ: the entries feed maq_kernel (maq.cu) instead of leaving the device: per entry base | strand << 7 — or 0xFF for a
+// base MaqSnpCaller drops, quality below minimum_base_quality or '-' (maq.d:401-404) — and min(base quality, mapping
+// quality) (:407-409); no read_idx.
+template <bool COUNTS, bool WANT_Q, bool MAQ>
 __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, const int32_t* __restrict__ eend,
                                                                  const uint4* __restrict__ rinfo, ColumnScratch c,
-                                                                 ColumnOutput o, uint32_t n_col, int32_t* info) {
+                                                                 ColumnOutput o, uint32_t n_col, const uint32_t* __restrict__ redo,
+                                                                 int32_t* info) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = blockIdx.x * ENT_WARPS + (threadIdx.x >> 5);
   const uint32_t lt = (1u << lane) - 1;
   const uint32_t c0 = warp * CHUNK;
   if (c0 >= n_col) return;
+  if (redo && !redo[warp]) return;          // this chunk was done by entries_tile_kernel
   const uint32_t ncols = min((uint32_t)CHUNK, n_col - c0);
   const uint64_t chunk_off = o.col_off[c0];
   int32_t my_p = 0;               // BAM positions are int32 (read.d:93)
@@ -319,11 +324,16 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
     const uint32_t j = cand ? list[w0 + lane] : 0;
     int32_t e = DEAD, pos = 0, lseq = 0;
     uint4 ri = make_uint4(0, 0, 0, 0);
+    uint32_t mapq = 0, rev = 0;
     if (cand) {
       e = eend[j];
       pos = v.pos[j];
       ri = rinfo[j];
       lseq = v.l_seq[j];
+      if (MAQ) {
+        mapq = (v.bin_mq_nl[j] >> 8) & 0xff;        // read.d:958-962
+        rev = (v.flag_nc[j] >> 20) & 1;             // flag 0x10: is_reverse_strand
+      }
     }
     const uint8_t* seq = (const uint8_t*)(uintptr_t)(((uint64_t)ri.y << 32) | ri.x);
     const uint8_t* ql = seq + (((uint32_t)lseq + 1) >> 1);
@@ -363,7 +373,11 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
           qual = en.qual;
           qoff = en.qoff;
         }
-        if (!COUNTS) {
+        if (MAQ) {
+          const bool ok = qual >= (uint32_t)o.maq_min_base_quality && base != '-';
+          o.base[slot] = ok ? (uint8_t)(base | (rev << 7)) : (uint8_t)0xFF;
+          o.qual[slot] = (uint8_t)(qual < mapq ? qual : mapq);
+        } else if (!COUNTS) {
           o.read_idx[slot] = ri.w;
           o.base[slot] = (uint8_t)base;
           o.qual[slot] = (uint8_t)qual;
@@ -389,16 +403,202 @@ __global__ void __launch_bounds__(ENT_WARPS * 32) entries_kernel(ReadsView v, co
     for (int q = 0; q < 6; ++q) o.counts[(size_t)(c0 + lane) * 6 + q] = cnt[q];
 }
 
+// ---- column entries, column-stationary ---------------------------------------------------------------------------
+// The same entries, built the other way round: a warp owns TCHUNK consecutive columns, LANE = COLUMN, and the chunk's
+// candidate reads are taken one after the other (file order) with their cursor data broadcast to the warp.  A lane whose
+// position the read covers appends one entry to its own column — its running count IS the entry's rank, so the ballot,
+// the rank popcount and the per-column shuffles of entries_kernel disappear (3x fewer instructions per entry) — and
+// neighbouring lanes read neighbouring bases / qualities of the read (coalesced).  The chunk's entries are contiguous in
+// the output ([col_off[c0], col_off[c0 + TCHUNK))), so they are staged in shared memory and written out in one coalesced
+// sweep.  A chunk with more entries than the tile holds is left to entries_kernel (flagged in `redo`).
+// MODE 0: read_idx + base + qual.  MODE 1 (compact_reads): base + qual, and per column the sequential encoding of its
+// read list — last read, 64-bit window mask, number of stragglers (reads more than 63 records older than the last) —
+// without ever writing read_idx.  MODE 2 (MAQ): base | strand << 7 (0xFF = dropped) + min(quality, mapq).
+constexpr int TCHUNK = 32;
+constexpr int TILE_WARPS = 4;
+constexpr int TILE_CAP = 1280;          // entries staged per warp: 32 columns x coverage 40
+
+template <int MODE>
+__global__ void __launch_bounds__(TILE_WARPS * 32) entries_tile_kernel(ReadsView v, const int32_t* __restrict__ eend,
+                                                                       const uint4* __restrict__ rinfo, ColumnScratch c,
+                                                                       ColumnOutput o, uint32_t n_col, uint32_t* last_read,
+                                                                       uint64_t* live_mask, uint32_t* nstrag, uint32_t* redo,
+                                                                       int32_t* info) {
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * TILE_WARPS + wib;
+  const uint32_t c0 = warp * TCHUNK;
+  if (c0 >= n_col) return;
+  const uint32_t ncols = min((uint32_t)TCHUNK, n_col - c0);
+  const uint64_t chunk_off = o.col_off[c0];
+  const uint32_t n_chunk = (uint32_t)(o.col_off[c0 + ncols] - chunk_off);
+  const bool mine = lane < ncols;
+  int32_t p = 0;
+  uint32_t cnt = 0;                       // next entry of column `lane`, relative to chunk_off
+  if (mine) {
+    p = (int32_t)o.col_pos[c0 + lane];
+    cnt = (uint32_t)(o.col_off[c0 + lane] - chunk_off);
+  }
+  if (n_chunk > (uint32_t)TILE_CAP) {     // (warp-uniform) too deep for the tile: entries_kernel redoes this chunk
+    if (lane == 0) redo[warp] = 1;
+    if (MODE == 1 && mine) { last_read[c0 + lane] = 0; live_mask[c0 + lane] = 0; nstrag[c0 + lane] = 0; }
+    return;
+  }
+  if (lane == 0) redo[warp] = 0;
+  const int32_t p_first = __shfl_sync(0xffffffffu, p, 0), p_last = __shfl_sync(0xffffffffu, p, ncols - 1);
+  uint32_t lo = c.lo[c0];
+  const uint32_t hi = c.hi[c0 + ncols - 1];
+  __shared__ uint32_t s_ridx[MODE == 0 ? TILE_WARPS * TILE_CAP : 1];
+  __shared__ __align__(16) uint8_t s_base[TILE_WARPS][TILE_CAP];
+  __shared__ __align__(16) uint8_t s_qual[TILE_WARPS][TILE_CAP];
+  uint32_t* t_ridx = s_ridx + (MODE == 0 ? wib * TILE_CAP : 0);
+  uint8_t* t_base = s_base[wib];
+  uint8_t* t_qual = s_qual[wib];
+  // MODE 1: the read list of column `lane` as (last read, mask of the 64 records up to it, count of older ones)
+  uint32_t m_last = 0, m_ns = 0, m_any = 0;
+  uint64_t m_mask = 0;
+  lo = lo ? lo - 1 : 0;
+  for (uint32_t j0 = lo; j0 < hi; j0 += 32) {
+    // 32 reads of the range at a time: their cursor data into the lanes' registers, handed round by shuffles
+    const uint32_t jl = j0 + lane;
+    int32_t re = DEAD, rpos = 0, rlseq = 0;
+    uint4 ri = make_uint4(0, 0, 0, 0);
+    uint32_t rmq = 0;
+    bool cand = false;
+    if (jl < hi) {
+      re = eend[jl];
+      rpos = v.pos[jl];
+      cand = re != DEAD && re > p_first && rpos <= p_last;
+      if (cand) {
+        ri = rinfo[jl];
+        rlseq = v.l_seq[jl];
+        if (MODE == 2) rmq = ((v.bin_mq_nl[jl] >> 8) & 0xff) | (((v.flag_nc[jl] >> 20) & 1) << 8);
+      }
+    }
+    uint32_t cm = __ballot_sync(0xffffffffu, cand);
+    while (cm) {
+      const uint32_t k = (uint32_t)__ffs(cm) - 1;
+      cm &= cm - 1;
+      const int32_t e = __shfl_sync(0xffffffffu, re, k), pos = __shfl_sync(0xffffffffu, rpos, k);
+      const int32_t lseq = __shfl_sync(0xffffffffu, rlseq, k);
+      const uint32_t sx = __shfl_sync(0xffffffffu, ri.x, k), sy = __shfl_sync(0xffffffffu, ri.y, k);
+      const uint32_t sz = __shfl_sync(0xffffffffu, ri.z, k), gidx = __shfl_sync(0xffffffffu, ri.w, k);
+      const uint32_t mq = MODE == 2 ? __shfl_sync(0xffffffffu, rmq, k) : 0;
+      const bool live = mine && pos <= p && e > p;
+      if (!live) continue;
+      const uint8_t* seq = (const uint8_t*)(uintptr_t)(((uint64_t)sy << 32) | sx);
+      const uint8_t* ql = seq + (((uint32_t)lseq + 1) >> 1);
+      const uint32_t kk = (uint32_t)(p - pos);
+      uint32_t base = '-', qual = 255;
+      if (sz & 0x80000000u) {
+        // single M/=/X run: the query offset is linear in the column (pileup.d:195-203)
+        const uint32_t qoff = (sz & 0x7fffffffu) + kk;
+        if (qoff < (uint32_t)lseq) {
+          const uint32_t byte = __ldg(seq + (qoff >> 1));
+          base = base_char((qoff & 1) ? (byte & 0xF) : (byte >> 4));
+          qual = __ldg(ql + qoff);
+        } else {
+          base = 0;        // SEQ shorter than the CIGAR says: see cursor_eval
+        }
+      } else {
+        // any other CIGAR: every lane walks it from the start to its own offset (5 % of the reads, a few operations)
+        const uint32_t nc = v.flag_nc[j0 + k] & 0xFFFF;
+        Cursor cur;
+        cursor_init(cur, seq - 4 * nc, nc);
+        const Entry en = cursor_eval(cur, seq - 4 * nc, nc, seq, ql, lseq, kk);
+        base = en.base;
+        qual = en.qual;
+      }
+      const uint32_t slot = cnt++;
+      if (MODE == 2) {
+        const bool ok = qual >= (uint32_t)o.maq_min_base_quality && base != '-';
+        t_base[slot] = ok ? (uint8_t)(base | ((mq >> 8) << 7)) : (uint8_t)0xFF;
+        t_qual[slot] = (uint8_t)(qual < (mq & 0xff) ? qual : (mq & 0xff));
+      } else {
+        t_base[slot] = (uint8_t)base;
+        t_qual[slot] = (uint8_t)qual;
+        if (MODE == 0) t_ridx[slot] = gidx;
+      }
+      if (MODE == 1) {
+        // reads come in file order: the new one becomes the last, the window moves up by the index gap
+        const uint32_t sh = m_any ? gidx - m_last : 0;
+        m_ns += sh >= 64 ? (uint32_t)__popcll(m_mask) : (sh ? (uint32_t)__popcll(m_mask >> (64 - sh)) : 0u);
+        m_mask = (sh >= 64 ? 0ull : m_mask << sh) | 1ull;
+        m_last = gidx;
+        m_any = 1;
+      }
+    }
+  }
+  __syncwarp();
+  if (MODE == 1 && mine) { last_read[c0 + lane] = m_last; live_mask[c0 + lane] = m_mask; nstrag[c0 + lane] = m_ns; }
+  // write-out: the tile is one contiguous stretch of the entry arrays
+  if (MODE == 0)
+    for (uint32_t i = lane; i < n_chunk; i += 32) o.read_idx[chunk_off + i] = t_ridx[i];
+  {
+    uint8_t* gb = o.base + chunk_off;
+    uint8_t* gq = o.qual + chunk_off;
+    // bytes up to the first 16-byte boundary of the global arrays, then 16 bytes per lane, then the tail
+    const uint32_t head = min(n_chunk, (uint32_t)((16 - (chunk_off & 15)) & 15));
+    if (lane < head) { gb[lane] = t_base[lane]; gq[lane] = t_qual[lane]; }
+    const uint32_t n16 = (n_chunk - head) >> 4;
+    for (uint32_t i = lane; i < n16; i += 32) {
+      uint4 vb, vq;
+      const uint8_t* sb = t_base + head + 16 * i;
+      const uint8_t* sq = t_qual + head + 16 * i;
+      if ((head & 3) == 0) {
+        vb = make_uint4(((const uint32_t*)sb)[0], ((const uint32_t*)sb)[1], ((const uint32_t*)sb)[2], ((const uint32_t*)sb)[3]);
+        vq = make_uint4(((const uint32_t*)sq)[0], ((const uint32_t*)sq)[1], ((const uint32_t*)sq)[2], ((const uint32_t*)sq)[3]);
+      } else {
+        uint32_t wb[4], wq[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          wb[w] = sb[4 * w] | (sb[4 * w + 1] << 8) | (sb[4 * w + 2] << 16) | ((uint32_t)sb[4 * w + 3] << 24);
+          wq[w] = sq[4 * w] | (sq[4 * w + 1] << 8) | (sq[4 * w + 2] << 16) | ((uint32_t)sq[4 * w + 3] << 24);
+        }
+        vb = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+        vq = make_uint4(wq[0], wq[1], wq[2], wq[3]);
+      }
+      *reinterpret_cast<uint4*>(gb + head + 16 * i) = vb;
+      *reinterpret_cast<uint4*>(gq + head + 16 * i) = vq;
+    }
+    const uint32_t done = head + (n16 << 4);
+    if (done + lane < n_chunk) { gb[done + lane] = t_base[done + lane]; gq[done + lane] = t_qual[done + lane]; }
+  }
+}
+
+// compact_reads without read_idx: the stragglers of the (few) columns that have any, by walking the column's candidate
+// reads once more.  One thread per column; strag_off = exclusive scan of nstrag.
+__global__ void strag_walk_kernel(ReadsView v, const int32_t* __restrict__ eend, const uint4* __restrict__ rinfo,
+                                  const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi,
+                                  const uint64_t* __restrict__ col_pos, uint32_t n_col, const uint32_t* __restrict__ strag_off,
+                                  uint32_t* strag_col, uint32_t* strag_idx) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_col) return;
+  const uint32_t s0 = strag_off[c], ns = strag_off[c + 1] - s0;
+  if (ns == 0) return;
+  const int32_t p = (int32_t)col_pos[c];
+  uint32_t j = lo[c] ? lo[c] - 1 : 0, k = 0;
+  for (; j < hi[c] && k < ns; ++j) {
+    const int32_t e = eend[j];
+    if (e != DEAD && v.pos[j] <= p && e > p) {       // live at the column: the first ns of them are the stragglers
+      strag_col[s0 + k] = c;
+      strag_idx[s0 + k] = rinfo[j].w;
+      ++k;
+    }
+  }
+}
+
 // ---- compact read lists (biodb_pileup_params.compact_reads) -----------------------------------------------
 // The reads of a column are file-ordered, and all but a few long-spanning ones lie within a short window of record
 // indices.  One thread per column turns the column's read_idx list into: the index of its last read, a 64-bit mask
 // (bit d = read `last - d` is in the column) and the number of leading reads older than that window ("stragglers",
 // copied out verbatim by compact_strag_kernel).  12 bytes per column instead of 4 bytes per entry cross PCIe.
 __global__ void compact_mask_kernel(const uint64_t* __restrict__ col_off, const uint32_t* __restrict__ read_idx,
-                                    uint32_t n_col, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag) {
+                                    uint32_t n_col, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag,
+                                    const uint32_t* __restrict__ redo) {
   const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > n_col) return;
   if (c == n_col) { nstrag[c] = 0; return; }
+  if (redo && !redo[c / CHUNK]) return;       // entries_tile_kernel wrote this column's list itself
   const uint64_t b = col_off[c], e = col_off[c + 1];
   uint32_t last = 0, ns = 0;
   uint64_t m = 0;
@@ -639,21 +839,44 @@ void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_isla
   launch1d(colpos_kernel, n_col, st, s.islands, s.colbase, n_islands, n_col, o.col_pos);
 }
 
-void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st) {
+void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st,
+                    const uint32_t* redo) {
   if (n_col == 0) return;
+  static_assert(CHUNK == TCHUNK, "redo[] is indexed by the chunks of both kernels");
   uint32_t warps = (n_col + CHUNK - 1) / CHUNK;
   uint32_t grid = (warps + ENT_WARPS - 1) / ENT_WARPS;
-  if (o.counts) entries_kernel<true, false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
-  else if (o.qoff) entries_kernel<false, true><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
-  else entries_kernel<false, false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, s.info);
+  if (o.maq_min_base_quality >= 0) entries_kernel<false, false, true><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, redo, s.info);
+  else if (o.counts) entries_kernel<true, false, false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, redo, s.info);
+  else if (o.qoff) entries_kernel<false, true, false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, redo, s.info);
+  else entries_kernel<false, false, false><<<grid, ENT_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, redo, s.info);
   ++g_kernel_launches;
+}
+
+// Column-stationary entries (entries_tile_kernel) for the plain, compact and MAQ forms; chunks too deep for the tile are
+// flagged in redo[] and done by entries_kernel (pileup_entries with the same arguments and redo).  mode: 0 / 1 / 2.
+uint32_t pileup_tile_chunks(uint32_t n_col) { return (n_col + TCHUNK - 1) / TCHUNK; }
+void pileup_entries_tile(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, int mode,
+                         uint32_t* last_read, uint64_t* live_mask, uint32_t* nstrag, uint32_t* redo, cudaStream_t st) {
+  if (n_col == 0) return;
+  const uint32_t warps = pileup_tile_chunks(n_col);
+  const uint32_t grid = (warps + TILE_WARPS - 1) / TILE_WARPS;
+  if (mode == 0) entries_tile_kernel<0><<<grid, TILE_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, last_read, live_mask, nstrag, redo, s.info);
+  else if (mode == 1) entries_tile_kernel<1><<<grid, TILE_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, last_read, live_mask, nstrag, redo, s.info);
+  else entries_tile_kernel<2><<<grid, TILE_WARPS * 32, 0, st>>>(v, s.eend, s.rinfo, c, o, n_col, last_read, live_mask, nstrag, redo, s.info);
+  ++g_kernel_launches;
+}
+
+void pileup_strag_walk(const ReadsView& v, uint32_t n_col, GroupScratch& s, const uint32_t* lo, const uint32_t* hi,
+                       const uint64_t* col_pos, const uint32_t* strag_off, uint32_t* strag_col, uint32_t* strag_idx,
+                       cudaStream_t st) {
+  launch1d(strag_walk_kernel, n_col, st, v, s.eend, s.rinfo, lo, hi, col_pos, n_col, strag_off, strag_col, strag_idx);
 }
 
 // Compact read lists, step 1: per-column last read, window mask and straggler offsets (exclusive scan; the total is
 // strag_off[n_col], read by the host after a sync).  Step 2 copies the stragglers.
 void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag,
-                          uint32_t* strag_off, GroupScratch& s, cudaStream_t st) {
-  launch1d(compact_mask_kernel, n_col + 1, st, o.col_off, o.read_idx, n_col, last_read, mask, nstrag);
+                          uint32_t* strag_off, GroupScratch& s, cudaStream_t st, const uint32_t* redo) {
+  launch1d(compact_mask_kernel, n_col + 1, st, o.col_off, o.read_idx, n_col, last_read, mask, nstrag, redo);
   device_scan<false>(nstrag, strag_off, (uint64_t)n_col + 1, s.tmp_u32, OpAdd(), 0u, st);
 }
 

@@ -66,6 +66,7 @@ struct ColumnOutput {
   uint8_t* qual;
   uint32_t* qoff;                // or nullptr
   uint32_t* counts;              // counts_only: [n_col*6] A,C,G,T,other,deletion; entries are then not written
+  int32_t maq_min_base_quality;  // >= 0: MAQ mode — base / qual hold the caller's view of the entries (see entries_kernel)
 };
 
 struct CarryOut {
@@ -111,9 +112,19 @@ void pileup_phase1(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t drop_b
 void pileup_island_cols(uint32_t n_islands, GroupScratch& s, cudaStream_t st);
 void pileup_phase2(const ReadsView& v, uint32_t g0, uint32_t g1, uint32_t n_islands, uint32_t n_col, GroupScratch& s,
                    ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
-void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st);
+// redo (may be null): only the chunks of 32 columns flagged there are done (the others were done by the tile kernel)
+void pileup_entries(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, cudaStream_t st,
+                    const uint32_t* redo = nullptr);
+// column-stationary form (pileup.cu: entries_tile_kernel); mode 0 explicit, 1 compact (last_read / live_mask / nstrag
+// written directly, no read_idx), 2 MAQ.  redo[pileup_tile_chunks(n_col)]: chunks left to pileup_entries.
+uint32_t pileup_tile_chunks(uint32_t n_col);
+void pileup_entries_tile(const ReadsView& v, uint32_t n_col, GroupScratch& s, ColumnScratch& c, ColumnOutput& o, int mode,
+                         uint32_t* last_read, uint64_t* live_mask, uint32_t* nstrag, uint32_t* redo, cudaStream_t st);
+void pileup_strag_walk(const ReadsView& v, uint32_t n_col, GroupScratch& s, const uint32_t* lo, const uint32_t* hi,
+                       const uint64_t* col_pos, const uint32_t* strag_off, uint32_t* strag_col, uint32_t* strag_idx,
+                       cudaStream_t st);
 void pileup_compact_masks(uint32_t n_col, const ColumnOutput& o, uint32_t* last_read, uint64_t* mask, uint32_t* nstrag,
-                          uint32_t* strag_off, GroupScratch& s, cudaStream_t st);
+                          uint32_t* strag_off, GroupScratch& s, cudaStream_t st, const uint32_t* redo = nullptr);
 void pileup_compact_stragglers(uint32_t n_col, const ColumnOutput& o, const uint32_t* strag_off, uint32_t* strag_col,
                                uint32_t* strag_idx, cudaStream_t st);
 uint32_t pileup_pack_blocks(uint64_t n_entries);

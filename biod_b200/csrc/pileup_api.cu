@@ -4,6 +4,7 @@
 // (not including) the position of its last read, later columns wait for the next batch.
 #include <algorithm>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -14,6 +15,7 @@
 #include <memory>
 
 #include "bai.h"
+#include "maq.h"
 #include "md_chain.h"
 #include "runtime.h"
 #include "scan.cuh"
@@ -45,6 +47,10 @@ struct OutSet {
                     // reference_base
   PinBuf h[17];     // col_pos, col_off, nstart, read_idx, base|qual, qoff, counts, last_read, live_mask, run_pos,
                     // strag_idx, strag_col, run_first_col, base4, special_entry, special_base, reference_base
+  // maq_mode: per column gt0, gt1, s0, s1, n_valid; calls: col, pos, gt, ref, qual
+  DevBuf dm[10];
+  PinBuf hm[10];
+  uint32_t n_calls = 0;
   uint32_t n_strag = 0, n_runs = 0, n_special = 0;
   size_t col_cap = 0, ent_cap = 0;
   cudaEvent_t computed = nullptr, done = nullptr;
@@ -84,10 +90,18 @@ struct biodb_pileup {
   // reference bases from MD tags (use_md_tag; mdtag.cu, md_chain.h)
   std::unique_ptr<MdChain> md;       // which read's dna() serves which positions; its state runs across batches
   std::vector<MdSegment> md_segs;    // segments of the group being produced
+  DevBuf maq_ent[2];                 // maq_mode: the entries as the caller sees them (base | strand, min(quality, mapq))
+  DevBuf redo;                       // chunks of 32 columns the tile kernel left to the read-stationary one
+  int tile_mode = 1;                 // BIODB_PILEUP_TILE: 0 = the read-stationary kernel alone, 2 = the column-stationary
+                                     // kernel for every form, default 1 = for the forms that do not deliver read_idx
+                                     // (compact_reads, MAQ), where it saves writing and re-reading 4 bytes per entry
   DevBuf md_len, md_dsegs, md_keep_buf[2][2];
   PinBuf md_h, md_hsegs;
   MdKeep md_keep{{~0ull, ~0ull}, {0, 0}, {nullptr, nullptr}};   // providers materialised by the previous batch
   int md_keep_set = 0;
+  // maq_mode (maq.h)
+  MaqParams maq;
+  MaqDevTables maq_tab{nullptr, nullptr, nullptr};
   // region mode (biodb_pileup_begin_region): the reads are those of bam[ref][beg .. end) — the index's chunks read one
   // after the other, every batch reduced to the reads of the region (region.cu) before the pileup sees it
   bool region = false, region_done = false;
@@ -410,6 +424,12 @@ void biodb_pileup::reset(const biodb_pileup_params* p) {
   chunk_i = 0;
   region_index = 0;
   md.reset(prm.use_md_tag ? new MdChain(prm.skip_zero_coverage != 0) : nullptr);
+  maq = MaqParams();
+  maq_tab = MaqDevTables{nullptr, nullptr, nullptr};
+  {
+    const char* e = getenv("BIODB_PILEUP_TILE");
+    tile_mode = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
+  }
   md_segs.clear();
   md_keep.id[0] = md_keep.id[1] = ~0ull;
   md_keep_set = 0;
@@ -472,6 +492,45 @@ biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, b
     if (s == BIODB_OK && (cudaEventCreate(&o.computed) != cudaSuccess || cudaEventCreate(&o.done) != cudaSuccess)) s = BIODB_ERR_CUDA;
   if (s != BIODB_OK) { delete pl; return s; }
   *out = pl;
+  return BIODB_OK;
+}
+
+biodb_status biodb_pileup_maq_params(biodb_pileup* pl, const biodb_maq_params* mp) {
+  if (!pl || pl->worker_started) return BIODB_ERR_ARG;
+  pl->maq = MaqParams();
+  if (mp) {
+    pl->maq.depcorr = mp->depcorr; pl->maq.eta = mp->eta; pl->maq.minimum_call_quality = mp->minimum_call_quality;
+    pl->maq.minimum_base_quality = mp->minimum_base_quality;
+  }
+  if (pl->maq.minimum_base_quality < 0 || pl->maq.minimum_base_quality > 255) return BIODB_ERR_ARG;
+  pl->maq_tab = MaqDevTables{nullptr, nullptr, nullptr};
+  return BIODB_OK;
+}
+
+// The MAQ coefficient tables of (depcorr, eta) on the device: computed on the host the way ErrorModelCoefficients'
+// constructor does (maq.d:80-120) once per reader and pair of values.
+static biodb_status maq_tables(biodb_pileup* pl) {
+  if (pl->maq_tab.fk) return BIODB_OK;
+  biodb_reader* r = pl->r;
+  std::lock_guard<std::mutex> lk(r->pool_mu);
+  for (auto& c : r->maq_cache)
+    if (c->depcorr == pl->maq.depcorr && c->eta == pl->maq.eta) {
+      pl->maq_tab = MaqDevTables{c->fk.as<double>(), c->beta.as<double>(), c->lhet.as<double>()};
+      return BIODB_OK;
+    }
+  // MaqSnpCaller keeps depcorr / eta as floats and hands them to ErrorModel(float, float) (maq.d:329-338)
+  MaqTablesHost h((double)pl->maq.depcorr, (double)pl->maq.eta);
+  std::unique_ptr<biodb_reader::MaqCache> c(new biodb_reader::MaqCache);
+  c->depcorr = pl->maq.depcorr;
+  c->eta = pl->maq.eta;
+  if (c->fk.ensure(h.fk.size() * 8) != cudaSuccess || c->beta.ensure(h.beta.size() * 8) != cudaSuccess ||
+      c->lhet.ensure(h.lhet.size() * 8) != cudaSuccess ||
+      cudaMemcpy(c->fk.p, h.fk.data(), h.fk.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(c->beta.p, h.beta.data(), h.beta.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(c->lhet.p, h.lhet.data(), h.lhet.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+    return BIODB_ERR_CUDA;
+  pl->maq_tab = MaqDevTables{c->fk.as<double>(), c->beta.as<double>(), c->lhet.as<double>()};
+  r->maq_cache.push_back(std::move(c));
   return BIODB_OK;
 }
 
@@ -941,16 +1000,18 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       s.clo = clo;
       s.chi = chi;
       ColumnScratch c{pl->cs[0].as<int32_t>(), os.d[2].as<uint32_t>(), pl->cs[1].as<uint32_t>(), pl->cs[2].as<uint32_t>()};
-      ColumnOutput o{os.d[0].as<uint64_t>(), os.d[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr, nullptr};
+      ColumnOutput o{os.d[0].as<uint64_t>(), os.d[1].as<uint64_t>(), nullptr, nullptr, nullptr, nullptr, nullptr, -1};
       p.stage_begin();
       pileup_phase2(v, g0, g1, n_islands, n_col, s, c, o, st);
       p.stage_end(&p.stats.pileup_ms);
       PL_TRY(launch_copy_bytes(pl->h_small.p, o.col_off + n_col, 8, st));
       PL_TRY(cudaStreamSynchronize(st));
       n_entries = *pl->h_small.as<uint64_t>();
-      const bool counts_only = pl->prm.counts_only != 0;
-      const bool want_q = pl->prm.want_query_offset != 0 && !counts_only;
-      const bool compact = pl->prm.compact_reads != 0 && !counts_only;
+      const int maq_mode = pl->prm.maq_mode;
+      const bool maq = maq_mode > 0;
+      const bool counts_only = pl->prm.counts_only != 0 && !maq;
+      const bool want_q = pl->prm.want_query_offset != 0 && !counts_only && !maq;
+      const bool compact = pl->prm.compact_reads != 0 && !counts_only && !maq;
       if (compact && n_entries >= 0xfffffff0ull)      // special_entry[] indexes entries with 32 bits
         return pl->fail(BIODB_ERR_NOMEM, "too many column entries in one batch for the compact encoding; lower blocks_per_batch");
       if (counts_only) {
@@ -958,7 +1019,17 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         if (!p.r->opts.device_output) PL_TRY(os.h[6].ensure(os.col_cap * 24));
         o.counts = os.d[7].as<uint32_t>();
       }
-      if (!counts_only && n_entries + 8 > os.ent_cap) {
+      if (maq) {
+        // the entries stay on the device, as the caller's view of them: base | strand, min(quality, mapping quality)
+        biodb_status ms = maq_tables(pl);
+        if (ms != BIODB_OK) return pl->fail(ms, "cannot set up the MAQ coefficient tables on the device");
+        PL_TRY(pl->maq_ent[0].ensure((size_t)n_entries + 64, st));
+        PL_TRY(pl->maq_ent[1].ensure((size_t)n_entries + 64, st));
+        o.base = pl->maq_ent[0].as<uint8_t>();
+        o.qual = pl->maq_ent[1].as<uint8_t>();
+        o.maq_min_base_quality = pl->maq.minimum_base_quality;
+      }
+      if (!counts_only && !maq && n_entries + 8 > os.ent_cap) {
         size_t cap = (size_t)n_entries + n_entries / 8 + 4096;
         PL_TRY(os.d[3].ensure(cap * 4, st));
         PL_TRY(os.d[4].ensure(cap, st));
@@ -973,14 +1044,32 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         PL_TRY(os.d[6].ensure(os.ent_cap * 4, st));
         if (!p.r->opts.device_output) PL_TRY(os.h[5].ensure(os.ent_cap * 4));
       }
-      if (!counts_only) {
+      if (!counts_only && !maq) {
         o.read_idx = os.d[3].as<uint32_t>();
         o.base = os.d[4].as<uint8_t>();
         o.qual = os.d[5].as<uint8_t>();
       }
       o.qoff = want_q ? os.d[6].as<uint32_t>() : nullptr;
+      // entries: the column-stationary kernel for the plain / compact / MAQ forms (chunks deeper than its tile, and
+      // the counts / query-offset forms, go to the read-stationary kernel)
+      const bool tile = !counts_only && !want_q && (pl->tile_mode == 2 || (pl->tile_mode == 1 && (compact || maq)));
+      uint32_t* redo = nullptr;
+      if (tile) {
+        PL_TRY(pl->redo.ensure((size_t)(pileup_tile_chunks(n_col) + 8) * 4, st));
+        redo = pl->redo.as<uint32_t>();
+        if (compact) {
+          PL_TRY(os.d[8].ensure(os.col_cap * 4, st));
+          PL_TRY(os.d[9].ensure(os.col_cap * 8, st));
+        }
+      }
       p.stage_begin();
-      pileup_entries(v, n_col, s, c, o, st);
+      if (tile) {
+        pileup_entries_tile(v, n_col, s, c, o, maq ? 2 : compact ? 1 : 0, os.d[8].as<uint32_t>(), os.d[9].as<uint64_t>(),
+                            pl->cs[0].as<uint32_t>(), redo, st);
+        pileup_entries(v, n_col, s, c, o, st, redo);
+      } else {
+        pileup_entries(v, n_col, s, c, o, st);
+      }
       p.stage_end(&p.stats.pileup_ms);
       if (use_md) {
         // reference_base: 'N' everywhere, then the providers' dna() replayed over the columns their segments cover
@@ -1005,6 +1094,44 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       os.n_strag = 0;
       os.n_runs = 0;
       os.n_special = 0;
+      os.n_calls = 0;
+      MaqColumns mq{nullptr, nullptr, nullptr, nullptr, nullptr};
+      if (maq) {
+        // genotype likelihoods of every column (maq.cu), then findSNPs' filter as a compaction
+        PL_TRY(os.dm[0].ensure(os.col_cap, st));
+        PL_TRY(os.dm[1].ensure(os.col_cap, st));
+        PL_TRY(os.dm[2].ensure(os.col_cap * 4, st));
+        PL_TRY(os.dm[3].ensure(os.col_cap * 4, st));
+        PL_TRY(os.dm[4].ensure(os.col_cap * 2, st));
+        mq = MaqColumns{os.dm[0].as<uint8_t>(), os.dm[1].as<uint8_t>(), os.dm[2].as<float>(), os.dm[3].as<float>(),
+                        os.dm[4].as<uint16_t>()};
+        uint32_t* flag = pl->cs[1].as<uint32_t>();          // the candidate windows (lo / hi) are dead after the entries kernel
+        uint32_t* incl = pl->cs[2].as<uint32_t>();
+        const uint8_t* refb = use_md ? os.d[20].as<uint8_t>() : nullptr;
+        p.stage_begin();
+        maq_columns(o.col_off, o.base, o.qual, n_col, pl->maq_tab, mq, st);
+        maq_call_flags(mq, refb, n_col, pl->maq.minimum_call_quality, flag, st);
+        device_scan<true>(flag, incl, (uint64_t)n_col, s.tmp_u32b, OpAdd(), 0u, st);
+        p.stage_end(&p.stats.pileup_ms);
+        PL_TRY(launch_copy_bytes(pl->h_small.p, incl + (n_col - 1), 4, st));
+        PL_TRY(cudaStreamSynchronize(st));
+        os.n_calls = pl->h_small.as<uint32_t>()[0];
+        static const size_t csz[5] = {4, 8, 1, 1, 4};
+        for (int k = 0; k < 5; ++k) {
+          PL_TRY(os.dm[5 + k].ensure((size_t)os.n_calls * csz[k] + 64, st));
+          if (!p.r->opts.device_output) PL_TRY(os.hm[5 + k].ensure((size_t)os.n_calls * csz[k] + 64));
+        }
+        if (os.n_calls) {
+          p.stage_begin();
+          maq_call_gather(mq, refb, o.col_pos, n_col, flag, incl, os.dm[5].as<uint32_t>(), os.dm[6].as<uint64_t>(),
+                          os.dm[7].as<uint8_t>(), os.dm[8].as<uint8_t>(), os.dm[9].as<float>(), st);
+          p.stage_end(&p.stats.pileup_ms);
+        }
+        if (maq_mode >= 2 && !p.r->opts.device_output) {
+          static const size_t msz[5] = {1, 1, 4, 4, 2};
+          for (int k = 0; k < 5; ++k) PL_TRY(os.hm[k].ensure(os.col_cap * msz[k]));
+        }
+      }
       if (compact) {
         // sequential compact encoding (include/biod_b200.h): read lists as last read + window mask + stragglers
         // (compact_mask_kernel), positions as runs of consecutive positions (run_flag_kernel)
@@ -1019,7 +1146,17 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         uint32_t* run_incl = pl->cs[2].as<uint32_t>();
         p.stage_begin();
         pileup_compact_masks(n_col, o, os.d[8].as<uint32_t>(), os.d[9].as<uint64_t>(), pl->cs[0].as<uint32_t>(),
-                             os.d[10].as<uint32_t>(), s, st);
+                             os.d[10].as<uint32_t>(), s, st, redo);
+        // the stragglers of the columns that have any: walked out of the candidate reads now, while their windows (lo / hi)
+        // are still there — the position-run scratch below reuses those arrays
+        PL_TRY(launch_copy_bytes(pl->h_small.p, os.d[10].as<uint32_t>() + n_col, 4, st));
+        PL_TRY(cudaStreamSynchronize(st));
+        os.n_strag = pl->h_small.as<uint32_t>()[0];
+        PL_TRY(os.d[11].ensure((size_t)os.n_strag * 4 + 64, st));
+        PL_TRY(os.d[12].ensure((size_t)os.n_strag * 4 + 64, st));
+        if (os.n_strag)
+          pileup_strag_walk(v, n_col, s, c.lo, c.hi, o.col_pos, os.d[10].as<uint32_t>(), os.d[12].as<uint32_t>(),
+                            os.d[11].as<uint32_t>(), st);
         pileup_position_runs_scan(n_col, o, run_flag, run_incl, s, st);
         // bases two per byte + the list of entries that are not a base ('-' in D / N, 0 past l_seq)
         const uint32_t npb = pileup_pack_blocks(n_entries);
@@ -1035,7 +1172,6 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         PL_TRY(launch_copy_bytes(pl->h_small.as<uint32_t>() + 1, run_incl + (n_col - 1), 4, st));
         if (npb) PL_TRY(launch_copy_bytes(pl->h_small.as<uint32_t>() + 2, os.d[17].as<uint32_t>() + npb, 4, st));
         PL_TRY(cudaStreamSynchronize(st));
-        os.n_strag = pl->h_small.as<uint32_t>()[0];
         os.n_runs = pl->h_small.as<uint32_t>()[1];
         os.n_special = npb ? pl->h_small.as<uint32_t>()[2] : 0;
         PL_TRY(os.d[18].ensure((size_t)os.n_special * 4 + 64, st));
@@ -1044,8 +1180,6 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
           PL_TRY(os.h[14].ensure((size_t)os.n_special * 4 + 64));
           PL_TRY(os.h[15].ensure((size_t)os.n_special + 64));
         }
-        PL_TRY(os.d[11].ensure((size_t)os.n_strag * 4 + 64, st));
-        PL_TRY(os.d[12].ensure((size_t)os.n_strag * 4 + 64, st));
         PL_TRY(os.d[13].ensure((size_t)os.n_runs * 8 + 64, st));
         PL_TRY(os.d[14].ensure((size_t)(os.n_runs + 1) * 4 + 64, st));
         if (!p.r->opts.device_output) {
@@ -1055,8 +1189,6 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
           PL_TRY(os.h[12].ensure((size_t)(os.n_runs + 1) * 4 + 64));
         }
         p.stage_begin();
-        if (os.n_strag)
-          pileup_compact_stragglers(n_col, o, os.d[10].as<uint32_t>(), os.d[12].as<uint32_t>(), os.d[11].as<uint32_t>(), st);
         pileup_position_runs_scatter(n_col, o, run_flag, run_incl, os.d[13].as<uint64_t>(), os.d[14].as<uint32_t>(), st);
         if (os.n_special)
           pileup_pack_specials(n_entries, o.base, os.d[17].as<uint32_t>(), os.d[18].as<uint32_t>(), os.d[19].as<uint8_t>(), st);
@@ -1067,7 +1199,20 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       if (!p.r->opts.device_output) {
         cudaStream_t cs = pl->copy_st;
         PL_TRY(cudaStreamWaitEvent(cs, os.computed, 0));
-        if (compact) {
+        if (maq) {
+          static const size_t csz[5] = {4, 8, 1, 1, 4}, msz[5] = {1, 1, 4, 4, 2};
+          for (int k = 0; k < 5 && os.n_calls; ++k)
+            PL_TRY(cudaMemcpyAsync(os.hm[5 + k].p, os.dm[5 + k].p, (size_t)os.n_calls * csz[k], cudaMemcpyDeviceToHost, cs));
+          p.stats.d2h_bytes += (uint64_t)os.n_calls * 18;
+          if (maq_mode >= 2) {
+            PL_TRY(cudaMemcpyAsync(os.h[0].p, o.col_pos, (size_t)n_col * 8, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[1].p, o.col_off, (size_t)(n_col + 1) * 8, cudaMemcpyDeviceToHost, cs));
+            PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
+            for (int k = 0; k < 5; ++k)
+              PL_TRY(cudaMemcpyAsync(os.hm[k].p, os.dm[k].p, (size_t)n_col * msz[k], cudaMemcpyDeviceToHost, cs));
+            p.stats.d2h_bytes += (uint64_t)n_col * 32 + 8;
+          }
+        } else if (compact) {
           p.stats.d2h_bytes += (uint64_t)n_col * 16 + n_entries + (n_entries + 1) / 2 + n_entries * (want_q ? 4 : 0) +
                                (uint64_t)os.n_strag * 8 + (uint64_t)os.n_runs * 12 + 4 + (uint64_t)os.n_special * 5;
           PL_TRY(cudaMemcpyAsync(os.h[2].p, c.nstart, (size_t)n_col * 4, cudaMemcpyDeviceToHost, cs));
@@ -1099,7 +1244,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
           }
         }
         if (want_q) PL_TRY(cudaMemcpyAsync(os.h[5].p, o.qoff, (size_t)n_entries * 4, cudaMemcpyDeviceToHost, cs));
-        if (use_md) {
+        if (use_md && !(maq && maq_mode < 2)) {
           PL_TRY(cudaMemcpyAsync(os.h[16].p, os.d[20].p, (size_t)n_col, cudaMemcpyDeviceToHost, cs));
           p.stats.d2h_bytes += n_col;
         }
@@ -1208,6 +1353,14 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         cols->run_first_col = os.d[14].as<uint32_t>();
       }
       cols->reference_base = use_md ? os.d[20].as<uint8_t>() : nullptr;
+      if (pl->prm.maq_mode > 0) {
+        cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
+        cols->n_calls = os.n_calls;
+        cols->call_col = os.dm[5].as<uint32_t>(); cols->call_pos = os.dm[6].as<uint64_t>(); cols->call_gt = os.dm[7].as<uint8_t>();
+        cols->call_ref = os.dm[8].as<uint8_t>(); cols->call_qual = os.dm[9].as<float>();
+        cols->maq_gt0 = os.dm[0].as<uint8_t>(); cols->maq_gt1 = os.dm[1].as<uint8_t>(); cols->maq_s0 = os.dm[2].as<float>();
+        cols->maq_s1 = os.dm[3].as<float>(); cols->maq_n_valid = os.dm[4].as<uint16_t>();
+      }
       return BIODB_OK;
     }
     cols->position = os.h[0].as<uint64_t>();
@@ -1236,6 +1389,19 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       cols->run_first_col = os.h[12].as<uint32_t>();
     }
     cols->reference_base = use_md ? os.h[16].as<uint8_t>() : nullptr;
+    if (pl->prm.maq_mode > 0) {
+      cols->read_idx = nullptr; cols->base = nullptr; cols->qual = nullptr; cols->query_offset = nullptr;
+      cols->n_calls = os.n_calls;
+      cols->call_col = os.hm[5].as<uint32_t>(); cols->call_pos = os.hm[6].as<uint64_t>(); cols->call_gt = os.hm[7].as<uint8_t>();
+      cols->call_ref = os.hm[8].as<uint8_t>(); cols->call_qual = os.hm[9].as<float>();
+      if (pl->prm.maq_mode >= 2) {
+        cols->maq_gt0 = os.hm[0].as<uint8_t>(); cols->maq_gt1 = os.hm[1].as<uint8_t>(); cols->maq_s0 = os.hm[2].as<float>();
+        cols->maq_s1 = os.hm[3].as<float>(); cols->maq_n_valid = os.hm[4].as<uint16_t>();
+      } else {
+        cols->position = nullptr; cols->col_off = nullptr; cols->n_starting_here = nullptr;
+        if (use_md) cols->reference_base = nullptr;       // (the calls carry their reference base)
+      }
+    }
     return BIODB_OK;
   }
 }

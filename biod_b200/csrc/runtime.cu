@@ -1233,8 +1233,12 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
                                const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
                                int32_t* status, uint32_t* crc, void* stream) {
   InflateArgs ia{comp, payload_off, cdata_size, out_off, isize, out, status, n_blocks, WalkOut{}, nullptr};
-  if (launch_inflate(ia, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
-  if (crc && launch_crc32(out, out_off, isize, n_blocks, crc, (cudaStream_t)stream) != cudaSuccess) return BIODB_ERR_CUDA;
+  cudaError_t e = launch_inflate(ia, (cudaStream_t)stream);
+  if (e == cudaSuccess && crc) e = launch_crc32(out, out_off, isize, n_blocks, crc, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, std::string("biodb_dev_inflate: ") + cudaGetErrorString(e));   // biodb_open_error()
+    return BIODB_ERR_CUDA;
+  }
   return BIODB_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -77,6 +78,9 @@ struct biodb_reader {
   std::vector<uint64_t> block_index;
   uint64_t data_end_coffset = 0;
   biodb_status build_block_index();
+  // MAQ coefficient tables on the device (maq.h), kept per (depcorr, eta)
+  struct MaqCache { float depcorr, eta; biodb::DevBuf fk, beta, lhet; };
+  std::vector<std::unique_ptr<MaqCache>> maq_cache;
   // cuts of the file into n shards (biodb_shard_cuts), kept per n
   struct ShardCuts { uint32_t n = 0; std::vector<uint64_t> vo; std::vector<int32_t> ref; std::vector<int64_t> pos; };
   std::vector<ShardCuts> shard_cuts;

@@ -181,8 +181,24 @@ typedef struct biodb_pileup_params {
   int32_t counts_only;         /* 1 = per-column A,C,G,T,other,del counts instead of entries */
   int32_t compact_reads;       /* 1 = sequential compact encoding of the column table (position runs, read lists as
                                   last_read / live_mask / stragglers): see biodb_column_batch */
-  int32_t reserved[2];
+  int32_t maq_mode;            /* MAQ genotype likelihoods over the columns, computed on the device (SURVEY.md 8f row N3;
+                                  MaqSnpCaller, bio/std/hts/snpcallers/maq.d:319-540) INSTEAD of delivering the entries:
+                                  1 = findSNPs — only the calls that differ from the reference base and exceed
+                                      minimum_call_quality leave the device (a few bytes per call);
+                                  2 = also genotypeLikelihoodInfo / makeCall of every column (12 bytes per column) with
+                                      position, col_off, n_starting_here.
+                                  Set the caller's knobs with biodb_pileup_maq_params before the first _next.  findSNPs
+                                  needs reference bases: combine with use_md_tag (without it every base is 'N'). */
+  int32_t reserved[1];
 } biodb_pileup_params;
+
+/* MaqSnpCaller's knobs (maq.d:327-380) and their defaults */
+typedef struct biodb_maq_params {
+  float depcorr;               /* 0.17 */
+  float eta;                   /* 0.03 */
+  float minimum_call_quality;  /* 6.0 */
+  int32_t minimum_base_quality;/* 13 */
+} biodb_maq_params;
 
 typedef struct biodb_column_batch {
   uint64_t n_columns;
@@ -225,6 +241,23 @@ typedef struct biodb_column_batch {
   /* use_md_tag = 1 (any encoding): PileupColumn.reference_base per column (pileup.d:252-254,614-653), 'N' where no
    * read's MD tag supplies it; NULL otherwise (BioD's default column has 'N', pileup.d:239). */
   const uint8_t* reference_base; /* [n_columns] */
+  /* maq_mode >= 1: the calls of findSNPs (maq.d:489-540) among this batch's columns, in column order.  Genotypes are
+   * DiploidGenotype!Base5 codes, first allele * 5 + second with A C G T N = 0..4 (bio/core/genotype.d:33-37); a
+   * heterozygote is stored as (later nucleotide)|(earlier nucleotide), as computeLikelihoods keys it (maq.d:218-228).
+   * call_qual = score of the second best genotype - score of the best (maq.d:480-482). */
+  uint64_t n_calls;
+  const uint32_t* call_col;      /* [n_calls] column index within the batch */
+  const uint64_t* call_pos;      /* [n_calls] */
+  const uint8_t* call_gt;        /* [n_calls] */
+  const uint8_t* call_ref;       /* [n_calls] reference base character */
+  const float* call_qual;        /* [n_calls] */
+  /* maq_mode == 2: per column the two best genotypes (255 = no base passed the filters) and their scores
+   * (GenotypeLikelihoodInfo[0], [1], maq.d:252-310), and the number of bases that passed the filters. */
+  const uint8_t* maq_gt0;        /* [n_columns] */
+  const uint8_t* maq_gt1;
+  const float* maq_s0;
+  const float* maq_s1;
+  const uint16_t* maq_n_valid;
 } biodb_column_batch;
 
 biodb_status biodb_pileup_begin(biodb_reader* r, const biodb_pileup_params* p, biodb_pileup** out);
@@ -282,6 +315,8 @@ biodb_status biodb_pileup_begin_range(biodb_reader* r, const biodb_pileup_params
  * biodb_reads_begin_region yields them.  BIODB_ERR_ARG: beg >= end or invalid reference index. */
 biodb_status biodb_pileup_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
                                        const biodb_pileup_params* p, biodb_pileup** out);
+/* The knobs of maq_mode (NULL = MaqSnpCaller's defaults).  Call before the first biodb_pileup_next. */
+biodb_status biodb_pileup_maq_params(biodb_pileup* pl, const biodb_maq_params* mp);
 biodb_status biodb_pileup_next(biodb_pileup* pl, biodb_column_batch* cols);
 void biodb_pileup_end(biodb_pileup* pl);
 /* Reference id of the pileup (AbstractPileup.ref_id, pileup.d:455-457); valid after the first _next. */
