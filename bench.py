@@ -131,13 +131,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False, halo_voffset=None):
+def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False, halo_voffset=None, maq=False, calls=None):
     """One full pileup pass (pileupColumns); shard=(rank, world) runs this rank's shard of it (halo guessed at 8 BGZF
     blocks, or starting at halo_voffset).  Returns (stats, n_records, n_cols, n_entries)."""
     p = capi.PileupParams()
     p.single_ref, p.skip_zero_coverage, p.end_at = 0, 1, 2**64 - 1
     p.compact_reads = int(compact)
     p.use_md_tag = int(use_md)
+    p.maq_mode = 1 if maq else 0
     pl = C.c_void_p()
     sharded = shard is not None and shard[1] > 1
     if sharded and halo_voffset is not None:
@@ -149,12 +150,16 @@ def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False
     if st != capi.OK:
         raise RuntimeError(L.biodb_last_error(reader).contents.message.decode())
     cb = capi.ColumnBatch()
+    n_calls = 0
     while True:
         st = L.biodb_pileup_next(pl, C.byref(cb))
         if st == capi.EOF:
             break
         if st != capi.OK:
             raise RuntimeError(L.biodb_last_error(reader).contents.message.decode())
+        n_calls += int(cb.n_calls)
+    if calls is not None:
+        calls.append(n_calls)
     s = capi.Stats()
     L.biodb_pileup_stats(pl, C.byref(s))
     nr, nc, ne = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -337,6 +342,13 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
         e_rerun = float(eredo[0].total_ms) if eredo else 0.0
         ex = run_pass(L, capi, rd, shard, compact=False)     # same pass with explicit read_idx lists, for comparison
         barrier()
+        # the fused consumer (row N3): MAQ genotype likelihoods of every column computed on the device behind the pileup
+        # (reference bases from the MD tags), only the SNP calls copied back — MaqSnpCaller.findSNPs end to end
+        minfo, ncalls = {}, []
+        run_pass(L, capi, rd, shard, minfo, use_md=True, maq=True)
+        barrier()
+        mq = [run_pass(L, capi, rd, shard, minfo, use_md=True, maq=True, calls=ncalls) for _ in range(steps)]
+        barrier()
         rp = None
         if want_reads_pass and world == 1:
             # BamReader.reads alone: every record (raw bytes + field tables) delivered to host memory
@@ -359,6 +371,22 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
                                  "last_read, 64-bit window mask (+ stragglers); per entry base + qual",
                       "with_explicit_read_idx": {"ms_per_step": float(ex[0].total_ms), "d2h_bytes_per_step": int(ex[0].d2h_bytes),
                                                  "value": (tot_col / (float(ex[0].total_ms) * 1e-3)) if world == 1 else None}}
+        m_ms = sum(s[0].total_ms for s in mq)
+        tm = torch.tensor([m_ms, float(ncalls[-1])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tmx = tm.clone()
+            dist.all_reduce(tmx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tm, op=dist.ReduceOp.SUM)
+            m_ms, tot_calls = float(tmx[0]) / steps, int(tm[1])
+        else:
+            m_ms, tot_calls = m_ms / steps, int(ncalls[-1])
+        out["maq_e2e"] = {"value": tot_col / (m_ms * 1e-3), "unit": "positions/s", "ms_per_step": m_ms,
+                          "h2d_bytes_per_step": int(mq[-1][0].h2d_bytes), "d2h_bytes_per_step": int(mq[-1][0].d2h_bytes),
+                          "snp_calls": tot_calls,
+                          "what": "MaqSnpCaller.findSNPs(makePileup(reads, use_md_tag)) through the C ABI from host memory: inflate, "
+                                  "decode, pileup, MD reference bases and MAQ likelihoods on the device; only the calls "
+                                  "(18 B each) and the MD chain's inputs (12 B per read) cross PCIe device->host"
+                                  + ("" if world == 1 else "; shards start their MD provider chain at their halo, as BioD's chunks do")}
         if rp is not None:
             out["reads_pass_e2e"] = {"records_per_sec": rp[1] / (float(rp[0].total_ms) * 1e-3), "ms_per_step": float(rp[0].total_ms),
                                      "h2d_bytes_per_step": int(rp[0].h2d_bytes), "d2h_bytes_per_step": int(rp[0].d2h_bytes),
@@ -499,6 +527,8 @@ def main():
         line["e2e"] = m["e2e"]
     if "reads_pass_e2e" in m:
         line["reads_pass_e2e"] = m["reads_pass_e2e"]
+    if "maq_e2e" in m:
+        line["maq_e2e"] = m["maq_e2e"]
     # diagnostics of the lane-parallel inflate kernel over everything run so far (0 blocks given up = no fallback)
     try:
         cnt = (C.c_uint64 * 8)()
@@ -519,7 +549,7 @@ def main():
                 "workload": workload_name(CONFIGS[xc], xn, CONFIGS[xc]["reads"]), "value": x["value"], "unit": "positions/s",
                 "ms_per_step": x["ms_per_step"], "records_per_sec": x["records_per_sec"],
                 "total_reads": x["totals"][2], "total_positions": x["totals"][0], "halo": x["halo"],
-                "e2e": x.get("e2e"), "stitch": x["stitch"], "generated_in_s": x["generated_in_s"],
+                "e2e": x.get("e2e"), "maq_e2e": x.get("maq_e2e"), "stitch": x["stitch"], "generated_in_s": x["generated_in_s"],
                 "stage_ms": {"inflate": float(np.mean([s[0].inflate_ms for s in x["runs"]])),
                              "record_scan": float(np.mean([s[0].scan_ms for s in x["runs"]])),
                              "pileup": float(np.mean([s[0].pileup_ms for s in x["runs"]]))}}

@@ -140,8 +140,6 @@ def lib():
     L.biodb_input_is_pinned.argtypes = [vp]
     L.biodb_debug_inflate_counters.restype = C.c_int
     L.biodb_debug_inflate_counters.argtypes = [u64p, C.c_int32]
-    L.biodb_debug_inflate_cycles.restype = C.c_int
-    L.biodb_debug_inflate_cycles.argtypes = [u64p, C.c_int32]
     L.biodb_debug_md_chain.restype = C.c_int64
     L.biodb_debug_md_chain.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int32, C.c_uint64, vp, C.c_uint64]
     L.biodb_index_open.restype = C.c_int
@@ -210,7 +208,7 @@ EXPORTS = [
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_begin_shard_at", "biodb_pileup_shard_info",
     "biodb_pileup_shard_reach", "biodb_shard_cuts", "biodb_pileup_begin_range", "biodb_pileup_maq_params",
-    "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_inflate_cycles", "biodb_debug_md_chain",
+    "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
     "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",
     "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",

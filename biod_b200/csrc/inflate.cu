@@ -65,7 +65,7 @@ struct __align__(16) WarpSmem {
 
 }  // namespace
 
-// retry_only != 0: redo only the blocks that inflate_par_kernel gave up on (status == STATUS_RETRY)
+// retry_only != 0: redo only the blocks that the decode / resolve kernels gave up on (status == STATUS_RETRY)
 __global__ void __launch_bounds__(32) inflate_kernel(InflateArgs a, int retry_only) {
   __shared__ WarpSmem sm;
   WarpSmem* s = &sm;
@@ -478,39 +478,23 @@ unsigned long long g_kernel_launches = 0;
 
 size_t inflate_smem_bytes() { return sizeof(WarpSmem); }
 
-// Which kernels inflate: the decode + resolve pair (inflate_tok.cu) unless BIODB_INFLATE says otherwise — "duo" = one
-// kernel with a decoder and a resolver warp per block (inflate_duo.cu), "par" = the one-warp lane-parallel kernel
-// (inflate_par.cu), "serial" = the warp-serial kernel alone (A/B measurements).
-enum { MODE_TOK = 0, MODE_DUO = 1, MODE_PAR = 2, MODE_SERIAL = 3 };
+// Which kernels inflate: the decode + resolve pair (inflate_tok.cu) followed by this file's warp-serial kernel on the
+// blocks they gave up on, unless BIODB_INFLATE=serial selects the warp-serial kernel alone (A/B measurements).
+enum { MODE_TOK = 0, MODE_SERIAL = 1 };
 static int inflate_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("BIODB_INFLATE");
-    v = (e && e[0] == 's') ? MODE_SERIAL : (e && e[0] == 'p') ? MODE_PAR : (e && e[0] == 'd') ? MODE_DUO : MODE_TOK;
+    v = (e && e[0] == 's') ? MODE_SERIAL : MODE_TOK;
   }
   return v;
 }
 
-int inflate_resident_blocks(int device) {
-  const int m = inflate_mode();
-  return m == MODE_TOK ? inflate_tok_resident_blocks(device) : m == MODE_DUO ? inflate_duo_resident_blocks(device)
-                                                                             : inflate_par_resident_blocks(device);
-}
+int inflate_resident_blocks(int device) { return inflate_tok_resident_blocks(device); }
 
-size_t inflate_token_bytes(uint32_t n_blocks) {
-  const int m = inflate_mode();
-  return m == MODE_TOK ? inflate_tok_token_bytes(n_blocks) : m == MODE_DUO ? inflate_duo_token_bytes(n_blocks) : 0;
-}
+size_t inflate_token_bytes(uint32_t n_blocks) { return inflate_mode() == MODE_TOK ? inflate_tok_token_bytes(n_blocks) : 0; }
 
-cudaError_t inflate_counters(unsigned long long* out8, int reset) {
-  unsigned long long p[8], d[8], t[8];
-  cudaError_t e = inflate_par_counters(p, reset);
-  if (e == cudaSuccess) e = inflate_duo_counters(d, reset);
-  if (e == cudaSuccess) e = inflate_tok_counters(t, reset);
-  if (e == cudaSuccess)
-    for (int i = 0; i < 8; ++i) out8[i] = p[i] + d[i] + t[i];
-  return e;
-}
+cudaError_t inflate_counters(unsigned long long* out8, int reset) { return inflate_tok_counters(out8, reset); }
 
 static InflateArgs slice_args(const InflateArgs& a, uint32_t b0, uint32_t n) {
   InflateArgs s = a;
@@ -521,36 +505,32 @@ static InflateArgs slice_args(const InflateArgs& a, uint32_t b0, uint32_t n) {
 
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st) {
   if (a.n_blocks == 0) return cudaSuccess;
-  const int mode = inflate_mode();
-  if (mode == MODE_SERIAL) {
+  if (inflate_mode() == MODE_SERIAL) {
     inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 0);
     ++g_kernel_launches;
     return cudaGetLastError();
   }
   cudaError_t e = cudaSuccess;
-  if (mode == MODE_PAR) {
-    e = launch_inflate_par(a, st);                 // one-warp lane-parallel kernel; marks the blocks it gives up on
-    g_kernel_launches += 1;
-  } else if (a.tok) {
-    e = mode == MODE_TOK ? launch_inflate_tok(a, st) : launch_inflate_duo(a, st);
-    g_kernel_launches += mode == MODE_TOK ? 2 : 1;
+  if (a.tok) {
+    e = launch_inflate_tok(a, st);
+    g_kernel_launches += 2;
   } else {
     // callers without a token area of their own (the device-resident stage API, no fused record walk): one is allocated
     // for the call (stream-ordered) and the blocks go through it slab by slab
     const uint32_t slab = std::min<uint32_t>(a.n_blocks, 8192);
     void* tmp = nullptr;
-    e = cudaMallocAsync(&tmp, inflate_token_bytes(slab), st);
+    e = cudaMallocAsync(&tmp, inflate_tok_token_bytes(slab), st);
     if (e != cudaSuccess) return e;
     for (uint32_t b0 = 0; b0 < a.n_blocks && e == cudaSuccess; b0 += slab) {
       InflateArgs s = slice_args(a, b0, std::min<uint32_t>(slab, a.n_blocks - b0));
       s.tok = (uint16_t*)tmp;
-      e = mode == MODE_TOK ? launch_inflate_tok(s, st) : launch_inflate_duo(s, st);
-      g_kernel_launches += mode == MODE_TOK ? 2 : 1;
+      e = launch_inflate_tok(s, st);
+      g_kernel_launches += 2;
     }
     cudaFreeAsync(tmp, st);
   }
   if (e != cudaSuccess) return e;
-  inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 1);
+  inflate_kernel<<<a.n_blocks, 32, 0, st>>>(a, 1);      // redo what they gave up on (status STATUS_RETRY)
   g_kernel_launches += 1;
   return cudaGetLastError();
 }

@@ -1,4 +1,4 @@
-// Shared pieces of the two BGZF inflate kernels (inflate.cu: warp-serial; inflate_par.cu: lane-parallel):
+// Shared pieces of the BGZF inflate kernels (inflate.cu: warp-serial; inflate_tok.cu: lane-parallel decode + resolve):
 // shared-memory / mbarrier / TMA primitives, canonical-Huffman table construction (RFC 1951 §3.2.2) and the
 // fused record-chain walker.  Nothing here is derived from zlib's source.
 #pragma once
@@ -470,7 +470,7 @@ struct Walker {
   }
 };
 
-// status written by inflate_par_kernel for a block it could not finish (malformed or unusual stream): the warp-serial
+// status written by the lane-parallel kernels (inflate_tok.cu) for a block they could not finish (malformed or unusual stream): the warp-serial
 // kernel then redoes the block and produces zlib's exact return code
 constexpr int STATUS_RETRY = 0x7fffff01;
 

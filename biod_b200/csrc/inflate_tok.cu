@@ -4,15 +4,22 @@
 // Replaces decompressBgzfBlock (bio/core/bgzf/block.d:127-216), i.e. libz's inflateInit2(-15) / inflate(Z_FINISH) /
 // inflateEnd on one <=64 KiB raw-DEFLATE payload.  The algorithm is RFC 1951; nothing here is derived from zlib.
 //
+// The lane-parallel idea: Huffman decoding is serial by nature — the start of a code is known only once the code before
+// it is decoded — but Huffman codes self-synchronise.  The bit stream of a DEFLATE block is cut into "super-chunks" of
+// 32 sub-sequences; lane L decodes sub-sequence L from its nominal first bit, which is almost never the start of a
+// code, yet after a few codes the lane is on the true code chain, and the bit where it crosses into sub-sequence L+1
+// is that sub-sequence's true start.  A second round from the true starts is the real decode; lanes whose predecessor
+// had not synchronised are repaired in further rounds (2.24 rounds per super-chunk of BAM data).
+//
 // Why two kernels.  Huffman decoding is one long dependency chain per warp: measured on the B200, a warp of the decode
 // loop issues one instruction every ~10 cycles whatever else the SM does, so the throughput of an SM is the number of
-// RESIDENT DECODING WARPS times that rate until the four schedulers saturate near 36-40 warps.  inflate_par.cu (one
-// warp per block doing everything: 11 KB of shared memory, 19 warps per SM, every code decoded 3.24 times) and
-// inflate_duo.cu (a decoder and a resolver warp per block, 16-18 blocks per SM, the resolver idle half of the time) both
-// ran at ~55-65 % of the issue slots for that reason.  Here
+// RESIDENT DECODING WARPS times that rate until the schedulers' integer pipes saturate.  Round 1's predecessors — one
+// warp per block doing everything (11 KB of shared memory, 19 warps per SM, every code decoded 3.24 times: 93 GB/s of
+// inflated bytes), then a decoder and a resolver warp per block in one kernel (16-18 blocks per SM, the resolver asleep
+// half of the time: 108 GB/s) — ran at 55-65 % of the issue slots for that reason (git history).  Here
 //   * inflate_decode_kernel (one warp per block) keeps only what decoding needs in shared memory — the TMA staging ring,
 //     the Huffman tables — ~7 KB, so 28 blocks are resident per SM.  It decodes "super-chunks" of 32 sub-sequences of
-//     SUB_BITS bits lane-parallel (see inflate_par.cu for the idea): round 1 only looks for the points where the
+//     SUB_BITS bits lane-parallel (above): round 1 only looks for the points where the
 //     sub-sequences synchronise (code lengths alone: the LUT entry carries the extra-bit count); from round 2 on a lane
 //     decodes from where its predecessor ended and RECORDS what it decodes as 16-bit tokens — literal / length /
 //     distance, one per loop trip — straight into the block's record stream in global memory (64 contiguous bytes per warp
@@ -61,7 +68,7 @@ constexpr uint32_t POM = POUT - 1;
 constexpr int OUT_BUDGET = POUT - 1536;
 constexpr int LANE_CAP = 512;                  // a lane stops taking codes once it has produced this many bytes ...
 constexpr int MLIST = BIODB_TOK_MLIST;         // matches one super-chunk may hold
-constexpr int TOK_TRIPS = DUO_TOK_TRIPS;       // ... or TOK_TRIPS - 1 tokens
+constexpr int TOK_TRIPS = TOK_MAX_TRIPS;       // ... or TOK_TRIPS - 1 tokens
 constexpr int LANE_MCAP = TOK_TRIPS / 2;       // (hence at most this many matches)
 constexpr int FLUSH_ALIGN = 128;
 constexpr int SUB_CAP = LIT_BITS >= 10 ? 320 : 352;
@@ -133,9 +140,9 @@ __device__ __forceinline__ uint32_t fetch32(uint32_t in_ring, uint32_t pos) {
 // Every lane with `active` decodes the codes that start in [t, limit) of its own sub-sequence; all 32 lanes of the
 // decoder warp must call this together.  One loop trip decodes one Huffman code per lane, whichever kind the lane needs
 // next — a literal/length code or the distance code of the length it met in the previous trip — and, when that code
-// was a plain literal (nine codes in ten of BAM data are), the literal/length code behind it as well: both come out of
-// the same 32-bit window (<= 15 + 10 + 5 bits), so the second one costs a table lookup but no second fetch, vote or
-// loop turn.  Everything is straight-line, select-based code, so that the lanes stay converged.
+// was a plain literal (nine codes in ten of BAM data are) or a distance that left room, the literal/length code behind
+// it as well: both come out of the same 32-bit window (<= 17 + 10 + 5 bits), so the second one costs a table lookup but
+// no second fetch, vote or loop turn.  Everything is straight-line, select-based code, so that the lanes stay converged.
 // RECORD = false: only the bit position moves (round 1: where do the sub-sequences synchronise?).
 // RECORD = true: the lane also counts the bytes and matches it produces and writes one row entry (two tokens) per trip.
 template <bool RECORD>
@@ -169,15 +176,17 @@ __device__ __forceinline__ void lane_decode(const DCtx& c, bool active, uint32_t
     const uint32_t kraw = (e >> 8) & 3;                            // kind of a literal/length entry (distance entries: 0)
     const uint32_t is_len = st | (kraw == K_LEN ? 1u : 0u);        // a distance code is handled like a length code
     const uint32_t eb = is_len ? ENTRY_EXTRA_BITS(e) : 0u;
-    // the code behind a plain literal: taken if it starts inside the lane's range and the first-level table knows it
+    // the literal/length code behind a plain literal or behind a distance: taken if the first code left room for it in
+    // the window (<= 17 bits used, 10 + 5 to come), it starts inside the lane's range and the first-level table knows it
     const uint32_t lit1 = (st | kraw) ? 0u : 1u;
-    const uint32_t bits2 = bits >> cl;
+    const uint32_t adv1 = cl + eb;
+    const uint32_t bits2 = bits >> adv1;
     const uint32_t e2 = lds16(c.lutl + ((bits2 << 1) & LITMSK));
     const uint32_t k2 = (e2 >> 8) & 3, cl2 = e2 >> 12;
-    uint32_t ok2 = lit1 & (k2 != K_SPECIAL ? 1u : 0u) & (pos + cl < lim ? 1u : 0u);
-    if (RECORD) ok2 &= (o + 1 < (uint32_t)LANE_CAP ? 1u : 0u);     // (the byte cap is checked between codes)
+    uint32_t ok2 = (lit1 | st) & (adv1 <= 17 ? 1u : 0u) & (k2 != K_SPECIAL ? 1u : 0u) & (pos + adv1 < lim ? 1u : 0u);
+    if (RECORD) ok2 &= (o + lit1 + (st ? len : 0u) < (uint32_t)LANE_CAP ? 1u : 0u);     // (the byte cap is checked between codes)
     const uint32_t eb2 = k2 == K_LEN ? ENTRY_EXTRA_BITS(e2) : 0u;
-    const uint32_t adv = cl + eb + (ok2 ? cl2 + eb2 : 0u);         // <= 15 + 10 + 5 bits of the 32
+    const uint32_t adv = adv1 + (ok2 ? cl2 + eb2 : 0u);
     pos += run ? adv : 0u;
     if (RECORD) {
       const uint32_t val = lds32(c.auxtab + (((st << 5) | (e & 31)) << 2)) + ((bits >> cl) & ~(0xffffffffu << eb));
@@ -223,7 +232,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 
 }  // namespace
 
-// diagnostics (biodb_debug_inflate_counters), same slots as inflate_par.cu's
+// diagnostics (biodb_debug_inflate_counters): the slots kernels.h lists
 __device__ unsigned long long g_tok_counters[8];
 
 // ===================================================================================== decode kernel ====
@@ -306,7 +315,7 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
   const uint32_t total_bits = staged * 8;
   ctx.total_bits = total_bits;
   int status = 0;
-  uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0;
+  uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0, n_lanes = 0;
   uint32_t produced = 0;    // bytes handed to the resolver so far
   uint32_t cur = 0;         // next free word of the arena
   uint32_t sub_bits = SUB_BITS;   // bits per lane of the next super-chunk (adapts to the stream, see below)
@@ -494,6 +503,11 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
         ++rounds;
       }
       n_rounds += rounds;
+      // A stream whose codes do not synchronise — fixed-length codes, e.g. a fixed-Huffman block of bytes below 144 —
+      // gains one lane per round: it is serial work, which the warp-serial kernel does three times cheaper than this
+      // loop.  Give such a block up early instead of grinding through it (and flooding the record stream with rows of
+      // lanes that are thrown away).
+      if (n_super >= 8 && n_lanes < 2 * n_rounds) { status = STATUS_RETRY; break; }
       // commit the longest prefix of lanes that fits the resolver's output ring and match list
       const uint32_t ncand = kstop < 32 ? kstop + 1 : vcut;
       const uint32_t inc_out = warp_incl_scan(out_, lane);
@@ -512,6 +526,7 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
         h[0] = REC_CHUNK; h[1] = (uint16_t)k; h[2] = (uint16_t)rows;
       }
       cur += REC_HEAD + REC_LANES + rows * ROW_WORDS;
+      n_lanes += k;
       // Streams that expand a lot (long matches, one-bit codes) fill the resolver's ring with fewer than 32 lanes: the
       // other lanes' decoding — and their rows of the record stream — would be thrown away super-chunk after super-chunk.
       // Shorter sub-sequences make 32 lanes fit again; they grow back when the output gets small.
@@ -593,13 +608,19 @@ __global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) 
   bool bad = false;
   int dstatus = 0;
   uint32_t cur = 0;
+  // The head of the next record and its lane words are requested while the current record is still being worked on: the
+  // record stream comes from HBM / L2, and three dependent loads per record would otherwise sit on the critical path.
+  uint2 head = __ldcg(reinterpret_cast<const uint2*>(arena));                        // {kind | lanes << 16, rows | ...}
+  uint32_t lane_word = __ldcg(reinterpret_cast<const uint32_t*>(arena + REC_HEAD) + lane);
   while (!bad) {
-    const uint32_t kind = __ldcg(arena + cur);
-    if (kind == REC_DONE) { dstatus = (int)__ldcg(arena + cur + 1); break; }
+    const uint32_t kind = head.x & 0xffff;
+    if (kind == REC_DONE) { dstatus = (int)(head.x >> 16); break; }
     if (kind == REC_STORED) {
       const uint32_t off = (uint32_t)__ldcg(arena + cur + 4) | ((uint32_t)__ldcg(arena + cur + 5) << 16);
       const uint32_t len = (uint32_t)__ldcg(arena + cur + 6) | ((uint32_t)__ldcg(arena + cur + 7) << 16);
       cur += REC_HEAD;
+      head = __ldcg(reinterpret_cast<const uint2*>(arena + cur));
+      lane_word = __ldcg(reinterpret_cast<const uint32_t*>(arena + cur + REC_HEAD) + lane);
       if (OPOS() + len > isize) { bad = true; break; }
       for (uint32_t p0 = 0; p0 < len; p0 += STORE_PIECE) {
         const uint32_t piece = len - p0 < (uint32_t)STORE_PIECE ? len - p0 : (uint32_t)STORE_PIECE;
@@ -613,10 +634,12 @@ __global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) 
     }
     if (kind != REC_CHUNK) { bad = true; break; }             // (cannot happen: the decode kernel wrote the stream)
     // ---- a super-chunk: k lanes of the decoder are committed -----------------------------------------------
-    const uint32_t k = __ldcg(arena + cur + 1), rows = __ldcg(arena + cur + 2);
-    const uint32_t mine = (uint32_t)lane < k ? __ldcg(reinterpret_cast<const uint32_t*>(arena + cur + REC_HEAD) + lane) : 0u;
+    const uint32_t k = head.x >> 16, rows = head.y & 0xffff;
+    const uint32_t mine = (uint32_t)lane < k ? lane_word : 0u;
     const uint32_t* tok = reinterpret_cast<const uint32_t*>(arena + cur + REC_HEAD + REC_LANES) + lane;
     cur += REC_HEAD + REC_LANES + rows * ROW_WORDS;
+    head = __ldcg(reinterpret_cast<const uint2*>(arena + cur));                      // (the arena ends with room for this)
+    lane_word = __ldcg(reinterpret_cast<const uint32_t*>(arena + cur + REC_HEAD) + lane);
     const uint32_t out_ = mine & 0xffff, nm_ = (mine >> 16) & 0xff, nt_ = mine >> 24;
     const uint32_t inc_out = warp_incl_scan(out_, lane);
     const uint32_t inc_nm = warp_incl_scan(nm_, lane);
@@ -629,10 +652,17 @@ __global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) 
       uint32_t oo = o + (inc_out - out_);               // ring-relative position of this lane's next byte
       uint32_t slot = inc_nm - nm_;
       uint32_t len = 0;
-      for (uint32_t t0 = 0; t0 < rows; t0 += 8) {
-        uint32_t tk[8];
+      // rows eight at a time, the next eight requested before the current ones are replayed
+      uint32_t tk[8], nx[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tk[j] = (t0 + j < nt_) ? __ldcs(tok + (size_t)(t0 + j) * 32) : (TOK_NONE | (TOK_NONE << 16));
+      for (int j = 0; j < 8; ++j) nx[j] = ((uint32_t)j < nt_) ? __ldcs(tok + (size_t)j * 32) : (TOK_NONE | (TOK_NONE << 16));
+      for (uint32_t t0 = 0; t0 < rows; t0 += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tk[j] = nx[j];
+        if (t0 + 8 < rows) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nx[j] = (t0 + 8 + j < nt_) ? __ldcs(tok + (size_t)(t0 + 8 + j) * 32) : (TOK_NONE | (TOK_NONE << 16));
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
 #pragma unroll
@@ -703,7 +733,8 @@ __global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) 
           const uint32_t sr = dr - dist;
           if (dist >= len) {
             if ((uint32_t)lane < len) sts8(ring + ((dr + lane) & POM), lds8(ring + ((sr + lane) & POM)));
-            for (uint32_t i = lane + 32; i < len; i += 32) sts8(ring + ((dr + i) & POM), lds8(ring + ((sr + i) & POM)));
+            if (len > 32)
+              for (uint32_t i = lane + 32; i < len; i += 32) sts8(ring + ((dr + i) & POM), lds8(ring + ((sr + i) & POM)));
           } else {
             uint32_t m = (uint32_t)lane % dist;
             const uint32_t step = 32u % dist;
@@ -754,7 +785,8 @@ cudaError_t inflate_tok_counters(unsigned long long* out8, int reset) {
   return e;
 }
 
-size_t inflate_tok_token_bytes(uint32_t n_blocks) { return (size_t)n_blocks * ARENA * sizeof(uint16_t); }
+// (+ 512 bytes: the resolver requests the head and lane words of the record behind the last one before it looks at it)
+size_t inflate_tok_token_bytes(uint32_t n_blocks) { return (size_t)n_blocks * ARENA * sizeof(uint16_t) + 512; }
 
 cudaError_t launch_inflate_tok(const InflateArgs& a, cudaStream_t st) {
   if (a.n_blocks == 0) return cudaSuccess;

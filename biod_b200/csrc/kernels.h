@@ -44,39 +44,31 @@ struct InflateArgs {
   int32_t* status;              // [n] 0 / Z_DATA_ERROR / Z_BUF_ERROR
   uint32_t n_blocks;
   WalkOut walk;
-  uint16_t* tok;                // device: token area of inflate_duo_kernel, inflate_token_bytes(n_blocks) bytes; nullptr =
-                                // launch_inflate allocates it for the call (stream-ordered)
+  uint16_t* tok;                // device: the blocks' record streams (inflate_tok.cu), inflate_token_bytes(n_blocks) bytes;
+                                // nullptr = launch_inflate allocates it for the call (stream-ordered)
 };
-// inflate_duo.cu / inflate_tok.cu: tokens (decode trips) one lane of the decoder warp may record per super-chunk
-constexpr int DUO_TOK_TRIPS = 128;
+// inflate_tok.cu: token rows (decode trips) one lane of the decode kernel may record per super-chunk
+constexpr int TOK_MAX_TRIPS = 128;
 // inflate_tok.cu: 16-bit words of one block's record stream (token rows + super-chunk headers).  A block of 64 KiB has
 // at most 65536 tokens; rows hold two tokens per lane and are padded to the longest lane: BAM data needs ~57 K words,
-// an all-literal block ~85 K.  A stream that outgrows the arena goes to the warp-serial kernel.
-constexpr uint32_t TOK_ARENA_WORDS = 144 * 1024;
+// an all-literal block ~85 K, a block dense in 3-byte matches ~130 K.  A stream that outgrows the arena goes to the
+// warp-serial kernel.
+constexpr uint32_t TOK_ARENA_WORDS = 160 * 1024;
+// inflate.cu: the kernels chosen by BIODB_INFLATE (default: the decode + resolve pair of inflate_tok.cu, then the
+// warp-serial kernel on the blocks they gave up on; "serial": the warp-serial kernel alone)
 cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st);
 // bytes of InflateArgs::tok for n_blocks blocks (0 when the selected kernel needs none)
 size_t inflate_token_bytes(uint32_t n_blocks);
-// inflate_duo.cu: the two-warp kernel alone; blocks it cannot finish get status STATUS_RETRY
-cudaError_t launch_inflate_duo(const InflateArgs& a, cudaStream_t st);
-size_t inflate_duo_token_bytes(uint32_t n_blocks);
-int inflate_duo_resident_blocks(int device);
-cudaError_t inflate_duo_counters(unsigned long long* out8, int reset);
-cudaError_t inflate_duo_cycles(unsigned long long* out16, int reset);
-int inflate_par_resident_blocks(int device);
-// inflate_tok.cu: decode kernel + resolve kernel; blocks they cannot finish get status STATUS_RETRY
+// inflate_tok.cu: decode kernel + resolve kernel; blocks they cannot finish get status STATUS_RETRY (inflate_common.cuh)
 cudaError_t launch_inflate_tok(const InflateArgs& a, cudaStream_t st);
 size_t inflate_tok_token_bytes(uint32_t n_blocks);
 int inflate_tok_resident_blocks(int device);
+// diagnostics since the last reset: [0] blocks given up (redone by the warp-serial kernel), [1] super-chunks,
+// [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks
 cudaError_t inflate_tok_counters(unsigned long long* out8, int reset);
-// inflate_par.cu: the lane-parallel kernel alone; blocks it cannot finish get status STATUS_RETRY (inflate_common.cuh)
-cudaError_t launch_inflate_par(const InflateArgs& a, cudaStream_t st);
-// diagnostics of the lane-parallel kernels since the last reset: [0] blocks given up (redone by the warp-serial kernel),
-// [1] super-chunks, [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks
-cudaError_t inflate_par_counters(unsigned long long* out8, int reset);
-// the same, summed over whichever kernels ran
 cudaError_t inflate_counters(unsigned long long* out8, int reset);
 size_t inflate_smem_bytes();
-// BGZF blocks (CTAs of inflate_par_kernel) resident on the whole device at once; 0 if unknown
+// BGZF blocks (CTAs of the decode kernel) resident on the whole device at once; 0 if unknown
 int inflate_resident_blocks(int device);
 
 // ---- crc32.cu ---------------------------------------------------------------------------------

@@ -941,16 +941,19 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       E = h[0];
       chi = std::min(chi, E);
     }
-    if (use_md) {
-      // the chain over the new reads: segments "positions [first, first+count) read dna(read)[offset...]".  A group that
-      // later batches continue is drained up to E, the position its columns stop at; a complete one is finished.
+    // use_md_tag: the chain over the new reads (host): segments "positions [first, first+count) read dna(read)[offset...]".
+    // A group that later batches continue is drained up to E, the position its columns stop at; a complete one is
+    // finished.  It needs nothing from the device beyond what the sync above brought, and the device needs its segments
+    // only for md_replay — so it runs while the entries kernel does (below), not in front of it.
+    auto run_md_chain = [&]() {
+      if (!use_md) return;
       pl->md_segs.clear();
       const int32_t* hm = pl->md_h.as<int32_t>();
       const uint64_t id0 = pl->first_index + (md_a0 - pl->n_carry_view);
       pl->md->admit_many(id0, ref, hm, hm + md_n, hm + 2 * md_n, md_n, &pl->md_segs);   // (end INT32_MIN = not a read of the pileup)
       if (trailing) pl->md->drain(E, &pl->md_segs);
       else pl->md->finish_reference(&pl->md_segs);
-    }
+    };
     s.clo = clo;
     s.chi = chi;
     // with skip_zero_coverage=false the column run of a continued group restarts exactly where the
@@ -976,6 +979,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     if (n_col > 0x7ff00000u) return pl->fail(BIODB_ERR_NOMEM, "too many pileup columns in one batch; lower blocks_per_batch");
     // ---- phase 2: columns ---------------------------------------------------------------------------------
     uint64_t n_entries = 0;
+    if (!n_col) run_md_chain();
     if (n_col) {
       if ((size_t)n_col + 8 > pl->col_cap) {
         size_t cap = (size_t)n_col + n_col / 4 + 1024;
@@ -1071,6 +1075,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         pileup_entries(v, n_col, s, c, o, st);
       }
       p.stage_end(&p.stats.pileup_ms);
+      run_md_chain();                          // (host work, while the entries kernel runs)
       if (use_md) {
         // reference_base: 'N' everywhere, then the providers' dna() replayed over the columns their segments cover
         static_assert(sizeof(MdSegment) == sizeof(MdSeg), "MdSegment is uploaded as MdSeg");

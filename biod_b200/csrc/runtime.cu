@@ -5,8 +5,13 @@
 #include "md_chain.h"
 #include "md_walk.h"
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cstdio>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 
@@ -68,9 +73,11 @@ static void set_error(biodb_error* e, int status, int zerr, uint64_t off, const 
 
 // BGZF member header — the checks and messages of fillBgzfBufferFromStream
 // (bio/core/bgzf/inputstream.d:54-199).  1 = block, 0 = clean end of stream, <0 = BgzfException.
-int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, BlockInfo* b, biodb_error* e) {
+// d[0 .. len) are the file's bytes from absolute offset `abs` on; pos is relative to d.
+int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, BlockInfo* b, biodb_error* e, uint64_t abs) {
   auto bad = [&](const std::string& why) {
-    set_error(e, BIODB_ERR_BGZF, 0, pos, "Error reading BGZF block starting from offset " + std::to_string(pos) + ": " + why);
+    set_error(e, BIODB_ERR_BGZF, 0, abs + pos,
+              "Error reading BGZF block starting from offset " + std::to_string(abs + pos) + ": " + why);
     return (int)BIODB_ERR_BGZF;
   };
   static const char* kShort = "stream error: not enough data in stream";
@@ -104,8 +111,8 @@ int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, BlockInfo* b
   if (cdata > 65536)
     return bad("compressed data size is more than 65536 bytes, which is not allowed by current BAM specification");
   if (cdata < 0 || q + (uint64_t)cdata + 8 > len) return bad(kShort);
-  b->coffset = pos;
-  b->payload = q;
+  b->coffset = abs + pos;
+  b->payload = abs + q;
   b->bsize = bsize;
   b->cdata_size = (uint32_t)cdata;
   b->crc32 = le32(d + q + cdata);
@@ -259,7 +266,7 @@ static void walk_headers(const biodb_reader* r, uint64_t stop_coffset, uint32_t 
   while (blocks.size() < max_blocks && !supplier_done && !pending.status) {
     if (next_coffset > stop_coffset || (next_coffset == stop_coffset && stop_uoffset == 0)) { supplier_done = true; break; }
     BlockInfo b;
-    int rc = parse_bgzf_header(r->file, r->flen, next_coffset, &b, &pending);
+    int rc = const_cast<biodb_reader*>(r)->header_at(next_coffset, &b, &pending);
     if (rc < 0) break;
     if (rc == 0 || b.isize == 0) { supplier_done = true; break; }     // EOF block ends the stream (inputstream.d:393-394)
     if (b.isize > 65536) {                                             // block.d:150-152
@@ -269,6 +276,19 @@ static void walk_headers(const biodb_reader* r, uint64_t stop_coffset, uint32_t 
     blocks.push_back(b);
     next_coffset = b.coffset + b.bsize + 1;
   }
+}
+
+const uint8_t* Pass::stage_host(uint64_t c0, uint64_t c1, cudaError_t* err) {
+  *err = cudaSuccess;
+  if (r->file) return r->file + c0;
+  // streamed file: into the slab that is not the source of the copy issued last (that copy has been waited for by the
+  // time a third range is staged: every batch synchronises its stream)
+  slab_cur ^= 1;
+  PinBuf& sl = h_slab[slab_cur];
+  const size_t n = (size_t)(c1 - c0);
+  if (n + 64 > sl.cap && (*err = sl.ensure(n + n / 8 + 65536)) != cudaSuccess) return nullptr;
+  if (!r->read_bytes(c0, n, sl.p, 4)) { *err = cudaErrorUnknown; return nullptr; }
+  return sl.as<uint8_t>();
 }
 
 biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
@@ -367,14 +387,21 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
       if ((size_t)(c1 - c0) + 256 > d_comp2[comp_cur].cap)
         CUDA_TRY(d_comp2[comp_cur].ensure((size_t)(c1 - c0) + 256, st, (size_t)(pf_c1 - c0)));
       if (pf_c1 < c1) {
-        CUDA_TRY(cudaMemcpyAsync(d_comp2[comp_cur].as<uint8_t>() + (pf_c1 - c0), r->file + pf_c1, (size_t)(c1 - pf_c1),
+        cudaError_t he;
+        const uint8_t* hp = stage_host(pf_c1, c1, &he);
+        if (!hp) return fail(he == cudaErrorUnknown ? BIODB_ERR_IO : BIODB_ERR_CUDA, 0, pf_c1, "cannot read the file");
+        CUDA_TRY(cudaMemcpyAsync(d_comp2[comp_cur].as<uint8_t>() + (pf_c1 - c0), hp, (size_t)(c1 - pf_c1),
                                  cudaMemcpyHostToDevice, st));
+        if (!r->file) CUDA_TRY(cudaStreamSynchronize(st));      // (a top-up of a streamed file: rare, and its slab is reused next)
         stats.h2d_bytes += c1 - pf_c1;
       }
     } else {
       CUDA_TRY(cudaStreamSynchronize(h2d_st));     // a stale prefetch must not land later
       CUDA_TRY(d_comp2[comp_cur].ensure((size_t)(c1 - c0) + 256, st));
-      CUDA_TRY(cudaMemcpyAsync(d_comp2[comp_cur].p, r->file + c0, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
+      cudaError_t he;
+      const uint8_t* hp = stage_host(c0, c1, &he);
+      if (!hp) return fail(he == cudaErrorUnknown ? BIODB_ERR_IO : BIODB_ERR_CUDA, 0, c0, "cannot read the file");
+      CUDA_TRY(cudaMemcpyAsync(d_comp2[comp_cur].p, hp, (size_t)(c1 - c0), cudaMemcpyHostToDevice, st));
       stats.h2d_bytes += c1 - c0;
     }
     pf_c1 = 0;
@@ -404,24 +431,6 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
     stage_begin();
     CUDA_TRY(launch_inflate(ia, st));
     stage_end(&stats.inflate_ms);
-    if (!resident) {
-      CUDA_TRY(cudaEventRecord(comp_free[comp_cur], st));
-      // prefetch what follows: the next batch starts at c1 and is about as long as this one
-      const uint64_t lim = std::min<uint64_t>(r->flen, stop_coffset == ~0ull ? r->flen : stop_coffset + 65536 + 64);
-      if (!last_batch && c1 < lim) {
-        const uint64_t want = std::min<uint64_t>(lim - c1, (c1 - c0) + (c1 - c0) / 32 + 65536);
-        const int nxt = comp_cur ^ 1;
-        // the other buffer was last read by the inflate kernel of the previous batch, which precedes this batch's
-        // kernels on the compute stream
-        CUDA_TRY(cudaStreamWaitEvent(h2d_st, comp_free[nxt], 0));
-        CUDA_TRY(d_comp2[nxt].ensure((size_t)want + (want >> 4) + 65536 + 256, h2d_st));
-        CUDA_TRY(cudaMemcpyAsync(d_comp2[nxt].p, r->file + c1, (size_t)want, cudaMemcpyHostToDevice, h2d_st));
-        CUDA_TRY(cudaEventRecord(pf_done, h2d_st));
-        stats.h2d_bytes += want;
-        pf_c0 = c1;
-        pf_c1 = c1 + want;
-      }
-    }
     stats.inflate_launches += 1;
     stats.n_blocks += nb;
     stats.compressed_bytes += c1 - c0;
@@ -435,6 +444,27 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
       walk_headers(r, stop_coffset, stop_uoffset, max_blocks, pre_blocks, pre_next_coffset, pre_supplier_done, pre_pending);
       pre_max = max_blocks;
       pre_valid = true;
+    }
+    if (!resident) {
+      CUDA_TRY(cudaEventRecord(comp_free[comp_cur], st));
+      // prefetch the next batch's bytes — its blocks are known by now — to the other device buffer on the copy stream
+      if (!last_batch && !pre_blocks.empty()) {
+        const uint64_t n0 = pre_blocks.front().coffset;
+        const uint64_t n1 = pre_blocks.back().coffset + pre_blocks.back().bsize + 1;
+        const int nxt = comp_cur ^ 1;
+        // the other buffer was last read by the inflate kernel of the previous batch, which precedes this batch's
+        // kernels on the compute stream
+        CUDA_TRY(cudaStreamWaitEvent(h2d_st, comp_free[nxt], 0));
+        CUDA_TRY(d_comp2[nxt].ensure((size_t)(n1 - n0) + (size_t)((n1 - n0) >> 4) + 65536 + 256, h2d_st));
+        cudaError_t he;
+        const uint8_t* hp = stage_host(n0, n1, &he);          // (a streamed file is read here, while the GPU inflates)
+        if (!hp) return fail(he == cudaErrorUnknown ? BIODB_ERR_IO : BIODB_ERR_CUDA, 0, n0, "cannot read the file");
+        CUDA_TRY(cudaMemcpyAsync(d_comp2[nxt].p, hp, (size_t)(n1 - n0), cudaMemcpyHostToDevice, h2d_st));
+        CUDA_TRY(cudaEventRecord(pf_done, h2d_st));
+        stats.h2d_bytes += n1 - n0;
+        pf_c0 = n0;
+        pf_c1 = n1;
+      }
     }
     const bool check_crc = r->opts.verify_crc != 0;
     if (check_crc) {
@@ -544,6 +574,51 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
 
 }  // namespace biodb
 
+int biodb_reader::header_at(uint64_t pos, biodb::BlockInfo* b, biodb_error* e) {
+  if (file) return parse_bgzf_header(file, flen, pos, b, e, 0);
+  // streamed: a BGZF member is at most 64 KiB of payload behind a header of at most 64 KiB of extra fields, so a window
+  // that reaches WIN_NEED bytes past pos (or the end of the file) shows parse_bgzf_header everything it may look at
+  constexpr uint64_t WIN_NEED = 192 * 1024, WIN_SIZE = 8ull << 20;
+  std::lock_guard<std::mutex> lk(hdr_mu);
+  if (pos >= flen) return 0;
+  const uint64_t need_end = std::min(flen, pos + WIN_NEED);
+  if (pos < hdr_off || need_end > hdr_off + hdr_win.size()) {
+    const uint64_t n = std::min(flen - pos, WIN_SIZE);
+    hdr_win.resize((size_t)n);
+    hdr_off = pos;
+    if (!read_bytes(pos, (size_t)n, hdr_win.data())) {
+      set_error(e, BIODB_ERR_IO, 0, pos, "read error at file offset " + std::to_string(pos));
+      hdr_win.clear();
+      return (int)BIODB_ERR_IO;
+    }
+  }
+  return parse_bgzf_header(hdr_win.data(), hdr_win.size(), pos - hdr_off, b, e, hdr_off);
+}
+
+bool biodb_reader::read_bytes(uint64_t off, size_t len, void* dst, int threads) const {
+  if (off > flen || len > flen - off) return false;
+  if (file) { memcpy(dst, file + off, len); return true; }
+  auto part = [&](uint64_t o, size_t n, uint8_t* d) -> bool {
+    while (n) {
+      const ssize_t got = pread(fd, d, n, (off_t)o);
+      if (got <= 0) return false;
+      o += (uint64_t)got; d += got; n -= (size_t)got;
+    }
+    return true;
+  };
+  if (threads <= 1 || len < (8u << 20)) return part(off, len, (uint8_t*)dst);
+  std::vector<std::thread> th;
+  std::vector<char> ok((size_t)threads, 1);
+  const size_t per = (len + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    const size_t a = std::min(len, (size_t)t * per), z = std::min(len, a + per);
+    th.emplace_back([&, t, a, z] { ok[(size_t)t] = part(off + a, z - a, (uint8_t*)dst + a) ? 1 : 0; });
+  }
+  for (auto& x : th) x.join();
+  for (char c : ok) if (!c) return false;
+  return true;
+}
+
 void biodb_reader::ensure_pinned(uint64_t lo, uint64_t hi) {
   if (opts.pin_input != 2 || !file || lo >= hi) return;
   const uint64_t page = 4096;
@@ -580,7 +655,7 @@ biodb_status biodb_reader::build_block_index() {
   biodb_error e{};
   while (true) {
     BlockInfo b;
-    int rc = parse_bgzf_header(file, flen, pos, &b, &e);
+    int rc = header_at(pos, &b, &e);
     if (rc < 0) { err = e; return (biodb_status)e.status; }
     if (rc == 0 || b.isize == 0) break;
     block_index.push_back(pos);
@@ -719,8 +794,19 @@ static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biod
     return s;
   }
   if (r->opts.resident_input && r->flen) {
-    if (r->d_file.ensure((size_t)r->flen + 256) != cudaSuccess ||
-        cudaMemcpy(r->d_file.p, r->file, (size_t)r->flen, cudaMemcpyHostToDevice) != cudaSuccess) {
+    bool ok = r->d_file.ensure((size_t)r->flen + 256) == cudaSuccess;
+    if (ok && r->file) ok = cudaMemcpy(r->d_file.p, r->file, (size_t)r->flen, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && !r->file) {                       // streamed file: through one pinned slab
+      biodb::PinBuf slab;
+      const size_t step = 256u << 20;
+      ok = slab.ensure(std::min<size_t>(step, (size_t)r->flen) + 64) == cudaSuccess;
+      for (uint64_t o = 0; ok && o < r->flen; o += step) {
+        const size_t n = (size_t)std::min<uint64_t>(step, r->flen - o);
+        ok = r->read_bytes(o, n, slab.p, 4) &&
+             cudaMemcpy(r->d_file.as<uint8_t>() + o, slab.p, n, cudaMemcpyHostToDevice) == cudaSuccess;
+      }
+    }
+    if (!ok) {
       set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "cannot make the compressed file resident in device memory");
       delete r;
       return BIODB_ERR_CUDA;
@@ -744,30 +830,18 @@ biodb_status biodb_open_memory(const void* data, size_t len, const biodb_options
 
 biodb_status biodb_open(const char* path, const biodb_options* opts, biodb_reader** out) {
   if (!path || !out) return BIODB_ERR_ARG;
-  FILE* f = fopen(path, "rb");
-  if (!f) {
+  const int fd = open(path, O_RDONLY | O_CLOEXEC);
+  struct stat sb;
+  if (fd < 0 || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) {
+    if (fd >= 0) close(fd);
     set_error(&g_open_error, BIODB_ERR_IO, 0, 0, std::string("cannot open ") + path);
     return BIODB_ERR_IO;
   }
-  fseek(f, 0, SEEK_END);
-  long sz = ftell(f);
-  fseek(f, 0, SEEK_SET);
+  // the file is streamed (runtime.h): nothing but the header blocks is read here, whatever its size (off_t is 64 bits)
   biodb_reader* r = new biodb_reader;
-  if (r->owned.ensure((size_t)sz + 64) != cudaSuccess) {
-    fclose(f);
-    delete r;
-    set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "cannot allocate pinned memory for the file (no CUDA device?)");
-    return BIODB_ERR_CUDA;
-  }
-  size_t got = fread(r->owned.p, 1, (size_t)sz, f);
-  fclose(f);
-  if (got != (size_t)sz) {
-    delete r;
-    set_error(&g_open_error, BIODB_ERR_IO, 0, 0, std::string("short read on ") + path);
-    return BIODB_ERR_IO;
-  }
-  r->file = r->owned.as<uint8_t>();
-  r->flen = (uint64_t)sz;
+  r->fd = fd;
+  r->file = nullptr;
+  r->flen = (uint64_t)sb.st_size;
   return finish_open(r, opts, out);
 }
 
@@ -780,6 +854,7 @@ void biodb_close(biodb_reader* r) {
   for (void* p : r->reads_pool) reads_destroy_pooled(p);
   if (r->registered) cudaHostUnregister((void*)r->file);
   for (const auto& g : r->pinned) cudaHostUnregister((void*)(uintptr_t)g.first);
+  if (r->fd >= 0) close(r->fd);
   delete r;
 }
 
@@ -1299,15 +1374,6 @@ biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset) {
   unsigned long long v[8];
   if (inflate_counters(v, reset) != cudaSuccess) return BIODB_ERR_CUDA;
   for (int i = 0; i < 8; ++i) out8[i] = v[i];
-  return BIODB_OK;
-}
-
-biodb_status biodb_debug_inflate_cycles(uint64_t* out16, int32_t reset) {
-  if (!out16) return BIODB_ERR_ARG;
-  cudaDeviceSynchronize();
-  unsigned long long v[16];
-  if (inflate_duo_cycles(v, reset) != cudaSuccess) return BIODB_ERR_CUDA;
-  for (int i = 0; i < 16; ++i) out16[i] = v[i];
   return BIODB_OK;
 }
 

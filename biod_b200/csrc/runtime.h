@@ -32,6 +32,9 @@ struct PinBuf {
   template <typename T> T* as() const { return (T*)p; }
 };
 
+struct BlockInfo;
+}
+namespace biodb {
 struct BlockInfo {      // BgzfBlock (bgzf/block.d:42-73)
   uint64_t coffset;     // start_offset
   uint64_t payload;     // file offset of the deflate payload
@@ -54,9 +57,20 @@ struct Seg {            // where a run of uncompressed bytes of the current slic
 struct biodb_reader {
   biodb_options opts;
   int device = 0;
-  const uint8_t* file = nullptr;
+  const uint8_t* file = nullptr;  // the whole file in host memory (biodb_open_memory), or nullptr: streamed from fd
   uint64_t flen = 0;
-  biodb::PinBuf owned;            // file contents when opened by path
+  // biodb_open(path): the file is STREAMED, as BioD's reader streams it through n_tasks x 128 KiB of read-ahead
+  // (bgzf/inputstream.d:467-478) — never held whole.  Block headers are parsed out of a small sliding window (hdr_win),
+  // the compressed bytes of a batch are pread into one of the pass's two pinned slabs while the GPU inflates the batch
+  // before (Pass::stage_host), so the pinned memory a reader needs is two batches, whatever the file's size.
+  int fd = -1;
+  std::vector<uint8_t> hdr_win;   // file bytes [hdr_off, hdr_off + hdr_win.size())
+  uint64_t hdr_off = 0;
+  std::mutex hdr_mu;
+  // parse the BGZF member header at file offset pos (in memory or through the window): as parse_bgzf_header
+  int header_at(uint64_t pos, biodb::BlockInfo* b, biodb_error* e);
+  // copy file bytes [off, off + len) to dst (host memory): memcpy or pread, on `threads` threads for large ranges
+  bool read_bytes(uint64_t off, size_t len, void* dst, int threads = 1) const;
   bool registered = false;        // the whole caller buffer is page-locked (options.pin_input == 1)
   // options.pin_input == 2: page-lock on demand, only the byte ranges passes really read (one shard of many GPUs' worth
   // of file must not make every process pin the whole file)
@@ -123,6 +137,10 @@ struct Pass {
   PinBuf h_status, h_result;
   // device
   DevBuf d_comp2[2], d_tab, d_status, d_u, d_carry_tail, d_ws, d_result, d_tok;
+  PinBuf h_slab[2];                 // streamed files: the compressed bytes of a batch on their way to the device
+  int slab_cur = 0;
+  // host address of file bytes [c0, c1) for a host->device copy: the caller's buffer, or (streamed file) the next slab
+  const uint8_t* stage_host(uint64_t c0, uint64_t c1, cudaError_t* err);
   // host->device prefetch of the next batch's compressed bytes (input not resident): while batch k is inflated out of
   // d_comp2[cur], the bytes that follow it in the file go to d_comp2[cur^1] on their own stream
   cudaStream_t h2d_st = nullptr;

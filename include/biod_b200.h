@@ -388,14 +388,10 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
                                const uint64_t* out_off, const uint32_t* isize, uint32_t n_blocks, uint8_t* out,
                                int32_t* status, uint32_t* crc, void* stream);
 
-/* Diagnostics of the lane-parallel inflate kernel since the last reset (synchronises the device):
- * out8[0] blocks it gave up on (redone by the warp-serial kernel: malformed or unusual streams), [1] super-chunks,
+/* Diagnostics of the lane-parallel inflate kernels since the last reset (synchronises the device):
+ * out8[0] blocks they gave up on (redone by the warp-serial kernel: malformed or unusual streams), [1] super-chunks,
  * [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks; [6..7] reserved. */
 biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset);
-/* Cycles per phase of the two-warp inflate kernel, summed over blocks — all zero unless the library was built with
- * -DBIODB_DUO_TIMING (a measurement build; csrc/inflate_duo.cu lists the 16 slots). */
-biodb_status biodb_debug_inflate_cycles(uint64_t* out16, int32_t reset);
-
 /* Host-only building blocks of the MD-tag reference bases (row N1 of the plan, pileup.d:522-654), exported so that the
  * CPU test suite can check them against the oracle.  Neither needs a GPU.
  * biodb_debug_md_chain (csrc/md_chain.h): which read's dna() string supplies PileupColumn.reference_base at which

@@ -484,3 +484,40 @@ def test_sharded_pileup_with_compact_columns():
     o = orc.Bam(data).decode()
     g = gpu_pileup_sharded(data, 3, halo_blocks=4, blocks_per_batch=8, compact_reads=True)
     assert_pileup_equal(g, o.pileup_columns())
+
+
+def test_streamed_file_equals_in_memory(tmp_path):
+    """biodb_open(path) streams the file (header window + two pinned slabs per pass, inputstream.d:467-478) instead of
+    holding it: the same records, offsets and columns as over the in-memory buffer — on a fixture, and on a file several
+    times the size of the header window whose batches cross the window many times."""
+    from biod_b200 import BamReader
+    from tools import bamgen
+    for name, data, bpb in (("ex1_header.bam", fixture_bytes("ex1_header.bam"), 2),
+                            ("synthetic", bamgen.generate(300_000, 2, True, level=1, threads=4).tobytes(), 97)):
+        path = tmp_path / (name + ".bam")
+        path.write_bytes(data)
+        a = BamReader(str(path), blocks_per_batch=bpb, want_offsets=True)
+        b = BamReader(data, blocks_per_batch=bpb, want_offsets=True)
+        assert a.header_text == b.header_text and a.reads_start_voffset == b.reads_start_voffset
+        n = 0
+        for x, y in zip(a.read_batches(copy=True), b.read_batches(copy=True)):
+            assert x.n == y.n and np.array_equal(x.pos, y.pos) and np.array_equal(x.end_pos, y.end_pos)
+            assert np.array_equal(x.start_voffset, y.start_voffset) and np.array_equal(x.cigar, y.cigar)
+            assert x.data[:int(x.rec_off[-1])].tobytes() == y.data[:int(y.rec_off[-1])].tobytes()
+            n += x.n
+        assert n == (3270 if name == "ex1_header.bam" else 300_000)
+        ca = [(c.n_columns, c.n_entries, int(c.position[0]), int(c.base.astype(np.uint64).sum())) for c in a.column_batches(False)]
+        cb = [(c.n_columns, c.n_entries, int(c.position[0]), int(c.base.astype(np.uint64).sum())) for c in b.column_batches(False)]
+        assert ca == cb and ca
+        # shards read the file through the same window
+        sa = [(s, c.n_columns, c.n_entries) for s, c in a.sharded_column_batches(3)]
+        assert sum(x[1] for x in sa) == sum(x[0] for x in ca)
+    # a truncated file surfaces as it does in memory: the records before the cut, then the error
+    data = fixture_bytes("ex1_header.bam")
+    path = tmp_path / "cut.bam"
+    path.write_bytes(data[:len(data) // 2])
+    got = 0
+    with pytest.raises(Exception):
+        for _ in BamReader(str(path), blocks_per_batch=2).reads():
+            got += 1
+    assert 0 < got < 3270

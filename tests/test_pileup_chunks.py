@@ -135,7 +135,8 @@ def test_chunks_match_the_oracle(name, block_size, use_md):
     if name != "mg1655_chunk.bam":
         assert np.array_equal(got_pos, seq.col_pos) and np.array_equal(got_ref, seq.col_ref)
     # iterating a chunk yields PileupColumn objects, like BioD's range of pileups
-    col = next(iter(chunks[0]))
+    first = next(ch for ch in chunks if ch.start_position < ch.end_position)
+    col = next(iter(first))
     assert col.position == int(seq.col_pos[0]) and col.coverage == int(seq.col_off[1])
 
 

@@ -1,5 +1,5 @@
 """Design aid (not product, not oracle): token statistics of the DEFLATE streams in a BGZF file and a simulation of the
-lane-parallel speculative decode used by inflate_par_kernel (how many chain-repair rounds a 32-lane super-chunk needs
+lane-parallel speculative decode used by inflate_decode_kernel (inflate_tok.cu) (how many chain-repair rounds a 32-lane super-chunk needs
 for a given sub-sequence size).  RFC 1951 decoder written from the RFC."""
 import struct
 import sys
