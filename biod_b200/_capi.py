@@ -191,6 +191,8 @@ def lib():
     L.biodb_writer_end.argtypes = [vp]
     L.biodb_debug_deflate_block.restype = C.c_int64
     L.biodb_debug_deflate_block.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_int32]
+    L.biodb_debug_deflate_stats.restype = C.c_int
+    L.biodb_debug_deflate_stats.argtypes = [C.c_int32, vp]
     L.biodb_debug_md_dna.restype = C.c_int64
     L.biodb_debug_md_dna.argtypes = [vp, C.c_int64, vp, C.c_uint64]
     L.biodb_dev_scan_workspace_bytes.restype = C.c_size_t
@@ -212,6 +214,6 @@ EXPORTS = [
     "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",
     "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",
-    "biodb_debug_deflate_block", "biodb_writer_begin", "biodb_writer_header", "biodb_writer_records", "biodb_writer_flush",
+    "biodb_debug_deflate_block", "biodb_debug_deflate_stats", "biodb_writer_begin", "biodb_writer_header", "biodb_writer_records", "biodb_writer_flush",
     "biodb_writer_finish", "biodb_writer_layout", "biodb_writer_index", "biodb_writer_debug_set_output", "biodb_writer_error", "biodb_writer_end",
 ]

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
   const uint32_t total_bits = staged * 8;
   ctx.total_bits = total_bits;
   int status = 0;
-  uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0, n_lanes = 0;
+  uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0, n_stuck = 0;
   uint32_t produced = 0;    // bytes handed to the resolver so far
   uint32_t cur = 0;         // next free word of the arena
   uint32_t sub_bits = SUB_BITS;   // bits per lane of the next super-chunk (adapts to the stream, see below)
@@ -503,11 +503,6 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
         ++rounds;
       }
       n_rounds += rounds;
-      // A stream whose codes do not synchronise — fixed-length codes, e.g. a fixed-Huffman block of bytes below 144 —
-      // gains one lane per round: it is serial work, which the warp-serial kernel does three times cheaper than this
-      // loop.  Give such a block up early instead of grinding through it (and flooding the record stream with rows of
-      // lanes that are thrown away).
-      if (n_super >= 8 && n_lanes < 2 * n_rounds) { status = STATUS_RETRY; break; }
       // commit the longest prefix of lanes that fits the resolver's output ring and match list
       const uint32_t ncand = kstop < 32 ? kstop + 1 : vcut;
       const uint32_t inc_out = warp_incl_scan(out_, lane);
@@ -519,6 +514,18 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
       const uint32_t newpos = __shfl_sync(0xffffffffu, e_, kl);
       const uint32_t stop_flag = (kl == kstop) ? __shfl_sync(0xffffffffu, fl_, kl) : 0;
       if (stop_flag == F_ERR || stop_flag == F_INEND || produced + chunk_out > isize) { status = STATUS_RETRY; break; }
+      // A stream whose codes do not synchronise — fixed-length codes, e.g. a fixed-Huffman block of bytes below 144 —
+      // gains one lane per round: the rounds run out with a consistent prefix of a few lanes and a few dozen bytes.  That
+      // is serial work, which the warp-serial kernel does three times cheaper than this loop; give such a block up
+      // after sixteen super-chunks in a row that ended that way, instead of grinding through it and flooding the record
+      // stream with rows of lanes that are thrown away.  (Streams of long matches do not synchronise either — a lane
+      // that starts on a distance code reads it as a length code for ever — but there the resolver's ring is what limits
+      // a commit, a few lanes fill it, and nothing is lost: those never count here.)
+      if (vcut <= 8 && k == ncand && chunk_out < 512) {
+        if (++n_stuck >= 16) { status = STATUS_RETRY; break; }
+      } else {
+        n_stuck = 0;
+      }
       const uint32_t rows = __reduce_max_sync(0xffffffffu, (uint32_t)lane < k ? nt_ : 0u);
       reinterpret_cast<uint32_t*>(arena + cur + REC_HEAD)[lane] = (uint32_t)lane < k ? (out_ | (nm_ << 16) | (nt_ << 24)) : 0u;
       if (lane == 0) {
@@ -526,7 +533,6 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
         h[0] = REC_CHUNK; h[1] = (uint16_t)k; h[2] = (uint16_t)rows;
       }
       cur += REC_HEAD + REC_LANES + rows * ROW_WORDS;
-      n_lanes += k;
       // Streams that expand a lot (long matches, one-bit codes) fill the resolver's ring with fewer than 32 lanes: the
       // other lanes' decoding — and their rows of the record stream — would be thrown away super-chunk after super-chunk.
       // Shorter sub-sequences make 32 lanes fit again; they grow back when the output gets small.

@@ -361,9 +361,14 @@ biodb_status biodb_writer_index(biodb_writer* w, const uint8_t** data, size_t* l
 biodb_status biodb_writer_debug_set_output(biodb_writer* w, const uint8_t* data, size_t len);
 const char* biodb_writer_error(const biodb_writer* w);
 void biodb_writer_end(biodb_writer* w);
-/* Host-only test hook: the device's DEFLATE encoder (csrc/deflate_enc.h) compiled for the CPU; raw DEFLATE of one
+/* Host-only test hook: the device's DEFLATE encoder as plain host loops (csrc/deflate_enc.h: deflate_block_host — the
+ * same windows, candidates, tokens and codes as the warp of deflate_warp_kernel, so the same bytes); raw DEFLATE of one
  * chunk of at most 65535 bytes.  Returns the size, 0 if cap is too small. */
 int64_t biodb_debug_deflate_block(const uint8_t* in, uint32_t n, uint8_t* out, uint32_t cap, int32_t level);
+/* Statistics of the last biodb_bgzf_compress / biodb_writer_finish on `device` (-1: the current one): out[0] =
+ * microseconds the encoder kernel of the first slab (at most 2048 blocks) took, out[1] = CTAs of its persistent grid,
+ * out[2] = calls so far, out[3] = 0. */
+biodb_status biodb_debug_deflate_stats(int32_t device, uint64_t* out);
 
 /* ---- measurement ---------------------------------------------------------------------------------------- */
 typedef struct biodb_stats {

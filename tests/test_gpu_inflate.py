@@ -151,10 +151,12 @@ def test_valid_streams_of_every_shape_match_zlib():
     # that are serial by nature or pathological, and still returns the right bytes (checked above):
     #  * Z_FIXED over bytes below 144: every code is 8 bits long, sub-sequences never synchronise (inflate_tok.cu gives
     #    such a block up after a few super-chunks);
-    #  * memLevel 1: hundreds of DEFLATE blocks of ~128 symbols per BGZF block, one record of the token stream each.
+    #  * memLevel 1: hundreds of DEFLATE blocks of ~128 symbols per BGZF block, one record of the token stream each;
+    #  * codes of (nearly) one length for another reason: 30 000 random bytes in front of their repeats ("far_repeat":
+    #    256 codes of 8 bits), a random string over four letters ("acgt": four codes of 2 bits).
     if cnt[0] != 0:
         gave_up = [names[i] for i in range(len(payloads)) if dev_inflate([payloads[i]], [isizes[i]])[3][0]]
-        unexpected = [g for g in gave_up if g[2] != zlib.Z_FIXED and g[3] != 1]
+        unexpected = [g for g in gave_up if g[2] != zlib.Z_FIXED and g[3] != 1 and g[0] not in ("far_repeat", "acgt")]
         assert not unexpected, f"streams that went to the fallback kernel: {unexpected}"
     assert cnt[1] > 0 and cnt[5] >= len(payloads), cnt
 
@@ -207,20 +209,28 @@ def test_fast_path_takes_all_fixture_blocks():
     L = _capi.lib()
     cnt = (C.c_uint64 * 8)()
     assert L.biodb_debug_inflate_counters(cnt, 1) == 0
-    n_expected = 0
+    gave_up, supers, rounds = {}, 0, 0
+
+    def tally(what):
+        nonlocal supers, rounds
+        assert L.biodb_debug_inflate_counters(cnt, 1) == 0
+        if cnt[0]:
+            gave_up[what] = int(cnt[0])
+        supers += int(cnt[1])
+        rounds += int(cnt[2])
     for name in ["ex1_header.bam", "bins.bam", "tags.bam", "b7_295_chunk.bam", "mg1655_chunk.bam", "ion_20_chunk.bam",
                  "illu_20_chunk.bam", "long_header.bam"]:
         rd, g, raws, err = gpu_records(fixture_bytes(name))
         assert err is None
+        tally(name)
     for mixed, level, straddle in [(False, -1, False), (True, -1, False), (True, 1, True), (False, 9, False), (False, 0, False)]:
         data = bamgen.generate(60000, 1, mixed, level, bamgen.SEED_BASE + 2, straddle=straddle)
         rd, g, raws, err = gpu_records(data.tobytes())
         assert err is None
-        n_expected += 60000
         assert len(raws) == 60000
-    assert L.biodb_debug_inflate_counters(cnt, 1) == 0
-    assert cnt[0] == 0, list(cnt)
-    assert cnt[1] > 0 and cnt[2] >= cnt[1], list(cnt)
+        tally(("bamgen", mixed, level, straddle))
+    assert not gave_up, gave_up
+    assert supers > 0 and rounds >= supers
 
 
 def _random_payload(rng):

@@ -87,3 +87,48 @@ def test_bam_written_by_the_gpu_reads_back(name):
             p = int(b.rec_off[i]) + 4
             raws.append(b.data[p:p + int(b.block_size[i])].tobytes())
     assert raws == [o.record_bytes(i).tobytes() for i in range(o.n_records)]
+
+
+def host_block(chunk, level=-1):
+    """The host's statement of the encoder (deflate_enc.h: deflate_block_host) for one chunk."""
+    from biod_b200 import _capi
+    L = _capi.lib()
+    a = np.frombuffer(bytes(chunk) + b"\0", dtype=np.uint8)
+    out = np.zeros(len(chunk) + 64, dtype=np.uint8)
+    n = int(L.biodb_debug_deflate_block(a.ctypes.data, len(chunk), out.ctypes.data, out.size, level))
+    assert n > 0
+    return out[:n].tobytes()
+
+
+def test_device_bytes_equal_the_host_statement():
+    # the warp's parse, code construction and bit packing against the plain loops the CPU suite checks with zlib: the
+    # payload of every block, byte for byte
+    from biod_b200 import bgzf_compress
+    rng = np.random.default_rng(11)
+    u = bytes(orc.Bam(fixture_bytes("ex1_header.bam")).decode().udata)
+    text = (b"the quick brown fox jumps over the lazy dog " * 3000)
+    streams = {
+        "bam": u[:6 * 0xFF00 + 1234],
+        "zeros": bytes(2 * 0xFF00 + 17),
+        "random": rng.integers(0, 256, 0xFF00 + 999, dtype=np.uint8).tobytes(),
+        "acgt": bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 2 * 0xFF00)),
+        "text": text,
+        "period3": b"abc" * 40000,
+        "long_then_noise": b"x" * 70000 + rng.integers(0, 256, 5000, dtype=np.uint8).tobytes() + b"y" * 300,
+        "far": (lambda unit: unit + unit + unit[:5000])(rng.integers(0, 256, 30000, dtype=np.uint8).tobytes()),
+        "tiny": b"abcdefg",
+        "short": b"hello hello hello hello",
+        "hi_bytes": bytes(rng.integers(144, 256, 5000, dtype=np.uint8)),
+    }
+    for name, data in streams.items():
+        for level in (-1, 0):
+            s = bgzf_compress(data, level, eof=False)
+            back, sizes = bgzf_read(s)
+            assert back == data, name
+            p = k = 0
+            while p < len(s):
+                bsize = struct.unpack_from("<H", s, p + 16)[0] + 1
+                chunk = data[k * 0xFF00:(k + 1) * 0xFF00]
+                assert s[p + 18:p + bsize - 8] == host_block(chunk, level), (name, level, k)
+                p += bsize
+                k += 1

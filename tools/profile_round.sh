@@ -3,9 +3,9 @@
 # one `--set full` capture of the three hot kernels.  Outputs land in gpurun_out/; tools/summarize_profiles.py turns
 # them into the CSV/JSON summaries committed under profiles/.
 set -x
-R=${1:-r1}
+R=${1:-r2}
 mkdir -p gpurun_out
-CMD="python bench.py --reads 4000000 --steps 1 --warmup 1 --no-e2e --no-cpu"
+CMD="python bench.py --reads 8000000 --steps 1 --warmup 1 --no-e2e --no-cpu --no-extra"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_$R.csv $CMD > gpurun_out/launches_$R.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"inflate_decode_kernel|inflate_resolve_kernel|entries_kernel|entries_tile_kernel|scan_extract_kernel" -s 3 -c 3 -o gpurun_out/prof_$R $CMD > gpurun_out/prof_$R.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"inflate_decode_kernel|inflate_resolve_kernel|entries_kernel|entries_tile_kernel|scan_extract_kernel" -s 10 -c 10 -o gpurun_out/prof_$R $CMD > gpurun_out/prof_$R.log 2>&1
 ls -la gpurun_out

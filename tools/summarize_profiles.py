@@ -6,7 +6,7 @@ import subprocess
 import sys
 from collections import defaultdict
 
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
 KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -48,6 +48,12 @@ for r in rows[2:]:
     t = sum(st.values()) or 1
     d["stall_share"] = {k: round(v / t, 3) for k, v in sorted(st.items(), key=lambda x: -x[1])[:6]}
     out.append(d)
+# the inflate stage is the decode + resolve pair: flag the largest launch of each (bench.py sums their DRAM bytes per
+# BGZF block for roofline.traffic)
+for name in ("inflate_decode_kernel", "inflate_resolve_kernel"):
+    best = max((d for d in out if d["kernel"].endswith(name)), key=lambda d: float(d["launch__grid_size"].split()[0]), default=None)
+    if best is not None:
+        best["dominant_inflate"] = True
 json.dump(out, open(f"profiles/ncu_full_{R}_summary.json", "w"), indent=1)
 print(open(f"profiles/launches_{R}_summary.csv").read())
 print(json.dumps(out, indent=1)[:3000])
