@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
   ctx.total_bits = total_bits;
   int status = 0;
   uint32_t n_super = 0, n_rounds = 0, n_dblocks = 0, n_stuck = 0;
+  int why = 0;                      // 1: the arena ran out, 2: the stream does not synchronise (counters 6 / 7)
   uint32_t produced = 0;    // bytes handed to the resolver so far
   uint32_t cur = 0;         // next free word of the arena
   uint32_t sub_bits = SUB_BITS;   // bits per lane of the next super-chunk (adapts to the stream, see below)
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
     // ---- the codes of the block, one super-chunk of 32 sub-sequences at a time -------------------------------
     bool eob = false;
     while (!eob) {
-      if (cur + CHUNK_MAX + REC_HEAD > ARENA) { status = STATUS_RETRY; break; }   // the record stream outgrew its arena
+      if (cur + CHUNK_MAX + REC_HEAD > ARENA) { status = STATUS_RETRY; why = 1; break; }   // the record stream outgrew its arena
       const uint32_t base = pos;
       ensure_input(base >> 3, (base >> 3) + SUPER_BYTES + 24);
       const uint32_t lim = base + (uint32_t)(lane + 1) * sub_bits;
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
       // that starts on a distance code reads it as a length code for ever — but there the resolver's ring is what limits
       // a commit, a few lanes fill it, and nothing is lost: those never count here.)
       if (vcut <= 8 && k == ncand && chunk_out < 512) {
-        if (++n_stuck >= 16) { status = STATUS_RETRY; break; }
+        if (++n_stuck >= 16) { status = STATUS_RETRY; why = 2; break; }
       } else {
         n_stuck = 0;
       }
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
     atomicAdd(&g_tok_counters[1], (unsigned long long)n_super);
     atomicAdd(&g_tok_counters[2], (unsigned long long)n_rounds);
     atomicAdd(&g_tok_counters[5], (unsigned long long)n_dblocks);
+    if (why) atomicAdd(&g_tok_counters[5 + why], 1ull);
   }
 }
 

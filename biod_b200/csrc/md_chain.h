@@ -91,21 +91,45 @@ class MdChain {
         int64_t at = cur_;                 // position of the last read taken
         bool hz = adm_had_zero_;
         const size_t k0 = k;
-        for (; k < n; ++k) {
-          const int32_t e = end[k];
-          if (e == INT32_MIN) continue;
-          const int64_t p = pos[k];
-          if (p > last_safe) break;
-          if (p != at) {
-            if (skip_zero_ && max_end_ < p) break;                   // the sweep jumps: the general path handles it
-            hz = max_end_ < p;
-            at = p;
+        // The stretch in one sweep: its reads (positions up to last_safe) and the largest end among them.  If the reads
+        // admitted so far already reach past the stretch's last position and that position lies inside the chunk's
+        // reference span, neither a jump of the sweep nor the rule of pileup.d:579 can come up in it, and all the
+        // stretch does to the state is: the pending provider becomes the first read with the largest end, if that end
+        // beats the chunk's and the pending provider's.
+        size_t j = k;
+        int32_t m = INT32_MIN;
+        for (; j < n && pos[j] <= last_safe; ++j) m = end[j] > m ? end[j] : m;
+        size_t jl = j;                     // one past the last read of the stretch that is a read of the pileup
+        while (jl > k && end[jl - 1] == INT32_MIN) --jl;
+        if (jl > k && max_end_ >= pos[jl - 1] && (uint32_t)pos[jl - 1] <= chunk_end_) {
+          if ((uint32_t)m > chunk_end_) {
+            if (!has_provider_ || m > (int32_t)provider_.end) {
+              size_t a = k;
+              while (end[a] != m) ++a;
+              provider_ = Rd{id0 + a, pos[a], m, len[a]};
+            }
+            has_provider_ = true;
           }
-          if ((uint32_t)p > chunk_end_) break;                       // (the rare rule of pileup.d:579: general path)
-          if ((uint32_t)e > chunk_end_ && (!has_provider_ || e > (int32_t)provider_.end))
-            provider_ = Rd{id0 + k, p, e, len[k]};
-          if ((uint32_t)e > chunk_end_) has_provider_ = true;
-          if (e > max_end_) max_end_ = e;
+          if (m > max_end_) max_end_ = m;
+          if (pos[jl - 1] != at) { hz = false; at = pos[jl - 1]; }
+          k = j;
+        } else {
+          for (; k < n; ++k) {
+            const int32_t e = end[k];
+            if (e == INT32_MIN) continue;
+            const int64_t p = pos[k];
+            if (p > last_safe) break;
+            if (p != at) {
+              if (skip_zero_ && max_end_ < p) break;                   // the sweep jumps: the general path handles it
+              hz = max_end_ < p;
+              at = p;
+            }
+            if ((uint32_t)p > chunk_end_) break;                       // (the rare rule of pileup.d:579: general path)
+            if ((uint32_t)e > chunk_end_ && (!has_provider_ || e > (int32_t)provider_.end))
+              provider_ = Rd{id0 + k, p, e, len[k]};
+            if ((uint32_t)e > chunk_end_) has_provider_ = true;
+            if (e > max_end_) max_end_ = e;
+          }
         }
         if (at != cur_ || k != k0) {
           ci_ += at - cur_;

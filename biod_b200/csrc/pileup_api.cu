@@ -943,17 +943,24 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     }
     // use_md_tag: the chain over the new reads (host): segments "positions [first, first+count) read dna(read)[offset...]".
     // A group that later batches continue is drained up to E, the position its columns stop at; a complete one is
-    // finished.  It needs nothing from the device beyond what the sync above brought, and the device needs its segments
-    // only for md_replay — so it runs while the entries kernel does (below), not in front of it.
-    auto run_md_chain = [&]() {
-      if (!use_md) return;
+    // finished.  It needs nothing from the device beyond what the syncs above brought, and the device needs its segments
+    // only for md_replay — so it runs on a thread of its own from here on, beside the kernels that build the columns
+    // (and, in maq_mode, the likelihood kernel), and is joined where md_replay is launched.
+    struct MdThread {
+      std::thread t;
+      void join() { if (t.joinable()) t.join(); }
+      ~MdThread() { join(); }
+    } md_thread;
+    if (use_md) {
       pl->md_segs.clear();
       const int32_t* hm = pl->md_h.as<int32_t>();
       const uint64_t id0 = pl->first_index + (md_a0 - pl->n_carry_view);
-      pl->md->admit_many(id0, ref, hm, hm + md_n, hm + 2 * md_n, md_n, &pl->md_segs);   // (end INT32_MIN = not a read of the pileup)
-      if (trailing) pl->md->drain(E, &pl->md_segs);
-      else pl->md->finish_reference(&pl->md_segs);
-    };
+      md_thread.t = std::thread([pl, hm, id0, ref, md_n, trailing, E]() {
+        pl->md->admit_many(id0, ref, hm, hm + md_n, hm + 2 * md_n, md_n, &pl->md_segs);   // (end INT32_MIN = not a read of the pileup)
+        if (trailing) pl->md->drain(E, &pl->md_segs);
+        else pl->md->finish_reference(&pl->md_segs);
+      });
+    }
     s.clo = clo;
     s.chi = chi;
     // with skip_zero_coverage=false the column run of a continued group restarts exactly where the
@@ -979,7 +986,7 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
     if (n_col > 0x7ff00000u) return pl->fail(BIODB_ERR_NOMEM, "too many pileup columns in one batch; lower blocks_per_batch");
     // ---- phase 2: columns ---------------------------------------------------------------------------------
     uint64_t n_entries = 0;
-    if (!n_col) run_md_chain();
+    if (!n_col) md_thread.join();
     if (n_col) {
       if ((size_t)n_col + 8 > pl->col_cap) {
         size_t cap = (size_t)n_col + n_col / 4 + 1024;
@@ -1075,7 +1082,21 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
         pileup_entries(v, n_col, s, c, o, st);
       }
       p.stage_end(&p.stats.pileup_ms);
-      run_md_chain();                          // (host work, while the entries kernel runs)
+      MaqColumns mq{nullptr, nullptr, nullptr, nullptr, nullptr};
+      if (maq) {
+        // genotype likelihoods of every column (maq.cu): they do not depend on the reference bases, so they go first
+        PL_TRY(os.dm[0].ensure(os.col_cap, st));
+        PL_TRY(os.dm[1].ensure(os.col_cap, st));
+        PL_TRY(os.dm[2].ensure(os.col_cap * 4, st));
+        PL_TRY(os.dm[3].ensure(os.col_cap * 4, st));
+        PL_TRY(os.dm[4].ensure(os.col_cap * 2, st));
+        mq = MaqColumns{os.dm[0].as<uint8_t>(), os.dm[1].as<uint8_t>(), os.dm[2].as<float>(), os.dm[3].as<float>(),
+                        os.dm[4].as<uint16_t>()};
+        p.stage_begin();
+        maq_columns(o.col_off, o.base, o.qual, n_col, pl->maq_tab, mq, st);
+        p.stage_end(&p.stats.pileup_ms);
+      }
+      md_thread.join();                        // the chain's segments are needed from here on
       if (use_md) {
         // reference_base: 'N' everywhere, then the providers' dna() replayed over the columns their segments cover
         static_assert(sizeof(MdSegment) == sizeof(MdSeg), "MdSegment is uploaded as MdSeg");
@@ -1100,21 +1121,12 @@ static biodb_status produce(biodb_pileup* pl, OutSet& os, biodb_column_batch* co
       os.n_runs = 0;
       os.n_special = 0;
       os.n_calls = 0;
-      MaqColumns mq{nullptr, nullptr, nullptr, nullptr, nullptr};
       if (maq) {
-        // genotype likelihoods of every column (maq.cu), then findSNPs' filter as a compaction
-        PL_TRY(os.dm[0].ensure(os.col_cap, st));
-        PL_TRY(os.dm[1].ensure(os.col_cap, st));
-        PL_TRY(os.dm[2].ensure(os.col_cap * 4, st));
-        PL_TRY(os.dm[3].ensure(os.col_cap * 4, st));
-        PL_TRY(os.dm[4].ensure(os.col_cap * 2, st));
-        mq = MaqColumns{os.dm[0].as<uint8_t>(), os.dm[1].as<uint8_t>(), os.dm[2].as<float>(), os.dm[3].as<float>(),
-                        os.dm[4].as<uint16_t>()};
+        // findSNPs' filter as a compaction
         uint32_t* flag = pl->cs[1].as<uint32_t>();          // the candidate windows (lo / hi) are dead after the entries kernel
         uint32_t* incl = pl->cs[2].as<uint32_t>();
         const uint8_t* refb = use_md ? os.d[20].as<uint8_t>() : nullptr;
         p.stage_begin();
-        maq_columns(o.col_off, o.base, o.qual, n_col, pl->maq_tab, mq, st);
         maq_call_flags(mq, refb, n_col, pl->maq.minimum_call_quality, flag, st);
         device_scan<true>(flag, incl, (uint64_t)n_col, s.tmp_u32b, OpAdd(), 0u, st);
         p.stage_end(&p.stats.pileup_ms);

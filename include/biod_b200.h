@@ -395,7 +395,8 @@ biodb_status biodb_dev_inflate(const uint8_t* comp, const uint64_t* payload_off,
 
 /* Diagnostics of the lane-parallel inflate kernels since the last reset (synchronises the device):
  * out8[0] blocks they gave up on (redone by the warp-serial kernel: malformed or unusual streams), [1] super-chunks,
- * [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks; [6..7] reserved. */
+ * [2] decode rounds, [3] matches read back from L2, [4] matches, [5] DEFLATE blocks; of the blocks given up: [6] those
+ * whose record stream outgrew its arena, [7] those whose sub-sequences never synchronised (codes of one length). */
 biodb_status biodb_debug_inflate_counters(uint64_t* out8, int32_t reset);
 /* Host-only building blocks of the MD-tag reference bases (row N1 of the plan, pileup.d:522-654), exported so that the
  * CPU test suite can check them against the oracle.  Neither needs a GPU.

@@ -215,7 +215,7 @@ def test_fast_path_takes_all_fixture_blocks():
         nonlocal supers, rounds
         assert L.biodb_debug_inflate_counters(cnt, 1) == 0
         if cnt[0]:
-            gave_up[what] = int(cnt[0])
+            gave_up[what] = (int(cnt[0]), "arena", int(cnt[6]), "stuck", int(cnt[7]))
         supers += int(cnt[1])
         rounds += int(cnt[2])
     for name in ["ex1_header.bam", "bins.bam", "tags.bam", "b7_295_chunk.bam", "mg1655_chunk.bam", "ion_20_chunk.bam",

@@ -278,3 +278,19 @@ def test_admit_many_equals_admit_on_large_inputs():
                 assert 0 < k <= len(seg) // 4
                 res.append(seg[:4 * k].reshape(k, 4))
             assert np.array_equal(res[0], res[1]), (sh, skip)
+            # reads that are not part of the pileup (end = INT32_MIN in the batch arrays) are passed over: the same
+            # segments as the chain over the remaining reads alone, with their indices
+            keep = rng.random(n) > 0.1
+            end_m = np.where(keep, end, -2**31).astype(np.int64)
+            seg = np.zeros(4 * (4 * n + 64), dtype=np.int64)
+            k = L.biodb_debug_md_chain(ref.ctypes.data, pos.ctypes.data, end_m.ctypes.data, ln.ctypes.data, n, skip, 10**9,
+                                       seg.ctypes.data, len(seg) // 4)
+            a = seg[:4 * k].reshape(k, 4)
+            idx = np.nonzero(keep)[0]
+            r2, p2, e2, l2 = (np.ascontiguousarray(x[idx]) for x in (ref, pos, end, ln))
+            seg2 = np.zeros(4 * (4 * n + 64), dtype=np.int64)
+            k2 = L.biodb_debug_md_chain(r2.ctypes.data, p2.ctypes.data, e2.ctypes.data, l2.ctypes.data, len(idx), skip, 0,
+                                        seg2.ctypes.data, len(seg2) // 4)
+            b = seg2[:4 * k2].reshape(k2, 4).copy()
+            b[:, 2] = idx[b[:, 2]]
+            assert np.array_equal(a, b), (sh, skip, "markers")
