@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--straddle", action="store_true", help="htsjdk-style file: records cut across BGZF blocks")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-input", default="memory", choices=["memory", "file"],
+                    help="e2e leg: the caller's buffer (biodb_open_memory; page-locked whole at N = 1, the shard's range at N > 1) "
+                         "or the file itself (biodb_open: pread into the library's pinned slabs)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the blocks for the other named configs (config3 / config4)")
     ap.add_argument("--md", action="store_true",
@@ -93,7 +96,9 @@ def synth_file(args, config, cfg, n_reads, rank, world, barrier):
     barrier()
     # N > 1: every rank maps the same file read-only (one copy in the page cache; only the shard's pages are touched);
     # N = 1: a private copy that can be pinned
-    data = np.fromfile(path, dtype=np.uint8) if world == 1 else np.memmap(path, dtype=np.uint8, mode="r")
+    # N > 1: every rank maps the one file privately ("c": the mapping is writable, which cudaHostRegister asks for; nothing
+    # is ever written) and page-locks only its own shard's byte range (pin_input = 2)
+    data = np.fromfile(path, dtype=np.uint8) if world == 1 else np.memmap(path, dtype=np.uint8, mode="c")
     return data, path, time.time() - t0, made
 
 
@@ -247,13 +252,16 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
     data, path, t_gen, made = synth_file(args, config, cfg, n_reads, rank, world, barrier)
     bpb = args.blocks_per_batch or (0 if world == 1 else (-2 if world == 2 else -1))
 
-    def open_reader(resident, device_output, pin):
+    def open_reader(resident, device_output, pin, from_file=False):
         o = capi.Options()
         L.biodb_default_options(C.byref(o))
         o.device, o.blocks_per_batch = local, bpb
         o.resident_input, o.device_output, o.pin_input = int(resident), int(device_output), int(pin)
         h = C.c_void_p()
-        st = L.biodb_open_memory(data.ctypes.data, data.size, C.byref(o), C.byref(h))
+        if from_file:        # BamReader(filename): the library reads the file itself (pread into its pinned slabs)
+            st = L.biodb_open(path.encode(), C.byref(o), C.byref(h))
+        else:
+            st = L.biodb_open_memory(data.ctypes.data, data.size, C.byref(o), C.byref(h))
         if st != capi.OK:
             raise RuntimeError(L.biodb_open_error().contents.message.decode())
         return h
@@ -331,10 +339,11 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
     if want_e2e:
         # N = 1: the private copy of the file is page-locked whole; N > 1: every rank maps the shared file and page-locks
         # only the byte range of its own shard (+ halo), on demand
-        rd = open_reader(False, False, 1 if world == 1 else 2)
-        input_pinned = bool(L.biodb_input_is_pinned(rd))
+        from_file = args.e2e_input == "file"
+        rd = open_reader(False, False, 1 if world == 1 else 2, from_file)
         einfo = {}
         run_pass(L, capi, rd, shard, einfo, compact=True)
+        input_pinned = bool(L.biodb_input_is_pinned(rd)) or from_file
         barrier()
         es = [run_pass(L, capi, rd, shard, einfo, compact=True) for _ in range(steps)]
         barrier()
@@ -362,7 +371,7 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
         e_ms = float(te[0]) / steps + float(te[1])
         out["e2e"] = {"value": tot_col / (e_ms * 1e-3), "unit": "positions/s", "ms_per_step": e_ms,
                       "h2d_bytes_per_step": int(es[-1][0].h2d_bytes), "d2h_bytes_per_step": int(es[-1][0].d2h_bytes),
-                      "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned,
+                      "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned, "input": args.e2e_input,
                       "pcie_d2h_gbs": es[-1][0].d2h_bytes / (e_ms * 1e-3) / 1e9,
                       "stage_ms": {"inflate": float(np.mean([s[0].inflate_ms for s in es])),
                                    "record_scan": float(np.mean([s[0].scan_ms for s in es])),
@@ -508,7 +517,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "reads_per_gpu": n_rec, "positions_per_gpu": n_col, "entries_per_gpu": n_ent,
                        "total_reads": tot_rec, "total_positions": tot_col, "halo": m["halo"],
-                       "halo_check_passed": True,
+                       "halo_check_passed": bool(m["halo"].get("exact")),
                        "compressed_bytes": m["compressed_bytes"],
                        "blocks_per_batch": args.blocks_per_batch or ("library default: 3 full waves of the inflate kernel" if world == 1
                                                                      else f"{2 if world == 2 else 1} full wave(s) of the inflate kernel"),
@@ -530,13 +539,22 @@ def main():
     if "maq_e2e" in m:
         line["maq_e2e"] = m["maq_e2e"]
     # diagnostics of the lane-parallel inflate kernel over everything run so far (0 blocks given up = no fallback)
+    given_up = None
     try:
         cnt = (C.c_uint64 * 8)()
         if L.biodb_debug_inflate_counters(cnt, 0) == 0:
+            given_up = int(cnt[0])
             line["inflate_counters"] = {"blocks_given_up": int(cnt[0]), "super_chunks": int(cnt[1]), "decode_rounds": int(cnt[2]),
                                         "matches_from_l2": int(cnt[3]), "matches": int(cnt[4]), "deflate_blocks": int(cnt[5])}
     except Exception:  # noqa: BLE001
         pass
+    # size-independent checks of the full-size pass (the oracle does not run at this scale; tests/test_gpu_configs.py
+    # compares its first 2 M reads column by column): every generated read came out of the record scan, a 150M read
+    # makes exactly 150 column entries, the shards' columns add up across ranks, and (this rank's) inflate kernels
+    # needed the fallback for no block
+    line["checks"] = {"records_equal_generated": bool(tot_rec == n_reads),
+                      "entries_equal_150_per_read": bool(tot_ent == 150 * tot_rec) if args.config == 2 else None,
+                      "no_block_given_up": (given_up == 0) if given_up is not None else None}
 
     # ---- the other configs BASELINE.json names, as blocks of the same line --------------------------------
     if not args.no_extra and args.config == 2 and not args.reads:

@@ -123,6 +123,7 @@ int parse_bgzf_header(const uint8_t* d, uint64_t len, uint64_t pos, BlockInfo* b
 // ---------------------------------------------------------------------------------- Pass ----
 
 Pass::~Pass() {
+  join_prefetch();
   if (st) {
     cudaStreamSynchronize(st);
     cudaStreamDestroy(st);
@@ -210,6 +211,7 @@ void Pass::rewind(uint64_t coffset, uint32_t uoffset) {
   next_coffset = coffset;
   first_skip = uoffset;
   entry_search = false;
+  join_prefetch();
   pf_c0 = pf_c1 = 0;
   pre_valid = false;
   if (h2d_st) cudaStreamSynchronize(h2d_st);
@@ -276,6 +278,10 @@ static void walk_headers(const biodb_reader* r, uint64_t stop_coffset, uint32_t 
     blocks.push_back(b);
     next_coffset = b.coffset + b.bsize + 1;
   }
+}
+
+int Pass::join_prefetch() {
+  return pf_job.valid() ? pf_job.get() : 0;
 }
 
 const uint8_t* Pass::stage_host(uint64_t c0, uint64_t c1, cudaError_t* err) {
@@ -378,6 +384,7 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
   const uint32_t* d_isize = d_cdata + nb;
   // ---- 3. device buffers -------------------------------------------------------------------------------
   const bool resident = r->d_file.p != nullptr;
+  if (const int jr = join_prefetch()) return fail(jr == 1 ? BIODB_ERR_IO : BIODB_ERR_CUDA, 0, pf_c0, "cannot read the file");
   if (!resident && nb) {
     if (pf_c1 && pf_c0 == c0) {
       // the start of this batch was prefetched while the previous one was computed: switch buffers, wait for the copy
@@ -456,11 +463,25 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
         // kernels on the compute stream
         CUDA_TRY(cudaStreamWaitEvent(h2d_st, comp_free[nxt], 0));
         CUDA_TRY(d_comp2[nxt].ensure((size_t)(n1 - n0) + (size_t)((n1 - n0) >> 4) + 65536 + 256, h2d_st));
-        cudaError_t he;
-        const uint8_t* hp = stage_host(n0, n1, &he);          // (a streamed file is read here, while the GPU inflates)
-        if (!hp) return fail(he == cudaErrorUnknown ? BIODB_ERR_IO : BIODB_ERR_CUDA, 0, n0, "cannot read the file");
-        CUDA_TRY(cudaMemcpyAsync(d_comp2[nxt].p, hp, (size_t)(n1 - n0), cudaMemcpyHostToDevice, h2d_st));
-        CUDA_TRY(cudaEventRecord(pf_done, h2d_st));
+        if (r->file) {
+          CUDA_TRY(cudaMemcpyAsync(d_comp2[nxt].p, r->file + n0, (size_t)(n1 - n0), cudaMemcpyHostToDevice, h2d_st));
+          CUDA_TRY(cudaEventRecord(pf_done, h2d_st));
+        } else {
+          // a streamed file: pread into the slab that is not the source of the copy issued last, then the copy — on a
+          // thread of its own, so that reading the next batch overlaps everything this batch still has to do (joined
+          // at the top of the next call)
+          slab_cur ^= 1;
+          PinBuf* sl = &h_slab[slab_cur];
+          const size_t nbytes = (size_t)(n1 - n0);
+          if (nbytes + 64 > sl->cap) CUDA_TRY(sl->ensure(nbytes + nbytes / 8 + 65536));
+          void* dst = d_comp2[nxt].p;
+          pf_job = std::async(std::launch::async, [this, sl, dst, n0, nbytes]() -> int {
+            cudaSetDevice(r->device);
+            if (!r->read_bytes(n0, nbytes, sl->p, 8)) return 1;
+            if (cudaMemcpyAsync(dst, sl->p, nbytes, cudaMemcpyHostToDevice, h2d_st) != cudaSuccess) return 2;
+            return cudaEventRecord(pf_done, h2d_st) == cudaSuccess ? 0 : 2;
+          });
+        }
         stats.h2d_bytes += n1 - n0;
         pf_c0 = n0;
         pf_c1 = n1;

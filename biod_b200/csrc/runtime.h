@@ -8,6 +8,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <future>
 #include <vector>
 
 #include "../../include/biod_b200.h"
@@ -139,6 +140,8 @@ struct Pass {
   DevBuf d_comp2[2], d_tab, d_status, d_u, d_carry_tail, d_ws, d_result, d_tok;
   PinBuf h_slab[2];                 // streamed files: the compressed bytes of a batch on their way to the device
   int slab_cur = 0;
+  std::future<int> pf_job;          // streamed files: the prefetch (pread into a slab, then the copy) on a thread of its own
+  int join_prefetch();              // waits for it; 0 = none / fine, 1 = read error, 2 = CUDA error
   // host address of file bytes [c0, c1) for a host->device copy: the caller's buffer, or (streamed file) the next slab
   const uint8_t* stage_host(uint64_t c0, uint64_t c1, cudaError_t* err);
   // host->device prefetch of the next batch's compressed bytes (input not resident): while batch k is inflated out of
