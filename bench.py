@@ -103,13 +103,51 @@ def synth_file(args, config, cfg, n_reads, rank, world, barrier):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU DURING the timed region: NVML polled every 10 ms on a thread (the timed
+    calls release the GIL); nvidia-smi -lms as the fallback when NVML cannot be loaded."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.sm, self.mx, self.reasons, self.stop_flag, self.thread, self.h = [], None, set(), False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; NVML sees every GPU of the box
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.h = None
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            r = int(get(self.h))
+            for nm, bit in self.BITS.items():
+                if r & bit:
+                    self.reasons.add(nm)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _poll(self):
+        while not self.stop_flag:
+            try:
+                self._sample()
+            except Exception:  # noqa: BLE001
+                return
+            time.sleep(0.01)
 
     def start(self):
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
@@ -122,6 +160,12 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.h is not None:
+            self.stop_flag = True
+            if self.thread:
+                self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, every 10 ms during the timed passes"}
         if self.proc:
             self.proc.terminate()
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -133,7 +177,7 @@ class ClockSampler:
                 if len(r) > 3 + k and r[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False, halo_voffset=None, maq=False, calls=None):
