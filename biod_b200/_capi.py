@@ -147,6 +147,10 @@ def lib():
     L.biodb_index_close.argtypes = [vp]
     L.biodb_index_n_refs.restype = C.c_int32
     L.biodb_index_n_refs.argtypes = [vp]
+    L.biodb_reads_begin_regions.restype = C.c_int
+    L.biodb_reads_begin_regions.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp, C.POINTER(vp)]
+    L.biodb_index_regions_chunks.restype = C.c_int64
+    L.biodb_index_regions_chunks.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, vp, C.c_uint64]
     L.biodb_index_chunks.restype = C.c_int64
     L.biodb_index_chunks.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp, C.c_uint64]
     L.biodb_index_last_linear_offset.restype = C.c_int32
@@ -211,7 +215,7 @@ EXPORTS = [
     "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_begin_shard_at", "biodb_pileup_shard_info",
     "biodb_pileup_shard_reach", "biodb_shard_cuts", "biodb_pileup_begin_range", "biodb_pileup_maq_params",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
-    "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",
+    "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_regions_chunks", "biodb_reads_begin_regions", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",
     "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",
     "biodb_debug_deflate_block", "biodb_debug_deflate_stats", "biodb_writer_begin", "biodb_writer_header", "biodb_writer_records", "biodb_writer_flush",

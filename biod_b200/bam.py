@@ -357,6 +357,44 @@ class BamReader:
         finally:
             L.biodb_reads_end(it)
 
+    def regions_batches(self, regions, copy=False):
+        """Batches of getReadsOverlapping(regions) (reader.d:361, randomaccessmanager.d:316-337): regions = BamRegion-like
+        triples (ref_id, start, end) in any order; they are grouped by reference, and the groups are read one after the
+        other in reference order, each through biodb_reads_begin_regions."""
+        by_ref = {}
+        for ref_id, start, end in regions:
+            if not start < end:
+                raise Exception("start must be less than end")
+            by_ref.setdefault(int(ref_id), []).append((int(start), int(end)))
+        L = self._L
+        for ref_id in sorted(by_ref):
+            begs = np.array([a for a, _ in by_ref[ref_id]], dtype=np.uint32)
+            ends = np.array([b for _, b in by_ref[ref_id]], dtype=np.uint32)
+            it = C.c_void_p()
+            st = L.biodb_reads_begin_regions(self._h, self._bai()._h, ref_id, len(begs), begs.ctypes.data, ends.ctypes.data, C.byref(it))
+            if st == capi.ERR_ARG:
+                raise Exception(L.biodb_last_error(self._h).contents.message.decode("latin-1"))
+            if st != capi.OK:
+                self._err()
+            try:
+                while True:
+                    b = capi.RecordBatch()
+                    st = L.biodb_reads_next(it, C.byref(b))
+                    if st == capi.EOF:
+                        break
+                    if st != capi.OK:
+                        self._err()
+                    yield RecordBatch(b, copy)
+            finally:
+                L.biodb_reads_end(it)
+
+    def getReadsOverlapping(self, regions):
+        """reader.d:361: the reads that overlap any of the regions [(ref_id, start, end), ...], every read once, in file
+        order within a reference, references in ascending order."""
+        for batch in self.regions_batches(regions, copy=True):
+            for i in range(batch.n):
+                yield BamRead(batch, i)
+
     def getReadsBetween(self, from_voffset, to_voffset=None, max_blocks=0):
         """reader.d:350-356: the reads from one virtual offset (the start of a record) to another (the end of one;
         None = the end of the file)."""

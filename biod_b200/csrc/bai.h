@@ -125,6 +125,45 @@ struct BaiIndex {
     }
     return true;
   }
+
+  // getGroupChunks (randomaccessmanager.d:246-296): the chunks of every bin that the bin bitset of ALL the regions (one
+  // reference; sorted, non-overlapping, each begin < end) marks, cut at the linear index's minimum offset for the first
+  // region's start, sorted and merged.  The reference's bitset has BAI_MAX_BIN_ID = 37449 entries and is indexed with
+  // every bin id of the index, so the pseudo-bin 37450 of samtools' and BioD's own indexes is out of its range (an
+  // error in D): bins beyond the bitset are passed over here, as Bin.canOverlapWith does for a single region.
+  bool regions_chunks(uint32_t ref_id, const std::vector<std::pair<uint32_t, uint32_t>>& regions, std::vector<VoChunk>* out) const {
+    out->clear();
+    if (ref_id >= refs.size() || regions.empty()) return false;
+    const BaiRef& r = refs[ref_id];
+    std::vector<char> bitset(37449, 0);
+    bitset[0] = 1;
+    for (const auto& rg : regions) {
+      const uint32_t beg = rg.first, end = rg.second - 1;
+      uint32_t k;
+      for (k = 1 + (beg >> 26); k <= 1 + (end >> 26); ++k) bitset[k] = 1;
+      for (k = 9 + (beg >> 23); k <= 9 + (end >> 23); ++k) bitset[k] = 1;
+      for (k = 73 + (beg >> 20); k <= 73 + (end >> 20); ++k) bitset[k] = 1;
+      for (k = 585 + (beg >> 17); k <= 585 + (end >> 17); ++k) bitset[k] = 1;
+      for (k = 4681 + (beg >> 14); k <= 4681 + (end >> 14) && k < 37449; ++k) bitset[k] = 1;
+    }
+    const int32_t pos = std::max<int32_t>(0, (int32_t)regions.front().first);
+    const int32_t w = std::min<int32_t>(pos / 16384, (int32_t)r.ioffsets.size() - 1);
+    const uint64_t min_offset = w == -1 ? 0 : r.ioffsets[(size_t)w];
+    std::vector<VoChunk> all;
+    for (size_t k = 0; k < r.bin_id.size(); ++k) {
+      if (r.bin_id[k] >= bitset.size() || !bitset[r.bin_id[k]]) continue;
+      for (uint32_t c = r.bin_first[k]; c < r.bin_first[k + 1]; ++c) {
+        const VoChunk& ch = r.chunks[c];
+        if (ch.end > min_offset) all.push_back(VoChunk{std::max(ch.beg, min_offset), ch.end});
+      }
+    }
+    std::sort(all.begin(), all.end(), [](const VoChunk& a, const VoChunk& b) { return a.beg != b.beg ? a.beg < b.beg : a.end < b.end; });
+    for (const VoChunk& ch : all) {
+      if (!out->empty() && out->back().end >= ch.beg) out->back().end = std::max(out->back().end, ch.end);
+      else out->push_back(ch);
+    }
+    return true;
+  }
 };
 
 }  // namespace biodb

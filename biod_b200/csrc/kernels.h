@@ -116,7 +116,10 @@ cudaError_t launch_scan_records(const uint8_t* u, uint64_t u_len, const uint64_t
 // info (device, 4 x u32): [0] index of the first read that ends the range (0xffffffff = none), [1] reads kept,
 // [2] their CIGAR words.
 size_t region_scratch_elems(uint64_t n);
+// regs / n_regs (getReads(BamRegion[])): n_regs > 1 sorted, non-overlapping regions of `ref` as (begin, end) pairs on the
+// device; [beg, end) is then the first region's begin and the last one's end.
 cudaError_t launch_region_filter(const RecordArrays& in, uint64_t n, uint32_t ref, uint32_t beg, uint32_t end,
-                                 const RecordArrays& out, uint32_t* scratch, uint32_t* info, cudaStream_t st);
+                                 const RecordArrays& out, uint32_t* scratch, uint32_t* info, cudaStream_t st,
+                                 const uint32_t* regs = nullptr, uint32_t n_regs = 0);
 
 }  // namespace biodb

@@ -1,5 +1,6 @@
 // Region filter over the record tables of a batch: BamReadFilter of
-// bio/std/hts/bam/randomaccessmanager.d:366-462, for one region [beg, end) of one reference.
+// bio/std/hts/bam/randomaccessmanager.d:366-462, for one region [beg, end) — or several sorted, non-overlapping
+// regions — of one reference.
 //
 // The reference walks the reads of the index's chunks one by one: reads of earlier references are skipped, the first
 // read of a later reference or with position >= end ends the range, and a read is kept when it starts inside the
@@ -29,10 +30,22 @@ __global__ void region_stop_kernel(const int32_t* __restrict__ ref_id, const int
 __global__ void region_keep_kernel(const int32_t* __restrict__ ref_id, const int32_t* __restrict__ pos,
                                    const int32_t* __restrict__ end_pos, const uint32_t* __restrict__ flag_nc, uint32_t n,
                                    uint32_t ref, uint32_t beg, const uint32_t* __restrict__ first_stop,
-                                   uint32_t* __restrict__ keep, uint32_t* __restrict__ ccnt) {
+                                   uint32_t* __restrict__ keep, uint32_t* __restrict__ ccnt,
+                                   const uint32_t* __restrict__ regs, uint32_t n_regs) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   bool k = j < *first_stop && (uint32_t)ref_id[j] == ref;
+  if (k && n_regs > 1) {
+    // several regions (randomaccessmanager.d:396-450): the filter's region pointer only moves forward, when a read starts
+    // at or beyond the current region's end — so a read is judged against the first region that ends behind its position
+    const uint32_t p = (uint32_t)pos[j];
+    uint32_t lo = 0, hi = n_regs;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (regs[2 * mid + 1] > p) hi = mid; else lo = mid + 1;
+    }
+    beg = regs[2 * min(lo, n_regs - 1)];                                 // (lo < n_regs: the read is in front of first_stop)
+  }
   if (k) k = (uint32_t)pos[j] > beg || (uint32_t)end_pos[j] > beg;       // end_pos = position + basesCovered()
   keep[j] = k ? 1u : 0u;
   ccnt[j] = k ? (flag_nc[j] & 0xFFFFu) : 0u;
@@ -69,7 +82,8 @@ __global__ void region_totals_kernel(const uint32_t* a, const uint32_t* b, uint3
 size_t region_scratch_elems(uint64_t n) { return 4 * (size_t)(n + 8) + 2 * (scan_temp_elems(n) + 8) + 16; }
 
 cudaError_t launch_region_filter(const RecordArrays& in, uint64_t n64, uint32_t ref, uint32_t beg, uint32_t end,
-                                 const RecordArrays& out, uint32_t* scratch, uint32_t* info, cudaStream_t st) {
+                                 const RecordArrays& out, uint32_t* scratch, uint32_t* info, cudaStream_t st,
+                                 const uint32_t* regs, uint32_t n_regs) {
   const uint32_t n = (uint32_t)n64;
   uint32_t* keep = scratch;
   uint32_t* slot = keep + (n + 8);
@@ -81,7 +95,7 @@ cudaError_t launch_region_filter(const RecordArrays& in, uint64_t n64, uint32_t 
   if (n) {
     const uint32_t grid = (n + 255) / 256;
     region_stop_kernel<<<grid, 256, 0, st>>>(in.ref_id, in.pos, n, ref, end, info);
-    region_keep_kernel<<<grid, 256, 0, st>>>(in.ref_id, in.pos, in.end_pos, in.flag_nc, n, ref, beg, info, keep, ccnt);
+    region_keep_kernel<<<grid, 256, 0, st>>>(in.ref_id, in.pos, in.end_pos, in.flag_nc, n, ref, beg, info, keep, ccnt, regs, n_regs);
     g_kernel_launches += 2;
   }
   device_scan<true>(keep, slot, n, tmp_a, OpAdd(), 0u, st);          // tmp_a[tiles] = number of kept reads

@@ -6,6 +6,7 @@
 #include "md_walk.h"
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -597,7 +598,8 @@ biodb_status Pass::next(uint32_t max_blocks, uint64_t front_slots) {
 
 int biodb_reader::header_at(uint64_t pos, biodb::BlockInfo* b, biodb_error* e) {
   if (file) return parse_bgzf_header(file, flen, pos, b, e, 0);
-  // streamed: a BGZF member is at most 64 KiB of payload behind a header of at most 64 KiB of extra fields, so a window
+  if (hdr_map) return parse_bgzf_header(hdr_map, flen, pos, b, e, 0);
+  // streamed, no mapping: a BGZF member is at most 64 KiB of payload behind a header of at most 64 KiB of extra fields, so a window
   // that reaches WIN_NEED bytes past pos (or the end of the file) shows parse_bgzf_header everything it may look at
   constexpr uint64_t WIN_NEED = 192 * 1024, WIN_SIZE = 8ull << 20;
   std::lock_guard<std::mutex> lk(hdr_mu);
@@ -790,12 +792,20 @@ static biodb_status open_common(biodb_reader* r) {
   return BIODB_OK;
 }
 
+// a reader that did not make it through finish_open: what biodb_close would release
+static void drop_reader(biodb_reader* r) {
+  if (r->hdr_map) munmap((void*)r->hdr_map, (size_t)r->flen);
+  if (r->fd >= 0) close(r->fd);
+  if (r->registered) cudaHostUnregister((void*)r->file);
+  delete r;
+}
+
 static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biodb_reader** out) {
   if (opts) r->opts = *opts; else biodb_default_options(&r->opts);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "no CUDA device: biod_b200 has no CPU fallback");
-    delete r;
+    drop_reader(r);
     return BIODB_ERR_CUDA;
   }
   if (r->opts.device < 0) { if (cudaGetDevice(&r->device) != cudaSuccess) r->device = 0; }
@@ -811,7 +821,7 @@ static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biod
   if (s != BIODB_OK) {
     g_open_error = r->err;
     if (!g_open_error.status) set_error(&g_open_error, s, 0, 0, "open failed");
-    delete r;
+    drop_reader(r);
     return s;
   }
   if (r->opts.resident_input && r->flen) {
@@ -829,7 +839,7 @@ static biodb_status finish_open(biodb_reader* r, const biodb_options* opts, biod
     }
     if (!ok) {
       set_error(&g_open_error, BIODB_ERR_CUDA, 0, 0, "cannot make the compressed file resident in device memory");
-      delete r;
+      drop_reader(r);
       return BIODB_ERR_CUDA;
     }
   }
@@ -863,6 +873,12 @@ biodb_status biodb_open(const char* path, const biodb_options* opts, biodb_reade
   r->fd = fd;
   r->file = nullptr;
   r->flen = (uint64_t)sb.st_size;
+  if (r->flen) {
+    // walking the BSIZE chain through a window would copy the whole file a second time: look at the block headers
+    // through a mapping instead (a few bytes per block; the bulk of the file still goes pread -> pinned slab -> device)
+    void* m = mmap(nullptr, (size_t)r->flen, PROT_READ, MAP_SHARED, fd, 0);
+    if (m != MAP_FAILED) r->hdr_map = (const uint8_t*)m;
+  }
   return finish_open(r, opts, out);
 }
 
@@ -875,6 +891,7 @@ void biodb_close(biodb_reader* r) {
   for (void* p : r->reads_pool) reads_destroy_pooled(p);
   if (r->registered) cudaHostUnregister((void*)r->file);
   for (const auto& g : r->pinned) cudaHostUnregister((void*)(uintptr_t)g.first);
+  if (r->hdr_map) munmap((void*)r->hdr_map, (size_t)r->flen);
   if (r->fd >= 0) close(r->fd);
   delete r;
 }
@@ -933,6 +950,8 @@ struct biodb_reads {
   std::vector<VoChunk> chunks;
   size_t chunk_i = 0;                  // chunk being read
   uint32_t reg_ref = 0, reg_beg = 0, reg_end = 0;
+  std::vector<uint32_t> regs;          // several regions (biodb_reads_begin_regions): (begin, end) pairs, also on the device
+  DevBuf d_regs;
   DevBuf d_sel[10], d_scratch, d_info;
   PinBuf h_info;
   uint64_t sel_cap = 0, sel_cig_cap = 0;
@@ -959,6 +978,7 @@ struct biodb_reads {
     chunk_blocks = 0;
     chunks.clear();
     chunk_i = 0;
+    regs.clear();
   }
 };
 
@@ -1004,7 +1024,8 @@ static biodb_status region_next(biodb_reads* it) {
                      it->d_sel[8].as<uint64_t>(), it->d_sel[9].as<uint32_t>(), it->sel_cap, it->sel_cig_cap};
     p.stage_begin();
     cudaError_t e = launch_region_filter(in, p.n, it->reg_ref, it->reg_beg, it->reg_end, out, it->d_scratch.as<uint32_t>(),
-                                         it->d_info.as<uint32_t>(), st);
+                                         it->d_info.as<uint32_t>(), st, it->regs.size() > 2 ? it->d_regs.as<uint32_t>() : nullptr,
+                                         (uint32_t)(it->regs.size() / 2));
     p.stage_end(&p.stats.scan_ms);
     if (e != cudaSuccess || launch_copy_bytes(it->h_info.p, it->d_info.p, 12, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess)
@@ -1222,6 +1243,83 @@ biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, ui
   it->reg_end = end;
   if (!it->chunks.empty()) region_seek(it, 0);
   return BIODB_OK;
+}
+
+// getReads(BamRegion[]) for the regions of ONE reference (randomaccessmanager.d:286-296 per group of :316-337; the
+// caller joins the groups of several references one after the other, as the reference does): the regions are sorted,
+// overlapping ones joined (nonOverlapping, algo.d:95-162: prev.end >= next.begin), the chunks of all of them read as
+// one stream and filtered by the multi-region BamReadFilter.
+biodb_status biodb_reads_begin_regions(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t n, const uint32_t* begs,
+                                       const uint32_t* ends, biodb_reads** out) {
+  if (!r || !ix || !out || !n || !begs || !ends) return BIODB_ERR_ARG;
+  std::vector<std::pair<uint32_t, uint32_t>> rg(n), merged;
+  for (uint32_t k = 0; k < n; ++k) {
+    if (begs[k] >= ends[k]) {                              // enforce(beg < end), randomaccessmanager.d:256
+      set_error(&r->err, BIODB_ERR_ARG, 0, 0, "start must be less than end");
+      return BIODB_ERR_ARG;
+    }
+    rg[k] = {begs[k], ends[k]};
+  }
+  std::sort(rg.begin(), rg.end());
+  for (const auto& x : rg) {
+    if (!merged.empty() && merged.back().second >= x.first) merged.back().second = std::max(merged.back().second, x.second);
+    else merged.push_back(x);
+  }
+  std::vector<VoChunk> c, cc;
+  if (!ix->bai.regions_chunks(ref_id, merged, &c)) {
+    set_error(&r->err, BIODB_ERR_ARG, 0, 0, "Invalid reference sequence index");
+    return BIODB_ERR_ARG;
+  }
+  for (size_t k = 0; k < c.size();) {                      // moveToNextChunk: chunks that begin in the same block are one stretch
+    size_t i = k + 1;
+    while (i < c.size() && (c[i].beg >> 16) <= (c[k].beg >> 16)) ++i;
+    cc.push_back(VoChunk{c[k].beg, c[i - 1].end});
+    k = i;
+  }
+  biodb_status s = biodb_reads_begin(r, out);
+  if (s != BIODB_OK) return s;
+  biodb_reads* it = *out;
+  it->region = true;
+  it->filter = true;
+  it->region_done = false;
+  it->chunks.swap(cc);
+  it->chunk_i = 0;
+  it->reg_ref = ref_id;
+  it->reg_beg = merged.front().first;
+  it->reg_end = merged.back().second;
+  it->regs.clear();
+  for (const auto& x : merged) { it->regs.push_back(x.first); it->regs.push_back(x.second); }
+  if (it->regs.size() > 2) {
+    if (it->d_regs.ensure(it->regs.size() * 4, it->pass.st) != cudaSuccess ||
+        cudaMemcpyAsync(it->d_regs.p, it->regs.data(), it->regs.size() * 4, cudaMemcpyHostToDevice, it->pass.st) != cudaSuccess ||
+        cudaStreamSynchronize(it->pass.st) != cudaSuccess) {
+      biodb_reads_end(it);
+      *out = nullptr;
+      return BIODB_ERR_CUDA;
+    }
+  }
+  if (!it->chunks.empty()) region_seek(it, 0);
+  return BIODB_OK;
+}
+
+// Host-only: the chunk list of the above (merged regions -> getGroupChunks), (begin, end) virtual offsets into out2.
+int64_t biodb_index_regions_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t n, const uint32_t* begs, const uint32_t* ends,
+                                   uint64_t* out2, uint64_t cap) {
+  if (!ix || !n || !begs || !ends) return -1;
+  std::vector<std::pair<uint32_t, uint32_t>> rg(n), merged;
+  for (uint32_t k = 0; k < n; ++k) {
+    if (begs[k] >= ends[k]) return -1;
+    rg[k] = {begs[k], ends[k]};
+  }
+  std::sort(rg.begin(), rg.end());
+  for (const auto& x : rg) {
+    if (!merged.empty() && merged.back().second >= x.first) merged.back().second = std::max(merged.back().second, x.second);
+    else merged.push_back(x);
+  }
+  std::vector<VoChunk> c;
+  if (!ix->bai.regions_chunks(ref_id, merged, &c)) return -1;
+  for (uint64_t k = 0; k < c.size() && k < cap && out2; ++k) { out2[2 * k] = c[k].beg; out2[2 * k + 1] = c[k].end; }
+  return (int64_t)c.size();
 }
 
 biodb_status biodb_reads_begin_between(biodb_reader* r, uint64_t from_voffset, uint64_t to_voffset, uint32_t max_blocks,

@@ -65,6 +65,8 @@ struct biodb_reader {
   // the compressed bytes of a batch are pread into one of the pass's two pinned slabs while the GPU inflates the batch
   // before (Pass::stage_host), so the pinned memory a reader needs is two batches, whatever the file's size.
   int fd = -1;
+  const uint8_t* hdr_map = nullptr;   // read-only mapping of the file, used ONLY to look at the 26 header / footer bytes of
+                                      // each block (no copy; the window below is the fallback when mmap is refused)
   std::vector<uint8_t> hdr_win;   // file bytes [hdr_off, hdr_off + hdr_win.size())
   uint64_t hdr_off = 0;
   std::mutex hdr_mu;

@@ -159,6 +159,17 @@ void biodb_index_builder_end(biodb_index_builder* b);
  * whole slice the reads lie in).  BIODB_ERR_ARG: beg >= end or invalid reference index. */
 biodb_status biodb_reads_begin_region(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t beg, uint32_t end,
                                       biodb_reads** out);
+/* getReads(BamRegion[]) = BamReader.getReadsOverlapping(regions) (reader.d:361, randomaccessmanager.d:246-296,316-337) for
+ * the n regions [begs[k], ends[k]) of ONE reference: they are sorted and overlapping ones joined, the chunks of all their
+ * bins are read as one stream and filtered by the multi-region BamReadFilter (:366-462) on the device.  The caller runs
+ * the groups of several references one after the other, in reference order, as the reference does.  Restatement-defined:
+ * the reference indexes a bitset of 37449 entries with every bin id of the index, which fails on the pseudo-bin 37450 that
+ * samtools and BioD's own IndexBuilder write; bins beyond the bitset are passed over here.  BIODB_ERR_ARG: a begin >= its
+ * end, n == 0, or an invalid reference index.  biodb_index_regions_chunks: the chunk list of such a group (host only). */
+biodb_status biodb_reads_begin_regions(biodb_reader* r, const biodb_index* ix, uint32_t ref_id, uint32_t n, const uint32_t* begs,
+                                       const uint32_t* ends, biodb_reads** out);
+int64_t biodb_index_regions_chunks(const biodb_index* ix, uint32_t ref_id, uint32_t n, const uint32_t* begs, const uint32_t* ends,
+                                   uint64_t* out2, uint64_t cap);
 
 /* getReadsBetween(from, to) (reader.d:350-356, randomaccessmanager.d:186-196): the records from virtual offset `from`
  * (which must point at the start of a record) up to virtual offset `to` — the end offset of some record, or

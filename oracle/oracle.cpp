@@ -1042,6 +1042,67 @@ void region_filter(const std::vector<RegionRead>& in, uint32_t ref_id, uint32_t 
   }
 }
 
+// getGroupChunks (randomaccessmanager.d:246-296): the chunks of every bin the bitset of ALL regions (of one reference,
+// sorted, non-overlapping) marks, cut at the linear index's minimum offset for the FIRST region's start, merged.
+// Restatement-defined: the reference's bitset has BAI_MAX_BIN_ID = 37449 entries and is indexed with every bin id of the
+// index — the pseudo-bin 37450 that samtools (and BioD's own IndexBuilder) write is out of its range, an error in D.
+// Pinned: bins with an id beyond the bitset are passed over, as Bin.canOverlapWith does for a single region (bin.d:58).
+std::vector<Chunk> group_chunks(const Bai* bai, uint32_t ref_id, const std::vector<std::pair<uint32_t, uint32_t>>& regions, int* status) {
+  std::vector<Chunk> out;
+  if (regions.empty() || ref_id >= bai->idx.size()) { *status = ORC_ERR_ARG; return out; }
+  std::vector<char> bitset(37449, 0);
+  bitset[0] = 1;
+  for (const auto& rg : regions) {
+    const uint32_t beg = rg.first;
+    uint32_t end = rg.second;
+    if (!(beg < end)) { *status = ORC_ERR_ARG; return out; }        // enforce(beg < end)
+    --end;
+    uint32_t k;
+    for (k = 1 + (beg >> 26); k <= 1 + (end >> 26); ++k) bitset[k] = 1;
+    for (k = 9 + (beg >> 23); k <= 9 + (end >> 23); ++k) bitset[k] = 1;
+    for (k = 73 + (beg >> 20); k <= 73 + (end >> 20); ++k) bitset[k] = 1;
+    for (k = 585 + (beg >> 17); k <= 585 + (end >> 17); ++k) bitset[k] = 1;
+    for (k = 4681 + (beg >> 14); k <= 4681 + (end >> 14) && k < 37449; ++k) bitset[k] = 1;
+  }
+  const BaiIndex& ix = bai->idx[ref_id];
+  const int32_t pos = std::max(0, (int32_t)regions.front().first);
+  const int32_t i = std::min(pos / 16384, (int32_t)ix.ioffsets.size() - 1);
+  const uint64_t min_offset = i == -1 ? 0 : ix.ioffsets[(size_t)i];
+  for (const BaiBin& b : ix.bins) {
+    if (b.id >= bitset.size() || !bitset[b.id]) continue;
+    for (const Chunk& c : b.chunks)
+      if (c.second > min_offset) out.push_back({std::max(c.first, min_offset), c.second});
+  }
+  std::sort(out.begin(), out.end());
+  std::vector<Chunk> merged;
+  for (const Chunk& c : out) {
+    if (!merged.empty() && merged.back().second >= c.first) merged.back().second = std::max(merged.back().second, c.second);
+    else merged.push_back(c);
+  }
+  return merged;
+}
+
+// BamReadFilter.findNext for several regions of one reference (randomaccessmanager.d:396-450): the region pointer only
+// moves forward, when a read starts at or beyond the current region's end
+void regions_filter(const std::vector<RegionRead>& in, uint32_t ref_id, const std::vector<std::pair<uint32_t, uint32_t>>& regions,
+                    std::vector<RegionRead>* out) {
+  size_t k = 0;
+  for (size_t i = 0; i < in.size();) {
+    const RegionRead& r = in[i];
+    const uint32_t cur = (uint32_t)r.ref_id;
+    if (cur > ref_id) return;
+    if (cur < ref_id) { ++i; continue; }
+    if ((uint32_t)r.pos >= regions[k].second) {
+      if (++k == regions.size()) return;
+      continue;                                                 // the same read against the next region
+    }
+    if ((uint32_t)r.pos > regions[k].first) { out->push_back(r); ++i; continue; }
+    if ((uint32_t)(r.pos + (r.end_pos - r.pos)) <= regions[k].first) { ++i; continue; }
+    out->push_back(r);
+    ++i;
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------ C API ----
@@ -1188,6 +1249,57 @@ int64_t orc_region_reads(orc_bam* s, const orc_bai* b, uint32_t ref_id, uint32_t
     if (end_vo) end_vo[k] = keep[k].end_vo;
   }
   return (int64_t)keep.size();
+}
+// getGroupChunks for the (sorted, non-overlapping) regions of one reference: the chunk list, for the tests of the
+// product's biodb_index_regions_chunks
+int64_t orc_group_chunks(const orc_bai* b, uint32_t ref_id, uint64_t n, const uint32_t* begs, const uint32_t* ends, uint64_t* out2, uint64_t cap) {
+  std::vector<std::pair<uint32_t, uint32_t>> group;
+  for (uint64_t k = 0; k < n; ++k) group.push_back({begs[k], ends[k]});
+  int st = 0;
+  const std::vector<Chunk> c = group_chunks(b, ref_id, group, &st);
+  if (st) return st;
+  for (uint64_t k = 0; k < c.size() && k < cap; ++k) { out2[2 * k] = c[k].first; out2[2 * k + 1] = c[k].second; }
+  return (int64_t)c.size();
+}
+// getReads(BamRegion[]) (:316-337): regions sorted, grouped by reference, overlapping ones joined (nonOverlapping:
+// prev.end >= next.start); per group filteredReads (:286-296); the groups one after the other.  Regions: n triples
+// (ref_id, start, end).  Output as orc_region_reads.
+int64_t orc_regions_reads(orc_bam* s, const orc_bai* b, const uint32_t* regions3, uint64_t n, int64_t* index,
+                          uint64_t* start_vo, uint64_t* end_vo, uint64_t cap) {
+  struct Rg { uint32_t ref, beg, end; };
+  std::vector<Rg> rg(n);
+  for (uint64_t k = 0; k < n; ++k) rg[k] = Rg{regions3[3 * k], regions3[3 * k + 1], regions3[3 * k + 2]};
+  std::sort(rg.begin(), rg.end(), [](const Rg& a, const Rg& c) {               // BamRegion.opCmp (region.d)
+    if (a.ref != c.ref) return a.ref < c.ref;
+    if (a.beg != c.beg) return a.beg < c.beg;
+    return a.end < c.end;
+  });
+  uint64_t total = 0;
+  for (size_t i = 0; i < rg.size();) {
+    size_t j = i;
+    std::vector<std::pair<uint32_t, uint32_t>> group;
+    for (; j < rg.size() && rg[j].ref == rg[i].ref; ++j) {
+      if (!group.empty() && group.back().second >= rg[j].beg) group.back().second = std::max(group.back().second, rg[j].end);
+      else group.push_back({rg[j].beg, rg[j].end});
+    }
+    int st = 0;
+    const std::vector<Chunk> c = group_chunks(b, rg[i].ref, group, &st);
+    if (st) return st;
+    std::vector<RegionRead> all, keep;
+    st = chunk_stream_reads(s, c, ~0ull, &all);
+    if (st) return st;
+    regions_filter(all, rg[i].ref, group, &keep);
+    for (const RegionRead& r : keep) {
+      if (total < cap) {
+        index[total] = r.index;
+        if (start_vo) start_vo[total] = r.start_vo;
+        if (end_vo) end_vo[total] = r.end_vo;
+      }
+      ++total;
+    }
+    i = j;
+  }
+  return (int64_t)total;
 }
 // getReadsBetween(from, to) (:186-196)
 int64_t orc_reads_between(orc_bam* s, uint64_t from_vo, uint64_t to_vo, int64_t* index, uint64_t cap) {

@@ -374,6 +374,38 @@ def region_reads(bam, bai, ref_id, beg, end):
     return idx[:n].copy(), sv[:n].copy(), ev[:n].copy()
 
 
+def group_chunks(bai, ref_id, regions):
+    """getGroupChunks (randomaccessmanager.d:246-296) for sorted, non-overlapping regions [(start, end), ...] of one
+    reference: [(beg voffset, end voffset), ...]."""
+    L = bai._L if hasattr(bai, "_L") else lib()
+    begs = np.array([a for a, _ in regions], dtype=np.uint32)
+    ends = np.array([b for _, b in regions], dtype=np.uint32)
+    L.orc_group_chunks.restype = C.c_int64
+    L.orc_group_chunks.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    cap = 1 << 16
+    out = np.zeros(2 * cap, dtype=np.uint64)
+    n = int(L.orc_group_chunks(bai._h, ref_id, len(begs), begs.ctypes.data, ends.ctypes.data, out.ctypes.data, cap))
+    if n < 0:
+        raise OracleError(n, "group chunks failed")
+    return [(int(out[2 * k]), int(out[2 * k + 1])) for k in range(n)]
+
+
+def regions_reads(bam, bai, regions):
+    """getReads(BamRegion[]) (randomaccessmanager.d:316-337): regions = [(ref_id, start, end), ...] in any order.
+    Returns (record indices, start voffsets, end voffsets)."""
+    cap = max(16, 2 * bam.n_records + 16)
+    idx = np.zeros(cap, dtype=np.int64)
+    sv = np.zeros(cap, dtype=np.uint64)
+    ev = np.zeros(cap, dtype=np.uint64)
+    rg = np.ascontiguousarray(np.array(regions, dtype=np.uint32).reshape(-1, 3))
+    bam._L.orc_regions_reads.restype = C.c_int64
+    bam._L.orc_regions_reads.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    n = int(bam._L.orc_regions_reads(bam._h, bai._h, rg.ctypes.data, len(rg), idx.ctypes.data, sv.ctypes.data, ev.ctypes.data, cap))
+    if n < 0:
+        raise OracleError(n, "multi-region read failed")
+    return idx[:n].copy(), sv[:n].copy(), ev[:n].copy()
+
+
 def reads_between(bam, from_vo, to_vo):
     """getReadsBetween (randomaccessmanager.d:186-196): record indices."""
     cap = max(16, bam.n_records + 16)

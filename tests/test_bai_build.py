@@ -95,3 +95,42 @@ def test_builder_errors():
         class NoOffsets:
             start_voffset = None
         IndexBuilder(1).put(NoOffsets())
+
+
+def _parse_bai(raw):
+    import struct
+    assert raw[:4] == b"BAI\1"
+    n, p, refs = struct.unpack_from("<i", raw, 4)[0], 8, []
+    for _ in range(n):
+        nb = struct.unpack_from("<i", raw, p)[0]
+        p += 4
+        bins = {}
+        for _ in range(nb):
+            bid, nc = struct.unpack_from("<Ii", raw, p)
+            p += 8
+            bins[bid] = [struct.unpack_from("<QQ", raw, p + 16 * k) for k in range(nc)]
+            p += 16 * nc
+        nl = struct.unpack_from("<i", raw, p)[0]
+        p += 4 + 8 * nl
+        refs.append(bins)
+    return refs
+
+
+@pytest.mark.parametrize("name", ["ex1_header.bam", "bins.bam", "tags.bam"])
+def test_bins_and_chunks_agree_with_the_fixture_indexes_of_another_tool(name):
+    """An outside check (not a pin of indexing.d, which no reference test exercises): the reference's test data carries
+    .bai files written by samtools.  Bin by bin, the chunk lists the product's builder writes are the ones samtools
+    wrote, once three habits of that tool are set aside — it tells the END of the file (past the EOF block) as the end
+    offset of the file's last record where BioD's stream tells the EOF block's start; one of the files has empty chunks
+    (begin == end); older files lack the pseudo-bin 37450.  (The linear indexes differ in the entry of the first window,
+    as the module docstring says, and are not compared.)"""
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    mine = _parse_bai(product_index(o, step=500))
+    theirs = _parse_bai(fixture_bytes(name + ".bai"))
+    eof_vo = (len(data) - 28) << 16
+    assert len(mine) == len(theirs)
+    for a, b in zip(mine, theirs):
+        a = {k: v for k, v in a.items() if k != 37450}
+        b = {k: [(x, min(y, eof_vo)) for x, y in v if x != y] for k, v in b.items() if k != 37450}
+        assert a == {k: v for k, v in b.items() if v}

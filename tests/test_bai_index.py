@@ -101,3 +101,57 @@ def test_last_linear_offset():
             out = C.c_uint64()
             got = L.biodb_index_last_linear_offset(ix._h, n, C.byref(out))
             assert (int(out.value) if got else None) == want, (name, n)
+
+
+def merged_groups(regions):
+    """regions [(ref, start, end), ...] -> {ref: [(start, end), ...]} sorted, overlapping ones joined (algo.d:95-162)."""
+    by = {}
+    for r, a, b in sorted(regions):
+        g = by.setdefault(r, [])
+        if g and g[-1][1] >= a:
+            g[-1][1] = max(g[-1][1], b)
+        else:
+            g.append([a, b])
+    return {r: [tuple(x) for x in g] for r, g in by.items()}
+
+
+def random_regions(rng, o, n_max=6, span=None):
+    out = []
+    for _ in range(int(rng.integers(1, n_max + 1))):
+        r = int(rng.integers(0, len(o.ref_names)))
+        a = int(rng.integers(0, max(1, o.ref_lens[r])))
+        b = a + 1 + int(rng.integers(0, span or max(1, o.ref_lens[r])))
+        out.append((r, a, b))
+    return out
+
+
+@pytest.mark.parametrize("name", ["bins.bam", "ex1_header.bam", "tags.bam"])
+def test_multi_region_reads_of_the_oracle_and_group_chunks(name):
+    """getReads(BamRegion[]) (randomaccessmanager.d:246-296,316-337; no reference test exercises it): the oracle's
+    restatement returns, per reference, the sorted union of what the single-region reads of the merged regions return —
+    every read once — and the product's chunk lists (biodb_index_regions_chunks) are the oracle's."""
+    import ctypes as C
+    from biod_b200 import BaiFile
+    o = orc.Bam(fixture_bytes(name)).decode()
+    raw = fixture_bytes(name + ".bai")
+    bai = orc.Bai(raw)
+    ix = BaiFile(raw)
+    rng = np.random.default_rng(41)
+    for trial in range(60):
+        regions = random_regions(rng, o, span=3000 if trial % 2 else None)
+        got = [int(i) for i in orc.regions_reads(o, bai, regions)[0]]
+        want = []
+        for r, group in sorted(merged_groups(regions).items()):
+            one = set()
+            for a, b in group:
+                one |= set(int(i) for i in orc.region_reads(o, bai, r, a, b)[0])
+            want += sorted(one)
+            # the product's chunks for this group
+            begs = np.array([a for a, _ in group], dtype=np.uint32)
+            ends = np.array([b for _, b in group], dtype=np.uint32)
+            n = int(ix._L.biodb_index_regions_chunks(ix._h, r, len(begs), begs.ctypes.data, ends.ctypes.data, None, 0))
+            out = np.zeros(2 * max(n, 1), dtype=np.uint64)
+            ix._L.biodb_index_regions_chunks(ix._h, r, len(begs), begs.ctypes.data, ends.ctypes.data, out.ctypes.data, n)
+            assert [(int(out[2 * k]), int(out[2 * k + 1])) for k in range(n)] == orc.group_chunks(bai, r, group), (name, regions)
+        assert got == want, (name, regions)
+    ix.close()

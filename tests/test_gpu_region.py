@@ -229,3 +229,38 @@ def test_unmapped_reads_and_eof_offset():
     data = fixture_bytes("ex1_header.bam")
     rd = BamReader(data, want_offsets=True, index=fixture_bytes("ex1_header.bam.bai"))
     assert list(rd.unmappedReads()) == []
+
+
+@pytest.mark.parametrize("name,bpb", [("bins.bam", 0), ("bins.bam", 1), ("ex1_header.bam", 0), ("tags.bam", 0)])
+def test_reads_overlapping_several_regions(name, bpb):
+    """getReadsOverlapping(BamRegion[]) (reader.d:361, randomaccessmanager.d:316-337): regions in any order, overlapping
+    ones among them, several references — the same reads as the oracle's restatement, every read once, raw bytes and
+    virtual offsets included."""
+    from biod_b200 import BamReader
+    from test_bai_index import random_regions
+    data = fixture_bytes(name)
+    o = orc.Bam(data).decode()
+    raw_bai = fixture_bytes(name + ".bai")
+    bai = orc.Bai(raw_bai)
+    rd = BamReader(data, blocks_per_batch=bpb, want_offsets=True, index=raw_bai)
+    rng = np.random.default_rng(43)
+    some = 0
+    for trial in range(25):
+        regions = random_regions(rng, o, span=3000 if trial % 2 else None)
+        idx, wsv, wev = orc.regions_reads(o, bai, regions)
+        raws, sv, ev = [], [], []
+        for b in rd.regions_batches(regions, copy=True):
+            for i in range(b.n):
+                p = int(b.rec_off[i]) + 4
+                raws.append(b.data[p:p + int(b.block_size[i])].tobytes())
+            sv += b.start_voffset.tolist()
+            ev += b.end_voffset.tolist()
+        assert len(raws) == len(idx), (name, regions, len(raws), len(idx))
+        assert raws == [o.record_bytes(int(i)).tobytes() for i in idx], (name, regions)
+        assert sv == wsv.tolist() and ev == wev.tolist(), (name, regions)
+        some += len(idx)
+    assert some > 0
+    got = [r.raw.tobytes() for r in rd.getReadsOverlapping([(0, 0, 50), (0, 20, 80)])]
+    assert got == [o.record_bytes(int(i)).tobytes() for i in orc.regions_reads(o, bai, [(0, 0, 50), (0, 20, 80)])[0]]
+    with pytest.raises(Exception):
+        list(rd.getReadsOverlapping([(0, 10, 10)]))
