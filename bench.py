@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--cpu-sample-reads", type=int, default=2_000_000)
     ap.add_argument("--straddle", action="store_true", help="htsjdk-style file: records cut across BGZF blocks")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-shards", default="weighted", choices=["weighted", "equal"],
+                    help="N > 1, e2e legs: shares of the file in proportion to each rank's measured device->host rate, or equal")
     ap.add_argument("--e2e-input", default="memory", choices=["memory", "file"],
                     help="e2e leg: the caller's buffer (biodb_open_memory; page-locked whole at N = 1, the shard's range at N > 1) "
                          "or the file itself (biodb_open: pread into the library's pinned slabs)")
@@ -181,8 +183,9 @@ class ClockSampler:
 
 
 def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False, halo_voffset=None, maq=False, calls=None):
-    """One full pileup pass (pileupColumns); shard=(rank, world) runs this rank's shard of it (halo guessed at 8 BGZF
-    blocks, or starting at halo_voffset).  Returns (stats, n_records, n_cols, n_entries)."""
+    """One full pileup pass (pileupColumns); shard=(rank, world) runs this rank's shard of it, shard=(first, n, count) the
+    shards [first, first + count) of n (halo guessed at 8 BGZF blocks, or starting at halo_voffset).
+    Returns (stats, n_records, n_cols, n_entries)."""
     p = capi.PileupParams()
     p.single_ref, p.skip_zero_coverage, p.end_at = 0, 1, 2**64 - 1
     p.compact_reads = int(compact)
@@ -190,10 +193,11 @@ def run_pass(L, capi, reader, shard=None, info=None, compact=False, use_md=False
     p.maq_mode = 1 if maq else 0
     pl = C.c_void_p()
     sharded = shard is not None and shard[1] > 1
+    count = shard[2] if sharded and len(shard) > 2 else 1       # shard=(first, n_shards, count): a span of shards as one pass
     if sharded and halo_voffset is not None:
-        st = L.biodb_pileup_begin_shard_at(reader, C.byref(p), shard[0], shard[1], int(halo_voffset), C.byref(pl))
+        st = L.biodb_pileup_begin_shard_span_at(reader, C.byref(p), shard[0], count, shard[1], int(halo_voffset), C.byref(pl))
     elif sharded:
-        st = L.biodb_pileup_begin_shard(reader, C.byref(p), shard[0], shard[1], 8, C.byref(pl))
+        st = L.biodb_pileup_begin_shard_span(reader, C.byref(p), shard[0], count, shard[1], 8, C.byref(pl))
     else:
         st = L.biodb_pileup_begin(reader, C.byref(p), C.byref(pl))
     if st != capi.OK:
@@ -286,6 +290,39 @@ def cpu_reference_block(args, config, cfg, threads, runs=1):
            "note": "restated BioD CPU path (libz, g++ -O3), not the D binary: no D toolchain in this image" +
                    ("" if not d_compilers else f" (found on the box: {d_compilers}; not used)")}
     return blk, t_full * 1e3, r
+
+
+def link_shares(torch, dist, world, per_rank=4):
+    """Shares of the end-to-end pass for ranks whose host links are not equally fast (on this pool's 8-GPU node four GPUs
+    copy device->host at 11 GB/s and four at 18 GB/s when all copy at once, tools/pcie_bw.py): every rank copies 256 MiB
+    device->host four times, all ranks at the same time; the file is cut into per_rank * world shards and rank r gets a
+    run of them in proportion to its rate (at least one).  Returns (first shard of every rank, counts, GB/s per rank)."""
+    n = 256 << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device="cuda")
+    h.copy_(d, non_blocking=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(4):
+        h.copy_(d, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    mine = torch.tensor([4 * n / (a.elapsed_time(b) * 1e-3) / 1e9], dtype=torch.float64, device="cuda")
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    gbs = [float(v[0]) for v in allv]
+    n_fine = per_rank * world
+    raw = [n_fine * g / sum(gbs) for g in gbs]
+    counts = [max(1, int(round(x))) for x in raw]
+    while sum(counts) != n_fine:                      # settle the rounding on the rank it distorts least
+        over = sum(counts) > n_fine
+        k = max((i for i in range(world) if not over or counts[i] > 1),
+                key=lambda i: (counts[i] - raw[i]) if over else (raw[i] - counts[i]))
+        counts[k] += -1 if over else 1
+    firsts = [sum(counts[:k]) for k in range(world)]
+    return firsts, counts, gbs
 
 
 def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, barrier, steps, warmup, want_e2e, want_reads_pass,
@@ -385,6 +422,21 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
         # only the byte range of its own shard (+ halo), on demand
         from_file = args.e2e_input == "file"
         rd = open_reader(False, False, 1 if world == 1 else 2, from_file)
+        # N > 1: the shares of this leg follow the ranks' host-link speeds (link_shares); the device-resident leg above
+        # keeps equal shards
+        shares = None
+        if world > 1 and args.e2e_shards == "weighted":
+            firsts, counts, gbs = link_shares(torch, dist, world)
+            shard = (firsts[rank], sum(counts), counts[rank])
+            shares = {"shards": sum(counts), "per_rank": counts, "probe_d2h_gbs": [round(g, 1) for g in gbs]}
+
+            def exact_halo_pass(rd, info, **kw):                # the same exchange over spans: a span's halo must reach
+                t0 = time.time()                                # back to what reaches its FIRST shard
+                rows, used = gather_reach(info["reach"], info["halo_voffset"], device="cuda")
+                need, redo = exact_halos([[row[a] for a in firsts] for row in rows], used)
+                ms = (time.time() - t0) * 1e3
+                res = run_pass(L, capi, rd, shard, info, halo_voffset=need[rank], **kw) if rank in redo else None
+                return res, {"exact": True, "rerun_shards": redo, "exchange_ms": ms}
         einfo = {}
         run_pass(L, capi, rd, shard, einfo, compact=True)
         input_pinned = bool(L.biodb_input_is_pinned(rd)) or from_file
@@ -398,9 +450,10 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
         # the fused consumer (row N3): MAQ genotype likelihoods of every column computed on the device behind the pileup
         # (reference bases from the MD tags), only the SNP calls copied back — MaqSnpCaller.findSNPs end to end
         minfo, ncalls = {}, []
-        run_pass(L, capi, rd, shard, minfo, use_md=True, maq=True)
+        shard_eq = (rank, world)      # (equal shards: this pass is bound by GPU and host work, not by the link)
+        run_pass(L, capi, rd, shard_eq, minfo, use_md=True, maq=True)
         barrier()
-        mq = [run_pass(L, capi, rd, shard, minfo, use_md=True, maq=True, calls=ncalls) for _ in range(steps)]
+        mq = [run_pass(L, capi, rd, shard_eq, minfo, use_md=True, maq=True, calls=ncalls) for _ in range(steps)]
         barrier()
         rp = None
         if want_reads_pass and world == 1:
@@ -410,13 +463,18 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
         L.biodb_close(rd)
         e_ms = sum(s[0].total_ms for s in es)
         te = torch.tensor([e_ms, e_rerun], dtype=torch.float64, device="cuda")
+        tb = torch.tensor([float(es[-1][0].h2d_bytes), float(es[-1][0].d2h_bytes)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         e_ms = float(te[0]) / steps + float(te[1])
+        h2d_all, d2h_all = int(tb[0]), int(tb[1])
         out["e2e"] = {"value": tot_col / (e_ms * 1e-3), "unit": "positions/s", "ms_per_step": e_ms,
                       "h2d_bytes_per_step": int(es[-1][0].h2d_bytes), "d2h_bytes_per_step": int(es[-1][0].d2h_bytes),
+                      "h2d_bytes_all_ranks": h2d_all, "d2h_bytes_all_ranks": d2h_all,
                       "records_per_sec": tot_rec / (e_ms * 1e-3), "input_pinned": input_pinned, "input": args.e2e_input,
-                      "pcie_d2h_gbs": es[-1][0].d2h_bytes / (e_ms * 1e-3) / 1e9,
+                      "shares": shares,
+                      "pcie_d2h_gbs": d2h_all / world / (e_ms * 1e-3) / 1e9,      # per GPU, averaged over the ranks
                       "stage_ms": {"inflate": float(np.mean([s[0].inflate_ms for s in es])),
                                    "record_scan": float(np.mean([s[0].scan_ms for s in es])),
                                    "pileup": float(np.mean([s[0].pileup_ms for s in es]))},

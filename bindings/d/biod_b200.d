@@ -89,6 +89,10 @@ extern (C) nothrow @nogc {
     int biodb_pileup_begin_shard(biodb_reader*, const(biodb_pileup_params)*, uint shard, uint n_shards, uint halo_blocks, biodb_pileup**);
     int biodb_pileup_begin_shard_at(biodb_reader*, const(biodb_pileup_params)*, uint shard, uint n_shards, ulong halo_voffset,
                                     biodb_pileup**);
+    int biodb_pileup_begin_shard_span(biodb_reader*, const(biodb_pileup_params)*, uint first, uint count, uint n_shards,
+                                      uint halo_blocks, biodb_pileup**);
+    int biodb_pileup_begin_shard_span_at(biodb_reader*, const(biodb_pileup_params)*, uint first, uint count, uint n_shards,
+                                         ulong halo_voffset, biodb_pileup**);
     void biodb_pileup_shard_info(const(biodb_pileup)*, biodb_shard_info*);
     void biodb_pileup_shard_reach(const(biodb_pileup)*, ulong* reach);
     int biodb_pileup_begin_range(biodb_reader*, const(biodb_pileup_params)*, ulong from_voffset, ulong to_voffset,
@@ -102,6 +106,8 @@ extern (C) nothrow @nogc {
     int biodb_index_n_refs(const(biodb_index)*);
     long biodb_index_chunks(const(biodb_index)*, uint ref_id, uint beg, uint end, ulong* out2, ulong cap);
     int biodb_reads_begin_region(biodb_reader*, const(biodb_index)*, uint ref_id, uint beg, uint end, biodb_reads**);
+    int biodb_reads_begin_regions(biodb_reader*, const(biodb_index)*, uint ref_id, uint n, const(uint)* begs, const(uint)* ends,
+                                  biodb_reads**);
     int biodb_reads_begin_between(biodb_reader*, ulong from_voffset, ulong to_voffset, uint max_blocks, biodb_reads**);
     int biodb_pileup_begin_region(biodb_reader*, const(biodb_index)*, uint ref_id, uint beg, uint end,
                                   const(biodb_pileup_params)*, biodb_pileup**);
@@ -159,6 +165,14 @@ struct GpuBamReadRange(bool withOffsets = false) {
     this(biodb_reader* h, IBamSamReader reader, const(biodb_index)* ix, uint ref_id, uint beg, uint end) {
         _h = h; _reader = reader;
         if (biodb_reads_begin_region(h, ix, ref_id, beg, end, &_it) != BIODB_OK) raise(biodb_last_error(h));
+        fetch();
+    }
+    /// the reads of reference ref_id overlapping any of the regions [begs[k], ends[k]) — one reference group of
+    /// getReads(BamRegion[]) (randomaccessmanager.d:286-296); getReadsOverlapping chains the groups (:316-337)
+    this(biodb_reader* h, IBamSamReader reader, const(biodb_index)* ix, uint ref_id, const(uint)[] begs, const(uint)[] ends) {
+        _h = h; _reader = reader;
+        if (biodb_reads_begin_regions(h, ix, ref_id, cast(uint)begs.length, begs.ptr, ends.ptr, &_it) != BIODB_OK)
+            raise(biodb_last_error(h));
         fetch();
     }
     ~this() { if (_it !is null) { biodb_reads_end(_it); _it = null; } }

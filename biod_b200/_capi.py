@@ -118,6 +118,10 @@ def lib():
     L.biodb_pileup_shard_info.argtypes = [vp, C.POINTER(ShardInfo)]
     L.biodb_pileup_begin_shard_at.restype = C.c_int
     L.biodb_pileup_begin_shard_at.argtypes = [vp, C.POINTER(PileupParams), C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(vp)]
+    L.biodb_pileup_begin_shard_span.restype = C.c_int
+    L.biodb_pileup_begin_shard_span.argtypes = [vp, C.POINTER(PileupParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.biodb_pileup_begin_shard_span_at.restype = C.c_int
+    L.biodb_pileup_begin_shard_span_at.argtypes = [vp, C.POINTER(PileupParams), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(vp)]
     L.biodb_pileup_shard_reach.argtypes = [vp, u64p]
     L.biodb_shard_cuts.restype = C.c_int
     L.biodb_shard_cuts.argtypes = [vp, C.c_uint32, u64p, C.POINTER(C.c_int32), C.POINTER(C.c_int64)]
@@ -212,7 +216,7 @@ EXPORTS = [
     "biodb_open_error", "biodb_header_text", "biodb_n_refs", "biodb_ref_info", "biodb_reads_start_voffset",
     "biodb_file_size", "biodb_input_is_pinned", "biodb_reads_begin", "biodb_reads_next", "biodb_reads_end", "biodb_reads_progress",
     "biodb_pileup_begin", "biodb_pileup_next", "biodb_pileup_end", "biodb_pileup_ref_id", "biodb_pileup_totals",
-    "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_begin_shard_at", "biodb_pileup_shard_info",
+    "biodb_reads_stats", "biodb_pileup_stats", "biodb_pileup_begin_shard", "biodb_pileup_begin_shard_at", "biodb_pileup_begin_shard_span", "biodb_pileup_begin_shard_span_at", "biodb_pileup_shard_info",
     "biodb_pileup_shard_reach", "biodb_shard_cuts", "biodb_pileup_begin_range", "biodb_pileup_maq_params",
     "biodb_dev_inflate", "biodb_dev_scan_records", "biodb_dev_scan_workspace_bytes", "biodb_debug_inflate_counters", "biodb_debug_md_chain",
     "biodb_debug_md_dna", "biodb_index_open", "biodb_index_close", "biodb_index_n_refs", "biodb_index_chunks", "biodb_index_regions_chunks", "biodb_reads_begin_regions", "biodb_index_last_linear_offset", "biodb_index_builder_begin", "biodb_index_builder_put",

@@ -503,7 +503,8 @@ class BamReader:
     def column_batches(self, single_ref, use_md_tag=False, start_from=0, end_at=2**64 - 1, skip_zero_coverage=True,
                        want_query_offset=False, copy=False, shard=None, halo_blocks=8, halo_voffset=None, shard_info=None,
                        counts_only=False, compact_reads=False, region=None, record_range=None, maq=None, maq_mode=0):
-        """shard=(index, count) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015): its halo
+        """shard=(index, n_shards) runs one shard of a sharded pileup (pileupChunks semantics, pileup.d:859-1015) — or
+        shard=(first, n_shards, count) the shards [first, first + count) as one pass: its halo
         starts halo_blocks BGZF blocks in front of it (a guess) or at the record at halo_voffset; shard_info receives
         the biodb_shard_info fields plus "reach" (see biod_b200.stitch.exact_halos).
         region=(ref_id, start, end) piles up the reads of bam[ref][start .. end) only (read_idx then counts those).
@@ -522,9 +523,11 @@ class BamReader:
         elif record_range is not None:
             st = L.biodb_pileup_begin_range(self._h, C.byref(p), *[int(x) for x in record_range], C.byref(pl))
         elif shard is not None and halo_voffset is not None:
-            st = L.biodb_pileup_begin_shard_at(self._h, C.byref(p), shard[0], shard[1], int(halo_voffset), C.byref(pl))
+            st = L.biodb_pileup_begin_shard_span_at(self._h, C.byref(p), shard[0], shard[2] if len(shard) > 2 else 1, shard[1],
+                                                    int(halo_voffset), C.byref(pl))
         elif shard is not None:
-            st = L.biodb_pileup_begin_shard(self._h, C.byref(p), shard[0], shard[1], halo_blocks, C.byref(pl))
+            st = L.biodb_pileup_begin_shard_span(self._h, C.byref(p), shard[0], shard[2] if len(shard) > 2 else 1, shard[1],
+                                                 halo_blocks, C.byref(pl))
         else:
             st = L.biodb_pileup_begin(self._h, C.byref(p), C.byref(pl))
         if st == capi.ERR_ARG:
@@ -572,15 +575,19 @@ class BamReader:
         at once from a guess and biod_b200.stitch.exact_halos says which to run again).  Yields (shard, batch)."""
         need = [2**64 - 1] * n_shards
         cuts = self.shard_cuts(n_shards)
-        for s in range(n_shards):
+        spans = kw.pop("spans", None) or [1] * n_shards        # spans=[2, 1, 4]: shards 0-1, 2, 3-6 as three passes
+        assert sum(spans) == n_shards and all(c > 0 for c in spans)
+        s = 0
+        for count in spans:
             info = {}
             hv = min(need[s], cuts[s][0])
-            for b in self.column_batches(False, shard=(s, n_shards), halo_voffset=hv, shard_info=info, **kw):
+            for b in self.column_batches(False, shard=(s, n_shards, count), halo_voffset=hv, shard_info=info, **kw):
                 yield s, b
-            for t in range(s + 1, n_shards):
+            for t in range(s + count, n_shards):
                 need[t] = min(need[t], info["reach"][t])
             if shard_infos is not None:
                 shard_infos.append(info)
+            s += count
 
 
 def _popcount64(x):

@@ -80,7 +80,7 @@ struct biodb_pileup {
   biodb_shard_info shard{};
   bool own_reached = false;          // the first own record has been met: index_bias is final
   uint64_t index_bias = 0;           // records of the halo: read_idx counts from the first record read
-  uint32_t shard_index = 0, shard_count = 0;
+  uint32_t shard_index = 0, shard_count = 0, shard_last = 0;   // the pass covers shards [shard_index, shard_last)
   std::vector<int32_t> later_ref;    // (ref, pos) of the cuts behind this shard, i.e. of shards shard_index+1 ...
   std::vector<int64_t> later_pos;
   std::vector<uint64_t> reach;       // [shard_count] first own record reaching into each later shard (voffset), ~0 = none
@@ -316,7 +316,7 @@ static biodb_status load_batch(biodb_pileup* pl) {
       PL_TRY(cudaStreamSynchronize(p.st));
       const uint64_t* hr = pl->h_reach.as<uint64_t>();
       for (uint32_t k = 0; k < nk; ++k) {
-        uint64_t& slot = pl->reach[pl->shard_index + 1 + k];
+        uint64_t& slot = pl->reach[pl->shard_last + k];
         if (hr[k] != ~0ull && slot == ~0ull) slot = p.voffset_of(hr[k]);   // batches come in file order: the first hit is the minimum
       }
     }
@@ -415,7 +415,7 @@ void biodb_pileup::reset(const biodb_pileup_params* p) {
   memset(&shard, 0, sizeof shard);
   own_reached = false;
   index_bias = 0;
-  shard_index = shard_count = 0;
+  shard_index = shard_count = shard_last = 0;
   later_ref.clear();
   later_pos.clear();
   reach.clear();
@@ -677,13 +677,16 @@ biodb_status biodb_pileup_begin_range(biodb_reader* r, const biodb_pileup_params
   return begin_clipped(r, prm, from_voffset, from_voffset, to_voffset, lo_ref, lo_pos, hi_ref, hi_pos, out);
 }
 
-static biodb_status begin_shard_common(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
-                                       bool by_blocks, uint32_t halo_blocks, uint64_t halo_vo, biodb_pileup** out) {
-  if (!r || !out || n_shards == 0 || shard >= n_shards) return BIODB_ERR_ARG;
+// shards [shard, shard + count) of n_shards as ONE pass (count = 1: a single shard)
+static biodb_status begin_shard_common(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t count,
+                                       uint32_t n_shards, bool by_blocks, uint32_t halo_blocks, uint64_t halo_vo,
+                                       biodb_pileup** out) {
+  if (!r || !out || n_shards == 0 || count == 0 || shard >= n_shards || count > n_shards - shard) return BIODB_ERR_ARG;
+  const uint32_t last = shard + count;                    // first shard behind the span
   const biodb_reader::ShardCuts* c = nullptr;
   biodb_status s = shard_cuts(r, n_shards, &c);
   if (s != BIODB_OK) return s;
-  const uint64_t own = c->vo[shard], end = c->vo[shard + 1];
+  const uint64_t own = c->vo[shard], end = c->vo[last];
   uint64_t from = own;
   if (shard > 0 && by_blocks && halo_blocks) {
     // a guess: the halo starts halo_blocks BGZF blocks in front of the block the shard's first record starts in
@@ -703,13 +706,14 @@ static biodb_status begin_shard_common(biodb_reader* r, const biodb_pileup_param
   // shard 0 also owns whatever precedes its first record's position; the last shard everything to the end
   const int32_t lo_ref = shard == 0 ? 0 : c->ref[shard];
   const int64_t lo_pos = shard == 0 ? INT64_MIN : c->pos[shard];
-  s = begin_clipped(r, prm, from, own, end, lo_ref, lo_pos, c->ref[shard + 1], c->pos[shard + 1], out);
+  s = begin_clipped(r, prm, from, own, end, lo_ref, lo_pos, c->ref[last], c->pos[last], out);
   if (s != BIODB_OK) return s;
   biodb_pileup* pl = *out;
   pl->shard_index = shard;
   pl->shard_count = n_shards;
   pl->reach.assign(n_shards, ~0ull);
-  for (uint32_t t = shard + 1; t < n_shards; ++t) { pl->later_ref.push_back(c->ref[t]); pl->later_pos.push_back(c->pos[t]); }
+  pl->shard_last = last;
+  for (uint32_t t = last; t < n_shards; ++t) { pl->later_ref.push_back(c->ref[t]); pl->later_pos.push_back(c->pos[t]); }
   const size_t nk = pl->later_ref.size();
   if (nk) {
     const size_t poff = (nk * 4 + 7) & ~(size_t)7;
@@ -728,12 +732,22 @@ static biodb_status begin_shard_common(biodb_reader* r, const biodb_pileup_param
 
 biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
                                       uint32_t halo_blocks, biodb_pileup** out) {
-  return begin_shard_common(r, prm, shard, n_shards, true, halo_blocks, 0, out);
+  return begin_shard_common(r, prm, shard, 1, n_shards, true, halo_blocks, 0, out);
 }
 
 biodb_status biodb_pileup_begin_shard_at(biodb_reader* r, const biodb_pileup_params* prm, uint32_t shard, uint32_t n_shards,
                                          uint64_t halo_voffset, biodb_pileup** out) {
-  return begin_shard_common(r, prm, shard, n_shards, false, 0, halo_voffset, out);
+  return begin_shard_common(r, prm, shard, 1, n_shards, false, 0, halo_voffset, out);
+}
+
+biodb_status biodb_pileup_begin_shard_span(biodb_reader* r, const biodb_pileup_params* prm, uint32_t first, uint32_t count,
+                                           uint32_t n_shards, uint32_t halo_blocks, biodb_pileup** out) {
+  return begin_shard_common(r, prm, first, count, n_shards, true, halo_blocks, 0, out);
+}
+
+biodb_status biodb_pileup_begin_shard_span_at(biodb_reader* r, const biodb_pileup_params* prm, uint32_t first, uint32_t count,
+                                              uint32_t n_shards, uint64_t halo_voffset, biodb_pileup** out) {
+  return begin_shard_common(r, prm, first, count, n_shards, false, 0, halo_voffset, out);
 }
 
 void biodb_pileup_shard_info(const biodb_pileup* pl, biodb_shard_info* out) {

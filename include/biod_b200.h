@@ -308,6 +308,14 @@ biodb_status biodb_pileup_begin_shard(biodb_reader* r, const biodb_pileup_params
 /* The same shard with its halo starting at the record at halo_voffset (<= the shard's first record). */
 biodb_status biodb_pileup_begin_shard_at(biodb_reader* r, const biodb_pileup_params* p, uint32_t shard, uint32_t n_shards,
                                          uint64_t halo_voffset, biodb_pileup** out);
+/* Shards [first, first + count) of n_shards as ONE pass: own records from cut `first` to cut `first + count`.  With
+ * n_shards a multiple of the number of workers this hands workers unequal shares of one file (bench.py sizes the shares of
+ * the end-to-end pass by each GPU's measured host-link speed) while every cut stays one of the n_shards + 1 cuts all workers
+ * agree on.  _shard_reach then reports the later cuts t >= first + count. */
+biodb_status biodb_pileup_begin_shard_span(biodb_reader* r, const biodb_pileup_params* p, uint32_t first, uint32_t count,
+                                           uint32_t n_shards, uint32_t halo_blocks, biodb_pileup** out);
+biodb_status biodb_pileup_begin_shard_span_at(biodb_reader* r, const biodb_pileup_params* p, uint32_t first, uint32_t count,
+                                              uint32_t n_shards, uint64_t halo_voffset, biodb_pileup** out);
 void biodb_pileup_shard_info(const biodb_pileup* pl, biodb_shard_info* out);
 /* reach[t], t in (shard, n_shards): virtual offset of the first OWN record of this shard that reaches into the columns
  * of shard t, UINT64_MAX if none does; entries t <= shard are UINT64_MAX.  Valid at EOF.  `reach` has n_shards elements. */

@@ -67,18 +67,23 @@ def assert_pileup_equal(g, o):
     assert np.array_equal(g["qoff"], o.qoff)
 
 
-def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, exact=True, **kw):
+def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, exact=True, spans=None, **kw):
     """Run every shard of a sharded pileup (one after the other on this GPU) and stitch the column tables the way
     biod_b200.stitch does across ranks: concatenate in shard order, rebase read_idx by the record counts.
     exact=True: the shards run the way several GPUs run them — all from the halo_blocks guess, then exact_halos says which
-    halos were too short and those shards run again from the exact offset (res["redone"]).  exact=False: the guess only."""
+    halos were too short and those shards run again from the exact offset (res["redone"]).  exact=False: the guess only.
+    spans=[2, 1, 4]: the shards are run as passes over shards 0-1, 2 and 3-6 (biodb_pileup_begin_shard_span)."""
     from biod_b200.stitch import exact_halos
     rd = BamReader(data, blocks_per_batch=blocks_per_batch)
 
-    def run(s, halo_voffset=None):
+    spans = spans or [1] * n_shards
+    assert sum(spans) == n_shards
+    firsts = [sum(spans[:k]) for k in range(len(spans))]
+
+    def run(k, halo_voffset=None):
         pos, ref, cov, nstart, ridx, base, qual, qoff, refb = [], [], [], [], [], [], [], [], []
         info = {}
-        for b in rd.column_batches(False, want_query_offset=True, copy=True, shard=(s, n_shards), halo_blocks=halo_blocks,
+        for b in rd.column_batches(False, want_query_offset=True, copy=True, shard=(firsts[k], n_shards, spans[k]), halo_blocks=halo_blocks,
                                    halo_voffset=halo_voffset, shard_info=info, **kw):
             pos.append(b.position)
             ref.append(np.full(b.n_columns, b.ref_id, dtype=np.int32))
@@ -93,11 +98,12 @@ def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, exact=
         return (pos, ref, cov, nstart, ridx, base, qual, qoff, refb), info
 
     parts, infos = [], []
-    for s in range(n_shards):
-        part, info = run(s)
+    for k in range(len(spans)):
+        part, info = run(k)
         parts.append(part)
         infos.append(info)
-    need, redo = exact_halos([i["reach"] for i in infos], [i["halo_voffset"] for i in infos])
+    # a span's halo must reach back to the first earlier record that reaches its FIRST shard's columns
+    need, redo = exact_halos([[i["reach"][a] for a in firsts] for i in infos], [i["halo_voffset"] for i in infos])
     if exact:
         for t in redo:
             parts[t], infos[t] = run(t, need[t])

@@ -283,6 +283,25 @@ def test_sharded_pileup_synthetic(skip):
         assert_pileup_equal(g, o.pileup_columns(skip))
 
 
+def test_sharded_pileup_in_spans_of_shards():
+    """biodb_pileup_begin_shard_span: 7 shards run as three passes of 2, 1 and 4 shards (unequal shares of one file for
+    workers of unequal speed) — the same columns as the sequential pass, halos exact."""
+    from gpu_util import gpu_pileup_sharded
+    from tools import bamgen
+    data = bamgen.generate(40000, 2, True, level=1, threads=4).tobytes()
+    o = orc.Bam(data).decode()
+    for spans in ([2, 1, 4], [7], [1, 6], [3, 3, 1]):
+        g = gpu_pileup_sharded(data, 7, halo_blocks=1, blocks_per_batch=9, spans=spans)
+        assert len(g["shards"]) == len(spans) and sum(i["n_own_records"] for i in g["shards"]) == o.n_records
+        assert_pileup_equal(g, o.pileup_columns())
+    from biod_b200 import BamReader
+    rd = BamReader(data, blocks_per_batch=9)
+    n_col = sum(b.n_columns for _, b in rd.sharded_column_batches(7, spans=[2, 1, 4]))
+    assert n_col == o.pileup_columns().n_columns
+    with pytest.raises(ValueError):
+        list(rd.column_batches(False, shard=(5, 7, 3)))
+
+
 def test_sharded_pileup_of_a_straddling_file():
     """htsjdk layout at scale: records cut across BGZF blocks, mixed CIGARs with long N-skips, 6 shards, halo guessed
     at one block — cuts enter through the plausibility search, exact halos repair the guess."""
