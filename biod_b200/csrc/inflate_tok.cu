@@ -9,7 +9,7 @@
 // 32 sub-sequences; lane L decodes sub-sequence L from its nominal first bit, which is almost never the start of a
 // code, yet after a few codes the lane is on the true code chain, and the bit where it crosses into sub-sequence L+1
 // is that sub-sequence's true start.  A second round from the true starts is the real decode; lanes whose predecessor
-// had not synchronised are repaired in further rounds (2.24 rounds per super-chunk of BAM data).
+// had not synchronised are repaired in further rounds (2.24 rounds per super-chunk of BAM data), at most five.
 //
 // Why two kernels.  Huffman decoding is one long dependency chain per warp: measured on the B200, a warp of the decode
 // loop issues one instruction every ~10 cycles whatever else the SM does, so the throughput of an SM is the number of
@@ -22,9 +22,12 @@
 //     SUB_BITS bits lane-parallel (above): round 1 only looks for the points where the
 //     sub-sequences synchronise (code lengths alone: the LUT entry carries the extra-bit count); from round 2 on a lane
 //     decodes from where its predecessor ended and RECORDS what it decodes as 16-bit tokens — literal / length /
-//     distance, one per loop trip — straight into the block's record stream in global memory (64 contiguous bytes per warp
-//     store).  When the chain of lanes is consistent it appends the super-chunk's header (lanes committed, per-lane byte /
-//     match / token counts) and goes on; it never waits for anybody.
+//     distance, two per loop trip: its code and, behind a literal or a short distance, the literal/length code that
+//     follows — straight into the block's record stream in global memory (128 contiguous bytes per warp store).  When the
+//     chain of lanes is consistent it appends the super-chunk's header (lanes committed, per-lane byte / match / token
+//     counts) and goes on; it never waits for anybody.  Sub-sequences shrink when a super-chunk's output would overflow
+//     the resolver's ring (streams of long matches) and grow back; a stream whose codes have one length never
+//     synchronises and is handed to the warp-serial kernel after sixteen super-chunks that got nowhere.
 //   * inflate_resolve_kernel (one warp per block, ~5 KB of shared memory: 32 blocks per SM) walks the record stream:
 //     scans the counts into output offsets, REPLAYS the tokens (literals into the shared-memory output ring, matches
 //     into a list: ~10 instructions per token instead of a Huffman decode), copies the LZ77 matches (in-ring sources in

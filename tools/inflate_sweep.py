@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--max-gib", type=int, default=64)
     ap.add_argument("--reads", type=int, default=4_000_000)
     ap.add_argument("--levels", default="0,1,6")
-    ap.add_argument("--blocks-per-launch", type=int, default=7992)
+    ap.add_argument("--blocks-per-launch", type=int, default=12432)   # 3 waves of the decode kernel
     a = ap.parse_args()
     import torch
     from biod_b200 import _capi
