@@ -98,7 +98,7 @@ def chunk_tables(chunk):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,block_size", [("ex1_header.bam", 20_000), ("bins.bam", 5000), ("mg1655_chunk.bam", 30_000),
+@pytest.mark.parametrize("name,block_size", [("ex1_header.bam", 20_000), ("bins.bam", 20_000), ("mg1655_chunk.bam", 30_000),
                                               ("illu_20_chunk.bam", 1500)])
 @pytest.mark.parametrize("use_md", [False, True])
 def test_chunks_match_the_oracle(name, block_size, use_md):
