@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "inflate_common.cuh"
 
@@ -516,10 +517,34 @@ cudaError_t launch_inflate(const InflateArgs& a, cudaStream_t st) {
     g_kernel_launches += 2;
   } else {
     // callers without a token area of their own (the device-resident stage API, no fused record walk): one is allocated
-    // for the call (stream-ordered) and the blocks go through it slab by slab
-    const uint32_t slab = std::min<uint32_t>(a.n_blocks, 8192);
+    // for the call — stream-ordered, from a pool of this library's own that keeps its memory between calls — and the
+    // blocks go through it in slabs of three waves of the decode kernel
+    static cudaMemPool_t pools[64] = {};
+    static std::mutex pool_mu;
+    int dev = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    cudaMemPool_t pool = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(pool_mu);
+      if (dev >= 0 && dev < 64 && !pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) == cudaSuccess) {
+          uint64_t keep = ~0ull;
+          cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+          pools[dev] = nullptr;
+          cudaGetLastError();
+        }
+      }
+      if (dev >= 0 && dev < 64) pool = pools[dev];
+    }
+    const uint32_t slab = std::min<uint32_t>(a.n_blocks, std::max<uint32_t>(1u, 3u * (uint32_t)std::max(0, inflate_resident_blocks(dev))));
     void* tmp = nullptr;
-    e = cudaMallocAsync(&tmp, inflate_tok_token_bytes(slab), st);
+    e = pool ? cudaMallocFromPoolAsync(&tmp, inflate_tok_token_bytes(slab), pool, st)
+             : cudaMallocAsync(&tmp, inflate_tok_token_bytes(slab), st);
     if (e != cudaSuccess) return e;
     for (uint32_t b0 = 0; b0 < a.n_blocks && e == cudaSuccess; b0 += slab) {
       InflateArgs s = slice_args(a, b0, std::min<uint32_t>(slab, a.n_blocks - b0));

@@ -369,9 +369,12 @@ __global__ void __launch_bounds__(32, BIODB_TOK_DECODE_CTAS) inflate_decode_kern
       cur += REC_HEAD;
       produced += len;
       // the decoder only skips the bytes, but the staging ring has to pass them: its chunks are issued and waited for
-      // strictly in order (the mbarrier parities count every chunk), at most NCH in flight
-      for (uint32_t b = pos >> 3, e = (pos >> 3) + len; b < e; b += (NCH - 2) * CH)
-        ensure_input(b, (b + (NCH - 2) * CH < e ? b + (NCH - 2) * CH : e));
+      // strictly in order (the mbarrier parities count every chunk), at most NCH in flight.  Not behind the LAST block
+      // of the stream — what a level-0 writer produces: one final stored block per BGZF block — where nothing more is
+      // read (the chunks still in flight are drained at the end).
+      if (!last)
+        for (uint32_t b = pos >> 3, e = (pos >> 3) + len; b < e; b += (NCH - 2) * CH)
+          ensure_input(b, (b + (NCH - 2) * CH < e ? b + (NCH - 2) * CH : e));
       pos += len * 8;
       continue;
     }
