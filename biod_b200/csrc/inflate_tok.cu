@@ -75,7 +75,7 @@ constexpr int TOK_TRIPS = TOK_MAX_TRIPS;       // ... or TOK_TRIPS - 1 tokens
 constexpr int LANE_MCAP = TOK_TRIPS / 2;       // (hence at most this many matches)
 constexpr int FLUSH_ALIGN = 128;
 constexpr int SUB_CAP = LIT_BITS >= 10 ? 320 : 352;
-constexpr int STORE_PIECE = 1024;              // stored blocks are copied in pieces of this many bytes
+constexpr int STORE_PIECE = 2048;              // stored blocks are copied in pieces of this many bytes
 constexpr int HDR_BYTES = 640;                 // >= longest dynamic block header
 constexpr int MAX_ROUNDS = BIODB_TOK_MAX_ROUNDS;   // decode rounds per super-chunk before the consistent prefix is committed as it is
 static_assert(LANE_CAP > SUB_BITS, "literals alone never reach the cap, so it is checked between codes only");
@@ -639,7 +639,21 @@ __global__ void __launch_bounds__(32, 32) inflate_resolve_kernel(InflateArgs a) 
       for (uint32_t p0 = 0; p0 < len; p0 += STORE_PIECE) {
         const uint32_t piece = len - p0 < (uint32_t)STORE_PIECE ? len - p0 : (uint32_t)STORE_PIECE;
         const uint8_t* g = pay + off + p0;
-        for (uint32_t i = lane; i < piece; i += 32) sts8(ring + ((o + i) & POM), __ldg(g + i));
+        // bytes up to the next word boundary of the ring, then whole words (the source read as aligned words and
+        // funnel-shifted into place), then the tail
+        uint32_t hb = (4u - (o & 3u)) & 3u;
+        if (hb > piece) hb = piece;
+        if ((uint32_t)lane < hb) sts8(ring + ((o + lane) & POM), __ldg(g + lane));
+        const uint32_t nw = (piece - hb) >> 2;
+        const uintptr_t ga = (uintptr_t)(g + hb);
+        const uint32_t sh = (uint32_t)(ga & 3) * 8;
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(ga & ~(uintptr_t)3);
+        for (uint32_t k = lane; k < nw; k += 32) {
+          const uint32_t lo = __ldg(gw + k), hi = sh ? __ldg(gw + k + 1) : 0u;
+          sts32(ring + ((o + hb + 4 * k) & POM), __funnelshift_r(lo, hi, sh));
+        }
+        const uint32_t done = hb + 4 * nw;
+        if (done + lane < piece) sts8(ring + ((o + done + lane) & POM), __ldg(g + done + lane));
         __syncwarp();
         o += piece;
         produced();
