@@ -1,12 +1,6 @@
 #!/bin/bash
-# one GPU call of round 2: inflate tests + the level-0 leg of the inflate sweep after the word-wide stored copy
+# last GPU call of round 2: the core parity tests and the smoke entry on the committed library
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_inflate.py "tests/test_gpu_parity.py::test_synthetic_mixed_cigar" -q -m gpu --timeout=120 -p no:cacheprovider > gpurun_out/cg_tests.log 2>&1
-grep -E "^(FAILED|ERROR)|passed|failed|Error" gpurun_out/cg_tests.log | cut -c1-400 | tail -8
-timeout 200 python tools/inflate_sweep.py --max-gib 4 --levels 0 > gpurun_out/inflate_sweep_r2d.jsonl 2> gpurun_out/inflate_sweep_r2d.err
-python - <<'PY'
-import json
-for l in open('gpurun_out/inflate_sweep_r2d.jsonl'):
-    if l.startswith('{'):
-        d=json.loads(l); print('sweep', d['level'], d['gib'], round(d['out_gbs'],1), round(d['algorithmic_gbs'],1), round(d['frac_of_hbm_peak'],4))
-PY
+timeout 400 python -m pytest tests/test_gpu_parity.py -k "records_match_oracle or pileup_columns_match_oracle or corrupted or synthetic_mixed or stream_stops or truncated" tests/test_gpu_configs.py::test_config0_make_pileup_example -q -m gpu --timeout=200 -p no:cacheprovider > gpurun_out/ch_tests.log 2>&1
+grep -E "^(FAILED|ERROR)|passed|failed|Error" gpurun_out/ch_tests.log | cut -c1-400 | tail -8
+timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1
