@@ -117,6 +117,7 @@ extern (C) nothrow @nogc {
     int biodb_writer_header(biodb_writer*, const(char)* text, size_t text_len, int n_refs, const(char*)* names, const(int)* lengths);
     int biodb_writer_records(biodb_writer*, const(ubyte)* records, size_t len);
     int biodb_writer_flush(biodb_writer*);
+    int biodb_writer_drain(biodb_writer*, uint min_blocks, const(ubyte)** data, size_t* len);
     int biodb_writer_finish(biodb_writer*, const(ubyte)** data, size_t* len);
     const(char)* biodb_writer_error(const(biodb_writer)*);
     void biodb_writer_end(biodb_writer*);

@@ -186,6 +186,8 @@ def lib():
     L.biodb_writer_records.argtypes = [vp, vp, C.c_size_t]
     L.biodb_writer_flush.restype = C.c_int
     L.biodb_writer_flush.argtypes = [vp]
+    L.biodb_writer_drain.restype = C.c_int
+    L.biodb_writer_drain.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.biodb_writer_finish.restype = C.c_int
     L.biodb_writer_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.biodb_writer_layout.restype = C.c_int
@@ -223,5 +225,5 @@ EXPORTS = [
     "biodb_index_builder_finish", "biodb_index_builder_error", "biodb_index_builder_end",
     "biodb_reads_begin_region", "biodb_reads_begin_between", "biodb_pileup_begin_region", "biodb_bgzf_compress_bound", "biodb_bgzf_compress",
     "biodb_debug_deflate_block", "biodb_debug_deflate_stats", "biodb_writer_begin", "biodb_writer_header", "biodb_writer_records", "biodb_writer_flush",
-    "biodb_writer_finish", "biodb_writer_layout", "biodb_writer_index", "biodb_writer_debug_set_output", "biodb_writer_error", "biodb_writer_end",
+    "biodb_writer_drain", "biodb_writer_finish", "biodb_writer_layout", "biodb_writer_index", "biodb_writer_debug_set_output", "biodb_writer_error", "biodb_writer_end",
 ]

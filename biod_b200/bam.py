@@ -986,11 +986,15 @@ class BgzfOutputStream:
 
 
 class BamWriter:
-    """bam/writer.d:67-300 (without the automatic index): collects header and records the way BamWriter lays them out
-    and compresses the BGZF blocks on the GPU at finish().  `sink` is a file-like object or a path."""
+    """bam/writer.d:67-300: collects header and records the way BamWriter lays them out and compresses the BGZF blocks on
+    the GPU — in slabs of `stream_blocks` blocks as they accumulate, the rest at finish().  `sink` is a file-like object
+    or a path."""
 
-    def __init__(self, sink, compression_level=-1, task_pool=None, device=-1):
+    def __init__(self, sink, compression_level=-1, task_pool=None, device=-1, stream_blocks=2048):
+        """stream_blocks: complete BGZF blocks are compressed and written to the sink whenever that many have accumulated
+        (0: everything at finish()), so the writer holds ~stream_blocks x 64 KiB, not the file."""
         self._L = L = capi.lib()
+        self._stream_blocks = int(stream_blocks)
         if not -1 <= compression_level <= 9:
             raise ValueError("compression level must be within -1 .. 9")
         self._sink = open(sink, "wb") if isinstance(sink, (str, os.PathLike)) else sink
@@ -1033,6 +1037,14 @@ class BamWriter:
         """Any number of records, back to back, each with its block_size prefix."""
         buf = np.frombuffer(bytes(records), dtype=np.uint8)
         self._check(self._L.biodb_writer_records(self._h, buf.ctypes.data if buf.size else None, buf.size))
+        if self._stream_blocks > 0:
+            self._drain(self._stream_blocks)
+
+    def _drain(self, min_blocks):
+        d, n = C.c_void_p(), C.c_size_t()
+        self._check(self._L.biodb_writer_drain(self._h, min_blocks, C.byref(d), C.byref(n)))
+        if n.value:
+            self._sink.write(C.string_at(d, n.value))
 
     def flush(self):
         self._check(self._L.biodb_writer_flush(self._h))

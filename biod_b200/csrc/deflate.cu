@@ -603,8 +603,13 @@ inline uint16_t reg2bin(int32_t beg, int32_t end) {
 struct biodb_writer {
   int32_t device = -1, level = -1;
   // BgzfOutputStream (bgzf/outputstream.d:50-223): the bytes written so far and where its blocks begin
-  std::vector<uint8_t> bytes;
-  std::vector<uint64_t> cuts{0};       // starts of the blocks that are complete; the current block starts at cuts.back()
+  std::vector<uint8_t> bytes;          // stream bytes from offset bytes_base on (blocks already compressed are dropped)
+  uint64_t bytes_base = 0;
+  uint64_t stream_len() const { return bytes_base + bytes.size(); }
+  std::vector<uint64_t> cuts{0};       // starts (stream offsets) of the blocks that are complete; the current block starts at cuts.back()
+  size_t cuts_done = 0;                // blocks [0, cuts_done) have been compressed (biodb_writer_drain / _finish)
+  std::vector<uint64_t> block_at{0};   // file offset of every compressed block, then the length of the file so far
+  bool drained = false, finished = false;
   size_t stream_cur = 0;               // _current_size of the stream: bytes in the current block
   // BamWriter (bam/writer.d)
   size_t rec_cur = 0;                  // _current_size of the writer: record bytes it believes the current block holds
@@ -619,7 +624,7 @@ struct biodb_writer {
 
   void flush_current_block() {         // outputstream.d:136-161
     if (stream_cur == 0) return;
-    cuts.push_back(bytes.size());
+    cuts.push_back(stream_len());
     stream_cur = 0;
   }
   void write(const uint8_t* p, size_t size) {     // writeBlock, outputstream.d:107-132
@@ -713,11 +718,11 @@ biodb_status biodb_writer_records(biodb_writer* w, const uint8_t* records, size_
     const size_t read_size = rec.size();                                   // size_in_bytes (read.d:609-611)
     if (read_size + w->rec_cur > BGZF_CHUNK) {
       w->flush_current_block();
-      w->recs.push_back(biodb_writer::Rec{w->bytes.size(), (uint32_t)read_size, ref_id, pos, (int32_t)((uint32_t)pos + covered), bin, (flag & 4) != 0});
+      w->recs.push_back(biodb_writer::Rec{w->stream_len(), (uint32_t)read_size, ref_id, pos, (int32_t)((uint32_t)pos + covered), bin, (flag & 4) != 0});
       w->write(rec.data(), rec.size());
       w->rec_cur = read_size;
     } else {
-      w->recs.push_back(biodb_writer::Rec{w->bytes.size(), (uint32_t)read_size, ref_id, pos, (int32_t)((uint32_t)pos + covered), bin, (flag & 4) != 0});
+      w->recs.push_back(biodb_writer::Rec{w->stream_len(), (uint32_t)read_size, ref_id, pos, (int32_t)((uint32_t)pos + covered), bin, (flag & 4) != 0});
       w->write(rec.data(), rec.size());
       w->rec_cur += read_size;
     }
@@ -736,6 +741,7 @@ biodb_status biodb_writer_flush(biodb_writer* w) {                         // wr
 // (n_cuts entries; a last block still open runs to *len).  For the CPU tests of the block layout.
 biodb_status biodb_writer_layout(const biodb_writer* w, const uint8_t** data, size_t* len, const uint64_t** cuts, size_t* n_cuts) {
   if (!w || !data || !len || !cuts || !n_cuts) return BIODB_ERR_ARG;
+  if (w->bytes_base) return BIODB_ERR_ARG;                              // (blocks were already handed out: biodb_writer_drain)
   *data = w->bytes.data();
   *len = w->bytes.size();
   *cuts = w->cuts.data();
@@ -743,16 +749,62 @@ biodb_status biodb_writer_layout(const biodb_writer* w, const uint8_t** data, si
   return BIODB_OK;
 }
 
-// finish (writer.d:276-280): every block compressed on the device, the EOF block appended; *data stays valid until
-// biodb_writer_end.
+// Compress the complete blocks [cuts_done, upto) into w->out (appended), note where each lands in the file, drop their
+// uncompressed bytes.
+static biodb_status writer_compress(biodb_writer* w, size_t upto) {
+  if (upto <= w->cuts_done) return BIODB_OK;
+  std::vector<uint64_t> rel(upto - w->cuts_done + 1);
+  for (size_t k = 0; k < rel.size(); ++k) rel[k] = w->cuts[w->cuts_done + k] - w->bytes_base;
+  const size_t at = w->out.size();
+  const biodb_status rc = compress_chunks(w->device, w->bytes.data(), rel.data(), rel.size() - 1, w->level, &w->out);
+  if (rc != BIODB_OK) return rc;
+  // the BSIZE chain of what was just written: the file offsets of these blocks
+  uint64_t file0 = w->block_at.back();
+  w->block_at.pop_back();
+  size_t p = at;
+  while (p + 18 <= w->out.size()) {
+    w->block_at.push_back(file0 + (p - at));
+    p += ((size_t)w->out[p + 16] | ((size_t)w->out[p + 17] << 8)) + 1;
+  }
+  w->block_at.push_back(file0 + (w->out.size() - at));
+  const uint64_t drop = w->cuts[upto] - w->bytes_base;
+  w->bytes.erase(w->bytes.begin(), w->bytes.begin() + (ptrdiff_t)drop);
+  w->bytes_base = w->cuts[upto];
+  w->cuts_done = upto;
+  return BIODB_OK;
+}
+
+// Streaming use (bgzf/outputstream.d:136-173 hands every full block to the task pool as it completes): if at least
+// min_blocks complete blocks have accumulated, compress them now and hand their BGZF bytes out — *data is valid until the
+// next call on this writer; *len = 0 if there was not enough to do.  The uncompressed bytes of those blocks are released:
+// a writer that is drained regularly holds min_blocks blocks, not the file.  After a drain, biodb_writer_finish returns
+// only what has not been handed out yet.
+biodb_status biodb_writer_drain(biodb_writer* w, uint32_t min_blocks, const uint8_t** data, size_t* len) {
+  if (!w || !data || !len || w->finished) return BIODB_ERR_ARG;
+  *data = nullptr;
+  *len = 0;
+  const size_t ready = w->cuts.size() - 1 - w->cuts_done;
+  if (ready == 0 || ready < min_blocks) return BIODB_OK;
+  w->out.clear();
+  w->drained = true;
+  const biodb_status rc = writer_compress(w, w->cuts.size() - 1);
+  if (rc != BIODB_OK) return rc;
+  *data = w->out.data();
+  *len = w->out.size();
+  return BIODB_OK;
+}
+
+// finish (writer.d:276-280): every block not yet handed out compressed on the device, the EOF block appended; *data stays
+// valid until biodb_writer_end.  Without earlier drains that is the whole file.
 biodb_status biodb_writer_finish(biodb_writer* w, const uint8_t** data, size_t* len) {
   static const uint8_t EOF_BLOCK[28] = {31, 139, 8, 4, 0, 0, 0, 0, 0, 255, 6, 0, 66, 67, 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (!w || !data || !len) return BIODB_ERR_ARG;
+  if (!w || !data || !len || w->finished) return BIODB_ERR_ARG;
   w->flush_current_block();
   w->out.clear();
-  const biodb_status rc = compress_chunks(w->device, w->bytes.data(), w->cuts.data(), w->cuts.size() - 1, w->level, &w->out);
+  const biodb_status rc = writer_compress(w, w->cuts.size() - 1);
   if (rc != BIODB_OK) return rc;
   w->out.insert(w->out.end(), EOF_BLOCK, EOF_BLOCK + 28);
+  w->finished = true;
   *data = w->out.data();
   *len = w->out.size();
   return BIODB_OK;
@@ -764,6 +816,14 @@ biodb_status biodb_writer_debug_set_output(biodb_writer* w, const uint8_t* data,
   if (!w || (!data && len)) return BIODB_ERR_ARG;
   w->flush_current_block();
   w->out.assign(data, data + len);
+  w->block_at.clear();
+  size_t p = 0;
+  while (p + 18 <= len && w->block_at.size() < w->cuts.size() - 1) {      // the blocks of the layout (the EOF block is not one)
+    w->block_at.push_back(p);
+    p += ((size_t)data[p + 16] | ((size_t)data[p + 17] << 8)) + 1;
+  }
+  w->block_at.push_back(p);
+  w->finished = true;
   return BIODB_OK;
 }
 
@@ -771,15 +831,10 @@ biodb_status biodb_writer_debug_set_output(biodb_writer* w, const uint8_t* data,
 // 171-175: IndexBuilder with check_bins, fed with every record and the virtual offsets it got in the file).  Call after
 // biodb_writer_finish.  BIODB_ERR_UNSORTED if the records were not in coordinate order.
 biodb_status biodb_writer_index(biodb_writer* w, const uint8_t** data, size_t* len) {
-  if (!w || !data || !len || w->out.empty()) return BIODB_ERR_ARG;
-  // where the blocks of the layout begin in the file: the BSIZE chain of the finished stream
+  if (!w || !data || !len || !w->finished) return BIODB_ERR_ARG;
+  // where the blocks of the layout begin in the file: noted while they were compressed (block_at)
   const size_t nb = w->cuts.size() - 1;
-  std::vector<uint64_t> cb;
-  size_t p = 0;
-  while (p + 18 <= w->out.size() && cb.size() <= nb) {
-    cb.push_back(p);
-    p += ((size_t)w->out[p + 16] | ((size_t)w->out[p + 17] << 8)) + 1;
-  }
+  const std::vector<uint64_t>& cb = w->block_at;
   if (cb.size() != nb + 1) { w->err = "the finished file does not have the writer's block layout"; return BIODB_ERR_FORMAT; }
   auto voffset = [&](uint64_t x) -> uint64_t {                    // of byte x of the uncompressed stream
     const size_t i = (size_t)(std::upper_bound(w->cuts.begin(), w->cuts.end(), x) - w->cuts.begin()) - 1;   // cuts[i] <= x

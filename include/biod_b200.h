@@ -357,12 +357,17 @@ biodb_status biodb_bgzf_compress(int32_t device, const void* data, size_t len, i
 /* BamWriter (bio/std/hts/bam/writer.d:67-300) over that compressor.  The writer collects the uncompressed stream on the
  * host exactly as BamWriter + BgzfOutputStream lay it out — "BAM\1", header text, reference table, a block boundary,
  * then the records, where a record that would not fit into the current block starts a new one (writer.d:259-267) and
- * a record longer than a block is cut every 0xFF00 bytes (outputstream.d:107-132) — and compresses all blocks on the
- * device at finish.  The index a BamWriter creates for coordinate-sorted output (bai/indexing.d) is not built.
+ * a record longer than a block is cut every 0xFF00 bytes (outputstream.d:107-132) — and compresses the blocks on the
+ * device: all at _finish, or as they accumulate when the caller drains the writer (_drain), in which case the writer
+ * holds a few thousand blocks at a time, not the file.
  *  _header : writeSamHeader + writeReferenceSequenceInfo (names are NUL-terminated strings); once, before records
  *  _records: writeRecord for every record of the buffer (block_size prefix + body, back to back); the bin field is
  *            recalculated (read.d:1028-1030); BIODB_ERR_ARG "Read reference ID is out of range" (writer.d:245-246)
- *  _flush  : ends the current block;  _finish: the whole file (valid until _end), EOF block included
+ *  _flush  : ends the current block
+ *  _drain  : if at least min_blocks complete blocks have accumulated: compresses them and hands their BGZF bytes out
+ *            (*data valid until the next call on this writer; *len = 0 when there was not enough to do) and releases
+ *            their uncompressed bytes
+ *  _finish : the rest of the file (the whole file if _drain was never used), EOF block included; valid until _end
  *  _layout : host-only view of the uncompressed bytes and the block starts chosen so far (for tests) */
 typedef struct biodb_writer biodb_writer;
 biodb_status biodb_writer_begin(int32_t device, int32_t level, biodb_writer** out);
@@ -370,6 +375,7 @@ biodb_status biodb_writer_header(biodb_writer* w, const char* text, size_t text_
                                  const int32_t* lengths);
 biodb_status biodb_writer_records(biodb_writer* w, const uint8_t* records, size_t len);
 biodb_status biodb_writer_flush(biodb_writer* w);
+biodb_status biodb_writer_drain(biodb_writer* w, uint32_t min_blocks, const uint8_t** data, size_t* len);
 biodb_status biodb_writer_finish(biodb_writer* w, const uint8_t** data, size_t* len);
 biodb_status biodb_writer_layout(const biodb_writer* w, const uint8_t** data, size_t* len, const uint64_t** cuts, size_t* n_cuts);
 /* The BAI index of the finished file: what BamWriter builds while it writes coordinate-sorted output (writer.d:139-195:
