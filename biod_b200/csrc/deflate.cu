@@ -425,10 +425,11 @@ biodb_status compress_slabs(int32_t device, const uint8_t* data, size_t len, con
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, deflate_warp_kernel, 32, 0) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || per_sm < 1 || sms < 1)
       return BIODB_ERR_CUDA;
-    cx->grid = per_sm * sms;
     for (EncSet& s : cx->set)
-      if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return BIODB_ERR_CUDA;
-    if (cudaEventCreate(&cx->ev0) != cudaSuccess || cudaEventCreate(&cx->ev1) != cudaSuccess) return BIODB_ERR_CUDA;
+      if (!s.st && cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return BIODB_ERR_CUDA;
+    if ((!cx->ev0 && cudaEventCreate(&cx->ev0) != cudaSuccess) || (!cx->ev1 && cudaEventCreate(&cx->ev1) != cudaSuccess))
+      return BIODB_ERR_CUDA;
+    cx->grid = per_sm * sms;                               // (set last: a context that failed half-way is set up again)
   }
   cx->kernel_us = 0;
   ++cx->calls;
