@@ -1,11 +1,6 @@
 #!/bin/bash
-# inflate parameter variants (rounds per super-chunk, sub-sequence length, match list) against the committed build
+# last GPU call of round 2: the freshly rebuilt library — smoke entry, inflate / write-path / region tests
 mkdir -p gpurun_out
-for L in libbiod_b200.so libbiod_b200_r4.so libbiod_b200_r6.so libbiod_b200_s192.so libbiod_b200_m96.so; do
-  BIODB_LIB=$PWD/biod_b200/$L timeout 120 python bench.py --reads 20000000 --steps 3 --warmup 1 --no-e2e --no-cpu --no-extra 2>/dev/null | tail -1 > gpurun_out/var_$L.json
-  python - $L <<'PY'
-import json,sys
-d=json.loads(open('gpurun_out/var_%s.json'%sys.argv[1]).read())
-print(sys.argv[1], round(d['value']/1e6,1), round(d['ms_per_step'],2), d['roofline']['stage_ms'], d['inflate_counters']['blocks_given_up'], d['checks'])
-PY
-done
+timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1
+timeout 400 python -m pytest tests/test_gpu_inflate.py tests/test_gpu_x_writer.py tests/test_gpu_x_deflate.py tests/test_gpu_region.py -q -m gpu --timeout=200 -p no:cacheprovider > gpurun_out/cj_tests.log 2>&1
+grep -E "^(FAILED|ERROR)|passed|failed|Error" gpurun_out/cj_tests.log | cut -c1-400 | tail -8
