@@ -1,6 +1,6 @@
 #!/bin/bash
-# last GPU call of round 2: the freshly rebuilt library — smoke entry, inflate / write-path / region tests
+# ncu capture of the MD / MAQ kernels (rows N1, N3)
 mkdir -p gpurun_out
-timeout 120 python __graft_entry__.py smoke 2>&1 | tail -1
-timeout 400 python -m pytest tests/test_gpu_inflate.py tests/test_gpu_x_writer.py tests/test_gpu_x_deflate.py tests/test_gpu_region.py -q -m gpu --timeout=200 -p no:cacheprovider > gpurun_out/cj_tests.log 2>&1
-grep -E "^(FAILED|ERROR)|passed|failed|Error" gpurun_out/cj_tests.log | cut -c1-400 | tail -8
+timeout 200 ncu --set full --clock-control none -k regex:"maq_kernel|md_len_kernel|md_replay_kernel" -s 3 -c 3 -o gpurun_out/prof_r2_maq python tools/maq_profile.py 6000000 > gpurun_out/prof_r2_maq.log 2>&1
+tail -3 gpurun_out/prof_r2_maq.log
+ls -la gpurun_out/prof_r2_maq.ncu-rep
