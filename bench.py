@@ -328,7 +328,7 @@ def link_shares(torch, dist, world, per_rank=4):
 def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, barrier, steps, warmup, want_e2e, want_reads_pass,
             want_md):
     """The device-resident and the end-to-end measurement of one config.  Returns a dict (rank 0 uses it)."""
-    from biod_b200.stitch import exact_halos, gather_reach, stitch_counts
+    from biod_b200.stitch import exact_halos, exact_halos_of_spans, gather_reach, stitch_counts
     cfg = CONFIGS[config]
     data, path, t_gen, made = synth_file(args, config, cfg, n_reads, rank, world, barrier)
     bpb = args.blocks_per_batch or (0 if world == 1 else (-2 if world == 2 else -1))
@@ -433,7 +433,7 @@ def measure(args, L, capi, torch, dist, config, n_reads, rank, world, local, bar
             def exact_halo_pass(rd, info, **kw):                # the same exchange over spans: a span's halo must reach
                 t0 = time.time()                                # back to what reaches its FIRST shard
                 rows, used = gather_reach(info["reach"], info["halo_voffset"], device="cuda")
-                need, redo = exact_halos([[row[a] for a in firsts] for row in rows], used)
+                need, redo = exact_halos_of_spans(rows, used, firsts)
                 ms = (time.time() - t0) * 1e3
                 res = run_pass(L, capi, rd, shard, info, halo_voffset=need[rank], **kw) if rank in redo else None
                 return res, {"exact": True, "rerun_shards": redo, "exchange_ms": ms}

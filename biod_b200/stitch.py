@@ -38,6 +38,13 @@ def exact_halos(reach_rows, halo_used):
     return need, redo
 
 
+def exact_halos_of_spans(reach_rows, halo_used, firsts):
+    """exact_halos for workers that each run a SPAN of consecutive shards (biodb_pileup_begin_shard_span): worker j runs
+    the shards from firsts[j] on, its reach row is indexed by shard, and its halo must reach back to the first earlier
+    record that reaches the columns of its FIRST shard.  Returns (need, redo) per worker."""
+    return exact_halos([[row[a] for a in firsts] for row in reach_rows], halo_used)
+
+
 def gather_reach(reach_row, halo_voffset, device="cpu"):
     """All-gather of every rank's reach row and halo start (one row of world + 1 integers per rank); returns
     (reach_rows, halo_used) for exact_halos.  Offsets travel as int64 (NONE = -1)."""

@@ -73,7 +73,7 @@ def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, exact=
     exact=True: the shards run the way several GPUs run them — all from the halo_blocks guess, then exact_halos says which
     halos were too short and those shards run again from the exact offset (res["redone"]).  exact=False: the guess only.
     spans=[2, 1, 4]: the shards are run as passes over shards 0-1, 2 and 3-6 (biodb_pileup_begin_shard_span)."""
-    from biod_b200.stitch import exact_halos
+    from biod_b200.stitch import exact_halos_of_spans
     rd = BamReader(data, blocks_per_batch=blocks_per_batch)
 
     spans = spans or [1] * n_shards
@@ -103,7 +103,7 @@ def gpu_pileup_sharded(data, n_shards, halo_blocks=8, blocks_per_batch=0, exact=
         parts.append(part)
         infos.append(info)
     # a span's halo must reach back to the first earlier record that reaches its FIRST shard's columns
-    need, redo = exact_halos([[i["reach"][a] for a in firsts] for i in infos], [i["halo_voffset"] for i in infos])
+    need, redo = exact_halos_of_spans([i["reach"] for i in infos], [i["halo_voffset"] for i in infos], firsts)
     if exact:
         for t in redo:
             parts[t], infos[t] = run(t, need[t])

@@ -96,3 +96,20 @@ def test_exact_halos_single_process():
     # three shards: shard 0 reaches shards 1 and 2, shard 1 reaches shard 2 from further on; shard 2's guess was too short
     need, redo = exact_halos([[NONE, 100, 120], [NONE, NONE, 300], [NONE, NONE, NONE]], [0, 90, 250])
     assert need == [NONE, 100, 120] and redo == [2]
+
+
+def test_exact_halos_of_spans():
+    """Workers that run spans of shards (unequal shares on common cuts): the halo a worker needs is what earlier workers
+    report for the FIRST shard of its span."""
+    sys.path.insert(0, ROOT)
+    from biod_b200.stitch import NONE, exact_halos_of_spans
+    # 6 shards; three workers run the shards [0, 1], [2] and [3, 4, 5].  Worker 0's own records reach into shards 2
+    # (from offset 700) and 3 (from 900); worker 1's into shard 3 (from 1500) and 4.
+    rows = [[NONE, NONE, 700, 900, NONE, NONE],
+            [NONE, NONE, NONE, 1500, 1600, NONE],
+            [NONE] * 6]
+    need, redo = exact_halos_of_spans(rows, [0, 650, 1400], [0, 2, 3])
+    assert need == [NONE, 700, 900]              # worker 2 needs the earlier of 900 and 1500
+    assert redo == [2]                           # its halo started at 1400, behind 900; worker 1 started early enough
+    need, redo = exact_halos_of_spans(rows, [0, 650, 880], [0, 2, 3])
+    assert redo == []
